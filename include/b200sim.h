@@ -1,0 +1,154 @@
+/*
+ * b200sim.h -- C ABI of the B200-native batched rigid-body simulation step.
+ *
+ * This is the drop-in boundary for ONE hot path of ami-iit/jaxsim: the vmapped
+ * `jaxsim.api.model.step` (reference: src/jaxsim/api/model.py:2601-2681) and the functions
+ * under it.  The reference has no FFI of its own (it is a jitted Python function), so these
+ * entry points are what a maintainer would bind from Python (ctypes stub: INTEGRATION.md)
+ * in place of `jax.jit(jax.vmap(step, in_axes=(None, 0)))`.
+ *
+ * Conventions (identical to the reference):
+ *   - all batched arrays are row-major with a leading batch axis B, contiguous,
+ *     element type float (dtype 0) or double (dtype 1); pointers are DEVICE pointers;
+ *   - quaternions are wxyz; 6D vectors are [linear; angular];
+ *   - base/link velocities and link forces are in INERTIAL-FIXED representation
+ *     (api/data.py:36-39); forces are [f; moment about the world origin];
+ *   - DoF j (0-based) drives link j+1; link 0 is the base (rbda/aba.py:133).
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default
+ *     stream); the caller owns all buffers; nothing is allocated per call.
+ * Return value: 0 ok; <0 invalid argument (B200SIM_E_*); >0 a cudaError_t.
+ * Thread safety: a B200SimModel is immutable after create (except the explicit update_*
+ * calls) and may be used concurrently from several host threads / streams.
+ */
+#ifndef B200SIM_H
+#define B200SIM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SIM_ABI_VERSION 1
+
+#define B200SIM_DTYPE_F32 0
+#define B200SIM_DTYPE_F64 1
+
+#define B200SIM_CONTACT_NONE 0
+#define B200SIM_CONTACT_SOFT 1 /* rbda/contacts/soft.py */
+
+#define B200SIM_E_INVALID (-1)     /* NULL / negative size / bad dtype */
+#define B200SIM_E_UNSUPPORTED (-2) /* valid in the reference, not implemented here */
+#define B200SIM_E_TOO_LARGE (-3)   /* model does not fit the shared-memory workspace */
+
+/* Host description of a model: a field-for-field image of the reference's
+ * KinDynParameters (src/jaxsim/api/kin_dyn_parameters.py:21-63) + the Static fields of
+ * JaxSimModel (src/jaxsim/api/model.py:46-90) the step reads.  All pointers are HOST
+ * pointers to float64 / int32 arrays; they are copied by b200sim_model_create. */
+typedef struct B200SimModelDesc {
+  int32_t abi_version; /* = B200SIM_ABI_VERSION */
+  int32_t n_links;     /* nL */
+  int32_t n_dofs;      /* n  (= nL - 1) */
+  int32_t n_points;    /* collidable points (enabled or not), contact_parameters.body */
+  int32_t floating_base; /* joint_dofs[0] == 6 (api/model.py:722-730) */
+  int32_t contact_model; /* B200SIM_CONTACT_* */
+  int32_t enable_friction; /* ActuationParams.enable_friction (rbda/actuation/common.py:19) */
+  int32_t reserved0;
+
+  const int32_t *parent;     /* [nL]   parent_array, parent[0] = -1 */
+  const int32_t *joint_type; /* [nL]   0 fixed (index 0 only), 1 revolute, 2 prismatic */
+  const double *lam_H_pre;   /* [nL,4,4] JointModel.lam_H_pre (math/joint_model.py:16-44) */
+  const double *suc_H_i;     /* [nL,4,4] JointModel.suc_H_i */
+  const double *joint_axis;  /* [nL,3]  row 0 unused; axis of joint i in its own frame */
+  const double *link_mass;   /* [nL]    LinkParameters.mass */
+  const double *link_com;    /* [nL,3]  LinkParameters.center_of_mass (link frame) */
+  const double *link_inertia;/* [nL,6]  LinkParameters.inertia_elements (triu, at the CoM) */
+  /* JointParameters (api/kin_dyn_parameters.py:502-571), all [n] */
+  const double *friction_static;
+  const double *friction_viscous;
+  const double *position_limits_min;
+  const double *position_limits_max;
+  const double *position_limit_spring;
+  const double *position_limit_damper;
+  /* ContactParameters (api/kin_dyn_parameters.py:765-840) */
+  const int32_t *point_body;    /* [nc] */
+  const double *point_position; /* [nc,3] L_p_C */
+  const int32_t *point_enabled; /* [nc] 0/1 */
+
+  double time_step;      /* JaxSimModel.time_step */
+  double gravity;        /* JaxSimModel.gravity: z acceleration, NEGATIVE (-9.81) */
+  double terrain_height; /* FlatTerrain._height (terrain/terrain.py:66-113) */
+  /* SoftContactsParams (rbda/contacts/soft.py:24-46) */
+  double soft_K, soft_D, soft_mu, soft_p, soft_q;
+  /* ActuationParams (rbda/actuation/common.py:10-19) */
+  double torque_max, omega_th, omega_max;
+} B200SimModelDesc;
+
+typedef struct B200SimModel B200SimModel;
+
+/* Upload a model to `device` (CUDA ordinal).  Replaces building the KinDynParameters
+ * pytree leaves on device (api/model.py:224-330). */
+int b200sim_model_create(const B200SimModelDesc *desc, int device, B200SimModel **out);
+void b200sim_model_destroy(B200SimModel *model);
+
+/* Replace the inertial parameters of every link (host float64 arrays, same layout as the
+ * descriptor).  Counterpart of KinDynParameters.set_link_mass / update_hw_parameters
+ * feeding new LinkParameters (api/kin_dyn_parameters.py:453-499). Synchronous. */
+int b200sim_model_update_link_params(B200SimModel *model, const double *link_mass,
+                                     const double *link_com, const double *link_inertia);
+
+/* Tuning knobs (0 = automatic): lanes per environment (1,2,4,8,16,32) and environments per
+ * thread block.  Only affects performance, never results. */
+int b200sim_model_set_tuning(B200SimModel *model, int lanes_per_env, int envs_per_block);
+
+/* Query sizes / launch geometry chosen for a batch (for benchmarks and tests). */
+int b200sim_model_query(const B200SimModel *model, int dtype, int64_t B, int32_t *lanes_per_env,
+                        int32_t *envs_per_block, int32_t *grid, int32_t *smem_bytes);
+
+/* One simulation step for B environments == jax.vmap(js.model.step, in_axes=(None, 0))
+ * with SoftContacts (or no collidable points) and SemiImplicitEuler:
+ *   actuation model (api/actuation_model.py:7-126) -> collidable-point kinematics and
+ *   Hunt/Crossley forces (rbda/collidable_points.py, rbda/contacts/soft.py:195-444) ->
+ *   ABA (rbda/aba.py:12-292) -> semi-implicit Euler (api/integrators.py:14-88) ->
+ *   cache refresh = joint transforms + FK (api/data.py:406-523, rbda/forward_kinematics.py).
+ *
+ * in : s, sd (B,n); q_wxyz (B,4); v_lin, omega, p (B,3); m_tan (B,nc,3) or NULL (== zeros);
+ *      tau_ref (B,n) joint_force_references or NULL; f_ext (B,nL,6) inertial-fixed link
+ *      forces or NULL.  The link transforms/velocities the reference reads from the input
+ *      data's caches are recomputed from the state (they are functions of it).
+ * out: *_o new state leaves (may alias the inputs); m_tan_o (B,nc,3) or NULL;
+ *      caches (each may be NULL to skip): W_H_B (B,4,4) _base_transform,
+ *      i_X_lam (B,nL,6,6) _joint_transforms, W_H_L (B,nL,4,4) _link_transforms,
+ *      W_v_WL (B,nL,6) _link_velocities.
+ */
+int b200sim_step(const B200SimModel *model, int dtype, int64_t B,
+                 const void *s, const void *sd, const void *q_wxyz, const void *v_lin,
+                 const void *omega, const void *p, const void *m_tan,
+                 const void *tau_ref, const void *f_ext,
+                 void *s_o, void *sd_o, void *q_o, void *v_lin_o, void *omega_o, void *p_o,
+                 void *m_tan_o,
+                 void *W_H_B, void *i_X_lam, void *W_H_L, void *W_v_WL,
+                 void *stream);
+
+/* Cache computation only (JaxSimModelData.build / .replace, api/data.py:66-202,406-523):
+ * normalises q (written to q_o if not NULL) and fills the requested caches. */
+int b200sim_fk(const B200SimModel *model, int dtype, int64_t B,
+               const void *s, const void *sd, const void *q_wxyz, const void *v_lin,
+               const void *omega, const void *p, void *q_o,
+               void *W_H_B, void *i_X_lam, void *W_H_L, void *W_v_WL, void *stream);
+
+/* Forward dynamics == vmapped rbda.aba (rbda/aba.py:12-292) with the given joint forces tau
+ * (B,n) or NULL and inertial-fixed link forces f_ext (B,nL,6) or NULL (no actuation model,
+ * no contacts).  out: W_vd_WB (B,6) inertial-fixed base acceleration, sdd (B,n). */
+int b200sim_aba(const B200SimModel *model, int dtype, int64_t B,
+                const void *s, const void *sd, const void *q_wxyz, const void *v_lin,
+                const void *omega, const void *p, const void *tau, const void *f_ext,
+                void *W_vd_WB, void *sdd, void *stream);
+
+/* Library / build information: "b200sim <abi> sm_100a ..." */
+const char *b200sim_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SIM_H */

@@ -1,0 +1,418 @@
+"""``JaxSimModel`` and the drop-in ``step`` (host side).
+
+Mirrors the public surface of ``src/jaxsim/api/model.py`` for the hot path only:
+
+* ``JaxSimModel`` (``:46-90``) with the same field names and builders (``:128-330``);
+* ``step(model, data, *, link_forces=None, joint_force_references=None)`` (``:2601-2681``);
+* ``forward_dynamics_aba`` (``:1269-1406``).
+
+Everything numerical happens in ``libb200sim.so`` (``csrc/``) through the C ABI of
+``include/b200sim.h``; torch tensors are only the device-buffer type.  There is no CPU path:
+calling these functions without the CUDA library or with CPU tensors raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import enum
+import pathlib
+import weakref
+
+import numpy as np
+import torch
+
+from jaxsim_b200 import _lib
+from jaxsim_b200.parsers.urdf import build_kin_dyn_parameters
+from jaxsim_b200.rbda.actuation import ActuationParams
+from jaxsim_b200.rbda.contacts import RigidContacts, SoftContacts, SoftContactsParams
+from jaxsim_b200.terrain import FlatTerrain
+
+from . import data as _data
+from .common import VelRepr, other_representation_to_inertial
+from .kin_dyn_parameters import KinDynParameters
+
+STANDARD_GRAVITY = 9.81  # src/jaxsim/math/__init__.py:14
+
+
+class IntegratorType(enum.IntEnum):
+    """``src/jaxsim/api/model.py:33-43``. Only SemiImplicitEuler is on the hot path."""
+
+    SemiImplicitEuler = enum.auto()
+    RungeKutta4 = enum.auto()
+    RungeKutta4Fast = enum.auto()
+
+
+def _np(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class _DeviceModel:
+    """Owns one ``B200SimModel*`` (one per CUDA device)."""
+
+    def __init__(self, model: "JaxSimModel", device_index: int):
+        lib = _lib.load()
+        kd = model.kin_dyn_parameters
+        nL, n = kd.number_of_links(), kd.number_of_joints()
+        cp = kd.contact_parameters
+        nc = len(cp.body)
+        keep = {}
+
+        def dp(name, arr):
+            keep[name] = _np(arr, np.float64)
+            return keep[name].ctypes.data_as(_lib.c_dp)
+
+        def ip(name, arr):
+            keep[name] = _np(arr, np.int32)
+            return keep[name].ctypes.data_as(_lib.c_ip)
+
+        axis = np.zeros((nL, 3))
+        if n > 0:
+            axis[1:] = kd.joint_model.joint_axis
+        if model.contact_model is None or nc == 0:
+            cm = 0
+        elif isinstance(model.contact_model, SoftContacts):
+            cm = 1
+        else:
+            raise NotImplementedError(f"contact model {type(model.contact_model).__name__} is not implemented")
+        prm = model.contact_params if isinstance(model.contact_params, SoftContactsParams) else SoftContactsParams()
+        jp = kd.joint_parameters
+        d = _lib.B200SimModelDesc(
+            abi_version=_lib.ABI_VERSION, n_links=nL, n_dofs=n, n_points=nc,
+            floating_base=int(model.floating_base()), contact_model=cm,
+            enable_friction=int(model.actuation_params.enable_friction), reserved0=0,
+            parent=ip("parent", kd.parent_array), joint_type=ip("jt", kd.joint_model.joint_types),
+            lam_H_pre=dp("lam", kd.joint_model.lam_H_pre), suc_H_i=dp("suc", kd.joint_model.suc_H_i),
+            joint_axis=dp("axis", axis),
+            link_mass=dp("mass", kd.link_parameters.mass), link_com=dp("com", kd.link_parameters.center_of_mass),
+            link_inertia=dp("inertia", kd.link_parameters.inertia_elements),
+            friction_static=dp("kc", jp.friction_static), friction_viscous=dp("kv", jp.friction_viscous),
+            position_limits_min=dp("smin", jp.position_limits_min), position_limits_max=dp("smax", jp.position_limits_max),
+            position_limit_spring=dp("ks", jp.position_limit_spring), position_limit_damper=dp("kd", jp.position_limit_damper),
+            point_body=ip("pb", np.array(cp.body, dtype=np.int32)),
+            point_position=dp("pp", np.asarray(cp.point, dtype=float).reshape(-1, 3) if nc else np.zeros((0, 3))),
+            point_enabled=ip("pe", np.array(cp.enabled, dtype=np.int32)),
+            time_step=float(model.time_step), gravity=float(model.gravity),
+            terrain_height=float(model.terrain.height()),
+            soft_K=prm.K, soft_D=prm.D, soft_mu=prm.mu, soft_p=prm.p, soft_q=prm.q,
+            torque_max=model.actuation_params.torque_max, omega_th=model.actuation_params.omega_th,
+            omega_max=model.actuation_params.omega_max,
+        )
+        handle = C.c_void_p()
+        _lib.check(lib.b200sim_model_create(C.byref(d), int(device_index), C.byref(handle)), "b200sim_model_create")
+        self.handle = handle
+        self.device_index = device_index
+        self._finalizer = weakref.finalize(self, lib.b200sim_model_destroy, handle)
+
+
+@dataclasses.dataclass(eq=False)
+class JaxSimModel:
+    """``src/jaxsim/api/model.py:46-90`` (host container; the device blob is created lazily
+    per CUDA device on first use)."""
+
+    model_name: str
+    time_step: float = 0.001
+    terrain: FlatTerrain = dataclasses.field(default_factory=FlatTerrain.build)
+    gravity: float = -STANDARD_GRAVITY
+    contact_model: object | None = None
+    contact_params: object | None = None
+    actuation_params: ActuationParams | None = None
+    kin_dyn_parameters: KinDynParameters | None = None
+    integrator: IntegratorType = IntegratorType.SemiImplicitEuler
+    built_from: object | None = None
+    _floating_base: bool = True
+    _devices: dict = dataclasses.field(default_factory=dict, repr=False)
+    _tuning: tuple = (0, 0)
+
+    # ------------------------------------------------------------------ builders
+    @classmethod
+    def build_from_model_description(
+        cls,
+        model_description: str | pathlib.Path,
+        *,
+        model_name: str | None = None,
+        time_step: float | None = None,
+        terrain: FlatTerrain | None = None,
+        contact_model=None,
+        contact_params=None,
+        actuation_params: ActuationParams | None = None,
+        integrator: IntegratorType | None = None,
+        is_urdf: bool | None = None,
+        considered_joints=None,
+        gravity: float = STANDARD_GRAVITY,
+    ) -> "JaxSimModel":
+        """``JaxSimModel.build_from_model_description`` (``api/model.py:128-223``): URDF path
+        or XML string.  ``gravity`` is passed positive and stored negated (``:206``)."""
+        if considered_joints is not None:
+            raise NotImplementedError("model reduction (api/model.py:807-878) is out of scope")
+        name, kd, floating = build_kin_dyn_parameters(model_description)
+        return cls.build(
+            kd, floating_base=floating, model_name=model_name or name, time_step=time_step, terrain=terrain,
+            contact_model=contact_model, contact_params=contact_params, actuation_params=actuation_params,
+            integrator=integrator, gravity=-gravity, built_from=model_description,
+        )
+
+    @classmethod
+    def build(
+        cls,
+        kin_dyn_parameters: KinDynParameters,
+        *,
+        floating_base: bool,
+        model_name: str = "model",
+        time_step: float | None = None,
+        terrain: FlatTerrain | None = None,
+        contact_model=None,
+        contact_params=None,
+        actuation_params: ActuationParams | None = None,
+        integrator: IntegratorType | None = None,
+        gravity: float = -STANDARD_GRAVITY,
+        built_from=None,
+    ) -> "JaxSimModel":
+        """``JaxSimModel.build`` (``api/model.py:224-330``): defaults are SoftContacts with
+        default parameters, default ActuationParams, SemiImplicitEuler, flat terrain at 0."""
+        contact_model = contact_model if contact_model is not None else SoftContacts.build()
+        if isinstance(contact_model, RigidContacts):
+            raise NotImplementedError("RigidContacts (rbda/contacts/rigid.py) is not implemented yet")
+        if contact_params is None:
+            contact_params = contact_model._parameters_class()
+        integrator = integrator if integrator is not None else IntegratorType.SemiImplicitEuler
+        if integrator != IntegratorType.SemiImplicitEuler:
+            raise NotImplementedError("only IntegratorType.SemiImplicitEuler is on the hot path")
+        return cls(
+            model_name=model_name,
+            time_step=float(time_step) if time_step is not None else 0.001,
+            terrain=terrain if terrain is not None else FlatTerrain.build(),
+            gravity=float(gravity),
+            contact_model=contact_model,
+            contact_params=contact_params,
+            actuation_params=actuation_params if actuation_params is not None else ActuationParams(),
+            kin_dyn_parameters=kin_dyn_parameters,
+            integrator=integrator,
+            built_from=built_from,
+            _floating_base=bool(floating_base),
+        )
+
+    # ------------------------------------------------------------------ properties
+    def name(self) -> str:
+        return self.model_name
+
+    def number_of_links(self) -> int:
+        return self.kin_dyn_parameters.number_of_links()
+
+    def number_of_joints(self) -> int:
+        return self.kin_dyn_parameters.number_of_joints()
+
+    def dofs(self) -> int:
+        return self.kin_dyn_parameters.number_of_joints()
+
+    def floating_base(self) -> bool:
+        return self._floating_base
+
+    def base_link(self) -> str:
+        return self.kin_dyn_parameters.link_names[0]
+
+    def link_names(self) -> tuple[str, ...]:
+        return self.kin_dyn_parameters.link_names
+
+    def joint_names(self) -> tuple[str, ...]:
+        return self.kin_dyn_parameters.joint_model.joint_names[1:]
+
+    def number_of_collidable_points(self) -> int:
+        return len(self.kin_dyn_parameters.contact_parameters.body)
+
+    # ------------------------------------------------------------------ device side
+    def device_model(self, device: torch.device) -> _DeviceModel:
+        if device.type != "cuda":
+            raise RuntimeError(
+                "jaxsim_b200 runs on CUDA devices only (no CPU fallback): move the data to a B200 first"
+            )
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        dm = self._devices.get(idx)
+        if dm is None:
+            dm = _DeviceModel(self, idx)
+            if self._tuning != (0, 0):
+                _lib.check(_lib.load().b200sim_model_set_tuning(dm.handle, *self._tuning), "set_tuning")
+            self._devices[idx] = dm
+        return dm
+
+    def set_tuning(self, lanes_per_env: int = 0, envs_per_block: int = 0) -> None:
+        """Performance knobs (never change results): see ``b200sim_model_set_tuning``."""
+        self._tuning = (int(lanes_per_env), int(envs_per_block))
+        for dm in self._devices.values():
+            _lib.check(_lib.load().b200sim_model_set_tuning(dm.handle, *self._tuning), "set_tuning")
+
+    def launch_geometry(self, batch: int, dtype: torch.dtype, device: torch.device) -> dict:
+        dm = self.device_model(device)
+        out = [C.c_int32() for _ in range(4)]
+        _lib.check(
+            _lib.load().b200sim_model_query(dm.handle, _dtype_code(dtype), int(batch), *[C.byref(o) for o in out]),
+            "b200sim_model_query",
+        )
+        return dict(lanes_per_env=out[0].value, envs_per_block=out[1].value, grid=out[2].value, smem_bytes=out[3].value)
+
+
+def _dtype_code(dtype: torch.dtype) -> int:
+    if dtype == torch.float32:
+        return 0
+    if dtype == torch.float64:
+        return 1
+    raise TypeError(f"unsupported dtype {dtype}: the step computes in float32 or float64")
+
+
+def _ptr(t: torch.Tensor | None):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream_ptr(device: torch.device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _batched(t: torch.Tensor, unbatched_ndim: int) -> torch.Tensor:
+    return t if t.dim() > unbatched_ndim else t.unsqueeze(0)
+
+
+# =============================================================================
+# step
+# =============================================================================
+
+
+def step(
+    model: JaxSimModel,
+    data: "_data.JaxSimModelData",
+    *,
+    link_forces: torch.Tensor | None = None,
+    joint_force_references: torch.Tensor | None = None,
+    update_caches: bool = True,
+) -> "_data.JaxSimModelData":
+    """Perform a simulation step: drop-in for ``jaxsim.api.model.step``
+    (``src/jaxsim/api/model.py:2601-2681``), batched over the leading axis of ``data``.
+
+    Args:
+        model: the model.
+        data: the (batched) state.
+        link_forces: 6D forces on the links, ``(B, nL, 6)`` (or ``(nL, 6)``), expressed in
+            ``data.velocity_representation`` like in the reference (``:2617-2618``).
+        joint_force_references: ``(B, n)`` joint force references.
+        update_caches: if False, the cached transforms of the returned data are not
+            materialised (rollout mode, "B_min" of SURVEY.md 8d); accessing them raises.
+
+    Returns:
+        The new ``JaxSimModelData`` (same velocity representation, new tensors: the input
+        is not modified, like the reference's immutable pytrees).
+    """
+    s = data._joint_positions
+    unbatched = s.dim() == 1
+    dev = s.device
+    dm = model.device_model(dev)
+    dtype = s.dtype
+    code = _dtype_code(dtype)
+    nL, n, nc = model.number_of_links(), model.dofs(), model.number_of_collidable_points()
+
+    s = _batched(data._joint_positions, 1).contiguous()
+    sd = _batched(data._joint_velocities, 1).contiguous()
+    q = _batched(data._base_quaternion, 1).contiguous()
+    vl = _batched(data._base_linear_velocity, 1).contiguous()
+    om = _batched(data._base_angular_velocity, 1).contiguous()
+    p = _batched(data._base_position, 1).contiguous()
+    B = q.shape[0]
+    if s.shape != (B, n) or sd.shape != (B, n):
+        raise ValueError((s.shape, sd.shape), (B, n))  # rbda/utils.py:102-133
+    for t, w in ((q, 4), (vl, 3), (om, 3), (p, 3)):
+        if t.shape != (B, w):
+            raise ValueError(t.shape, (B, w))
+
+    m = data.contact_state.get("tangential_deformation") if data.contact_state else None
+    if m is not None:
+        m = _batched(m, 2).contiguous()
+        if m.shape != (B, nc, 3):
+            raise ValueError(m.shape, (B, nc, 3))
+
+    tau = None
+    if joint_force_references is not None:
+        tau = _batched(torch.as_tensor(joint_force_references, dtype=dtype, device=dev), 1).contiguous()
+        if tau.shape != (B, n):
+            raise ValueError(tau.shape, (B, n))
+
+    fext = None
+    if link_forces is not None:
+        O_f = _batched(torch.as_tensor(link_forces, dtype=dtype, device=dev), 2)
+        if O_f.shape != (B, nL, 6):
+            raise ValueError(O_f.shape, (B, nL, 6))
+        # api/model.py:2641-2646: expressed in data.velocity_representation -> inertial-fixed
+        fext = other_representation_to_inertial(
+            O_f, data.velocity_representation, _batched(data.link_transforms, 3), is_force=True
+        ).contiguous()
+
+    new = lambda *shape: torch.empty(shape, dtype=dtype, device=dev)  # noqa: E731
+    s_o, sd_o, q_o, vl_o, om_o, p_o = new(B, n), new(B, n), new(B, 4), new(B, 3), new(B, 3), new(B, 3)
+    soft = isinstance(model.contact_model, SoftContacts)
+    m_o = new(B, nc, 3) if soft else None
+    if soft and m is None:
+        m = torch.zeros(B, nc, 3, dtype=dtype, device=dev)
+    if update_caches:
+        W_H_B, iXl, W_H_L, W_v = new(B, 4, 4), new(B, nL, 6, 6), new(B, nL, 4, 4), new(B, nL, 6)
+    else:
+        W_H_B = iXl = W_H_L = W_v = None
+
+    with torch.cuda.device(dev):
+        rc = _lib.load().b200sim_step(
+            dm.handle, code, B,
+            _ptr(s), _ptr(sd), _ptr(q), _ptr(vl), _ptr(om), _ptr(p), _ptr(m), _ptr(tau), _ptr(fext),
+            _ptr(s_o), _ptr(sd_o), _ptr(q_o), _ptr(vl_o), _ptr(om_o), _ptr(p_o), _ptr(m_o),
+            _ptr(W_H_B), _ptr(iXl), _ptr(W_H_L), _ptr(W_v), _stream_ptr(dev),
+        )
+    _lib.check(rc, "b200sim_step")
+
+    sq = (lambda t: t.squeeze(0) if t is not None else None) if unbatched else (lambda t: t)
+    contact_state = dict(data.contact_state) if data.contact_state else {}
+    if soft:
+        contact_state["tangential_deformation"] = sq(m_o)
+    return _data.JaxSimModelData(
+        velocity_representation=data.velocity_representation,
+        _joint_positions=sq(s_o), _joint_velocities=sq(sd_o), _base_quaternion=sq(q_o),
+        _base_linear_velocity=sq(vl_o), _base_angular_velocity=sq(om_o), _base_position=sq(p_o),
+        _base_transform=sq(W_H_B), _joint_transforms=sq(iXl), _link_transforms=sq(W_H_L),
+        _link_velocities=sq(W_v), contact_state=contact_state,
+    )
+
+
+def forward_dynamics_aba(
+    model: JaxSimModel,
+    data: "_data.JaxSimModelData",
+    *,
+    joint_forces: torch.Tensor | None = None,
+    link_forces: torch.Tensor | None = None,
+) -> tuple[torch.Tensor, torch.Tensor]:
+    """``js.model.forward_dynamics_aba`` (``src/jaxsim/api/model.py:1269-1406``) for
+    ``VelRepr.Inertial`` data: returns the inertial-fixed base acceleration ``(B, 6)`` and
+    the joint accelerations ``(B, n)``.  (The Body/Mixed ``to_active`` conversion of
+    ``:1356-1404`` is a thin host-side shim that is not needed by ``step``.)"""
+    if data.velocity_representation != VelRepr.Inertial:
+        raise NotImplementedError("forward_dynamics_aba: only VelRepr.Inertial data (step forces it, integrators.py:22)")
+    s = _batched(data._joint_positions, 1).contiguous()
+    dev, dtype = s.device, s.dtype
+    dm = model.device_model(dev)
+    nL, n = model.number_of_links(), model.dofs()
+    sd = _batched(data._joint_velocities, 1).contiguous()
+    q = _batched(data._base_quaternion, 1).contiguous()
+    vl = _batched(data._base_linear_velocity, 1).contiguous()
+    om = _batched(data._base_angular_velocity, 1).contiguous()
+    p = _batched(data._base_position, 1).contiguous()
+    B = q.shape[0]
+    tau = None if joint_forces is None else _batched(torch.as_tensor(joint_forces, dtype=dtype, device=dev), 1).contiguous()
+    fext = None if link_forces is None else _batched(torch.as_tensor(link_forces, dtype=dtype, device=dev), 2).contiguous()
+    if tau is not None and tau.shape != (B, n):
+        raise ValueError(tau.shape, (B, n))
+    if fext is not None and fext.shape != (B, nL, 6):
+        raise ValueError(fext.shape, (B, nL, 6))
+    avd = torch.empty(B, 6, dtype=dtype, device=dev)
+    sdd = torch.empty(B, n, dtype=dtype, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().b200sim_aba(
+            dm.handle, _dtype_code(dtype), B, _ptr(s), _ptr(sd), _ptr(q), _ptr(vl), _ptr(om), _ptr(p),
+            _ptr(tau), _ptr(fext), _ptr(avd), _ptr(sdd), _stream_ptr(dev),
+        )
+    _lib.check(rc, "b200sim_aba")
+    if data._joint_positions.dim() == 1:
+        return avd.squeeze(0), sdd.squeeze(0)
+    return avd, sdd

@@ -1,0 +1,491 @@
+// b200sim.cu -- C ABI (include/b200sim.h) over the fused step kernel.
+//
+// Host responsibilities: validate the descriptor, derive the static tables the kernel
+// wants (tree levels, children lists, per-link collidable-point lists, link inertia about
+// the link origin), upload them once, pick the launch geometry, launch on the caller's
+// stream.  No torch types cross this boundary.
+
+#include "b200sim.h"
+#include "b200sim_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace b200sim;
+
+struct B200SimModel {
+  int device = 0;
+  int num_sms = 148;
+  int max_smem_optin = 227 * 1024;
+  int nL = 0, n = 0, nc = 0, depth = 0;
+  int floating = 0, contact_model = 0, enable_friction = 1, flags = 0;
+  double dt = 1e-3, g = -9.81, h_terrain = 0;
+  double K = 1e6, D = 2e3, mu = 0.5, pexp = 0.5, qexp = 0.5;
+  double tau_max = 3000, w_th = 30, w_max = 100;
+  // host copies needed for update_link_params
+  std::vector<double> cst_h;   // nL*CREC
+  std::vector<double> csuc_h;  // nL*12
+  std::vector<double> pt_h;    // nc*3
+  std::vector<int> itab_h;
+  int o_parent = 0, o_jtype = 0, o_lvl_start = 0, o_lvl_links = 0, o_child_start = 0, o_child_idx = 0,
+      o_pt_start = 0, o_pt_idx = 0, o_pt_body = 0, o_pt_enabled = 0;
+  // device blobs
+  float *cst_f = nullptr, *csuc_f = nullptr, *pt_f = nullptr;
+  double *cst_d = nullptr, *csuc_d = nullptr, *pt_d = nullptr;
+  int* itab_d = nullptr;
+  // tuning
+  int tune_G = 0, tune_epb = 0;
+};
+
+namespace {
+
+constexpr int kMaxThreads = 512;
+
+#define CK(x)                         \
+  do {                                \
+    cudaError_t e_ = (x);             \
+    if (e_ != cudaSuccess) return (int)e_; \
+  } while (0)
+
+template <typename T>
+int upload(const std::vector<double>& h, T** d) {
+  std::vector<T> tmp(h.size() > 0 ? h.size() : 1);
+  for (size_t i = 0; i < h.size(); ++i) tmp[i] = (T)h[i];
+  if (!*d) CK(cudaMalloc((void**)d, tmp.size() * sizeof(T)));
+  CK(cudaMemcpy(*d, tmp.data(), tmp.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+void fill_link_consts(B200SimModel* m, const double* mass, const double* com, const double* inertia6) {
+  for (int i = 0; i < m->nL; ++i) {
+    double* c = m->cst_h.data() + (size_t)i * CREC;
+    const double ms = mass[i];
+    const double cx = com[3 * i], cy = com[3 * i + 1], cz = com[3 * i + 2];
+    const double* I = inertia6 + 6 * i;  // xx xy xz yy yz zz at the CoM
+    c[C_MASS] = ms;
+    c[C_COM] = cx; c[C_COM + 1] = cy; c[C_COM + 2] = cz;
+    // D = I_c + m S(c) S(c)^T = I_c + m (|c|^2 1 - c c^T)   (math/inertia.py:32-39)
+    const double cc = cx * cx + cy * cy + cz * cz;
+    c[C_DL + 0] = I[0] + ms * (cc - cx * cx);
+    c[C_DL + 1] = I[1] - ms * cx * cy;
+    c[C_DL + 2] = I[2] - ms * cx * cz;
+    c[C_DL + 3] = I[3] + ms * (cc - cy * cy);
+    c[C_DL + 4] = I[4] - ms * cy * cz;
+    c[C_DL + 5] = I[5] + ms * (cc - cz * cz);
+  }
+}
+
+bool is_identity4(const double* H, double tol = 0.0) {
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c)
+      if (std::fabs(H[4 * r + c] - (r == c ? 1.0 : 0.0)) > tol) return false;
+  return true;
+}
+
+size_t static_smem_bytes(const B200SimModel* m, size_t ts) {
+  size_t w = (size_t)m->nL * CREC * ts;
+  w += (((size_t)m->nc * 3 + 3) & ~size_t(3)) * ts;
+  w += (((size_t)m->itab_h.size() + 3) & ~size_t(3)) * sizeof(int);
+  return w;
+}
+
+size_t env_smem_bytes(const B200SimModel* m, size_t ts) {
+  size_t w = (size_t)m->nL * REC + (size_t)m->nc * PTREC;
+  w = (w + 3) & ~size_t(3);
+  return w * ts;
+}
+
+struct Geometry {
+  int G, epb, grid;
+  size_t smem;
+};
+
+int pick_geometry(const B200SimModel* m, int dtype, long long B, Geometry* g) {
+  const size_t ts = dtype == B200SIM_DTYPE_F64 ? 8 : 4;
+  const size_t st = static_smem_bytes(m, ts), pe = env_smem_bytes(m, ts);
+  const size_t budget = (size_t)m->max_smem_optin - 1024;
+  if (st + pe > budget) return B200SIM_E_TOO_LARGE;
+  int G = m->tune_G;
+  if (G == 0) {
+    // widest tree level / link count bound the useful lanes; 8 balances the sequential
+    // level walks against the link-parallel phases for humanoid-size trees
+    G = 8;
+    while (G > 1 && G / 2 >= m->nL) G /= 2;
+  }
+  const int wg = 32 / G;  // groups per warp
+  long long epb_smem = (long long)((budget - st) / pe);
+  long long epb_thr = kMaxThreads / G;
+  long long epb = std::min(epb_smem, epb_thr);
+  if (m->tune_epb > 0) epb = std::min<long long>(epb, m->tune_epb);
+  // spread a small batch over all SMs
+  long long per_sm = (B + m->num_sms - 1) / m->num_sms;
+  if (m->tune_epb == 0) epb = std::min(epb, std::max<long long>(per_sm, 1));
+  // whole warps only
+  epb = ((epb + wg - 1) / wg) * wg;
+  while (epb > wg && (epb > epb_smem || epb > epb_thr)) epb -= wg;
+  if (epb < 1 || epb > epb_smem) {
+    // a single warp-group row does not fit next to the model: shrink to what fits
+    epb = std::min<long long>(epb_smem, wg);
+    if (epb < 1) return B200SIM_E_TOO_LARGE;
+  }
+  long long blocks = (B + epb - 1) / epb;
+  const size_t smem = st + (size_t)epb * pe;
+  long long resident = std::max<long long>(1, (long long)(budget + 1024) / (long long)(smem + 1024));
+  long long cap = (long long)m->num_sms * resident;
+  g->G = G;
+  g->epb = (int)epb;
+  g->grid = (int)std::max<long long>(1, std::min(blocks, cap));
+  g->smem = smem;
+  return 0;
+}
+
+template <typename T>
+struct Blob;
+template <>
+struct Blob<float> {
+  static const float* cst(const B200SimModel* m) { return m->cst_f; }
+  static const float* csuc(const B200SimModel* m) { return m->csuc_f; }
+  static const float* pt(const B200SimModel* m) { return m->pt_f; }
+};
+template <>
+struct Blob<double> {
+  static const double* cst(const B200SimModel* m) { return m->cst_d; }
+  static const double* csuc(const B200SimModel* m) { return m->csuc_d; }
+  static const double* pt(const B200SimModel* m) { return m->pt_d; }
+};
+
+template <typename T>
+void fill_model_params(const B200SimModel* m, Params<T>& P) {
+  P.cst = Blob<T>::cst(m);
+  P.csuc = Blob<T>::csuc(m);
+  P.pt_pos = Blob<T>::pt(m);
+  P.itab = m->itab_d;
+  P.itab_words = (int)m->itab_h.size();
+  P.nL = m->nL; P.n = m->n; P.nc = m->nc; P.depth = m->depth;
+  P.floating = m->floating; P.contact_model = m->contact_model; P.enable_friction = m->enable_friction;
+  P.flags = m->flags;
+  P.o_parent = m->o_parent; P.o_jtype = m->o_jtype; P.o_lvl_start = m->o_lvl_start; P.o_lvl_links = m->o_lvl_links;
+  P.o_child_start = m->o_child_start; P.o_child_idx = m->o_child_idx; P.o_pt_start = m->o_pt_start;
+  P.o_pt_idx = m->o_pt_idx; P.o_pt_body = m->o_pt_body; P.o_pt_enabled = m->o_pt_enabled;
+  P.dt = (T)m->dt; P.g = (T)m->g; P.h_terrain = (T)m->h_terrain;
+  P.K = (T)m->K; P.D = (T)m->D; P.mu = (T)m->mu; P.pexp = (T)m->pexp; P.qexp = (T)m->qexp;
+  P.tau_max = (T)m->tau_max; P.w_th = (T)m->w_th; P.w_max = (T)m->w_max;
+}
+
+template <typename T, int G>
+int launch_g(const Params<T>& P, const Geometry& g, cudaStream_t st) {
+  auto kern = step_kernel<T, G>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+  kern<<<g.grid, g.epb * G, g.smem, st>>>(P);
+  return (int)cudaGetLastError();
+}
+
+template <typename T>
+int launch(const B200SimModel* m, Params<T>& P, int dtype, void* stream) {
+  Geometry g;
+  int rc = pick_geometry(m, dtype, P.B, &g);
+  if (rc) return rc;
+  P.envs_per_block = g.epb;
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev != m->device) CK(cudaSetDevice(m->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (g.G) {
+    case 1: rc = launch_g<T, 1>(P, g, st); break;
+    case 2: rc = launch_g<T, 2>(P, g, st); break;
+    case 4: rc = launch_g<T, 4>(P, g, st); break;
+    case 8: rc = launch_g<T, 8>(P, g, st); break;
+    case 16: rc = launch_g<T, 16>(P, g, st); break;
+    case 32: rc = launch_g<T, 32>(P, g, st); break;
+    default: rc = B200SIM_E_INVALID;
+  }
+  if (dev != m->device) cudaSetDevice(dev);
+  return rc;
+}
+
+template <typename T>
+int step_t(const B200SimModel* m, int dtype, int64_t B, const void* s, const void* sd, const void* q,
+           const void* vlin, const void* omega, const void* p, const void* mt, const void* tau, const void* fext,
+           void* s_o, void* sd_o, void* q_o, void* vlin_o, void* omega_o, void* p_o, void* m_o, void* W_H_B,
+           void* iXl, void* W_H_L, void* W_v, void* stream) {
+  Params<T> P;
+  std::memset(&P, 0, sizeof(P));
+  fill_model_params(m, P);
+  P.B = B;
+  P.s = (const T*)s; P.sd = (const T*)sd; P.q = (const T*)q; P.vlin = (const T*)vlin; P.omega = (const T*)omega;
+  P.p = (const T*)p; P.m = (const T*)mt; P.tau = (const T*)tau; P.fext = (const T*)fext;
+  P.s_o = (T*)s_o; P.sd_o = (T*)sd_o; P.q_o = (T*)q_o; P.vlin_o = (T*)vlin_o; P.omega_o = (T*)omega_o;
+  P.p_o = (T*)p_o; P.m_o = (T*)m_o;
+  P.W_H_B = (T*)W_H_B; P.iXl = (T*)iXl; P.W_H_L = (T*)W_H_L; P.W_v = (T*)W_v;
+  P.mode = MODE_STEP;
+  return launch(m, P, dtype, stream);
+}
+
+template <typename T>
+int fk_t(const B200SimModel* m, int dtype, int64_t B, const void* s, const void* sd, const void* q, const void* vlin,
+         const void* omega, const void* p, void* q_o, void* W_H_B, void* iXl, void* W_H_L, void* W_v, void* stream) {
+  Params<T> P;
+  std::memset(&P, 0, sizeof(P));
+  fill_model_params(m, P);
+  P.B = B;
+  P.s = (const T*)s; P.sd = (const T*)sd; P.q = (const T*)q; P.vlin = (const T*)vlin; P.omega = (const T*)omega;
+  P.p = (const T*)p;
+  P.q_o = (T*)q_o;
+  P.W_H_B = (T*)W_H_B; P.iXl = (T*)iXl; P.W_H_L = (T*)W_H_L; P.W_v = (T*)W_v;
+  P.mode = MODE_FK;
+  return launch(m, P, dtype, stream);
+}
+
+template <typename T>
+int aba_t(const B200SimModel* m, int dtype, int64_t B, const void* s, const void* sd, const void* q, const void* vlin,
+          const void* omega, const void* p, const void* tau, const void* fext, void* avd, void* sdd, void* stream) {
+  Params<T> P;
+  std::memset(&P, 0, sizeof(P));
+  fill_model_params(m, P);
+  P.B = B;
+  P.s = (const T*)s; P.sd = (const T*)sd; P.q = (const T*)q; P.vlin = (const T*)vlin; P.omega = (const T*)omega;
+  P.p = (const T*)p; P.tau = (const T*)tau; P.fext = (const T*)fext;
+  P.avd = (T*)avd; P.sdd_o = (T*)sdd;
+  P.mode = MODE_ABA;
+  return launch(m, P, dtype, stream);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b200sim_version(void) { return "b200sim abi1 sm_100a fused-step"; }
+
+int b200sim_model_create(const B200SimModelDesc* d, int device, B200SimModel** out) {
+  if (!d || !out) return B200SIM_E_INVALID;
+  if (d->abi_version != B200SIM_ABI_VERSION) return B200SIM_E_INVALID;
+  const int nL = d->n_links, n = d->n_dofs, nc = d->n_points;
+  if (nL < 1 || n != nL - 1 || nc < 0) return B200SIM_E_INVALID;
+  if (!d->parent || !d->joint_type || !d->lam_H_pre || !d->suc_H_i || !d->joint_axis || !d->link_mass ||
+      !d->link_com || !d->link_inertia)
+    return B200SIM_E_INVALID;
+  if (n > 0 && (!d->friction_static || !d->friction_viscous || !d->position_limits_min || !d->position_limits_max ||
+                !d->position_limit_spring || !d->position_limit_damper))
+    return B200SIM_E_INVALID;
+  if (nc > 0 && (!d->point_body || !d->point_position || !d->point_enabled)) return B200SIM_E_INVALID;
+  if (d->contact_model != B200SIM_CONTACT_NONE && d->contact_model != B200SIM_CONTACT_SOFT) return B200SIM_E_UNSUPPORTED;
+  if (d->parent[0] != -1) return B200SIM_E_INVALID;
+  for (int i = 1; i < nL; ++i) {
+    if (d->parent[i] < 0 || d->parent[i] >= i) return B200SIM_E_INVALID;  // lambda(i) < i
+    if (d->joint_type[i] != 1 && d->joint_type[i] != 2) return B200SIM_E_UNSUPPORTED;
+  }
+  for (int k = 0; k < nc; ++k)
+    if (d->point_body[k] < 0 || d->point_body[k] >= nL) return B200SIM_E_INVALID;
+
+  B200SimModel* m = new (std::nothrow) B200SimModel();
+  if (!m) return B200SIM_E_INVALID;
+  m->device = device;
+  m->nL = nL; m->n = n; m->nc = nc;
+  m->floating = d->floating_base ? 1 : 0;
+  m->contact_model = d->contact_model;
+  m->enable_friction = d->enable_friction ? 1 : 0;
+  m->dt = d->time_step; m->g = d->gravity; m->h_terrain = d->terrain_height;
+  m->K = d->soft_K; m->D = d->soft_D; m->mu = d->soft_mu; m->pexp = d->soft_p; m->qexp = d->soft_q;
+  m->tau_max = d->torque_max; m->w_th = d->omega_th; m->w_max = d->omega_max;
+
+  // ---- per-link constants
+  m->cst_h.assign((size_t)nL * CREC, 0.0);
+  m->csuc_h.assign((size_t)nL * 12, 0.0);
+  bool suc_nonid = false;
+  for (int i = 0; i < nL; ++i) {
+    double* c = m->cst_h.data() + (size_t)i * CREC;
+    const double* H = d->lam_H_pre + 16 * (size_t)i;
+    const double* Hs = d->suc_H_i + 16 * (size_t)i;
+    for (int r = 0; r < 3; ++r) {
+      for (int cc = 0; cc < 3; ++cc) {
+        c[C_RPRE + 3 * r + cc] = H[4 * r + cc];
+        m->csuc_h[(size_t)i * 12 + 3 * r + cc] = Hs[4 * r + cc];
+      }
+      c[C_TPRE + r] = H[4 * r + 3];
+      m->csuc_h[(size_t)i * 12 + 9 + r] = Hs[4 * r + 3];
+    }
+    if (i >= 1 && !is_identity4(Hs)) suc_nonid = true;
+    for (int r = 0; r < 3; ++r) c[C_AXIS + r] = d->joint_axis[3 * (size_t)i + r];
+    if (i >= 1) {
+      const int j = i - 1;
+      c[C_KS] = d->position_limit_spring[j];
+      c[C_KD] = d->position_limit_damper[j];
+      c[C_SMIN] = d->position_limits_min[j];
+      c[C_SMAX] = d->position_limits_max[j];
+      c[C_KC] = d->friction_static[j];
+      c[C_KV] = d->friction_viscous[j];
+    }
+  }
+  fill_link_consts(m, d->link_mass, d->link_com, d->link_inertia);
+  m->pt_h.assign(d->point_position, d->point_position + (size_t)nc * 3);
+
+  m->flags = 0;
+  if (suc_nonid) m->flags |= F_SUC_NONID;
+  if (!m->floating || !is_identity4(d->suc_H_i)) m->flags |= F_GENERIC_FK;
+  if (d->soft_p == 0.5) m->flags |= F_SQRT_P;
+  if (d->soft_q == 0.5) m->flags |= F_SQRT_Q;
+
+  // ---- integer tables
+  std::vector<int> depth(nL, 0);
+  int maxd = 0;
+  for (int i = 1; i < nL; ++i) { depth[i] = depth[d->parent[i]] + 1; maxd = std::max(maxd, depth[i]); }
+  m->depth = maxd;
+  std::vector<int> lvl_start(maxd + 2, 0), lvl_links;
+  for (int l = 0; l <= maxd; ++l) {
+    lvl_start[l] = (int)lvl_links.size();
+    for (int i = 0; i < nL; ++i) if (depth[i] == l) lvl_links.push_back(i);
+  }
+  lvl_start[maxd + 1] = (int)lvl_links.size();
+  std::vector<int> child_start(nL + 1, 0), child_idx;
+  for (int i = 0; i < nL; ++i) {
+    child_start[i] = (int)child_idx.size();
+    for (int c = 1; c < nL; ++c) if (d->parent[c] == i) child_idx.push_back(c);
+  }
+  child_start[nL] = (int)child_idx.size();
+  std::vector<int> pt_start(nL + 1, 0), pt_idx;
+  for (int i = 0; i < nL; ++i) {
+    pt_start[i] = (int)pt_idx.size();
+    for (int k = 0; k < nc; ++k) if (d->point_body[k] == i) pt_idx.push_back(k);
+  }
+  pt_start[nL] = (int)pt_idx.size();
+
+  auto push = [&](const int* src, size_t cnt) {
+    int off = (int)m->itab_h.size();
+    m->itab_h.insert(m->itab_h.end(), src, src + cnt);
+    return off;
+  };
+  std::vector<int> lvl_start2(lvl_start);  // lvl_start has depth+2 entries: [0..depth+1]
+  m->o_parent = push(d->parent, nL);
+  m->o_jtype = push(d->joint_type, nL);
+  m->o_lvl_start = push(lvl_start2.data(), lvl_start2.size());
+  m->o_lvl_links = push(lvl_links.data(), lvl_links.size());
+  m->o_child_start = push(child_start.data(), child_start.size());
+  m->o_child_idx = push(child_idx.data(), child_idx.size());
+  m->o_pt_start = push(pt_start.data(), pt_start.size());
+  m->o_pt_idx = push(pt_idx.data(), pt_idx.size());
+  m->o_pt_body = push(d->point_body, nc);
+  m->o_pt_enabled = push(d->point_enabled, nc);
+  if (m->itab_h.empty()) m->itab_h.push_back(0);
+
+  // ---- upload
+  int prev = 0;
+  cudaError_t e = cudaGetDevice(&prev);
+  if (e != cudaSuccess) { delete m; return (int)e; }
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) { delete m; return (int)e; }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) { delete m; return (int)e; }
+  m->num_sms = prop.multiProcessorCount;
+  m->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  int rc = 0;
+  if (!rc) rc = upload(m->cst_h, &m->cst_f);
+  if (!rc) rc = upload(m->cst_h, &m->cst_d);
+  if (!rc) rc = upload(m->csuc_h, &m->csuc_f);
+  if (!rc) rc = upload(m->csuc_h, &m->csuc_d);
+  if (!rc) rc = upload(m->pt_h, &m->pt_f);
+  if (!rc) rc = upload(m->pt_h, &m->pt_d);
+  if (!rc) {
+    e = cudaMalloc((void**)&m->itab_d, m->itab_h.size() * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpy(m->itab_d, m->itab_h.data(), m->itab_h.size() * sizeof(int), cudaMemcpyHostToDevice);
+    rc = (int)e;
+  }
+  cudaSetDevice(prev);
+  if (rc) { b200sim_model_destroy(m); return rc; }
+  // the model must fit at least one environment per block in both precisions we may be asked for
+  Geometry g;
+  rc = pick_geometry(m, B200SIM_DTYPE_F32, 1, &g);
+  if (rc) { b200sim_model_destroy(m); return rc; }
+  *out = m;
+  return 0;
+}
+
+void b200sim_model_destroy(B200SimModel* m) {
+  if (!m) return;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(m->device);
+  cudaFree(m->cst_f); cudaFree(m->cst_d); cudaFree(m->csuc_f); cudaFree(m->csuc_d);
+  cudaFree(m->pt_f); cudaFree(m->pt_d); cudaFree(m->itab_d);
+  cudaSetDevice(prev);
+  delete m;
+}
+
+int b200sim_model_update_link_params(B200SimModel* m, const double* mass, const double* com, const double* inertia6) {
+  if (!m || !mass || !com || !inertia6) return B200SIM_E_INVALID;
+  fill_link_consts(m, mass, com, inertia6);
+  int prev = 0;
+  CK(cudaGetDevice(&prev));
+  CK(cudaSetDevice(m->device));
+  CK(cudaDeviceSynchronize());
+  int rc = upload(m->cst_h, &m->cst_f);
+  if (!rc) rc = upload(m->cst_h, &m->cst_d);
+  cudaSetDevice(prev);
+  return rc;
+}
+
+int b200sim_model_set_tuning(B200SimModel* m, int lanes_per_env, int envs_per_block) {
+  if (!m) return B200SIM_E_INVALID;
+  const int G = lanes_per_env;
+  if (!(G == 0 || G == 1 || G == 2 || G == 4 || G == 8 || G == 16 || G == 32)) return B200SIM_E_INVALID;
+  if (envs_per_block < 0) return B200SIM_E_INVALID;
+  m->tune_G = G;
+  m->tune_epb = envs_per_block;
+  return 0;
+}
+
+int b200sim_model_query(const B200SimModel* m, int dtype, int64_t B, int32_t* G, int32_t* epb, int32_t* grid, int32_t* smem) {
+  if (!m || B < 1 || (dtype != 0 && dtype != 1)) return B200SIM_E_INVALID;
+  Geometry g;
+  int rc = pick_geometry(m, dtype, B, &g);
+  if (rc) return rc;
+  if (G) *G = g.G;
+  if (epb) *epb = g.epb;
+  if (grid) *grid = g.grid;
+  if (smem) *smem = (int32_t)g.smem;
+  return 0;
+}
+
+int b200sim_step(const B200SimModel* m, int dtype, int64_t B, const void* s, const void* sd, const void* q,
+                 const void* vlin, const void* omega, const void* p, const void* mt, const void* tau, const void* fext,
+                 void* s_o, void* sd_o, void* q_o, void* vlin_o, void* omega_o, void* p_o, void* m_o, void* W_H_B,
+                 void* iXl, void* W_H_L, void* W_v, void* stream) {
+  if (!m || B < 0 || (dtype != 0 && dtype != 1)) return B200SIM_E_INVALID;
+  if (B == 0) return 0;
+  if (!q || !vlin || !omega || !p || !q_o || !vlin_o || !omega_o || !p_o) return B200SIM_E_INVALID;
+  if (m->n > 0 && (!s || !sd || !s_o || !sd_o)) return B200SIM_E_INVALID;
+  if (dtype == 0)
+    return step_t<float>(m, dtype, B, s, sd, q, vlin, omega, p, mt, tau, fext, s_o, sd_o, q_o, vlin_o, omega_o, p_o, m_o,
+                         W_H_B, iXl, W_H_L, W_v, stream);
+  return step_t<double>(m, dtype, B, s, sd, q, vlin, omega, p, mt, tau, fext, s_o, sd_o, q_o, vlin_o, omega_o, p_o, m_o,
+                        W_H_B, iXl, W_H_L, W_v, stream);
+}
+
+int b200sim_fk(const B200SimModel* m, int dtype, int64_t B, const void* s, const void* sd, const void* q,
+               const void* vlin, const void* omega, const void* p, void* q_o, void* W_H_B, void* iXl, void* W_H_L,
+               void* W_v, void* stream) {
+  if (!m || B < 0 || (dtype != 0 && dtype != 1)) return B200SIM_E_INVALID;
+  if (B == 0) return 0;
+  if (!q || !vlin || !omega || !p) return B200SIM_E_INVALID;
+  if (m->n > 0 && (!s || !sd)) return B200SIM_E_INVALID;
+  if (dtype == 0) return fk_t<float>(m, dtype, B, s, sd, q, vlin, omega, p, q_o, W_H_B, iXl, W_H_L, W_v, stream);
+  return fk_t<double>(m, dtype, B, s, sd, q, vlin, omega, p, q_o, W_H_B, iXl, W_H_L, W_v, stream);
+}
+
+int b200sim_aba(const B200SimModel* m, int dtype, int64_t B, const void* s, const void* sd, const void* q,
+                const void* vlin, const void* omega, const void* p, const void* tau, const void* fext, void* avd,
+                void* sdd, void* stream) {
+  if (!m || B < 0 || (dtype != 0 && dtype != 1)) return B200SIM_E_INVALID;
+  if (B == 0) return 0;
+  if (!q || !vlin || !omega || !p || !avd) return B200SIM_E_INVALID;
+  if (m->n > 0 && (!s || !sd || !sdd)) return B200SIM_E_INVALID;
+  if (dtype == 0) return aba_t<float>(m, dtype, B, s, sd, q, vlin, omega, p, tau, fext, avd, sdd, stream);
+  return aba_t<double>(m, dtype, B, s, sd, q, vlin, omega, p, tau, fext, avd, sdd, stream);
+}
+
+}  // extern "C"

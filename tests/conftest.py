@@ -1,0 +1,27 @@
+"""pytest configuration: the ``gpu`` marker + shared fixtures.
+
+``-m "not gpu"`` (CPU box): oracle pins, loader/host logic, C-ABI symbol checks, gloo tests.
+``-m gpu`` (B200): parity of the CUDA path against the oracle, through the C ABI.
+"""
+
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def cuda_device():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")

@@ -1,0 +1,88 @@
+"""Shared helpers for the parity tests: bridge between the product objects
+(``jaxsim_b200.api``) and the oracle's (``oracle.jaxsim_oracle``)."""
+
+from __future__ import annotations
+
+import numpy as np
+
+import jaxsim_b200.api as js
+from jaxsim_b200 import models
+from jaxsim_b200.rbda.contacts import SoftContacts
+from oracle import jaxsim_oracle as O
+
+# north_star tolerances: 1e-5 rel (fp64) / 1e-3 rel (fp32)
+RTOL = {"float64": 1e-5, "float32": 1e-3}
+
+
+def build_model(name: str, **kw):
+    return js.model.JaxSimModel.build_from_model_description(models.urdf(name), **kw)
+
+
+def oracle_model(model) -> O.OracleModel:
+    prm = model.contact_params
+    soft = isinstance(model.contact_model, SoftContacts)
+    return O.OracleModel(
+        kin_dyn_parameters=model.kin_dyn_parameters, floating_base=model.floating_base(),
+        time_step=model.time_step, gravity=model.gravity, terrain_height=model.terrain.height(),
+        contact_model="soft" if soft else "none",
+        K=prm.K, D=prm.D, mu=prm.mu, p=prm.p, q=prm.q,
+        torque_max=model.actuation_params.torque_max, omega_th=model.actuation_params.omega_th,
+        omega_max=model.actuation_params.omega_max, enable_friction=model.actuation_params.enable_friction,
+    )
+
+
+def to_product(model, od: O.OracleData, dtype, device, velocity_representation=None):
+    """OracleData (numpy) -> JaxSimModelData (torch on device) holding the SAME numbers."""
+    import torch
+
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device=device)  # noqa: E731
+    vr = js.common.VelRepr.Inertial if velocity_representation is None else velocity_representation
+    cs = {}
+    if od.tangential_deformation is not None and isinstance(model.contact_model, SoftContacts):
+        cs["tangential_deformation"] = t(od.tangential_deformation)
+    # velocities are given inertial-fixed: build in Inertial representation then relabel
+    d = js.data.JaxSimModelData.build(
+        model, base_position=t(od.base_position), base_quaternion=t(od.base_quaternion),
+        joint_positions=t(od.joint_positions), joint_velocities=t(od.joint_velocities),
+        base_linear_velocity=t(od.base_linear_velocity), base_angular_velocity=t(od.base_angular_velocity),
+        contact_state=cs, velocity_representation=js.common.VelRepr.Inertial,
+        batch_size=od.base_position.shape[0], dtype=dtype, device=device,
+    )
+    d.velocity_representation = vr
+    return d
+
+
+LEAVES = [
+    ("joint_positions", "_joint_positions"), ("joint_velocities", "_joint_velocities"),
+    ("base_quaternion", "_base_quaternion"), ("base_linear_velocity", "_base_linear_velocity"),
+    ("base_angular_velocity", "_base_angular_velocity"), ("base_position", "_base_position"),
+    ("base_transform", "_base_transform"), ("joint_transforms", "_joint_transforms"),
+    ("link_transforms", "_link_transforms"), ("link_velocities", "_link_velocities"),
+]
+
+
+def rel_err(x: np.ndarray, ref: np.ndarray) -> float:
+    """max |x - ref| / max(|ref|, tiny): relative to the scale of the leaf."""
+    if ref.size == 0:
+        return 0.0
+    scale = max(float(np.max(np.abs(ref))), 1e-12)
+    return float(np.max(np.abs(x.astype(np.float64) - ref.astype(np.float64)))) / scale
+
+
+def compare_data(pd, od: O.OracleData, rtol: float, what="") -> dict:
+    errs = {}
+    for oname, pname in LEAVES:
+        ref = getattr(od, oname)
+        got = getattr(pd, pname)
+        if got is None:
+            continue
+        errs[oname] = rel_err(got.detach().cpu().numpy(), ref)
+    if "tangential_deformation" in pd.contact_state and od.tangential_deformation is not None:
+        ref = od.tangential_deformation
+        got = pd.contact_state["tangential_deformation"].detach().cpu().numpy()
+        # the deformation state is O(1e-6): compare against the scale of dt * velocity
+        scale = max(float(np.max(np.abs(ref))), 1e-6)
+        errs["tangential_deformation"] = float(np.max(np.abs(got - ref))) / scale
+    bad = {k: v for k, v in errs.items() if not (v <= rtol)}
+    assert not bad, f"{what}: leaves out of tolerance {rtol}: {bad} (all: {errs})"
+    return errs
