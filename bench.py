@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the batched simulation step (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--batch B] [--dtype f32|f64]
+
+Workload (config.workload): BASELINE.json configs[1] -- iCub-like 23-DoF floating-base
+humanoid, soft contacts, fp32, batch 4096 PER GPU (weak scaling: every rank steps its own
+shard of environments, no data-path collective; one NCCL all_gather of the state leaves is
+performed after the timed region and reported separately as `readback_allgather_ms`).
+
+One "step" = one call of the drop-in `step` over the whole batch.  Timing rules followed:
+W >= 3 warm-ups; the K timed steps walk a RING of independent state sets whose total
+footprint exceeds 2x the 126 MB L2, so every step's inputs come from HBM (config.l2);
+CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
+
+Keys beyond the base contract: `roofline` (HBM, algorithmic bytes B_api of SURVEY.md 8d /
+measured copy bandwidth), `cpu_baseline` (the NumPy oracle port timed on the host cores on
+a bounded sample), `e2e` (same metric through the public API with pinned HOST buffers:
+H2D of the state + torques, step, D2H of the new state, every step), `clocks`,
+`gpu_launches`.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import pathlib
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+
+METRIC = "env-steps/sec"
+UNIT = "env-steps/s"
+WORKLOAD = "icub_like 23-DoF floating base, soft contacts (BASELINE.json configs[1])"
+L2_BYTES = 126 * 1024 * 1024
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="environments per GPU")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--model", default="icub_like")
+    ap.add_argument("--lanes", type=int, default=0, help="lanes per env (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="also time batch 16384 and 65536 on this GPU")
+    return ap.parse_args()
+
+
+def algorithmic_bytes_per_env(n, nL, nc, w, caches=True):
+    """B_api / B_min of SURVEY.md 8d."""
+    b = 2 * (2 * n + 13) + 6 * nc + n
+    if caches:
+        b += 16 + 58 * nL
+    return w * b
+
+
+def measured_peak_gbs():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for t, line in self.lines:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                if t0 - 0.2 <= t <= t1 + 0.2:
+                    sm.append(float(parts[0]))
+                smax = float(parts[1])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                if val.lower().startswith("active") and t0 - 0.2 <= t <= t1 + 0.2:
+                    reasons.add(name)
+        if not sm:  # region shorter than the sampling period: use every sample we have
+            for t, line in self.lines:
+                try:
+                    sm.append(float(line.split(",")[0]))
+                except ValueError:
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def _oracle_setup(model_name, B, seed, dtype_np):
+    from oracle import jaxsim_oracle as O
+    from tests import helpers as H
+
+    model = H.build_model(model_name)
+    om = H.oracle_model(model)
+    od = O.random_model_data(om, B, seed=seed, dtype=dtype_np)
+    return O, om, od
+
+
+def _cpu_worker(args):
+    model_name, B, seed, dtype_name, reps = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    dtype_np = np.float32 if dtype_name == "f32" else np.float64
+    O, om, od = _oracle_setup(model_name, B, seed, dtype_np)
+    O.step(om, od)  # warm
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        od2 = O.step(om, od)
+    return time.perf_counter() - t0, float(od2.joint_positions.sum()) if od2.joint_positions.size else 0.0
+
+
+def cpu_oracle_throughput(model_name, dtype_name, sample_envs, reps, procs):
+    """The NumPy oracle port on `procs` host processes, each stepping sample_envs/procs envs."""
+    import multiprocessing as mp
+
+    per = max(1, sample_envs // procs)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(procs) as pool:
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker, [(model_name, per, 100 + i, dtype_name, reps) for i in range(procs)])
+        wall = time.perf_counter() - t0
+    busy = max(r[0] for r in res)
+    return per * procs * reps / busy, per * procs, busy, wall
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU implementation of the path.  JAX/jaxsim are
+    not installable offline, so this times the oracle PORT (NumPy restatement)
+    on all host cores; each step = a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64))
+    sample = min(args.batch, 64 * procs)
+    # warmup + timed inside the workers; K steps each
+    t = time.perf_counter()
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_oracle_throughput(args.model, args.dtype, sample, 1, procs)
+    K = max(1, min(args.steps, 20))
+    value, n_envs, busy, wall = cpu_oracle_throughput(args.model, args.dtype, sample, K, procs)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+        "warmup": args.warmup, "ms_per_step": 1e3 * busy / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic (random_model_data distribution, NumPy Philox)",
+        "config": {"workload": WORKLOAD, "model": args.model, "batch_per_gpu": args.batch, "dt": 1e-3,
+                   "note": "reference arm = NumPy oracle port of the jaxsim step (JAX not installable offline)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
+                         "sample": f"{n_envs} of {args.batch} envs per step, {K} steps, {procs} processes"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import jaxsim_b200.api as js
+    from jaxsim_b200 import models
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    dtype = torch.float32 if args.dtype == "f32" else torch.float64
+    w = 4 if args.dtype == "f32" else 8
+
+    model = js.model.JaxSimModel.build_from_model_description(models.urdf(args.model), time_step=1e-3)
+    if args.lanes:
+        model.set_tuning(lanes_per_env=args.lanes)
+    n, nL, nc = model.dofs(), model.number_of_links(), model.number_of_collidable_points()
+    B = args.batch
+    bytes_env = algorithmic_bytes_per_env(n, nL, nc, w, caches=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def time_steps(Bq, K, W):
+        """K device-resident steps over a ring of state sets larger than L2."""
+        ring = max(2, int(np.ceil(2 * L2_BYTES / (Bq * bytes_env))))
+        ring = min(ring, 64)
+        datas = [js.data.random_model_data(model, batch_size=Bq, seed=1000 * rank + r, dtype=dtype, device=dev,
+                                           velocity_representation=js.common.VelRepr.Inertial) for r in range(ring)]
+        taus = [10 * torch.rand(Bq, n, dtype=dtype, device=dev) for _ in range(ring)]
+        for i in range(W):
+            js.model.step(model, datas[i % ring], joint_force_references=taus[i % ring])
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for i in range(K):
+            out = js.model.step(model, datas[i % ring], joint_force_references=taus[i % ring])
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        return ms, ring, out
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    t0 = time.time()
+    ms, ring, out = time_steps(B, args.steps, max(3, args.warmup))
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = B * world * args.steps / (ms_max * 1e-3)
+
+    # ---- state readback across ranks (config 4: NCCL all_gather only at readback)
+    gather_ms = None
+    if world > 1:
+        leaves = torch.cat([out._joint_positions, out._joint_velocities, out._base_quaternion, out._base_linear_velocity,
+                            out._base_angular_velocity, out._base_position,
+                            out.contact_state["tangential_deformation"].reshape(B, -1)], dim=-1).contiguous()
+        full = torch.empty(world * B, leaves.shape[1], dtype=dtype, device=dev)
+        dist.all_gather_into_tensor(full, leaves)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        dist.all_gather_into_tensor(full, leaves)
+        g1.record()
+        barrier()
+        tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        gather_ms = float(tg.item())
+
+    # ---- e2e: public API with pinned host buffers, H2D + step + D2H every step
+    Ke = max(5, min(args.steps, 50))
+    host = js.data.random_model_data(model, batch_size=B, seed=7 + rank, dtype=dtype, device=dev,
+                                     velocity_representation=js.common.VelRepr.Inertial)
+    names = ["_joint_positions", "_joint_velocities", "_base_quaternion", "_base_linear_velocity",
+             "_base_angular_velocity", "_base_position"]
+    h_in = {k: getattr(host, k).cpu().pin_memory() for k in names}
+    h_in["m"] = host.contact_state["tangential_deformation"].cpu().pin_memory()
+    h_in["tau"] = (10 * torch.rand(B, n, dtype=dtype)).pin_memory()
+    h_out = {k: torch.empty_like(v).pin_memory() for k, v in h_in.items() if k != "tau"}
+    h2d = sum(v.numel() * v.element_size() for v in h_in.values())
+    d2h = sum(v.numel() * v.element_size() for v in h_out.values())
+
+    def e2e_step():
+        d = {k: v.to(dev, non_blocking=True) for k, v in h_in.items()}
+        data = js.data.JaxSimModelData(
+            velocity_representation=js.common.VelRepr.Inertial, _joint_positions=d["_joint_positions"],
+            _joint_velocities=d["_joint_velocities"], _base_quaternion=d["_base_quaternion"],
+            _base_linear_velocity=d["_base_linear_velocity"], _base_angular_velocity=d["_base_angular_velocity"],
+            _base_position=d["_base_position"], contact_state={"tangential_deformation": d["m"]},
+        )
+        o = js.model.step(model, data, joint_force_references=d["tau"])
+        for k in names:
+            h_out[k].copy_(getattr(o, k), non_blocking=True)
+        h_out["m"].copy_(o.contact_state["tangential_deformation"], non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(Ke):
+        e2e_step()
+    e1.record()
+    barrier()
+    te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = B * world * Ke / (float(te.item()) * 1e-3)
+
+    # ---- optional batch sweep on this GPU (metric is quoted "batch 4096 -> 65536")
+    sweep = None
+    if args.sweep and world == 1:
+        sweep = []
+        for Bq in (4096, 16384, 65536):
+            msq, rq, _ = time_steps(Bq, max(20, args.steps // 4), 3)
+            Kq = max(20, args.steps // 4)
+            sweep.append({"batch": Bq, "value": Bq * Kq / (msq * 1e-3), "ms_per_step": msq / Kq, "ring": rq})
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak_gbs()
+    ms_step = ms_max / args.steps
+    achieved = B * bytes_env / (ms_step * 1e-3) / 1e9
+    geo = model.launch_geometry(B, dtype, dev)
+    traffic = None
+    tp = ROOT / "profiles" / "traffic_per_launch.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get(f"{args.model}_{args.dtype}_B{B}")
+        except Exception:
+            traffic = None
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        procs = max(1, min(cores, 64))
+        sample = min(B, 32 * procs)
+        v, n_envs, busy, wall = cpu_oracle_throughput(args.model, args.dtype, sample, 5, procs)
+        cpu = {"value": v, "unit": UNIT, "cores": procs, "kind": "port",
+               "sample": f"{n_envs} of {B} envs per step x 5 steps on {procs} processes (NumPy oracle port; JAX unavailable)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.dtype, "data": "synthetic (random_model_data distribution, seeded torch generator; random-init state)",
+        "config": {"workload": WORKLOAD, "model": args.model, "dofs": n, "links": nL, "collidable_points": nc,
+                   "batch_per_gpu": B, "global_batch": B * world, "dt": 1e-3, "contact_model": "soft",
+                   "integrator": "semi_implicit_euler", "parallelism": f"env-parallel x{world} (no data-path collective)",
+                   "l2": f"inputs larger than L2: ring of {ring} independent state sets ({ring * B * bytes_env / 2**20:.0f} MiB)",
+                   "launch": geo, "caches_written": True},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "bytes_per_env_step": bytes_env, "peak_source": peak_src,
+                     "note": "algorithmic bytes = B_api (SURVEY.md 8d): read state+contact state+tau, write state+contact state+all caches"},
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
+                "note": "public API js.model.step with pinned host buffers: H2D(state, contact state, tau) + step + D2H(new state, contact state) each step; caches stay on device"},
+        "gpu_launches": args.steps,
+        "clocks": clocks,
+    }
+    if gather_ms is not None:
+        line["readback_allgather_ms"] = gather_ms
+    if sweep is not None:
+        line["sweep"] = sweep
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

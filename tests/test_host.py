@@ -1,0 +1,131 @@
+"""CPU tests of the host logic: URDF loader, model container, C-ABI surface."""
+
+import ctypes
+import os
+import pathlib
+import re
+
+import numpy as np
+import pytest
+
+import jaxsim_b200.api as js
+from jaxsim_b200 import _lib, models
+from jaxsim_b200.api.kin_dyn_parameters import LinkParameters
+from jaxsim_b200.parsers.urdf import build_kin_dyn_parameters
+
+ROOT = pathlib.Path(__file__).resolve().parents[1]
+
+
+def test_icub_like_topology():
+    name, kd, floating = build_kin_dyn_parameters(models.urdf("icub_like"))
+    assert floating and kd.number_of_links() == 24 and kd.number_of_joints() == 23
+    assert kd.link_names[0] == "root_link"
+    # BFS with children sorted by name (parsers/kinematic_graph.py:669-709)
+    assert kd.link_names[1:4] == ("l_hip_1", "r_hip_1", "torso_1")
+    assert np.all(kd.parent_array[1:] < np.arange(1, 24)) and kd.parent_array[0] == -1
+    # joint index == child link index
+    assert kd.joint_model.joint_names[1] == "l_hip_pitch" and kd.joint_model.joint_names[3] == "torso_pitch"
+    # levels are contiguous index ranges
+    flat = [i for lvl in kd.levels() for i in lvl]
+    assert flat == list(range(24))
+    # the head (fixed joint) was lumped into the chest and became a frame
+    chest = kd.link_names.index("chest")
+    assert abs(kd.link_parameters.mass[chest] - 7.8) < 1e-12
+    assert "head" in kd.frame_parameters.name and "head" not in kd.link_names
+    # two feet x 8 box corners
+    assert len(kd.contact_parameters.body) == 16
+    assert set(kd.contact_parameters.body) == {kd.link_names.index("l_foot"), kd.link_names.index("r_foot")}
+    # URDF convention: suc_H_i = I, lam_H_pre = joint origin
+    assert np.allclose(kd.joint_model.suc_H_i, np.eye(4))
+    assert np.allclose(kd.motion_subspaces[0], 0)
+
+
+def test_fixed_base_and_lumping():
+    name, kd, floating = build_kin_dyn_parameters(models.urdf("pendulum"))
+    assert not floating and kd.link_names == ("base", "arm")
+    # world joint origin lands in suc_H_i[0] (math/joint_model.py:78-83, parser.py:192-197)
+    assert np.allclose(kd.joint_model.suc_H_i[0][0:3, 3], [0, 0, 1.0])
+    assert kd.joint_model.joint_dofs[0] == 0
+    # bob (1 kg at -0.5) lumped into the arm (0.5 kg at -0.25): M += X^T M X
+    assert abs(kd.link_parameters.mass[1] - 1.5) < 1e-12
+    assert np.allclose(kd.link_parameters.center_of_mass[1], [0, 0, -(0.5 * 0.25 + 1.0 * 0.5) / 1.5])
+    # collidable points: base box 8 + bob sphere 50 (moved to the arm)
+    assert kd.contact_parameters.body.count(0) == 8 and kd.contact_parameters.body.count(1) == 50
+    # continuous joint: unbounded limits
+    assert kd.joint_parameters.position_limits_max[0] > 1e300
+
+
+def test_spatial_inertia_roundtrip():
+    rng = np.random.default_rng(0)
+    _, kd, _ = build_kin_dyn_parameters(models.urdf("ergocub_like"))
+    M = kd.link_parameters.spatial_inertias()
+    lp2 = LinkParameters.from_spatial_inertias(M)
+    assert np.allclose(lp2.mass, kd.link_parameters.mass)
+    assert np.allclose(lp2.center_of_mass, kd.link_parameters.center_of_mass)
+    assert np.allclose(lp2.inertia_elements, kd.link_parameters.inertia_elements)
+    for Mi in M:
+        assert np.allclose(Mi, Mi.T) and np.all(np.linalg.eigvalsh(Mi) > 0)
+
+
+def test_collision_env_vars(monkeypatch):
+    monkeypatch.setenv("JAXSIM_COLLISION_USE_BOTTOM_ONLY", "1")
+    _, kd, _ = build_kin_dyn_parameters(models.urdf("box"))
+    assert len(kd.contact_parameters.body) == 4
+    assert np.all(kd.contact_parameters.point[:, 2] < 0)
+    monkeypatch.setenv("JAXSIM_COLLISION_USE_BOTTOM_ONLY", "0")
+    monkeypatch.setenv("JAXSIM_COLLISION_SPHERE_POINTS", "20")
+    _, kd, _ = build_kin_dyn_parameters(models.urdf("sphere"))
+    assert len(kd.contact_parameters.body) == 20
+    assert np.allclose(np.linalg.norm(kd.contact_parameters.point, axis=1), 0.1)
+
+
+def test_model_defaults():
+    m = js.model.JaxSimModel.build_from_model_description(models.urdf("icub_like"))
+    assert m.time_step == 0.001 and m.gravity == -9.81  # api/model.py:54-62,206
+    assert type(m.contact_model).__name__ == "SoftContacts"
+    assert (m.contact_params.K, m.contact_params.D, m.contact_params.mu) == (1e6, 2000.0, 0.5)
+    assert m.actuation_params.torque_max == 3000.0 and m.actuation_params.enable_friction
+    assert m.dofs() == 23 and m.floating_base() and len(m.joint_names()) == 23
+    with pytest.raises(NotImplementedError):
+        js.model.JaxSimModel.build_from_model_description(
+            models.urdf("box"), contact_model=__import__("jaxsim_b200").rbda.contacts.RigidContacts.build()
+        )
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "b200sim.h").read_text()
+    declared = set(re.findall(r"\b(b200sim_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    lib = _lib.load()
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert b"sm_100a" in lib.b200sim_version()
+    # descriptor layout: ctypes mirror == C struct (8 int32 + 17 pointers + 11 doubles)
+    assert ctypes.sizeof(_lib.B200SimModelDesc) == 8 * 4 + 17 * 8 + 11 * 8
+
+
+def test_invalid_arguments_are_rejected_without_a_gpu():
+    lib = _lib.load()
+    out = ctypes.c_void_p()
+    assert lib.b200sim_model_create(None, 0, ctypes.byref(out)) == -1
+    d = _lib.B200SimModelDesc(abi_version=999)
+    assert lib.b200sim_model_create(ctypes.byref(d), 0, ctypes.byref(out)) == -1
+    assert lib.b200sim_model_set_tuning(None, 8, 0) == -1
+    assert lib.b200sim_step(None, 0, 1, *([None] * 21)) == -1
+    assert lib.b200sim_fk(None, 0, 1, *([None] * 12)) == -1
+    assert lib.b200sim_aba(None, 0, 1, *([None] * 11)) == -1
+
+
+def test_product_path_has_no_cpu_fallback():
+    import torch
+
+    m = js.model.JaxSimModel.build_from_model_description(models.urdf("box"))
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(RuntimeError):
+        js.data.JaxSimModelData.build(m, device="cpu")
+
+
+def test_product_does_not_import_the_oracle():
+    for p in (ROOT / "jaxsim_b200").rglob("*.py"):
+        assert "oracle" not in p.read_text(), p
