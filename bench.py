@@ -12,6 +12,8 @@ One "step" = one call of the drop-in `step` over the whole batch.  Timing rules 
 W >= 3 warm-ups; the K timed steps walk a RING of independent state sets whose total
 footprint exceeds 2x the 126 MB L2, so every step's inputs come from HBM (config.l2);
 CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
+The K timed launches are replayed from one CUDA graph (launch-bound inner loop; `eager`
+reports the same K steps launched one by one from Python).
 
 Keys beyond the base contract: `roofline` (HBM, algorithmic bytes B_api of SURVEY.md 8d /
 measured copy bandwidth), `cpu_baseline` (the NumPy oracle port timed on the host cores on
@@ -53,6 +55,10 @@ def parse():
     ap.add_argument("--model", default="icub_like")
     ap.add_argument("--lanes", type=int, default=0, help="lanes per env (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
+    ap.add_argument("--no-tma", action="store_true", help="128-bit stores instead of TMA bulk stores for the joint adjoints")
+    ap.add_argument("--profile", action="store_true", help="cudaProfilerStart/Stop around the eager timed region (ncu --profile-from-start off)")
+    ap.add_argument("--rollout", type=int, default=0, help="also time step_n with this many fused steps per launch")
     ap.add_argument("--sweep", action="store_true", help="also time batch 16384 and 65536 on this GPU")
     return ap.parse_args()
 
@@ -219,6 +225,8 @@ def run_b200(args):
     model = js.model.JaxSimModel.build_from_model_description(models.urdf(args.model), time_step=1e-3)
     if args.lanes:
         model.set_tuning(lanes_per_env=args.lanes)
+    if args.no_tma:
+        model.set_options(tma_store=False)
     n, nL, nc = model.dofs(), model.number_of_links(), model.number_of_collidable_points()
     B = args.batch
     bytes_env = algorithmic_bytes_per_env(n, nL, nc, w, caches=True)
@@ -228,47 +236,72 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def time_steps(Bq, K, W):
-        """K device-resident steps over a ring of state sets larger than L2."""
+    def time_steps(Bq, K, W, use_graph=True):
+        """K device-resident steps over a ring of state sets larger than L2.  Returns
+        (ms of the K steps launched eagerly, ms of the same K steps replayed from a CUDA
+        graph or None, ring, last output)."""
         ring = max(2, int(np.ceil(2 * L2_BYTES / (Bq * bytes_env))))
         ring = min(ring, 64)
         datas = [js.data.random_model_data(model, batch_size=Bq, seed=1000 * rank + r, dtype=dtype, device=dev,
                                            velocity_representation=js.common.VelRepr.Inertial) for r in range(ring)]
         taus = [10 * torch.rand(Bq, n, dtype=dtype, device=dev) for _ in range(ring)]
-        for i in range(W):
-            js.model.step(model, datas[i % ring], joint_force_references=taus[i % ring])
+        # preallocated outputs (`out=`): the step then performs no allocation and is capturable
+        outs = [js.model.step(model, datas[r], joint_force_references=taus[r]) for r in range(ring)]
+
+        def run(count):
+            o = None
+            for i in range(count):
+                o = js.model.step(model, datas[i % ring], joint_force_references=taus[i % ring], out=outs[i % ring])
+            return o
+
+        run(W)
         barrier()
+        if args.profile:
+            torch.cuda.profiler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        out = None
-        for i in range(K):
-            out = js.model.step(model, datas[i % ring], joint_force_references=taus[i % ring])
+        out = run(K)
         e1.record()
         barrier()
-        ms = e0.elapsed_time(e1)
-        return ms, ring, out
+        if args.profile:
+            torch.cuda.profiler.stop()
+        ms_eager = e0.elapsed_time(e1)
+        ms_graph = None
+        if use_graph:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                run(K)
+            g.replay()
+            barrier()
+            e0.record()
+            g.replay()
+            e1.record()
+            barrier()
+            ms_graph = e0.elapsed_time(e1)
+        return ms_eager, ms_graph, ring, out
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
     t0 = time.time()
-    ms, ring, out = time_steps(B, args.steps, max(3, args.warmup))
+    ms_eager, ms_graph, ring, out = time_steps(B, args.steps, max(3, args.warmup), use_graph=not args.no_graph)
+    ms = ms_graph if ms_graph is not None else ms_eager
     t1 = time.time()
     clocks = sampler.stop(t0, t1) if rank == 0 else None
 
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, ms_eager], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    ms_max, ms_eager_max = float(t[0].item()), float(t[1].item())
     value = B * world * args.steps / (ms_max * 1e-3)
 
     # ---- state readback across ranks (config 4: NCCL all_gather only at readback)
     gather_ms = None
     if world > 1:
-        leaves = torch.cat([out._joint_positions, out._joint_velocities, out._base_quaternion, out._base_linear_velocity,
-                            out._base_angular_velocity, out._base_position,
-                            out.contact_state["tangential_deformation"].reshape(B, -1)], dim=-1).contiguous()
+        from jaxsim_b200.distributed import pack_state
+
+        leaves = pack_state(out)
         full = torch.empty(world * B, leaves.shape[1], dtype=dtype, device=dev)
         dist.all_gather_into_tensor(full, leaves)
         barrier()
@@ -326,9 +359,34 @@ def run_b200(args):
     if args.sweep and world == 1:
         sweep = []
         for Bq in (4096, 16384, 65536):
-            msq, rq, _ = time_steps(Bq, max(20, args.steps // 4), 3)
             Kq = max(20, args.steps // 4)
+            mse, msg, rq, _ = time_steps(Bq, Kq, 3, use_graph=not args.no_graph)
+            msq = msg if msg is not None else mse
             sweep.append({"batch": Bq, "value": Bq * Kq / (msq * 1e-3), "ms_per_step": msq / Kq, "ring": rq})
+
+    rollout = None
+    if args.rollout > 0:
+        Tn = args.rollout
+        d0 = js.data.random_model_data(model, batch_size=B, seed=55 + rank, dtype=dtype, device=dev,
+                                       velocity_representation=js.common.VelRepr.Inertial)
+        tau_T = 10 * torch.rand(Tn, B, n, dtype=dtype, device=dev)
+        o = js.model.step_n(model, d0, Tn, joint_force_references=tau_T, update_caches=False)
+        for _ in range(3):
+            js.model.step_n(model, d0, Tn, joint_force_references=tau_T, update_caches=False, out=o)
+        barrier()
+        reps = 5
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            js.model.step_n(model, d0, Tn, joint_force_references=tau_T, update_caches=False, out=o)
+        e1.record()
+        barrier()
+        tr = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+        rollout = {"steps_per_launch": Tn, "value": B * world * Tn * reps / (float(tr.item()) * 1e-3), "unit": UNIT,
+                   "ms_per_step": float(tr.item()) / (reps * Tn),
+                   "note": "step_n: state kept on chip, per-step HBM traffic = joint force references only; no caches written"}
 
     if rank != 0:
         if world > 1:
@@ -364,7 +422,8 @@ def run_b200(args):
                    "batch_per_gpu": B, "global_batch": B * world, "dt": 1e-3, "contact_model": "soft",
                    "integrator": "semi_implicit_euler", "parallelism": f"env-parallel x{world} (no data-path collective)",
                    "l2": f"inputs larger than L2: ring of {ring} independent state sets ({ring * B * bytes_env / 2**20:.0f} MiB)",
-                   "launch": geo, "caches_written": True},
+                   "launch": geo, "caches_written": True, "cuda_graph": ms_graph is not None,
+                   "joint_adjoint_store": "128-bit STG" if args.no_tma else "TMA cp.async.bulk"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "bytes_per_env_step": bytes_env, "peak_source": peak_src,
                      "note": "algorithmic bytes = B_api (SURVEY.md 8d): read state+contact state+tau, write state+contact state+all caches"},
@@ -372,12 +431,16 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                 "note": "public API js.model.step with pinned host buffers: H2D(state, contact state, tau) + step + D2H(new state, contact state) each step; caches stay on device"},
         "gpu_launches": args.steps,
+        "eager": {"value": B * world * args.steps / (ms_eager_max * 1e-3), "ms_per_step": ms_eager_max / args.steps,
+                  "note": "same K steps launched one by one from Python (host launch latency included)"},
         "clocks": clocks,
     }
     if gather_ms is not None:
         line["readback_allgather_ms"] = gather_ms
     if sweep is not None:
         line["sweep"] = sweep
+    if rollout is not None:
+        line["rollout"] = rollout
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -101,6 +101,12 @@ int b200sim_model_update_link_params(B200SimModel *model, const double *link_mas
  * thread block.  Only affects performance, never results. */
 int b200sim_model_set_tuning(B200SimModel *model, int lanes_per_env, int envs_per_block);
 
+/* Implementation options (bit mask; never change results).  Default: B200SIM_OPT_TMA_STORE.
+ *   B200SIM_OPT_TMA_STORE: the (B,nL,6,6) joint-transform cache leaves shared memory through
+ *   the TMA engine (cp.async.bulk) instead of 128-bit stores from registers. */
+#define B200SIM_OPT_TMA_STORE 1
+int b200sim_model_set_options(B200SimModel *model, int32_t options);
+
 /* Query sizes / launch geometry chosen for a batch (for benchmarks and tests). */
 int b200sim_model_query(const B200SimModel *model, int dtype, int64_t B, int32_t *lanes_per_env,
                         int32_t *envs_per_block, int32_t *grid, int32_t *smem_bytes);
@@ -129,6 +135,23 @@ int b200sim_step(const B200SimModel *model, int dtype, int64_t B,
                  void *m_tan_o,
                  void *W_H_B, void *i_X_lam, void *W_H_L, void *W_v_WL,
                  void *stream);
+
+/* `nsteps` consecutive steps in ONE launch (the caller's `for _ in range(T): data =
+ * step(model, data, ...)` loop, README.md:80-84): the state stays on chip between steps,
+ * only the joint force references are read per step.  tau_ref is (nsteps,B,n) with
+ * `tau_step_stride` elements between consecutive steps (0: the same (B,n) block every
+ * step); likewise f_ext with `fext_step_stride`.  Outputs are those of the LAST step.
+ * b200sim_step == b200sim_step_n with nsteps = 1.  All cache output pointers must be
+ * 16-byte aligned. */
+int b200sim_step_n(const B200SimModel *model, int dtype, int64_t B, int32_t nsteps,
+                   const void *s, const void *sd, const void *q_wxyz, const void *v_lin,
+                   const void *omega, const void *p, const void *m_tan,
+                   const void *tau_ref, int64_t tau_step_stride,
+                   const void *f_ext, int64_t fext_step_stride,
+                   void *s_o, void *sd_o, void *q_o, void *v_lin_o, void *omega_o, void *p_o,
+                   void *m_tan_o,
+                   void *W_H_B, void *i_X_lam, void *W_H_L, void *W_v_WL,
+                   void *stream);
 
 /* Cache computation only (JaxSimModelData.build / .replace, api/data.py:66-202,406-523):
  * normalises q (written to q_o if not NULL) and fills the requested caches. */

@@ -60,14 +60,17 @@ class B200SimModelDesc(C.Structure):
 
 
 ABI_VERSION = 1
+OPT_TMA_STORE = 1
 EXPORTED_SYMBOLS = (
     "b200sim_version",
     "b200sim_model_create",
     "b200sim_model_destroy",
     "b200sim_model_update_link_params",
     "b200sim_model_set_tuning",
+    "b200sim_model_set_options",
     "b200sim_model_query",
     "b200sim_step",
+    "b200sim_step_n",
     "b200sim_fk",
     "b200sim_aba",
 )
@@ -98,6 +101,12 @@ def load() -> C.CDLL:
     lib.b200sim_model_set_tuning.restype = C.c_int
     lib.b200sim_model_query.argtypes = [vp, C.c_int, C.c_int64, c_ip, c_ip, c_ip, c_ip]
     lib.b200sim_model_query.restype = C.c_int
+    lib.b200sim_model_set_options.argtypes = [vp, C.c_int32]
+    lib.b200sim_model_set_options.restype = C.c_int
+    lib.b200sim_step_n.argtypes = (
+        [vp, C.c_int, C.c_int64, C.c_int32] + [vp] * 8 + [C.c_int64, vp, C.c_int64] + [vp] * 12
+    )
+    lib.b200sim_step_n.restype = C.c_int
     lib.b200sim_step.argtypes = [vp, C.c_int, C.c_int64] + [vp] * 21
     lib.b200sim_step.restype = C.c_int
     lib.b200sim_fk.argtypes = [vp, C.c_int, C.c_int64] + [vp] * 12

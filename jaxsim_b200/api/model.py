@@ -13,9 +13,11 @@ calling these functions without the CUDA library or with CPU tensors raises.
 
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import dataclasses
 import enum
+import math
 import pathlib
 import weakref
 
@@ -33,6 +35,7 @@ from .common import VelRepr, other_representation_to_inertial
 from .kin_dyn_parameters import KinDynParameters
 
 STANDARD_GRAVITY = 9.81  # src/jaxsim/math/__init__.py:14
+_NULLCTX = contextlib.nullcontext()
 
 
 class IntegratorType(enum.IntEnum):
@@ -123,6 +126,7 @@ class JaxSimModel:
     _floating_base: bool = True
     _devices: dict = dataclasses.field(default_factory=dict, repr=False)
     _tuning: tuple = (0, 0)
+    _options: int | None = None
 
     # ------------------------------------------------------------------ builders
     @classmethod
@@ -232,6 +236,8 @@ class JaxSimModel:
             dm = _DeviceModel(self, idx)
             if self._tuning != (0, 0):
                 _lib.check(_lib.load().b200sim_model_set_tuning(dm.handle, *self._tuning), "set_tuning")
+            if self._options is not None:
+                _lib.check(_lib.load().b200sim_model_set_options(dm.handle, self._options), "set_options")
             self._devices[idx] = dm
         return dm
 
@@ -240,6 +246,12 @@ class JaxSimModel:
         self._tuning = (int(lanes_per_env), int(envs_per_block))
         for dm in self._devices.values():
             _lib.check(_lib.load().b200sim_model_set_tuning(dm.handle, *self._tuning), "set_tuning")
+
+    def set_options(self, tma_store: bool = True) -> None:
+        """Implementation switches (never change results): ``b200sim_model_set_options``."""
+        self._options = _lib.OPT_TMA_STORE if tma_store else 0
+        for dm in self._devices.values():
+            _lib.check(_lib.load().b200sim_model_set_options(dm.handle, self._options), "set_options")
 
     def launch_geometry(self, batch: int, dtype: torch.dtype, device: torch.device) -> dict:
         dm = self.device_model(device)
@@ -276,30 +288,27 @@ def _batched(t: torch.Tensor, unbatched_ndim: int) -> torch.Tensor:
 # =============================================================================
 
 
-def step(
-    model: JaxSimModel,
-    data: "_data.JaxSimModelData",
-    *,
-    link_forces: torch.Tensor | None = None,
-    joint_force_references: torch.Tensor | None = None,
-    update_caches: bool = True,
-) -> "_data.JaxSimModelData":
-    """Perform a simulation step: drop-in for ``jaxsim.api.model.step``
-    (``src/jaxsim/api/model.py:2601-2681``), batched over the leading axis of ``data``.
+def _alloc_outputs(model, B, dtype, dev, update_caches, soft):
+    """One allocation for all the outputs of a step, carved into the leaves."""
+    nL, n, nc = model.number_of_links(), model.dofs(), model.number_of_collidable_points()
+    # every block is a multiple of 4 elements so that each leaf stays 16-byte aligned
+    r4 = lambda k: (k + 3) & ~3  # noqa: E731
+    sizes = [("s", (B, n)), ("sd", (B, n)), ("q", (B, 4)), ("vl", (B, 3)), ("om", (B, 3)), ("p", (B, 3))]
+    if soft:
+        sizes.append(("m", (B, nc, 3)))
+    if update_caches:
+        sizes += [("W_H_B", (B, 4, 4)), ("iXl", (B, nL, 6, 6)), ("W_H_L", (B, nL, 4, 4)), ("W_v", (B, nL, 6))]
+    total = sum(r4(math.prod(shape)) for _, shape in sizes)
+    flat = torch.empty(total, dtype=dtype, device=dev)
+    out, o = {}, 0
+    for name, shape in sizes:
+        k = math.prod(shape)
+        out[name] = flat[o : o + k].view(shape)
+        o += r4(k)
+    return out
 
-    Args:
-        model: the model.
-        data: the (batched) state.
-        link_forces: 6D forces on the links, ``(B, nL, 6)`` (or ``(nL, 6)``), expressed in
-            ``data.velocity_representation`` like in the reference (``:2617-2618``).
-        joint_force_references: ``(B, n)`` joint force references.
-        update_caches: if False, the cached transforms of the returned data are not
-            materialised (rollout mode, "B_min" of SURVEY.md 8d); accessing them raises.
 
-    Returns:
-        The new ``JaxSimModelData`` (same velocity representation, new tensors: the input
-        is not modified, like the reference's immutable pytrees).
-    """
+def _step_impl(model, data, n_steps, link_forces, joint_force_references, update_caches, out):
     s = data._joint_positions
     unbatched = s.dim() == 1
     dev = s.device
@@ -327,53 +336,136 @@ def step(
         if m.shape != (B, nc, 3):
             raise ValueError(m.shape, (B, nc, 3))
 
-    tau = None
+    tau, tau_stride = None, 0
     if joint_force_references is not None:
-        tau = _batched(torch.as_tensor(joint_force_references, dtype=dtype, device=dev), 1).contiguous()
-        if tau.shape != (B, n):
-            raise ValueError(tau.shape, (B, n))
+        tau = torch.as_tensor(joint_force_references, dtype=dtype, device=dev)
+        if tau.dim() == 3:  # (T, B, n): one row of references per step
+            if tau.shape != (n_steps, B, n):
+                raise ValueError(tau.shape, (n_steps, B, n))
+            tau_stride = B * n
+        else:
+            tau = _batched(tau, 1)
+            if tau.shape != (B, n):
+                raise ValueError(tau.shape, (B, n))
+        tau = tau.contiguous()
 
-    fext = None
+    fext, fext_stride = None, 0
     if link_forces is not None:
-        O_f = _batched(torch.as_tensor(link_forces, dtype=dtype, device=dev), 2)
-        if O_f.shape != (B, nL, 6):
+        O_f = torch.as_tensor(link_forces, dtype=dtype, device=dev)
+        per_step = O_f.dim() == 4
+        O_f = O_f if per_step else _batched(O_f, 2)
+        if O_f.shape[-3:] != (B, nL, 6) or (per_step and O_f.shape[0] != n_steps):
             raise ValueError(O_f.shape, (B, nL, 6))
-        # api/model.py:2641-2646: expressed in data.velocity_representation -> inertial-fixed
-        fext = other_representation_to_inertial(
-            O_f, data.velocity_representation, _batched(data.link_transforms, 3), is_force=True
-        ).contiguous()
+        if data.velocity_representation != VelRepr.Inertial:
+            if per_step and n_steps > 1:
+                raise NotImplementedError("per-step link_forces of a multi-step launch must be in VelRepr.Inertial")
+            # api/model.py:2641-2646: expressed in data.velocity_representation -> inertial-fixed
+            O_f = other_representation_to_inertial(
+                O_f, data.velocity_representation, _batched(data.link_transforms, 3), is_force=True
+            )
+        fext = O_f.contiguous()
+        fext_stride = B * nL * 6 if per_step else 0
 
-    new = lambda *shape: torch.empty(shape, dtype=dtype, device=dev)  # noqa: E731
-    s_o, sd_o, q_o, vl_o, om_o, p_o = new(B, n), new(B, n), new(B, 4), new(B, 3), new(B, 3), new(B, 3)
     soft = isinstance(model.contact_model, SoftContacts)
-    m_o = new(B, nc, 3) if soft else None
-    if soft and m is None:
-        m = torch.zeros(B, nc, 3, dtype=dtype, device=dev)
-    if update_caches:
-        W_H_B, iXl, W_H_L, W_v = new(B, 4, 4), new(B, nL, 6, 6), new(B, nL, 4, 4), new(B, nL, 6)
+    if out is None:
+        o = _alloc_outputs(model, B, dtype, dev, update_caches, soft)
     else:
-        W_H_B = iXl = W_H_L = W_v = None
+        # reuse the buffers of an existing (batched) data object: no allocation at all
+        o = {"s": out._joint_positions, "sd": out._joint_velocities, "q": out._base_quaternion,
+             "vl": out._base_linear_velocity, "om": out._base_angular_velocity, "p": out._base_position}
+        if soft:
+            o["m"] = out.contact_state["tangential_deformation"]
+        if update_caches:
+            o.update(W_H_B=out._base_transform, iXl=out._joint_transforms, W_H_L=out._link_transforms,
+                     W_v=out._link_velocities)
+        if o["q"].shape != (B, 4) or o["q"].dtype != dtype or o["q"].device != dev:
+            raise ValueError("`out` does not match the batch/dtype/device of `data`")
+        if any(v is None or not v.is_contiguous() for v in o.values()):
+            raise ValueError("`out` must hold contiguous buffers for every requested leaf")
 
-    with torch.cuda.device(dev):
-        rc = _lib.load().b200sim_step(
-            dm.handle, code, B,
-            _ptr(s), _ptr(sd), _ptr(q), _ptr(vl), _ptr(om), _ptr(p), _ptr(m), _ptr(tau), _ptr(fext),
-            _ptr(s_o), _ptr(sd_o), _ptr(q_o), _ptr(vl_o), _ptr(om_o), _ptr(p_o), _ptr(m_o),
-            _ptr(W_H_B), _ptr(iXl), _ptr(W_H_L), _ptr(W_v), _stream_ptr(dev),
+    g = o.get
+    if torch.cuda.current_device() != dm.device_index:
+        ctx = torch.cuda.device(dev)
+    else:
+        ctx = _NULLCTX
+    with ctx:
+        rc = _lib.load().b200sim_step_n(
+            dm.handle, code, B, int(n_steps),
+            _ptr(s), _ptr(sd), _ptr(q), _ptr(vl), _ptr(om), _ptr(p), _ptr(m), _ptr(tau), tau_stride,
+            _ptr(fext), fext_stride,
+            _ptr(o["s"]), _ptr(o["sd"]), _ptr(o["q"]), _ptr(o["vl"]), _ptr(o["om"]), _ptr(o["p"]), _ptr(g("m")),
+            _ptr(g("W_H_B")), _ptr(g("iXl")), _ptr(g("W_H_L")), _ptr(g("W_v")), _stream_ptr(dev),
         )
-    _lib.check(rc, "b200sim_step")
+    _lib.check(rc, "b200sim_step_n")
 
+    if out is not None:
+        out.velocity_representation = data.velocity_representation
+        if not update_caches:
+            out._base_transform = out._joint_transforms = out._link_transforms = out._link_velocities = None
+        return out
     sq = (lambda t: t.squeeze(0) if t is not None else None) if unbatched else (lambda t: t)
     contact_state = dict(data.contact_state) if data.contact_state else {}
     if soft:
-        contact_state["tangential_deformation"] = sq(m_o)
+        contact_state["tangential_deformation"] = sq(o["m"])
     return _data.JaxSimModelData(
         velocity_representation=data.velocity_representation,
-        _joint_positions=sq(s_o), _joint_velocities=sq(sd_o), _base_quaternion=sq(q_o),
-        _base_linear_velocity=sq(vl_o), _base_angular_velocity=sq(om_o), _base_position=sq(p_o),
-        _base_transform=sq(W_H_B), _joint_transforms=sq(iXl), _link_transforms=sq(W_H_L),
-        _link_velocities=sq(W_v), contact_state=contact_state,
+        _joint_positions=sq(o["s"]), _joint_velocities=sq(o["sd"]), _base_quaternion=sq(o["q"]),
+        _base_linear_velocity=sq(o["vl"]), _base_angular_velocity=sq(o["om"]), _base_position=sq(o["p"]),
+        _base_transform=sq(g("W_H_B")), _joint_transforms=sq(g("iXl")), _link_transforms=sq(g("W_H_L")),
+        _link_velocities=sq(g("W_v")), contact_state=contact_state,
     )
+
+
+def step(
+    model: JaxSimModel,
+    data: "_data.JaxSimModelData",
+    *,
+    link_forces: torch.Tensor | None = None,
+    joint_force_references: torch.Tensor | None = None,
+    update_caches: bool = True,
+    out: "_data.JaxSimModelData | None" = None,
+) -> "_data.JaxSimModelData":
+    """Perform a simulation step: drop-in for ``jaxsim.api.model.step``
+    (``src/jaxsim/api/model.py:2601-2681``), batched over the leading axis of ``data``.
+
+    Args:
+        model: the model.
+        data: the (batched) state.
+        link_forces: 6D forces on the links, ``(B, nL, 6)`` (or ``(nL, 6)``), expressed in
+            ``data.velocity_representation`` like in the reference (``:2617-2618``).
+        joint_force_references: ``(B, n)`` joint force references.
+        update_caches: if False, the cached transforms of the returned data are not
+            materialised (rollout mode, "B_min" of SURVEY.md 8d); accessing them raises.
+        out: optional data object whose buffers receive the result (like NumPy's ``out=``);
+            avoids every allocation and makes the call CUDA-graph capturable.  ``out`` may
+            be ``data`` itself (in-place step).
+
+    Returns:
+        The new ``JaxSimModelData`` (same velocity representation; new tensors unless
+        ``out`` is given: the input is not modified, like the reference's immutable pytrees).
+    """
+    return _step_impl(model, data, 1, link_forces, joint_force_references, update_caches, out)
+
+
+def step_n(
+    model: JaxSimModel,
+    data: "_data.JaxSimModelData",
+    n_steps: int,
+    *,
+    link_forces: torch.Tensor | None = None,
+    joint_force_references: torch.Tensor | None = None,
+    update_caches: bool = True,
+    out: "_data.JaxSimModelData | None" = None,
+) -> "_data.JaxSimModelData":
+    """``n_steps`` consecutive ``step`` calls fused in ONE kernel launch -- the user loop
+    ``for _ in range(T): data = js.model.step(model, data, ...)`` (``README.md:80-84``) with the
+    state kept on chip between steps.  ``joint_force_references`` is
+    ``(B, n)`` (held constant) or ``(n_steps, B, n)``; ``link_forces`` likewise
+    ``(B, nL, 6)`` or ``(n_steps, B, nL, 6)``.  Returns the data after the last step;
+    results are identical to calling ``step`` ``n_steps`` times."""
+    if n_steps < 1:
+        raise ValueError(n_steps)
+    return _step_impl(model, data, int(n_steps), link_forces, joint_force_references, update_caches, out)
 
 
 def forward_dynamics_aba(

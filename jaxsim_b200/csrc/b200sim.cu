@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstdint>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -40,11 +41,12 @@ struct B200SimModel {
   int* itab_d = nullptr;
   // tuning
   int tune_G = 0, tune_epb = 0;
+  int opt_flags = B200SIM_OPT_TMA_STORE;
 };
 
 namespace {
 
-constexpr int kMaxThreads = 512;
+inline int max_threads_for(int G) { return G <= 8 ? 288 : 512; }  // == LaunchBounds<G>::kThreads
 
 #define CK(x)                         \
   do {                                \
@@ -119,7 +121,7 @@ int pick_geometry(const B200SimModel* m, int dtype, long long B, Geometry* g) {
   }
   const int wg = 32 / G;  // groups per warp
   long long epb_smem = (long long)((budget - st) / pe);
-  long long epb_thr = kMaxThreads / G;
+  long long epb_thr = max_threads_for(G) / G;
   long long epb = std::min(epb_smem, epb_thr);
   if (m->tune_epb > 0) epb = std::min<long long>(epb, m->tune_epb);
   // spread a small batch over all SMs
@@ -168,7 +170,7 @@ void fill_model_params(const B200SimModel* m, Params<T>& P) {
   P.itab_words = (int)m->itab_h.size();
   P.nL = m->nL; P.n = m->n; P.nc = m->nc; P.depth = m->depth;
   P.floating = m->floating; P.contact_model = m->contact_model; P.enable_friction = m->enable_friction;
-  P.flags = m->flags;
+  P.flags = m->flags | ((m->opt_flags & B200SIM_OPT_TMA_STORE) ? F_TMA_STORE : 0);
   P.o_parent = m->o_parent; P.o_jtype = m->o_jtype; P.o_lvl_start = m->o_lvl_start; P.o_lvl_links = m->o_lvl_links;
   P.o_child_start = m->o_child_start; P.o_child_idx = m->o_child_idx; P.o_pt_start = m->o_pt_start;
   P.o_pt_idx = m->o_pt_idx; P.o_pt_body = m->o_pt_body; P.o_pt_enabled = m->o_pt_enabled;
@@ -212,7 +214,7 @@ template <typename T>
 int step_t(const B200SimModel* m, int dtype, int64_t B, const void* s, const void* sd, const void* q,
            const void* vlin, const void* omega, const void* p, const void* mt, const void* tau, const void* fext,
            void* s_o, void* sd_o, void* q_o, void* vlin_o, void* omega_o, void* p_o, void* m_o, void* W_H_B,
-           void* iXl, void* W_H_L, void* W_v, void* stream) {
+           void* iXl, void* W_H_L, void* W_v, int nsteps, long long tau_stride, long long fext_stride, void* stream) {
   Params<T> P;
   std::memset(&P, 0, sizeof(P));
   fill_model_params(m, P);
@@ -222,6 +224,7 @@ int step_t(const B200SimModel* m, int dtype, int64_t B, const void* s, const voi
   P.s_o = (T*)s_o; P.sd_o = (T*)sd_o; P.q_o = (T*)q_o; P.vlin_o = (T*)vlin_o; P.omega_o = (T*)omega_o;
   P.p_o = (T*)p_o; P.m_o = (T*)m_o;
   P.W_H_B = (T*)W_H_B; P.iXl = (T*)iXl; P.W_H_L = (T*)W_H_L; P.W_v = (T*)W_v;
+  P.nsteps = nsteps; P.tau_step_stride = tau_stride; P.fext_step_stride = fext_stride;
   P.mode = MODE_STEP;
   return launch(m, P, dtype, stream);
 }
@@ -237,6 +240,7 @@ int fk_t(const B200SimModel* m, int dtype, int64_t B, const void* s, const void*
   P.p = (const T*)p;
   P.q_o = (T*)q_o;
   P.W_H_B = (T*)W_H_B; P.iXl = (T*)iXl; P.W_H_L = (T*)W_H_L; P.W_v = (T*)W_v;
+  P.nsteps = 1;
   P.mode = MODE_FK;
   return launch(m, P, dtype, stream);
 }
@@ -251,6 +255,7 @@ int aba_t(const B200SimModel* m, int dtype, int64_t B, const void* s, const void
   P.s = (const T*)s; P.sd = (const T*)sd; P.q = (const T*)q; P.vlin = (const T*)vlin; P.omega = (const T*)omega;
   P.p = (const T*)p; P.tau = (const T*)tau; P.fext = (const T*)fext;
   P.avd = (T*)avd; P.sdd_o = (T*)sdd;
+  P.nsteps = 1;
   P.mode = MODE_ABA;
   return launch(m, P, dtype, stream);
 }
@@ -301,16 +306,38 @@ int b200sim_model_create(const B200SimModelDesc* d, int device, B200SimModel** o
     double* c = m->cst_h.data() + (size_t)i * CREC;
     const double* H = d->lam_H_pre + 16 * (size_t)i;
     const double* Hs = d->suc_H_i + 16 * (size_t)i;
+    double Rpre[9], ax[3];
     for (int r = 0; r < 3; ++r) {
       for (int cc = 0; cc < 3; ++cc) {
-        c[C_RPRE + 3 * r + cc] = H[4 * r + cc];
+        Rpre[3 * r + cc] = H[4 * r + cc];
         m->csuc_h[(size_t)i * 12 + 3 * r + cc] = Hs[4 * r + cc];
       }
       c[C_TPRE + r] = H[4 * r + 3];
       m->csuc_h[(size_t)i * 12 + 9 + r] = Hs[4 * r + 3];
+      ax[r] = d->joint_axis[3 * (size_t)i + r];
+      c[C_AXIS + r] = ax[r];
+    }
+    // R_rel(s) = Rpre (cos I + sin S(a) + (1 - cos) a a^T) = M0 + cos M1 + sin M2
+    const double Sa[9] = {0, -ax[2], ax[1], ax[2], 0, -ax[0], -ax[1], ax[0], 0};
+    for (int r = 0; r < 3; ++r) {
+      for (int cc = 0; cc < 3; ++cc) {
+        double raa = 0, rsa = 0;
+        for (int k = 0; k < 3; ++k) { raa += Rpre[3 * r + k] * ax[k] * ax[cc]; rsa += Rpre[3 * r + k] * Sa[3 * k + cc]; }
+        if (i >= 1 && d->joint_type[i] == 1) {
+          c[C_M0 + 3 * r + cc] = raa;
+          c[C_M1 + 3 * r + cc] = Rpre[3 * r + cc] - raa;
+          c[C_M2 + 3 * r + cc] = rsa;
+        } else {
+          c[C_M0 + 3 * r + cc] = Rpre[3 * r + cc];
+          c[C_M1 + 3 * r + cc] = 0.0;
+          c[C_M2 + 3 * r + cc] = 0.0;
+        }
+      }
+      double ra = 0;
+      for (int k = 0; k < 3; ++k) ra += Rpre[3 * r + k] * ax[k];
+      c[C_RA + r] = (i >= 1 && d->joint_type[i] == 2) ? ra : 0.0;
     }
     if (i >= 1 && !is_identity4(Hs)) suc_nonid = true;
-    for (int r = 0; r < 3; ++r) c[C_AXIS + r] = d->joint_axis[3 * (size_t)i + r];
     if (i >= 1) {
       const int j = i - 1;
       c[C_KS] = d->position_limit_spring[j];
@@ -439,6 +466,12 @@ int b200sim_model_set_tuning(B200SimModel* m, int lanes_per_env, int envs_per_bl
   return 0;
 }
 
+int b200sim_model_set_options(B200SimModel* m, int32_t options) {
+  if (!m || (options & ~B200SIM_OPT_TMA_STORE)) return B200SIM_E_INVALID;
+  m->opt_flags = options;
+  return 0;
+}
+
 int b200sim_model_query(const B200SimModel* m, int dtype, int64_t B, int32_t* G, int32_t* epb, int32_t* grid, int32_t* smem) {
   if (!m || B < 1 || (dtype != 0 && dtype != 1)) return B200SIM_E_INVALID;
   Geometry g;
@@ -451,19 +484,34 @@ int b200sim_model_query(const B200SimModel* m, int dtype, int64_t B, int32_t* G,
   return 0;
 }
 
+static bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+int b200sim_step_n(const B200SimModel* m, int dtype, int64_t B, int32_t nsteps, const void* s, const void* sd,
+                   const void* q, const void* vlin, const void* omega, const void* p, const void* mt, const void* tau,
+                   int64_t tau_step_stride, const void* fext, int64_t fext_step_stride, void* s_o, void* sd_o, void* q_o,
+                   void* vlin_o, void* omega_o, void* p_o, void* m_o, void* W_H_B, void* iXl, void* W_H_L, void* W_v,
+                   void* stream) {
+  if (!m || B < 0 || nsteps < 1 || (dtype != 0 && dtype != 1)) return B200SIM_E_INVALID;
+  if (tau_step_stride < 0 || fext_step_stride < 0) return B200SIM_E_INVALID;
+  if (B == 0) return 0;
+  if (!q || !vlin || !omega || !p || !q_o || !vlin_o || !omega_o || !p_o) return B200SIM_E_INVALID;
+  if (m->n > 0 && (!s || !sd || !s_o || !sd_o)) return B200SIM_E_INVALID;
+  // vector / TMA stores: the cache outputs must be 16-byte aligned (8 for float W_v rows)
+  if (!aligned(W_H_B, 16) || !aligned(iXl, 16) || !aligned(W_H_L, 16) || !aligned(W_v, dtype == 0 ? 8 : 16))
+    return B200SIM_E_INVALID;
+  if (dtype == 0)
+    return step_t<float>(m, dtype, B, s, sd, q, vlin, omega, p, mt, tau, fext, s_o, sd_o, q_o, vlin_o, omega_o, p_o, m_o,
+                         W_H_B, iXl, W_H_L, W_v, nsteps, tau_step_stride, fext_step_stride, stream);
+  return step_t<double>(m, dtype, B, s, sd, q, vlin, omega, p, mt, tau, fext, s_o, sd_o, q_o, vlin_o, omega_o, p_o, m_o,
+                        W_H_B, iXl, W_H_L, W_v, nsteps, tau_step_stride, fext_step_stride, stream);
+}
+
 int b200sim_step(const B200SimModel* m, int dtype, int64_t B, const void* s, const void* sd, const void* q,
                  const void* vlin, const void* omega, const void* p, const void* mt, const void* tau, const void* fext,
                  void* s_o, void* sd_o, void* q_o, void* vlin_o, void* omega_o, void* p_o, void* m_o, void* W_H_B,
                  void* iXl, void* W_H_L, void* W_v, void* stream) {
-  if (!m || B < 0 || (dtype != 0 && dtype != 1)) return B200SIM_E_INVALID;
-  if (B == 0) return 0;
-  if (!q || !vlin || !omega || !p || !q_o || !vlin_o || !omega_o || !p_o) return B200SIM_E_INVALID;
-  if (m->n > 0 && (!s || !sd || !s_o || !sd_o)) return B200SIM_E_INVALID;
-  if (dtype == 0)
-    return step_t<float>(m, dtype, B, s, sd, q, vlin, omega, p, mt, tau, fext, s_o, sd_o, q_o, vlin_o, omega_o, p_o, m_o,
-                         W_H_B, iXl, W_H_L, W_v, stream);
-  return step_t<double>(m, dtype, B, s, sd, q, vlin, omega, p, mt, tau, fext, s_o, sd_o, q_o, vlin_o, omega_o, p_o, m_o,
-                        W_H_B, iXl, W_H_L, W_v, stream);
+  return b200sim_step_n(m, dtype, B, 1, s, sd, q, vlin, omega, p, mt, tau, 0, fext, 0, s_o, sd_o, q_o, vlin_o, omega_o,
+                        p_o, m_o, W_H_B, iXl, W_H_L, W_v, stream);
 }
 
 int b200sim_fk(const B200SimModel* m, int dtype, int64_t B, const void* s, const void* sd, const void* q,
@@ -473,6 +521,8 @@ int b200sim_fk(const B200SimModel* m, int dtype, int64_t B, const void* s, const
   if (B == 0) return 0;
   if (!q || !vlin || !omega || !p) return B200SIM_E_INVALID;
   if (m->n > 0 && (!s || !sd)) return B200SIM_E_INVALID;
+  if (!aligned(W_H_B, 16) || !aligned(iXl, 16) || !aligned(W_H_L, 16) || !aligned(W_v, dtype == 0 ? 8 : 16))
+    return B200SIM_E_INVALID;
   if (dtype == 0) return fk_t<float>(m, dtype, B, s, sd, q, vlin, omega, p, q_o, W_H_B, iXl, W_H_L, W_v, stream);
   return fk_t<double>(m, dtype, B, s, sd, q, vlin, omega, p, q_o, W_H_B, iXl, W_H_L, W_v, stream);
 }

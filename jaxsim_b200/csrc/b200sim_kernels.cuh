@@ -1,17 +1,18 @@
 // b200sim_kernels.cuh -- fused batched rigid-body step kernel for sm_100a.
 //
 // One launch performs, for every environment, everything `jaxsim.api.model.step` does
-// (reference call stack: SURVEY.md section 3.1):
-//   joint transforms -> FK -> collidable points + Hunt/Crossley -> actuation -> ABA passes
-//   1/2/3 -> semi-implicit Euler -> joint transforms + FK of the new state -> caches.
+// (reference call stack: SURVEY.md section 3.1), optionally for several consecutive steps:
+//   joint transforms -> FK -> [ collidable points + Hunt/Crossley -> actuation -> ABA passes
+//   1/2/3 -> semi-implicit Euler -> joint transforms + FK of the new state ] x nsteps -> caches.
 //
 // Mapping:  G lanes of one warp cooperate on one environment (G in
 // {1,2,4,8,16,32}); the per-link state of the environment lives in a shared-memory record
-// (REC words per link) for the whole step; phases that are independent per link / per
+// (REC words per link) for the whole launch; phases that are independent per link / per
 // collidable point / per DoF stride over them with the G lanes; the sequential tree
 // recursions advance one tree LEVEL at a time with the lanes spread over the links of the
-// level, separated by __syncwarp().  No global-memory traffic between the first read of
-// the state and the final write of the new state + caches.
+// level, separated by __syncwarp().  Inputs are pulled from HBM with one burst of
+// cp.async (LDGSTS) per environment; the big cache output (the 6x6 joint adjoints) leaves
+// through the TMA engine (cp.async.bulk shared->global), the rest through 128-bit stores.
 //
 // Formulation: the reference runs ABA in body-fixed link coordinates with dense 6x6
 // adjoints (rbda/aba.py).  Here every link's spatial quantities are expressed in the frame
@@ -27,6 +28,7 @@
 // A, D symmetric stored as 6 (xx,xy,xz,yy,yz,zz), B full row-major 9.
 #pragma once
 
+#include <cuda_pipeline.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -36,40 +38,52 @@ namespace b200sim {
 // layouts
 // ------------------------------------------------------------------------------------
 constexpr int REC = 60;   // workspace words per link (60 = 4*15: conflict-free 128-bit rows)
-constexpr int CREC = 36;  // model-constant words per link (36 = 4*9)
+constexpr int CREC = 52;  // model-constant words per link (52 = 4*13)
 
-// workspace record offsets.  R/P are live until phase 3 overwrites them with IA/PA.
-constexpr int O_R = 0;     // 9  world rotation of the link (ABA chain)
-constexpr int O_P = 9;     // 3  world position of the link origin
-constexpr int O_IA = 0;    // 6  A (sym)
-constexpr int O_IB = 6;    // 9  B
-constexpr int O_ID = 15;   // 6  D (sym)
-constexpr int O_PA = 21;   // 6  articulated bias force
-constexpr int O_V = 28;    // 6  spatial velocity in F_i, later spatial acceleration
-constexpr int O_C = 34;    // 6  velocity-product term c_i
-constexpr int O_U = 40;    // 6  U_i
-constexpr int O_DINV = 46; // 1  1/d_i
-constexpr int O_UU = 47;   // 1  u_i
-constexpr int O_AX = 48;   // 3  joint axis in world axes
-constexpr int O_SDD = 51;  // 1  joint acceleration
-constexpr int O_RR = 52;   // 3  r_i = p_i - p_parent (world axes)
-constexpr int O_SD = 55;   // 1  joint velocity
-constexpr int O_TAU = 56;  // 1  resultant joint torque
-constexpr int PTREC = 6;   // per collidable point staging: force(3), lever arm(3)
+// workspace record.  Words 0..26 hold (R,p) while kinematics are needed and the
+// articulated inertia + bias force during ABA; words 12..47 double as the staging area of
+// the link's 6x6 joint adjoint when the caches are written.
+constexpr int O_R = 0;      // 9  world rotation of the link (ABA chain)
+constexpr int O_P = 9;      // 3  world position of the link origin
+constexpr int O_IA = 0;     // 6  A (sym)
+constexpr int O_IB = 6;     // 9  B
+constexpr int O_ID = 15;    // 6  D (sym)
+constexpr int O_PA = 21;    // 6  articulated bias force
+constexpr int O_C = 28;     // 6  velocity-product term c_i
+constexpr int O_U = 34;     // 6  U_i
+constexpr int O_DINV = 40;  // 1  1/d_i
+constexpr int O_UU = 41;    // 1  u_i
+constexpr int O_AX = 42;    // 3  joint axis in world axes
+constexpr int O_RR = 45;    // 3  r_i = p_i - p_parent (world axes)
+constexpr int O_X = 12;     // 36 staging of i_X_lambda(i) (output phase only)
+constexpr int O_V = 48;     // 6  spatial velocity in F_i, later spatial acceleration
+constexpr int O_SD = 54;    // 1  joint velocity
+constexpr int O_S = 55;     // 1  joint position
+constexpr int O_TAU = 56;   // 1  resultant joint torque
+constexpr int O_SDD = 57;   // 1  joint acceleration
+constexpr int O_TREF = 58;  // 1  joint force reference of the current step
+// per collidable point: contact force (3), lever arm (3), tangential deformation (3)
+constexpr int PTREC = 9;
+constexpr int PT_F = 0, PT_LEV = 3, PT_M = 6;
 
-// model constant record offsets
-constexpr int C_RPRE = 0;  // 9 rotation of lam_H_pre
-constexpr int C_TPRE = 9;  // 3 translation of lam_H_pre
-constexpr int C_AXIS = 12; // 3
-constexpr int C_MASS = 15; // 1
-constexpr int C_COM = 16;  // 3
-constexpr int C_DL = 19;   // 6 I_c + m S(c)S(c)^T in link axes (sym)
-constexpr int C_KS = 25;   // position_limit_spring
-constexpr int C_KD = 26;   // position_limit_damper
-constexpr int C_SMIN = 27;
-constexpr int C_SMAX = 28;
-constexpr int C_KC = 29;   // friction_static
-constexpr int C_KV = 30;   // friction_viscous
+// model constant record: R_rel(s) = M0 + cos(s) M1 + sin(s) M2, t_rel(s) = TPRE + s RA
+// (revolute: M0 = Rpre a a^T, M1 = Rpre - M0, M2 = Rpre S(a), RA = 0;
+//  prismatic: M0 = Rpre, M1 = M2 = 0, RA = Rpre a)
+constexpr int C_M0 = 0;     // 9
+constexpr int C_M1 = 9;     // 9
+constexpr int C_M2 = 18;    // 9
+constexpr int C_TPRE = 27;  // 3
+constexpr int C_RA = 30;    // 3
+constexpr int C_AXIS = 33;  // 3 joint axis in link coordinates (motion subspace)
+constexpr int C_MASS = 36;  // 1
+constexpr int C_COM = 37;   // 3
+constexpr int C_DL = 40;    // 6 I_c + m S(c)S(c)^T in link axes (sym)
+constexpr int C_KS = 46;    // position_limit_spring
+constexpr int C_KD = 47;    // position_limit_damper
+constexpr int C_SMIN = 48;
+constexpr int C_SMAX = 49;
+constexpr int C_KC = 50;    // friction_static
+constexpr int C_KV = 51;    // friction_viscous
 
 enum Mode : int { MODE_STEP = 0, MODE_FK = 1, MODE_ABA = 2 };
 enum Flags : int {
@@ -77,6 +91,7 @@ enum Flags : int {
   F_GENERIC_FK = 2,  // suc_H_i[0] != I or fixed base: FK poses differ from the ABA chain
   F_SQRT_P = 4,      // soft_p == 0.5
   F_SQRT_Q = 8,      // soft_q == 0.5
+  F_TMA_STORE = 16,  // joint adjoints leave through cp.async.bulk (TMA) instead of STG.128
 };
 
 template <typename T>
@@ -98,6 +113,9 @@ struct Params {
   T *s_o, *sd_o, *q_o, *vlin_o, *omega_o, *p_o, *m_o;
   T *W_H_B, *iXl, *W_H_L, *W_v;
   T *avd, *sdd_o;
+  long long tau_step_stride;   // elements between the torque rows of consecutive steps (0: constant)
+  long long fext_step_stride;  // same for the external link forces
+  int nsteps;
   int mode;
   int envs_per_block;
 };
@@ -165,10 +183,6 @@ __device__ __forceinline__ void sym3_vec(const T* S, const T* v, T* o) {
   o[1] = S[1] * v[0] + S[3] * v[1] + S[4] * v[2];
   o[2] = S[2] * v[0] + S[4] * v[1] + S[5] * v[2];
 }
-template <typename T>
-__device__ __forceinline__ void ld(const T* src, T* dst, int n) {
-  for (int k = 0; k < n; ++k) dst[k] = src[k];
-}
 template <int N, typename T>
 __device__ __forceinline__ void ldn(const T* src, T* dst) {
 #pragma unroll
@@ -179,6 +193,47 @@ __device__ __forceinline__ void stn(T* dst, const T* src) {
 #pragma unroll
   for (int k = 0; k < N; ++k) dst[k] = src[k];
 }
+
+// 16-byte vector stores to global memory (dst must be 16-byte aligned; N*sizeof(T) % 16 == 0)
+template <int N>
+__device__ __forceinline__ void stg_vec(float* dst, const float* src) {
+  static_assert(N % 4 == 0, "N");
+#pragma unroll
+  for (int k = 0; k < N; k += 4) *reinterpret_cast<float4*>(dst + k) = make_float4(src[k], src[k + 1], src[k + 2], src[k + 3]);
+}
+template <int N>
+__device__ __forceinline__ void stg_vec(double* dst, const double* src) {
+  static_assert(N % 2 == 0, "N");
+#pragma unroll
+  for (int k = 0; k < N; k += 2) *reinterpret_cast<double2*>(dst + k) = make_double2(src[k], src[k + 1]);
+}
+// 6-vector rows: (B,nL,6) rows are 24 B (float, 8-byte aligned) / 48 B (double, 16-byte aligned)
+__device__ __forceinline__ void stg_vec6(float* dst, const float* src) {
+#pragma unroll
+  for (int k = 0; k < 6; k += 2) *reinterpret_cast<float2*>(dst + k) = make_float2(src[k], src[k + 1]);
+}
+__device__ __forceinline__ void stg_vec6(double* dst, const double* src) {
+#pragma unroll
+  for (int k = 0; k < 6; k += 2) *reinterpret_cast<double2*>(dst + k) = make_double2(src[k], src[k + 1]);
+}
+
+// ---- async copies -------------------------------------------------------------------
+// one element global -> shared without a register round trip (LDGSTS)
+template <typename T>
+__device__ __forceinline__ void cp_async_elem(T* smem_dst, const T* gsrc) {
+  __pipeline_memcpy_async(smem_dst, gsrc, sizeof(T));
+}
+// TMA bulk store shared -> global (cp.async.bulk, SASS UBLKCP): bytes % 16 == 0, both
+// addresses 16-byte aligned.  The generic-proxy writes to shared memory must be fenced
+// before the async proxy reads them.
+__device__ __forceinline__ void tma_store_bulk(void* gdst, const void* smem_src, unsigned bytes) {
+  const unsigned saddr = static_cast<unsigned>(__cvta_generic_to_shared(smem_src));
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(saddr), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // jaxlie SO3(wxyz).as_matrix() (reference call sites rbda/aba.py:79-86)
 template <typename T>
@@ -230,17 +285,6 @@ __device__ __forceinline__ void solve6_spd_neg(T M[6][6], const T* b, T* x) {
   }
 }
 
-// ------------------------------------------------------------------------------------
-// shared-memory view
-// ------------------------------------------------------------------------------------
-template <typename T>
-struct Smem {
-  const T* cst;     // [nL*CREC]
-  const T* pt_pos;  // [nc*3]
-  const int* itab;
-  T* ws;            // this environment's workspace: nL*REC + nc*PTREC words
-};
-
 template <typename T>
 __host__ __device__ inline size_t env_ws_words(int nL, int nc) {
   size_t w = (size_t)nL * REC + (size_t)nc * PTREC;
@@ -248,62 +292,35 @@ __host__ __device__ inline size_t env_ws_words(int nL, int nc) {
 }
 
 // lam_H_i = lam_H_pre * J(s) * suc_H_i  (api/kin_dyn_parameters.py:396-451,
-// math/joint_model.py:146-200, math/rotation.py:58-84).  Returns rotation + translation.
+// math/joint_model.py:146-200, math/rotation.py:58-84) from the precomputed constant
+// matrices: R = M0 + cos(s) M1 + sin(s) M2, t = TPRE + s RA.
 template <typename T>
 __device__ __forceinline__ void joint_rel_transform(const Params<T>& P, const T* c, int jtype, int i, T s,
                                                     T* Rrel, T* trel) {
-  T Rpre[9], tpre[3], ax[3];
-  ldn<9>(c + C_RPRE, Rpre);
-  ldn<3>(c + C_TPRE, tpre);
-  ldn<3>(c + C_AXIS, ax);
-  T RJ[9];
-  T tJ[3] = {T(0), T(0), T(0)};
-  if (jtype == 1) {
-    T sn, cs;
-    sincos_t(s, &sn, &cs);
-    const T c1 = T(1) - cs;
-    // Rodrigues: c I + s S(a) + (1-c) a a^T
-    RJ[0] = cs + c1 * ax[0] * ax[0];
-    RJ[1] = c1 * ax[0] * ax[1] - sn * ax[2];
-    RJ[2] = c1 * ax[0] * ax[2] + sn * ax[1];
-    RJ[3] = c1 * ax[1] * ax[0] + sn * ax[2];
-    RJ[4] = cs + c1 * ax[1] * ax[1];
-    RJ[5] = c1 * ax[1] * ax[2] - sn * ax[0];
-    RJ[6] = c1 * ax[2] * ax[0] - sn * ax[1];
-    RJ[7] = c1 * ax[2] * ax[1] + sn * ax[0];
-    RJ[8] = cs + c1 * ax[2] * ax[2];
-    mat3_mul(Rpre, RJ, Rrel);
-  } else {
-    if (jtype == 2) { tJ[0] = s * ax[0]; tJ[1] = s * ax[1]; tJ[2] = s * ax[2]; }
+  T sn = T(0), cs = T(1);
+  if (jtype == 1) sincos_t(s, &sn, &cs);
 #pragma unroll
-    for (int k = 0; k < 9; ++k) { RJ[k] = (k % 4 == 0) ? T(1) : T(0); Rrel[k] = Rpre[k]; }
-  }
+  for (int k = 0; k < 9; ++k) Rrel[k] = c[C_M0 + k] + cs * c[C_M1 + k] + sn * c[C_M2 + k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) trel[k] = c[C_TPRE + k] + s * c[C_RA + k];
   if (P.flags & F_SUC_NONID) {
     const T* su = P.csuc + (size_t)i * 12;
     T Rs[9], ts[3], tmp[9], t2[3];
     ldn<9>(su, Rs);
     ldn<3>(su + 9, ts);
-    // t_rel = tpre + Rpre (tJ + RJ ts);  R_rel = Rpre RJ Rs
-    mat3_vec(RJ, ts, t2);
-    t2[0] += tJ[0]; t2[1] += tJ[1]; t2[2] += tJ[2];
-    mat3_vec(Rpre, t2, trel);
-    trel[0] += tpre[0]; trel[1] += tpre[1]; trel[2] += tpre[2];
+    mat3_vec(Rrel, ts, t2);  // (Rpre RJ) t_suc
+    trel[0] += t2[0]; trel[1] += t2[1]; trel[2] += t2[2];
     mat3_mul(Rrel, Rs, tmp);
     stn<9>(Rrel, tmp);
-  } else {
-    T t2[3];
-    mat3_vec(Rpre, tJ, t2);
-    trel[0] = tpre[0] + t2[0]; trel[1] = tpre[1] + t2[1]; trel[2] = tpre[2] + t2[2];
   }
 }
 
-// write the 6x6 adjoint of H^-1 for H = (R, t): [[R^T, S(p')R^T],[0, R^T]], p' = -R^T t
+// the 6x6 adjoint of H^-1 for H = (R, t): [[R^T, S(p')R^T],[0, R^T]], p' = -R^T t
 template <typename T>
-__device__ __forceinline__ void store_inverse_adjoint(T* out, const T* R, const T* t) {
+__device__ __forceinline__ void inverse_adjoint(T* X, const T* R, const T* t) {
   T pi[3];
   mat3T_vec(R, t, pi);
   pi[0] = -pi[0]; pi[1] = -pi[1]; pi[2] = -pi[2];
-  T X[36];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
 #pragma unroll
@@ -314,24 +331,20 @@ __device__ __forceinline__ void store_inverse_adjoint(T* out, const T* R, const 
       X[6 * (i + 3) + j] = T(0);
     }
   }
-  // S(p') R^T : row i = p' x (column... ) -> (S(p) M)(i,j) = (p x col_j(M))_i
+  // (S(p) M)(i,j) = (p x col_j(M))_i ; col_j(R^T) = row_j(R)
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
-    const T c0 = R[3 * j + 0], c1 = R[3 * j + 1], c2 = R[3 * j + 2];  // col_j(R^T) = row_j(R)
+    const T c0 = R[3 * j + 0], c1 = R[3 * j + 1], c2 = R[3 * j + 2];
     X[6 * 0 + 3 + j] = pi[1] * c2 - pi[2] * c1;
     X[6 * 1 + 3 + j] = pi[2] * c0 - pi[0] * c2;
     X[6 * 2 + 3 + j] = pi[0] * c1 - pi[1] * c0;
   }
-#pragma unroll
-  for (int k = 0; k < 36; ++k) out[k] = X[k];
 }
 
 template <typename T>
 __device__ __forceinline__ void store_transform(T* out, const T* R, const T* p) {
-  out[0] = R[0]; out[1] = R[1]; out[2] = R[2];  out[3] = p[0];
-  out[4] = R[3]; out[5] = R[4]; out[6] = R[5];  out[7] = p[1];
-  out[8] = R[6]; out[9] = R[7]; out[10] = R[8]; out[11] = p[2];
-  out[12] = T(0); out[13] = T(0); out[14] = T(0); out[15] = T(1);
+  const T H[16] = {R[0], R[1], R[2], p[0], R[3], R[4], R[5], p[1], R[6], R[7], R[8], p[2], T(0), T(0), T(0), T(1)};
+  stg_vec<16>(out, H);
 }
 
 // Base state of one environment, replicated in the registers of every lane of the group.
@@ -397,8 +410,7 @@ __device__ __forceinline__ void fk_view(const Params<T>& P, const BaseState<T>& 
   T Wv[3], d[3], dw[3], t[3];
   cross3(pa, va + 3, Wv);
   Wv[0] += va[0]; Wv[1] += va[1]; Wv[2] += va[2];
-  // chain root velocity (inertial-fixed): W_v_WB if floating else 0
-  const T f = P.floating ? T(1) : T(0);
+  const T f = P.floating ? T(1) : T(0);  // chain root velocity: W_v_WB if floating else 0
   d[0] = Wv[0] - f * b.vlin[0]; d[1] = Wv[1] - f * b.vlin[1]; d[2] = Wv[2] - f * b.vlin[2];
   dw[0] = va[3] - f * b.w[0]; dw[1] = va[4] - f * b.w[1]; dw[2] = va[5] - f * b.w[2];
   // X_T [d; dw] = [R_T d + p_T x (R_T dw); R_T dw]
@@ -409,16 +421,20 @@ __device__ __forceinline__ void fk_view(const Params<T>& P, const BaseState<T>& 
   T Fv[3];
   Fv[0] = b.vlin[0] + rd[0] + t[0]; Fv[1] = b.vlin[1] + rd[1] + t[1]; Fv[2] = b.vlin[2] + rd[2] + t[2];
   w[0] = b.w[0] + rw[0]; w[1] = b.w[1] + rw[1]; w[2] = b.w[2] + rw[2];
-  // mixed at p: vlin = Fv + w x p
-  cross3(w, p, t);
+  cross3(w, p, t);  // mixed at p: vlin = Fv + w x p
   vlin[0] = Fv[0] + t[0]; vlin[1] = Fv[1] + t[1]; vlin[2] = Fv[2] + t[2];
 }
+
+template <int G>
+struct LaunchBounds {
+  static constexpr int kThreads = (G <= 8) ? 288 : 512;
+};
 
 // ------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------
 template <typename T, int G>
-__global__ void __launch_bounds__(512, 1) step_kernel(const Params<T> P) {
+__global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(const Params<T> P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sm_cst = reinterpret_cast<T*>(smem_raw);
   const int nL = P.nL, n = P.n, nc = P.nc;
@@ -426,9 +442,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const Params<T> P) {
   const size_t pt_words = ((size_t)nc * 3 + 3) & ~size_t(3);
   int* sm_itab = reinterpret_cast<int*>(sm_pt + pt_words);
   const size_t itab_words = ((size_t)P.itab_words + 3) & ~size_t(3);
-  // workspace base: keep it 16-byte aligned for both float and double
-  unsigned char* wsb = reinterpret_cast<unsigned char*>(sm_itab + itab_words);
-  T* ws_base = reinterpret_cast<T*>(wsb);
+  T* ws_base = reinterpret_cast<T*>(sm_itab + itab_words);
 
   // ---- stage the model once per block
   for (int k = threadIdx.x; k < nL * CREC; k += blockDim.x) sm_cst[k] = P.cst[k];
@@ -454,19 +468,48 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const Params<T> P) {
   T* ptws = ws + (size_t)nL * REC;
   const long long stride = (long long)gridDim.x * P.envs_per_block;
   const T dt = P.dt;
+  const bool soft = (P.mode == MODE_STEP) && (P.contact_model == 1) && nc > 0;
+  const bool tma = (P.flags & F_TMA_STORE) != 0;
 
-  // number of loop trips is uniform across the block so that __syncwarp() is safe
+  // the number of loop trips is uniform across the block so that __syncwarp() is safe
   const long long first = (long long)blockIdx.x * P.envs_per_block;
   for (long long env0 = first; env0 < P.B; env0 += stride) {
     long long env = env0 + grp;
     const bool active = env < P.B;
     if (!active) env = P.B - 1;  // idle groups shadow the last environment, stores masked
 
+    // =========================================================== prefetch (one burst)
+    // joint state, first-step torque reference and contact state go global -> shared with
+    // cp.async; the 13 base scalars go to registers.  Nothing is consumed before the wait.
+    if (tma) tma_store_wait_read();  // the previous environment's staging areas are reused below
+    for (int i = 1 + lane; i < nL; i += G) {
+      T* ri = ws + (size_t)i * REC;
+      cp_async_elem(ri + O_S, P.s + env * n + (i - 1));
+      cp_async_elem(ri + O_SD, P.sd + env * n + (i - 1));
+      if (P.tau) cp_async_elem(ri + O_TREF, P.tau + env * n + (i - 1));
+      else ri[O_TREF] = T(0);
+    }
+    if (P.mode == MODE_STEP) {
+      for (int k = lane; k < nc; k += G) {
+        T* pw = ptws + (size_t)k * PTREC + PT_M;
+        if (P.m) {
+          const T* src = P.m + (env * nc + k) * 3;
+          cp_async_elem(pw, src); cp_async_elem(pw + 1, src + 1); cp_async_elem(pw + 2, src + 2);
+        } else {
+          pw[0] = T(0); pw[1] = T(0); pw[2] = T(0);
+        }
+      }
+    }
+    __pipeline_commit();
+
     // =========================================================== phase 0: base
     BaseState<T> b;
     {
       const T* q = P.q + env * 4;
       T qr[4] = {q[0], q[1], q[2], q[3]};
+      ldn<3>(P.p + env * 3, b.p);
+      ldn<3>(P.vlin + env * 3, b.vlin);
+      ldn<3>(P.omega + env * 3, b.w);
       const T nrm = sqrt_t(qr[0] * qr[0] + qr[1] * qr[1] + qr[2] * qr[2] + qr[3] * qr[3]);
       T den;
       if (P.mode == MODE_FK) den = (nrm == T(0)) ? T(1) : nrm;            // data.replace (api/data.py:441-447)
@@ -475,9 +518,6 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const Params<T> P) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) b.qn[k] = qr[k] * inv;
       quat_to_dcm(b.qn, b.R);
-      ldn<3>(P.p + env * 3, b.p);
-      ldn<3>(P.vlin + env * 3, b.vlin);
-      ldn<3>(P.omega + env * 3, b.w);
     }
     FkMap<T> fm;
     if (P.flags & F_GENERIC_FK) make_fk_map(P, b, fm);
@@ -498,14 +538,14 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const Params<T> P) {
           for (int k = 0; k < 6; ++k) v0[k] = T(0);  // rbda/aba.py:109-121: v[0] stays zero
         }
         stn<6>(r0 + O_V, v0);
-        r0[O_RR] = T(0); r0[O_RR + 1] = T(0); r0[O_RR + 2] = T(0);
       }
     };
-    write_base_record(b);
 
     // FK + velocity chain over the tree levels (rbda/forward_kinematics.py:80-113 and
-    // pass 1 of rbda/aba.py:131-171, in F_i coordinates)
-    auto fk_chain = [&]() {
+    // pass 1 of rbda/aba.py:131-171, in F_i coordinates).  `for_aba` also stores the world
+    // joint axis and the offset to the parent (not needed when only caches follow, and
+    // their slots then hold the joint-adjoint staging).
+    auto fk_chain = [&](const bool for_aba) {
       for (int l = 1; l <= P.depth; ++l) {
         __syncwarp();
         const int e = lvl_start[l + 1];
@@ -536,27 +576,58 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const Params<T> P) {
           else if (jt == 2) { v[0] += sdi * aw[0]; v[1] += sdi * aw[1]; v[2] += sdi * aw[2]; }
           stn<9>(ri + O_R, R);
           stn<3>(ri + O_P, pw);
-          stn<3>(ri + O_RR, r);
-          stn<3>(ri + O_AX, aw);
           stn<6>(ri + O_V, v);
+          if (for_aba) {
+            stn<3>(ri + O_RR, r);
+            stn<3>(ri + O_AX, aw);
+          }
         }
       }
       __syncwarp();
     };
 
+    auto write_fk_caches = [&](const BaseState<T>& bs, const FkMap<T>& f) {
+      for (int i = lane; i < nL; i += G) {
+        T R[9], p[3], vl[3], w[3];
+        fk_view(P, bs, f, ws + (size_t)i * REC, R, p, vl, w);
+        if (P.W_H_L) store_transform(P.W_H_L + (env * nL + i) * 16, R, p);
+        if (P.W_v) {
+          T t[3];
+          cross3(p, w, t);  // inertial-fixed linear part: vlin + p x w
+          const T o[6] = {vl[0] + t[0], vl[1] + t[1], vl[2] + t[2], w[0], w[1], w[2]};
+          stg_vec6(P.W_v + (env * nL + i) * 6, o);
+        }
+      }
+    };
+
+    // joint adjoint output of link i (R,t = lam_H_i): TMA from the record's staging area
+    // or 128-bit stores from registers
+    auto emit_joint_adjoint = [&](T* ri, long long i, const T* R, const T* t) {
+      T X[36];
+      inverse_adjoint(X, R, t);
+      T* dst = P.iXl + (env * nL + i) * 36;
+      if (tma) {
+        stn<36>(ri + O_X, X);
+        tma_store_bulk(dst, ri + O_X, 36 * sizeof(T));
+      } else {
+        stg_vec<36>(dst, X);
+      }
+    };
+
+    __pipeline_wait_prior(0);
+    write_base_record(b);
+
     // =========================================================== phase 1: joint transforms
     for (int i = 1 + lane; i < nL; i += G) {
       T* ri = ws + (size_t)i * REC;
-      const T si = P.s[env * n + (i - 1)];
       T Rrel[9], trel[3];
-      joint_rel_transform(P, sm_cst + (size_t)i * CREC, jtypes[i], i, si, Rrel, trel);
+      joint_rel_transform(P, sm_cst + (size_t)i * CREC, jtypes[i], i, ri[O_S], Rrel, trel);
       stn<9>(ri + O_R, Rrel);
       stn<3>(ri + O_P, trel);
-      ri[O_SD] = P.sd[env * n + (i - 1)];
-      if (P.mode == MODE_FK && P.iXl && active) store_inverse_adjoint(P.iXl + (env * nL + i) * 36, Rrel, trel);
+      if (P.mode == MODE_FK && P.iXl && active) emit_joint_adjoint(ri, i, Rrel, trel);
     }
     // =========================================================== phase 2: FK chain
-    fk_chain();
+    fk_chain(P.mode != MODE_FK);
 
     if (P.mode == MODE_FK) {
       // JaxSimModelData.build / replace: caches of the given state
@@ -566,242 +637,351 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const Params<T> P) {
           if (P.W_H_B) store_transform(P.W_H_B + env * 16, b.R, b.p);
           if (P.iXl) {
             // index 0: Ad((W_H_B suc_H_i[0])^-1)  (api/kin_dyn_parameters.py:417-449)
-            T R0[9], p0[3], t[3];
+            T R0[9], p0[3], t[3], X[36];
             mat3_mul(b.R, P.csuc, R0);
             mat3_vec(b.R, P.csuc + 9, t);
             p0[0] = b.p[0] + t[0]; p0[1] = b.p[1] + t[1]; p0[2] = b.p[2] + t[2];
-            store_inverse_adjoint(P.iXl + env * nL * 36, R0, p0);
+            inverse_adjoint(X, R0, p0);
+            stg_vec<36>(P.iXl + env * nL * 36, X);
           }
         }
-        for (int i = lane; i < nL; i += G) {
-          T R[9], p[3], vl[3], w[3];
-          fk_view(P, b, fm, ws + (size_t)i * REC, R, p, vl, w);
-          if (P.W_H_L) store_transform(P.W_H_L + (env * nL + i) * 16, R, p);
-          if (P.W_v) {
-            T* o = P.W_v + (env * nL + i) * 6;
-            T t[3];
-            cross3(p, w, t);  // inertial-fixed linear part: vlin + p x w
-            o[0] = vl[0] + t[0]; o[1] = vl[1] + t[1]; o[2] = vl[2] + t[2];
-            o[3] = w[0]; o[4] = w[1]; o[5] = w[2];
-          }
-        }
+        write_fk_caches(b, fm);
       }
       __syncwarp();
       continue;
     }
 
-    // =========================================================== contacts (point-parallel)
-    const bool soft = (P.mode == MODE_STEP) && (P.contact_model == 1) && nc > 0;
-    if (soft) {
-      for (int k = lane; k < nc; k += G) {
-        const int bi = pt_body[k];
-        const T* rb = ws + (size_t)bi * REC;
-        T R[9], p[3], vl[3], w[3];
-        fk_view(P, b, fm, rb, R, p, vl, w);
-        T Lp[3], d[3], pc[3], pd[3];
-        ldn<3>(sm_pt + 3 * k, Lp);
-        mat3_vec(R, Lp, d);
-        pc[0] = p[0] + d[0]; pc[1] = p[1] + d[1]; pc[2] = p[2] + d[2];
-        cross3(w, d, pd);
-        pd[0] += vl[0]; pd[1] += vl[1]; pd[2] += vl[2];
-        T m[3] = {T(0), T(0), T(0)};
-        if (P.m) ldn<3>(P.m + (env * nc + k) * 3, m);
-        T f[3] = {T(0), T(0), T(0)};
-        T md[3] = {T(0), T(0), T(0)};
-        if (pt_enabled[k]) {
-          // compute_penetration_data, FlatTerrain: n = z (rbda/contacts/common.py:25-63)
-          const T delta = max_t(T(0), P.h_terrain - pc[2]);
-          const T ddot = (delta > T(0)) ? -pd[2] : T(0);
-          const T eps = Lim<T>::eps();
-          const T dp = (P.flags & F_SQRT_P) ? sqrt_t(delta + eps) : pow_t(delta + eps, P.pexp);
-          const T dq = (P.flags & F_SQRT_Q) ? sqrt_t(delta + eps) : pow_t(delta + eps, P.qexp);
-          const T Kdp = P.K * dp, Ddq = P.D * dq;
-          const T fn = max_t(T(0), Kdp * delta + Ddq * ddot);
-          // tangential quantities (n = z): v_t = (vx,vy,0), m_t = (mx,my,0), m_n = (0,0,mz)
-          T ft0 = -(Kdp * m[0] + Ddq * pd[0]);
-          T ft1 = -(Kdp * m[1] + Ddq * pd[1]);
-          const T mufn = P.mu * fn;
-          const bool nocontact = delta <= T(0);
-          const bool sticking = nocontact || (ft0 * ft0 + ft1 * ft1 <= mufn * mufn);
-          const T nrm = sqrt_t(ft0 * ft0 + ft1 * ft1);
-          const T idn = T(1) / (nrm + eps * (nrm == T(0) ? T(1) : T(0)));
-          if (!sticking) {
-            const T sc = min_t(mufn, nrm) * idn;
-            ft0 *= sc; ft1 *= sc;
-          }
-          if (nocontact) { ft0 = T(0); ft1 = T(0); }
-          const T KoD = P.K / P.D;
-          if (nocontact) {
-            md[0] = -KoD * m[0]; md[1] = -KoD * m[1]; md[2] = -KoD * m[2];
-          } else if (sticking) {
-            md[0] = pd[0]; md[1] = pd[1]; md[2] = -KoD * m[2];
-          } else {
-            const T iD = T(1) / Ddq;
-            md[0] = -(ft0 + Kdp * m[0]) * iD; md[1] = -(ft1 + Kdp * m[1]) * iD; md[2] = T(0);
-          }
-          f[0] = ft0; f[1] = ft1; f[2] = fn;
-        }
-        // lever arm w.r.t. the origin of the ABA-chain frame of the body
-        T lev[3];
-        if (P.flags & F_GENERIC_FK) {
-          lev[0] = pc[0] - rb[O_P]; lev[1] = pc[1] - rb[O_P + 1]; lev[2] = pc[2] - rb[O_P + 2];
-        } else {
-          lev[0] = d[0]; lev[1] = d[1]; lev[2] = d[2];
-        }
-        T* pw = ptws + (size_t)k * PTREC;
-        stn<3>(pw, f);
-        stn<3>(pw + 3, lev);
-        if (active && P.m_o) {
-          T* mo = P.m_o + (env * nc + k) * 3;
-          mo[0] = m[0] + dt * md[0]; mo[1] = m[1] + dt * md[1]; mo[2] = m[2] + dt * md[2];
-        }
-      }
-    } else if (P.mode == MODE_STEP && P.m_o && P.m && active) {
-      for (int k = lane; k < nc * 3; k += G) P.m_o[env * nc * 3 + k] = P.m[env * nc * 3 + k];
-    }
-    __syncwarp();
+    T Wa[6];
+    for (int step = 0; step < P.nsteps; ++step) {
+      const bool last = (step == P.nsteps - 1);
+      const T* fext_step = P.fext ? P.fext + (long long)step * P.fext_step_stride : nullptr;
 
-    // =========================================================== phase 3: link-parallel
-    for (int i = lane; i < nL; i += G) {
-      T* ri = ws + (size_t)i * REC;
-      const T* c = sm_cst + (size_t)i * CREC;
-      T R[9], p[3], v[6];
-      ldn<9>(ri + O_R, R);
-      ldn<3>(ri + O_P, p);
-      ldn<6>(ri + O_V, v);
-      // total external wrench on the link in F_i: contacts + user forces
-      T fe[3] = {T(0), T(0), T(0)}, ne[3] = {T(0), T(0), T(0)};
+      // ========================================================= contacts (point-parallel)
       if (soft) {
-        const int e = pt_start[i + 1];
-        for (int kk = pt_start[i]; kk < e; ++kk) {
-          const T* pw = ptws + (size_t)pt_idx[kk] * PTREC;
-          T f[3], lev[3];
-          ldn<3>(pw, f);
-          ldn<3>(pw + 3, lev);
-          fe[0] += f[0]; fe[1] += f[1]; fe[2] += f[2];
-          cross3_add(lev, f, ne);
-        }
-      }
-      if (P.fext) {
-        const T* fx = P.fext + (env * nL + i) * 6;
-        T f[3] = {fx[0], fx[1], fx[2]};
-        fe[0] += f[0]; fe[1] += f[1]; fe[2] += f[2];
-        ne[0] += fx[3]; ne[1] += fx[4]; ne[2] += fx[5];
-        T t[3];
-        cross3(p, f, t);  // moment about the link origin = moment about W origin - p x f
-        ne[0] -= t[0]; ne[1] -= t[1]; ne[2] -= t[2];
-      }
-      // link inertia in world axes about the link origin
-      const T mass = c[C_MASS];
-      T com[3], cw[3], Dl[6];
-      ldn<3>(c + C_COM, com);
-      ldn<6>(c + C_DL, Dl);
-      mat3_vec(R, com, cw);
-      T Dw[6];
-      {
-        const T Df[9] = {Dl[0], Dl[1], Dl[2], Dl[1], Dl[3], Dl[4], Dl[2], Dl[4], Dl[5]};
-        T Tm[9];
-        mat3_mul(R, Df, Tm);
-        Dw[0] = Tm[0] * R[0] + Tm[1] * R[1] + Tm[2] * R[2];
-        Dw[1] = Tm[0] * R[3] + Tm[1] * R[4] + Tm[2] * R[5];
-        Dw[2] = Tm[0] * R[6] + Tm[1] * R[7] + Tm[2] * R[8];
-        Dw[3] = Tm[3] * R[3] + Tm[4] * R[4] + Tm[5] * R[5];
-        Dw[4] = Tm[3] * R[6] + Tm[4] * R[7] + Tm[5] * R[8];
-        Dw[5] = Tm[6] * R[6] + Tm[7] * R[7] + Tm[8] * R[8];
-      }
-      // I v = [m (v + w x c); m c x v + D w]
-      T fI[3], nI[3], t[3];
-      cross3(v + 3, cw, t);
-      fI[0] = mass * (v[0] + t[0]); fI[1] = mass * (v[1] + t[1]); fI[2] = mass * (v[2] + t[2]);
-      sym3_vec(Dw, v + 3, nI);
-      cross3(cw, v, t);
-      nI[0] += mass * t[0]; nI[1] += mass * t[1]; nI[2] += mass * t[2];
-      // pA = v x* (I v) - f_ext = [w x fI ; v x fI + w x nI] - [fe; ne]
-      T pA[6];
-      cross3(v + 3, fI, pA);
-      cross3(v, fI, pA + 3);
-      cross3_add(v + 3, nI, pA + 3);
-      pA[0] -= fe[0]; pA[1] -= fe[1]; pA[2] -= fe[2];
-      pA[3] -= ne[0]; pA[4] -= ne[1]; pA[5] -= ne[2];
-      if (i == 0 && !P.floating) {
-#pragma unroll
-        for (int k = 0; k < 6; ++k) pA[k] = T(0);
-      }
-      // c_i = v x vJ (rbda/aba.py:143-144) and the resultant joint torque
-      if (i > 0) {
-        const int jt = jtypes[i];
-        const T sdi = ri[O_SD];
-        T aw[3];
-        ldn<3>(ri + O_AX, aw);
-        T cc[6];
-        if (jt == 1) {
-          T vJ[3] = {sdi * aw[0], sdi * aw[1], sdi * aw[2]};
-          cross3(v, vJ, cc);       // v_lin x vJ_ang
-          cross3(v + 3, vJ, cc + 3);
-        } else {
-          T vJ[3] = {sdi * aw[0], sdi * aw[1], sdi * aw[2]};
-          if (jt != 2) { vJ[0] = vJ[1] = vJ[2] = T(0); }
-          cross3(v + 3, vJ, cc);   // w x vJ_lin
-          cc[3] = cc[4] = cc[5] = T(0);
-        }
-        stn<6>(ri + O_C, cc);
-        T tau;
-        if (P.mode == MODE_ABA) {
-          tau = P.tau ? P.tau[env * n + (i - 1)] : T(0);
-        } else {
-          // api/actuation_model.py:7-126
-          const T si = P.s[env * n + (i - 1)];
-          const T tref = P.tau ? P.tau[env * n + (i - 1)] : T(0);
-          const T lower = min_t(si - c[C_SMIN], T(0));
-          const T upper = max_t(si - c[C_SMAX], T(0));
-          T tlim = -c[C_KS] * (lower + upper);
-          tlim = tlim - tlim * c[C_KD] * sdi;
-          T tfr = T(0);
-          if (P.enable_friction) {
-            const T sg = (sdi > T(0)) ? T(1) : ((sdi < T(0)) ? T(-1) : T(0));
-            tfr = -(c[C_KC] * sg + c[C_KV] * sdi);
+        for (int k = lane; k < nc; k += G) {
+          const int bi = pt_body[k];
+          const T* rb = ws + (size_t)bi * REC;
+          T R[9], p[3], vl[3], w[3];
+          fk_view(P, b, fm, rb, R, p, vl, w);
+          T Lp[3], d[3], pc[3], pd[3];
+          ldn<3>(sm_pt + 3 * k, Lp);
+          mat3_vec(R, Lp, d);
+          pc[0] = p[0] + d[0]; pc[1] = p[1] + d[1]; pc[2] = p[2] + d[2];
+          cross3(w, d, pd);
+          pd[0] += vl[0]; pd[1] += vl[1]; pd[2] += vl[2];
+          T* pw = ptws + (size_t)k * PTREC;
+          T m[3];
+          ldn<3>(pw + PT_M, m);
+          T f[3] = {T(0), T(0), T(0)};
+          T md[3] = {T(0), T(0), T(0)};
+          if (pt_enabled[k]) {
+            // compute_penetration_data, FlatTerrain: n = z (rbda/contacts/common.py:25-63)
+            const T delta = max_t(T(0), P.h_terrain - pc[2]);
+            const T ddot = (delta > T(0)) ? -pd[2] : T(0);
+            const T eps = Lim<T>::eps();
+            const T dp = (P.flags & F_SQRT_P) ? sqrt_t(delta + eps) : pow_t(delta + eps, P.pexp);
+            const T dq = (P.flags & F_SQRT_Q) ? sqrt_t(delta + eps) : pow_t(delta + eps, P.qexp);
+            const T Kdp = P.K * dp, Ddq = P.D * dq;
+            const T fn = max_t(T(0), Kdp * delta + Ddq * ddot);
+            // tangential quantities (n = z): v_t = (vx,vy,0), m_t = (mx,my,0), m_n = (0,0,mz)
+            T ft0 = -(Kdp * m[0] + Ddq * pd[0]);
+            T ft1 = -(Kdp * m[1] + Ddq * pd[1]);
+            const T mufn = P.mu * fn;
+            const bool nocontact = delta <= T(0);
+            const bool sticking = nocontact || (ft0 * ft0 + ft1 * ft1 <= mufn * mufn);
+            const T nrm = sqrt_t(ft0 * ft0 + ft1 * ft1);
+            const T idn = T(1) / (nrm + eps * (nrm == T(0) ? T(1) : T(0)));
+            if (!sticking) {
+              const T sc = min_t(mufn, nrm) * idn;
+              ft0 *= sc; ft1 *= sc;
+            }
+            if (nocontact) { ft0 = T(0); ft1 = T(0); }
+            const T KoD = P.K / P.D;
+            if (nocontact) {
+              md[0] = -KoD * m[0]; md[1] = -KoD * m[1]; md[2] = -KoD * m[2];
+            } else if (sticking) {
+              md[0] = pd[0]; md[1] = pd[1]; md[2] = -KoD * m[2];
+            } else {
+              const T iD = T(1) / Ddq;
+              md[0] = -(ft0 + Kdp * m[0]) * iD; md[1] = -(ft1 + Kdp * m[1]) * iD; md[2] = T(0);
+            }
+            f[0] = ft0; f[1] = ft1; f[2] = fn;
           }
-          T tt = tref + tfr + tlim;
-          const T av = abs_t(sdi);
-          T lim;
-          if (av <= P.w_th) lim = P.tau_max;
-          else if (av <= P.w_max) lim = P.tau_max * (T(1) - (av - P.w_th) / (P.w_max - P.w_th));
-          else lim = T(0);
-          tau = min_t(max_t(tt, -lim), lim);
+          // lever arm w.r.t. the origin of the ABA-chain frame of the body
+          T lev[3];
+          if (P.flags & F_GENERIC_FK) {
+            lev[0] = pc[0] - rb[O_P]; lev[1] = pc[1] - rb[O_P + 1]; lev[2] = pc[2] - rb[O_P + 2];
+          } else {
+            lev[0] = d[0]; lev[1] = d[1]; lev[2] = d[2];
+          }
+          stn<3>(pw + PT_F, f);
+          stn<3>(pw + PT_LEV, lev);
+          // m+ = m + dt * m_dot (api/integrators.py:67-71); stays on chip between steps
+          m[0] += dt * md[0]; m[1] += dt * md[1]; m[2] += dt * md[2];
+          stn<3>(pw + PT_M, m);
+          if (last && active && P.m_o) {
+            T* mo = P.m_o + (env * nc + k) * 3;
+            mo[0] = m[0]; mo[1] = m[1]; mo[2] = m[2];
+          }
         }
-        ri[O_TAU] = tau;
+      } else if (P.mode == MODE_STEP && last && P.m_o && P.m && active) {
+        for (int k = lane; k < nc * 3; k += G) P.m_o[env * nc * 3 + k] = P.m[env * nc * 3 + k];
       }
-      // articulated inertia init (overwrites R/p): A = m 1, B = -m S(c_w), D = D_w
-      T IA[21];
-      IA[0] = mass; IA[1] = T(0); IA[2] = T(0); IA[3] = mass; IA[4] = T(0); IA[5] = mass;
-      IA[6] = T(0);            IA[7] = mass * cw[2];   IA[8] = -mass * cw[1];
-      IA[9] = -mass * cw[2];   IA[10] = T(0);          IA[11] = mass * cw[0];
-      IA[12] = mass * cw[1];   IA[13] = -mass * cw[0]; IA[14] = T(0);
-#pragma unroll
-      for (int k = 0; k < 6; ++k) IA[15 + k] = Dw[k];
-      if (i == 0 && !P.floating) {
-#pragma unroll
-        for (int k = 0; k < 21; ++k) IA[k] = T(0);
-      }
-      stn<21>(ri + O_IA, IA);
-      stn<6>(ri + O_PA, pA);
-    }
-
-    // =========================================================== phase 4: ABA pass 2
-    for (int l = P.depth; l >= 1; --l) {
       __syncwarp();
-      const int e = lvl_start[l + 1];
-      for (int idx = lvl_start[l] + lane; idx < e; idx += G) {
-        const int i = lvl_links[idx];
+
+      // ========================================================= phase 3: link-parallel
+      for (int i = lane; i < nL; i += G) {
         T* ri = ws + (size_t)i * REC;
-        T A[6], Bm[9], D[6], pA[6];
-        ldn<6>(ri + O_IA, A);
-        ldn<9>(ri + O_IB, Bm);
-        ldn<6>(ri + O_ID, D);
-        ldn<6>(ri + O_PA, pA);
+        const T* c = sm_cst + (size_t)i * CREC;
+        T R[9], p[3], v[6];
+        ldn<9>(ri + O_R, R);
+        ldn<3>(ri + O_P, p);
+        ldn<6>(ri + O_V, v);
+        // total external wrench on the link in F_i: contacts + user forces
+        T fe[3] = {T(0), T(0), T(0)}, ne[3] = {T(0), T(0), T(0)};
+        if (soft) {
+          const int e = pt_start[i + 1];
+          for (int kk = pt_start[i]; kk < e; ++kk) {
+            const T* pw = ptws + (size_t)pt_idx[kk] * PTREC;
+            T f[3], lev[3];
+            ldn<3>(pw + PT_F, f);
+            ldn<3>(pw + PT_LEV, lev);
+            fe[0] += f[0]; fe[1] += f[1]; fe[2] += f[2];
+            cross3_add(lev, f, ne);
+          }
+        }
+        if (fext_step) {
+          const T* fx = fext_step + (env * nL + i) * 6;
+          T f[3] = {fx[0], fx[1], fx[2]};
+          fe[0] += f[0]; fe[1] += f[1]; fe[2] += f[2];
+          ne[0] += fx[3]; ne[1] += fx[4]; ne[2] += fx[5];
+          T t[3];
+          cross3(p, f, t);  // moment about the link origin = moment about W origin - p x f
+          ne[0] -= t[0]; ne[1] -= t[1]; ne[2] -= t[2];
+        }
+        // link inertia in world axes about the link origin
+        const T mass = c[C_MASS];
+        T com[3], cw[3], Dl[6];
+        ldn<3>(c + C_COM, com);
+        ldn<6>(c + C_DL, Dl);
+        mat3_vec(R, com, cw);
+        T Dw[6];
         {
-          const int ce = child_start[i + 1];
-          for (int cc = child_start[i]; cc < ce; ++cc) {
+          const T Df[9] = {Dl[0], Dl[1], Dl[2], Dl[1], Dl[3], Dl[4], Dl[2], Dl[4], Dl[5]};
+          T Tm[9];
+          mat3_mul(R, Df, Tm);
+          Dw[0] = Tm[0] * R[0] + Tm[1] * R[1] + Tm[2] * R[2];
+          Dw[1] = Tm[0] * R[3] + Tm[1] * R[4] + Tm[2] * R[5];
+          Dw[2] = Tm[0] * R[6] + Tm[1] * R[7] + Tm[2] * R[8];
+          Dw[3] = Tm[3] * R[3] + Tm[4] * R[4] + Tm[5] * R[5];
+          Dw[4] = Tm[3] * R[6] + Tm[4] * R[7] + Tm[5] * R[8];
+          Dw[5] = Tm[6] * R[6] + Tm[7] * R[7] + Tm[8] * R[8];
+        }
+        // I v = [m (v + w x c); m c x v + D w]
+        T fI[3], nI[3], t[3];
+        cross3(v + 3, cw, t);
+        fI[0] = mass * (v[0] + t[0]); fI[1] = mass * (v[1] + t[1]); fI[2] = mass * (v[2] + t[2]);
+        sym3_vec(Dw, v + 3, nI);
+        cross3(cw, v, t);
+        nI[0] += mass * t[0]; nI[1] += mass * t[1]; nI[2] += mass * t[2];
+        // pA = v x* (I v) - f_ext = [w x fI ; v x fI + w x nI] - [fe; ne]
+        T pA[6];
+        cross3(v + 3, fI, pA);
+        cross3(v, fI, pA + 3);
+        cross3_add(v + 3, nI, pA + 3);
+        pA[0] -= fe[0]; pA[1] -= fe[1]; pA[2] -= fe[2];
+        pA[3] -= ne[0]; pA[4] -= ne[1]; pA[5] -= ne[2];
+        if (i == 0 && !P.floating) {
+#pragma unroll
+          for (int k = 0; k < 6; ++k) pA[k] = T(0);
+        }
+        // c_i = v x vJ (rbda/aba.py:143-144) and the resultant joint torque
+        if (i > 0) {
+          const int jt = jtypes[i];
+          const T sdi = ri[O_SD];
+          T aw[3];
+          ldn<3>(ri + O_AX, aw);
+          T cc[6];
+          const T vJ[3] = {sdi * aw[0], sdi * aw[1], sdi * aw[2]};
+          if (jt == 1) {
+            cross3(v, vJ, cc);  // v_lin x vJ_ang
+            cross3(v + 3, vJ, cc + 3);
+          } else {
+            cross3(v + 3, vJ, cc);  // w x vJ_lin
+            cc[3] = cc[4] = cc[5] = T(0);
+          }
+          stn<6>(ri + O_C, cc);
+          const T tref = ri[O_TREF];
+          T tau;
+          if (P.mode == MODE_ABA) {
+            tau = tref;
+          } else {
+            // api/actuation_model.py:7-126
+            const T si = ri[O_S];
+            const T lower = min_t(si - c[C_SMIN], T(0));
+            const T upper = max_t(si - c[C_SMAX], T(0));
+            T tlim = -c[C_KS] * (lower + upper);
+            tlim = tlim - tlim * c[C_KD] * sdi;
+            T tfr = T(0);
+            if (P.enable_friction) {
+              const T sg = (sdi > T(0)) ? T(1) : ((sdi < T(0)) ? T(-1) : T(0));
+              tfr = -(c[C_KC] * sg + c[C_KV] * sdi);
+            }
+            const T tt = tref + tfr + tlim;
+            const T av = abs_t(sdi);
+            T lim;
+            if (av <= P.w_th) lim = P.tau_max;
+            else if (av <= P.w_max) lim = P.tau_max * (T(1) - (av - P.w_th) / (P.w_max - P.w_th));
+            else lim = T(0);
+            tau = min_t(max_t(tt, -lim), lim);
+          }
+          ri[O_TAU] = tau;
+          // torque reference of the NEXT step: its latency hides behind the ABA passes
+          if (!last && P.tau && P.tau_step_stride)
+            cp_async_elem(ri + O_TREF, P.tau + (long long)(step + 1) * P.tau_step_stride + env * n + (i - 1));
+        }
+        // articulated inertia init (overwrites R/p): A = m 1, B = -m S(c_w), D = D_w
+        T IA[21];
+        IA[0] = mass; IA[1] = T(0); IA[2] = T(0); IA[3] = mass; IA[4] = T(0); IA[5] = mass;
+        IA[6] = T(0);            IA[7] = mass * cw[2];   IA[8] = -mass * cw[1];
+        IA[9] = -mass * cw[2];   IA[10] = T(0);          IA[11] = mass * cw[0];
+        IA[12] = mass * cw[1];   IA[13] = -mass * cw[0]; IA[14] = T(0);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) IA[15 + k] = Dw[k];
+        if (i == 0 && !P.floating) {
+#pragma unroll
+          for (int k = 0; k < 21; ++k) IA[k] = T(0);
+        }
+        stn<21>(ri + O_IA, IA);
+        stn<6>(ri + O_PA, pA);
+      }
+      __pipeline_commit();
+
+      // ========================================================= phase 4: ABA pass 2
+      for (int l = P.depth; l >= 1; --l) {
+        __syncwarp();
+        const int e = lvl_start[l + 1];
+        for (int idx = lvl_start[l] + lane; idx < e; idx += G) {
+          const int i = lvl_links[idx];
+          T* ri = ws + (size_t)i * REC;
+          T A[6], Bm[9], D[6], pA[6];
+          ldn<6>(ri + O_IA, A);
+          ldn<9>(ri + O_IB, Bm);
+          ldn<6>(ri + O_ID, D);
+          ldn<6>(ri + O_PA, pA);
+          {
+            const int ce = child_start[i + 1];
+            for (int cc = child_start[i]; cc < ce; ++cc) {
+              const T* rc = ws + (size_t)child_idx[cc] * REC;
+#pragma unroll
+              for (int k = 0; k < 6; ++k) A[k] += rc[O_IA + k];
+#pragma unroll
+              for (int k = 0; k < 9; ++k) Bm[k] += rc[O_IB + k];
+#pragma unroll
+              for (int k = 0; k < 6; ++k) D[k] += rc[O_ID + k];
+#pragma unroll
+              for (int k = 0; k < 6; ++k) pA[k] += rc[O_PA + k];
+            }
+          }
+          T aw[3], cI[6], r[3];
+          ldn<3>(ri + O_AX, aw);
+          ldn<6>(ri + O_C, cI);
+          ldn<3>(ri + O_RR, r);
+          const int jt = jtypes[i];
+          T Ul[3], Ua[3], d, u;
+          const T tau = ri[O_TAU];
+          if (jt == 1) {
+            mat3_vec(Bm, aw, Ul);  // B a
+            sym3_vec(D, aw, Ua);   // D a
+            d = dot3(aw, Ua);
+            u = tau - dot3(aw, pA + 3);
+          } else {
+            sym3_vec(A, aw, Ul);    // A a
+            mat3T_vec(Bm, aw, Ua);  // B^T a
+            d = dot3(aw, Ul);
+            u = tau - dot3(aw, pA);
+          }
+          const T dinv = T(1) / d;
+          stn<3>(ri + O_U, Ul);
+          stn<3>(ri + O_U + 3, Ua);
+          ri[O_DINV] = dinv;
+          ri[O_UU] = u;
+          const int par = parent[i];
+          if (par != 0 || P.floating) {
+            // Ma = IA - U U^T / d
+            const T Uls[3] = {Ul[0] * dinv, Ul[1] * dinv, Ul[2] * dinv};
+            const T Uas[3] = {Ua[0] * dinv, Ua[1] * dinv, Ua[2] * dinv};
+            A[0] -= Uls[0] * Ul[0]; A[1] -= Uls[0] * Ul[1]; A[2] -= Uls[0] * Ul[2];
+            A[3] -= Uls[1] * Ul[1]; A[4] -= Uls[1] * Ul[2]; A[5] -= Uls[2] * Ul[2];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+              for (int bb = 0; bb < 3; ++bb) Bm[3 * a + bb] -= Uls[a] * Ua[bb];
+            D[0] -= Uas[0] * Ua[0]; D[1] -= Uas[0] * Ua[1]; D[2] -= Uas[0] * Ua[2];
+            D[3] -= Uas[1] * Ua[1]; D[4] -= Uas[1] * Ua[2]; D[5] -= Uas[2] * Ua[2];
+            // pa = pA + Ma c + U u/d
+            const T ud = u * dinv;
+            T pa[6], t3[3];
+            sym3_vec(A, cI, t3);
+            pa[0] = pA[0] + t3[0] + Ul[0] * ud; pa[1] = pA[1] + t3[1] + Ul[1] * ud; pa[2] = pA[2] + t3[2] + Ul[2] * ud;
+            mat3_vec(Bm, cI + 3, t3);
+            pa[0] += t3[0]; pa[1] += t3[1]; pa[2] += t3[2];
+            mat3T_vec(Bm, cI, t3);
+            pa[3] = pA[3] + t3[0] + Ua[0] * ud; pa[4] = pA[4] + t3[1] + Ua[1] * ud; pa[5] = pA[5] + t3[2] + Ua[2] * ud;
+            sym3_vec(D, cI + 3, t3);
+            pa[3] += t3[0]; pa[4] += t3[1]; pa[5] += t3[2];
+            // shift to the parent's origin: X = [[1, -S(r)],[0, 1]]
+            //   B'' = B' - A' S(r)        (row_i(A' S) = row_i(A') x r)
+            //   D'' = D' + S(r) B' + (S(r) B'')^T
+            const T Af[9] = {A[0], A[1], A[2], A[1], A[3], A[4], A[2], A[4], A[5]};
+            T B2[9];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+              T rowx[3];
+              cross3(Af + 3 * a, r, rowx);
+              B2[3 * a] = Bm[3 * a] - rowx[0]; B2[3 * a + 1] = Bm[3 * a + 1] - rowx[1]; B2[3 * a + 2] = Bm[3 * a + 2] - rowx[2];
+            }
+            // SB1(i,j) = (r x col_j(B'))_i ; SB2(i,j) = (r x col_j(B''))_i
+            T SB1[9], SB2[9];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              const T c1[3] = {Bm[j], Bm[3 + j], Bm[6 + j]};
+              const T c2[3] = {B2[j], B2[3 + j], B2[6 + j]};
+              T o1[3], o2[3];
+              cross3(r, c1, o1);
+              cross3(r, c2, o2);
+              SB1[j] = o1[0]; SB1[3 + j] = o1[1]; SB1[6 + j] = o1[2];
+              SB2[j] = o2[0]; SB2[3 + j] = o2[1]; SB2[6 + j] = o2[2];
+            }
+            T D2[6];
+            D2[0] = D[0] + SB1[0] + SB2[0];
+            D2[1] = D[1] + SB1[1] + SB2[3];
+            D2[2] = D[2] + SB1[2] + SB2[6];
+            D2[3] = D[3] + SB1[4] + SB2[4];
+            D2[4] = D[4] + SB1[5] + SB2[7];
+            D2[5] = D[5] + SB1[8] + SB2[8];
+            cross3_add(r, pa, pa + 3);
+            stn<6>(ri + O_IA, A);
+            stn<9>(ri + O_IB, B2);
+            stn<6>(ri + O_ID, D2);
+            stn<6>(ri + O_PA, pa);
+          }
+        }
+      }
+      __syncwarp();
+
+      // ========================================================= phase 5: base acceleration
+      if (lane == 0) {
+        T a0[6];
+        if (P.floating) {
+          T* r0 = ws;
+          T A[6], Bm[9], D[6], pA[6];
+          ldn<6>(r0 + O_IA, A);
+          ldn<9>(r0 + O_IB, Bm);
+          ldn<6>(r0 + O_ID, D);
+          ldn<6>(r0 + O_PA, pA);
+          const int ce = child_start[1];
+          for (int cc = child_start[0]; cc < ce; ++cc) {
             const T* rc = ws + (size_t)child_idx[cc] * REC;
 #pragma unroll
             for (int k = 0; k < 6; ++k) A[k] += rc[O_IA + k];
@@ -812,176 +992,148 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const Params<T> P) {
 #pragma unroll
             for (int k = 0; k < 6; ++k) pA[k] += rc[O_PA + k];
           }
-        }
-        T aw[3], cI[6], r[3];
-        ldn<3>(ri + O_AX, aw);
-        ldn<6>(ri + O_C, cI);
-        ldn<3>(ri + O_RR, r);
-        const int jt = jtypes[i];
-        T Ul[3], Ua[3], d, u;
-        const T tau = ri[O_TAU];
-        if (jt == 1) {
-          mat3_vec(Bm, aw, Ul);  // B a
-          sym3_vec(D, aw, Ua);   // D a
-          d = dot3(aw, Ua);
-          u = tau - dot3(aw, pA + 3);
-        } else {
-          sym3_vec(A, aw, Ul);    // A a
-          mat3T_vec(Bm, aw, Ua);  // B^T a
-          d = dot3(aw, Ul);
-          u = tau - dot3(aw, pA);
-        }
-        const T dinv = T(1) / d;
-        stn<3>(ri + O_U, Ul);
-        stn<3>(ri + O_U + 3, Ua);
-        ri[O_DINV] = dinv;
-        ri[O_UU] = u;
-        const int par = parent[i];
-        if (par != 0 || P.floating) {
-          // Ma = IA - U U^T / d
-          const T Uls[3] = {Ul[0] * dinv, Ul[1] * dinv, Ul[2] * dinv};
-          const T Uas[3] = {Ua[0] * dinv, Ua[1] * dinv, Ua[2] * dinv};
-          A[0] -= Uls[0] * Ul[0]; A[1] -= Uls[0] * Ul[1]; A[2] -= Uls[0] * Ul[2];
-          A[3] -= Uls[1] * Ul[1]; A[4] -= Uls[1] * Ul[2]; A[5] -= Uls[2] * Ul[2];
+          T M[6][6];
+          M[0][0] = A[0]; M[0][1] = A[1]; M[0][2] = A[2]; M[1][1] = A[3]; M[1][2] = A[4]; M[2][2] = A[5];
+          M[1][0] = A[1]; M[2][0] = A[2]; M[2][1] = A[4];
 #pragma unroll
           for (int a = 0; a < 3; ++a)
 #pragma unroll
-            for (int bb = 0; bb < 3; ++bb) Bm[3 * a + bb] -= Uls[a] * Ua[bb];
-          D[0] -= Uas[0] * Ua[0]; D[1] -= Uas[0] * Ua[1]; D[2] -= Uas[0] * Ua[2];
-          D[3] -= Uas[1] * Ua[1]; D[4] -= Uas[1] * Ua[2]; D[5] -= Uas[2] * Ua[2];
-          // pa = pA + Ma c + U u/d
-          const T ud = u * dinv;
-          T pa[6], t3[3];
-          sym3_vec(A, cI, t3);
-          pa[0] = pA[0] + t3[0] + Ul[0] * ud; pa[1] = pA[1] + t3[1] + Ul[1] * ud; pa[2] = pA[2] + t3[2] + Ul[2] * ud;
-          mat3_vec(Bm, cI + 3, t3);
-          pa[0] += t3[0]; pa[1] += t3[1]; pa[2] += t3[2];
-          mat3T_vec(Bm, cI, t3);
-          pa[3] = pA[3] + t3[0] + Ua[0] * ud; pa[4] = pA[4] + t3[1] + Ua[1] * ud; pa[5] = pA[5] + t3[2] + Ua[2] * ud;
-          sym3_vec(D, cI + 3, t3);
-          pa[3] += t3[0]; pa[4] += t3[1]; pa[5] += t3[2];
-          // shift to the parent's origin: X = [[1, -S(r)],[0, 1]]
-          //   B'' = B' - A' S(r)        (row_i(A' S) = row_i(A') x r)
-          //   D'' = D' + S(r) B' + (S(r) B'')^T
-          const T Af[9] = {A[0], A[1], A[2], A[1], A[3], A[4], A[2], A[4], A[5]};
-          T B2[9];
-#pragma unroll
-          for (int a = 0; a < 3; ++a) {
-            T rowx[3];
-            cross3(Af + 3 * a, r, rowx);
-            B2[3 * a] = Bm[3 * a] - rowx[0]; B2[3 * a + 1] = Bm[3 * a + 1] - rowx[1]; B2[3 * a + 2] = Bm[3 * a + 2] - rowx[2];
-          }
-          // SB1(i,j) = (r x col_j(B'))_i ; SB2(i,j) = (r x col_j(B''))_i
-          T SB1[9], SB2[9];
-#pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            const T c1[3] = {Bm[j], Bm[3 + j], Bm[6 + j]};
-            const T c2[3] = {B2[j], B2[3 + j], B2[6 + j]};
-            T o1[3], o2[3];
-            cross3(r, c1, o1);
-            cross3(r, c2, o2);
-            SB1[j] = o1[0]; SB1[3 + j] = o1[1]; SB1[6 + j] = o1[2];
-            SB2[j] = o2[0]; SB2[3 + j] = o2[1]; SB2[6 + j] = o2[2];
-          }
-          T D2[6];
-          D2[0] = D[0] + SB1[0] + SB2[0];
-          D2[1] = D[1] + SB1[1] + SB2[3];
-          D2[2] = D[2] + SB1[2] + SB2[6];
-          D2[3] = D[3] + SB1[4] + SB2[4];
-          D2[4] = D[4] + SB1[5] + SB2[7];
-          D2[5] = D[5] + SB1[8] + SB2[8];
-          cross3_add(r, pa, pa + 3);
-          stn<6>(ri + O_IA, A);
-          stn<9>(ri + O_IB, B2);
-          stn<6>(ri + O_ID, D2);
-          stn<6>(ri + O_PA, pa);
+            for (int bb = 0; bb < 3; ++bb) { M[a][3 + bb] = Bm[3 * a + bb]; M[3 + bb][a] = Bm[3 * a + bb]; }
+          M[3][3] = D[0]; M[3][4] = D[1]; M[3][5] = D[2]; M[4][4] = D[3]; M[4][5] = D[4]; M[5][5] = D[5];
+          M[4][3] = D[1]; M[5][3] = D[2]; M[5][4] = D[4];
+          solve6_spd_neg(M, pA, a0);
         } else {
-          // fixed base: nothing is propagated to link 0 (rbda/aba.py:217-222)
-#pragma unroll
-          for (int k = 0; k < 27; ++k) ri[O_IA + k] = T(0);
+          a0[0] = T(0); a0[1] = T(0); a0[2] = -P.g; a0[3] = T(0); a0[4] = T(0); a0[5] = T(0);
+        }
+        stn<6>(ws + O_V, a0);
+      }
+
+      // ========================================================= phase 6: ABA pass 3
+      for (int l = 1; l <= P.depth; ++l) {
+        __syncwarp();
+        const int e = lvl_start[l + 1];
+        for (int idx = lvl_start[l] + lane; idx < e; idx += G) {
+          const int i = lvl_links[idx];
+          T* ri = ws + (size_t)i * REC;
+          const T* rp = ws + (size_t)parent[i] * REC;
+          T ap[6], r[3], cI[6], U[6], aw[3];
+          ldn<6>(rp + O_V, ap);
+          ldn<3>(ri + O_RR, r);
+          ldn<6>(ri + O_C, cI);
+          ldn<6>(ri + O_U, U);
+          ldn<3>(ri + O_AX, aw);
+          T a[6];
+          cross3(ap + 3, r, a);
+          a[0] += ap[0] + cI[0]; a[1] += ap[1] + cI[1]; a[2] += ap[2] + cI[2];
+          a[3] = ap[3] + cI[3]; a[4] = ap[4] + cI[4]; a[5] = ap[5] + cI[5];
+          const T sdd = (ri[O_UU] - (U[0] * a[0] + U[1] * a[1] + U[2] * a[2] + U[3] * a[3] + U[4] * a[4] + U[5] * a[5])) * ri[O_DINV];
+          const int jt = jtypes[i];
+          if (jt == 1) { a[3] += sdd * aw[0]; a[4] += sdd * aw[1]; a[5] += sdd * aw[2]; }
+          else if (jt == 2) { a[0] += sdd * aw[0]; a[1] += sdd * aw[1]; a[2] += sdd * aw[2]; }
+          stn<6>(ri + O_V, a);
+          ri[O_SDD] = sdd;
         }
       }
-    }
-    __syncwarp();
-
-    // =========================================================== phase 5: base acceleration
-    if (lane == 0) {
-      T a0[6];
-      if (P.floating) {
-        T* r0 = ws;
-        T A[6], Bm[9], D[6], pA[6];
-        ldn<6>(r0 + O_IA, A);
-        ldn<9>(r0 + O_IB, Bm);
-        ldn<6>(r0 + O_ID, D);
-        ldn<6>(r0 + O_PA, pA);
-        const int ce = child_start[1];
-        for (int cc = child_start[0]; cc < ce; ++cc) {
-          const T* rc = ws + (size_t)child_idx[cc] * REC;
-#pragma unroll
-          for (int k = 0; k < 6; ++k) A[k] += rc[O_IA + k];
-#pragma unroll
-          for (int k = 0; k < 9; ++k) Bm[k] += rc[O_IB + k];
-#pragma unroll
-          for (int k = 0; k < 6; ++k) D[k] += rc[O_ID + k];
-#pragma unroll
-          for (int k = 0; k < 6; ++k) pA[k] += rc[O_PA + k];
-        }
-        T M[6][6];
-        M[0][0] = A[0]; M[0][1] = A[1]; M[0][2] = A[2]; M[1][1] = A[3]; M[1][2] = A[4]; M[2][2] = A[5];
-        M[1][0] = A[1]; M[2][0] = A[2]; M[2][1] = A[4];
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-#pragma unroll
-          for (int bb = 0; bb < 3; ++bb) { M[a][3 + bb] = Bm[3 * a + bb]; M[3 + bb][a] = Bm[3 * a + bb]; }
-        M[3][3] = D[0]; M[3][4] = D[1]; M[3][5] = D[2]; M[4][4] = D[3]; M[4][5] = D[4]; M[5][5] = D[5];
-        M[4][3] = D[1]; M[5][3] = D[2]; M[5][4] = D[4];
-        solve6_spd_neg(M, pA, a0);
-      } else {
-        a0[0] = T(0); a0[1] = T(0); a0[2] = -P.g; a0[3] = T(0); a0[4] = T(0); a0[5] = T(0);
-      }
-      stn<6>(ws + O_V, a0);
-    }
-
-    // =========================================================== phase 6: ABA pass 3
-    for (int l = 1; l <= P.depth; ++l) {
       __syncwarp();
-      const int e = lvl_start[l + 1];
-      for (int idx = lvl_start[l] + lane; idx < e; idx += G) {
-        const int i = lvl_links[idx];
-        T* ri = ws + (size_t)i * REC;
-        const T* rp = ws + (size_t)parent[i] * REC;
-        T ap[6], r[3], cI[6], U[6], aw[3];
-        ldn<6>(rp + O_V, ap);
-        ldn<3>(ri + O_RR, r);
-        ldn<6>(ri + O_C, cI);
-        ldn<6>(ri + O_U, U);
-        ldn<3>(ri + O_AX, aw);
-        T a[6];
-        cross3(ap + 3, r, a);
-        a[0] += ap[0] + cI[0]; a[1] += ap[1] + cI[1]; a[2] += ap[2] + cI[2];
-        a[3] = ap[3] + cI[3]; a[4] = ap[4] + cI[4]; a[5] = ap[5] + cI[5];
-        const T sdd = (ri[O_UU] - (U[0] * a[0] + U[1] * a[1] + U[2] * a[2] + U[3] * a[3] + U[4] * a[4] + U[5] * a[5])) * ri[O_DINV];
-        const int jt = jtypes[i];
-        if (jt == 1) { a[3] += sdd * aw[0]; a[4] += sdd * aw[1]; a[5] += sdd * aw[2]; }
-        else if (jt == 2) { a[0] += sdd * aw[0]; a[1] += sdd * aw[1]; a[2] += sdd * aw[2]; }
-        stn<6>(ri + O_V, a);
-        ri[O_SDD] = sdd;
-      }
-    }
-    __syncwarp();
 
-    // base acceleration in inertial-fixed representation + gravity (rbda/aba.py:284-288)
-    T Wa[6];
-    if (P.floating) {
-      T a0[6];
-      ldn<6>(ws + O_V, a0);
-      cross3(b.p, a0 + 3, Wa);
-      Wa[0] += a0[0]; Wa[1] += a0[1]; Wa[2] += a0[2] + P.g;
-      Wa[3] = a0[3]; Wa[4] = a0[4]; Wa[5] = a0[5];
-    } else {
+      // base acceleration in inertial-fixed representation + gravity (rbda/aba.py:284-288)
+      if (P.floating) {
+        T a0[6];
+        ldn<6>(ws + O_V, a0);
+        cross3(b.p, a0 + 3, Wa);
+        Wa[0] += a0[0]; Wa[1] += a0[1]; Wa[2] += a0[2] + P.g;
+        Wa[3] = a0[3]; Wa[4] = a0[4]; Wa[5] = a0[5];
+      } else {
 #pragma unroll
-      for (int k = 0; k < 6; ++k) Wa[k] = T(0);
-    }
+        for (int k = 0; k < 6; ++k) Wa[k] = T(0);
+      }
+      if (P.mode == MODE_ABA) break;
+
+      // ========================================================= phase 7: semi-implicit Euler
+      // (api/integrators.py:14-88), base part replicated in every lane
+      {
+        BaseState<T> nb;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { nb.vlin[k] = b.vlin[k] + dt * Wa[k]; nb.w[k] = b.w[k] + dt * Wa[3 + k]; }
+        T pd[3];
+        cross3(nb.w, b.p, pd);
+        pd[0] += nb.vlin[0]; pd[1] += nb.vlin[1]; pd[2] += nb.vlin[2];
+        // Quaternion.derivative (math/quaternion.py:68-132), inertial-fixed omega, K = 0.1
+        const T nw = sqrt_t(dot3(nb.w, nb.w));
+        const T nq = sqrt_t(b.qn[0] * b.qn[0] + b.qn[1] * b.qn[1] + b.qn[2] * b.qn[2] + b.qn[3] * b.qn[3]);
+        const T v0 = T(0.1) * nw * (T(1) - nq);
+        const T qw = b.qn[0], qx = b.qn[1], qy = b.qn[2], qz = b.qn[3];
+        const T wx = nb.w[0], wy = nb.w[1], wz = nb.w[2];
+        T qd[4];
+        qd[0] = T(0.5) * (qw * v0 - qx * wx - qy * wy - qz * wz);
+        qd[1] = T(0.5) * (qx * v0 + qw * wx + qz * wy - qy * wz);
+        qd[2] = T(0.5) * (qy * v0 - qz * wx + qw * wy + qx * wz);
+        qd[3] = T(0.5) * (qz * v0 + qy * wx - qx * wy + qw * wz);
+        T qn2[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) qn2[k] = b.qn[k] + dt * qd[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) nb.p[k] = b.p[k] + dt * pd[k];
+        // normalise (integrators.py:61-63) and again in data.replace (api/data.py:441-447)
+#pragma unroll
+        for (int rep = 0; rep < 2; ++rep) {
+          const T nn = sqrt_t(qn2[0] * qn2[0] + qn2[1] * qn2[1] + qn2[2] * qn2[2] + qn2[3] * qn2[3]);
+          const T inv = T(1) / ((nn == T(0)) ? T(1) : nn);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) qn2[k] *= inv;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) nb.qn[k] = qn2[k];
+        quat_to_dcm(nb.qn, nb.R);
+        b = nb;
+      }
+      if (P.flags & F_GENERIC_FK) make_fk_map(P, b, fm);
+      const bool want_caches = last && (P.W_H_L || P.W_v);
+      if (last && active && lane == 0) {
+        stn<4>(P.q_o + env * 4, b.qn);
+        stn<3>(P.p_o + env * 3, b.p);
+        stn<3>(P.vlin_o + env * 3, b.vlin);
+        stn<3>(P.omega_o + env * 3, b.w);
+        if (P.W_H_B) store_transform(P.W_H_B + env * 16, b.R, b.p);
+        if (P.iXl) {
+          T R0[9], p0[3], t[3], X[36];
+          mat3_mul(b.R, P.csuc, R0);
+          mat3_vec(b.R, P.csuc + 9, t);
+          p0[0] = b.p[0] + t[0]; p0[1] = b.p[1] + t[1]; p0[2] = b.p[2] + t[2];
+          inverse_adjoint(X, R0, p0);
+          stg_vec<36>(P.iXl + env * nL * 36, X);
+        }
+      }
+      // joints: new velocity/position (+ joint transforms of the new state when kinematics
+      // are needed again: next step, or cache outputs)
+      const bool need_fk = !last || want_caches || (P.iXl != nullptr);
+      __pipeline_wait_prior(0);  // next step's torque references have landed
+      for (int i = 1 + lane; i < nL; i += G) {
+        T* ri = ws + (size_t)i * REC;
+        const T sdn = ri[O_SD] + dt * ri[O_SDD];
+        const T sn = ri[O_S] + dt * sdn;
+        ri[O_SD] = sdn;
+        ri[O_S] = sn;
+        if (last && active) {
+          P.sd_o[env * n + (i - 1)] = sdn;
+          P.s_o[env * n + (i - 1)] = sn;
+        }
+        if (need_fk) {
+          T Rrel[9], trel[3];
+          joint_rel_transform(P, sm_cst + (size_t)i * CREC, jtypes[i], i, sn, Rrel, trel);
+          stn<9>(ri + O_R, Rrel);
+          stn<3>(ri + O_P, trel);
+          if (last && active && P.iXl) emit_joint_adjoint(ri, i, Rrel, trel);
+        }
+      }
+      // ========================================================= phase 8: FK of the new state
+      if (!last || want_caches) {
+        write_base_record(b);
+        fk_chain(!last);
+        if (last && active) write_fk_caches(b, fm);
+      }
+      __syncwarp();
+    }  // steps
 
     if (P.mode == MODE_ABA) {
       if (active) {
@@ -989,100 +1141,9 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const Params<T> P) {
         for (int i = 1 + lane; i < nL; i += G) P.sdd_o[env * n + (i - 1)] = ws[(size_t)i * REC + O_SDD];
       }
       __syncwarp();
-      continue;
     }
-
-    // =========================================================== phase 7: semi-implicit Euler
-    // (api/integrators.py:14-88), base part replicated in every lane
-    BaseState<T> nb;
-    {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) { nb.vlin[k] = b.vlin[k] + dt * Wa[k]; nb.w[k] = b.w[k] + dt * Wa[3 + k]; }
-      T pd[3];
-      cross3(nb.w, b.p, pd);
-      pd[0] += nb.vlin[0]; pd[1] += nb.vlin[1]; pd[2] += nb.vlin[2];
-      // Quaternion.derivative (math/quaternion.py:68-132), inertial-fixed omega, K = 0.1
-      const T nw = sqrt_t(dot3(nb.w, nb.w));
-      const T nq = sqrt_t(b.qn[0] * b.qn[0] + b.qn[1] * b.qn[1] + b.qn[2] * b.qn[2] + b.qn[3] * b.qn[3]);
-      const T v0 = T(0.1) * nw * (T(1) - nq);
-      const T qw = b.qn[0], qx = b.qn[1], qy = b.qn[2], qz = b.qn[3];
-      const T wx = nb.w[0], wy = nb.w[1], wz = nb.w[2];
-      T qd[4];
-      qd[0] = T(0.5) * (qw * v0 - qx * wx - qy * wy - qz * wz);
-      qd[1] = T(0.5) * (qx * v0 + qw * wx + qz * wy - qy * wz);
-      qd[2] = T(0.5) * (qy * v0 - qz * wx + qw * wy + qx * wz);
-      qd[3] = T(0.5) * (qz * v0 + qy * wx - qx * wy + qw * wz);
-      T qn2[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) qn2[k] = b.qn[k] + dt * qd[k];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) nb.p[k] = b.p[k] + dt * pd[k];
-      // normalise (integrators.py:61-63) and again in data.replace (api/data.py:441-447)
-#pragma unroll
-      for (int rep = 0; rep < 2; ++rep) {
-        const T nn = sqrt_t(qn2[0] * qn2[0] + qn2[1] * qn2[1] + qn2[2] * qn2[2] + qn2[3] * qn2[3]);
-        const T inv = T(1) / ((nn == T(0)) ? T(1) : nn);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) qn2[k] *= inv;
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) nb.qn[k] = qn2[k];
-      quat_to_dcm(nb.qn, nb.R);
-    }
-    if (active && lane == 0) {
-      stn<4>(P.q_o + env * 4, nb.qn);
-      stn<3>(P.p_o + env * 3, nb.p);
-      stn<3>(P.vlin_o + env * 3, nb.vlin);
-      stn<3>(P.omega_o + env * 3, nb.w);
-      if (P.W_H_B) store_transform(P.W_H_B + env * 16, nb.R, nb.p);
-      if (P.iXl) {
-        T R0[9], p0[3], t[3];
-        mat3_mul(nb.R, P.csuc, R0);
-        mat3_vec(nb.R, P.csuc + 9, t);
-        p0[0] = nb.p[0] + t[0]; p0[1] = nb.p[1] + t[1]; p0[2] = nb.p[2] + t[2];
-        store_inverse_adjoint(P.iXl + env * nL * 36, R0, p0);
-      }
-    }
-    // joints: new velocity/position + joint transforms of the new state
-    for (int i = 1 + lane; i < nL; i += G) {
-      T* ri = ws + (size_t)i * REC;
-      const T sdn = ri[O_SD] + dt * ri[O_SDD];
-      const T sn = P.s[env * n + (i - 1)] + dt * sdn;
-      if (active) {
-        P.sd_o[env * n + (i - 1)] = sdn;
-        P.s_o[env * n + (i - 1)] = sn;
-      }
-      T Rrel[9], trel[3];
-      joint_rel_transform(P, sm_cst + (size_t)i * CREC, jtypes[i], i, sn, Rrel, trel);
-      stn<9>(ri + O_R, Rrel);
-      stn<3>(ri + O_P, trel);
-      ri[O_SD] = sdn;
-      if (active && P.iXl) store_inverse_adjoint(P.iXl + (env * nL + i) * 36, Rrel, trel);
-    }
-    __syncwarp();
-    // =========================================================== phase 8: FK of the new state
-    if (P.W_H_L || P.W_v) {
-      FkMap<T> nfm;
-      if (P.flags & F_GENERIC_FK) make_fk_map(P, nb, nfm);
-      write_base_record(nb);
-      fk_chain();
-      if (active) {
-        for (int i = lane; i < nL; i += G) {
-          T R[9], p[3], vl[3], w[3];
-          fk_view(P, nb, nfm, ws + (size_t)i * REC, R, p, vl, w);
-          if (P.W_H_L) store_transform(P.W_H_L + (env * nL + i) * 16, R, p);
-          if (P.W_v) {
-            T* o = P.W_v + (env * nL + i) * 6;
-            T t[3];
-            cross3(p, w, t);
-            o[0] = vl[0] + t[0]; o[1] = vl[1] + t[1]; o[2] = vl[2] + t[2];
-            o[3] = w[0]; o[4] = w[1]; o[5] = w[2];
-          }
-        }
-      }
-    }
-    __syncwarp();
   }
+  if (tma) tma_store_wait_all();
 }
 
 }  // namespace b200sim
