@@ -168,6 +168,20 @@ int b200sim_aba(const B200SimModel *model, int dtype, int64_t B,
                 const void *omega, const void *p, const void *tau, const void *f_ext,
                 void *W_vd_WB, void *sdd, void *stream);
 
+/* Inverse dynamics == vmapped rbda.rnea (rbda/rnea.py:12-238).  in: state as above,
+ * W_vd_WB (B,6) inertial-fixed base acceleration or NULL (zeros), sdd (B,n) or NULL,
+ * f_ext (B,nL,6) inertial-fixed link forces or NULL.  out: W_f_B (B,6) the inertial-fixed
+ * 6D force on the base, tau (B,n). */
+int b200sim_rnea(const B200SimModel *model, int dtype, int64_t B,
+                 const void *s, const void *sd, const void *q_wxyz, const void *v_lin,
+                 const void *omega, const void *p, const void *W_vd_WB, const void *sdd,
+                 const void *f_ext, void *W_f_B, void *tau, void *stream);
+
+/* Free-floating mass matrix == vmapped rbda.crba (rbda/crba.py:10-170), body-fixed
+ * representation.  in: s (B,n).  out: M (B,6+n,6+n) (fully written). */
+int b200sim_crba(const B200SimModel *model, int dtype, int64_t B, const void *s, void *M,
+                 void *stream);
+
 /* Library / build information: "b200sim <abi> sm_100a ..." */
 const char *b200sim_version(void);
 

@@ -73,6 +73,8 @@ EXPORTED_SYMBOLS = (
     "b200sim_step_n",
     "b200sim_fk",
     "b200sim_aba",
+    "b200sim_rnea",
+    "b200sim_crba",
 )
 
 _lib = None
@@ -113,6 +115,10 @@ def load() -> C.CDLL:
     lib.b200sim_fk.restype = C.c_int
     lib.b200sim_aba.argtypes = [vp, C.c_int, C.c_int64] + [vp] * 11
     lib.b200sim_aba.restype = C.c_int
+    lib.b200sim_rnea.argtypes = [vp, C.c_int, C.c_int64] + [vp] * 12
+    lib.b200sim_rnea.restype = C.c_int
+    lib.b200sim_crba.argtypes = [vp, C.c_int, C.c_int64, vp, vp, vp]
+    lib.b200sim_crba.restype = C.c_int
     _lib = lib
     return lib
 

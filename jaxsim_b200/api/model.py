@@ -508,3 +508,83 @@ def forward_dynamics_aba(
     if data._joint_positions.dim() == 1:
         return avd.squeeze(0), sdd.squeeze(0)
     return avd, sdd
+
+
+def inverse_dynamics(
+    model: JaxSimModel,
+    data: "_data.JaxSimModelData",
+    *,
+    joint_accelerations: torch.Tensor | None = None,
+    base_acceleration: torch.Tensor | None = None,
+    link_forces: torch.Tensor | None = None,
+) -> tuple[torch.Tensor, torch.Tensor]:
+    """``js.model.inverse_dynamics`` (``src/jaxsim/api/model.py:1746-1894``) -> vmapped
+    ``rbda.rnea`` (``rbda/rnea.py:12-238``) for ``VelRepr.Inertial`` data: returns the
+    inertial-fixed 6D base force ``(B, 6)`` and the joint forces ``(B, n)``."""
+    if data.velocity_representation != VelRepr.Inertial:
+        raise NotImplementedError("inverse_dynamics: only VelRepr.Inertial data (the kernel's native representation)")
+    s = _batched(data._joint_positions, 1).contiguous()
+    dev, dtype = s.device, s.dtype
+    dm = model.device_model(dev)
+    nL, n = model.number_of_links(), model.dofs()
+    sd = _batched(data._joint_velocities, 1).contiguous()
+    q = _batched(data._base_quaternion, 1).contiguous()
+    vl = _batched(data._base_linear_velocity, 1).contiguous()
+    om = _batched(data._base_angular_velocity, 1).contiguous()
+    p = _batched(data._base_position, 1).contiguous()
+    B = q.shape[0]
+
+    def opt(x, shape, nd):
+        if x is None:
+            return None
+        x = _batched(torch.as_tensor(x, dtype=dtype, device=dev), nd).contiguous()
+        if x.shape != shape:
+            raise ValueError(x.shape, shape)
+        return x
+
+    sdd = opt(joint_accelerations, (B, n), 1)
+    avd = opt(base_acceleration, (B, 6), 1)
+    fext = opt(link_forces, (B, nL, 6), 2)
+    W_f = torch.empty(B, 6, dtype=dtype, device=dev)
+    tau = torch.empty(B, n, dtype=dtype, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().b200sim_rnea(
+            dm.handle, _dtype_code(dtype), B, _ptr(s), _ptr(sd), _ptr(q), _ptr(vl), _ptr(om), _ptr(p),
+            _ptr(avd), _ptr(sdd), _ptr(fext), _ptr(W_f), _ptr(tau), _stream_ptr(dev),
+        )
+    _lib.check(rc, "b200sim_rnea")
+    if data._joint_positions.dim() == 1:
+        return W_f.squeeze(0), tau.squeeze(0)
+    return W_f, tau
+
+
+def free_floating_mass_matrix(model: JaxSimModel, data: "_data.JaxSimModelData") -> torch.Tensor:
+    """``js.model.free_floating_mass_matrix`` (``src/jaxsim/api/model.py:1556-1592``):
+    CRBA (``rbda/crba.py:10-170``) in body-fixed representation, then ``_transform_M_block``
+    (``:1527-1553``) into the active representation."""
+    from .common import adjoint_from_transform
+
+    s = _batched(data._joint_positions, 1).contiguous()
+    dev, dtype = s.device, s.dtype
+    dm = model.device_model(dev)
+    n = model.dofs()
+    B = s.shape[0] if n > 0 else _batched(data._base_quaternion, 1).shape[0]
+    M = torch.empty(B, 6 + n, 6 + n, dtype=dtype, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().b200sim_crba(dm.handle, _dtype_code(dtype), B, _ptr(s), _ptr(M), _stream_ptr(dev))
+    _lib.check(rc, "b200sim_crba")
+    vr = data.velocity_representation
+    if vr != VelRepr.Body:
+        H = _batched(data.base_transform, 2)
+        if vr == VelRepr.Mixed:
+            H = H.clone()
+            H[..., 0:3, 3] = 0
+        X = adjoint_from_transform(H, inverse=True)  # B_X_W or B_X_BW
+        Xt = X.transpose(-1, -2)
+        Mt = torch.empty_like(M)
+        Mt[:, :6, :6] = Xt @ M[:, :6, :6] @ X
+        Mt[:, :6, 6:] = Xt @ M[:, :6, 6:]
+        Mt[:, 6:, :6] = M[:, 6:, :6] @ X
+        Mt[:, 6:, 6:] = M[:, 6:, 6:]
+        M = Mt
+    return M.squeeze(0) if data._joint_positions.dim() == 1 else M

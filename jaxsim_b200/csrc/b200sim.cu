@@ -7,6 +7,7 @@
 
 #include "b200sim.h"
 #include "b200sim_kernels.cuh"
+#include "b200sim_rbda_kernels.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -208,6 +209,82 @@ int launch(const B200SimModel* m, Params<T>& P, int dtype, void* stream) {
   }
   if (dev != m->device) cudaSetDevice(dev);
   return rc;
+}
+
+enum RbdaKind { RBDA_RNEA = 0, RBDA_CRBA = 1 };
+
+template <typename T, int G>
+int launch_rbda_g(int kind, const Params<T>& P, const RbdaArgs<T>& A, const Geometry& g, cudaStream_t st) {
+  if (kind == RBDA_RNEA) {
+    auto kern = rnea_kernel<T, G>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+    kern<<<g.grid, g.epb * G, g.smem, st>>>(P, A);
+  } else {
+    auto kern = crba_kernel<T, G>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+    kern<<<g.grid, g.epb * G, g.smem, st>>>(P, A);
+  }
+  return (int)cudaGetLastError();
+}
+
+template <typename T>
+int launch_rbda(const B200SimModel* m, int kind, Params<T>& P, const RbdaArgs<T>& A, int dtype, void* stream) {
+  Geometry g;
+  int rc = pick_geometry(m, dtype, P.B, &g);
+  if (rc) return rc;
+  P.envs_per_block = g.epb;
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev != m->device) CK(cudaSetDevice(m->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (kind == RBDA_CRBA) {
+    const size_t N = 6 + (size_t)m->n;
+    rc = (int)cudaMemsetAsync(A.M, 0, (size_t)P.B * N * N * sizeof(T), st);
+  }
+  if (!rc) {
+    switch (g.G) {
+      case 1: rc = launch_rbda_g<T, 1>(kind, P, A, g, st); break;
+      case 2: rc = launch_rbda_g<T, 2>(kind, P, A, g, st); break;
+      case 4: rc = launch_rbda_g<T, 4>(kind, P, A, g, st); break;
+      case 8: rc = launch_rbda_g<T, 8>(kind, P, A, g, st); break;
+      case 16: rc = launch_rbda_g<T, 16>(kind, P, A, g, st); break;
+      case 32: rc = launch_rbda_g<T, 32>(kind, P, A, g, st); break;
+      default: rc = B200SIM_E_INVALID;
+    }
+  }
+  if (dev != m->device) cudaSetDevice(dev);
+  return rc;
+}
+
+template <typename T>
+int rnea_t(const B200SimModel* m, int dtype, int64_t B, const void* s, const void* sd, const void* q, const void* vlin,
+           const void* omega, const void* p, const void* avd, const void* sdd, const void* fext, void* W_f0, void* tau,
+           void* stream) {
+  Params<T> P;
+  std::memset(&P, 0, sizeof(P));
+  fill_model_params(m, P);
+  P.B = B;
+  P.s = (const T*)s; P.sd = (const T*)sd; P.q = (const T*)q; P.vlin = (const T*)vlin; P.omega = (const T*)omega;
+  P.p = (const T*)p; P.fext = (const T*)fext;
+  P.nsteps = 1;
+  RbdaArgs<T> A;
+  std::memset(&A, 0, sizeof(A));
+  A.avd = (const T*)avd; A.sdd = (const T*)sdd; A.W_f0 = (T*)W_f0; A.tau_o = (T*)tau;
+  return launch_rbda(m, RBDA_RNEA, P, A, dtype, stream);
+}
+
+template <typename T>
+int crba_t(const B200SimModel* m, int dtype, int64_t B, const void* s, void* M, void* stream) {
+  Params<T> P;
+  std::memset(&P, 0, sizeof(P));
+  fill_model_params(m, P);
+  P.B = B;
+  P.s = (const T*)s;
+  P.nsteps = 1;
+  RbdaArgs<T> A;
+  std::memset(&A, 0, sizeof(A));
+  A.M = (T*)M;
+  return launch_rbda(m, RBDA_CRBA, P, A, dtype, stream);
 }
 
 template <typename T>
@@ -536,6 +613,25 @@ int b200sim_aba(const B200SimModel* m, int dtype, int64_t B, const void* s, cons
   if (m->n > 0 && (!s || !sd || !sdd)) return B200SIM_E_INVALID;
   if (dtype == 0) return aba_t<float>(m, dtype, B, s, sd, q, vlin, omega, p, tau, fext, avd, sdd, stream);
   return aba_t<double>(m, dtype, B, s, sd, q, vlin, omega, p, tau, fext, avd, sdd, stream);
+}
+
+int b200sim_rnea(const B200SimModel* m, int dtype, int64_t B, const void* s, const void* sd, const void* q,
+                 const void* vlin, const void* omega, const void* p, const void* W_vd_WB, const void* sdd,
+                 const void* fext, void* W_f_B, void* tau, void* stream) {
+  if (!m || B < 0 || (dtype != 0 && dtype != 1)) return B200SIM_E_INVALID;
+  if (B == 0) return 0;
+  if (!q || !vlin || !omega || !p || !W_f_B) return B200SIM_E_INVALID;
+  if (m->n > 0 && (!s || !sd || !tau)) return B200SIM_E_INVALID;
+  if (dtype == 0) return rnea_t<float>(m, dtype, B, s, sd, q, vlin, omega, p, W_vd_WB, sdd, fext, W_f_B, tau, stream);
+  return rnea_t<double>(m, dtype, B, s, sd, q, vlin, omega, p, W_vd_WB, sdd, fext, W_f_B, tau, stream);
+}
+
+int b200sim_crba(const B200SimModel* m, int dtype, int64_t B, const void* s, void* M, void* stream) {
+  if (!m || B < 0 || (dtype != 0 && dtype != 1)) return B200SIM_E_INVALID;
+  if (B == 0) return 0;
+  if (!M || (m->n > 0 && !s)) return B200SIM_E_INVALID;
+  if (dtype == 0) return crba_t<float>(m, dtype, B, s, M, stream);
+  return crba_t<double>(m, dtype, B, s, M, stream);
 }
 
 }  // extern "C"

@@ -217,3 +217,58 @@ def test_in_place_step_and_cuda_graph(cuda_device):
     torch.cuda.synchronize()
     for _, leaf in H.LEAVES:
         assert torch.equal(getattr(a, leaf), getattr(ref, leaf)), leaf
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("name", MODELS)
+def test_rnea(name, dtype, cuda_device):
+    """inverse_dynamics == oracle rnea (rbda/rnea.py) and RNEA(ABA(tau)) == tau on the GPU."""
+    import torch
+
+    model = H.build_model(name)
+    om = H.oracle_model(model)
+    B = 29
+    od = O.random_model_data(om, B, seed=37)
+    rng = np.random.default_rng(3)
+    sdd = rng.uniform(-3, 3, size=(B, om.dofs()))
+    avd = rng.uniform(-2, 2, size=(B, 6))
+    W_f = rng.uniform(size=(B, om.number_of_links(), 6))
+    fB_ref, tau_ref = O.rnea(om, od.base_position, od.base_orientation, od.joint_positions, od.base_linear_velocity,
+                             od.base_angular_velocity, od.joint_velocities, avd, sdd, W_f)
+    td = _dtype(dtype)
+    pd = H.to_product(model, od, td, cuda_device)
+    t = lambda a: torch.as_tensor(a, dtype=td, device=cuda_device)  # noqa: E731
+    fB, tau = js.model.inverse_dynamics(model, pd, joint_accelerations=t(sdd), base_acceleration=t(avd), link_forces=t(W_f))
+    rt = H.RTOL[dtype]
+    if om.floating_base:
+        assert H.rel_err(fB.cpu().numpy(), fB_ref) <= rt
+    else:
+        assert float(fB.abs().max()) == 0.0
+    if om.dofs():
+        assert H.rel_err(tau.cpu().numpy(), tau_ref) <= rt
+        # FD/ID consistency on the device (tests/test_api_model.py:495-577)
+        tau_in = t(10 * rng.uniform(size=(B, om.dofs())))
+        W_f2 = W_f.copy()
+        if not om.floating_base:
+            W_f2[:, 0] = 0
+        a, sdd2 = js.model.forward_dynamics_aba(model, pd, joint_forces=tau_in, link_forces=t(W_f2))
+        fB2, tau2 = js.model.inverse_dynamics(model, pd, joint_accelerations=sdd2, base_acceleration=a, link_forces=t(W_f2))
+        scale = float(tau_in.abs().max())
+        assert float((tau2 - tau_in).abs().max()) / scale <= (1e-9 if dtype == "float64" else 2e-3)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("name", MODELS)
+def test_crba(name, dtype, cuda_device):
+    """free_floating_mass_matrix == oracle crba (rbda/crba.py), body-fixed representation."""
+    model = H.build_model(name)
+    om = H.oracle_model(model)
+    B = 21
+    od = O.random_model_data(om, B, seed=41)
+    M_ref = O.crba(om, od.joint_positions)
+    pd = H.to_product(model, od, _dtype(dtype), cuda_device, velocity_representation=js.common.VelRepr.Body)
+    M = js.model.free_floating_mass_matrix(model, pd)
+    assert M.shape == M_ref.shape
+    assert H.rel_err(M.cpu().numpy(), M_ref) <= H.RTOL[dtype]
+    Mn = M.cpu().numpy().astype(np.float64)
+    assert np.abs(Mn - np.swapaxes(Mn, 1, 2)).max() == 0.0  # exactly symmetric by construction
