@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--model", default="icub_like")
     ap.add_argument("--lanes", type=int, default=0, help="lanes per env (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-caches", action="store_true", help="diagnostic: do not materialise the cached transforms (B_min traffic)")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
     ap.add_argument("--no-tma", action="store_true", help="128-bit stores instead of TMA bulk stores for the joint adjoints")
     ap.add_argument("--profile", action="store_true", help="cudaProfilerStart/Stop around the eager timed region (ncu --profile-from-start off)")
@@ -229,7 +230,7 @@ def run_b200(args):
         model.set_options(tma_store=False)
     n, nL, nc = model.dofs(), model.number_of_links(), model.number_of_collidable_points()
     B = args.batch
-    bytes_env = algorithmic_bytes_per_env(n, nL, nc, w, caches=True)
+    bytes_env = algorithmic_bytes_per_env(n, nL, nc, w, caches=not args.no_caches)
 
     def barrier():
         if world > 1:
@@ -246,12 +247,13 @@ def run_b200(args):
                                            velocity_representation=js.common.VelRepr.Inertial) for r in range(ring)]
         taus = [10 * torch.rand(Bq, n, dtype=dtype, device=dev) for _ in range(ring)]
         # preallocated outputs (`out=`): the step then performs no allocation and is capturable
-        outs = [js.model.step(model, datas[r], joint_force_references=taus[r]) for r in range(ring)]
+        outs = [js.model.step(model, datas[r], joint_force_references=taus[r], update_caches=not args.no_caches) for r in range(ring)]
 
         def run(count):
             o = None
             for i in range(count):
-                o = js.model.step(model, datas[i % ring], joint_force_references=taus[i % ring], out=outs[i % ring])
+                o = js.model.step(model, datas[i % ring], joint_force_references=taus[i % ring], out=outs[i % ring],
+                                  update_caches=not args.no_caches)
             return o
 
         run(W)
@@ -422,7 +424,7 @@ def run_b200(args):
                    "batch_per_gpu": B, "global_batch": B * world, "dt": 1e-3, "contact_model": "soft",
                    "integrator": "semi_implicit_euler", "parallelism": f"env-parallel x{world} (no data-path collective)",
                    "l2": f"inputs larger than L2: ring of {ring} independent state sets ({ring * B * bytes_env / 2**20:.0f} MiB)",
-                   "launch": geo, "caches_written": True, "cuda_graph": ms_graph is not None,
+                   "launch": geo, "caches_written": not args.no_caches, "cuda_graph": ms_graph is not None,
                    "joint_adjoint_store": "128-bit STG" if args.no_tma else "TMA cp.async.bulk"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "bytes_per_env_step": bytes_env, "peak_source": peak_src,

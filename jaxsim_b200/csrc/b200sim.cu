@@ -57,7 +57,8 @@ inline int max_threads_for(int G) { return G <= 8 ? 288 : 512; }  // == LaunchBo
 
 template <typename T>
 int upload(const std::vector<double>& h, T** d) {
-  std::vector<T> tmp(h.size() > 0 ? h.size() : 1);
+  // padded to whole 16-byte chunks (+1 chunk) so the kernel can stage with 16-byte cp.async
+  std::vector<T> tmp(((h.size() + 3) & ~size_t(3)) + 4, T(0));
   for (size_t i = 0; i < h.size(); ++i) tmp[i] = (T)h[i];
   if (!*d) CK(cudaMalloc((void**)d, tmp.size() * sizeof(T)));
   CK(cudaMemcpy(*d, tmp.data(), tmp.size() * sizeof(T), cudaMemcpyHostToDevice));
@@ -400,7 +401,12 @@ int b200sim_model_create(const B200SimModelDesc* d, int device, B200SimModel** o
       for (int cc = 0; cc < 3; ++cc) {
         double raa = 0, rsa = 0;
         for (int k = 0; k < 3; ++k) { raa += Rpre[3 * r + k] * ax[k] * ax[cc]; rsa += Rpre[3 * r + k] * Sa[3 * k + cc]; }
-        if (i >= 1 && d->joint_type[i] == 1) {
+        if (i == 0) {
+          // link 0 has no joint: its slots carry suc_H_i[0] (root -> base link pose)
+          c[C_M0 + 3 * r + cc] = Hs[4 * r + cc];
+          c[C_M1 + 3 * r + cc] = 0.0;
+          c[C_M2 + 3 * r + cc] = 0.0;
+        } else if (d->joint_type[i] == 1) {
           c[C_M0 + 3 * r + cc] = raa;
           c[C_M1 + 3 * r + cc] = Rpre[3 * r + cc] - raa;
           c[C_M2 + 3 * r + cc] = rsa;
@@ -413,6 +419,7 @@ int b200sim_model_create(const B200SimModelDesc* d, int device, B200SimModel** o
       double ra = 0;
       for (int k = 0; k < 3; ++k) ra += Rpre[3 * r + k] * ax[k];
       c[C_RA + r] = (i >= 1 && d->joint_type[i] == 2) ? ra : 0.0;
+      if (i == 0) c[C_TPRE + r] = Hs[4 * r + 3];
     }
     if (i >= 1 && !is_identity4(Hs)) suc_nonid = true;
     if (i >= 1) {
@@ -495,8 +502,10 @@ int b200sim_model_create(const B200SimModelDesc* d, int device, B200SimModel** o
   if (!rc) rc = upload(m->pt_h, &m->pt_f);
   if (!rc) rc = upload(m->pt_h, &m->pt_d);
   if (!rc) {
-    e = cudaMalloc((void**)&m->itab_d, m->itab_h.size() * sizeof(int));
-    if (e == cudaSuccess) e = cudaMemcpy(m->itab_d, m->itab_h.data(), m->itab_h.size() * sizeof(int), cudaMemcpyHostToDevice);
+    std::vector<int> padded(((m->itab_h.size() + 3) & ~size_t(3)) + 4, 0);
+    std::copy(m->itab_h.begin(), m->itab_h.end(), padded.begin());
+    e = cudaMalloc((void**)&m->itab_d, padded.size() * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpy(m->itab_d, padded.data(), padded.size() * sizeof(int), cudaMemcpyHostToDevice);
     rc = (int)e;
   }
   cudaSetDevice(prev);

@@ -138,6 +138,13 @@ __device__ __forceinline__ double abs_t(double x) { return fabs(x); }
 __device__ __forceinline__ float max_t(float a, float b) { return fmaxf(a, b); }
 __device__ __forceinline__ double max_t(double a, double b) { return fmax(a, b); }
 __device__ __forceinline__ float min_t(float a, float b) { return fminf(a, b); }
+// reciprocal of the joint-space inertia d_i > 0: MUFU.RCP (<= 1 ulp) for float, IEEE for double
+__device__ __forceinline__ float rcp_t(float x) {
+  float r;
+  asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ double rcp_t(double x) { return 1.0 / x; }
 __device__ __forceinline__ double min_t(double a, double b) { return fmin(a, b); }
 
 template <typename T>
@@ -222,6 +229,16 @@ __device__ __forceinline__ void stg_vec6(double* dst, const double* src) {
 template <typename T>
 __device__ __forceinline__ void cp_async_elem(T* smem_dst, const T* gsrc) {
   __pipeline_memcpy_async(smem_dst, gsrc, sizeof(T));
+}
+
+// cooperative global -> shared copy of `words` elements (a multiple of 16 bytes, both
+// sides 16-byte aligned) with 16-byte LDGSTS chunks
+template <typename E>
+__device__ __forceinline__ void stage_async(E* smem_dst, const E* gsrc, int words) {
+  constexpr int per = 16 / sizeof(E);
+  const int chunks = words / per;
+  for (int k = threadIdx.x; k < chunks; k += blockDim.x)
+    __pipeline_memcpy_async(smem_dst + (size_t)k * per, gsrc + (size_t)k * per, 16);
 }
 // TMA bulk store shared -> global (cp.async.bulk, SASS UBLKCP): bytes % 16 == 0, both
 // addresses 16-byte aligned.  The generic-proxy writes to shared memory must be fenced
@@ -367,11 +384,10 @@ struct FkMap {
 };
 
 template <typename T>
-__device__ __forceinline__ void make_fk_map(const Params<T>& P, const BaseState<T>& b, FkMap<T>& m) {
-  const T* su = P.csuc;  // suc_H_i[0]
-  T Rg[9], tg[3], tmp[9];
-  ldn<9>(su, Rg);
-  ldn<3>(su + 9, tg);
+__device__ __forceinline__ void make_fk_map(const T* cst0, const BaseState<T>& b, FkMap<T>& m) {
+  T Rg[9], tg[3], tmp[9];  // suc_H_i[0]: record 0 of the constants
+  ldn<9>(cst0 + C_M0, Rg);
+  ldn<3>(cst0 + C_TPRE, tg);
   mat3_mul(b.R, Rg, tmp);
   // R_T = R_B R_G R_B^T
 #pragma unroll
@@ -444,10 +460,13 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
   const size_t itab_words = ((size_t)P.itab_words + 3) & ~size_t(3);
   T* ws_base = reinterpret_cast<T*>(sm_itab + itab_words);
 
-  // ---- stage the model once per block
-  for (int k = threadIdx.x; k < nL * CREC; k += blockDim.x) sm_cst[k] = P.cst[k];
-  for (int k = threadIdx.x; k < nc * 3; k += blockDim.x) sm_pt[k] = P.pt_pos[k];
-  for (int k = threadIdx.x; k < P.itab_words; k += blockDim.x) sm_itab[k] = P.itab[k];
+  // ---- stage the model once per block: 16-byte cp.async chunks, all in flight at once
+  // (the device blobs are padded to whole chunks by b200sim_model_create)
+  stage_async(sm_cst, P.cst, nL * CREC);
+  stage_async(sm_pt, P.pt_pos, (int)pt_words);
+  stage_async(sm_itab, P.itab, (int)itab_words);
+  __pipeline_commit();
+  __pipeline_wait_prior(0);
   __syncthreads();
 
   const int* parent = sm_itab + P.o_parent;
@@ -520,7 +539,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
       quat_to_dcm(b.qn, b.R);
     }
     FkMap<T> fm;
-    if (P.flags & F_GENERIC_FK) make_fk_map(P, b, fm);
+    if (P.flags & F_GENERIC_FK) make_fk_map(sm_cst, b, fm);
 
     auto write_base_record = [&](const BaseState<T>& bs) {
       if (lane == 0) {
@@ -638,8 +657,8 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
           if (P.iXl) {
             // index 0: Ad((W_H_B suc_H_i[0])^-1)  (api/kin_dyn_parameters.py:417-449)
             T R0[9], p0[3], t[3], X[36];
-            mat3_mul(b.R, P.csuc, R0);
-            mat3_vec(b.R, P.csuc + 9, t);
+            mat3_mul(b.R, sm_cst + C_M0, R0);      // suc_H_i[0] lives in record 0 of the constants
+            mat3_vec(b.R, sm_cst + C_TPRE, t);
             p0[0] = b.p[0] + t[0]; p0[1] = b.p[1] + t[1]; p0[2] = b.p[2] + t[2];
             inverse_adjoint(X, R0, p0);
             stg_vec<36>(P.iXl + env * nL * 36, X);
@@ -901,7 +920,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
             d = dot3(aw, Ul);
             u = tau - dot3(aw, pA);
           }
-          const T dinv = T(1) / d;
+          const T dinv = rcp_t(d);
           stn<3>(ri + O_U, Ul);
           stn<3>(ri + O_U + 3, Ua);
           ri[O_DINV] = dinv;
@@ -1087,7 +1106,6 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
         quat_to_dcm(nb.qn, nb.R);
         b = nb;
       }
-      if (P.flags & F_GENERIC_FK) make_fk_map(P, b, fm);
       const bool want_caches = last && (P.W_H_L || P.W_v);
       if (last && active && lane == 0) {
         stn<4>(P.q_o + env * 4, b.qn);
@@ -1097,8 +1115,8 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
         if (P.W_H_B) store_transform(P.W_H_B + env * 16, b.R, b.p);
         if (P.iXl) {
           T R0[9], p0[3], t[3], X[36];
-          mat3_mul(b.R, P.csuc, R0);
-          mat3_vec(b.R, P.csuc + 9, t);
+          mat3_mul(b.R, sm_cst + C_M0, R0);
+          mat3_vec(b.R, sm_cst + C_TPRE, t);
           p0[0] = b.p[0] + t[0]; p0[1] = b.p[1] + t[1]; p0[2] = b.p[2] + t[2];
           inverse_adjoint(X, R0, p0);
           stg_vec<36>(P.iXl + env * nL * 36, X);
@@ -1127,6 +1145,17 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
         }
       }
       // ========================================================= phase 8: FK of the new state
+      if (!last) {
+        // the next fused step starts like a fresh call: base_orientation normalises the
+        // stored quaternion once more (api/data.py:283-285), bit-identical to repeated steps
+        const T nrm = sqrt_t(b.qn[0] * b.qn[0] + b.qn[1] * b.qn[1] + b.qn[2] * b.qn[2] + b.qn[3] * b.qn[3]);
+        const T inv = T(1) / (nrm + Lim<T>::eps() * (nrm == T(0) ? T(1) : T(0)));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) b.qn[k] *= inv;
+        quat_to_dcm(b.qn, b.R);
+      }
+      if (P.flags & F_GENERIC_FK) make_fk_map(sm_cst, b, fm);
+      __syncwarp();  // every lane has read the base acceleration out of record 0
       if (!last || want_caches) {
         write_base_record(b);
         fk_chain(!last);

@@ -29,8 +29,10 @@ __device__ __forceinline__ BlockCtx<T> stage_model(const Params<T>& P, unsigned 
   c.itab = reinterpret_cast<int*>(c.pt + pt_words);
   const size_t itab_words = ((size_t)P.itab_words + 3) & ~size_t(3);
   T* ws_base = reinterpret_cast<T*>(c.itab + itab_words);
-  for (int k = threadIdx.x; k < P.nL * CREC; k += blockDim.x) c.cst[k] = P.cst[k];
-  for (int k = threadIdx.x; k < P.itab_words; k += blockDim.x) c.itab[k] = P.itab[k];
+  stage_async(c.cst, P.cst, P.nL * CREC);
+  stage_async(c.itab, P.itab, (int)itab_words);
+  __pipeline_commit();
+  __pipeline_wait_prior(0);
   __syncthreads();
   c.parent = c.itab + P.o_parent;
   c.jtypes = c.itab + P.o_jtype;
