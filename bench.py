@@ -316,40 +316,85 @@ def run_b200(args):
         dist.all_reduce(tg, op=dist.ReduceOp.MAX)
         gather_ms = float(tg.item())
 
-    # ---- e2e: public API with pinned host buffers, H2D + step + D2H every step
+    # ---- e2e: public API with pinned HOST buffers; every step = H2D of that step's inputs
+    # (state, contact state, joint force references), js.model.step, D2H of the new state.
+    # The leaves of a step live in ONE flat buffer per direction (one memcpy each way) and
+    # the three stages are double-buffered on three streams, as a host-driven rollout would.
     Ke = max(5, min(args.steps, 50))
-    host = js.data.random_model_data(model, batch_size=B, seed=7 + rank, dtype=dtype, device=dev,
-                                     velocity_representation=js.common.VelRepr.Inertial)
-    names = ["_joint_positions", "_joint_velocities", "_base_quaternion", "_base_linear_velocity",
-             "_base_angular_velocity", "_base_position"]
-    h_in = {k: getattr(host, k).cpu().pin_memory() for k in names}
-    h_in["m"] = host.contact_state["tangential_deformation"].cpu().pin_memory()
-    h_in["tau"] = (10 * torch.rand(B, n, dtype=dtype)).pin_memory()
-    h_out = {k: torch.empty_like(v).pin_memory() for k, v in h_in.items() if k != "tau"}
-    h2d = sum(v.numel() * v.element_size() for v in h_in.values())
-    d2h = sum(v.numel() * v.element_size() for v in h_out.values())
+    r4 = lambda k: (k + 3) & ~3  # noqa: E731
+    in_blocks = [("s", (B, n)), ("sd", (B, n)), ("q", (B, 4)), ("vl", (B, 3)), ("om", (B, 3)), ("p", (B, 3)),
+                 ("m", (B, nc, 3)), ("tau", (B, n))]
+    out_blocks = in_blocks[:-1]
 
-    def e2e_step():
-        d = {k: v.to(dev, non_blocking=True) for k, v in h_in.items()}
-        data = js.data.JaxSimModelData(
-            velocity_representation=js.common.VelRepr.Inertial, _joint_positions=d["_joint_positions"],
-            _joint_velocities=d["_joint_velocities"], _base_quaternion=d["_base_quaternion"],
-            _base_linear_velocity=d["_base_linear_velocity"], _base_angular_velocity=d["_base_angular_velocity"],
-            _base_position=d["_base_position"], contact_state={"tangential_deformation": d["m"]},
-        )
-        o = js.model.step(model, data, joint_force_references=d["tau"])
-        for k in names:
-            h_out[k].copy_(getattr(o, k), non_blocking=True)
-        h_out["m"].copy_(o.contact_state["tangential_deformation"], non_blocking=True)
+    def carve(flat, blocks):
+        views, o = {}, 0
+        for name, shape in blocks:
+            k = int(np.prod(shape))
+            views[name] = flat[o:o + k].view(shape)
+            o += r4(k)
+        return views
 
-    for _ in range(3):
-        e2e_step()
+    n_in = sum(r4(int(np.prod(s))) for _, s in in_blocks)
+    n_out = sum(r4(int(np.prod(s))) for _, s in out_blocks)
+    src = js.data.random_model_data(model, batch_size=B, seed=7 + rank, dtype=dtype, device=dev,
+                                    velocity_representation=js.common.VelRepr.Inertial)
+    h_in = torch.empty(n_in, dtype=dtype).pin_memory()
+    hv = carve(h_in, in_blocks)
+    for k, leaf in (("s", "_joint_positions"), ("sd", "_joint_velocities"), ("q", "_base_quaternion"),
+                    ("vl", "_base_linear_velocity"), ("om", "_base_angular_velocity"), ("p", "_base_position")):
+        hv[k].copy_(getattr(src, leaf).cpu())
+    hv["m"].zero_()
+    hv["tau"].copy_(10 * torch.rand(B, n, dtype=dtype))
+    h_out = [torch.empty(n_out, dtype=dtype).pin_memory() for _ in range(2)]
+    d_in = [torch.empty(n_in, dtype=dtype, device=dev) for _ in range(2)]
+    d_out = [torch.empty(n_out, dtype=dtype, device=dev) for _ in range(2)]
+
+    def mk(views, with_tau):
+        d = js.data.JaxSimModelData(
+            velocity_representation=js.common.VelRepr.Inertial, _joint_positions=views["s"], _joint_velocities=views["sd"],
+            _base_quaternion=views["q"], _base_linear_velocity=views["vl"], _base_angular_velocity=views["om"],
+            _base_position=views["p"], contact_state={"tangential_deformation": views["m"]})
+        return (d, views["tau"]) if with_tau else d
+
+    din = [mk(carve(d_in[j], in_blocks), True) for j in range(2)]
+    dout = [mk(carve(d_out[j], out_blocks), False) for j in range(2)]
+    for d in dout:  # the step does the same device work as the `value` arm: caches are written (not copied back)
+        d._base_transform = torch.empty(B, 4, 4, dtype=dtype, device=dev)
+        d._joint_transforms = torch.empty(B, nL, 6, 6, dtype=dtype, device=dev)
+        d._link_transforms = torch.empty(B, nL, 4, 4, dtype=dtype, device=dev)
+        d._link_velocities = torch.empty(B, nL, 6, dtype=dtype, device=dev)
+    h2d = n_in * h_in.element_size()
+    d2h = n_out * h_in.element_size()
+    s_in, s_cmp, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_cmp = [torch.cuda.Event() for _ in range(2)]
+    ev_out = [torch.cuda.Event() for _ in range(2)]
+
+    def e2e_run(count):
+        for i in range(count):
+            j = i & 1
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(ev_cmp[j])       # the step that last read d_in[j] is done
+                d_in[j].copy_(h_in, non_blocking=True)
+                ev_in[j].record(s_in)
+            with torch.cuda.stream(s_cmp):
+                s_cmp.wait_event(ev_in[j])
+                s_cmp.wait_event(ev_out[j])      # the D2H that last read d_out[j] is done
+                js.model.step(model, din[j][0], joint_force_references=din[j][1], out=dout[j])
+                ev_cmp[j].record(s_cmp)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_cmp[j])
+                h_out[j].copy_(d_out[j], non_blocking=True)
+                ev_out[j].record(s_out)
+
+    e2e_run(4)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(Ke):
-        e2e_step()
-    e1.record()
+    e0.record(s_cmp)
+    e2e_run(Ke)
+    s_cmp.wait_event(ev_out[0])
+    s_cmp.wait_event(ev_out[1])
+    e1.record(s_cmp)
     barrier()
     te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -431,7 +476,7 @@ def run_b200(args):
                      "note": "algorithmic bytes = B_api (SURVEY.md 8d): read state+contact state+tau, write state+contact state+all caches"},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-                "note": "public API js.model.step with pinned host buffers: H2D(state, contact state, tau) + step + D2H(new state, contact state) each step; caches stay on device"},
+                "note": "public API js.model.step with pinned host buffers, every step: one H2D (state + contact state + tau), step, one D2H (new state + contact state); double-buffered over 3 streams; the caches are written on the device like in `value` but not copied back"},
         "gpu_launches": args.steps,
         "eager": {"value": B * world * args.steps / (ms_eager_max * 1e-3), "ms_per_step": ms_eager_max / args.steps,
                   "note": "same K steps launched one by one from Python (host launch latency included)"},

@@ -182,6 +182,23 @@ int b200sim_rnea(const B200SimModel *model, int dtype, int64_t B,
 int b200sim_crba(const B200SimModel *model, int dtype, int64_t B, const void *s, void *M,
                  void *stream);
 
+/* Forward-mode derivative of `nsteps` steps (BASELINE config 5: d(step)/d(link masses,
+ * joint positions, ...)): == jax.jvp(step) of the reference
+ * (tests/test_automatic_differentiation.py:346-420).  float64 only.  Every batched array is
+ * the primal array with one extra trailing axis of size 2: [..., 0] = value, [..., 1] =
+ * tangent (e.g. s is (B,n,2)).  link_mass_tangent: HOST (nL) direction in the space of
+ * LinkParameters.mass (api/kin_dyn_parameters.py:596) or NULL; it enters through
+ * Inertia.to_sixd (math/inertia.py:32-39) with the CoM and the CoM inertia held fixed.
+ * Outputs: value and tangent of every output leaf of b200sim_step (same NULL rules).
+ * Synchronises `stream` once (constant upload); not thread-safe per model. */
+int b200sim_step_jvp(B200SimModel *model, int64_t B, int32_t nsteps,
+                     const double *link_mass_tangent,
+                     const void *s, const void *sd, const void *q_wxyz, const void *v_lin,
+                     const void *omega, const void *p, const void *m_tan, const void *tau_ref,
+                     void *s_o, void *sd_o, void *q_o, void *v_lin_o, void *omega_o, void *p_o,
+                     void *m_tan_o,
+                     void *W_H_B, void *i_X_lam, void *W_H_L, void *W_v_WL, void *stream);
+
 /* Library / build information: "b200sim <abi> sm_100a ..." */
 const char *b200sim_version(void);
 

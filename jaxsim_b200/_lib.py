@@ -75,6 +75,7 @@ EXPORTED_SYMBOLS = (
     "b200sim_aba",
     "b200sim_rnea",
     "b200sim_crba",
+    "b200sim_step_jvp",
 )
 
 _lib = None
@@ -119,6 +120,8 @@ def load() -> C.CDLL:
     lib.b200sim_rnea.restype = C.c_int
     lib.b200sim_crba.argtypes = [vp, C.c_int, C.c_int64, vp, vp, vp]
     lib.b200sim_crba.restype = C.c_int
+    lib.b200sim_step_jvp.argtypes = [vp, C.c_int64, C.c_int32, c_dp] + [vp] * 20
+    lib.b200sim_step_jvp.restype = C.c_int
     _lib = lib
     return lib
 

@@ -588,3 +588,88 @@ def free_floating_mass_matrix(model: JaxSimModel, data: "_data.JaxSimModelData")
         Mt[:, 6:, 6:] = M[:, 6:, 6:]
         M = Mt
     return M.squeeze(0) if data._joint_positions.dim() == 1 else M
+
+
+_JVP_LEAVES = (
+    ("joint_positions", "_joint_positions"), ("joint_velocities", "_joint_velocities"),
+    ("base_quaternion", "_base_quaternion"), ("base_linear_velocity", "_base_linear_velocity"),
+    ("base_angular_velocity", "_base_angular_velocity"), ("base_position", "_base_position"),
+)
+
+
+def step_jvp(
+    model: JaxSimModel,
+    data: "_data.JaxSimModelData",
+    tangents: dict,
+    *,
+    joint_force_references: torch.Tensor | None = None,
+    n_steps: int = 1,
+) -> tuple["_data.JaxSimModelData", "_data.JaxSimModelData"]:
+    """Forward-mode derivative of ``step`` (BASELINE config 5): the counterpart of
+    ``jax.jvp(lambda theta: js.model.step(model(theta), data(theta)), ...)`` checked by the
+    reference in ``tests/test_automatic_differentiation.py:346-420``.
+
+    ``tangents`` maps input names to tangent arrays: any of ``joint_positions``,
+    ``joint_velocities``, ``base_quaternion``, ``base_linear_velocity``,
+    ``base_angular_velocity``, ``base_position`` (inertial-fixed, shapes of the leaves),
+    ``tangential_deformation`` ``(B, nc, 3)``, ``joint_force_references`` ``(B, n)`` and
+    ``link_masses`` ``(nL,)`` -- the ``LinkParameters.mass`` leaf, entering through
+    ``Inertia.to_sixd`` with CoM and CoM-inertia held fixed.
+    Missing entries are zero.  float64, batched data, ``VelRepr`` is irrelevant (no link
+    forces).  Returns ``(data_out, tangent_out)``: the stepped data and a data object whose
+    leaves (state, contact state and caches) hold the directional derivatives."""
+    q = data._base_quaternion
+    if q.dim() != 2 or q.dtype != torch.float64:
+        raise ValueError("step_jvp needs batched float64 data")
+    unknown = set(tangents) - {k for k, _ in _JVP_LEAVES} - {"tangential_deformation", "joint_force_references", "link_masses"}
+    if unknown:
+        raise KeyError(f"unknown tangent inputs: {sorted(unknown)}")
+    dev = q.device
+    dm = model.device_model(dev)
+    B = q.shape[0]
+    nL, n, nc = model.number_of_links(), model.dofs(), model.number_of_collidable_points()
+    soft = isinstance(model.contact_model, SoftContacts)
+
+    def pack(val, tan):
+        tan = torch.zeros_like(val) if tan is None else torch.as_tensor(tan, dtype=torch.float64, device=dev).expand_as(val)
+        return torch.stack([val, tan], dim=-1).contiguous()
+
+    ins = [pack(getattr(data, leaf), tangents.get(name)) for name, leaf in _JVP_LEAVES]
+    m = data.contact_state.get("tangential_deformation") if data.contact_state else None
+    if m is None and soft:
+        m = torch.zeros(B, nc, 3, dtype=torch.float64, device=dev)
+    m_in = pack(m, tangents.get("tangential_deformation")) if m is not None else None
+    tau_in = None
+    if joint_force_references is not None or "joint_force_references" in tangents:
+        tv = torch.zeros(B, n, dtype=torch.float64, device=dev) if joint_force_references is None else torch.as_tensor(
+            joint_force_references, dtype=torch.float64, device=dev).expand(B, n)
+        tau_in = pack(tv, tangents.get("joint_force_references"))
+    dmass = None
+    if "link_masses" in tangents:
+        dmass = np.ascontiguousarray(torch.as_tensor(tangents["link_masses"]).detach().cpu().numpy(), dtype=np.float64)
+        if dmass.shape != (nL,):
+            raise ValueError(dmass.shape, (nL,))
+    new = lambda *shape: torch.empty(*shape, 2, dtype=torch.float64, device=dev)  # noqa: E731
+    outs = [new(B, n), new(B, n), new(B, 4), new(B, 3), new(B, 3), new(B, 3)]
+    m_o = new(B, nc, 3) if soft else None
+    caches = [new(B, 4, 4), new(B, nL, 6, 6), new(B, nL, 4, 4), new(B, nL, 6)]
+    with torch.cuda.device(dev):
+        rc = _lib.load().b200sim_step_jvp(
+            dm.handle, B, int(n_steps), None if dmass is None else dmass.ctypes.data_as(_lib.c_dp),
+            *[_ptr(t) for t in ins], _ptr(m_in), _ptr(tau_in),
+            *[_ptr(t) for t in outs], _ptr(m_o), *[_ptr(t) for t in caches], _stream_ptr(dev),
+        )
+    _lib.check(rc, "b200sim_step_jvp")
+
+    def split(idx):
+        mk = lambda t: None if t is None else t[..., idx].contiguous()  # noqa: E731
+        cs = {"tangential_deformation": mk(m_o)} if soft else {}
+        return _data.JaxSimModelData(
+            velocity_representation=data.velocity_representation,
+            _joint_positions=mk(outs[0]), _joint_velocities=mk(outs[1]), _base_quaternion=mk(outs[2]),
+            _base_linear_velocity=mk(outs[3]), _base_angular_velocity=mk(outs[4]), _base_position=mk(outs[5]),
+            _base_transform=mk(caches[0]), _joint_transforms=mk(caches[1]), _link_transforms=mk(caches[2]),
+            _link_velocities=mk(caches[3]), contact_state=cs,
+        )
+
+    return split(0), split(1)

@@ -40,6 +40,7 @@ struct B200SimModel {
   float *cst_f = nullptr, *csuc_f = nullptr, *pt_f = nullptr;
   double *cst_d = nullptr, *csuc_d = nullptr, *pt_d = nullptr;
   int* itab_d = nullptr;
+  DualD *cst_dd = nullptr, *csuc_dd = nullptr, *pt_dd = nullptr;  // forward-mode AD blobs (value, tangent)
   // tuning
   int tune_G = 0, tune_epb = 0;
   int opt_flags = B200SIM_OPT_TMA_STORE;
@@ -110,7 +111,7 @@ struct Geometry {
 };
 
 int pick_geometry(const B200SimModel* m, int dtype, long long B, Geometry* g) {
-  const size_t ts = dtype == B200SIM_DTYPE_F64 ? 8 : 4;
+  const size_t ts = dtype == 2 ? 16 : (dtype == B200SIM_DTYPE_F64 ? 8 : 4);  // 2: Dual<double>
   const size_t st = static_smem_bytes(m, ts), pe = env_smem_bytes(m, ts);
   const size_t budget = (size_t)m->max_smem_optin - 1024;
   if (st + pe > budget) return B200SIM_E_TOO_LARGE;
@@ -161,6 +162,13 @@ struct Blob<double> {
   static const double* cst(const B200SimModel* m) { return m->cst_d; }
   static const double* csuc(const B200SimModel* m) { return m->csuc_d; }
   static const double* pt(const B200SimModel* m) { return m->pt_d; }
+};
+
+template <>
+struct Blob<DualD> {
+  static const DualD* cst(const B200SimModel* m) { return m->cst_dd; }
+  static const DualD* csuc(const B200SimModel* m) { return m->csuc_dd; }
+  static const DualD* pt(const B200SimModel* m) { return m->pt_dd; }
 };
 
 template <typename T>
@@ -339,6 +347,39 @@ int aba_t(const B200SimModel* m, int dtype, int64_t B, const void* s, const void
 }
 
 }  // namespace
+
+// ---- forward-mode AD (Dual<double>) -------------------------------------------------
+int upload_dual(const std::vector<double>& val, const std::vector<double>& tan, DualD** d) {
+  std::vector<DualD> tmp(((val.size() + 3) & ~size_t(3)) + 4, DualD(0.0, 0.0));
+  for (size_t i = 0; i < val.size(); ++i) tmp[i] = DualD(val[i], tan.empty() ? 0.0 : tan[i]);
+  if (!*d) CK(cudaMalloc((void**)d, tmp.size() * sizeof(DualD)));
+  CK(cudaMemcpy(*d, tmp.data(), tmp.size() * sizeof(DualD), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int launch_dual(const B200SimModel* m, Params<DualD>& P, void* stream) {
+  B200SimModel tuned = *m;  // geometry only: lanes fixed to the instantiated width
+  tuned.tune_G = 8;
+  while (tuned.tune_G > 1 && tuned.tune_G / 2 >= m->nL) tuned.tune_G /= 2;
+  Geometry g;
+  int rc = pick_geometry(&tuned, 2, P.B, &g);
+  tuned.cst_h.clear();
+  if (rc) return rc;
+  P.envs_per_block = g.epb;
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev != m->device) CK(cudaSetDevice(m->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (g.G) {
+    case 1: rc = launch_g<DualD, 1>(P, g, st); break;
+    case 2: rc = launch_g<DualD, 2>(P, g, st); break;
+    case 4: rc = launch_g<DualD, 4>(P, g, st); break;
+    case 8: rc = launch_g<DualD, 8>(P, g, st); break;
+    default: rc = B200SIM_E_INVALID;
+  }
+  if (dev != m->device) cudaSetDevice(dev);
+  return rc;
+}
 
 extern "C" {
 
@@ -525,6 +566,7 @@ void b200sim_model_destroy(B200SimModel* m) {
   cudaSetDevice(m->device);
   cudaFree(m->cst_f); cudaFree(m->cst_d); cudaFree(m->csuc_f); cudaFree(m->csuc_d);
   cudaFree(m->pt_f); cudaFree(m->pt_d); cudaFree(m->itab_d);
+  cudaFree(m->cst_dd); cudaFree(m->csuc_dd); cudaFree(m->pt_dd);
   cudaSetDevice(prev);
   delete m;
 }
@@ -641,6 +683,54 @@ int b200sim_crba(const B200SimModel* m, int dtype, int64_t B, const void* s, voi
   if (!M || (m->n > 0 && !s)) return B200SIM_E_INVALID;
   if (dtype == 0) return crba_t<float>(m, dtype, B, s, M, stream);
   return crba_t<double>(m, dtype, B, s, M, stream);
+}
+
+int b200sim_step_jvp(B200SimModel* m, int64_t B, int32_t nsteps, const double* link_mass_tangent, const void* s,
+                     const void* sd, const void* q, const void* vlin, const void* omega, const void* p, const void* mt,
+                     const void* tau, void* s_o, void* sd_o, void* q_o, void* vlin_o, void* omega_o, void* p_o,
+                     void* m_o, void* W_H_B, void* iXl, void* W_H_L, void* W_v, void* stream) {
+  if (!m || B < 0 || nsteps < 1) return B200SIM_E_INVALID;
+  if (B == 0) return 0;
+  if (!q || !vlin || !omega || !p || !q_o || !vlin_o || !omega_o || !p_o) return B200SIM_E_INVALID;
+  if (m->n > 0 && (!s || !sd || !s_o || !sd_o)) return B200SIM_E_INVALID;
+  // (value, tangent) image of the model constants for the requested mass direction:
+  // d(mass) = dm, d(D_link) = dm (|c|^2 1 - c c^T); everything else is constant
+  std::vector<double> tan(m->cst_h.size(), 0.0);
+  if (link_mass_tangent) {
+    for (int i = 0; i < m->nL; ++i) {
+      const double* c = m->cst_h.data() + (size_t)i * CREC;
+      double* tc = tan.data() + (size_t)i * CREC;
+      const double dm = link_mass_tangent[i];
+      const double cx = c[C_COM], cy = c[C_COM + 1], cz = c[C_COM + 2];
+      const double cc = cx * cx + cy * cy + cz * cz;
+      tc[C_MASS] = dm;
+      tc[C_DL + 0] = dm * (cc - cx * cx); tc[C_DL + 1] = -dm * cx * cy; tc[C_DL + 2] = -dm * cx * cz;
+      tc[C_DL + 3] = dm * (cc - cy * cy); tc[C_DL + 4] = -dm * cy * cz; tc[C_DL + 5] = dm * (cc - cz * cz);
+    }
+  }
+  int prev = 0;
+  CK(cudaGetDevice(&prev));
+  CK(cudaSetDevice(m->device));
+  CK(cudaStreamSynchronize((cudaStream_t)stream));  // the blobs may still be in use by a previous JVP
+  int rc = upload_dual(m->cst_h, tan, &m->cst_dd);
+  if (!rc && !m->csuc_dd) rc = upload_dual(m->csuc_h, {}, &m->csuc_dd);
+  if (!rc && !m->pt_dd) rc = upload_dual(m->pt_h, {}, &m->pt_dd);
+  cudaSetDevice(prev);
+  if (rc) return rc;
+  Params<DualD> P;
+  std::memset(&P, 0, sizeof(P));
+  fill_model_params(m, P);
+  P.flags &= ~F_TMA_STORE;
+  P.B = B;
+  typedef DualD T;
+  P.s = (const T*)s; P.sd = (const T*)sd; P.q = (const T*)q; P.vlin = (const T*)vlin; P.omega = (const T*)omega;
+  P.p = (const T*)p; P.m = (const T*)mt; P.tau = (const T*)tau;
+  P.s_o = (T*)s_o; P.sd_o = (T*)sd_o; P.q_o = (T*)q_o; P.vlin_o = (T*)vlin_o; P.omega_o = (T*)omega_o;
+  P.p_o = (T*)p_o; P.m_o = (T*)m_o;
+  P.W_H_B = (T*)W_H_B; P.iXl = (T*)iXl; P.W_H_L = (T*)W_H_L; P.W_v = (T*)W_v;
+  P.nsteps = nsteps;
+  P.mode = MODE_STEP;
+  return launch_dual(m, P, stream);
 }
 
 }  // extern "C"

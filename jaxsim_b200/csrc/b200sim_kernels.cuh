@@ -32,6 +32,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "b200sim_dual.cuh"
+
 namespace b200sim {
 
 // ------------------------------------------------------------------------------------
@@ -126,6 +128,7 @@ struct Params {
 template <typename T> struct Lim;
 template <> struct Lim<float> { static __device__ __forceinline__ float eps() { return 1.1920928955078125e-07f; } };
 template <> struct Lim<double> { static __device__ __forceinline__ double eps() { return 2.220446049250313e-16; } };
+template <> struct Lim<DualD> { static __device__ __forceinline__ DualD eps() { return DualD(2.220446049250313e-16); } };
 
 __device__ __forceinline__ void sincos_t(float x, float* s, float* c) { sincosf(x, s, c); }
 __device__ __forceinline__ void sincos_t(double x, double* s, double* c) { sincos(x, s, c); }
@@ -214,6 +217,11 @@ __device__ __forceinline__ void stg_vec(double* dst, const double* src) {
 #pragma unroll
   for (int k = 0; k < N; k += 2) *reinterpret_cast<double2*>(dst + k) = make_double2(src[k], src[k + 1]);
 }
+template <int N>
+__device__ __forceinline__ void stg_vec(DualD* dst, const DualD* src) {
+#pragma unroll
+  for (int k = 0; k < N; ++k) *reinterpret_cast<double2*>(dst + k) = make_double2(src[k].v, src[k].d);
+}
 // 6-vector rows: (B,nL,6) rows are 24 B (float, 8-byte aligned) / 48 B (double, 16-byte aligned)
 __device__ __forceinline__ void stg_vec6(float* dst, const float* src) {
 #pragma unroll
@@ -223,6 +231,8 @@ __device__ __forceinline__ void stg_vec6(double* dst, const double* src) {
 #pragma unroll
   for (int k = 0; k < 6; k += 2) *reinterpret_cast<double2*>(dst + k) = make_double2(src[k], src[k + 1]);
 }
+
+__device__ __forceinline__ void stg_vec6(DualD* dst, const DualD* src) { stg_vec<6>(dst, src); }
 
 // ---- async copies -------------------------------------------------------------------
 // one element global -> shared without a register round trip (LDGSTS)
