@@ -347,6 +347,8 @@ def test_step_jvp_matches_finite_differences(name, what, cuda_device):
     for oname, pname in H.LEAVES:
         fd = (getattr(fp, oname) - getattr(fm, oname)) / (2 * eps)
         got = getattr(dout, pname).cpu().numpy()
+        if fd.size == 0:
+            continue
         scale = max(float(np.abs(fd).max()), 1e-3)
         worst[oname] = float(np.abs(got - fd).max()) / scale
     fd = (fp.tangential_deformation - fm.tangential_deformation) / (2 * eps)
