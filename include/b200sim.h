@@ -168,6 +168,20 @@ int b200sim_aba(const B200SimModel *model, int dtype, int64_t B,
                 const void *omega, const void *p, const void *tau, const void *f_ext,
                 void *W_vd_WB, void *sdd, void *stream);
 
+/* State derivative == vmapped ode.system_dynamics (api/ode.py:174-225) in inertial-fixed
+ * representation: soft-contact forces of the given state, ABA with the given RESULTANT joint
+ * torques tau (B,n) or NULL (no actuation model here, like the reference's integrators
+ * receive joint_torques), inertial-fixed link forces f_ext or NULL.
+ * out: pd (B,3) base position derivative, qd (B,4) quaternion derivative (Baumgarte K = 1,
+ * api/ode.py:134-171), W_vd (B,6) base acceleration, sdd (B,n), md (B,nc,3) derivative of
+ * the tangential deformation (any of pd, qd, md may be NULL).  Building block of the
+ * RK4 integrators (api/integrators.py:91-263). */
+int b200sim_dynamics(const B200SimModel *model, int dtype, int64_t B,
+                     const void *s, const void *sd, const void *q_wxyz, const void *v_lin,
+                     const void *omega, const void *p, const void *m_tan, const void *tau,
+                     const void *f_ext, void *pd, void *qd, void *W_vd, void *sdd, void *md,
+                     void *stream);
+
 /* Inverse dynamics == vmapped rbda.rnea (rbda/rnea.py:12-238).  in: state as above,
  * W_vd_WB (B,6) inertial-fixed base acceleration or NULL (zeros), sdd (B,n) or NULL,
  * f_ext (B,nL,6) inertial-fixed link forces or NULL.  out: W_f_B (B,6) the inertial-fixed

@@ -76,6 +76,7 @@ EXPORTED_SYMBOLS = (
     "b200sim_rnea",
     "b200sim_crba",
     "b200sim_step_jvp",
+    "b200sim_dynamics",
 )
 
 _lib = None
@@ -122,6 +123,8 @@ def load() -> C.CDLL:
     lib.b200sim_crba.restype = C.c_int
     lib.b200sim_step_jvp.argtypes = [vp, C.c_int64, C.c_int32, c_dp] + [vp] * 20
     lib.b200sim_step_jvp.restype = C.c_int
+    lib.b200sim_dynamics.argtypes = [vp, C.c_int, C.c_int64] + [vp] * 15
+    lib.b200sim_dynamics.restype = C.c_int
     _lib = lib
     return lib
 

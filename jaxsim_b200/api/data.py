@@ -205,6 +205,7 @@ class JaxSimModelData:
         *,
         contact_state: dict | None = None,
         validate: bool = False,
+        _inertial_base_velocity: tuple | None = None,
     ) -> "JaxSimModelData":
         """``JaxSimModelData.replace`` (``api/data.py:406-523``): new object with the given
         leaves replaced, quaternion normalised and all caches recomputed."""
@@ -220,7 +221,10 @@ class JaxSimModelData:
         sd = pick(joint_velocities, self._joint_velocities)
         q = pick(base_quaternion, self._base_quaternion)
         p = pick(base_position, self._base_position)
-        if base_linear_velocity is None and base_angular_velocity is None:
+        if _inertial_base_velocity is not None:
+            vl = pick(_inertial_base_velocity[0], None)
+            om = pick(_inertial_base_velocity[1], None)
+        elif base_linear_velocity is None and base_angular_velocity is None:
             vl = pick(None, self._base_linear_velocity)
             om = pick(None, self._base_angular_velocity)
         else:

@@ -180,8 +180,8 @@ class JaxSimModel:
         if contact_params is None:
             contact_params = contact_model._parameters_class()
         integrator = integrator if integrator is not None else IntegratorType.SemiImplicitEuler
-        if integrator != IntegratorType.SemiImplicitEuler:
-            raise NotImplementedError("only IntegratorType.SemiImplicitEuler is on the hot path")
+        if integrator == IntegratorType.RungeKutta4Fast:
+            raise NotImplementedError("IntegratorType.RungeKutta4Fast is not implemented")
         return cls(
             model_name=model_name,
             time_step=float(time_step) if time_step is not None else 0.001,
@@ -444,6 +444,10 @@ def step(
         The new ``JaxSimModelData`` (same velocity representation; new tensors unless
         ``out`` is given: the input is not modified, like the reference's immutable pytrees).
     """
+    if model.integrator == IntegratorType.RungeKutta4:
+        from .integrators import step_rk4
+
+        return step_rk4(model, data, link_forces=link_forces, joint_force_references=joint_force_references)
     return _step_impl(model, data, 1, link_forces, joint_force_references, update_caches, out)
 
 
@@ -465,6 +469,8 @@ def step_n(
     results are identical to calling ``step`` ``n_steps`` times."""
     if n_steps < 1:
         raise ValueError(n_steps)
+    if model.integrator != IntegratorType.SemiImplicitEuler:
+        raise NotImplementedError("step_n fuses SemiImplicitEuler steps only")
     return _step_impl(model, data, int(n_steps), link_forces, joint_force_references, update_caches, out)
 
 

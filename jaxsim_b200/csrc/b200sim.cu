@@ -733,4 +733,35 @@ int b200sim_step_jvp(B200SimModel* m, int64_t B, int32_t nsteps, const double* l
   return launch_dual(m, P, stream);
 }
 
+int b200sim_dynamics(const B200SimModel* m, int dtype, int64_t B, const void* s, const void* sd, const void* q,
+                     const void* vlin, const void* omega, const void* p, const void* mt, const void* tau,
+                     const void* fext, void* pd, void* qd, void* W_vd, void* sdd, void* md, void* stream) {
+  if (!m || B < 0 || (dtype != 0 && dtype != 1)) return B200SIM_E_INVALID;
+  if (B == 0) return 0;
+  if (!q || !vlin || !omega || !p || !W_vd) return B200SIM_E_INVALID;
+  if (m->n > 0 && (!s || !sd || !sdd)) return B200SIM_E_INVALID;
+  if (dtype == 0) {
+    Params<float> P;
+    std::memset(&P, 0, sizeof(P));
+    fill_model_params(m, P);
+    typedef float T;
+    P.B = B;
+    P.s = (const T*)s; P.sd = (const T*)sd; P.q = (const T*)q; P.vlin = (const T*)vlin; P.omega = (const T*)omega;
+    P.p = (const T*)p; P.m = (const T*)mt; P.tau = (const T*)tau; P.fext = (const T*)fext;
+    P.p_o = (T*)pd; P.q_o = (T*)qd; P.avd = (T*)W_vd; P.sdd_o = (T*)sdd; P.m_o = (T*)md;
+    P.nsteps = 1; P.mode = MODE_DYN;
+    return launch(m, P, dtype, stream);
+  }
+  Params<double> P;
+  std::memset(&P, 0, sizeof(P));
+  fill_model_params(m, P);
+  typedef double T;
+  P.B = B;
+  P.s = (const T*)s; P.sd = (const T*)sd; P.q = (const T*)q; P.vlin = (const T*)vlin; P.omega = (const T*)omega;
+  P.p = (const T*)p; P.m = (const T*)mt; P.tau = (const T*)tau; P.fext = (const T*)fext;
+  P.p_o = (T*)pd; P.q_o = (T*)qd; P.avd = (T*)W_vd; P.sdd_o = (T*)sdd; P.m_o = (T*)md;
+  P.nsteps = 1; P.mode = MODE_DYN;
+  return launch(m, P, dtype, stream);
+}
+
 }  // extern "C"

@@ -87,7 +87,7 @@ constexpr int C_SMAX = 49;
 constexpr int C_KC = 50;    // friction_static
 constexpr int C_KV = 51;    // friction_viscous
 
-enum Mode : int { MODE_STEP = 0, MODE_FK = 1, MODE_ABA = 2 };
+enum Mode : int { MODE_STEP = 0, MODE_FK = 1, MODE_ABA = 2, MODE_DYN = 3 };
 enum Flags : int {
   F_SUC_NONID = 1,   // some suc_H_i[i>=1] is not the identity
   F_GENERIC_FK = 2,  // suc_H_i[0] != I or fixed base: FK poses differ from the ABA chain
@@ -497,7 +497,8 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
   T* ptws = ws + (size_t)nL * REC;
   const long long stride = (long long)gridDim.x * P.envs_per_block;
   const T dt = P.dt;
-  const bool soft = (P.mode == MODE_STEP) && (P.contact_model == 1) && nc > 0;
+  const bool with_contacts = (P.mode == MODE_STEP) || (P.mode == MODE_DYN);
+  const bool soft = with_contacts && (P.contact_model == 1) && nc > 0;
   const bool tma = (P.flags & F_TMA_STORE) != 0;
 
   // the number of loop trips is uniform across the block so that __syncwarp() is safe
@@ -518,7 +519,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
       if (P.tau) cp_async_elem(ri + O_TREF, P.tau + env * n + (i - 1));
       else ri[O_TREF] = T(0);
     }
-    if (P.mode == MODE_STEP) {
+    if (with_contacts) {
       for (int k = lane; k < nc; k += G) {
         T* pw = ptws + (size_t)k * PTREC + PT_M;
         if (P.m) {
@@ -745,16 +746,26 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
           }
           stn<3>(pw + PT_F, f);
           stn<3>(pw + PT_LEV, lev);
-          // m+ = m + dt * m_dot (api/integrators.py:67-71); stays on chip between steps
-          m[0] += dt * md[0]; m[1] += dt * md[1]; m[2] += dt * md[2];
-          stn<3>(pw + PT_M, m);
-          if (last && active && P.m_o) {
-            T* mo = P.m_o + (env * nc + k) * 3;
-            mo[0] = m[0]; mo[1] = m[1]; mo[2] = m[2];
+          if (P.mode == MODE_DYN) {
+            // system_dynamics: the contact-state derivative itself (api/ode.py:174-225)
+            if (active && P.m_o) {
+              T* mo = P.m_o + (env * nc + k) * 3;
+              mo[0] = md[0]; mo[1] = md[1]; mo[2] = md[2];
+            }
+          } else {
+            // m+ = m + dt * m_dot (api/integrators.py:67-71); stays on chip between steps
+            m[0] += dt * md[0]; m[1] += dt * md[1]; m[2] += dt * md[2];
+            stn<3>(pw + PT_M, m);
+            if (last && active && P.m_o) {
+              T* mo = P.m_o + (env * nc + k) * 3;
+              mo[0] = m[0]; mo[1] = m[1]; mo[2] = m[2];
+            }
           }
         }
       } else if (P.mode == MODE_STEP && last && P.m_o && P.m && active) {
         for (int k = lane; k < nc * 3; k += G) P.m_o[env * nc * 3 + k] = P.m[env * nc * 3 + k];
+      } else if (P.mode == MODE_DYN && P.m_o && active) {
+        for (int k = lane; k < nc * 3; k += G) P.m_o[env * nc * 3 + k] = T(0);
       }
       __syncwarp();
 
@@ -842,7 +853,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
           stn<6>(ri + O_C, cc);
           const T tref = ri[O_TREF];
           T tau;
-          if (P.mode == MODE_ABA) {
+          if (P.mode != MODE_STEP) {
             tau = tref;
           } else {
             // api/actuation_model.py:7-126
@@ -1076,7 +1087,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
 #pragma unroll
         for (int k = 0; k < 6; ++k) Wa[k] = T(0);
       }
-      if (P.mode == MODE_ABA) break;
+      if (P.mode != MODE_STEP) break;
 
       // ========================================================= phase 7: semi-implicit Euler
       // (api/integrators.py:14-88), base part replicated in every lane
@@ -1174,9 +1185,24 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
       __syncwarp();
     }  // steps
 
-    if (P.mode == MODE_ABA) {
+    if (P.mode != MODE_STEP) {
       if (active) {
         if (lane == 0) stn<6>(P.avd + env * 6, Wa);
+        if (lane == 0 && P.mode == MODE_DYN) {
+          // system_position_dynamics (api/ode.py:134-171): Baumgarte K = 1.0
+          T pd[3];
+          cross3(b.w, b.p, pd);
+          pd[0] += b.vlin[0]; pd[1] += b.vlin[1]; pd[2] += b.vlin[2];
+          const T nw = sqrt_t(dot3(b.w, b.w));
+          const T nq = sqrt_t(b.qn[0] * b.qn[0] + b.qn[1] * b.qn[1] + b.qn[2] * b.qn[2] + b.qn[3] * b.qn[3]);
+          const T v0 = nw * (T(1) - nq);
+          const T qw = b.qn[0], qx = b.qn[1], qy = b.qn[2], qz = b.qn[3];
+          const T wx = b.w[0], wy = b.w[1], wz = b.w[2];
+          const T qd[4] = {T(0.5) * (qw * v0 - qx * wx - qy * wy - qz * wz), T(0.5) * (qx * v0 + qw * wx + qz * wy - qy * wz),
+                           T(0.5) * (qy * v0 - qz * wx + qw * wy + qx * wz), T(0.5) * (qz * v0 + qy * wx - qx * wy + qw * wz)};
+          if (P.p_o) stn<3>(P.p_o + env * 3, pd);
+          if (P.q_o) stn<4>(P.q_o + env * 4, qd);
+        }
         for (int i = 1 + lane; i < nL; i += G) P.sdd_o[env * n + (i - 1)] = ws[(size_t)i * REC + O_SDD];
       }
       __syncwarp();

@@ -865,3 +865,64 @@ def _qmul(a, b):
         ],
         -1,
     )
+
+
+# =============================================================================
+# api/ode.py:134-225 + api/integrators.py:91-156  (RK4)
+# =============================================================================
+
+
+def system_dynamics(model: OracleModel, data: OracleData, W_f_L_external, tau_total) -> dict:
+    """``ode.system_dynamics`` (``api/ode.py:174-225``) in inertial-fixed representation,
+    with ``system_position_dynamics`` (``:134-171``, Baumgarte K = 1.0)."""
+    W_vd_WB, sdd, m_dot = system_acceleration(model, data, W_f_L_external, tau_total)
+    W_w = data.base_angular_velocity
+    W_pd_B = data.base_linear_velocity + np.einsum("bij,bj->bi", wedge(W_w), data.base_position)
+    W_Qd_B = quaternion_derivative(data.base_orientation, W_w, K=1.0)
+    return dict(
+        base_position=W_pd_B, base_quaternion=W_Qd_B, joint_positions=data.joint_velocities,
+        base_linear_velocity=W_vd_WB[:, 0:3], base_angular_velocity=W_vd_WB[:, 3:6], joint_velocities=sdd,
+        tangential_deformation=m_dot,
+    )
+
+
+def rk4_integration(model: OracleModel, data: OracleData, W_f_L_external, tau_total) -> OracleData:
+    """``rk4_integration`` (``api/integrators.py:91-156``)."""
+    dtype = data.joint_positions.dtype
+    dt = dtype.type(model.time_step)
+    qn = safe_norm(data.base_quaternion, axis=-1)
+    q0 = data.base_quaternion / np.where(qn == 0, 1.0, qn)[:, None]
+    x0 = dict(
+        base_position=data.base_position, base_quaternion=q0, joint_positions=data.joint_positions,
+        base_linear_velocity=data.base_linear_velocity, base_angular_velocity=data.base_angular_velocity,
+        joint_velocities=data.joint_velocities, tangential_deformation=data.tangential_deformation,
+    )
+
+    def f(x):
+        d = data_replace(model, x["joint_positions"], x["joint_velocities"], x["base_quaternion"],
+                         x["base_linear_velocity"], x["base_angular_velocity"], x["base_position"],
+                         x["tangential_deformation"])
+        return system_dynamics(model, d, W_f_L_external, tau_total)
+
+    mid = lambda x, k: {n: x[n] + (0.5 * dt) * k[n] for n in x}  # noqa: E731
+    fin = lambda x, k: {n: x[n] + dt * k[n] for n in x}  # noqa: E731
+    k1 = f(x0)
+    k2 = f(mid(x0, k1))
+    k3 = f(mid(x0, k2))
+    k4 = f(fin(x0, k3))
+    dxdt = {n: (k1[n] + 2 * k2[n] + 2 * k3[n] + k4[n]) / 6 for n in x0}
+    xf = fin(x0, dxdt)
+    return data_replace(model, xf["joint_positions"], xf["joint_velocities"], xf["base_quaternion"],
+                        xf["base_linear_velocity"], xf["base_angular_velocity"], xf["base_position"],
+                        xf["tangential_deformation"])
+
+
+def step_rk4(model: OracleModel, data: OracleData, link_forces_inertial=None, joint_force_references=None) -> OracleData:
+    """``js.model.step`` with ``IntegratorType.RungeKutta4`` (``api/model.py:2601-2681``)."""
+    B = data.joint_positions.shape[0]
+    dtype = data.joint_positions.dtype
+    nL, n = model.number_of_links(), model.dofs()
+    W_f = np.zeros((B, nL, 6), dtype=dtype) if link_forces_inertial is None else np.asarray(link_forces_inertial, dtype=dtype)
+    tau_ref = np.zeros((B, n), dtype=dtype) if joint_force_references is None else np.asarray(joint_force_references, dtype=dtype)
+    tau_total = compute_resultant_torques(model, data.joint_positions, data.joint_velocities, tau_ref)
+    return rk4_integration(model, data, W_f, tau_total)

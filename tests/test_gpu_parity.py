@@ -357,3 +357,41 @@ def test_step_jvp_matches_finite_differences(name, what, cuda_device):
         worst["tangential_deformation"] = float(np.abs(got - fd).max()) / max(float(np.abs(fd).max()), 1e-3)
     bad = {k: v for k, v in worst.items() if not v <= 2e-5}
     assert not bad, (bad, worst)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("name", ["icub_like", "double_pendulum", "box", "cartpole"])
+def test_step_rk4(name, dtype, cuda_device):
+    """IntegratorType.RungeKutta4 (api/integrators.py:91-156): 4 system_dynamics launches
+    + host-side combination == oracle rk4; also pins b200sim_dynamics against the oracle."""
+    import torch
+
+    model = H.build_model(name, integrator=js.model.IntegratorType.RungeKutta4)
+    om = H.oracle_model(model)
+    B = 17
+    od = O.random_model_data(om, B, seed=47, in_contact=(name in ("icub_like", "box")))
+    rng = np.random.default_rng(9)
+    tau = 5 * rng.uniform(-1, 1, size=(B, om.dofs()))
+    td = _dtype(dtype)
+    pd = H.to_product(model, od, td, cuda_device)
+    t = lambda a: torch.as_tensor(a, dtype=td, device=cuda_device)  # noqa: E731
+    # the state derivative itself
+    tau_tot = O.compute_resultant_torques(om, od.joint_positions, od.joint_velocities, tau)
+    ref_k = O.system_dynamics(om, od, np.zeros((B, om.number_of_links(), 6)), tau_tot)
+    x = dict(base_position=pd._base_position, base_quaternion=pd._base_quaternion, joint_positions=pd._joint_positions,
+             base_linear_velocity=pd._base_linear_velocity, base_angular_velocity=pd._base_angular_velocity,
+             joint_velocities=pd._joint_velocities, contact_state=pd.contact_state)
+    tt = js.ode.compute_resultant_torques(model, pd, joint_force_references=t(tau))
+    if om.dofs():
+        assert H.rel_err(tt.cpu().numpy(), tau_tot) <= H.RTOL[dtype]
+    k = js.ode.system_dynamics(model, x, joint_torques=tt)
+    rt = H.RTOL[dtype]
+    for key in ("base_position", "base_quaternion", "joint_positions", "base_linear_velocity", "base_angular_velocity", "joint_velocities"):
+        if ref_k[key].size:
+            assert H.rel_err(k[key].cpu().numpy(), ref_k[key]) <= rt, key
+    if ref_k["tangential_deformation"].size:
+        assert H.rel_err(k["contact_state"]["tangential_deformation"].cpu().numpy(), ref_k["tangential_deformation"]) <= rt
+    # one RK4 step through the public step()
+    ref = O.step_rk4(om, od, joint_force_references=tau)
+    out = js.model.step(model, pd, joint_force_references=t(tau))
+    H.compare_data(out, ref, rt, f"rk4 {name} {dtype}")
