@@ -56,6 +56,8 @@ def parse():
     ap.add_argument("--lanes", type=int, default=0, help="lanes per env (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-caches", action="store_true", help="diagnostic: do not materialise the cached transforms (B_min traffic)")
+    ap.add_argument("--skip-cache", default="", help="diagnostic: letters of caches NOT to write: X (joint transforms), H (link transforms), V (link velocities), B (base transform)")
+    ap.add_argument("--out-ring", type=int, default=0, help="diagnostic: number of distinct output buffer sets (0 = same as the input ring)")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
     ap.add_argument("--no-tma", action="store_true", help="128-bit stores instead of TMA bulk stores for the joint adjoints")
     ap.add_argument("--profile", action="store_true", help="cudaProfilerStart/Stop around the eager timed region (ncu --profile-from-start off)")
@@ -249,10 +251,17 @@ def run_b200(args):
         # preallocated outputs (`out=`): the step then performs no allocation and is capturable
         outs = [js.model.step(model, datas[r], joint_force_references=taus[r], update_caches=not args.no_caches) for r in range(ring)]
 
+        for o in outs:
+            if "X" in args.skip_cache: o._joint_transforms = None
+            if "H" in args.skip_cache: o._link_transforms = None
+            if "V" in args.skip_cache: o._link_velocities = None
+            if "B" in args.skip_cache: o._base_transform = None
+        oring = args.out_ring if args.out_ring > 0 else ring
+
         def run(count):
             o = None
             for i in range(count):
-                o = js.model.step(model, datas[i % ring], joint_force_references=taus[i % ring], out=outs[i % ring],
+                o = js.model.step(model, datas[i % ring], joint_force_references=taus[i % ring], out=outs[i % oring],
                                   update_caches=not args.no_caches)
             return o
 

@@ -376,8 +376,11 @@ def _step_impl(model, data, n_steps, link_forces, joint_force_references, update
         if soft:
             o["m"] = out.contact_state["tangential_deformation"]
         if update_caches:
-            o.update(W_H_B=out._base_transform, iXl=out._joint_transforms, W_H_L=out._link_transforms,
-                     W_v=out._link_velocities)
+            # caches left as None in `out` are not materialised
+            for key, buf in (("W_H_B", out._base_transform), ("iXl", out._joint_transforms),
+                             ("W_H_L", out._link_transforms), ("W_v", out._link_velocities)):
+                if buf is not None:
+                    o[key] = buf
         if o["q"].shape != (B, 4) or o["q"].dtype != dtype or o["q"].device != dev:
             raise ValueError("`out` does not match the batch/dtype/device of `data`")
         if any(v is None or not v.is_contiguous() for v in o.values()):
