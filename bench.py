@@ -140,66 +140,49 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU arm
-def _oracle_setup(model_name, B, seed, dtype_np):
+def cpu_oracle_throughput(model_name, batch, reps, threads):
+    """The reference's CPU implementation of the path.  JAX/jaxsim cannot be installed
+    offline, so this is the oracle PORT: the plain-C restatement
+    (oracle/c/jaxsim_oracle.c, float64 = the reference's default dtype, dense 6x6 algebra as
+    in the reference) on `threads` POSIX threads, each stepping a slice of the batch."""
+    from oracle import c_oracle as CO
     from oracle import jaxsim_oracle as O
     from tests import helpers as H
 
     model = H.build_model(model_name)
     om = H.oracle_model(model)
-    od = O.random_model_data(om, B, seed=seed, dtype=dtype_np)
-    return O, om, od
-
-
-def _cpu_worker(args):
-    model_name, B, seed, dtype_name, reps = args
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
-    dtype_np = np.float32 if dtype_name == "f32" else np.float64
-    O, om, od = _oracle_setup(model_name, B, seed, dtype_np)
-    O.step(om, od)  # warm
+    od = O.random_model_data(om, batch, seed=100)
+    tau = 10 * np.random.default_rng(0).uniform(size=(batch, om.dofs()))
+    CO.step(om, od, joint_force_references=tau, nthreads=threads)  # warm (also builds the library if needed)
     t0 = time.perf_counter()
     for _ in range(reps):
-        od2 = O.step(om, od)
-    return time.perf_counter() - t0, float(od2.joint_positions.sum()) if od2.joint_positions.size else 0.0
-
-
-def cpu_oracle_throughput(model_name, dtype_name, sample_envs, reps, procs):
-    """The NumPy oracle port on `procs` host processes, each stepping sample_envs/procs envs."""
-    import multiprocessing as mp
-
-    per = max(1, sample_envs // procs)
-    ctx = mp.get_context("fork")
-    with ctx.Pool(procs) as pool:
-        t0 = time.perf_counter()
-        res = pool.map(_cpu_worker, [(model_name, per, 100 + i, dtype_name, reps) for i in range(procs)])
-        wall = time.perf_counter() - t0
-    busy = max(r[0] for r in res)
-    return per * procs * reps / busy, per * procs, busy, wall
+        out = CO.step(om, od, joint_force_references=tau, nthreads=threads)
+    busy = time.perf_counter() - t0
+    assert np.all(np.isfinite(out.joint_positions))
+    return batch * reps / busy, busy
 
 
 def run_reference(args):
-    """`--impl reference`: the reference's CPU implementation of the path.  JAX/jaxsim are
-    not installable offline, so this times the oracle PORT (NumPy restatement)
-    on all host cores; each step = a bounded sample of the workload."""
+    """`--impl reference`: see cpu_oracle_throughput.  One step = the full batch of the
+    workload on all host cores; K steps, bounded to a few seconds."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    procs = max(1, min(cores, 64))
-    sample = min(args.batch, 64 * procs)
-    # warmup + timed inside the workers; K steps each
+    threads = max(1, min(os.cpu_count() or 1, 256))
     t = time.perf_counter()
-    for _ in range(max(0, min(args.warmup, 1))):
-        cpu_oracle_throughput(args.model, args.dtype, sample, 1, procs)
-    K = max(1, min(args.steps, 20))
-    value, n_envs, busy, wall = cpu_oracle_throughput(args.model, args.dtype, sample, K, procs)
+    K = max(1, min(args.steps, 50))
+    W = max(0, min(args.warmup, 3))
+    if W:
+        cpu_oracle_throughput(args.model, args.batch, W, threads)
+    value, busy = cpu_oracle_throughput(args.model, args.batch, K, threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
-        "warmup": args.warmup, "ms_per_step": 1e3 * busy / K, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic (random_model_data distribution, NumPy Philox)",
+        "warmup": W, "ms_per_step": 1e3 * busy / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic (random_model_data distribution, NumPy Philox)",
         "config": {"workload": WORKLOAD, "model": args.model, "batch_per_gpu": args.batch, "dt": 1e-3,
-                   "note": "reference arm = NumPy oracle port of the jaxsim step (JAX not installable offline)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
-                         "sample": f"{n_envs} of {args.batch} envs per step, {K} steps, {procs} processes"},
+                   "note": "reference arm = plain-C oracle port of the jaxsim step (JAX is not installable offline); float64 like the reference's default"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"full {args.batch}-env batch x {K} steps on {threads} threads (C oracle port)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t,
     }
@@ -463,12 +446,10 @@ def run_b200(args):
 
     cpu = None
     if not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        procs = max(1, min(cores, 64))
-        sample = min(B, 32 * procs)
-        v, n_envs, busy, wall = cpu_oracle_throughput(args.model, args.dtype, sample, 5, procs)
-        cpu = {"value": v, "unit": UNIT, "cores": procs, "kind": "port",
-               "sample": f"{n_envs} of {B} envs per step x 5 steps on {procs} processes (NumPy oracle port; JAX unavailable)"}
+        threads = max(1, min(os.cpu_count() or 1, 256))
+        v, busy = cpu_oracle_throughput(args.model, B, 10, threads)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"full {B}-env batch x 10 steps on {threads} threads (plain-C oracle port, float64; JAX unavailable offline)"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),

@@ -395,3 +395,35 @@ def test_step_rk4(name, dtype, cuda_device):
     ref = O.step_rk4(om, od, joint_force_references=tau)
     out = js.model.step(model, pd, joint_force_references=t(tau))
     H.compare_data(out, ref, rt, f"rk4 {name} {dtype}")
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("name,B", [("icub_like", 4096), ("ergocub_like", 16384), ("icub_like", 65536)])
+def test_full_size_parity(name, B, dtype, cuda_device):
+    """BASELINE.json's FULL batch sizes (configs 1, 2, 3): every environment of the batch
+    against the plain-C oracle (itself pinned to the NumPy oracle in tests/test_c_oracle.py),
+    half of the batch in the free-flight distribution and half touching the ground, plus two
+    size-independent properties: unit quaternions and RNEA(ABA(tau)) == tau."""
+    import torch
+
+    from oracle import c_oracle as CO
+
+    model = H.build_model(name)
+    om = H.oracle_model(model)
+    a = O.random_model_data(om, B // 2, seed=61)
+    b = O.random_model_data(om, B - B // 2, seed=62, in_contact=True)
+    od = O.OracleData(**{f.name: np.concatenate([getattr(a, f.name), getattr(b, f.name)], axis=0)
+                         for f in __import__("dataclasses").fields(O.OracleData)})
+    rng = np.random.default_rng(11)
+    tau = 10 * rng.uniform(size=(B, om.dofs()))
+    ref = CO.step(om, od, joint_force_references=tau)
+    td = _dtype(dtype)
+    pd = H.to_product(model, od, td, cuda_device)
+    tau_t = torch.as_tensor(tau, dtype=td, device=cuda_device)
+    out = js.model.step(model, pd, joint_force_references=tau_t)
+    H.compare_data(out, ref, H.RTOL[dtype], f"full size {name} B={B} {dtype}")
+    qn = torch.linalg.norm(out.base_quaternion, dim=-1)
+    assert float((qn - 1).abs().max()) <= (1e-12 if dtype == "float64" else 1e-6)
+    acc, sdd = js.model.forward_dynamics_aba(model, pd, joint_forces=tau_t)
+    _, tau_id = js.model.inverse_dynamics(model, pd, joint_accelerations=sdd, base_acceleration=acc)
+    assert float((tau_id - tau_t).abs().max()) / 10.0 <= (1e-9 if dtype == "float64" else 2e-3)
