@@ -1,0 +1,221 @@
+"""-m gpu: edge cases of the step path against the oracle -- the code paths the default
+models do not exercise (SURVEY.md 8c "edge cases the reference tests")."""
+
+import copy
+
+import numpy as np
+import pytest
+
+import jaxsim_b200.api as js
+from jaxsim_b200 import models
+from jaxsim_b200.rbda.actuation import ActuationParams
+from jaxsim_b200.rbda.contacts import SoftContactsParams
+from jaxsim_b200.terrain import FlatTerrain
+from oracle import jaxsim_oracle as O
+
+from . import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(model, om, od, cuda_device, tau=None, dtype="float64", rtol=None):
+    import torch
+
+    td = {"float64": torch.float64, "float32": torch.float32}[dtype]
+    pd = H.to_product(model, od, td, cuda_device)
+    t = None if tau is None else torch.as_tensor(tau, dtype=td, device=cuda_device)
+    out = js.model.step(model, pd, joint_force_references=t)
+    ref = O.step(om, od, joint_force_references=tau)
+    H.compare_data(out, ref, rtol if rtol is not None else H.RTOL[dtype], "edge")
+    return out, ref
+
+
+@pytest.mark.parametrize("B", [1, 3, 5, 37, 4097])
+def test_ragged_batch_sizes(B, cuda_device):
+    """Batches that do not fill a warp / a block / the grid (idle groups shadow the last env)."""
+    model = H.build_model("icub_like")
+    om = H.oracle_model(model)
+    od = O.random_model_data(om, B, seed=B, in_contact=True)
+    _run(model, om, od, cuda_device)
+
+
+def test_empty_batch_and_unbatched(cuda_device):
+    import torch
+
+    model = H.build_model("double_pendulum")
+    om = H.oracle_model(model)
+    # B = 0: nothing to do, shapes preserved
+    d0 = js.data.JaxSimModelData.build(model, batch_size=0, dtype=torch.float64, device=cuda_device,
+                                       velocity_representation=js.common.VelRepr.Inertial)
+    o0 = js.model.step(model, d0)
+    assert o0.joint_positions.shape == (0, 2)
+    # unbatched leaves (the reference's non-vmapped call)
+    od = O.random_model_data(om, 1, seed=4)
+    d1 = js.data.JaxSimModelData.build(
+        model, joint_positions=torch.as_tensor(od.joint_positions[0]), joint_velocities=torch.as_tensor(od.joint_velocities[0]),
+        dtype=torch.float64, device=cuda_device, velocity_representation=js.common.VelRepr.Inertial)
+    assert d1.joint_positions.shape == (2,) and d1.link_transforms.shape == (3, 4, 4)
+    o1 = js.model.step(model, d1)
+    ref = O.step(om, od)
+    assert o1.joint_positions.shape == (2,)
+    assert H.rel_err(o1.joint_positions.cpu().numpy()[None], ref.joint_positions) <= 1e-9
+    assert H.rel_err(o1.link_transforms.cpu().numpy()[None], ref.link_transforms) <= 1e-9
+
+
+def test_shape_errors_raise_value_error(cuda_device):
+    import torch
+
+    model = H.build_model("icub_like")
+    d = js.data.random_model_data(model, batch_size=4, dtype=torch.float32, device=cuda_device)
+    with pytest.raises(ValueError):
+        js.model.step(model, d, joint_force_references=torch.zeros(4, 22, device=cuda_device))
+    with pytest.raises(ValueError):
+        js.model.step(model, d, link_forces=torch.zeros(4, 23, 6, device=cuda_device))
+    with pytest.raises(ValueError):
+        js.data.JaxSimModelData.build(model, joint_positions=torch.zeros(4, 5), device=cuda_device)
+    with pytest.raises(TypeError):
+        js.model.step(model, js.data.random_model_data(model, batch_size=2, dtype=torch.float16, device=cuda_device))
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_non_default_contact_and_actuation_parameters(dtype, cuda_device):
+    """pow() exponents != 0.5, friction disabled, active joint limits with spring + damper,
+    tight torque-speed curve, raised terrain, weaker gravity, larger time step."""
+    kw = dict(
+        contact_params=SoftContactsParams.build(K=2e5, D=300.0, mu=0.8, p=0.7, q=0.3),
+        actuation_params=ActuationParams(torque_max=8.0, omega_th=0.4, omega_max=0.9, enable_friction=False),
+        terrain=FlatTerrain.build(height=0.07), time_step=2e-3, gravity=3.7,
+    )
+    model = H.build_model("icub_like", **kw)
+    jp = model.kin_dyn_parameters.joint_parameters
+    jp.position_limit_spring = np.full(23, 40.0)
+    jp.position_limit_damper = np.full(23, 0.3)
+    jp.position_limits_min = np.full(23, -0.2)
+    jp.position_limits_max = np.full(23, 0.25)
+    om = H.oracle_model(model)
+    assert (om.p, om.q, om.gravity, om.terrain_height) == (0.7, 0.3, -3.7, 0.07)
+    B = 24
+    od = O.random_model_data(om, B, seed=71, in_contact=True)
+    rng = np.random.default_rng(3)
+    tau = 20 * rng.uniform(-1, 1, size=(B, 23))
+    od.tangential_deformation = 1e-4 * rng.uniform(-1, 1, size=od.tangential_deformation.shape)
+    out, ref = _run(model, om, od, cuda_device, tau=tau, dtype=dtype)
+    # the limits and the tn-curve really were active in this test
+    assert np.any(od.joint_positions > 0.25) and np.any(np.abs(od.joint_velocities) > 0.9)
+
+
+def test_disabled_collidable_points(cuda_device):
+    """Disabled points produce no force and their deformation does not change
+    (rbda/contacts/soft.py:425-442)."""
+    model = H.build_model("box")
+    enabled = [True, False, True, False, False, True, True, False]
+    model.kin_dyn_parameters.contact_parameters.enabled = tuple(enabled)
+    om = H.oracle_model(model)
+    od = O.random_model_data(om, 16, seed=5, in_contact=True)
+    od.tangential_deformation = 1e-4 * np.random.default_rng(0).uniform(-1, 1, size=od.tangential_deformation.shape)
+    out, ref = _run(model, om, od, cuda_device)
+    m_out = out.contact_state["tangential_deformation"].cpu().numpy()
+    off = [k for k, e in enumerate(enabled) if not e]
+    assert np.array_equal(m_out[:, off], od.tangential_deformation[:, off])
+
+
+def test_fixed_base_with_rotated_mount_and_base_velocity(cuda_device):
+    """F_GENERIC_FK: suc_H_i[0] != I (rotated + translated world joint) and the reference's
+    quirks for fixed-base models (ABA ignores suc_H_i[0] and the base velocity, FK and the
+    contacts honour them; rbda/aba.py:79-121 vs rbda/forward_kinematics.py:66-73)."""
+    from jaxsim_b200.models import UrdfBuilder, box_inertia, cylinder_inertia, sphere_inertia
+
+    b = UrdfBuilder("tilted_arm")
+    b.massless_link("world")
+    b.link("base", 2.0, box_inertia(2.0, (0.2, 0.2, 0.1)), collisions=[("box", (0, 0, 0), (0, 0, 0), (0.2, 0.2, 0.1))])
+    b.link("l1", 1.0, cylinder_inertia(1.0, 0.03, 0.4), com=(0, 0, 0.2))
+    b.link("l2", 0.5, sphere_inertia(0.5, 0.05), com=(0.1, 0, 0), collisions=[("sphere", (0.1, 0, 0), (0, 0, 0), 0.05)])
+    b.joint("mount", "fixed", "world", "base", xyz=(0.3, -0.2, 0.06), rpy=(0.4, -0.3, 0.9))
+    b.joint("j1", "revolute", "base", "l1", xyz=(0, 0, 0.05), rpy=(0.2, 0, 0), axis=(0, 1, 0), limit=(-2, 2), damping=0.1)
+    b.joint("j2", "prismatic", "l1", "l2", xyz=(0, 0, 0.4), axis=(0.6, 0, 0.8), limit=(-0.2, 0.2), friction=0.3)
+    model = js.model.JaxSimModel.build_from_model_description(b.urdf())
+    assert not model.floating_base()
+    om = H.oracle_model(model)
+    B = 12
+    od = O.random_model_data(om, B, seed=9)
+    rng = np.random.default_rng(1)
+    # a user may hand over any base pose/velocity even for fixed-base models
+    od = O.data_replace(om, od.joint_positions, od.joint_velocities, O._quat_from_euler_xyz_intrinsic(rng.uniform(-0.5, 0.5, (B, 3))),
+                        rng.uniform(-0.3, 0.3, (B, 3)), rng.uniform(-0.3, 0.3, (B, 3)), rng.uniform(-0.1, 0.1, (B, 3)))
+    tau = rng.uniform(-2, 2, size=(B, 2))
+    _run(model, om, od, cuda_device, tau=tau)
+    _run(model, om, od, cuda_device, tau=tau, dtype="float32")
+
+
+def test_non_identity_successor_transforms(cuda_device):
+    """F_SUC_NONID: suc_H_i[i>=1] != I (SDF-style link poses, math/joint_model.py:92-98).
+    The URDF loader never produces them, so the KinDynParameters are edited directly."""
+    model = H.build_model("icub_like")
+    kd = copy.deepcopy(model.kin_dyn_parameters)
+    rng = np.random.default_rng(5)
+    for i in range(1, kd.number_of_links()):
+        e = rng.uniform(-0.3, 0.3, 3)
+        q = O._quat_from_euler_xyz_intrinsic(e[None])[0]
+        H4 = np.eye(4)
+        H4[0:3, 0:3] = O.quat_to_dcm(q)
+        H4[0:3, 3] = rng.uniform(-0.02, 0.02, 3)
+        kd.joint_model.suc_H_i[i] = H4
+    model2 = js.model.JaxSimModel.build(kd, floating_base=True, model_name="icub_suc")
+    om = H.oracle_model(model2)
+    od = O.random_model_data(om, 10, seed=13, in_contact=True)
+    _run(model2, om, od, cuda_device, tau=rng.uniform(-3, 3, (10, 23)))
+
+
+@pytest.mark.parametrize("vr", ["Body", "Mixed", "Inertial"])
+def test_build_converts_base_velocity_representation(vr, cuda_device):
+    """JaxSimModelData.build stores the base velocity inertial-fixed whatever representation it
+    is given in (api/data.py:151-156); base_velocity converts back (api/data.py:288-312)."""
+    import torch
+
+    model = H.build_model("icub_like")
+    om = H.oracle_model(model)
+    od = O.random_model_data(om, 6, seed=3)
+    repr_ = getattr(js.common.VelRepr, vr)
+    v_in = np.random.default_rng(2).uniform(-1, 1, size=(6, 6))
+    W_v = O.other_representation_to_inertial(v_in, vr.lower(), O.transform_from_quat_pos(od.base_quaternion, od.base_position), is_force=False)
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64, device=cuda_device)  # noqa: E731
+    d = js.data.JaxSimModelData.build(
+        model, base_position=t(od.base_position), base_quaternion=t(od.base_quaternion), joint_positions=t(od.joint_positions),
+        joint_velocities=t(od.joint_velocities), base_linear_velocity=t(v_in[:, 0:3]), base_angular_velocity=t(v_in[:, 3:6]),
+        velocity_representation=repr_, dtype=torch.float64, device=cuda_device)
+    got = torch.cat([d._base_linear_velocity, d._base_angular_velocity], -1).cpu().numpy()
+    assert H.rel_err(got, W_v) <= 1e-12
+    assert H.rel_err(d.base_velocity.cpu().numpy(), v_in) <= 1e-12
+    ref = O.data_replace(om, od.joint_positions, od.joint_velocities, od.base_quaternion, W_v[:, 0:3], W_v[:, 3:6], od.base_position)
+    assert H.rel_err(d.link_velocities.cpu().numpy(), ref.link_velocities) <= 1e-10
+    # replace() keeps the representation and accepts velocities in it
+    d2 = d.replace(model, base_linear_velocity=t(v_in[:, 0:3]), base_angular_velocity=t(v_in[:, 3:6]))
+    assert d2.velocity_representation == repr_
+    assert H.rel_err(d2._base_linear_velocity.cpu().numpy(), W_v[:, 0:3]) <= 1e-12
+
+
+def test_update_link_params_changes_the_dynamics(cuda_device):
+    """b200sim_model_update_link_params (HW-parametrisation hook): new masses take effect and
+    match an oracle model built with them."""
+    import ctypes
+
+    import torch
+
+    from jaxsim_b200 import _lib
+
+    model = H.build_model("icub_like")
+    om = H.oracle_model(model)
+    od = O.random_model_data(om, 8, seed=21)
+    pd = H.to_product(model, od, torch.float64, cuda_device)
+    lp = model.kin_dyn_parameters.link_parameters
+    new_mass = lp.mass * np.linspace(0.5, 1.5, lp.mass.size)
+    om2 = copy.deepcopy(om)
+    om2.kin_dyn_parameters.link_parameters.mass = new_mass
+    dm = model.device_model(cuda_device)
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(_lib.c_dp)  # noqa: E731
+    keep = [np.ascontiguousarray(new_mass), np.ascontiguousarray(lp.center_of_mass), np.ascontiguousarray(lp.inertia_elements)]
+    rc = _lib.load().b200sim_model_update_link_params(dm.handle, *[k.ctypes.data_as(_lib.c_dp) for k in keep])
+    assert rc == 0
+    out = js.model.step(model, pd)
+    H.compare_data(out, O.step(om2, od), 1e-5, "updated masses")
+    assert H.rel_err(out.joint_velocities.cpu().numpy(), O.step(om, od).joint_velocities) > 1e-4
