@@ -87,6 +87,9 @@ def test_non_default_contact_and_actuation_parameters(dtype, cuda_device):
         terrain=FlatTerrain.build(height=0.07), time_step=2e-3, gravity=3.7,
     )
     model = H.build_model("icub_like", **kw)
+    B = 24
+    # sample inside the URDF limits first, THEN narrow the limits so that many joints sit beyond them
+    od = O.random_model_data(H.oracle_model(model), B, seed=71, in_contact=True)
     jp = model.kin_dyn_parameters.joint_parameters
     jp.position_limit_spring = np.full(23, 40.0)
     jp.position_limit_damper = np.full(23, 0.3)
@@ -94,10 +97,11 @@ def test_non_default_contact_and_actuation_parameters(dtype, cuda_device):
     jp.position_limits_max = np.full(23, 0.25)
     om = H.oracle_model(model)
     assert (om.p, om.q, om.gravity, om.terrain_height) == (0.7, 0.3, -3.7, 0.07)
-    B = 24
-    od = O.random_model_data(om, B, seed=71, in_contact=True)
     rng = np.random.default_rng(3)
     tau = 20 * rng.uniform(-1, 1, size=(B, 23))
+    od.joint_velocities = 1.5 * rng.uniform(-1, 1, size=(B, 23))
+    od = O.data_replace(om, od.joint_positions, od.joint_velocities, od.base_quaternion, od.base_linear_velocity,
+                        od.base_angular_velocity, od.base_position)
     od.tangential_deformation = 1e-4 * rng.uniform(-1, 1, size=od.tangential_deformation.shape)
     out, ref = _run(model, om, od, cuda_device, tau=tau, dtype=dtype)
     # the limits and the tn-curve really were active in this test
