@@ -40,7 +40,7 @@ namespace b200sim {
 // layouts
 // ------------------------------------------------------------------------------------
 constexpr int REC = 60;   // workspace words per link (60 = 4*15: conflict-free 128-bit rows)
-constexpr int CREC = 52;  // model-constant words per link (52 = 4*13)
+constexpr int CREC = 60;  // model-constant words per link (60 = 4*15)
 
 // workspace record.  Words 0..26 hold (R,p) while kinematics are needed and the
 // articulated inertia + bias force during ABA; words 12..47 double as the staging area of
@@ -86,6 +86,7 @@ constexpr int C_SMIN = 48;
 constexpr int C_SMAX = 49;
 constexpr int C_KC = 50;    // friction_static
 constexpr int C_KV = 51;    // friction_viscous
+constexpr int C_PAX = 52;   // 3 joint axis in PARENT-link coordinates: R_rel(s) a = R_pre a for every s
 
 enum Mode : int { MODE_STEP = 0, MODE_FK = 1, MODE_ABA = 2, MODE_DYN = 3 };
 enum Flags : int {
