@@ -59,7 +59,6 @@ def parse():
     ap.add_argument("--skip-cache", default="", help="diagnostic: letters of caches NOT to write: X (joint transforms), H (link transforms), V (link velocities), B (base transform)")
     ap.add_argument("--out-ring", type=int, default=0, help="diagnostic: number of distinct output buffer sets (0 = same as the input ring)")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
-    ap.add_argument("--ws", action="store_true", help="warp-specialised step kernel (two roles per environment group)")
     ap.add_argument("--no-tma", action="store_true", help="128-bit stores instead of TMA bulk stores for the joint adjoints")
     ap.add_argument("--profile", action="store_true", help="cudaProfilerStart/Stop around the eager timed region (ncu --profile-from-start off)")
     ap.add_argument("--rollout", type=int, default=0, help="also time step_n with this many fused steps per launch")
@@ -212,8 +211,8 @@ def run_b200(args):
     model = js.model.JaxSimModel.build_from_model_description(models.urdf(args.model), time_step=1e-3)
     if args.lanes:
         model.set_tuning(lanes_per_env=args.lanes)
-    if args.no_tma or args.ws:
-        model.set_options(tma_store=not args.no_tma, warp_specialized=args.ws)
+    if args.no_tma:
+        model.set_options(tma_store=False)
     n, nL, nc = model.dofs(), model.number_of_links(), model.number_of_collidable_points()
     B = args.batch
     bytes_env = algorithmic_bytes_per_env(n, nL, nc, w, caches=not args.no_caches)
@@ -461,8 +460,7 @@ def run_b200(args):
                    "integrator": "semi_implicit_euler", "parallelism": f"env-parallel x{world} (no data-path collective)",
                    "l2": f"inputs larger than L2: ring of {ring} independent state sets ({ring * B * bytes_env / 2**20:.0f} MiB)",
                    "launch": geo, "caches_written": not args.no_caches, "cuda_graph": ms_graph is not None,
-                   "joint_adjoint_store": "128-bit STG" if args.no_tma else "TMA cp.async.bulk",
-                   "kernel": "warp-specialised (2 roles)" if args.ws else "single-role"},
+                   "joint_adjoint_store": "128-bit STG" if args.no_tma else "TMA cp.async.bulk"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "bytes_per_env_step": bytes_env, "peak_source": peak_src,
                      "note": "algorithmic bytes = B_api (SURVEY.md 8d): read state+contact state+tau, write state+contact state+all caches"},

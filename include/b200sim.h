@@ -105,11 +105,6 @@ int b200sim_model_set_tuning(B200SimModel *model, int lanes_per_env, int envs_pe
  *   B200SIM_OPT_TMA_STORE: the (B,nL,6,6) joint-transform cache leaves shared memory through
  *   the TMA engine (cp.async.bulk) instead of 128-bit stores from registers. */
 #define B200SIM_OPT_TMA_STORE 1
-/*   B200SIM_OPT_WARP_SPECIALIZED: b200sim_step/_step_n run the warp-specialised kernel (two
- *   warps with different roles per 4 environments) when the model allows it (floating-base,
- *   URDF-style successor frames); otherwise, and for every other entry point, the
- *   single-role kernel is used. */
-#define B200SIM_OPT_WARP_SPECIALIZED 2
 int b200sim_model_set_options(B200SimModel *model, int32_t options);
 
 /* Query sizes / launch geometry chosen for a batch (for benchmarks and tests). */

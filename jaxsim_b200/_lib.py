@@ -61,7 +61,6 @@ class B200SimModelDesc(C.Structure):
 
 ABI_VERSION = 1
 OPT_TMA_STORE = 1
-OPT_WARP_SPECIALIZED = 2
 EXPORTED_SYMBOLS = (
     "b200sim_version",
     "b200sim_model_create",

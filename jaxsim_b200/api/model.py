@@ -247,9 +247,9 @@ class JaxSimModel:
         for dm in self._devices.values():
             _lib.check(_lib.load().b200sim_model_set_tuning(dm.handle, *self._tuning), "set_tuning")
 
-    def set_options(self, tma_store: bool = True, warp_specialized: bool = False) -> None:
-        """Implementation switches (results agree to rounding): ``b200sim_model_set_options``."""
-        self._options = (_lib.OPT_TMA_STORE if tma_store else 0) | (_lib.OPT_WARP_SPECIALIZED if warp_specialized else 0)
+    def set_options(self, tma_store: bool = True) -> None:
+        """Implementation switches (never change results): ``b200sim_model_set_options``."""
+        self._options = _lib.OPT_TMA_STORE if tma_store else 0
         for dm in self._devices.values():
             _lib.check(_lib.load().b200sim_model_set_options(dm.handle, self._options), "set_options")
 

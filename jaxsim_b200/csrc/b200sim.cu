@@ -8,7 +8,6 @@
 #include "b200sim.h"
 #include "b200sim_kernels.cuh"
 #include "b200sim_rbda_kernels.cuh"
-#include "b200sim_ws_kernel.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -198,56 +197,8 @@ int launch_g(const Params<T>& P, const Geometry& g, cudaStream_t st) {
   return (int)cudaGetLastError();
 }
 
-// ---- warp-specialised step kernel (b200sim_ws_kernel.cuh) ---------------------------
-bool ws_eligible(const B200SimModel* m, int mode, int flags) {
-  return (m->opt_flags & B200SIM_OPT_WARP_SPECIALIZED) && mode == MODE_STEP && m->n >= 1 &&
-         !(flags & (F_GENERIC_FK | F_SUC_NONID)) && m->tune_G == 0;
-}
-
-int pick_geometry_ws(const B200SimModel* m, int dtype, long long B, Geometry* g) {
-  const size_t ts = dtype == B200SIM_DTYPE_F64 ? 8 : 4;
-  const size_t st = static_smem_bytes(m, ts);
-  const size_t pe = ws::env_ws_words(m->nL, m->nc) * ts;
-  const size_t budget = (size_t)m->max_smem_optin - 1024;
-  if (st + 4 * pe > budget) return B200SIM_E_TOO_LARGE;
-  long long pairs = std::min<long long>(8, (long long)((budget - st) / (4 * pe)));  // 8 pairs = 512 threads
-  if (m->tune_epb > 0) pairs = std::min<long long>(pairs, std::max(1, m->tune_epb / 4));
-  const long long per_sm = (B + m->num_sms - 1) / m->num_sms;
-  if (m->tune_epb == 0) pairs = std::min(pairs, std::max<long long>(1, (per_sm + 3) / 4));
-  const long long epb = pairs * 4;
-  const long long blocks = (B + epb - 1) / epb;
-  g->G = 8;
-  g->epb = (int)epb;
-  g->grid = (int)std::max<long long>(1, std::min<long long>(blocks, (long long)m->num_sms * 4));
-  g->smem = st + (size_t)epb * pe;
-  return 0;
-}
-
-template <typename T>
-int launch_ws(const B200SimModel* m, Params<T>& P, int dtype, void* stream) {
-  Geometry g;
-  int rc = pick_geometry_ws(m, dtype, P.B, &g);
-  if (rc) return rc;
-  P.envs_per_block = g.epb;
-  int dev = 0;
-  CK(cudaGetDevice(&dev));
-  if (dev != m->device) CK(cudaSetDevice(m->device));
-  auto kern = ws::step_kernel_ws<T>;
-  rc = (int)cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
-  if (!rc) {
-    kern<<<g.grid, (g.epb / 4) * 64, g.smem, (cudaStream_t)stream>>>(P);
-    rc = (int)cudaGetLastError();
-  }
-  if (dev != m->device) cudaSetDevice(dev);
-  return rc;
-}
-
 template <typename T>
 int launch(const B200SimModel* m, Params<T>& P, int dtype, void* stream) {
-  if (ws_eligible(m, P.mode, P.flags)) {
-    Geometry gw;
-    if (pick_geometry_ws(m, dtype, P.B, &gw) == 0) return launch_ws(m, P, dtype, stream);
-  }
   Geometry g;
   int rc = pick_geometry(m, dtype, P.B, &g);
   if (rc) return rc;
@@ -645,7 +596,7 @@ int b200sim_model_set_tuning(B200SimModel* m, int lanes_per_env, int envs_per_bl
 }
 
 int b200sim_model_set_options(B200SimModel* m, int32_t options) {
-  if (!m || (options & ~(B200SIM_OPT_TMA_STORE | B200SIM_OPT_WARP_SPECIALIZED))) return B200SIM_E_INVALID;
+  if (!m || (options & ~B200SIM_OPT_TMA_STORE)) return B200SIM_E_INVALID;
   m->opt_flags = options;
   return 0;
 }
@@ -653,9 +604,7 @@ int b200sim_model_set_options(B200SimModel* m, int32_t options) {
 int b200sim_model_query(const B200SimModel* m, int dtype, int64_t B, int32_t* G, int32_t* epb, int32_t* grid, int32_t* smem) {
   if (!m || B < 1 || (dtype != 0 && dtype != 1)) return B200SIM_E_INVALID;
   Geometry g;
-  int rc = 1;
-  if (ws_eligible(m, MODE_STEP, m->flags)) rc = pick_geometry_ws(m, dtype, B, &g);
-  if (rc) rc = pick_geometry(m, dtype, B, &g);
+  int rc = pick_geometry(m, dtype, B, &g);
   if (rc) return rc;
   if (G) *G = g.G;
   if (epb) *epb = g.epb;

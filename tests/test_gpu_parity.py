@@ -427,51 +427,3 @@ def test_full_size_parity(name, B, dtype, cuda_device):
     acc, sdd = js.model.forward_dynamics_aba(model, pd, joint_forces=tau_t)
     _, tau_id = js.model.inverse_dynamics(model, pd, joint_accelerations=sdd, base_acceleration=acc)
     assert float((tau_id - tau_t).abs().max()) / 10.0 <= (1e-9 if dtype == "float64" else 2e-3)
-
-
-@pytest.mark.parametrize("dtype", ["float64", "float32"])
-@pytest.mark.parametrize("name,B", [("icub_like", 45), ("ergocub_like", 33), ("double_pendulum", 9), ("icub_like", 4099)])
-def test_warp_specialized_kernel(name, B, dtype, cuda_device):
-    """The warp-specialised step kernel (two roles per environment group) against the oracle
-    and against the single-role kernel, single step and fused steps, with torques, external
-    forces and contacts.  (double_pendulum is fixed-base: falls back to the single-role
-    kernel, which must be transparent.)"""
-    import torch
-
-    model = H.build_model(name)
-    model.set_options(warp_specialized=True)
-    ref_model = H.build_model(name)
-    om = H.oracle_model(model)
-    od = O.random_model_data(om, B, seed=83, in_contact=(name != "double_pendulum"))
-    rng = np.random.default_rng(13)
-    T_ = 3
-    tau = 5 * rng.uniform(-1, 1, size=(T_, B, om.dofs()))
-    W_f = rng.uniform(-2, 2, size=(B, om.number_of_links(), 6))
-    if not om.floating_base:
-        W_f[:, 0] = 0
-    od.tangential_deformation = 1e-4 * rng.uniform(-1, 1, size=od.tangential_deformation.shape)
-    td = _dtype(dtype)
-    t = lambda a: torch.as_tensor(a, dtype=td, device=cuda_device)  # noqa: E731
-    pd = H.to_product(model, od, td, cuda_device)
-    if name != "double_pendulum":
-        geo = model.launch_geometry(B, td, cuda_device)
-        assert geo["envs_per_block"] % 4 == 0
-    out = js.model.step(model, pd, joint_force_references=t(tau[0]), link_forces=t(W_f))
-    ref = O.step(om, od, joint_force_references=tau[0], link_forces_inertial=W_f)
-    H.compare_data(out, ref, H.RTOL[dtype], f"ws {name} {dtype}")
-    out1 = js.model.step(ref_model, H.to_product(ref_model, od, td, cuda_device), joint_force_references=t(tau[0]), link_forces=t(W_f))
-    tol = 1e-10 if dtype == "float64" else 5e-4
-    for _, leaf in H.LEAVES:
-        x, y = getattr(out, leaf), getattr(out1, leaf)
-        assert float((x - y).abs().max()) <= tol * max(float(y.abs().max()), 1e-9), leaf
-    # fused steps with per-step torque rows, no caches
-    o3 = js.model.step_n(model, pd, T_, joint_force_references=t(tau), update_caches=False)
-    r3 = od
-    for k in range(T_):
-        r3 = O.step(om, r3, joint_force_references=tau[k])
-    r3.base_transform = r3.joint_transforms = r3.link_transforms = r3.link_velocities = None
-    errs = {}
-    for oname, pname in H.LEAVES[:6]:
-        if getattr(r3, oname).size:
-            errs[oname] = H.rel_err(getattr(o3, pname).cpu().numpy(), getattr(r3, oname))
-    assert all(v <= 10 * H.RTOL[dtype] for v in errs.values()), errs
