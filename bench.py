@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--no-caches", action="store_true", help="diagnostic: do not materialise the cached transforms (B_min traffic)")
     ap.add_argument("--skip-cache", default="", help="diagnostic: letters of caches NOT to write: X (joint transforms), H (link transforms), V (link velocities), B (base transform)")
     ap.add_argument("--out-ring", type=int, default=0, help="diagnostic: number of distinct output buffer sets (0 = same as the input ring)")
+    ap.add_argument("--no-input-caches", action="store_true", help="recompute the kinematics of the input state instead of reading its cached link transforms/velocities")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
     ap.add_argument("--no-tma", action="store_true", help="128-bit stores instead of TMA bulk stores for the joint adjoints")
     ap.add_argument("--profile", action="store_true", help="cudaProfilerStart/Stop around the eager timed region (ncu --profile-from-start off)")
@@ -245,7 +246,7 @@ def run_b200(args):
             o = None
             for i in range(count):
                 o = js.model.step(model, datas[i % ring], joint_force_references=taus[i % ring], out=outs[i % oring],
-                                  update_caches=not args.no_caches)
+                                  update_caches=not args.no_caches, use_input_caches=not args.no_input_caches)
             return o
 
         run(W)
@@ -459,11 +460,12 @@ def run_b200(args):
                    "batch_per_gpu": B, "global_batch": B * world, "dt": 1e-3, "contact_model": "soft",
                    "integrator": "semi_implicit_euler", "parallelism": f"env-parallel x{world} (no data-path collective)",
                    "l2": f"inputs larger than L2: ring of {ring} independent state sets ({ring * B * bytes_env / 2**20:.0f} MiB)",
-                   "launch": geo, "caches_written": not args.no_caches, "cuda_graph": ms_graph is not None,
+                   "launch": geo, "caches_written": not args.no_caches, "input_caches_read": not args.no_input_caches, "cuda_graph": ms_graph is not None,
                    "joint_adjoint_store": "128-bit STG" if args.no_tma else "TMA cp.async.bulk"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "bytes_per_env_step": bytes_env, "peak_source": peak_src,
-                     "note": "algorithmic bytes = B_api (SURVEY.md 8d): read state+contact state+tau, write state+contact state+all caches"},
+                     "note": "algorithmic bytes = B_api (SURVEY.md 8d): read state+contact state+tau, write state+contact state+all caches; the kernel additionally READS the input data's cached link transforms/velocities (88 B/link, +2112 B/env) instead of recomputing them, like the reference's contact code",
+                     "bytes_moved_per_env_step": bytes_env + (0 if (args.no_input_caches or args.no_caches) else w * 22 * nL)},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                 "note": "public API js.model.step with pinned host buffers, every step: one H2D (state + contact state + tau), step, one D2H (new state + contact state); double-buffered over 3 streams; the caches are written on the device like in `value` but not copied back"},

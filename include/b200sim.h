@@ -141,13 +141,18 @@ int b200sim_step(const B200SimModel *model, int dtype, int64_t B,
  * only the joint force references are read per step.  tau_ref is (nsteps,B,n) with
  * `tau_step_stride` elements between consecutive steps (0: the same (B,n) block every
  * step); likewise f_ext with `fext_step_stride`.  Outputs are those of the LAST step.
- * b200sim_step == b200sim_step_n with nsteps = 1.  All cache output pointers must be
- * 16-byte aligned. */
+ * W_H_L_in (B,nL,4,4) / W_v_WL_in (B,nL,6): the cached link transforms and velocities OF THE
+ * INPUT STATE (JaxSimModelData._link_transforms/_link_velocities, which the reference's
+ * contact code reads, api/contact.py:39-43), both or neither (NULL): given, the kernel skips
+ * the joint transforms + FK of the input state.  They must be consistent with the state.
+ * b200sim_step == b200sim_step_n with nsteps = 1 and no input caches.  All cache pointers
+ * must be 16-byte aligned. */
 int b200sim_step_n(const B200SimModel *model, int dtype, int64_t B, int32_t nsteps,
                    const void *s, const void *sd, const void *q_wxyz, const void *v_lin,
                    const void *omega, const void *p, const void *m_tan,
                    const void *tau_ref, int64_t tau_step_stride,
                    const void *f_ext, int64_t fext_step_stride,
+                   const void *W_H_L_in, const void *W_v_WL_in,
                    void *s_o, void *sd_o, void *q_o, void *v_lin_o, void *omega_o, void *p_o,
                    void *m_tan_o,
                    void *W_H_B, void *i_X_lam, void *W_H_L, void *W_v_WL,

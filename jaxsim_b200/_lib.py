@@ -108,7 +108,7 @@ def load() -> C.CDLL:
     lib.b200sim_model_set_options.argtypes = [vp, C.c_int32]
     lib.b200sim_model_set_options.restype = C.c_int
     lib.b200sim_step_n.argtypes = (
-        [vp, C.c_int, C.c_int64, C.c_int32] + [vp] * 8 + [C.c_int64, vp, C.c_int64] + [vp] * 12
+        [vp, C.c_int, C.c_int64, C.c_int32] + [vp] * 8 + [C.c_int64, vp, C.c_int64] + [vp] * 14
     )
     lib.b200sim_step_n.restype = C.c_int
     lib.b200sim_step.argtypes = [vp, C.c_int, C.c_int64] + [vp] * 21

@@ -308,7 +308,7 @@ def _alloc_outputs(model, B, dtype, dev, update_caches, soft):
     return out
 
 
-def _step_impl(model, data, n_steps, link_forces, joint_force_references, update_caches, out):
+def _step_impl(model, data, n_steps, link_forces, joint_force_references, update_caches, out, use_input_caches=True):
     s = data._joint_positions
     unbatched = s.dim() == 1
     dev = s.device
@@ -386,6 +386,13 @@ def _step_impl(model, data, n_steps, link_forces, joint_force_references, update
         if any(v is None or not v.is_contiguous() for v in o.values()):
             raise ValueError("`out` must hold contiguous buffers for every requested leaf")
 
+    # the cached kinematics of the input state spare the kernel a sincos + FK pass
+    Hin = Vin = None
+    if use_input_caches and not unbatched and data._link_transforms is not None and data._link_velocities is not None:
+        Hin, Vin = data._link_transforms, data._link_velocities
+        if not (Hin.is_contiguous() and Vin.is_contiguous() and Hin.dtype == dtype and Vin.dtype == dtype
+                and Hin.shape == (B, nL, 4, 4) and Vin.shape == (B, nL, 6) and Hin.data_ptr() % 16 == 0 and Vin.data_ptr() % 16 == 0):
+            Hin = Vin = None
     g = o.get
     if torch.cuda.current_device() != dm.device_index:
         ctx = torch.cuda.device(dev)
@@ -395,7 +402,7 @@ def _step_impl(model, data, n_steps, link_forces, joint_force_references, update
         rc = _lib.load().b200sim_step_n(
             dm.handle, code, B, int(n_steps),
             _ptr(s), _ptr(sd), _ptr(q), _ptr(vl), _ptr(om), _ptr(p), _ptr(m), _ptr(tau), tau_stride,
-            _ptr(fext), fext_stride,
+            _ptr(fext), fext_stride, _ptr(Hin), _ptr(Vin),
             _ptr(o["s"]), _ptr(o["sd"]), _ptr(o["q"]), _ptr(o["vl"]), _ptr(o["om"]), _ptr(o["p"]), _ptr(g("m")),
             _ptr(g("W_H_B")), _ptr(g("iXl")), _ptr(g("W_H_L")), _ptr(g("W_v")), _stream_ptr(dev),
         )
@@ -427,6 +434,7 @@ def step(
     joint_force_references: torch.Tensor | None = None,
     update_caches: bool = True,
     out: "_data.JaxSimModelData | None" = None,
+    use_input_caches: bool = True,
 ) -> "_data.JaxSimModelData":
     """Perform a simulation step: drop-in for ``jaxsim.api.model.step``
     (``src/jaxsim/api/model.py:2601-2681``), batched over the leading axis of ``data``.
@@ -442,6 +450,10 @@ def step(
         out: optional data object whose buffers receive the result (like NumPy's ``out=``);
             avoids every allocation and makes the call CUDA-graph capturable.  ``out`` may
             be ``data`` itself (in-place step).
+        use_input_caches: read the cached link transforms / velocities of ``data`` (like the
+            reference's contact code does) instead of recomputing the kinematics of the
+            input state; they are consistent with the state for every object this API
+            produces.  Set False for data whose private leaves were edited by hand.
 
     Returns:
         The new ``JaxSimModelData`` (same velocity representation; new tensors unless
@@ -451,7 +463,7 @@ def step(
         from .integrators import step_rk4
 
         return step_rk4(model, data, link_forces=link_forces, joint_force_references=joint_force_references)
-    return _step_impl(model, data, 1, link_forces, joint_force_references, update_caches, out)
+    return _step_impl(model, data, 1, link_forces, joint_force_references, update_caches, out, use_input_caches)
 
 
 def step_n(

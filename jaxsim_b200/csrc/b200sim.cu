@@ -300,7 +300,8 @@ template <typename T>
 int step_t(const B200SimModel* m, int dtype, int64_t B, const void* s, const void* sd, const void* q,
            const void* vlin, const void* omega, const void* p, const void* mt, const void* tau, const void* fext,
            void* s_o, void* sd_o, void* q_o, void* vlin_o, void* omega_o, void* p_o, void* m_o, void* W_H_B,
-           void* iXl, void* W_H_L, void* W_v, int nsteps, long long tau_stride, long long fext_stride, void* stream) {
+           void* iXl, void* W_H_L, void* W_v, int nsteps, long long tau_stride, long long fext_stride, const void* Hin,
+           const void* Vin, void* stream) {
   Params<T> P;
   std::memset(&P, 0, sizeof(P));
   fill_model_params(m, P);
@@ -311,6 +312,7 @@ int step_t(const B200SimModel* m, int dtype, int64_t B, const void* s, const voi
   P.p_o = (T*)p_o; P.m_o = (T*)m_o;
   P.W_H_B = (T*)W_H_B; P.iXl = (T*)iXl; P.W_H_L = (T*)W_H_L; P.W_v = (T*)W_v;
   P.nsteps = nsteps; P.tau_step_stride = tau_stride; P.fext_step_stride = fext_stride;
+  P.Hin = (const T*)Hin; P.Vin = (const T*)Vin;
   P.mode = MODE_STEP;
   return launch(m, P, dtype, stream);
 }
@@ -617,9 +619,9 @@ static bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_
 
 int b200sim_step_n(const B200SimModel* m, int dtype, int64_t B, int32_t nsteps, const void* s, const void* sd,
                    const void* q, const void* vlin, const void* omega, const void* p, const void* mt, const void* tau,
-                   int64_t tau_step_stride, const void* fext, int64_t fext_step_stride, void* s_o, void* sd_o, void* q_o,
-                   void* vlin_o, void* omega_o, void* p_o, void* m_o, void* W_H_B, void* iXl, void* W_H_L, void* W_v,
-                   void* stream) {
+                   int64_t tau_step_stride, const void* fext, int64_t fext_step_stride, const void* W_H_L_in,
+                   const void* W_v_in, void* s_o, void* sd_o, void* q_o, void* vlin_o, void* omega_o, void* p_o,
+                   void* m_o, void* W_H_B, void* iXl, void* W_H_L, void* W_v, void* stream) {
   if (!m || B < 0 || nsteps < 1 || (dtype != 0 && dtype != 1)) return B200SIM_E_INVALID;
   if (tau_step_stride < 0 || fext_step_stride < 0) return B200SIM_E_INVALID;
   if (B == 0) return 0;
@@ -628,19 +630,21 @@ int b200sim_step_n(const B200SimModel* m, int dtype, int64_t B, int32_t nsteps, 
   // vector / TMA stores: the cache outputs must be 16-byte aligned (8 for float W_v rows)
   if (!aligned(W_H_B, 16) || !aligned(iXl, 16) || !aligned(W_H_L, 16) || !aligned(W_v, dtype == 0 ? 8 : 16))
     return B200SIM_E_INVALID;
+  if ((W_H_L_in == nullptr) != (W_v_in == nullptr)) return B200SIM_E_INVALID;
+  if (!aligned(W_H_L_in, 16) || !aligned(W_v_in, dtype == 0 ? 8 : 16)) return B200SIM_E_INVALID;
   if (dtype == 0)
     return step_t<float>(m, dtype, B, s, sd, q, vlin, omega, p, mt, tau, fext, s_o, sd_o, q_o, vlin_o, omega_o, p_o, m_o,
-                         W_H_B, iXl, W_H_L, W_v, nsteps, tau_step_stride, fext_step_stride, stream);
+                         W_H_B, iXl, W_H_L, W_v, nsteps, tau_step_stride, fext_step_stride, W_H_L_in, W_v_in, stream);
   return step_t<double>(m, dtype, B, s, sd, q, vlin, omega, p, mt, tau, fext, s_o, sd_o, q_o, vlin_o, omega_o, p_o, m_o,
-                        W_H_B, iXl, W_H_L, W_v, nsteps, tau_step_stride, fext_step_stride, stream);
+                        W_H_B, iXl, W_H_L, W_v, nsteps, tau_step_stride, fext_step_stride, W_H_L_in, W_v_in, stream);
 }
 
 int b200sim_step(const B200SimModel* m, int dtype, int64_t B, const void* s, const void* sd, const void* q,
                  const void* vlin, const void* omega, const void* p, const void* mt, const void* tau, const void* fext,
                  void* s_o, void* sd_o, void* q_o, void* vlin_o, void* omega_o, void* p_o, void* m_o, void* W_H_B,
                  void* iXl, void* W_H_L, void* W_v, void* stream) {
-  return b200sim_step_n(m, dtype, B, 1, s, sd, q, vlin, omega, p, mt, tau, 0, fext, 0, s_o, sd_o, q_o, vlin_o, omega_o,
-                        p_o, m_o, W_H_B, iXl, W_H_L, W_v, stream);
+  return b200sim_step_n(m, dtype, B, 1, s, sd, q, vlin, omega, p, mt, tau, 0, fext, 0, nullptr, nullptr, s_o, sd_o, q_o,
+                        vlin_o, omega_o, p_o, m_o, W_H_B, iXl, W_H_L, W_v, stream);
 }
 
 int b200sim_fk(const B200SimModel* m, int dtype, int64_t B, const void* s, const void* sd, const void* q,

@@ -113,6 +113,7 @@ struct Params {
   // ---- batch
   long long B;
   const T *s, *sd, *q, *vlin, *omega, *p, *m, *tau, *fext;
+  const T *Hin, *Vin;  // optional cached kinematics of the INPUT state: W_H_L (B,nL,4,4), W_v_WL (B,nL,6)
   T *s_o, *sd_o, *q_o, *vlin_o, *omega_o, *p_o, *m_o;
   T *W_H_B, *iXl, *W_H_L, *W_v;
   T *avd, *sdd_o;
@@ -234,6 +235,40 @@ __device__ __forceinline__ void stg_vec6(double* dst, const double* src) {
 }
 
 __device__ __forceinline__ void stg_vec6(DualD* dst, const DualD* src) { stg_vec<6>(dst, src); }
+
+// 16-byte vector loads from global memory (src 16-byte aligned; 8-byte for float 6-rows)
+template <int N>
+__device__ __forceinline__ void ldg_vec(const float* src, float* dst) {
+  static_assert(N % 4 == 0, "N");
+#pragma unroll
+  for (int k = 0; k < N; k += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(src + k);
+    dst[k] = v.x; dst[k + 1] = v.y; dst[k + 2] = v.z; dst[k + 3] = v.w;
+  }
+}
+template <int N>
+__device__ __forceinline__ void ldg_vec(const double* src, double* dst) {
+  static_assert(N % 2 == 0, "N");
+#pragma unroll
+  for (int k = 0; k < N; k += 2) {
+    const double2 v = *reinterpret_cast<const double2*>(src + k);
+    dst[k] = v.x; dst[k + 1] = v.y;
+  }
+}
+template <int N>
+__device__ __forceinline__ void ldg_vec(const DualD* src, DualD* dst) {
+#pragma unroll
+  for (int k = 0; k < N; ++k) dst[k] = src[k];
+}
+__device__ __forceinline__ void ldg_vec6(const float* src, float* dst) {
+#pragma unroll
+  for (int k = 0; k < 6; k += 2) {
+    const float2 v = *reinterpret_cast<const float2*>(src + k);
+    dst[k] = v.x; dst[k + 1] = v.y;
+  }
+}
+__device__ __forceinline__ void ldg_vec6(const double* src, double* dst) { ldg_vec<6>(src, dst); }
+__device__ __forceinline__ void ldg_vec6(const DualD* src, DualD* dst) { ldg_vec<6>(src, dst); }
 
 // ---- async copies -------------------------------------------------------------------
 // one element global -> shared without a register round trip (LDGSTS)
@@ -646,19 +681,56 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
     };
 
     __pipeline_wait_prior(0);
-    write_base_record(b);
+    if (!((P.mode == MODE_STEP) && P.Hin && P.Vin && !(P.flags & F_GENERIC_FK))) write_base_record(b);
 
-    // =========================================================== phase 1: joint transforms
-    for (int i = 1 + lane; i < nL; i += G) {
-      T* ri = ws + (size_t)i * REC;
-      T Rrel[9], trel[3];
-      joint_rel_transform(P, sm_cst + (size_t)i * CREC, jtypes[i], i, ri[O_S], Rrel, trel);
-      stn<9>(ri + O_R, Rrel);
-      stn<3>(ri + O_P, trel);
-      if (P.mode == MODE_FK && P.iXl && active) emit_joint_adjoint(ri, i, Rrel, trel);
+    const bool use_cached = (P.mode == MODE_STEP) && P.Hin && P.Vin && !(P.flags & F_GENERIC_FK);
+    if (use_cached) {
+      // ========================================================= phases 1-2 from the caches
+      // The input data carries the link transforms / velocities of its own state (they are
+      // what the reference's contact code reads, api/contact.py:39-43): 88 B per link from
+      // L2/HBM instead of a sincos, two 3x3 products and a sequential tree walk.
+      for (int i = lane; i < nL; i += G) {
+        T* ri = ws + (size_t)i * REC;
+        T H[12], V[6];
+        ldg_vec<12>(P.Hin + (env * nL + i) * 16, H);
+        ldg_vec6(P.Vin + (env * nL + i) * 6, V);
+        const T R[9] = {H[0], H[1], H[2], H[4], H[5], H[6], H[8], H[9], H[10]};
+        const T p[3] = {H[3], H[7], H[11]};
+        T v[6], t[3];
+        cross3(V + 3, p, t);  // velocity of the link origin: W_v_lin + w x p
+        v[0] = V[0] + t[0]; v[1] = V[1] + t[1]; v[2] = V[2] + t[2];
+        v[3] = V[3]; v[4] = V[4]; v[5] = V[5];
+        stn<9>(ri + O_R, R);
+        stn<3>(ri + O_P, p);
+        stn<6>(ri + O_V, v);
+        if (i > 0) {
+          T ax[3], aw[3];
+          ldn<3>(sm_cst + (size_t)i * CREC + C_AXIS, ax);
+          mat3_vec(R, ax, aw);
+          stn<3>(ri + O_AX, aw);
+        }
+      }
+      __syncwarp();
+      for (int i = 1 + lane; i < nL; i += G) {
+        T* ri = ws + (size_t)i * REC;
+        const T* rp = ws + (size_t)parent[i] * REC;
+        const T r[3] = {ri[O_P] - rp[O_P], ri[O_P + 1] - rp[O_P + 1], ri[O_P + 2] - rp[O_P + 2]};
+        stn<3>(ri + O_RR, r);
+      }
+      __syncwarp();
+    } else {
+      // ========================================================= phase 1: joint transforms
+      for (int i = 1 + lane; i < nL; i += G) {
+        T* ri = ws + (size_t)i * REC;
+        T Rrel[9], trel[3];
+        joint_rel_transform(P, sm_cst + (size_t)i * CREC, jtypes[i], i, ri[O_S], Rrel, trel);
+        stn<9>(ri + O_R, Rrel);
+        stn<3>(ri + O_P, trel);
+        if (P.mode == MODE_FK && P.iXl && active) emit_joint_adjoint(ri, i, Rrel, trel);
+      }
+      // ========================================================= phase 2: FK chain
+      fk_chain(P.mode != MODE_FK);
     }
-    // =========================================================== phase 2: FK chain
-    fk_chain(P.mode != MODE_FK);
 
     if (P.mode == MODE_FK) {
       // JaxSimModelData.build / replace: caches of the given state

@@ -223,3 +223,33 @@ def test_update_link_params_changes_the_dynamics(cuda_device):
     out = js.model.step(model, pd)
     H.compare_data(out, O.step(om2, od), 1e-5, "updated masses")
     assert H.rel_err(out.joint_velocities.cpu().numpy(), O.step(om, od).joint_velocities) > 1e-4
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_cached_input_kinematics_path(dtype, cuda_device):
+    """step() reads the link transforms / velocities cached in the input data (like the
+    reference's contact code, api/contact.py:39-43) instead of recomputing them; both paths
+    agree with the oracle and with each other, over consecutive steps."""
+    import torch
+
+    td = {"float64": torch.float64, "float32": torch.float32}[dtype]
+    for name in ("icub_like", "ergocub_like"):
+        model = H.build_model(name)
+        om = H.oracle_model(model)
+        od = O.random_model_data(om, 31, seed=91, in_contact=True)
+        rng = np.random.default_rng(4)
+        tau = 4 * rng.uniform(-1, 1, size=(31, om.dofs()))
+        t = torch.as_tensor(tau, dtype=td, device=cuda_device)
+        a = H.to_product(model, od, td, cuda_device)
+        b = H.to_product(model, od, td, cuda_device)
+        ref = od
+        for _ in range(3):
+            a = js.model.step(model, a, joint_force_references=t)                          # cached inputs
+            b = js.model.step(model, b, joint_force_references=t, use_input_caches=False)  # recomputed
+            ref = O.step(om, ref, joint_force_references=tau)
+        H.compare_data(a, ref, 3 * H.RTOL[dtype], f"cached {name}")
+        H.compare_data(b, ref, 3 * H.RTOL[dtype], f"recomputed {name}")
+        tol = 1e-10 if dtype == "float64" else 1e-4
+        for _, leaf in H.LEAVES:
+            x, y = getattr(a, leaf), getattr(b, leaf)
+            assert float((x - y).abs().max()) <= tol * max(float(y.abs().max()), 1e-9), (name, leaf)

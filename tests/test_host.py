@@ -116,7 +116,7 @@ def test_invalid_arguments_are_rejected_without_a_gpu():
     assert lib.b200sim_aba(None, 0, 1, *([None] * 11)) == -1
     assert lib.b200sim_rnea(None, 0, 1, *([None] * 12)) == -1
     assert lib.b200sim_crba(None, 0, 1, None, None, None) == -1
-    assert lib.b200sim_step_n(None, 0, 1, 1, *([None] * 8), 0, None, 0, *([None] * 12)) == -1
+    assert lib.b200sim_step_n(None, 0, 1, 1, *([None] * 8), 0, None, 0, *([None] * 14)) == -1
 
 
 def test_product_path_has_no_cpu_fallback():
