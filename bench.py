@@ -62,6 +62,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
     ap.add_argument("--no-tma", action="store_true", help="128-bit stores instead of TMA bulk stores for the joint adjoints")
     ap.add_argument("--profile", action="store_true", help="cudaProfilerStart/Stop around the eager timed region (ncu --profile-from-start off)")
+    ap.add_argument("--jvp", action="store_true", help="also time BASELINE config 5: forward-mode d(step)/d(joint q, link masses), fp64")
     ap.add_argument("--rollout", type=int, default=0, help="also time step_n with this many fused steps per launch")
     ap.add_argument("--sweep", action="store_true", help="also time batch 16384 and 65536 on this GPU")
     return ap.parse_args()
@@ -428,6 +429,27 @@ def run_b200(args):
                    "ms_per_step": float(tr.item()) / (reps * Tn),
                    "note": "step_n: state kept on chip, per-step HBM traffic = joint force references only; no caches written"}
 
+    jvp = None
+    if args.jvp:
+        d64 = js.data.random_model_data(model, batch_size=B, seed=77 + rank, dtype=torch.float64, device=dev,
+                                        velocity_representation=js.common.VelRepr.Inertial)
+        tq = torch.randn(B, n, dtype=torch.float64, device=dev)
+        tm = torch.rand(nL, dtype=torch.float64)
+        for _ in range(3):
+            js.model.step_jvp(model, d64, {"joint_positions": tq, "link_masses": tm})
+        barrier()
+        reps = 10
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            js.model.step_jvp(model, d64, {"joint_positions": tq, "link_masses": tm})
+        e1.record()
+        barrier()
+        ms_j = e0.elapsed_time(e1) / reps
+        jvp = {"config": "BASELINE configs[4]: icub_like fp64, d(step)/d(joint q, link masses), batch %d" % B,
+               "ms_per_jvp": ms_j, "env_jvps_per_s": B / (ms_j * 1e-3),
+               "ms_full_jacobian": ms_j * (n + nL), "note": "one tangent direction per launch (value + tangent of every output leaf incl. caches); full Jacobian = n + nL launches"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -480,6 +502,8 @@ def run_b200(args):
         line["sweep"] = sweep
     if rollout is not None:
         line["rollout"] = rollout
+    if jvp is not None:
+        line["config5_jvp"] = jvp
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -548,6 +548,26 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
     // joint state, first-step torque reference and contact state go global -> shared with
     // cp.async; the 13 base scalars go to registers.  Nothing is consumed before the wait.
     if (tma) tma_store_wait_read();  // the previous environment's staging areas are reused below
+    const bool use_cached = (P.mode == MODE_STEP) && P.Hin && P.Vin && !(P.flags & F_GENERIC_FK);
+    if (use_cached) {
+      // cached kinematics of the input state: rows [R | p] of W_H_L and the 6D velocity land in
+      // the (still unused) IA / c slots of the record, 16 bytes per cp.async
+      constexpr int per = 16 / sizeof(T);        // elements per 16-byte chunk
+      for (int i = lane; i < nL; i += G) {
+        T* ri = ws + (size_t)i * REC;
+        const T* H = P.Hin + (env * nL + i) * 16;
+        const T* V = P.Vin + (env * nL + i) * 6;
+#pragma unroll
+        for (int k = 0; k < 12; k += per) __pipeline_memcpy_async(ri + O_X + k, H + k, 16);
+        if (sizeof(T) == 4) {
+#pragma unroll
+          for (int k = 0; k < 6; k += 2) __pipeline_memcpy_async(ri + O_C + k, V + k, 8);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 6; k += per) __pipeline_memcpy_async(ri + O_C + k, V + k, 16);
+        }
+      }
+    }
     for (int i = 1 + lane; i < nL; i += G) {
       T* ri = ws + (size_t)i * REC;
       cp_async_elem(ri + O_S, P.s + env * n + (i - 1));
@@ -681,9 +701,8 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
     };
 
     __pipeline_wait_prior(0);
-    if (!((P.mode == MODE_STEP) && P.Hin && P.Vin && !(P.flags & F_GENERIC_FK))) write_base_record(b);
+    if (!use_cached) write_base_record(b);
 
-    const bool use_cached = (P.mode == MODE_STEP) && P.Hin && P.Vin && !(P.flags & F_GENERIC_FK);
     if (use_cached) {
       // ========================================================= phases 1-2 from the caches
       // The input data carries the link transforms / velocities of its own state (they are
@@ -692,8 +711,8 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
       for (int i = lane; i < nL; i += G) {
         T* ri = ws + (size_t)i * REC;
         T H[12], V[6];
-        ldg_vec<12>(P.Hin + (env * nL + i) * 16, H);
-        ldg_vec6(P.Vin + (env * nL + i) * 6, V);
+        ldn<12>(ri + O_X, H);   // staged by the input burst
+        ldn<6>(ri + O_C, V);
         const T R[9] = {H[0], H[1], H[2], H[4], H[5], H[6], H[8], H[9], H[10]};
         const T p[3] = {H[3], H[7], H[11]};
         T v[6], t[3];
