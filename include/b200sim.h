@@ -29,13 +29,14 @@
 extern "C" {
 #endif
 
-#define B200SIM_ABI_VERSION 1
+#define B200SIM_ABI_VERSION 2
 
 #define B200SIM_DTYPE_F32 0
 #define B200SIM_DTYPE_F64 1
 
 #define B200SIM_CONTACT_NONE 0
 #define B200SIM_CONTACT_SOFT 1 /* rbda/contacts/soft.py */
+#define B200SIM_CONTACT_RIGID 2 /* rbda/contacts/rigid.py (b200sim_step only; floating base; enabled points a prefix) */
 
 #define B200SIM_E_INVALID (-1)     /* NULL / negative size / bad dtype */
 #define B200SIM_E_UNSUPPORTED (-2) /* valid in the reference, not implemented here */
@@ -78,10 +79,14 @@ typedef struct B200SimModelDesc {
   double time_step;      /* JaxSimModel.time_step */
   double gravity;        /* JaxSimModel.gravity: z acceleration, NEGATIVE (-9.81) */
   double terrain_height; /* FlatTerrain._height (terrain/terrain.py:66-113) */
-  /* SoftContactsParams (rbda/contacts/soft.py:24-46) */
+  /* SoftContactsParams (rbda/contacts/soft.py:24-46).  With B200SIM_CONTACT_RIGID, soft_K /
+   * soft_D / soft_mu carry RigidContactsParams.K / D / mu (Baumgarte gains and friction
+   * coefficient, rbda/contacts/rigid.py:27-42) and soft_p / soft_q are ignored. */
   double soft_K, soft_D, soft_mu, soft_p, soft_q;
   /* ActuationParams (rbda/actuation/common.py:10-19) */
   double torque_max, omega_th, omega_max;
+  /* RigidContacts.regularization_delassus (rbda/contacts/rigid.py:99-101), default 1e-6 */
+  double rigid_regularization;
 } B200SimModelDesc;
 
 typedef struct B200SimModel B200SimModel;
@@ -101,10 +106,13 @@ int b200sim_model_update_link_params(B200SimModel *model, const double *link_mas
  * thread block.  Only affects performance, never results. */
 int b200sim_model_set_tuning(B200SimModel *model, int lanes_per_env, int envs_per_block);
 
-/* Implementation options (bit mask; never change results).  Default: B200SIM_OPT_TMA_STORE.
+/* Implementation options (bit mask).  Default: B200SIM_OPT_TMA_STORE.
  *   B200SIM_OPT_TMA_STORE: the (B,nL,6,6) joint-transform cache leaves shared memory through
- *   the TMA engine (cp.async.bulk) instead of 128-bit stores from registers. */
+ *   the TMA engine (cp.async.bulk) instead of 128-bit stores from registers (same results).
+ *   B200SIM_OPT_RIGID_QP_F64: float32 rigid-contact steps factor and solve the contact QP /
+ *   impact system in float64 (the Delassus regularisation 1e-6 sits near float32 resolution). */
 #define B200SIM_OPT_TMA_STORE 1
+#define B200SIM_OPT_RIGID_QP_F64 2
 int b200sim_model_set_options(B200SimModel *model, int32_t options);
 
 /* Query sizes / launch geometry chosen for a batch (for benchmarks and tests). */

@@ -56,11 +56,13 @@ class B200SimModelDesc(C.Structure):
         ("torque_max", C.c_double),
         ("omega_th", C.c_double),
         ("omega_max", C.c_double),
+        ("rigid_regularization", C.c_double),
     ]
 
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 OPT_TMA_STORE = 1
+OPT_RIGID_QP_F64 = 2
 EXPORTED_SYMBOLS = (
     "b200sim_version",
     "b200sim_model_create",

@@ -27,7 +27,7 @@ import torch
 from jaxsim_b200 import _lib
 from jaxsim_b200.parsers.urdf import build_kin_dyn_parameters
 from jaxsim_b200.rbda.actuation import ActuationParams
-from jaxsim_b200.rbda.contacts import RigidContacts, SoftContacts, SoftContactsParams
+from jaxsim_b200.rbda.contacts import RigidContacts, RigidContactsParams, SoftContacts, SoftContactsParams
 from jaxsim_b200.terrain import FlatTerrain
 
 from . import data as _data
@@ -72,13 +72,20 @@ class _DeviceModel:
         axis = np.zeros((nL, 3))
         if n > 0:
             axis[1:] = kd.joint_model.joint_axis
+        reg = 1e-6
+        prm = model.contact_params if isinstance(model.contact_params, SoftContactsParams) else SoftContactsParams()
         if model.contact_model is None or nc == 0:
             cm = 0
         elif isinstance(model.contact_model, SoftContacts):
             cm = 1
+        elif isinstance(model.contact_model, RigidContacts):
+            cm = 2
+            rp = model.contact_params if isinstance(model.contact_params, RigidContactsParams) else RigidContactsParams()
+            # the descriptor's soft_K / soft_D / soft_mu slots carry the rigid K / D / mu (include/b200sim.h)
+            prm = SoftContactsParams(K=rp.K, D=rp.D, mu=rp.mu)
+            reg = float(model.contact_model.regularization_delassus)
         else:
             raise NotImplementedError(f"contact model {type(model.contact_model).__name__} is not implemented")
-        prm = model.contact_params if isinstance(model.contact_params, SoftContactsParams) else SoftContactsParams()
         jp = kd.joint_parameters
         d = _lib.B200SimModelDesc(
             abi_version=_lib.ABI_VERSION, n_links=nL, n_dofs=n, n_points=nc,
@@ -99,7 +106,7 @@ class _DeviceModel:
             terrain_height=float(model.terrain.height()),
             soft_K=prm.K, soft_D=prm.D, soft_mu=prm.mu, soft_p=prm.p, soft_q=prm.q,
             torque_max=model.actuation_params.torque_max, omega_th=model.actuation_params.omega_th,
-            omega_max=model.actuation_params.omega_max,
+            omega_max=model.actuation_params.omega_max, rigid_regularization=reg,
         )
         handle = C.c_void_p()
         _lib.check(lib.b200sim_model_create(C.byref(d), int(device_index), C.byref(handle)), "b200sim_model_create")
@@ -175,8 +182,6 @@ class JaxSimModel:
         """``JaxSimModel.build`` (``api/model.py:224-330``): defaults are SoftContacts with
         default parameters, default ActuationParams, SemiImplicitEuler, flat terrain at 0."""
         contact_model = contact_model if contact_model is not None else SoftContacts.build()
-        if isinstance(contact_model, RigidContacts):
-            raise NotImplementedError("RigidContacts (rbda/contacts/rigid.py) is not implemented yet")
         if contact_params is None:
             contact_params = contact_model._parameters_class()
         integrator = integrator if integrator is not None else IntegratorType.SemiImplicitEuler
@@ -247,9 +252,10 @@ class JaxSimModel:
         for dm in self._devices.values():
             _lib.check(_lib.load().b200sim_model_set_tuning(dm.handle, *self._tuning), "set_tuning")
 
-    def set_options(self, tma_store: bool = True) -> None:
-        """Implementation switches (never change results): ``b200sim_model_set_options``."""
-        self._options = _lib.OPT_TMA_STORE if tma_store else 0
+    def set_options(self, tma_store: bool = True, rigid_qp_f64: bool = False) -> None:
+        """Implementation switches: ``b200sim_model_set_options``.  ``rigid_qp_f64`` makes
+        float32 rigid-contact steps solve the contact QP / impact system in float64."""
+        self._options = (_lib.OPT_TMA_STORE if tma_store else 0) | (_lib.OPT_RIGID_QP_F64 if rigid_qp_f64 else 0)
         for dm in self._devices.values():
             _lib.check(_lib.load().b200sim_model_set_options(dm.handle, self._options), "set_options")
 
@@ -388,7 +394,18 @@ def _step_impl(model, data, n_steps, link_forces, joint_force_references, update
 
     # the cached kinematics of the input state spare the kernel a sincos + FK pass
     Hin = Vin = None
-    if use_input_caches and not unbatched and data._link_transforms is not None and data._link_velocities is not None:
+    if isinstance(model.contact_model, RigidContacts) and nc > 0:
+        # RigidContacts READS the cached link velocities on purpose: after an impact they are the
+        # pre-impact ones (rbda/contacts/rigid.py:429-434 never refreshes them) and the reference's
+        # penetration rate / Jacobian-derivative term use them (api/contact.py:39-43,470-477)
+        if n_steps != 1:
+            raise NotImplementedError("step_n is not available with RigidContacts")
+        if use_input_caches and data._link_transforms is not None and data._link_velocities is not None:
+            Hin = _batched(data._link_transforms, 3).to(dtype).contiguous()
+            Vin = _batched(data._link_velocities, 2).to(dtype).contiguous()
+            if Hin.data_ptr() % 16 or Vin.data_ptr() % 16:
+                Hin, Vin = Hin.clone(), Vin.clone()
+    elif use_input_caches and not unbatched and data._link_transforms is not None and data._link_velocities is not None:
         Hin, Vin = data._link_transforms, data._link_velocities
         if not (Hin.is_contiguous() and Vin.is_contiguous() and Hin.dtype == dtype and Vin.dtype == dtype
                 and Hin.shape == (B, nL, 4, 4) and Vin.shape == (B, nL, 6) and Hin.data_ptr() % 16 == 0 and Vin.data_ptr() % 16 == 0):

@@ -8,6 +8,7 @@
 #include "b200sim.h"
 #include "b200sim_kernels.cuh"
 #include "b200sim_rbda_kernels.cuh"
+#include "b200sim_rigid_kernels.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -35,7 +36,8 @@ struct B200SimModel {
   std::vector<double> pt_h;    // nc*3
   std::vector<int> itab_h;
   int o_parent = 0, o_jtype = 0, o_lvl_start = 0, o_lvl_links = 0, o_child_start = 0, o_child_idx = 0,
-      o_pt_start = 0, o_pt_idx = 0, o_pt_body = 0, o_pt_enabled = 0;
+      o_pt_start = 0, o_pt_idx = 0, o_pt_body = 0, o_pt_enabled = 0, o_anc = 0, o_ldepth = 0;
+  double reg = 1e-6;
   // device blobs
   float *cst_f = nullptr, *csuc_f = nullptr, *pt_f = nullptr;
   double *cst_d = nullptr, *csuc_d = nullptr, *pt_d = nullptr;
@@ -184,6 +186,7 @@ void fill_model_params(const B200SimModel* m, Params<T>& P) {
   P.o_parent = m->o_parent; P.o_jtype = m->o_jtype; P.o_lvl_start = m->o_lvl_start; P.o_lvl_links = m->o_lvl_links;
   P.o_child_start = m->o_child_start; P.o_child_idx = m->o_child_idx; P.o_pt_start = m->o_pt_start;
   P.o_pt_idx = m->o_pt_idx; P.o_pt_body = m->o_pt_body; P.o_pt_enabled = m->o_pt_enabled;
+  P.o_anc = m->o_anc; P.o_ldepth = m->o_ldepth; P.reg = (T)m->reg;
   P.dt = (T)m->dt; P.g = (T)m->g; P.h_terrain = (T)m->h_terrain;
   P.K = (T)m->K; P.D = (T)m->D; P.mu = (T)m->mu; P.pexp = (T)m->pexp; P.qexp = (T)m->qexp;
   P.tau_max = (T)m->tau_max; P.w_th = (T)m->w_th; P.w_max = (T)m->w_max;
@@ -216,6 +219,51 @@ int launch(const B200SimModel* m, Params<T>& P, int dtype, void* stream) {
     case 32: rc = launch_g<T, 32>(P, g, st); break;
     default: rc = B200SIM_E_INVALID;
   }
+  if (dev != m->device) cudaSetDevice(dev);
+  return rc;
+}
+
+// ---- rigid contacts: one warp per environment, as many warps per block as shared memory allows
+template <typename T, typename S>
+int rigid_geometry(const B200SimModel* m, long long B, int* warps, int* grid, size_t* smem) {
+  const size_t st = static_smem_bytes(m, sizeof(T));
+  const RigidLayout L = rigid_layout<T, S>(m->nL, m->nc, m->depth);
+  const size_t budget = (size_t)m->max_smem_optin - 1024;
+  if (st + L.total > budget) return B200SIM_E_TOO_LARGE;
+  long long w = std::min<long long>(RIGID_MAX_WARPS, (long long)((budget - st) / L.total));
+  if (m->tune_epb > 0) w = std::min<long long>(w, m->tune_epb);
+  const long long per_sm = (B + m->num_sms - 1) / m->num_sms;
+  if (m->tune_epb == 0) w = std::min(w, std::max<long long>(per_sm, 1));
+  *warps = (int)w;
+  *smem = st + (size_t)w * L.total;
+  const long long blocks_per_sm = std::max<long long>(1, std::min<long long>(4, (long long)((size_t)228 * 1024 / (*smem + 1024))));
+  const long long want = (B + w - 1) / w;
+  *grid = (int)std::min<long long>(want, (long long)m->num_sms * blocks_per_sm);
+  return 0;
+}
+
+template <typename T, typename S>
+int launch_rigid_s(const B200SimModel* m, Params<T>& P, cudaStream_t st) {
+  int warps = 0, grid = 0;
+  size_t smem = 0;
+  int rc = rigid_geometry<T, S>(m, P.B, &warps, &grid, &smem);
+  if (rc) return rc;
+  P.envs_per_block = warps;
+  auto kern = rigid_step_kernel<T, S>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, warps * 32, smem, st>>>(P);
+  return (int)cudaGetLastError();
+}
+
+template <typename T>
+int launch_rigid(const B200SimModel* m, Params<T>& P, void* stream) {
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev != m->device) CK(cudaSetDevice(m->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if (sizeof(T) == 4 && (m->opt_flags & B200SIM_OPT_RIGID_QP_F64)) rc = launch_rigid_s<T, double>(m, P, st);
+  else rc = launch_rigid_s<T, T>(m, P, st);
   if (dev != m->device) cudaSetDevice(dev);
   return rc;
 }
@@ -314,6 +362,10 @@ int step_t(const B200SimModel* m, int dtype, int64_t B, const void* s, const voi
   P.nsteps = nsteps; P.tau_step_stride = tau_stride; P.fext_step_stride = fext_stride;
   P.Hin = (const T*)Hin; P.Vin = (const T*)Vin;
   P.mode = MODE_STEP;
+  if (m->contact_model == B200SIM_CONTACT_RIGID && m->nc > 0) {
+    if (nsteps != 1) return B200SIM_E_UNSUPPORTED;
+    return launch_rigid(m, P, stream);
+  }
   return launch(m, P, dtype, stream);
 }
 
@@ -399,7 +451,18 @@ int b200sim_model_create(const B200SimModelDesc* d, int device, B200SimModel** o
                 !d->position_limit_spring || !d->position_limit_damper))
     return B200SIM_E_INVALID;
   if (nc > 0 && (!d->point_body || !d->point_position || !d->point_enabled)) return B200SIM_E_INVALID;
-  if (d->contact_model != B200SIM_CONTACT_NONE && d->contact_model != B200SIM_CONTACT_SOFT) return B200SIM_E_UNSUPPORTED;
+  if (d->contact_model != B200SIM_CONTACT_NONE && d->contact_model != B200SIM_CONTACT_SOFT &&
+      d->contact_model != B200SIM_CONTACT_RIGID)
+    return B200SIM_E_UNSUPPORTED;
+  if (d->contact_model == B200SIM_CONTACT_RIGID && nc > 0) {
+    // rigid.py:401-409 indexes the enabled subset twice: only a prefix makes that the identity
+    bool seen_disabled = false;
+    for (int k = 0; k < nc; ++k) {
+      if (!d->point_enabled[k]) seen_disabled = true;
+      else if (seen_disabled) return B200SIM_E_UNSUPPORTED;
+    }
+    if (!d->floating_base || !is_identity4(d->suc_H_i)) return B200SIM_E_UNSUPPORTED;
+  }
   if (d->parent[0] != -1) return B200SIM_E_INVALID;
   for (int i = 1; i < nL; ++i) {
     if (d->parent[i] < 0 || d->parent[i] >= i) return B200SIM_E_INVALID;  // lambda(i) < i
@@ -418,6 +481,7 @@ int b200sim_model_create(const B200SimModelDesc* d, int device, B200SimModel** o
   m->dt = d->time_step; m->g = d->gravity; m->h_terrain = d->terrain_height;
   m->K = d->soft_K; m->D = d->soft_D; m->mu = d->soft_mu; m->pexp = d->soft_p; m->qexp = d->soft_q;
   m->tau_max = d->torque_max; m->w_th = d->omega_th; m->w_max = d->omega_max;
+  m->reg = d->rigid_regularization;
 
   // ---- per-link constants
   m->cst_h.assign((size_t)nL * CREC, 0.0);
@@ -525,6 +589,16 @@ int b200sim_model_create(const B200SimModelDesc* d, int device, B200SimModel** o
   m->o_pt_idx = push(pt_idx.data(), pt_idx.size());
   m->o_pt_body = push(d->point_body, nc);
   m->o_pt_enabled = push(d->point_enabled, nc);
+  if (d->contact_model == B200SIM_CONTACT_RIGID && nc > 0) {
+    // ancestors of every link, root's child first, the link itself last
+    std::vector<int> anc((size_t)nL * std::max(maxd, 1), 0);
+    for (int i = 1; i < nL; ++i) {
+      int j = i;
+      for (int t = depth[i] - 1; t >= 0; --t) { anc[(size_t)i * maxd + t] = j; j = d->parent[j]; }
+    }
+    m->o_anc = push(anc.data(), anc.size());
+    m->o_ldepth = push(depth.data(), depth.size());
+  }
   if (m->itab_h.empty()) m->itab_h.push_back(0);
 
   // ---- upload
@@ -598,7 +672,7 @@ int b200sim_model_set_tuning(B200SimModel* m, int lanes_per_env, int envs_per_bl
 }
 
 int b200sim_model_set_options(B200SimModel* m, int32_t options) {
-  if (!m || (options & ~B200SIM_OPT_TMA_STORE)) return B200SIM_E_INVALID;
+  if (!m || (options & ~(B200SIM_OPT_TMA_STORE | B200SIM_OPT_RIGID_QP_F64))) return B200SIM_E_INVALID;
   m->opt_flags = options;
   return 0;
 }
@@ -694,6 +768,7 @@ int b200sim_step_jvp(B200SimModel* m, int64_t B, int32_t nsteps, const double* l
                      const void* sd, const void* q, const void* vlin, const void* omega, const void* p, const void* mt,
                      const void* tau, void* s_o, void* sd_o, void* q_o, void* vlin_o, void* omega_o, void* p_o,
                      void* m_o, void* W_H_B, void* iXl, void* W_H_L, void* W_v, void* stream) {
+  if (m && m->contact_model == B200SIM_CONTACT_RIGID && m->nc > 0) return B200SIM_E_UNSUPPORTED;
   if (!m || B < 0 || nsteps < 1) return B200SIM_E_INVALID;
   if (B == 0) return 0;
   if (!q || !vlin || !omega || !p || !q_o || !vlin_o || !omega_o || !p_o) return B200SIM_E_INVALID;
@@ -742,6 +817,7 @@ int b200sim_dynamics(const B200SimModel* m, int dtype, int64_t B, const void* s,
                      const void* vlin, const void* omega, const void* p, const void* mt, const void* tau,
                      const void* fext, void* pd, void* qd, void* W_vd, void* sdd, void* md, void* stream) {
   if (!m || B < 0 || (dtype != 0 && dtype != 1)) return B200SIM_E_INVALID;
+  if (m->contact_model == B200SIM_CONTACT_RIGID && m->nc > 0) return B200SIM_E_UNSUPPORTED;
   if (B == 0) return 0;
   if (!q || !vlin || !omega || !p || !W_vd) return B200SIM_E_INVALID;
   if (m->n > 0 && (!s || !sd || !sdd)) return B200SIM_E_INVALID;

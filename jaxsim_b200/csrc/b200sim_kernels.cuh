@@ -109,7 +109,9 @@ struct Params {
   int floating, contact_model, enable_friction, flags;
   int o_parent, o_jtype, o_lvl_start, o_lvl_links, o_child_start, o_child_idx, o_pt_start, o_pt_idx,
       o_pt_body, o_pt_enabled;
+  int o_anc, o_ldepth;  // rigid contacts only: ancestors of every link (root-first, [nL*depth]) and their count
   T dt, g, h_terrain, K, D, mu, pexp, qexp, tau_max, w_th, w_max;
+  T reg;                // rigid contacts: Delassus regularisation
   // ---- batch
   long long B;
   const T *s, *sd, *q, *vlin, *omega, *p, *m, *tau, *fext;

@@ -1,0 +1,1161 @@
+// jaxsim_b200 -- the rigid-contact variant of the simulation step (BASELINE config 3).
+//
+// Reference path (src/jaxsim): api/model.py:2601-2681 (step) with
+// rbda/contacts/rigid.py:222-436 (compute_contact_forces, update_velocity_after_impact),
+// api/contact.py:214-511 (contact Jacobians and their derivative), rbda/mass_inverse.py,
+// rbda/jacobian.py, api/ode.py:16-131, api/integrators.py:14-88.
+//
+// The reference assembles dense objects per environment -- M^-1 (6+n)^2, the stacked contact
+// Jacobians J, J_dot (nc,6,6+n), the Delassus matrix J M^-1 J^T (3nc)^2, a KKT matrix
+// (6+n+3nc)^2 for the impact -- and hands a QP with 3nc unknowns / 6nc inequalities to qpax.
+// None of M, M^-1, J, J_dot is ever formed here.  One warp owns one environment and keeps its
+// whole state in shared memory:
+//
+//   * kinematics, ABA (free acceleration) exactly as in the soft-contact kernel: world-aligned
+//     link-origin frames F_i, level-synchronous tree walks;
+//   * J_dot nu + J nu_dot_free of a contact point is the classical acceleration of that point,
+//     a_lin + alpha x rho + omega x pdot (plus gravity), read off the ABA's pass-3 link
+//     accelerations -- with the reference's quirk that `pdot` (and the penetration rate) come
+//     from the CACHED link velocities of the input data, which are the pre-impact velocities of
+//     the previous step (rigid.py:429-434 does not refresh the caches, api/contact.py:470-477
+//     reads them);
+//   * the Delassus matrix comes column by column from articulated-body impulse responses
+//     (unit force at an active point -> up the tree with the pass-2 quantities U_i, 1/d_i ->
+//     6x6 base solve -> down to every link that carries active points), one column per lane,
+//     O(active points x depth) instead of O((6+n)^3); only the ACTIVE points enter (the
+//     reference's QP pins the inactive ones to zero through rows 4-5 of G, rigid.py:478-492);
+//   * the QP (friction pyramids) is solved by a warp-cooperative primal-dual interior-point
+//     method (Mehrotra predictor-corrector) on a packed lower-triangular Hessian in shared
+//     memory, iterated to the resolution of the arithmetic (the reference stops qpax at 1e-3);
+//   * the contact forces act through one more articulated-body response (no second full ABA);
+//   * the impact (rigid.py:163-220: lstsq on the KKT system) is the M-orthogonal projection of
+//     nu onto {J_active nu = 0}: Delassus of the new configuration, a rank-revealing Cholesky
+//     (dependent constraints of coplanar points are skipped, which is what the minimum-norm
+//     lstsq solution amounts to for nu), and an impulse response.
+//
+// Supported: floating-base models whose base link frame is the ABA chain root (no
+// F_GENERIC_FK), enabled collidable points forming a prefix of the point list, nsteps == 1.
+#pragma once
+
+#include "b200sim_kernels.cuh"
+
+namespace b200sim {
+
+// per collidable point (words of T): lever arm rho in F_body (3), bias term (3), force (3)
+constexpr int RPT = 9;
+constexpr int RP_LEV = 0, RP_B = 3, RP_F = 6;
+constexpr int RIGID_MAX_WARPS = 8;
+
+struct RigidLayout {  // byte offsets inside one environment's (= one warp's) workspace
+  size_t links, pts, ainv, ucol, Qp, Hp, vecN, vecM, ints, total;
+};
+
+__host__ __device__ inline size_t rl_align(size_t x) { return (x + 15) & ~size_t(15); }
+
+template <typename T, typename S>
+__host__ __device__ inline RigidLayout rigid_layout(int nL, int nc, int depth) {
+  RigidLayout L;
+  size_t o = 0;
+  const size_t N = 3 * (size_t)nc, M = 5 * (size_t)nc, NP = N * (N + 1) / 2;
+  const size_t dd = depth > 0 ? depth : 1;
+  L.links = o; o = rl_align(o + sizeof(T) * (size_t)nL * REC);
+  L.pts = o;   o = rl_align(o + sizeof(T) * (size_t)nc * RPT);
+  L.ainv = o;  o = rl_align(o + sizeof(T) * 36);
+  L.ucol = o;  o = rl_align(o + sizeof(T) * 32 * dd);
+  L.Qp = o;    o = rl_align(o + sizeof(S) * NP);
+  L.Hp = o;    o = rl_align(o + sizeof(S) * NP);
+  L.vecN = o;  o = rl_align(o + sizeof(S) * 6 * N);
+  L.vecM = o;  o = rl_align(o + sizeof(S) * 7 * M);
+  L.ints = o;  o = rl_align(o + sizeof(int) * (2 * (size_t)nc + (size_t)nL + 4));
+  L.total = o;
+  return L;
+}
+
+template <typename S> struct QpTol;
+template <> struct QpTol<float> {
+  static __device__ __forceinline__ float tol() { return 2e-6f; }
+  static __device__ __forceinline__ float pivot_floor() { return 1e-7f; }
+  static __device__ __forceinline__ float rank_tol() { return 1e-4f; }
+  static constexpr int max_iter = 40;
+};
+template <> struct QpTol<double> {
+  static __device__ __forceinline__ double tol() { return 1e-11; }
+  static __device__ __forceinline__ double pivot_floor() { return 1e-15; }
+  static __device__ __forceinline__ double rank_tol() { return 1e-9; }
+  static constexpr int max_iter = 60;
+};
+
+constexpr unsigned FULL = 0xffffffffu;
+
+template <typename S>
+__device__ __forceinline__ S warp_sum(S v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+template <typename S>
+__device__ __forceinline__ S warp_max(S v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max_t(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+template <typename S>
+__device__ __forceinline__ S warp_min(S v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = min_t(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+
+__device__ __forceinline__ int pidx(int r, int c) { return r * (r + 1) / 2 + c; }  // r >= c
+
+// y = A x for a packed lower-triangular symmetric A (rows lane-strided)
+template <typename S>
+__device__ __forceinline__ void sym_matvec(const S* Ap, const S* x, S* y, int N, int lane) {
+  for (int r = lane; r < N; r += 32) {
+    S acc = S(0);
+    const S* row = Ap + pidx(r, 0);
+    for (int c = 0; c <= r; ++c) acc += row[c] * x[c];
+    for (int c = r + 1; c < N; ++c) acc += Ap[pidx(c, r)] * x[c];
+    y[r] = acc;
+  }
+}
+
+// In-place Cholesky of a packed lower-triangular matrix, warp-cooperative, right-looking.
+// `diag0` holds the diagonal before elimination.  semidef == false: pivots are floored at
+// pivot_floor * diag0 (the matrix is positive definite up to rounding).  semidef == true:
+// a pivot below rank_tol * diag0 marks a dependent row; it is skipped (L_kk = 0, column 0).
+template <typename S>
+__device__ __forceinline__ void chol_packed(S* Hp, const S* diag0, int N, int lane, bool semidef) {
+  for (int k = 0; k < N; ++k) {
+    S d = Hp[pidx(k, k)];
+    const S d0 = diag0[k];
+    bool skip = false;
+    if (semidef) {
+      skip = !(d > QpTol<S>::rank_tol() * d0);
+    } else {
+      d = max_t(d, QpTol<S>::pivot_floor() * d0);
+      if (!(d > S(0))) d = S(1);
+    }
+    const S piv = skip ? S(0) : sqrt_t(d);
+    const S ipiv = skip ? S(0) : S(1) / piv;
+    for (int r = k + 1 + lane; r < N; r += 32) Hp[pidx(r, k)] *= ipiv;
+    __syncwarp();
+    if (lane == 0) Hp[pidx(k, k)] = piv;
+    if (!skip) {
+      for (int r = k + 1 + lane; r < N; r += 32) {
+        const S lrk = Hp[pidx(r, k)];
+        S* row = Hp + pidx(r, 0);
+        for (int c = k + 1; c <= r; ++c) row[c] -= lrk * Hp[pidx(c, k)];
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// solve L L^T x = y in place (skipped rows of a semidefinite factor give x = 0)
+template <typename S>
+__device__ __forceinline__ void chol_solve(const S* Lp, S* y, int N, int lane) {
+  for (int k = 0; k < N; ++k) {
+    S yk = __shfl_sync(FULL, (lane == 0) ? y[k] : S(0), 0);
+    const S lkk = Lp[pidx(k, k)];
+    yk = (lkk > S(0)) ? yk / lkk : S(0);
+    for (int r = k + 1 + lane; r < N; r += 32) y[r] -= Lp[pidx(r, k)] * yk;
+    if (lane == 0) y[k] = yk;
+    __syncwarp();
+  }
+  for (int k = N - 1; k >= 0; --k) {
+    S xk = __shfl_sync(FULL, (lane == 0) ? y[k] : S(0), 0);
+    const S lkk = Lp[pidx(k, k)];
+    xk = (lkk > S(0)) ? xk / lkk : S(0);
+    const S* row = Lp + pidx(k, 0);
+    for (int r = lane; r < k; r += 32) y[r] -= row[r] * xk;
+    if (lane == 0) y[k] = xk;
+    __syncwarp();
+  }
+}
+
+// friction-pyramid rows of one point (rigid.py:478-489 rows 0-4): G v and G^T w
+template <typename S>
+__device__ __forceinline__ void pyr_G(S mu, const S* v, S* o) {
+  o[0] = v[0] - mu * v[2]; o[1] = v[1] - mu * v[2]; o[2] = -v[0] - mu * v[2]; o[3] = -v[1] - mu * v[2]; o[4] = -v[2];
+}
+template <typename S>
+__device__ __forceinline__ void pyr_GT(S mu, const S* w, S* o) {
+  o[0] = w[0] - w[2]; o[1] = w[1] - w[3]; o[2] = -mu * (w[0] + w[1] + w[2] + w[3]) - w[4];
+}
+
+// min 1/2 x'Qx + q'x  s.t. pyramid constraints per point; N = 3 na.  Result in x.
+template <typename S>
+__device__ __noinline__ void qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int na, S mu_f, int lane) {
+  const int N = 3 * na, M = 5 * na;
+  S* x = vN;
+  S* q = vN + N;
+  S* rd = vN + 2 * N;
+  S* dxa = vN + 3 * N;
+  S* dx = vN + 4 * N;
+  S* dg = vN + 5 * N;
+  S* s = vM;
+  S* z = vM + M;
+  S* rp = vM + 2 * M;
+  S* dsa = vM + 3 * M;
+  S* dza = vM + 4 * M;
+  S* ds = vM + 5 * M;
+  S* dz = vM + 6 * M;
+  for (int i = lane; i < N; i += 32) x[i] = S(0);
+  for (int j = lane; j < M; j += 32) { s[j] = S(1); z[j] = S(1); }
+  S qm = S(0);
+  for (int i = lane; i < N; i += 32) qm = max_t(qm, abs_t(q[i]));
+  qm = warp_max(qm);
+  __syncwarp();
+  const S tol = QpTol<S>::tol();
+  const int NP = N * (N + 1) / 2;
+  for (int it = 0; it < QpTol<S>::max_iter; ++it) {
+    // residuals
+    sym_matvec(Qp, x, rd, N, lane);
+    __syncwarp();
+    S xQx = S(0), qx = S(0), xm = S(0), Qxm = S(0);
+    for (int i = lane; i < N; i += 32) {
+      xQx += x[i] * rd[i]; qx += q[i] * x[i];
+      xm = max_t(xm, abs_t(x[i])); Qxm = max_t(Qxm, abs_t(rd[i]));
+    }
+    xQx = warp_sum(xQx); qx = warp_sum(qx); xm = warp_max(xm); Qxm = warp_max(Qxm);
+    S rdn = S(0), rpn = S(0), sz = S(0);
+    for (int a = lane; a < na; a += 32) {
+      S gz[3], gx[5];
+      pyr_GT(mu_f, z + 5 * a, gz);
+      pyr_G(mu_f, x + 3 * a, gx);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const S v = rd[3 * a + d] + q[3 * a + d] + gz[d];
+        rd[3 * a + d] = v;
+        rdn = max_t(rdn, abs_t(v));
+      }
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const S v = gx[j] + s[5 * a + j];
+        rp[5 * a + j] = v;
+        rpn = max_t(rpn, abs_t(v));
+        sz += s[5 * a + j] * z[5 * a + j];
+      }
+    }
+    rdn = warp_max(rdn); rpn = warp_max(rpn); sz = warp_sum(sz);
+    const S mu = sz / S(M);
+    if (rdn <= tol * (S(1) + qm + Qxm) && rpn <= tol * (S(1) + xm) && mu <= tol * (S(1) + abs_t(S(0.5) * xQx + qx))) break;
+    // H = Q + G' diag(z/s) G
+    for (int e = lane; e < NP; e += 32) Hp[e] = Qp[e];
+    __syncwarp();
+    for (int a = lane; a < na; a += 32) {
+      S w[5];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) w[j] = z[5 * a + j] / s[5 * a + j];
+      const int r0 = 3 * a;
+      Hp[pidx(r0, r0)] += w[0] + w[2];
+      Hp[pidx(r0 + 1, r0 + 1)] += w[1] + w[3];
+      Hp[pidx(r0 + 2, r0)] += -mu_f * (w[0] - w[2]);
+      Hp[pidx(r0 + 2, r0 + 1)] += -mu_f * (w[1] - w[3]);
+      Hp[pidx(r0 + 2, r0 + 2)] += mu_f * mu_f * (w[0] + w[1] + w[2] + w[3]) + w[4];
+    }
+    __syncwarp();
+    for (int i = lane; i < N; i += 32) dg[i] = Hp[pidx(i, i)];
+    __syncwarp();
+    chol_packed(Hp, dg, N, lane, false);
+    // predictor: r_c = s z
+    for (int a = lane; a < na; a += 32) {
+      S t[5], g[3];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) t[j] = z[5 * a + j] * (rp[5 * a + j] - s[5 * a + j]) / s[5 * a + j];
+      pyr_GT(mu_f, t, g);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) dxa[3 * a + d] = -(rd[3 * a + d] + g[d]);
+    }
+    __syncwarp();
+    chol_solve(Hp, dxa, N, lane);
+    S amax = S(1);
+    for (int a = lane; a < na; a += 32) {
+      S g[5];
+      pyr_G(mu_f, dxa + 3 * a, g);
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const S sj = s[5 * a + j], zj = z[5 * a + j];
+        const S dsj = -rp[5 * a + j] - g[j];
+        const S dzj = -(sj * zj + zj * dsj) / sj;
+        dsa[5 * a + j] = dsj; dza[5 * a + j] = dzj;
+        if (dsj < S(0)) amax = min_t(amax, -sj / dsj);
+        if (dzj < S(0)) amax = min_t(amax, -zj / dzj);
+      }
+    }
+    amax = warp_min(amax);
+    S mua = S(0);
+    for (int j = lane; j < M; j += 32) mua += (s[j] + amax * dsa[j]) * (z[j] + amax * dza[j]);
+    mua = warp_sum(mua) / S(M);
+    S sg = mua / mu;
+    sg = sg * sg * sg;
+    // corrector: r_c = s z + ds_a dz_a - sigma mu
+    for (int a = lane; a < na; a += 32) {
+      S t[5], g[3];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const S sj = s[5 * a + j], zj = z[5 * a + j];
+        const S rc = sj * zj + dsa[5 * a + j] * dza[5 * a + j] - sg * mu;
+        t[j] = (zj * rp[5 * a + j] - rc) / sj;
+      }
+      pyr_GT(mu_f, t, g);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) dx[3 * a + d] = -(rd[3 * a + d] + g[d]);
+    }
+    __syncwarp();
+    chol_solve(Hp, dx, N, lane);
+    S al = S(1e30);
+    for (int a = lane; a < na; a += 32) {
+      S g[5];
+      pyr_G(mu_f, dx + 3 * a, g);
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const S sj = s[5 * a + j], zj = z[5 * a + j];
+        const S rc = sj * zj + dsa[5 * a + j] * dza[5 * a + j] - sg * mu;
+        const S dsj = -rp[5 * a + j] - g[j];
+        const S dzj = -(rc + zj * dsj) / sj;
+        ds[5 * a + j] = dsj; dz[5 * a + j] = dzj;
+        if (dsj < S(0)) al = min_t(al, -sj / dsj);
+        if (dzj < S(0)) al = min_t(al, -zj / dzj);
+      }
+    }
+    al = min_t(S(1), S(0.99) * warp_min(al));
+    for (int i = lane; i < N; i += 32) x[i] += al * dx[i];
+    for (int j = lane; j < M; j += 32) { s[j] += al * ds[j]; z[j] += al * dz[j]; }
+    __syncwarp();
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------
+// the kernel: one warp per environment
+// ------------------------------------------------------------------------------------
+template <typename T, typename S>
+__global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(const Params<T> P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* sm_cst = reinterpret_cast<T*>(smem_raw);
+  const int nL = P.nL, n = P.n, nc = P.nc;
+  T* sm_pt = sm_cst + (size_t)nL * CREC;
+  const size_t pt_words = ((size_t)nc * 3 + 3) & ~size_t(3);
+  int* sm_itab = reinterpret_cast<int*>(sm_pt + pt_words);
+  const size_t itab_words = ((size_t)P.itab_words + 3) & ~size_t(3);
+  unsigned char* ws_base = reinterpret_cast<unsigned char*>(sm_itab + itab_words);
+
+  stage_async(sm_cst, P.cst, nL * CREC);
+  stage_async(sm_pt, P.pt_pos, (int)pt_words);
+  stage_async(sm_itab, P.itab, (int)itab_words);
+  __pipeline_commit();
+  __pipeline_wait_prior(0);
+  __syncthreads();
+
+  const int* parent = sm_itab + P.o_parent;
+  const int* jtypes = sm_itab + P.o_jtype;
+  const int* lvl_start = sm_itab + P.o_lvl_start;
+  const int* lvl_links = sm_itab + P.o_lvl_links;
+  const int* child_start = sm_itab + P.o_child_start;
+  const int* child_idx = sm_itab + P.o_child_idx;
+  const int* pt_start = sm_itab + P.o_pt_start;
+  const int* pt_idx = sm_itab + P.o_pt_idx;
+  const int* pt_body = sm_itab + P.o_pt_body;
+  const int* pt_enabled = sm_itab + P.o_pt_enabled;
+  const int* anc = sm_itab + P.o_anc;        // [nL * depth] ancestors root-first, incl. the link itself
+  const int* ldepth = sm_itab + P.o_ldepth;  // [nL]
+  const int depth = P.depth;
+
+  const int lane = threadIdx.x & 31;
+  const int wrp = threadIdx.x >> 5;
+  const RigidLayout L = rigid_layout<T, S>(nL, nc, depth);
+  unsigned char* wb = ws_base + (size_t)wrp * L.total;
+  T* ws = reinterpret_cast<T*>(wb + L.links);
+  T* pts = reinterpret_cast<T*>(wb + L.pts);
+  T* ainv = reinterpret_cast<T*>(wb + L.ainv);
+  T* ucol = reinterpret_cast<T*>(wb + L.ucol);
+  S* Qp = reinterpret_cast<S*>(wb + L.Qp);
+  S* Hp = reinterpret_cast<S*>(wb + L.Hp);
+  S* vN = reinterpret_cast<S*>(wb + L.vecN);
+  S* vM = reinterpret_cast<S*>(wb + L.vecM);
+  int* aidx = reinterpret_cast<int*>(wb + L.ints);  // [nc] compact index of an active point or -1
+  int* alist = aidx + nc;                           // [nc] point index of compact index
+  int* clist = alist + nc;                          // [nL] links that carry active points
+  const T dt = P.dt;
+  const long long stride = (long long)gridDim.x * P.envs_per_block;
+
+  for (long long env0 = (long long)blockIdx.x * P.envs_per_block; env0 < P.B; env0 += stride) {
+    const long long env = env0 + wrp;
+    if (env >= P.B) continue;  // whole warp: no block-level barrier inside the loop
+
+    // ============================================================== input state
+    for (int i = 1 + lane; i < nL; i += 32) {
+      T* ri = ws + (size_t)i * REC;
+      ri[O_S] = P.s[env * n + (i - 1)];
+      ri[O_SD] = P.sd[env * n + (i - 1)];
+      ri[O_TREF] = P.tau ? P.tau[env * n + (i - 1)] : T(0);
+    }
+    BaseState<T> b;
+    {
+      const T* q = P.q + env * 4;
+      const T qr[4] = {q[0], q[1], q[2], q[3]};
+      ldn<3>(P.p + env * 3, b.p);
+      ldn<3>(P.vlin + env * 3, b.vlin);
+      ldn<3>(P.omega + env * 3, b.w);
+      const T nrm = sqrt_t(qr[0] * qr[0] + qr[1] * qr[1] + qr[2] * qr[2] + qr[3] * qr[3]);
+      const T inv = T(1) / (nrm + Lim<T>::eps() * (nrm == T(0) ? T(1) : T(0)));  // api/data.py:283-285
+#pragma unroll
+      for (int k = 0; k < 4; ++k) b.qn[k] = qr[k] * inv;
+      quat_to_dcm(b.qn, b.R);
+    }
+
+    auto write_base_record = [&](const BaseState<T>& bs) {
+      if (lane == 0) {
+        T* r0 = ws;
+        stn<9>(r0 + O_R, bs.R);
+        stn<3>(r0 + O_P, bs.p);
+        T v0[6], t[3];
+        cross3(bs.w, bs.p, t);
+        v0[0] = bs.vlin[0] + t[0]; v0[1] = bs.vlin[1] + t[1]; v0[2] = bs.vlin[2] + t[2];
+        v0[3] = bs.w[0]; v0[4] = bs.w[1]; v0[5] = bs.w[2];
+        stn<6>(r0 + O_V, v0);
+      }
+    };
+
+    // joint transforms (relative) into the records, then the FK / velocity chain
+    auto kinematics = [&](const BaseState<T>& bs, const bool emit_adjoints) {
+      write_base_record(bs);
+      for (int i = 1 + lane; i < nL; i += 32) {
+        T* ri = ws + (size_t)i * REC;
+        T Rrel[9], trel[3];
+        joint_rel_transform(P, sm_cst + (size_t)i * CREC, jtypes[i], i, ri[O_S], Rrel, trel);
+        stn<9>(ri + O_R, Rrel);
+        stn<3>(ri + O_P, trel);
+        if (emit_adjoints && P.iXl) {
+          T X[36];
+          inverse_adjoint(X, Rrel, trel);
+          stg_vec<36>(P.iXl + (env * nL + i) * 36, X);
+        }
+      }
+      for (int l = 1; l <= depth; ++l) {
+        __syncwarp();
+        const int e = lvl_start[l + 1];
+        for (int idx = lvl_start[l] + lane; idx < e; idx += 32) {
+          const int i = lvl_links[idx];
+          const T* rp = ws + (size_t)parent[i] * REC;
+          T* ri = ws + (size_t)i * REC;
+          T Rp[9], pp[3], vp[6], Rrel[9], trel[3];
+          ldn<9>(rp + O_R, Rp);
+          ldn<3>(rp + O_P, pp);
+          ldn<6>(rp + O_V, vp);
+          ldn<9>(ri + O_R, Rrel);
+          ldn<3>(ri + O_P, trel);
+          T R[9], r[3], pw[3];
+          mat3_mul(Rp, Rrel, R);
+          mat3_vec(Rp, trel, r);
+          pw[0] = pp[0] + r[0]; pw[1] = pp[1] + r[1]; pw[2] = pp[2] + r[2];
+          T ax[3], aw[3];
+          ldn<3>(sm_cst + (size_t)i * CREC + C_AXIS, ax);
+          mat3_vec(R, ax, aw);
+          const T sdi = ri[O_SD];
+          T v[6];
+          cross3(vp + 3, r, v);
+          v[0] += vp[0]; v[1] += vp[1]; v[2] += vp[2];
+          v[3] = vp[3]; v[4] = vp[4]; v[5] = vp[5];
+          const int jt = jtypes[i];
+          if (jt == 1) { v[3] += sdi * aw[0]; v[4] += sdi * aw[1]; v[5] += sdi * aw[2]; }
+          else if (jt == 2) { v[0] += sdi * aw[0]; v[1] += sdi * aw[1]; v[2] += sdi * aw[2]; }
+          stn<9>(ri + O_R, R);
+          stn<3>(ri + O_P, pw);
+          stn<6>(ri + O_V, v);
+          stn<3>(ri + O_RR, r);
+          stn<3>(ri + O_AX, aw);
+        }
+      }
+      __syncwarp();
+    };
+
+    // collidable points of the current kinematics: lever arms, active set, and either the
+    // bias of the contact-acceleration equation (phase A) or the point velocity (impact)
+    //   returns the number of active points; fills aidx / alist / clist (ncl links)
+    int ncl = 0;
+    auto contact_points = [&](const bool impact) -> int {
+      for (int k = lane; k < nc; k += 32) {
+        const int bi = pt_body[k];
+        const T* rb = ws + (size_t)bi * REC;
+        T R[9], p[3], v[6];
+        ldn<9>(rb + O_R, R);
+        ldn<3>(rb + O_P, p);
+        ldn<6>(rb + O_V, v);
+        T Lp[3], d[3], pc[3], pd[3];
+        ldn<3>(sm_pt + 3 * k, Lp);
+        mat3_vec(R, Lp, d);
+        pc[0] = p[0] + d[0]; pc[1] = p[1] + d[1]; pc[2] = p[2] + d[2];
+        cross3(v + 3, d, pd);
+        pd[0] += v[0]; pd[1] += v[1]; pd[2] += v[2];
+        const T delta = max_t(T(0), P.h_terrain - pc[2]);  // rbda/contacts/common.py:25-63, FlatTerrain
+        const bool act = pt_enabled[k] && (delta > T(0));
+        T* pw = pts + (size_t)k * RPT;
+        stn<3>(pw + RP_LEV, d);
+        T bv[3];
+        if (impact) {
+          bv[0] = pd[0]; bv[1] = pd[1]; bv[2] = pd[2];
+        } else {
+          // pdot as the reference's contact code sees it: from the cached link velocities
+          T ps[3] = {pd[0], pd[1], pd[2]};
+          if (P.Vin) {
+            T V[6];
+            ldg_vec6(P.Vin + (env * nL + bi) * 6, V);
+            cross3(V + 3, pc, ps);
+            ps[0] += V[0]; ps[1] += V[1]; ps[2] += V[2];
+          }
+          const T ddot = -ps[2];
+          cross3(v + 3, ps, bv);                       // omega x pdot  (api/contact.py:470-477 term)
+          bv[2] -= P.K * delta + P.D * ddot;           // Baumgarte, n = z (rigid.py:527-539)
+        }
+        stn<3>(pw + RP_B, bv);
+        aidx[k] = act ? 1 : 0;
+      }
+      __syncwarp();
+      int base = 0;
+      for (int k0 = 0; k0 < nc; k0 += 32) {
+        const int k = k0 + lane;
+        const bool a = (k < nc) && (aidx[k] != 0);
+        const unsigned m = __ballot_sync(FULL, a);
+        if (k < nc) {
+          const int ci = a ? base + __popc(m & ((1u << lane) - 1u)) : -1;
+          aidx[k] = ci;
+          if (a) alist[ci] = k;
+        }
+        base += __popc(m);
+      }
+      __syncwarp();
+      // links that carry active points (ordered by link index)
+      int nl = 0;
+      for (int i0 = 0; i0 < nL; i0 += 32) {
+        const int i = i0 + lane;
+        bool has = false;
+        if (i < nL) {
+          const int e = pt_start[i + 1];
+          for (int kk = pt_start[i]; kk < e; ++kk) has = has || (aidx[pt_idx[kk]] >= 0);
+        }
+        const unsigned m = __ballot_sync(FULL, has);
+        if (has) clist[nl + __popc(m & ((1u << lane) - 1u))] = i;
+        nl += __popc(m);
+      }
+      ncl = nl;
+      __syncwarp();
+      return base;
+    };
+
+    // per-link initialisation of the ABA: inertia about the link origin in world axes, and
+    // (bias == true) velocity-product bias force, c_i, resultant joint torque
+    auto link_init = [&](const bool bias) {
+      for (int i = lane; i < nL; i += 32) {
+        T* ri = ws + (size_t)i * REC;
+        const T* c = sm_cst + (size_t)i * CREC;
+        T R[9], p[3], v[6];
+        ldn<9>(ri + O_R, R);
+        ldn<3>(ri + O_P, p);
+        ldn<6>(ri + O_V, v);
+        const T mass = c[C_MASS];
+        T com[3], cw[3], Dl[6];
+        ldn<3>(c + C_COM, com);
+        ldn<6>(c + C_DL, Dl);
+        mat3_vec(R, com, cw);
+        T Dw[6];
+        {
+          const T Df[9] = {Dl[0], Dl[1], Dl[2], Dl[1], Dl[3], Dl[4], Dl[2], Dl[4], Dl[5]};
+          T Tm[9];
+          mat3_mul(R, Df, Tm);
+          Dw[0] = Tm[0] * R[0] + Tm[1] * R[1] + Tm[2] * R[2];
+          Dw[1] = Tm[0] * R[3] + Tm[1] * R[4] + Tm[2] * R[5];
+          Dw[2] = Tm[0] * R[6] + Tm[1] * R[7] + Tm[2] * R[8];
+          Dw[3] = Tm[3] * R[3] + Tm[4] * R[4] + Tm[5] * R[5];
+          Dw[4] = Tm[3] * R[6] + Tm[4] * R[7] + Tm[5] * R[8];
+          Dw[5] = Tm[6] * R[6] + Tm[7] * R[7] + Tm[8] * R[8];
+        }
+        T pA[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+        T cc[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+        T tau = T(0);
+        if (bias) {
+          T fe[3] = {T(0), T(0), T(0)}, ne[3] = {T(0), T(0), T(0)};
+          if (P.fext) {
+            const T* fx = P.fext + (env * nL + i) * 6;
+            const T f[3] = {fx[0], fx[1], fx[2]};
+            fe[0] = f[0]; fe[1] = f[1]; fe[2] = f[2];
+            ne[0] = fx[3]; ne[1] = fx[4]; ne[2] = fx[5];
+            T t[3];
+            cross3(p, f, t);
+            ne[0] -= t[0]; ne[1] -= t[1]; ne[2] -= t[2];
+          }
+          T fI[3], nI[3], t[3];
+          cross3(v + 3, cw, t);
+          fI[0] = mass * (v[0] + t[0]); fI[1] = mass * (v[1] + t[1]); fI[2] = mass * (v[2] + t[2]);
+          sym3_vec(Dw, v + 3, nI);
+          cross3(cw, v, t);
+          nI[0] += mass * t[0]; nI[1] += mass * t[1]; nI[2] += mass * t[2];
+          cross3(v + 3, fI, pA);
+          cross3(v, fI, pA + 3);
+          cross3_add(v + 3, nI, pA + 3);
+          pA[0] -= fe[0]; pA[1] -= fe[1]; pA[2] -= fe[2];
+          pA[3] -= ne[0]; pA[4] -= ne[1]; pA[5] -= ne[2];
+          if (i > 0) {
+            const int jt = jtypes[i];
+            const T sdi = ri[O_SD];
+            T aw[3];
+            ldn<3>(ri + O_AX, aw);
+            const T vJ[3] = {sdi * aw[0], sdi * aw[1], sdi * aw[2]};
+            if (jt == 1) {
+              cross3(v, vJ, cc);
+              cross3(v + 3, vJ, cc + 3);
+            } else {
+              cross3(v + 3, vJ, cc);
+            }
+            // api/actuation_model.py:7-126
+            const T si = ri[O_S];
+            const T lower = min_t(si - c[C_SMIN], T(0));
+            const T upper = max_t(si - c[C_SMAX], T(0));
+            T tlim = -c[C_KS] * (lower + upper);
+            tlim = tlim - tlim * c[C_KD] * sdi;
+            T tfr = T(0);
+            if (P.enable_friction) {
+              const T sg = (sdi > T(0)) ? T(1) : ((sdi < T(0)) ? T(-1) : T(0));
+              tfr = -(c[C_KC] * sg + c[C_KV] * sdi);
+            }
+            const T tt = ri[O_TREF] + tfr + tlim;
+            const T av = abs_t(sdi);
+            T lim;
+            if (av <= P.w_th) lim = P.tau_max;
+            else if (av <= P.w_max) lim = P.tau_max * (T(1) - (av - P.w_th) / (P.w_max - P.w_th));
+            else lim = T(0);
+            tau = min_t(max_t(tt, -lim), lim);
+          }
+        }
+        T IA[21];
+        IA[0] = mass; IA[1] = T(0); IA[2] = T(0); IA[3] = mass; IA[4] = T(0); IA[5] = mass;
+        IA[6] = T(0);            IA[7] = mass * cw[2];   IA[8] = -mass * cw[1];
+        IA[9] = -mass * cw[2];   IA[10] = T(0);          IA[11] = mass * cw[0];
+        IA[12] = mass * cw[1];   IA[13] = -mass * cw[0]; IA[14] = T(0);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) IA[15 + k] = Dw[k];
+        stn<21>(ri + O_IA, IA);
+        stn<6>(ri + O_PA, pA);
+        stn<6>(ri + O_C, cc);
+        ri[O_TAU] = tau;
+      }
+    };
+
+    // ABA pass 2 (rbda/aba.py:173-231) + inverse of the base articulated inertia
+    auto pass2 = [&]() {
+      for (int l = depth; l >= 1; --l) {
+        __syncwarp();
+        const int e = lvl_start[l + 1];
+        for (int idx = lvl_start[l] + lane; idx < e; idx += 32) {
+          const int i = lvl_links[idx];
+          T* ri = ws + (size_t)i * REC;
+          T A[6], Bm[9], D[6], pA[6];
+          ldn<6>(ri + O_IA, A);
+          ldn<9>(ri + O_IB, Bm);
+          ldn<6>(ri + O_ID, D);
+          ldn<6>(ri + O_PA, pA);
+          const int ce = child_start[i + 1];
+          for (int cc = child_start[i]; cc < ce; ++cc) {
+            const T* rc = ws + (size_t)child_idx[cc] * REC;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) A[k] += rc[O_IA + k];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) Bm[k] += rc[O_IB + k];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) D[k] += rc[O_ID + k];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) pA[k] += rc[O_PA + k];
+          }
+          T aw[3], cI[6], r[3];
+          ldn<3>(ri + O_AX, aw);
+          ldn<6>(ri + O_C, cI);
+          ldn<3>(ri + O_RR, r);
+          const int jt = jtypes[i];
+          T Ul[3], Ua[3], d, u;
+          const T tau = ri[O_TAU];
+          if (jt == 1) {
+            mat3_vec(Bm, aw, Ul);
+            sym3_vec(D, aw, Ua);
+            d = dot3(aw, Ua);
+            u = tau - dot3(aw, pA + 3);
+          } else {
+            sym3_vec(A, aw, Ul);
+            mat3T_vec(Bm, aw, Ua);
+            d = dot3(aw, Ul);
+            u = tau - dot3(aw, pA);
+          }
+          const T dinv = T(1) / d;
+          stn<3>(ri + O_U, Ul);
+          stn<3>(ri + O_U + 3, Ua);
+          ri[O_DINV] = dinv;
+          ri[O_UU] = u;
+          const T Uls[3] = {Ul[0] * dinv, Ul[1] * dinv, Ul[2] * dinv};
+          const T Uas[3] = {Ua[0] * dinv, Ua[1] * dinv, Ua[2] * dinv};
+          A[0] -= Uls[0] * Ul[0]; A[1] -= Uls[0] * Ul[1]; A[2] -= Uls[0] * Ul[2];
+          A[3] -= Uls[1] * Ul[1]; A[4] -= Uls[1] * Ul[2]; A[5] -= Uls[2] * Ul[2];
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int bb = 0; bb < 3; ++bb) Bm[3 * a + bb] -= Uls[a] * Ua[bb];
+          D[0] -= Uas[0] * Ua[0]; D[1] -= Uas[0] * Ua[1]; D[2] -= Uas[0] * Ua[2];
+          D[3] -= Uas[1] * Ua[1]; D[4] -= Uas[1] * Ua[2]; D[5] -= Uas[2] * Ua[2];
+          const T ud = u * dinv;
+          T pa[6], t3[3];
+          sym3_vec(A, cI, t3);
+          pa[0] = pA[0] + t3[0] + Ul[0] * ud; pa[1] = pA[1] + t3[1] + Ul[1] * ud; pa[2] = pA[2] + t3[2] + Ul[2] * ud;
+          mat3_vec(Bm, cI + 3, t3);
+          pa[0] += t3[0]; pa[1] += t3[1]; pa[2] += t3[2];
+          mat3T_vec(Bm, cI, t3);
+          pa[3] = pA[3] + t3[0] + Ua[0] * ud; pa[4] = pA[4] + t3[1] + Ua[1] * ud; pa[5] = pA[5] + t3[2] + Ua[2] * ud;
+          sym3_vec(D, cI + 3, t3);
+          pa[3] += t3[0]; pa[4] += t3[1]; pa[5] += t3[2];
+          const T Af[9] = {A[0], A[1], A[2], A[1], A[3], A[4], A[2], A[4], A[5]};
+          T B2[9];
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            T rowx[3];
+            cross3(Af + 3 * a, r, rowx);
+            B2[3 * a] = Bm[3 * a] - rowx[0]; B2[3 * a + 1] = Bm[3 * a + 1] - rowx[1]; B2[3 * a + 2] = Bm[3 * a + 2] - rowx[2];
+          }
+          T SB1[9], SB2[9];
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const T c1[3] = {Bm[j], Bm[3 + j], Bm[6 + j]};
+            const T c2[3] = {B2[j], B2[3 + j], B2[6 + j]};
+            T o1[3], o2[3];
+            cross3(r, c1, o1);
+            cross3(r, c2, o2);
+            SB1[j] = o1[0]; SB1[3 + j] = o1[1]; SB1[6 + j] = o1[2];
+            SB2[j] = o2[0]; SB2[3 + j] = o2[1]; SB2[6 + j] = o2[2];
+          }
+          T D2[6];
+          D2[0] = D[0] + SB1[0] + SB2[0];
+          D2[1] = D[1] + SB1[1] + SB2[3];
+          D2[2] = D[2] + SB1[2] + SB2[6];
+          D2[3] = D[3] + SB1[4] + SB2[4];
+          D2[4] = D[4] + SB1[5] + SB2[7];
+          D2[5] = D[5] + SB1[8] + SB2[8];
+          cross3_add(r, pa, pa + 3);
+          stn<6>(ri + O_IA, A);
+          stn<9>(ri + O_IB, B2);
+          stn<6>(ri + O_ID, D2);
+          stn<6>(ri + O_PA, pa);
+        }
+      }
+      __syncwarp();
+      // base: total articulated inertia, its inverse (one column per lane), total bias
+      if (lane < 6) {
+        T* r0 = ws;
+        T A[6], Bm[9], D[6];
+        ldn<6>(r0 + O_IA, A);
+        ldn<9>(r0 + O_IB, Bm);
+        ldn<6>(r0 + O_ID, D);
+        const int ce = child_start[1];
+        for (int cc = child_start[0]; cc < ce; ++cc) {
+          const T* rc = ws + (size_t)child_idx[cc] * REC;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) A[k] += rc[O_IA + k];
+#pragma unroll
+          for (int k = 0; k < 9; ++k) Bm[k] += rc[O_IB + k];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) D[k] += rc[O_ID + k];
+        }
+        T Mx[6][6];
+        Mx[0][0] = A[0]; Mx[0][1] = A[1]; Mx[0][2] = A[2]; Mx[1][1] = A[3]; Mx[1][2] = A[4]; Mx[2][2] = A[5];
+        Mx[1][0] = A[1]; Mx[2][0] = A[2]; Mx[2][1] = A[4];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int bb = 0; bb < 3; ++bb) { Mx[a][3 + bb] = Bm[3 * a + bb]; Mx[3 + bb][a] = Bm[3 * a + bb]; }
+        Mx[3][3] = D[0]; Mx[3][4] = D[1]; Mx[3][5] = D[2]; Mx[4][4] = D[3]; Mx[4][5] = D[4]; Mx[5][5] = D[5];
+        Mx[4][3] = D[1]; Mx[5][3] = D[2]; Mx[5][4] = D[4];
+        T e[6], x[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) e[k] = (k == lane) ? T(-1) : T(0);
+        solve6_spd_neg(Mx, e, x);  // x = M^-1 e_lane
+#pragma unroll
+        for (int k = 0; k < 6; ++k) ainv[6 * k + lane] = x[k];
+      }
+      __syncwarp();
+    };
+
+    // total bias force at the base (own + children), all lanes
+    auto base_bias = [&](T* pA0) {
+      ldn<6>(ws + O_PA, pA0);
+      const int ce = child_start[1];
+      for (int cc = child_start[0]; cc < ce; ++cc) {
+        const T* rc = ws + (size_t)child_idx[cc] * REC;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) pA0[k] += rc[O_PA + k];
+      }
+    };
+    auto ainv_neg_mul = [&](const T* f, T* a) {  // a = -Ainv f
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        T acc = T(0);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) acc += ainv[6 * r + c] * f[c];
+        a[r] = -acc;
+      }
+    };
+
+    // articulated-body response of the whole tree to point forces (RP_F of the active
+    // points): delta acceleration of every link into O_C, of every joint into O_TAU.
+    // Uses U_i, 1/d_i, r_i, axes and Ainv of the last pass2().
+    auto tree_response = [&]() {
+      for (int i = lane; i < nL; i += 32) {
+        T* ri = ws + (size_t)i * REC;
+        T w[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+        const int e = pt_start[i + 1];
+        for (int kk = pt_start[i]; kk < e; ++kk) {
+          const int k = pt_idx[kk];
+          if (aidx[k] < 0) continue;
+          const T* pw = pts + (size_t)k * RPT;
+          T f[3], lev[3];
+          ldn<3>(pw + RP_F, f);
+          ldn<3>(pw + RP_LEV, lev);
+          w[0] -= f[0]; w[1] -= f[1]; w[2] -= f[2];
+          T t[3];
+          cross3(lev, f, t);
+          w[3] -= t[0]; w[4] -= t[1]; w[5] -= t[2];
+        }
+        stn<6>(ri + O_PA, w);
+      }
+      for (int l = depth; l >= 1; --l) {
+        __syncwarp();
+        const int e = lvl_start[l + 1];
+        for (int idx = lvl_start[l] + lane; idx < e; idx += 32) {
+          const int i = lvl_links[idx];
+          T* ri = ws + (size_t)i * REC;
+          T pA[6];
+          ldn<6>(ri + O_PA, pA);
+          const int ce = child_start[i + 1];
+          for (int cc = child_start[i]; cc < ce; ++cc) {
+            const T* rc = ws + (size_t)child_idx[cc] * REC;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) pA[k] += rc[O_PA + k];
+          }
+          T aw[3], U[6], r[3];
+          ldn<3>(ri + O_AX, aw);
+          ldn<6>(ri + O_U, U);
+          ldn<3>(ri + O_RR, r);
+          const T u = (jtypes[i] == 1) ? -dot3(aw, pA + 3) : -dot3(aw, pA);
+          ri[O_UU] = u;
+          const T ud = u * ri[O_DINV];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) pA[k] += U[k] * ud;
+          cross3_add(r, pA, pA + 3);
+          stn<6>(ri + O_PA, pA);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        T pA0[6], a0[6];
+        base_bias(pA0);
+        ainv_neg_mul(pA0, a0);
+        stn<6>(ws + O_C, a0);
+      }
+      for (int l = 1; l <= depth; ++l) {
+        __syncwarp();
+        const int e = lvl_start[l + 1];
+        for (int idx = lvl_start[l] + lane; idx < e; idx += 32) {
+          const int i = lvl_links[idx];
+          T* ri = ws + (size_t)i * REC;
+          const T* rp = ws + (size_t)parent[i] * REC;
+          T ap[6], r[3], U[6], aw[3];
+          ldn<6>(rp + O_C, ap);
+          ldn<3>(ri + O_RR, r);
+          ldn<6>(ri + O_U, U);
+          ldn<3>(ri + O_AX, aw);
+          T a[6];
+          cross3(ap + 3, r, a);
+          a[0] += ap[0]; a[1] += ap[1]; a[2] += ap[2];
+          a[3] = ap[3]; a[4] = ap[4]; a[5] = ap[5];
+          const T sdd = (ri[O_UU] - (U[0] * a[0] + U[1] * a[1] + U[2] * a[2] + U[3] * a[3] + U[4] * a[4] + U[5] * a[5])) * ri[O_DINV];
+          if (jtypes[i] == 1) { a[3] += sdd * aw[0]; a[4] += sdd * aw[1]; a[5] += sdd * aw[2]; }
+          else { a[0] += sdd * aw[0]; a[1] += sdd * aw[1]; a[2] += sdd * aw[2]; }
+          stn<6>(ri + O_C, a);
+          ri[O_TAU] = sdd;
+        }
+      }
+      __syncwarp();
+    };
+
+    // Delassus matrix of the active points, packed lower triangle, one column per lane:
+    // response to a unit force e_d at point a, evaluated at every active point
+    auto delassus = [&](const int na, const S reg) {
+      const int N = 3 * na;
+      for (int col = lane; col < N; col += 32) {
+        const int a = col / 3, d = col - 3 * a;
+        const int k = alist[a];
+        const int lk = pt_body[k];
+        T lev[3];
+        ldn<3>(pts + (size_t)k * RPT + RP_LEV, lev);
+        T pa[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+        pa[d] = T(-1);
+        {
+          T e[3] = {T(0), T(0), T(0)}, t[3];
+          e[d] = T(1);
+          cross3(lev, e, t);
+          pa[3] = -t[0]; pa[4] = -t[1]; pa[5] = -t[2];
+        }
+        const int dk = ldepth[lk];
+        int i = lk;
+        for (int t = dk - 1; t >= 0; --t) {
+          const T* ri = ws + (size_t)i * REC;
+          T aw[3], U[6], r[3];
+          ldn<3>(ri + O_AX, aw);
+          ldn<6>(ri + O_U, U);
+          ldn<3>(ri + O_RR, r);
+          const T u = (jtypes[i] == 1) ? -dot3(aw, pa + 3) : -dot3(aw, pa);
+          ucol[t * 32 + lane] = u;
+          const T ud = u * ri[O_DINV];
+#pragma unroll
+          for (int q = 0; q < 6; ++q) pa[q] += U[q] * ud;
+          cross3_add(r, pa, pa + 3);
+          i = parent[i];
+        }
+        T a0[6];
+        ainv_neg_mul(pa, a0);
+        for (int ci = 0; ci < ncl; ++ci) {
+          const int j = clist[ci];
+          const int dj = ldepth[j];
+          T acc[6];
+#pragma unroll
+          for (int q = 0; q < 6; ++q) acc[q] = a0[q];
+          for (int t = 0; t < dj; ++t) {
+            const int li = anc[j * depth + t];
+            const T* ri = ws + (size_t)li * REC;
+            T aw[3], U[6], r[3];
+            ldn<3>(ri + O_AX, aw);
+            ldn<6>(ri + O_U, U);
+            ldn<3>(ri + O_RR, r);
+            cross3_add(acc + 3, r, acc);
+            const T ut = (t < dk && anc[lk * depth + t] == li) ? ucol[t * 32 + lane] : T(0);
+            const T sdd = (ut - (U[0] * acc[0] + U[1] * acc[1] + U[2] * acc[2] + U[3] * acc[3] + U[4] * acc[4] + U[5] * acc[5])) * ri[O_DINV];
+            if (jtypes[li] == 1) { acc[3] += sdd * aw[0]; acc[4] += sdd * aw[1]; acc[5] += sdd * aw[2]; }
+            else { acc[0] += sdd * aw[0]; acc[1] += sdd * aw[1]; acc[2] += sdd * aw[2]; }
+          }
+          const int e = pt_start[j + 1];
+          for (int kk = pt_start[j]; kk < e; ++kk) {
+            const int k2 = pt_idx[kk];
+            const int a2 = aidx[k2];
+            if (a2 < 0) continue;
+            T lev2[3], val[3];
+            ldn<3>(pts + (size_t)k2 * RPT + RP_LEV, lev2);
+            cross3(acc + 3, lev2, val);
+            val[0] += acc[0]; val[1] += acc[1]; val[2] += acc[2];
+#pragma unroll
+            for (int d2 = 0; d2 < 3; ++d2) {
+              const int row = 3 * a2 + d2;
+              if (row >= col) Qp[pidx(row, col)] = S(val[d2]) + ((row == col) ? reg : S(0));
+            }
+          }
+        }
+      }
+      __syncwarp();
+    };
+
+    // ============================================================== phase A: state at t
+    kinematics(b, false);
+    const int na = contact_points(false);
+    link_init(true);
+    pass2();
+    // free acceleration (ABA pass 3, rbda/aba.py:233-288)
+    if (lane == 0) {
+      T pA0[6], a0[6];
+      base_bias(pA0);
+      ainv_neg_mul(pA0, a0);
+      stn<6>(ws + O_V, a0);
+    }
+    for (int l = 1; l <= depth; ++l) {
+      __syncwarp();
+      const int e = lvl_start[l + 1];
+      for (int idx = lvl_start[l] + lane; idx < e; idx += 32) {
+        const int i = lvl_links[idx];
+        T* ri = ws + (size_t)i * REC;
+        const T* rp = ws + (size_t)parent[i] * REC;
+        T ap[6], r[3], cI[6], U[6], aw[3];
+        ldn<6>(rp + O_V, ap);
+        ldn<3>(ri + O_RR, r);
+        ldn<6>(ri + O_C, cI);
+        ldn<6>(ri + O_U, U);
+        ldn<3>(ri + O_AX, aw);
+        T a[6];
+        cross3(ap + 3, r, a);
+        a[0] += ap[0] + cI[0]; a[1] += ap[1] + cI[1]; a[2] += ap[2] + cI[2];
+        a[3] = ap[3] + cI[3]; a[4] = ap[4] + cI[4]; a[5] = ap[5] + cI[5];
+        const T sdd = (ri[O_UU] - (U[0] * a[0] + U[1] * a[1] + U[2] * a[2] + U[3] * a[3] + U[4] * a[4] + U[5] * a[5])) * ri[O_DINV];
+        if (jtypes[i] == 1) { a[3] += sdd * aw[0]; a[4] += sdd * aw[1]; a[5] += sdd * aw[2]; }
+        else { a[0] += sdd * aw[0]; a[1] += sdd * aw[1]; a[2] += sdd * aw[2]; }
+        stn<6>(ri + O_V, a);
+        ri[O_SDD] = sdd;
+      }
+    }
+    __syncwarp();
+
+    T a0t[6];  // base acceleration in F_0 (gravity-shifted), free + contact response
+    ldn<6>(ws + O_V, a0t);
+    if (na > 0) {
+      // q = J_dot nu + J nu_dot_free - baumgarte  (rigid.py:316-343)
+      S* q = vN + 3 * na;
+      for (int a = lane; a < na; a += 32) {
+        const int k = alist[a];
+        const T* rb = ws + (size_t)pt_body[k] * REC;
+        const T* pw = pts + (size_t)k * RPT;
+        T acc[6], lev[3], bv[3], val[3];
+        ldn<6>(rb + O_V, acc);
+        ldn<3>(pw + RP_LEV, lev);
+        ldn<3>(pw + RP_B, bv);
+        cross3(acc + 3, lev, val);
+        q[3 * a + 0] = S(val[0] + acc[0] + bv[0]);
+        q[3 * a + 1] = S(val[1] + acc[1] + bv[1]);
+        q[3 * a + 2] = S(val[2] + acc[2] + P.g + bv[2]);
+      }
+      delassus(na, S(P.reg));
+      qp_pyramids<S>(Qp, Hp, vN, vM, na, S(P.mu), lane);
+      for (int a = lane; a < na; a += 32) {
+        T* pw = pts + (size_t)alist[a] * RPT;
+        pw[RP_F] = T(vN[3 * a]); pw[RP_F + 1] = T(vN[3 * a + 1]); pw[RP_F + 2] = T(vN[3 * a + 2]);
+      }
+      __syncwarp();
+      tree_response();
+      for (int i = 1 + lane; i < nL; i += 32) {
+        T* ri = ws + (size_t)i * REC;
+        ri[O_SDD] += ri[O_TAU];
+      }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) a0t[k] += ws[O_C + k];
+    }
+    __syncwarp();
+
+    // ============================================================== semi-implicit Euler
+    T Wa[6];
+    cross3(b.p, a0t + 3, Wa);
+    Wa[0] += a0t[0]; Wa[1] += a0t[1]; Wa[2] += a0t[2] + P.g;
+    Wa[3] = a0t[3]; Wa[4] = a0t[4]; Wa[5] = a0t[5];
+    {
+      BaseState<T> nb;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { nb.vlin[k] = b.vlin[k] + dt * Wa[k]; nb.w[k] = b.w[k] + dt * Wa[3 + k]; }
+      T pd[3];
+      cross3(nb.w, b.p, pd);
+      pd[0] += nb.vlin[0]; pd[1] += nb.vlin[1]; pd[2] += nb.vlin[2];
+      const T nw = sqrt_t(dot3(nb.w, nb.w));
+      const T nq = sqrt_t(b.qn[0] * b.qn[0] + b.qn[1] * b.qn[1] + b.qn[2] * b.qn[2] + b.qn[3] * b.qn[3]);
+      const T v0 = T(0.1) * nw * (T(1) - nq);
+      const T qw = b.qn[0], qx = b.qn[1], qy = b.qn[2], qz = b.qn[3];
+      const T wx = nb.w[0], wy = nb.w[1], wz = nb.w[2];
+      T qd[4];
+      qd[0] = T(0.5) * (qw * v0 - qx * wx - qy * wy - qz * wz);
+      qd[1] = T(0.5) * (qx * v0 + qw * wx + qz * wy - qy * wz);
+      qd[2] = T(0.5) * (qy * v0 - qz * wx + qw * wy + qx * wz);
+      qd[3] = T(0.5) * (qz * v0 + qy * wx - qx * wy + qw * wz);
+      T qn2[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) qn2[k] = b.qn[k] + dt * qd[k];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) nb.p[k] = b.p[k] + dt * pd[k];
+#pragma unroll
+      for (int rep = 0; rep < 2; ++rep) {
+        const T nn = sqrt_t(qn2[0] * qn2[0] + qn2[1] * qn2[1] + qn2[2] * qn2[2] + qn2[3] * qn2[3]);
+        const T inv = T(1) / ((nn == T(0)) ? T(1) : nn);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) qn2[k] *= inv;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) nb.qn[k] = qn2[k];
+      quat_to_dcm(nb.qn, nb.R);
+      b = nb;
+    }
+    for (int i = 1 + lane; i < nL; i += 32) {
+      T* ri = ws + (size_t)i * REC;
+      const T sdn = ri[O_SD] + dt * ri[O_SDD];
+      ri[O_SD] = sdn;
+      ri[O_S] = ri[O_S] + dt * sdn;
+    }
+    __syncwarp();
+
+    // ============================================================== phase B: state at t+dt
+    // kinematics of the new state with the PRE-impact velocities: these are the caches the
+    // reference returns (rigid.py:429-434 leaves them untouched)
+    kinematics(b, true);
+    if (lane == 0) {
+      stn<4>(P.q_o + env * 4, b.qn);
+      stn<3>(P.p_o + env * 3, b.p);
+      if (P.W_H_B) store_transform(P.W_H_B + env * 16, b.R, b.p);
+      if (P.iXl) {
+        T R0[9], p0[3], t[3], X[36];
+        mat3_mul(b.R, sm_cst + C_M0, R0);
+        mat3_vec(b.R, sm_cst + C_TPRE, t);
+        p0[0] = b.p[0] + t[0]; p0[1] = b.p[1] + t[1]; p0[2] = b.p[2] + t[2];
+        inverse_adjoint(X, R0, p0);
+        stg_vec<36>(P.iXl + env * nL * 36, X);
+      }
+    }
+    for (int i = lane; i < nL; i += 32) {
+      const T* ri = ws + (size_t)i * REC;
+      T R[9], p[3], v[6];
+      ldn<9>(ri + O_R, R);
+      ldn<3>(ri + O_P, p);
+      ldn<6>(ri + O_V, v);
+      if (P.W_H_L) store_transform(P.W_H_L + (env * nL + i) * 16, R, p);
+      if (P.W_v) {
+        T t[3];
+        cross3(p, v + 3, t);
+        const T o[6] = {v[0] + t[0], v[1] + t[1], v[2] + t[2], v[3], v[4], v[5]};
+        stg_vec6(P.W_v + (env * nL + i) * 6, o);
+      }
+    }
+    for (int i = 1 + lane; i < nL; i += 32) P.s_o[env * n + (i - 1)] = ws[(size_t)i * REC + O_S];
+
+    // impact (rigid.py:385-436): project nu onto {velocity of the active points = 0}
+    const int na2 = contact_points(true);
+    T dv0[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+    if (na2 > 0) {
+      link_init(false);
+      pass2();
+      delassus(na2, S(0));
+      const int N2 = 3 * na2;
+      S* lam = vN;
+      S* dg = vN + 5 * N2;
+      for (int a = lane; a < na2; a += 32) {
+        const T* pw = pts + (size_t)alist[a] * RPT;
+        lam[3 * a] = -S(pw[RP_B]); lam[3 * a + 1] = -S(pw[RP_B + 1]); lam[3 * a + 2] = -S(pw[RP_B + 2]);
+      }
+      for (int i = lane; i < N2; i += 32) dg[i] = Qp[pidx(i, i)];
+      __syncwarp();
+      chol_packed(Qp, dg, N2, lane, true);
+      chol_solve(Qp, lam, N2, lane);
+      for (int a = lane; a < na2; a += 32) {
+        T* pw = pts + (size_t)alist[a] * RPT;
+        pw[RP_F] = T(lam[3 * a]); pw[RP_F + 1] = T(lam[3 * a + 1]); pw[RP_F + 2] = T(lam[3 * a + 2]);
+      }
+      __syncwarp();
+      tree_response();
+      ldn<6>(ws + O_C, dv0);
+      for (int i = 1 + lane; i < nL; i += 32) {
+        T* ri = ws + (size_t)i * REC;
+        ri[O_SD] += ri[O_TAU];
+      }
+    }
+    __syncwarp();
+    for (int i = 1 + lane; i < nL; i += 32) P.sd_o[env * n + (i - 1)] = ws[(size_t)i * REC + O_SD];
+    if (lane == 0) {
+      // base: F_0 coordinates [pdot_B; omega] -> inertial-fixed linear part
+      T t[3], w2[3], pdB[3];
+      cross3(b.w, b.p, t);
+      pdB[0] = b.vlin[0] + t[0] + dv0[0]; pdB[1] = b.vlin[1] + t[1] + dv0[1]; pdB[2] = b.vlin[2] + t[2] + dv0[2];
+      w2[0] = b.w[0] + dv0[3]; w2[1] = b.w[1] + dv0[4]; w2[2] = b.w[2] + dv0[5];
+      cross3(w2, b.p, t);
+      const T vl[3] = {pdB[0] - t[0], pdB[1] - t[1], pdB[2] - t[2]};
+      stn<3>(P.vlin_o + env * 3, vl);
+      stn<3>(P.omega_o + env * 3, w2);
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace b200sim

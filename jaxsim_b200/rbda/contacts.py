@@ -40,10 +40,43 @@ class SoftContacts:
 
 
 @dataclasses.dataclass(frozen=True)
-class RigidContacts:
-    """Tag for ``rbda/contacts/rigid.py`` -- not implemented by the kernel yet: building a
-    model with it raises ``NotImplementedError`` (DESIGN.md "out of scope")."""
+class RigidContactsParams:
+    """``RigidContactsParams`` (``rbda/contacts/rigid.py:27-96``): friction coefficient and the
+    Baumgarte gains of the contact constraint (both zero by default)."""
+
+    mu: float = 0.5
+    K: float = 0.0
+    D: float = 0.0
 
     @classmethod
-    def build(cls, **kwargs) -> "RigidContacts":
-        return cls()
+    def build(cls, *, mu=None, K=None, D=None, **kwargs) -> "RigidContactsParams":
+        return cls(mu=float(0.5 if mu is None else mu), K=float(0.0 if K is None else K),
+                   D=float(0.0 if D is None else D))
+
+    def valid(self) -> bool:
+        return all(v >= 0.0 for v in (self.mu, self.K, self.D))
+
+
+@dataclasses.dataclass(frozen=True)
+class RigidContacts:
+    """Tag + static options of the rigid-contact model (``rbda/contacts/rigid.py:99-160``).
+
+    ``solver_options`` is accepted for signature compatibility.  The reference forwards it to
+    ``qpax.solve_qp`` (default ``solver_tol=1e-3``); the kernel's interior-point solver always
+    iterates to the resolution of its arithmetic (DESIGN.md "rigid contacts"), i.e. it returns
+    the optimum the reference's solver approximates."""
+
+    regularization_delassus: float = 1e-6
+    solver_options: tuple = (("solver_tol", 1e-3),)
+
+    _parameters_class = RigidContactsParams
+
+    @classmethod
+    def build(cls, regularization_delassus=None, solver_options=None, **kwargs) -> "RigidContacts":
+        opts = {"solver_tol": 1e-3} | (dict(solver_options) if solver_options is not None else {})
+        try:
+            hash(tuple(opts.values()))
+        except TypeError as exc:
+            raise ValueError("The values of the solver options must be hashable.") from exc
+        return cls(regularization_delassus=float(1e-6 if regularization_delassus is None else regularization_delassus),
+                   solver_options=tuple(opts.items()))

@@ -208,7 +208,8 @@ class OracleModel:
     time_step: float = 0.001
     gravity: float = -9.81  # model.gravity (api/model.py:62,206): NEGATIVE
     terrain_height: float = 0.0  # FlatTerrain (terrain/terrain.py:66-113)
-    contact_model: str = "soft"  # "soft" | "none"
+    contact_model: str = "soft"  # "soft" | "rigid" (oracle/rigid_oracle.py) | "none"
+    regularization_delassus: float = 1e-6  # RigidContacts (rbda/contacts/rigid.py:99-101)
     # SoftContactsParams (rbda/contacts/soft.py:24-46)
     K: float = 1e6
     D: float = 2000.0
@@ -811,7 +812,8 @@ def random_model_data(model: OracleModel, B: int, seed: int = 0, dtype=np.float6
     """``random_model_data`` (``api/data.py:552-682``): same distributions, NumPy Philox
     stream (JAX's threefry stream cannot be reproduced without JAX).  ``in_contact=True``
     is this repo's second distribution: the base is lowered so that the
-    lowest collidable point penetrates the ground by up to 5 mm."""
+    lowest collidable point penetrates the ground by up to 5 mm; ``in_contact="flat"`` also
+    levels the base and zeroes the joints (+-1e-3) so that several points touch at once."""
     rng = np.random.Generator(np.random.Philox(seed))
     n = model.dofs()
     p = rng.uniform(np.array(base_pos_bounds[0], float), np.array(base_pos_bounds[1], float), size=(B, 3))
@@ -830,12 +832,20 @@ def random_model_data(model: OracleModel, B: int, seed: int = 0, dtype=np.float6
     if in_contact and model.floating_base and len(model.kin_dyn_parameters.contact_parameters.body) > 0:
         # moderate attitude so that feet/corners point down, then drop to touch the ground
         rpy = rng.uniform(-0.3, 0.3, size=(B, 3))
+        lo = 0.0
+        if in_contact == "flat":
+            # near the zero pose with a level base: whole faces / soles touch the ground, so
+            # that several collidable points are active at once (rigid-contact parity cases)
+            rpy = rng.uniform(-1e-3, 1e-3, size=(B, 3))
+            jp = model.kin_dyn_parameters.joint_parameters
+            s = np.clip(rng.uniform(-1e-3, 1e-3, size=(B, n)), jp.position_limits_min, jp.position_limits_max) if n > 0 else s
+            lo = 0.002
         q = _quat_from_euler_xyz_intrinsic(rpy)
         d0 = data_replace(model, s, sd, q, v, w, p)
         W_p_C, _ = collidable_points_pos_vel(model, d0.link_transforms, d0.link_velocities)
         zmin = W_p_C[..., 2].min(axis=1)
         p = p.copy()
-        p[:, 2] += model.terrain_height - zmin - rng.uniform(0.0, 0.005, size=B)
+        p[:, 2] += model.terrain_height - zmin - rng.uniform(lo, 0.005, size=B)
         v = 0.1 * v
         w = 0.1 * w
         sd = 0.1 * sd

@@ -7,7 +7,7 @@ import numpy as np
 
 import jaxsim_b200.api as js
 from jaxsim_b200 import models
-from jaxsim_b200.rbda.contacts import SoftContacts
+from jaxsim_b200.rbda.contacts import RigidContacts, SoftContacts
 from oracle import jaxsim_oracle as O
 
 # north_star tolerances: 1e-5 rel (fp64) / 1e-3 rel (fp32)
@@ -21,13 +21,19 @@ def build_model(name: str, **kw):
 def oracle_model(model) -> O.OracleModel:
     prm = model.contact_params
     soft = isinstance(model.contact_model, SoftContacts)
+    rigid = isinstance(model.contact_model, RigidContacts)
+    kw = dict(K=prm.K, D=prm.D, mu=prm.mu)
+    if soft:
+        kw.update(p=prm.p, q=prm.q)
+    if rigid:
+        kw.update(regularization_delassus=model.contact_model.regularization_delassus)
     return O.OracleModel(
         kin_dyn_parameters=model.kin_dyn_parameters, floating_base=model.floating_base(),
         time_step=model.time_step, gravity=model.gravity, terrain_height=model.terrain.height(),
-        contact_model="soft" if soft else "none",
-        K=prm.K, D=prm.D, mu=prm.mu, p=prm.p, q=prm.q,
+        contact_model="soft" if soft else ("rigid" if rigid else "none"),
         torque_max=model.actuation_params.torque_max, omega_th=model.actuation_params.omega_th,
         omega_max=model.actuation_params.omega_max, enable_friction=model.actuation_params.enable_friction,
+        **kw,
     )
 
 

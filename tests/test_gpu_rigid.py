@@ -1,0 +1,134 @@
+"""-m gpu: the rigid-contact step (BASELINE config 3) through the C ABI
+against ``oracle/rigid_oracle.py`` on the same inputs.
+
+Parity is defined on the optimum of the contact QP (the reference stops ``qpax`` at
+``solver_tol=1e-3``; see the oracle's module docstring), tolerance = north_star's
+1e-5 rel (fp64) / 1e-3 rel (fp32) on every leaf of the returned data."""
+
+import dataclasses
+
+import numpy as np
+import pytest
+
+import jaxsim_b200.api as js
+from jaxsim_b200.rbda.contacts import RigidContacts, RigidContactsParams
+from oracle import jaxsim_oracle as O
+from oracle import rigid_oracle as R
+
+from . import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _dtype(name):
+    import torch
+
+    return {"float64": torch.float64, "float32": torch.float32}[name]
+
+
+def _model(name, **params):
+    return H.build_model(name, contact_model=RigidContacts.build(), contact_params=RigidContactsParams.build(**params))
+
+
+def _f32_representable(od):
+    """Round every leaf to float32 and recompute the caches in float64: the oracle then works
+    in float64 on exactly the numbers the float32 kernel receives."""
+    c = lambda a: np.asarray(a, dtype=np.float32).astype(np.float64)  # noqa: E731
+    return c
+
+
+def _inputs(om, B, seed, mode, dtype):
+    od = O.random_model_data(om, B, seed=seed, in_contact=mode)
+    if dtype == "float32":
+        c = lambda a: np.asarray(a, dtype=np.float32).astype(np.float64)  # noqa: E731
+        od = O.data_replace(om, c(od.joint_positions), c(od.joint_velocities), c(od.base_quaternion),
+                            c(od.base_linear_velocity), c(od.base_angular_velocity), c(od.base_position))
+    return od
+
+
+CASES = [("box", 16), ("sphere", 8), ("icub_like", 8), ("ergocub_like", 4)]
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("mode", [False, True, "flat"])
+@pytest.mark.parametrize("name,B", CASES)
+def test_rigid_step(name, B, mode, dtype, cuda_device):
+    import torch
+
+    model = _model(name, K=1e4, D=20.0)
+    om = H.oracle_model(model)
+    od = _inputs(om, B, 11, mode, dtype)
+    rng = np.random.default_rng(1)
+    tau = 10 * rng.uniform(size=(B, om.dofs())).astype(np.float32).astype(np.float64)
+    ref = R.step(om, od, joint_force_references=tau)
+    pd = H.to_product(model, od, _dtype(dtype), cuda_device)
+    out = js.model.step(model, pd, joint_force_references=torch.as_tensor(tau, dtype=_dtype(dtype), device=cuda_device))
+    assert not out.contact_state
+    H.compare_data(out, ref, H.RTOL[dtype], f"rigid step {name} {mode} {dtype}")
+
+
+@pytest.mark.parametrize("name,B", [("box", 8), ("icub_like", 4)])
+def test_rigid_step_f32_qp_in_f64(name, B, cuda_device):
+    """Option B200SIM_OPT_RIGID_QP_F64: same results within the fp32 tolerance."""
+    import torch
+
+    model = _model(name, K=1e4, D=20.0)
+    om = H.oracle_model(model)
+    od = _inputs(om, B, 5, "flat", "float32")
+    ref = R.step(om, od)
+    pd = H.to_product(model, od, torch.float32, cuda_device)
+    model.set_options(rigid_qp_f64=True)
+    out = js.model.step(model, pd)
+    H.compare_data(out, ref, H.RTOL["float32"], f"rigid step {name} qp64")
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_rigid_rollout_uses_stale_link_velocities(dtype, cuda_device):
+    """20 consecutive steps: the caches returned by step k (pre-impact link velocities,
+    rigid.py:429-434) feed step k+1 exactly like in the reference."""
+    name, B = "icub_like", 4
+    model = _model(name, K=1e4, D=20.0)
+    om = H.oracle_model(model)
+    od = _inputs(om, B, 3, "flat", dtype)
+    pd = H.to_product(model, od, _dtype(dtype), cuda_device)
+    for k in range(20):
+        od = R.step(om, od)
+        pd = js.model.step(model, pd)
+    tol = {"float64": 1e-5, "float32": 5e-3}[dtype]
+    H.compare_data(pd, od, tol, f"rigid rollout {dtype}")
+    # the quirk is observable: the cached link velocities differ from those of the state
+    fresh = O.data_replace(om, od.joint_positions, od.joint_velocities, od.base_quaternion, od.base_linear_velocity,
+                           od.base_angular_velocity, od.base_position)
+    assert np.abs(fresh.link_velocities - od.link_velocities).max() > 1e-6
+
+
+def test_rigid_box_comes_to_rest(cuda_device):
+    """The reference's known answer for this path (tests/test_simulations.py:245-292): a box
+    dropped from 2h with K=1e5 and its four bottom corners enabled rests at h/2 after 1 s."""
+    import torch
+
+    model = _model("box", K=1e5)
+    cp = model.kin_dyn_parameters.contact_parameters
+    model.kin_dyn_parameters.contact_parameters = dataclasses.replace(cp, enabled=tuple([True] * 4 + [False] * 4))
+    data = js.data.JaxSimModelData.build(model, base_position=torch.tensor([0.0, 0.0, 0.2], dtype=torch.float64),
+                                         velocity_representation=js.common.VelRepr.Inertial, batch_size=3,
+                                         dtype=torch.float64, device=cuda_device)
+    for _ in range(1000):
+        data = js.model.step(model, data)
+    p = data.base_position.cpu().numpy()
+    np.testing.assert_allclose(p[:, 0:2], 0.0, atol=1e-9)
+    np.testing.assert_allclose(p[:, 2], 0.05, rtol=1e-7)
+
+
+def test_rigid_unsupported_configurations(cuda_device):
+    import torch
+
+    model = _model("box")
+    cp = model.kin_dyn_parameters.contact_parameters
+    model.kin_dyn_parameters.contact_parameters = dataclasses.replace(cp, enabled=tuple([False, True] + [True] * 6))
+    with pytest.raises(Exception):  # enabled points must be a prefix (rigid.py:401-409 double indexing)
+        js.data.JaxSimModelData.build(model, batch_size=2, dtype=torch.float64, device=cuda_device)
+    model = _model("box")
+    data = js.data.JaxSimModelData.build(model, batch_size=2, dtype=torch.float64, device=cuda_device)
+    with pytest.raises(NotImplementedError):
+        js.model.step_n(model, data, 2)

@@ -86,10 +86,9 @@ def test_model_defaults():
     assert (m.contact_params.K, m.contact_params.D, m.contact_params.mu) == (1e6, 2000.0, 0.5)
     assert m.actuation_params.torque_max == 3000.0 and m.actuation_params.enable_friction
     assert m.dofs() == 23 and m.floating_base() and len(m.joint_names()) == 23
-    with pytest.raises(NotImplementedError):
-        js.model.JaxSimModel.build_from_model_description(
-            models.urdf("box"), contact_model=__import__("jaxsim_b200").rbda.contacts.RigidContacts.build()
-        )
+    rigid = __import__("jaxsim_b200").rbda.contacts.RigidContacts.build()
+    mr = js.model.JaxSimModel.build_from_model_description(models.urdf("box"), contact_model=rigid)
+    assert type(mr.contact_params).__name__ == "RigidContactsParams" and mr.contact_params.K == 0.0
 
 
 def test_library_exports_every_declared_symbol():
@@ -100,8 +99,8 @@ def test_library_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(lib, sym), sym
     assert b"sm_100a" in lib.b200sim_version()
-    # descriptor layout: ctypes mirror == C struct (8 int32 + 17 pointers + 11 doubles)
-    assert ctypes.sizeof(_lib.B200SimModelDesc) == 8 * 4 + 17 * 8 + 11 * 8
+    # descriptor layout: ctypes mirror == C struct (8 int32 + 17 pointers + 12 doubles)
+    assert ctypes.sizeof(_lib.B200SimModelDesc) == 8 * 4 + 17 * 8 + 12 * 8
 
 
 def test_invalid_arguments_are_rejected_without_a_gpu():
