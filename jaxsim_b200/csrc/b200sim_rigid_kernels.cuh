@@ -64,7 +64,7 @@ __host__ __device__ inline RigidLayout rigid_layout(int nL, int nc, int depth) {
   L.ucol = o;  o = rl_align(o + sizeof(T) * 32 * dd);
   L.Qp = o;    o = rl_align(o + sizeof(S) * NP);
   L.Hp = o;    o = rl_align(o + sizeof(S) * NP);
-  L.vecN = o;  o = rl_align(o + sizeof(S) * 6 * N);
+  L.vecN = o;  o = rl_align(o + sizeof(S) * 7 * N);
   L.vecM = o;  o = rl_align(o + sizeof(S) * 7 * M);
   L.ints = o;  o = rl_align(o + sizeof(int) * (2 * (size_t)nc + (size_t)nL + 4));
   L.total = o;
@@ -73,7 +73,7 @@ __host__ __device__ inline RigidLayout rigid_layout(int nL, int nc, int depth) {
 
 template <typename S> struct QpTol;
 template <> struct QpTol<float> {
-  static __device__ __forceinline__ float tol() { return 2e-6f; }
+  static __device__ __forceinline__ float tol() { return 1e-5f; }
   static __device__ __forceinline__ float pivot_floor() { return 1e-7f; }
   static __device__ __forceinline__ float rank_tol() { return 1e-4f; }
   static constexpr int max_iter = 40;
@@ -194,6 +194,7 @@ __device__ __noinline__ void qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int n
   S* dxa = vN + 3 * N;
   S* dx = vN + 4 * N;
   S* dg = vN + 5 * N;
+  S* xb = vN + 6 * N;  // best iterate so far (the answer if the iteration stalls at the resolution of S)
   S* s = vM;
   S* z = vM + M;
   S* rp = vM + 2 * M;
@@ -201,8 +202,9 @@ __device__ __noinline__ void qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int n
   S* dza = vM + 4 * M;
   S* ds = vM + 5 * M;
   S* dz = vM + 6 * M;
-  for (int i = lane; i < N; i += 32) x[i] = S(0);
+  for (int i = lane; i < N; i += 32) { x[i] = S(0); xb[i] = S(0); }
   for (int j = lane; j < M; j += 32) { s[j] = S(1); z[j] = S(1); }
+  S best = S(1e30);
   S qm = S(0);
   for (int i = lane; i < N; i += 32) qm = max_t(qm, abs_t(q[i]));
   qm = warp_max(qm);
@@ -240,7 +242,14 @@ __device__ __noinline__ void qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int n
     }
     rdn = warp_max(rdn); rpn = warp_max(rpn); sz = warp_sum(sz);
     const S mu = sz / S(M);
-    if (rdn <= tol * (S(1) + qm + Qxm) && rpn <= tol * (S(1) + xm) && mu <= tol * (S(1) + abs_t(S(0.5) * xQx + qx))) break;
+    const S m_d = rdn / (S(1) + qm + Qxm), m_p = rpn / (S(1) + xm), m_g = mu / (S(1) + abs_t(S(0.5) * xQx + qx));
+    const S merit = max_t(m_d, max_t(m_p, m_g));
+    if (merit < best) {  // false for NaN: a diverged iterate never replaces the best one
+      best = merit;
+      for (int i = lane; i < N; i += 32) xb[i] = x[i];
+    }
+    // converged, or the gap is far below the tolerance while a residual stalls at rounding level
+    if (!(merit > tol) || !(m_g > S(1e-3) * tol) || !(mu > S(0))) break;
     // H = Q + G' diag(z/s) G
     for (int e = lane; e < NP; e += 32) Hp[e] = Qp[e];
     __syncwarp();
@@ -325,6 +334,8 @@ __device__ __noinline__ void qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int n
     for (int j = lane; j < M; j += 32) { s[j] += al * ds[j]; z[j] += al * dz[j]; }
     __syncwarp();
   }
+  __syncwarp();
+  for (int i = lane; i < N; i += 32) x[i] = xb[i];
   __syncwarp();
 }
 
