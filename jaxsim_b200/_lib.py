@@ -62,7 +62,7 @@ class B200SimModelDesc(C.Structure):
 
 ABI_VERSION = 2
 OPT_TMA_STORE = 1
-OPT_RIGID_QP_F64 = 2
+OPT_RIGID_QP_F32 = 2
 EXPORTED_SYMBOLS = (
     "b200sim_version",
     "b200sim_model_create",

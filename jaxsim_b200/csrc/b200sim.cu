@@ -262,8 +262,8 @@ int launch_rigid(const B200SimModel* m, Params<T>& P, void* stream) {
   if (dev != m->device) CK(cudaSetDevice(m->device));
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
-  if (sizeof(T) == 4 && (m->opt_flags & B200SIM_OPT_RIGID_QP_F64)) rc = launch_rigid_s<T, double>(m, P, st);
-  else rc = launch_rigid_s<T, T>(m, P, st);
+  if (sizeof(T) == 4 && (m->opt_flags & B200SIM_OPT_RIGID_QP_F32)) rc = launch_rigid_s<T, T>(m, P, st);
+  else rc = launch_rigid_s<T, double>(m, P, st);
   if (dev != m->device) cudaSetDevice(dev);
   return rc;
 }
@@ -672,7 +672,7 @@ int b200sim_model_set_tuning(B200SimModel* m, int lanes_per_env, int envs_per_bl
 }
 
 int b200sim_model_set_options(B200SimModel* m, int32_t options) {
-  if (!m || (options & ~(B200SIM_OPT_TMA_STORE | B200SIM_OPT_RIGID_QP_F64))) return B200SIM_E_INVALID;
+  if (!m || (options & ~(B200SIM_OPT_TMA_STORE | B200SIM_OPT_RIGID_QP_F32))) return B200SIM_E_INVALID;
   m->opt_flags = options;
   return 0;
 }

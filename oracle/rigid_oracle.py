@@ -353,7 +353,9 @@ def solve_qp(Q, q, G, h, tol=1e-11, max_iter=200):
     """Primal-dual interior point (Mehrotra predictor-corrector) for an inequality-only,
     strictly convex QP.  Returns (x, s, z, converged, iters).  Rows of G that are identically
     zero with h == 0 (``rigid.py:478-489`` row 5 of active points) are dropped: they
-    constrain nothing."""
+    constrain nothing.  The best iterate (smallest scaled KKT residual) is returned; the
+    iteration stops when that residual is below ``tol`` or stalls at rounding level while the
+    duality gap is already far below ``tol`` (``converged`` then reports residual < 1e-8)."""
     Q = np.asarray(Q, dtype=np.float64)
     q = np.asarray(q, dtype=np.float64)
     G = np.asarray(G, dtype=np.float64)
@@ -367,20 +369,27 @@ def solve_qp(Q, q, G, h, tol=1e-11, max_iter=200):
         return x, np.zeros(G.shape[0]), np.zeros(G.shape[0]), True, 0
     s = np.ones(m)
     z = np.ones(m)
-    converged = False
+    best = (np.inf, x.copy(), s.copy(), z.copy())
     it = 0
     for it in range(1, max_iter + 1):
         Qx = Q @ x
         r_d = Qx + q + Gk.T @ z
         r_p = Gk @ x + s - hk
         mu = s @ z / m
-        scale_d = 1.0 + np.abs(q).max() + np.abs(Qx).max()
-        if max(np.abs(r_d).max() / scale_d, np.abs(r_p).max() / (1.0 + np.abs(x).max()), mu / (1.0 + abs(0.5 * x @ Q @ x + q @ x))) < tol:
-            converged = True
+        m_d = np.abs(r_d).max() / (1.0 + np.abs(q).max() + np.abs(Qx).max())
+        m_p = np.abs(r_p).max() / (1.0 + np.abs(x).max())
+        m_g = mu / (1.0 + abs(0.5 * x @ Qx + q @ x))
+        merit = max(m_d, m_p, m_g)
+        if merit < best[0]:
+            best = (merit, x.copy(), s.copy(), z.copy())
+        if not (merit > tol) or not (m_g > 1e-3 * tol) or not np.isfinite(merit):
             break
         W = z / s
         H = Q + Gk.T @ (W[:, None] * Gk)
-        L = np.linalg.cholesky(H)
+        try:
+            L = np.linalg.cholesky(H)
+        except np.linalg.LinAlgError:
+            break
 
         def newton(r_c):
             # r_c: target residual of s*z (to be driven to zero): s*dz + z*ds = -r_c
@@ -403,10 +412,11 @@ def solve_qp(Q, q, G, h, tol=1e-11, max_iter=200):
         x = x + a * dx
         s = s + a * ds
         z = z + a * dz
+    merit, x, s, z = best
     s_full = np.zeros(G.shape[0])
     z_full = np.zeros(G.shape[0])
     s_full[keep], z_full[keep] = s, z
-    return x, s_full, z_full, converged, it
+    return x, s_full, z_full, bool(merit < 1e-8), it
 
 
 # ---------------------------------------------------------------------------------------

@@ -75,14 +75,21 @@ def rel_err(x: np.ndarray, ref: np.ndarray) -> float:
     return float(np.max(np.abs(x.astype(np.float64) - ref.astype(np.float64)))) / scale
 
 
-def compare_data(pd, od: O.OracleData, rtol: float, what="") -> dict:
+def compare_data(pd, od: O.OracleData, rtol: float, what="", floors: dict | None = None) -> dict:
+    """``floors`` maps a leaf name to a minimal scale for its relative error (used where the
+    expected value is ~0, e.g. velocities after a perfectly inelastic impact: the error is then
+    measured against the scale of the same quantity before the step)."""
     errs = {}
     for oname, pname in LEAVES:
         ref = getattr(od, oname)
         got = getattr(pd, pname)
         if got is None:
             continue
-        errs[oname] = rel_err(got.detach().cpu().numpy(), ref)
+        e = rel_err(got.detach().cpu().numpy(), ref)
+        if floors and oname in floors and ref.size:
+            scale = max(float(np.max(np.abs(ref))), 1e-12)
+            e = e * scale / max(scale, float(floors[oname]))
+        errs[oname] = e
     if "tangential_deformation" in pd.contact_state and od.tangential_deformation is not None:
         ref = od.tangential_deformation
         got = pd.contact_state["tangential_deformation"].detach().cpu().numpy()

@@ -46,6 +46,13 @@ def _inputs(om, B, seed, mode, dtype):
     return od
 
 
+def _vel_floors(od):
+    """Scale of the velocities BEFORE the step: the impact can bring them to exactly zero."""
+    v = max(float(np.abs(od.base_linear_velocity).max()), float(np.abs(od.base_angular_velocity).max()),
+            float(np.abs(od.joint_velocities).max()) if od.joint_velocities.size else 0.0, 1e-3)
+    return {"base_linear_velocity": v, "base_angular_velocity": v, "joint_velocities": v, "link_velocities": v}
+
+
 CASES = [("box", 16), ("sphere", 8), ("icub_like", 8), ("ergocub_like", 4)]
 
 
@@ -64,12 +71,13 @@ def test_rigid_step(name, B, mode, dtype, cuda_device):
     pd = H.to_product(model, od, _dtype(dtype), cuda_device)
     out = js.model.step(model, pd, joint_force_references=torch.as_tensor(tau, dtype=_dtype(dtype), device=cuda_device))
     assert not out.contact_state
-    H.compare_data(out, ref, H.RTOL[dtype], f"rigid step {name} {mode} {dtype}")
+    H.compare_data(out, ref, H.RTOL[dtype], f"rigid step {name} {mode} {dtype}", floors=_vel_floors(od))
 
 
 @pytest.mark.parametrize("name,B", [("box", 8), ("icub_like", 4)])
-def test_rigid_step_f32_qp_in_f64(name, B, cuda_device):
-    """Option B200SIM_OPT_RIGID_QP_F64: same results within the fp32 tolerance."""
+def test_rigid_step_f32_qp_in_f32(name, B, cuda_device):
+    """Option B200SIM_OPT_RIGID_QP_F32 (all-float32 contact solve): forces good to ~1e-3 like
+    the reference's own solver tolerance, so the step is compared at 2e-2."""
     import torch
 
     model = _model(name, K=1e4, D=20.0)
@@ -77,9 +85,9 @@ def test_rigid_step_f32_qp_in_f64(name, B, cuda_device):
     od = _inputs(om, B, 5, "flat", "float32")
     ref = R.step(om, od)
     pd = H.to_product(model, od, torch.float32, cuda_device)
-    model.set_options(rigid_qp_f64=True)
+    model.set_options(rigid_qp_f32=True)
     out = js.model.step(model, pd)
-    H.compare_data(out, ref, H.RTOL["float32"], f"rigid step {name} qp64")
+    H.compare_data(out, ref, 2e-2, f"rigid step {name} qp32", floors=_vel_floors(od))
 
 
 @pytest.mark.parametrize("dtype", ["float64", "float32"])
@@ -90,12 +98,13 @@ def test_rigid_rollout_uses_stale_link_velocities(dtype, cuda_device):
     model = _model(name, K=1e4, D=20.0)
     om = H.oracle_model(model)
     od = _inputs(om, B, 3, "flat", dtype)
+    floors = _vel_floors(od)
     pd = H.to_product(model, od, _dtype(dtype), cuda_device)
     for k in range(20):
         od = R.step(om, od)
         pd = js.model.step(model, pd)
     tol = {"float64": 1e-5, "float32": 5e-3}[dtype]
-    H.compare_data(pd, od, tol, f"rigid rollout {dtype}")
+    H.compare_data(pd, od, tol, f"rigid rollout {dtype}", floors=floors)
     # the quirk is observable: the cached link velocities differ from those of the state
     fresh = O.data_replace(om, od.joint_positions, od.joint_velocities, od.base_quaternion, od.base_linear_velocity,
                            od.base_angular_velocity, od.base_position)
