@@ -66,7 +66,7 @@ __host__ __device__ inline RigidLayout rigid_layout(int nL, int nc, int depth) {
   L.Hp = o;    o = rl_align(o + sizeof(S) * NP);
   L.vecN = o;  o = rl_align(o + sizeof(S) * 7 * N);
   L.vecM = o;  o = rl_align(o + sizeof(S) * 7 * M);
-  L.ints = o;  o = rl_align(o + sizeof(int) * (2 * (size_t)nc + (size_t)nL + 4));
+  L.ints = o;  o = rl_align(o + sizeof(int) * (5 * (size_t)nc + (size_t)nL + 4));
   L.total = o;
   return L;
 }
@@ -75,15 +75,18 @@ template <typename S> struct QpTol;
 template <> struct QpTol<float> {
   static __device__ __forceinline__ float tol() { return 1e-5f; }
   static __device__ __forceinline__ float pivot_floor() { return 1e-7f; }
-  static __device__ __forceinline__ float rank_tol() { return 1e-4f; }
   static constexpr int max_iter = 40;
 };
 template <> struct QpTol<double> {
   static __device__ __forceinline__ double tol() { return 1e-11; }
   static __device__ __forceinline__ double pivot_floor() { return 1e-15; }
-  static __device__ __forceinline__ double rank_tol() { return 1e-9; }
   static constexpr int max_iter = 60;
 };
+
+// rank decisions of the impact solve depend on the precision the Delassus matrix was COMPUTED in
+template <typename T> struct RankTol;
+template <> struct RankTol<float> { static __device__ __forceinline__ double tol() { return 1e-4; } };
+template <> struct RankTol<double> { static __device__ __forceinline__ double tol() { return 1e-10; } };
 
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -121,38 +124,28 @@ __device__ __forceinline__ void sym_matvec(const S* Ap, const S* x, S* y, int N,
 }
 
 // In-place Cholesky of a packed lower-triangular matrix, warp-cooperative, right-looking.
-// `diag0` holds the diagonal before elimination.  semidef == false: pivots are floored at
-// pivot_floor * diag0 (the matrix is positive definite up to rounding).  semidef == true:
-// a pivot below rank_tol * diag0 marks a dependent row; it is skipped (L_kk = 0, column 0).
+// `diag0` holds the diagonal before elimination: pivots are floored at pivot_floor * diag0
+// (the interior-point Hessian is positive definite up to rounding).
 template <typename S>
-__device__ __forceinline__ void chol_packed(S* Hp, const S* diag0, int N, int lane, bool semidef) {
+__device__ __forceinline__ void chol_packed(S* Hp, const S* diag0, int N, int lane) {
   for (int k = 0; k < N; ++k) {
-    S d = Hp[pidx(k, k)];
-    const S d0 = diag0[k];
-    bool skip = false;
-    if (semidef) {
-      skip = !(d > QpTol<S>::rank_tol() * d0);
-    } else {
-      d = max_t(d, QpTol<S>::pivot_floor() * d0);
-      if (!(d > S(0))) d = S(1);
-    }
-    const S piv = skip ? S(0) : sqrt_t(d);
-    const S ipiv = skip ? S(0) : S(1) / piv;
+    S d = max_t(Hp[pidx(k, k)], QpTol<S>::pivot_floor() * diag0[k]);
+    if (!(d > S(0))) d = S(1);
+    const S piv = sqrt_t(d);
+    const S ipiv = S(1) / piv;
     for (int r = k + 1 + lane; r < N; r += 32) Hp[pidx(r, k)] *= ipiv;
     __syncwarp();
     if (lane == 0) Hp[pidx(k, k)] = piv;
-    if (!skip) {
-      for (int r = k + 1 + lane; r < N; r += 32) {
-        const S lrk = Hp[pidx(r, k)];
-        S* row = Hp + pidx(r, 0);
-        for (int c = k + 1; c <= r; ++c) row[c] -= lrk * Hp[pidx(c, k)];
-      }
+    for (int r = k + 1 + lane; r < N; r += 32) {
+      const S lrk = Hp[pidx(r, k)];
+      S* row = Hp + pidx(r, 0);
+      for (int c = k + 1; c <= r; ++c) row[c] -= lrk * Hp[pidx(c, k)];
     }
     __syncwarp();
   }
 }
 
-// solve L L^T x = y in place (skipped rows of a semidefinite factor give x = 0)
+// solve L L^T x = y in place
 template <typename S>
 __device__ __forceinline__ void chol_solve(const S* Lp, S* y, int N, int lane) {
   for (int k = 0; k < N; ++k) {
@@ -172,6 +165,79 @@ __device__ __forceinline__ void chol_solve(const S* Lp, S* y, int N, int lane) {
     if (lane == 0) y[k] = xk;
     __syncwarp();
   }
+}
+
+// Solve A x = y for a symmetric positive SEMI-definite, consistent system (packed lower A):
+// Cholesky with diagonal pivoting, stopped when the largest remaining diagonal falls below
+// rtol * (largest initial diagonal); the unknowns outside the selected independent set are zero.
+// L is built in permuted position space (packed), d = running diagonal, tmp = N scratch.
+template <typename S>
+__device__ __noinline__ void psd_solve_pivoted(const S* Ap, S* Lp, S* d, S* y, S* tmp, int* perm, int N, S rtol,
+                                               int lane) {
+  for (int i = lane; i < N; i += 32) { perm[i] = i; d[i] = Ap[pidx(i, i)]; }
+  __syncwarp();
+  int rank = 0;
+  S dref = S(0);
+  for (int k = 0; k < N; ++k) {
+    S best = S(-1);
+    int bp = k;
+    for (int pos = k + lane; pos < N; pos += 32) {
+      const S v = d[pos];
+      if (v > best) { best = v; bp = pos; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const S ob = __shfl_xor_sync(FULL, best, o);
+      const int op = __shfl_xor_sync(FULL, bp, o);
+      if (ob > best || (ob == best && op < bp)) { best = ob; bp = op; }
+    }
+    if (k == 0) dref = best;
+    if (!(best > rtol * dref)) break;
+    rank = k + 1;
+    if (bp != k) {
+      if (lane == 0) {
+        const int tp = perm[k]; perm[k] = perm[bp]; perm[bp] = tp;
+        const S td = d[k]; d[k] = d[bp]; d[bp] = td;
+      }
+      for (int c = lane; c < k; c += 32) {
+        const S a = Lp[pidx(k, c)];
+        Lp[pidx(k, c)] = Lp[pidx(bp, c)];
+        Lp[pidx(bp, c)] = a;
+      }
+    }
+    __syncwarp();
+    const S piv = sqrt_t(best);
+    const int pk = perm[k];
+    const S* rowk = Lp + pidx(k, 0);
+    for (int pos = k + 1 + lane; pos < N; pos += 32) {
+      const int pi = perm[pos];
+      S v = (pi >= pk) ? Ap[pidx(pi, pk)] : Ap[pidx(pk, pi)];
+      const S* row = Lp + pidx(pos, 0);
+      for (int c = 0; c < k; ++c) v -= row[c] * rowk[c];
+      v /= piv;
+      Lp[pidx(pos, k)] = v;
+      d[pos] -= v * v;
+    }
+    if (lane == 0) Lp[pidx(k, k)] = piv;
+    __syncwarp();
+  }
+  for (int i = lane; i < N; i += 32) tmp[i] = y[perm[i]];
+  __syncwarp();
+  for (int k = 0; k < rank; ++k) {
+    const S yk = __shfl_sync(FULL, (lane == 0) ? tmp[k] : S(0), 0) / Lp[pidx(k, k)];
+    for (int r = k + 1 + lane; r < rank; r += 32) tmp[r] -= Lp[pidx(r, k)] * yk;
+    if (lane == 0) tmp[k] = yk;
+    __syncwarp();
+  }
+  for (int k = rank - 1; k >= 0; --k) {
+    const S xk = __shfl_sync(FULL, (lane == 0) ? tmp[k] : S(0), 0) / Lp[pidx(k, k)];
+    const S* row = Lp + pidx(k, 0);
+    for (int r = lane; r < k; r += 32) tmp[r] -= row[r] * xk;
+    if (lane == 0) tmp[k] = xk;
+    __syncwarp();
+  }
+  for (int i = lane; i < N; i += 32) y[perm[i]] = (i < rank) ? tmp[i] : S(0);
+  __syncwarp();
 }
 
 // friction-pyramid rows of one point (rigid.py:478-489 rows 0-4): G v and G^T w
@@ -267,7 +333,7 @@ __device__ __noinline__ void qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int n
     __syncwarp();
     for (int i = lane; i < N; i += 32) dg[i] = Hp[pidx(i, i)];
     __syncwarp();
-    chol_packed(Hp, dg, N, lane, false);
+    chol_packed(Hp, dg, N, lane);
     // predictor: r_c = s z
     for (int a = lane; a < na; a += 32) {
       S t[5], g[3];
@@ -389,6 +455,7 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
   int* aidx = reinterpret_cast<int*>(wb + L.ints);  // [nc] compact index of an active point or -1
   int* alist = aidx + nc;                           // [nc] point index of compact index
   int* clist = alist + nc;                          // [nL] links that carry active points
+  int* perm = clist + nL;                           // [3 nc] pivot order of the impact solve
   const T dt = P.dt;
   const long long stride = (long long)gridDim.x * P.envs_per_block;
 
@@ -1136,10 +1203,8 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
         const T* pw = pts + (size_t)alist[a] * RPT;
         lam[3 * a] = -S(pw[RP_B]); lam[3 * a + 1] = -S(pw[RP_B + 1]); lam[3 * a + 2] = -S(pw[RP_B + 2]);
       }
-      for (int i = lane; i < N2; i += 32) dg[i] = Qp[pidx(i, i)];
       __syncwarp();
-      chol_packed(Qp, dg, N2, lane, true);
-      chol_solve(Qp, lam, N2, lane);
+      psd_solve_pivoted<S>(Qp, Hp, dg, lam, vN + N2, perm, N2, S(RankTol<T>::tol()), lane);
       for (int a = lane; a < na2; a += 32) {
         T* pw = pts + (size_t)alist[a] * RPT;
         pw[RP_F] = T(lam[3 * a]); pw[RP_F + 1] = T(lam[3 * a + 1]); pw[RP_F + 2] = T(lam[3 * a + 2]);
