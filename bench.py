@@ -63,6 +63,8 @@ def parse():
     ap.add_argument("--no-tma", action="store_true", help="128-bit stores instead of TMA bulk stores for the joint adjoints")
     ap.add_argument("--profile", action="store_true", help="cudaProfilerStart/Stop around the eager timed region (ncu --profile-from-start off)")
     ap.add_argument("--jvp", action="store_true", help="also time BASELINE config 5: forward-mode d(step)/d(joint q, link masses), fp64")
+    ap.add_argument("--config3", action="store_true", help="also time BASELINE config 3: ErgoCub-like ~50-DoF, RIGID contacts, batch 16384 fp32")
+    ap.add_argument("--c3-batch", type=int, default=16384)
     ap.add_argument("--rollout", type=int, default=0, help="also time step_n with this many fused steps per launch")
     ap.add_argument("--sweep", action="store_true", help="also time batch 16384 and 65536 on this GPU")
     return ap.parse_args()
@@ -429,6 +431,73 @@ def run_b200(args):
                    "ms_per_step": float(tr.item()) / (reps * Tn),
                    "note": "step_n: state kept on chip, per-step HBM traffic = joint force references only; no caches written"}
 
+    config3 = None
+    if args.config3:
+        from jaxsim_b200.rbda.contacts import RigidContacts, RigidContactsParams
+
+        m3 = js.model.JaxSimModel.build_from_model_description(
+            models.urdf("ergocub_like"), time_step=1e-3, contact_model=RigidContacts.build(),
+            contact_params=RigidContactsParams.build(K=1e4, D=20.0))
+        B3 = args.c3_batch
+        n3, nL3, nc3 = m3.dofs(), m3.number_of_links(), m3.number_of_collidable_points()
+
+        def standing(seed):
+            """level base, near-zero joints, soles 2-5 mm into the ground: several points active"""
+            gen = torch.Generator(device=dev).manual_seed(seed)
+            u = lambda *sh: 2 * torch.rand(*sh, dtype=dtype, device=dev, generator=gen) - 1  # noqa: E731
+            rpy = 1e-3 * u(B3, 3)
+            q = torch.cat([torch.ones(B3, 1, dtype=dtype, device=dev), 0.5 * rpy], dim=-1)
+            q = q / q.norm(dim=-1, keepdim=True)
+            p = torch.cat([u(B3, 2), torch.ones(B3, 1, dtype=dtype, device=dev)], dim=-1)
+            kw = dict(base_quaternion=q, joint_positions=1e-3 * u(B3, n3), joint_velocities=0.1 * u(B3, n3),
+                      base_linear_velocity=0.1 * u(B3, 3), base_angular_velocity=0.1 * u(B3, 3),
+                      velocity_representation=js.common.VelRepr.Inertial, batch_size=B3, dtype=dtype, device=dev)
+            d0 = js.data.JaxSimModelData.build(m3, base_position=p, **kw)
+            cp = m3.kin_dyn_parameters.contact_parameters
+            body = torch.as_tensor(np.array(cp.body), device=dev)
+            Lp = torch.as_tensor(np.asarray(cp.point), dtype=dtype, device=dev)
+            H = d0.link_transforms[:, body]
+            z = (H[..., 2, 0:3] * Lp).sum(-1) + H[..., 2, 3]
+            drop = z.min(dim=1).values + 0.002 + 0.003 * torch.rand(B3, dtype=dtype, device=dev, generator=gen)
+            p = p.clone()
+            p[:, 2] -= drop
+            d1 = js.data.JaxSimModelData.build(m3, base_position=p, **kw)
+            H = d1.link_transforms[:, body]
+            act = ((H[..., 2, 0:3] * Lp).sum(-1) + H[..., 2, 3] < 0).sum(dim=1).float().mean().item()
+            return d1, act
+
+        config3 = {"config": "BASELINE configs[2]: ergocub_like (%d DoF, %d links, %d collidable points), RigidContacts, batch %d %s"
+                             % (n3, nL3, nc3, B3, args.dtype), "unit": "env-steps/s"}
+        ring3 = 4
+        for label in ("random", "standing"):
+            if label == "random":
+                ds = [js.data.random_model_data(m3, batch_size=B3, seed=50 + r + 1000 * rank, dtype=dtype, device=dev,
+                                                velocity_representation=js.common.VelRepr.Inertial) for r in range(ring3)]
+                act = None
+            else:
+                pairs = [standing(70 + r + 1000 * rank) for r in range(ring3)]
+                ds, act = [p_[0] for p_ in pairs], float(np.mean([p_[1] for p_ in pairs]))
+            ts = [10 * torch.rand(B3, n3, dtype=dtype, device=dev) for _ in range(ring3)]
+            os_ = [js.model.step(m3, ds[r], joint_force_references=ts[r]) for r in range(ring3)]
+            K3 = max(4, min(args.steps, 20))
+            for i in range(3):
+                js.model.step(m3, ds[i % ring3], joint_force_references=ts[i % ring3], out=os_[i % ring3])
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(K3):
+                js.model.step(m3, ds[i % ring3], joint_force_references=ts[i % ring3], out=os_[i % ring3])
+            e1.record()
+            barrier()
+            t3 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+            ms3 = float(t3.item()) / K3
+            config3[label] = {"ms_per_step": ms3, "value": B3 * world / (ms3 * 1e-3), "steps": K3,
+                              "mean_active_points": act,
+                              "inputs": "random_model_data (base 0.5-1 m above ground: mostly no contact)" if label == "random"
+                              else "standing: level base, soles 2-5 mm into the ground"}
+
     jvp = None
     if args.jvp:
         d64 = js.data.random_model_data(model, batch_size=B, seed=77 + rank, dtype=torch.float64, device=dev,
@@ -504,6 +573,8 @@ def run_b200(args):
         line["rollout"] = rollout
     if jvp is not None:
         line["config5_jvp"] = jvp
+    if config3 is not None:
+        line["config3_rigid"] = config3
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
