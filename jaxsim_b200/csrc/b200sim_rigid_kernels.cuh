@@ -360,6 +360,7 @@ __device__ __noinline__ void qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int n
       }
     }
     amax = warp_min(amax);
+    __syncwarp();  // ds_a / dz_a were written point-wise, read element-wise below
     S mua = S(0);
     for (int j = lane; j < M; j += 32) mua += (s[j] + amax * dsa[j]) * (z[j] + amax * dza[j]);
     mua = warp_sum(mua) / S(M);
@@ -396,6 +397,7 @@ __device__ __noinline__ void qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int n
       }
     }
     al = min_t(S(1), S(0.99) * warp_min(al));
+    __syncwarp();
     for (int i = lane; i < N; i += 32) x[i] += al * dx[i];
     for (int j = lane; j < M; j += 32) { s[j] += al * ds[j]; z[j] += al * dz[j]; }
     __syncwarp();
