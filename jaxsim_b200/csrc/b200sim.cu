@@ -38,6 +38,8 @@ struct B200SimModel {
   int o_parent = 0, o_jtype = 0, o_lvl_start = 0, o_lvl_links = 0, o_child_start = 0, o_child_idx = 0,
       o_pt_start = 0, o_pt_idx = 0, o_pt_body = 0, o_pt_enabled = 0, o_anc = 0, o_ldepth = 0;
   double reg = 1e-6;
+  int* rigid_scratch = nullptr;      // work lists of the rigid-contact cascade
+  long long rigid_scratch_cap = 0;
   // device blobs
   float *cst_f = nullptr, *csuc_f = nullptr, *pt_f = nullptr;
   double *cst_d = nullptr, *csuc_d = nullptr, *pt_d = nullptr;
@@ -223,17 +225,23 @@ int launch(const B200SimModel* m, Params<T>& P, int dtype, void* stream) {
   return rc;
 }
 
-// ---- rigid contacts: one warp per environment, as many warps per block as shared memory allows
+// ---- rigid contacts: a cascade of three launches on the caller's stream
+//   level 0: the fused step kernel (G lanes per environment) finishes every environment whose
+//            collidable points stay above the ground; the others land on work list 1;
+//   level 1: the rigid kernel, one warp per listed environment, shared-memory workspace sized
+//            for RIGID_CAP1 simultaneously active points; environments with more -> list 2;
+//   level 2: the rigid kernel with a full-size workspace (only if nc > RIGID_CAP1).
+constexpr int RIGID_CAP1 = 16;
+
 template <typename T, typename S>
-int rigid_geometry(const B200SimModel* m, long long B, int* warps, int* grid, size_t* smem) {
+int rigid_geometry(const B200SimModel* m, long long B, int cap, int* warps, int* grid, size_t* smem) {
   const size_t st = static_smem_bytes(m, sizeof(T));
-  const RigidLayout L = rigid_layout<T, S>(m->nL, m->nc, m->depth);
+  const RigidLayout L = rigid_layout<T, S>(m->nL, m->nc, m->depth, cap);
   const size_t budget = (size_t)m->max_smem_optin - 1024;
   if (st + L.total > budget) return B200SIM_E_TOO_LARGE;
   long long w = std::min<long long>(RIGID_MAX_WARPS, (long long)((budget - st) / L.total));
-  if (m->tune_epb > 0) w = std::min<long long>(w, m->tune_epb);
   const long long per_sm = (B + m->num_sms - 1) / m->num_sms;
-  if (m->tune_epb == 0) w = std::min(w, std::max<long long>(per_sm, 1));
+  w = std::min(w, std::max<long long>(per_sm, 1));
   *warps = (int)w;
   *smem = st + (size_t)w * L.total;
   const long long blocks_per_sm = std::max<long long>(1, std::min<long long>(4, (long long)((size_t)228 * 1024 / (*smem + 1024))));
@@ -243,27 +251,62 @@ int rigid_geometry(const B200SimModel* m, long long B, int* warps, int* grid, si
 }
 
 template <typename T, typename S>
-int launch_rigid_s(const B200SimModel* m, Params<T>& P, cudaStream_t st) {
+int launch_rigid_level(const B200SimModel* m, Params<T>& P, int cap, cudaStream_t st) {
   int warps = 0, grid = 0;
   size_t smem = 0;
-  int rc = rigid_geometry<T, S>(m, P.B, &warps, &grid, &smem);
+  int rc = rigid_geometry<T, S>(m, P.B, cap, &warps, &grid, &smem);
   if (rc) return rc;
   P.envs_per_block = warps;
+  P.na_cap = cap;
   auto kern = rigid_step_kernel<T, S>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, warps * 32, smem, st>>>(P);
   return (int)cudaGetLastError();
 }
 
+// work lists: [0..3] counters, then two lists of `cap` ints.  Grown on demand (not during a
+// stream capture: run one eager step of the largest batch first).
+int ensure_rigid_scratch(B200SimModel* m, long long B) {
+  if (m->rigid_scratch && m->rigid_scratch_cap >= B) return 0;
+  if (m->rigid_scratch) CK(cudaFree(m->rigid_scratch));
+  m->rigid_scratch = nullptr;
+  CK(cudaMalloc((void**)&m->rigid_scratch, sizeof(int) * (4 + 2 * (size_t)B)));
+  m->rigid_scratch_cap = B;
+  return 0;
+}
+
 template <typename T>
-int launch_rigid(const B200SimModel* m, Params<T>& P, void* stream) {
+int launch_rigid(const B200SimModel* cm, Params<T>& P, int dtype, void* stream) {
+  B200SimModel* m = const_cast<B200SimModel*>(cm);
   int dev = 0;
   CK(cudaGetDevice(&dev));
   if (dev != m->device) CK(cudaSetDevice(m->device));
   cudaStream_t st = (cudaStream_t)stream;
-  int rc;
-  if (sizeof(T) == 4 && (m->opt_flags & B200SIM_OPT_RIGID_QP_F32)) rc = launch_rigid_s<T, T>(m, P, st);
-  else rc = launch_rigid_s<T, double>(m, P, st);
+  int rc = ensure_rigid_scratch(m, P.B);
+  int* cnt = m->rigid_scratch;
+  int* list1 = cnt ? cnt + 4 : nullptr;
+  int* list2 = cnt ? list1 + m->rigid_scratch_cap : nullptr;
+  if (!rc) rc = (int)cudaMemsetAsync(cnt, 0, 4 * sizeof(int), st);
+  if (!rc) {
+    // level 0: never reads the cached link velocities (they may be the pre-impact ones)
+    Params<T> P0 = P;
+    P0.Hin = nullptr; P0.Vin = nullptr;
+    P0.over_count = cnt; P0.over_list = list1;
+    rc = launch(m, P0, dtype, stream);
+  }
+  const bool qp32 = sizeof(T) == 4 && (m->opt_flags & B200SIM_OPT_RIGID_QP_F32);
+  const int cap1 = std::min(m->nc, RIGID_CAP1);
+  if (!rc) {
+    Params<T> P1 = P;
+    P1.work_count = cnt; P1.work_list = list1;
+    P1.over_count = cnt + 1; P1.over_list = list2;
+    rc = qp32 ? launch_rigid_level<T, T>(m, P1, cap1, st) : launch_rigid_level<T, double>(m, P1, cap1, st);
+  }
+  if (!rc && cap1 < m->nc) {
+    Params<T> P2 = P;
+    P2.work_count = cnt + 1; P2.work_list = list2;
+    rc = qp32 ? launch_rigid_level<T, T>(m, P2, m->nc, st) : launch_rigid_level<T, double>(m, P2, m->nc, st);
+  }
   if (dev != m->device) cudaSetDevice(dev);
   return rc;
 }
@@ -364,7 +407,7 @@ int step_t(const B200SimModel* m, int dtype, int64_t B, const void* s, const voi
   P.mode = MODE_STEP;
   if (m->contact_model == B200SIM_CONTACT_RIGID && m->nc > 0) {
     if (nsteps != 1) return B200SIM_E_UNSUPPORTED;
-    return launch_rigid(m, P, stream);
+    return launch_rigid(m, P, dtype, stream);
   }
   return launch(m, P, dtype, stream);
 }
@@ -642,7 +685,7 @@ void b200sim_model_destroy(B200SimModel* m) {
   cudaGetDevice(&prev);
   cudaSetDevice(m->device);
   cudaFree(m->cst_f); cudaFree(m->cst_d); cudaFree(m->csuc_f); cudaFree(m->csuc_d);
-  cudaFree(m->pt_f); cudaFree(m->pt_d); cudaFree(m->itab_d);
+  cudaFree(m->pt_f); cudaFree(m->pt_d); cudaFree(m->itab_d); cudaFree(m->rigid_scratch);
   cudaFree(m->cst_dd); cudaFree(m->csuc_dd); cudaFree(m->pt_dd);
   cudaSetDevice(prev);
   delete m;

@@ -124,6 +124,13 @@ struct Params {
   int nsteps;
   int mode;
   int envs_per_block;
+  // ---- rigid contacts: work lists of the cascade (b200sim_rigid_kernels.cuh).  An item is
+  // env | (impact_only << 31).  `work_*` is consumed, `over_*` is produced.
+  const int* work_count;
+  const int* work_list;
+  int* over_count;
+  int* over_list;
+  int na_cap;  // active points the consumer's shared-memory workspace is sized for
 };
 
 // ------------------------------------------------------------------------------------
@@ -494,6 +501,13 @@ struct LaunchBounds {
   static constexpr int kThreads = (G <= 8) ? 288 : 512;
 };
 
+// append an environment to the produced work list (rigid-contact cascade)
+template <typename T>
+__device__ __forceinline__ void over_push(const Params<T>& P, int env, int impact_only) {
+  const int slot = atomicAdd(P.over_count, 1);
+  P.over_list[slot] = env | (impact_only << 31);
+}
+
 // ------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------
@@ -537,13 +551,14 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
   const T dt = P.dt;
   const bool with_contacts = (P.mode == MODE_STEP) || (P.mode == MODE_DYN);
   const bool soft = with_contacts && (P.contact_model == 1) && nc > 0;
+  const bool rigid = (P.mode == MODE_STEP) && (P.contact_model == 2) && nc > 0;
   const bool tma = (P.flags & F_TMA_STORE) != 0;
 
   // the number of loop trips is uniform across the block so that __syncwarp() is safe
   const long long first = (long long)blockIdx.x * P.envs_per_block;
   for (long long env0 = first; env0 < P.B; env0 += stride) {
     long long env = env0 + grp;
-    const bool active = env < P.B;
+    bool active = env < P.B;
     if (!active) env = P.B - 1;  // idle groups shadow the last environment, stores masked
 
     // =========================================================== prefetch (one burst)
@@ -781,6 +796,25 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
       const T* fext_step = P.fext ? P.fext + (long long)step * P.fext_step_stride : nullptr;
 
       // ========================================================= contacts (point-parallel)
+      if (rigid) {
+        // RigidContacts, level 0 of the cascade: this kernel only finishes environments whose
+        // collidable points are all above the ground at t and at t+dt (then the contact forces
+        // and the impact are exactly zero, rbda/contacts/rigid.py:222-436).  The others go to
+        // the work list of the warp-per-environment rigid kernel; their stores are masked.
+        bool touch = false;
+        for (int k = lane; k < nc; k += G) {
+          const T* rb = ws + (size_t)pt_body[k] * REC;
+          const T* Lp = sm_pt + 3 * k;
+          const T z = rb[O_P + 2] + rb[O_R + 6] * Lp[0] + rb[O_R + 7] * Lp[1] + rb[O_R + 8] * Lp[2];
+          touch = touch || (pt_enabled[k] && (P.h_terrain - z > T(0)));
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, touch);
+        const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+        if (bal & gmask) {
+          if (active && lane == 0) over_push(P, (int)env, 0);
+          active = false;
+        }
+      }
       if (soft) {
         for (int k = lane; k < nc; k += G) {
           const int bi = pt_body[k];
@@ -1271,10 +1305,24 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
       }
       if (P.flags & F_GENERIC_FK) make_fk_map(sm_cst, b, fm);
       __syncwarp();  // every lane has read the base acceleration out of record 0
-      if (!last || want_caches) {
+      if (!last || want_caches || rigid) {
         write_base_record(b);
         fk_chain(!last);
-        if (last && active) write_fk_caches(b, fm);
+        if (last && active && want_caches) write_fk_caches(b, fm);
+      }
+      if (rigid) {
+        // a point below the ground at t+dt: the impact (rigid.py:385-436) is left to the rigid
+        // kernel, which starts from the pre-impact result this kernel has just stored
+        bool touch = false;
+        for (int k = lane; k < nc; k += G) {
+          const T* rb = ws + (size_t)pt_body[k] * REC;
+          const T* Lp = sm_pt + 3 * k;
+          const T z = rb[O_P + 2] + rb[O_R + 6] * Lp[0] + rb[O_R + 7] * Lp[1] + rb[O_R + 8] * Lp[2];
+          touch = touch || (pt_enabled[k] && (P.h_terrain - z > T(0)));
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, touch);
+        const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+        if ((bal & gmask) && active && lane == 0) over_push(P, (int)env, 1);
       }
       __syncwarp();
     }  // steps

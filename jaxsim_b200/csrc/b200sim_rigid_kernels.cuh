@@ -52,11 +52,12 @@ struct RigidLayout {  // byte offsets inside one environment's (= one warp's) wo
 
 __host__ __device__ inline size_t rl_align(size_t x) { return (x + 15) & ~size_t(15); }
 
+// `cap` = number of simultaneously active points the solver arrays are sized for (<= nc)
 template <typename T, typename S>
-__host__ __device__ inline RigidLayout rigid_layout(int nL, int nc, int depth) {
+__host__ __device__ inline RigidLayout rigid_layout(int nL, int nc, int depth, int cap) {
   RigidLayout L;
   size_t o = 0;
-  const size_t N = 3 * (size_t)nc, M = 5 * (size_t)nc, NP = N * (N + 1) / 2;
+  const size_t N = 3 * (size_t)cap, M = 5 * (size_t)cap, NP = N * (N + 1) / 2;
   const size_t dd = depth > 0 ? depth : 1;
   L.links = o; o = rl_align(o + sizeof(T) * (size_t)nL * REC);
   L.pts = o;   o = rl_align(o + sizeof(T) * (size_t)nc * RPT);
@@ -444,7 +445,8 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
 
   const int lane = threadIdx.x & 31;
   const int wrp = threadIdx.x >> 5;
-  const RigidLayout L = rigid_layout<T, S>(nL, nc, depth);
+  const int cap = P.na_cap;
+  const RigidLayout L = rigid_layout<T, S>(nL, nc, depth, cap);
   unsigned char* wb = ws_base + (size_t)wrp * L.total;
   T* ws = reinterpret_cast<T*>(wb + L.links);
   T* pts = reinterpret_cast<T*>(wb + L.pts);
@@ -461,19 +463,30 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
   const T dt = P.dt;
   const long long stride = (long long)gridDim.x * P.envs_per_block;
 
-  for (long long env0 = (long long)blockIdx.x * P.envs_per_block; env0 < P.B; env0 += stride) {
-    const long long env = env0 + wrp;
-    if (env >= P.B) continue;  // whole warp: no block-level barrier inside the loop
+  // work items: every environment of the batch, or the list produced by the previous level of
+  // the cascade (env | impact_only << 31)
+  const long long total = P.work_list ? (long long)(*P.work_count) : P.B;
+  for (long long it0 = (long long)blockIdx.x * P.envs_per_block; it0 < total; it0 += stride) {
+    const long long item_idx = it0 + wrp;
+    if (item_idx >= total) continue;  // whole warp: no block-level barrier inside the loop
+    long long env = item_idx;
+    bool impact_only = false;
+    if (P.work_list) {
+      const int item = P.work_list[item_idx];
+      env = item & 0x7fffffff;
+      impact_only = item < 0;
+    }
 
     // ============================================================== input state
-    for (int i = 1 + lane; i < nL; i += 32) {
-      T* ri = ws + (size_t)i * REC;
-      ri[O_S] = P.s[env * n + (i - 1)];
-      ri[O_SD] = P.sd[env * n + (i - 1)];
-      ri[O_TREF] = P.tau ? P.tau[env * n + (i - 1)] : T(0);
-    }
+    // (impact_only: the pre-impact result of this step, stored by the previous level)
     BaseState<T> b;
-    {
+    if (!impact_only) {
+      for (int i = 1 + lane; i < nL; i += 32) {
+        T* ri = ws + (size_t)i * REC;
+        ri[O_S] = P.s[env * n + (i - 1)];
+        ri[O_SD] = P.sd[env * n + (i - 1)];
+        ri[O_TREF] = P.tau ? P.tau[env * n + (i - 1)] : T(0);
+      }
       const T* q = P.q + env * 4;
       const T qr[4] = {q[0], q[1], q[2], q[3]};
       ldn<3>(P.p + env * 3, b.p);
@@ -483,6 +496,17 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
       const T inv = T(1) / (nrm + Lim<T>::eps() * (nrm == T(0) ? T(1) : T(0)));  // api/data.py:283-285
 #pragma unroll
       for (int k = 0; k < 4; ++k) b.qn[k] = qr[k] * inv;
+      quat_to_dcm(b.qn, b.R);
+    } else {
+      for (int i = 1 + lane; i < nL; i += 32) {
+        T* ri = ws + (size_t)i * REC;
+        ri[O_S] = P.s_o[env * n + (i - 1)];
+        ri[O_SD] = P.sd_o[env * n + (i - 1)];
+      }
+      ldn<4>(P.q_o + env * 4, b.qn);
+      ldn<3>(P.p_o + env * 3, b.p);
+      ldn<3>(P.vlin_o + env * 3, b.vlin);
+      ldn<3>(P.omega_o + env * 3, b.w);
       quat_to_dcm(b.qn, b.R);
     }
 
@@ -1038,9 +1062,14 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
       __syncwarp();
     };
 
+    if (!impact_only) {
     // ============================================================== phase A: state at t
     kinematics(b, false);
     const int na = contact_points(false);
+    if (na > cap) {  // more active points than this level's workspace holds: next level, untouched
+      if (lane == 0) over_push(P, (int)env, 0);
+      continue;
+    }
     link_init(true);
     pass2();
     // free acceleration (ABA pass 3, rbda/aba.py:233-288)
@@ -1190,9 +1219,25 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
       }
     }
     for (int i = 1 + lane; i < nL; i += 32) P.s_o[env * n + (i - 1)] = ws[(size_t)i * REC + O_S];
+    } else {
+      kinematics(b, false);
+    }
 
     // impact (rigid.py:385-436): project nu onto {velocity of the active points = 0}
     const int na2 = contact_points(true);
+    if (na2 > cap) {
+      // next level applies the impact to the pre-impact result, which must then be complete
+      if (!impact_only) {
+        for (int i = 1 + lane; i < nL; i += 32) P.sd_o[env * n + (i - 1)] = ws[(size_t)i * REC + O_SD];
+        if (lane == 0) {
+          stn<3>(P.vlin_o + env * 3, b.vlin);
+          stn<3>(P.omega_o + env * 3, b.w);
+        }
+        __threadfence();
+      }
+      if (lane == 0) over_push(P, (int)env, 1);
+      continue;
+    }
     T dv0[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
     if (na2 > 0) {
       link_init(false);
@@ -1221,7 +1266,10 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
     }
     __syncwarp();
     for (int i = 1 + lane; i < nL; i += 32) P.sd_o[env * n + (i - 1)] = ws[(size_t)i * REC + O_SD];
-    if (lane == 0) {
+    if (lane == 0 && na2 == 0) {
+      stn<3>(P.vlin_o + env * 3, b.vlin);
+      stn<3>(P.omega_o + env * 3, b.w);
+    } else if (lane == 0) {
       // base: F_0 coordinates [pdot_B; omega] -> inertial-fixed linear part
       T t[3], w2[3], pdB[3];
       cross3(b.w, b.p, t);

@@ -141,3 +141,63 @@ def test_rigid_unsupported_configurations(cuda_device):
     data = js.data.JaxSimModelData.build(model, batch_size=2, dtype=torch.float64, device=cuda_device)
     with pytest.raises(NotImplementedError):
         js.model.step_n(model, data, 2)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_rigid_cascade_mixed_batch(dtype, cuda_device):
+    """Airborne and in-contact environments in one batch: the airborne ones are finished by the
+    fused step kernel (level 0 of the cascade), the others by the rigid kernel; an airborne
+    environment that lands during the step takes the impact-only route."""
+    import torch
+
+    name, B = "icub_like", 24
+    model = _model(name, K=1e4, D=20.0)
+    om = H.oracle_model(model)
+    a = _inputs(om, B // 3, 21, False, dtype)
+    b = _inputs(om, B // 3, 22, "flat", dtype)
+    c = _inputs(om, B // 3, 23, "flat", dtype)
+    # c: just above the ground and falling -> in the air at t, in contact at t+dt
+    pc = c.base_position.copy()
+    pc[:, 2] += 0.0051
+    vc = c.base_linear_velocity.copy()
+    vc[:, 2] = -1.0 - np.cross(c.base_angular_velocity, pc)[:, 2]
+    cat = lambda f: np.concatenate([getattr(a, f), getattr(b, f), getattr(c, f)], axis=0)  # noqa: E731
+    p = np.concatenate([a.base_position, b.base_position, pc], axis=0)
+    v = np.concatenate([a.base_linear_velocity, b.base_linear_velocity, vc], axis=0)
+    if dtype == "float32":
+        p, v = p.astype(np.float32).astype(np.float64), v.astype(np.float32).astype(np.float64)
+    od = O.data_replace(om, cat("joint_positions"), cat("joint_velocities"), cat("base_quaternion"), v,
+                        cat("base_angular_velocity"), p)
+    W_p_C, _ = O.collidable_points_pos_vel(om, od.link_transforms, od.link_velocities)
+    touching = (W_p_C[..., 2] < 0).any(axis=1)
+    assert touching[B // 3:2 * B // 3].all() and not touching[2 * B // 3:].any()
+    ref = R.step(om, od)
+    W_p_C2, _ = O.collidable_points_pos_vel(om, ref.link_transforms, ref.link_velocities)
+    assert (W_p_C2[2 * B // 3:, :, 2] < 0).any(axis=1).all()  # group c has landed
+    pd = H.to_product(model, od, _dtype(dtype), cuda_device)
+    out = js.model.step(model, pd)
+    H.compare_data(out, ref, H.RTOL[dtype], f"rigid cascade {dtype}", floors=_vel_floors(od))
+    # in place: the result overwrites the input buffers
+    pd2 = H.to_product(model, od, _dtype(dtype), cuda_device)
+    pd2 = js.model.step(model, pd2, out=pd2)
+    for leaf in ("_joint_positions", "_joint_velocities", "_base_linear_velocity", "_link_velocities"):
+        assert torch.equal(getattr(pd2, leaf), getattr(out, leaf)), leaf
+
+
+def test_rigid_more_active_points_than_the_fast_workspace(cuda_device):
+    """ErgoCub-like with the terrain above the robot: all 32 collidable points are active,
+    which exceeds the 16-point workspace of cascade level 1 -> level 2 (full-size)."""
+    import torch
+
+    from jaxsim_b200.terrain import FlatTerrain
+
+    model = H.build_model("ergocub_like", contact_model=RigidContacts.build(), contact_params=RigidContactsParams.build(),
+                          terrain=FlatTerrain.build(height=3.0))
+    om = H.oracle_model(model)
+    od = _inputs(om, 2, 31, "flat", "float64")
+    W_p_C, _ = O.collidable_points_pos_vel(om, od.link_transforms, od.link_velocities)
+    assert (W_p_C[..., 2] < 3.0).all()
+    ref = R.step(om, od)
+    pd = H.to_product(model, od, torch.float64, cuda_device)
+    out = js.model.step(model, pd)
+    H.compare_data(out, ref, 1e-5, "rigid 32 active points", floors=_vel_floors(od))
