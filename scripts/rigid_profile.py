@@ -1,0 +1,65 @@
+"""Drive the rigid-contact step for profiling: ErgoCub-like model, 'standing' inputs (level
+base, soles 2-5 mm into the ground), a few eager steps bracketed by cudaProfilerStart/Stop.
+
+    ncu --profile-from-start off --set full --import-source on -k regex:rigid_step_kernel \
+        -o gpurun_out/rigid python scripts/rigid_profile.py --batch 4096
+"""
+import argparse
+import pathlib
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, str(pathlib.Path(__file__).resolve().parent.parent))
+import jaxsim_b200.api as js  # noqa: E402
+from jaxsim_b200 import models  # noqa: E402
+from jaxsim_b200.rbda.contacts import RigidContacts, RigidContactsParams  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=4096)
+ap.add_argument("--model", default="ergocub_like")
+ap.add_argument("--dtype", default="f32")
+ap.add_argument("--steps", type=int, default=2)
+ap.add_argument("--qp32", action="store_true")
+args = ap.parse_args()
+dev = torch.device("cuda:0")
+dtype = torch.float32 if args.dtype == "f32" else torch.float64
+m = js.model.JaxSimModel.build_from_model_description(
+    models.urdf(args.model), time_step=1e-3, contact_model=RigidContacts.build(),
+    contact_params=RigidContactsParams.build(K=1e4, D=20.0))
+if args.qp32:
+    m.set_options(rigid_qp_f32=True)
+B, n = args.batch, m.dofs()
+gen = torch.Generator(device=dev).manual_seed(0)
+u = lambda *sh: 2 * torch.rand(*sh, dtype=dtype, device=dev, generator=gen) - 1  # noqa: E731
+rpy = 1e-3 * u(B, 3)
+q = torch.cat([torch.ones(B, 1, dtype=dtype, device=dev), 0.5 * rpy], dim=-1)
+q = q / q.norm(dim=-1, keepdim=True)
+p = torch.cat([u(B, 2), torch.ones(B, 1, dtype=dtype, device=dev)], dim=-1)
+kw = dict(base_quaternion=q, joint_positions=1e-3 * u(B, n), joint_velocities=0.1 * u(B, n),
+          base_linear_velocity=0.1 * u(B, 3), base_angular_velocity=0.1 * u(B, 3),
+          velocity_representation=js.common.VelRepr.Inertial, batch_size=B, dtype=dtype, device=dev)
+d0 = js.data.JaxSimModelData.build(m, base_position=p, **kw)
+cp = m.kin_dyn_parameters.contact_parameters
+body = torch.as_tensor(np.array(cp.body), device=dev)
+Lp = torch.as_tensor(np.asarray(cp.point), dtype=dtype, device=dev)
+H = d0.link_transforms[:, body]
+z = (H[..., 2, 0:3] * Lp).sum(-1) + H[..., 2, 3]
+p[:, 2] -= z.min(dim=1).values + 0.002 + 0.003 * torch.rand(B, dtype=dtype, device=dev, generator=gen)
+data = js.data.JaxSimModelData.build(m, base_position=p, **kw)
+tau = 10 * torch.rand(B, n, dtype=dtype, device=dev)
+out = js.model.step(m, data, joint_force_references=tau)
+for _ in range(3):
+    js.model.step(m, data, joint_force_references=tau, out=out)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+torch.cuda.profiler.start()
+e0.record()
+for _ in range(args.steps):
+    js.model.step(m, data, joint_force_references=tau, out=out)
+e1.record()
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
+ms = e0.elapsed_time(e1) / args.steps
+print("rigid step: %.3f ms/step, %.0f env-steps/s (B=%d, %s, qp32=%s)" % (ms, B / ms * 1e3, B, args.dtype, args.qp32))

@@ -157,8 +157,9 @@ def test_rigid_cascade_mixed_batch(dtype, cuda_device):
     b = _inputs(om, B // 3, 22, "flat", dtype)
     c = _inputs(om, B // 3, 23, "flat", dtype)
     # c: just above the ground and falling -> in the air at t, in contact at t+dt
+    W_p_Cc, _ = O.collidable_points_pos_vel(om, c.link_transforms, c.link_velocities)
     pc = c.base_position.copy()
-    pc[:, 2] += 0.0051
+    pc[:, 2] += 0.0005 - W_p_Cc[..., 2].min(axis=1)  # lowest point 0.5 mm above the ground, falling at 1 m/s
     vc = c.base_linear_velocity.copy()
     vc[:, 2] = -1.0 - np.cross(c.base_angular_velocity, pc)[:, 2]
     cat = lambda f: np.concatenate([getattr(a, f), getattr(b, f), getattr(c, f)], axis=0)  # noqa: E731
@@ -195,6 +196,10 @@ def test_rigid_more_active_points_than_the_fast_workspace(cuda_device):
                           terrain=FlatTerrain.build(height=3.0))
     om = H.oracle_model(model)
     od = _inputs(om, 2, 31, "flat", "float64")
+    p = od.base_position.copy()
+    p[:, 2] -= 2.0
+    od = O.data_replace(om, od.joint_positions, od.joint_velocities, od.base_quaternion, od.base_linear_velocity,
+                        od.base_angular_velocity, p)
     W_p_C, _ = O.collidable_points_pos_vel(om, od.link_transforms, od.link_velocities)
     assert (W_p_C[..., 2] < 3.0).all()
     ref = R.step(om, od)
