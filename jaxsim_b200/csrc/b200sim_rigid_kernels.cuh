@@ -66,7 +66,7 @@ __host__ __device__ inline RigidLayout rigid_layout(int nL, int nc, int depth, i
   L.Qp = o;    o = rl_align(o + sizeof(S) * NP);
   L.Hp = o;    o = rl_align(o + sizeof(S) * NP);
   L.vecN = o;  o = rl_align(o + sizeof(S) * 7 * N);
-  L.vecM = o;  o = rl_align(o + sizeof(S) * 7 * M);
+  L.vecM = o;  o = rl_align(o + sizeof(S) * 9 * M);
   L.ints = o;  o = rl_align(o + sizeof(int) * (5 * (size_t)nc + (size_t)nL + 4));
   L.total = o;
   return L;
@@ -125,18 +125,18 @@ __device__ __forceinline__ void sym_matvec(const S* Ap, const S* x, S* y, int N,
 }
 
 // In-place Cholesky of a packed lower-triangular matrix, warp-cooperative, right-looking.
-// `diag0` holds the diagonal before elimination: pivots are floored at pivot_floor * diag0
-// (the interior-point Hessian is positive definite up to rounding).
+// `dg` holds the diagonal before elimination on entry (pivots are floored at pivot_floor * dg:
+// the interior-point Hessian is positive definite up to rounding) and 1 / L_kk on exit, so
+// that the triangular solves multiply instead of divide.
 template <typename S>
-__device__ __forceinline__ void chol_packed(S* Hp, const S* diag0, int N, int lane) {
+__device__ __forceinline__ void chol_packed(S* Hp, S* dg, int N, int lane) {
   for (int k = 0; k < N; ++k) {
-    S d = max_t(Hp[pidx(k, k)], QpTol<S>::pivot_floor() * diag0[k]);
+    S d = max_t(Hp[pidx(k, k)], QpTol<S>::pivot_floor() * dg[k]);
     if (!(d > S(0))) d = S(1);
-    const S piv = sqrt_t(d);
-    const S ipiv = S(1) / piv;
+    const S ipiv = S(1) / sqrt_t(d);
     for (int r = k + 1 + lane; r < N; r += 32) Hp[pidx(r, k)] *= ipiv;
     __syncwarp();
-    if (lane == 0) Hp[pidx(k, k)] = piv;
+    if (lane == 0) dg[k] = ipiv;
     for (int r = k + 1 + lane; r < N; r += 32) {
       const S lrk = Hp[pidx(r, k)];
       S* row = Hp + pidx(r, 0);
@@ -146,21 +146,17 @@ __device__ __forceinline__ void chol_packed(S* Hp, const S* diag0, int N, int la
   }
 }
 
-// solve L L^T x = y in place
+// solve L L^T x = y in place; invd = 1 / diag(L)
 template <typename S>
-__device__ __forceinline__ void chol_solve(const S* Lp, S* y, int N, int lane) {
+__device__ __forceinline__ void chol_solve(const S* Lp, const S* invd, S* y, int N, int lane) {
   for (int k = 0; k < N; ++k) {
-    S yk = __shfl_sync(FULL, (lane == 0) ? y[k] : S(0), 0);
-    const S lkk = Lp[pidx(k, k)];
-    yk = (lkk > S(0)) ? yk / lkk : S(0);
+    const S yk = __shfl_sync(FULL, (lane == 0) ? y[k] : S(0), 0) * invd[k];
     for (int r = k + 1 + lane; r < N; r += 32) y[r] -= Lp[pidx(r, k)] * yk;
     if (lane == 0) y[k] = yk;
     __syncwarp();
   }
   for (int k = N - 1; k >= 0; --k) {
-    S xk = __shfl_sync(FULL, (lane == 0) ? y[k] : S(0), 0);
-    const S lkk = Lp[pidx(k, k)];
-    xk = (lkk > S(0)) ? xk / lkk : S(0);
+    const S xk = __shfl_sync(FULL, (lane == 0) ? y[k] : S(0), 0) * invd[k];
     const S* row = Lp + pidx(k, 0);
     for (int r = lane; r < k; r += 32) y[r] -= row[r] * xk;
     if (lane == 0) y[k] = xk;
@@ -207,7 +203,7 @@ __device__ __noinline__ void psd_solve_pivoted(const S* Ap, S* Lp, S* d, S* y, S
       }
     }
     __syncwarp();
-    const S piv = sqrt_t(best);
+    const S ipiv = S(1) / sqrt_t(best);
     const int pk = perm[k];
     const S* rowk = Lp + pidx(k, 0);
     for (int pos = k + 1 + lane; pos < N; pos += 32) {
@@ -215,23 +211,23 @@ __device__ __noinline__ void psd_solve_pivoted(const S* Ap, S* Lp, S* d, S* y, S
       S v = (pi >= pk) ? Ap[pidx(pi, pk)] : Ap[pidx(pk, pi)];
       const S* row = Lp + pidx(pos, 0);
       for (int c = 0; c < k; ++c) v -= row[c] * rowk[c];
-      v /= piv;
+      v *= ipiv;
       Lp[pidx(pos, k)] = v;
       d[pos] -= v * v;
     }
-    if (lane == 0) Lp[pidx(k, k)] = piv;
+    if (lane == 0) d[k] = ipiv;  // position k is settled: its slot now holds 1 / L_kk
     __syncwarp();
   }
   for (int i = lane; i < N; i += 32) tmp[i] = y[perm[i]];
   __syncwarp();
   for (int k = 0; k < rank; ++k) {
-    const S yk = __shfl_sync(FULL, (lane == 0) ? tmp[k] : S(0), 0) / Lp[pidx(k, k)];
+    const S yk = __shfl_sync(FULL, (lane == 0) ? tmp[k] : S(0), 0) * d[k];
     for (int r = k + 1 + lane; r < rank; r += 32) tmp[r] -= Lp[pidx(r, k)] * yk;
     if (lane == 0) tmp[k] = yk;
     __syncwarp();
   }
   for (int k = rank - 1; k >= 0; --k) {
-    const S xk = __shfl_sync(FULL, (lane == 0) ? tmp[k] : S(0), 0) / Lp[pidx(k, k)];
+    const S xk = __shfl_sync(FULL, (lane == 0) ? tmp[k] : S(0), 0) * d[k];
     const S* row = Lp + pidx(k, 0);
     for (int r = lane; r < k; r += 32) tmp[r] -= row[r] * xk;
     if (lane == 0) tmp[k] = xk;
@@ -252,6 +248,9 @@ __device__ __forceinline__ void pyr_GT(S mu, const S* w, S* o) {
 }
 
 // min 1/2 x'Qx + q'x  s.t. pyramid constraints per point; N = 3 na.  Result in x.
+// Primal-dual interior point, Mehrotra predictor-corrector.  Divisions are the expensive
+// operation (float64 especially): 1/s and 1/z are formed once per iteration and every
+// ratio below multiplies by them; the Cholesky factor carries 1/L_kk.
 template <typename S>
 __device__ __noinline__ void qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int na, S mu_f, int lane) {
   const int N = 3 * na, M = 5 * na;
@@ -269,6 +268,8 @@ __device__ __noinline__ void qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int n
   S* dza = vM + 4 * M;
   S* ds = vM + 5 * M;
   S* dz = vM + 6 * M;
+  S* is = vM + 7 * M;  // 1 / s
+  S* iz = vM + 8 * M;  // 1 / z
   for (int i = lane; i < N; i += 32) { x[i] = S(0); xb[i] = S(0); }
   for (int j = lane; j < M; j += 32) { s[j] = S(1); z[j] = S(1); }
   S best = S(1e30);
@@ -278,6 +279,7 @@ __device__ __noinline__ void qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int n
   __syncwarp();
   const S tol = QpTol<S>::tol();
   const int NP = N * (N + 1) / 2;
+  const S inv_M = S(1) / S(M);
   for (int it = 0; it < QpTol<S>::max_iter; ++it) {
     // residuals
     sym_matvec(Qp, x, rd, N, lane);
@@ -301,14 +303,17 @@ __device__ __noinline__ void qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int n
       }
 #pragma unroll
       for (int j = 0; j < 5; ++j) {
-        const S v = gx[j] + s[5 * a + j];
+        const S sj = s[5 * a + j], zj = z[5 * a + j];
+        const S v = gx[j] + sj;
         rp[5 * a + j] = v;
         rpn = max_t(rpn, abs_t(v));
-        sz += s[5 * a + j] * z[5 * a + j];
+        sz += sj * zj;
+        is[5 * a + j] = S(1) / sj;
+        iz[5 * a + j] = S(1) / zj;
       }
     }
     rdn = warp_max(rdn); rpn = warp_max(rpn); sz = warp_sum(sz);
-    const S mu = sz / S(M);
+    const S mu = sz * inv_M;
     const S m_d = rdn / (S(1) + qm + Qxm), m_p = rpn / (S(1) + xm), m_g = mu / (S(1) + abs_t(S(0.5) * xQx + qx));
     const S merit = max_t(m_d, max_t(m_p, m_g));
     if (merit < best) {  // false for NaN: a diverged iterate never replaces the best one
@@ -323,7 +328,7 @@ __device__ __noinline__ void qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int n
     for (int a = lane; a < na; a += 32) {
       S w[5];
 #pragma unroll
-      for (int j = 0; j < 5; ++j) w[j] = z[5 * a + j] / s[5 * a + j];
+      for (int j = 0; j < 5; ++j) w[j] = z[5 * a + j] * is[5 * a + j];
       const int r0 = 3 * a;
       Hp[pidx(r0, r0)] += w[0] + w[2];
       Hp[pidx(r0 + 1, r0 + 1)] += w[1] + w[3];
@@ -339,14 +344,15 @@ __device__ __noinline__ void qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int n
     for (int a = lane; a < na; a += 32) {
       S t[5], g[3];
 #pragma unroll
-      for (int j = 0; j < 5; ++j) t[j] = z[5 * a + j] * (rp[5 * a + j] - s[5 * a + j]) / s[5 * a + j];
+      for (int j = 0; j < 5; ++j) t[j] = z[5 * a + j] * (rp[5 * a + j] - s[5 * a + j]) * is[5 * a + j];
       pyr_GT(mu_f, t, g);
 #pragma unroll
       for (int d = 0; d < 3; ++d) dxa[3 * a + d] = -(rd[3 * a + d] + g[d]);
     }
     __syncwarp();
-    chol_solve(Hp, dxa, N, lane);
-    S amax = S(1);
+    chol_solve(Hp, dg, dxa, N, lane);
+    // largest step keeping s, z positive: alpha = 1 / max_j(-ds_j / s_j, -dz_j / z_j)
+    S rmax = S(1);
     for (int a = lane; a < na; a += 32) {
       S g[5];
       pyr_G(mu_f, dxa + 3 * a, g);
@@ -354,17 +360,17 @@ __device__ __noinline__ void qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int n
       for (int j = 0; j < 5; ++j) {
         const S sj = s[5 * a + j], zj = z[5 * a + j];
         const S dsj = -rp[5 * a + j] - g[j];
-        const S dzj = -(sj * zj + zj * dsj) / sj;
+        const S dzj = -(sj * zj + zj * dsj) * is[5 * a + j];
         dsa[5 * a + j] = dsj; dza[5 * a + j] = dzj;
-        if (dsj < S(0)) amax = min_t(amax, -sj / dsj);
-        if (dzj < S(0)) amax = min_t(amax, -zj / dzj);
+        rmax = max_t(rmax, max_t(-dsj * is[5 * a + j], -dzj * iz[5 * a + j]));
       }
     }
-    amax = warp_min(amax);
+    rmax = warp_max(rmax);
+    const S amax = S(1) / rmax;  // rmax >= 1
     __syncwarp();  // ds_a / dz_a were written point-wise, read element-wise below
     S mua = S(0);
     for (int j = lane; j < M; j += 32) mua += (s[j] + amax * dsa[j]) * (z[j] + amax * dza[j]);
-    mua = warp_sum(mua) / S(M);
+    mua = warp_sum(mua) * inv_M;
     S sg = mua / mu;
     sg = sg * sg * sg;
     // corrector: r_c = s z + ds_a dz_a - sigma mu
@@ -374,15 +380,15 @@ __device__ __noinline__ void qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int n
       for (int j = 0; j < 5; ++j) {
         const S sj = s[5 * a + j], zj = z[5 * a + j];
         const S rc = sj * zj + dsa[5 * a + j] * dza[5 * a + j] - sg * mu;
-        t[j] = (zj * rp[5 * a + j] - rc) / sj;
+        t[j] = (zj * rp[5 * a + j] - rc) * is[5 * a + j];
       }
       pyr_GT(mu_f, t, g);
 #pragma unroll
       for (int d = 0; d < 3; ++d) dx[3 * a + d] = -(rd[3 * a + d] + g[d]);
     }
     __syncwarp();
-    chol_solve(Hp, dx, N, lane);
-    S al = S(1e30);
+    chol_solve(Hp, dg, dx, N, lane);
+    S rm2 = S(0);
     for (int a = lane; a < na; a += 32) {
       S g[5];
       pyr_G(mu_f, dx + 3 * a, g);
@@ -391,13 +397,14 @@ __device__ __noinline__ void qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int n
         const S sj = s[5 * a + j], zj = z[5 * a + j];
         const S rc = sj * zj + dsa[5 * a + j] * dza[5 * a + j] - sg * mu;
         const S dsj = -rp[5 * a + j] - g[j];
-        const S dzj = -(rc + zj * dsj) / sj;
+        const S dzj = -(rc + zj * dsj) * is[5 * a + j];
         ds[5 * a + j] = dsj; dz[5 * a + j] = dzj;
-        if (dsj < S(0)) al = min_t(al, -sj / dsj);
-        if (dzj < S(0)) al = min_t(al, -zj / dzj);
+        rm2 = max_t(rm2, max_t(-dsj * is[5 * a + j], -dzj * iz[5 * a + j]));
       }
     }
-    al = min_t(S(1), S(0.99) * warp_min(al));
+    rm2 = warp_max(rm2);
+    // alpha = min(1, 0.99 / rm2)
+    const S al = (rm2 > S(0.99)) ? S(0.99) / rm2 : S(1);
     __syncwarp();
     for (int i = lane; i < N; i += 32) x[i] += al * dx[i];
     for (int j = lane; j < M; j += 32) { s[j] += al * ds[j]; z[j] += al * dz[j]; }
