@@ -38,6 +38,7 @@ struct B200SimModel {
   int o_parent = 0, o_jtype = 0, o_lvl_start = 0, o_lvl_links = 0, o_child_start = 0, o_child_idx = 0,
       o_pt_start = 0, o_pt_idx = 0, o_pt_body = 0, o_pt_enabled = 0, o_anc = 0, o_ldepth = 0;
   double reg = 1e-6;
+  unsigned long long* dbg_d = nullptr;  // debug counters, allocated by b200sim_debug_counters
   int* rigid_scratch = nullptr;      // work lists of the rigid-contact cascade
   long long rigid_scratch_cap = 0;
   // device blobs
@@ -189,6 +190,7 @@ void fill_model_params(const B200SimModel* m, Params<T>& P) {
   P.o_child_start = m->o_child_start; P.o_child_idx = m->o_child_idx; P.o_pt_start = m->o_pt_start;
   P.o_pt_idx = m->o_pt_idx; P.o_pt_body = m->o_pt_body; P.o_pt_enabled = m->o_pt_enabled;
   P.o_anc = m->o_anc; P.o_ldepth = m->o_ldepth; P.reg = (T)m->reg;
+  P.dbg = m->dbg_d;
   P.dt = (T)m->dt; P.g = (T)m->g; P.h_terrain = (T)m->h_terrain;
   P.K = (T)m->K; P.D = (T)m->D; P.mu = (T)m->mu; P.pexp = (T)m->pexp; P.qexp = (T)m->qexp;
   P.tau_max = (T)m->tau_max; P.w_th = (T)m->w_th; P.w_max = (T)m->w_max;
@@ -685,7 +687,7 @@ void b200sim_model_destroy(B200SimModel* m) {
   cudaGetDevice(&prev);
   cudaSetDevice(m->device);
   cudaFree(m->cst_f); cudaFree(m->cst_d); cudaFree(m->csuc_f); cudaFree(m->csuc_d);
-  cudaFree(m->pt_f); cudaFree(m->pt_d); cudaFree(m->itab_d); cudaFree(m->rigid_scratch);
+  cudaFree(m->pt_f); cudaFree(m->pt_d); cudaFree(m->itab_d); cudaFree(m->rigid_scratch); cudaFree(m->dbg_d);
   cudaFree(m->cst_dd); cudaFree(m->csuc_dd); cudaFree(m->pt_dd);
   cudaSetDevice(prev);
   delete m;
@@ -711,6 +713,25 @@ int b200sim_model_set_tuning(B200SimModel* m, int lanes_per_env, int envs_per_bl
   if (envs_per_block < 0) return B200SIM_E_INVALID;
   m->tune_G = G;
   m->tune_epb = envs_per_block;
+  return 0;
+}
+
+// Undeclared diagnostic (not part of the ABI): enables, reads and resets the rigid-contact counters
+// [0] QP iterations, [1] QPs, [2] max iterations, [3] active points (QP), [4] full items,
+// [5] impact-only items, [6] impacts, [7] active points (impact).
+extern "C" int b200sim_debug_counters(B200SimModel* m, unsigned long long* out8) {
+  if (!m) return B200SIM_E_INVALID;
+  int prev = 0;
+  CK(cudaGetDevice(&prev));
+  CK(cudaSetDevice(m->device));
+  if (!m->dbg_d) {
+    CK(cudaMalloc((void**)&m->dbg_d, 8 * sizeof(unsigned long long)));
+    CK(cudaMemset(m->dbg_d, 0, 8 * sizeof(unsigned long long)));
+  }
+  CK(cudaDeviceSynchronize());
+  if (out8) CK(cudaMemcpy(out8, m->dbg_d, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  CK(cudaMemset(m->dbg_d, 0, 8 * sizeof(unsigned long long)));
+  cudaSetDevice(prev);
   return 0;
 }
 

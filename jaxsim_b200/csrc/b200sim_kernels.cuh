@@ -131,6 +131,7 @@ struct Params {
   int* over_count;
   int* over_list;
   int na_cap;  // active points the consumer's shared-memory workspace is sized for
+  unsigned long long* dbg;  // optional counters (b200sim_debug_counters): QP iterations, items per level, ...
 };
 
 // ------------------------------------------------------------------------------------

@@ -124,44 +124,70 @@ __device__ __forceinline__ void sym_matvec(const S* Ap, const S* x, S* y, int N,
   }
 }
 
-// In-place Cholesky of a packed lower-triangular matrix, warp-cooperative, right-looking.
+// In-place Cholesky of a packed lower-triangular matrix, warp-cooperative, LEFT-looking: at
+// step k every lane owns rows r > k and forms L[r,k] = (H[r,k] - <L[r,0:k], L[k,0:k]>) / L[k,k]
+// -- equal work per lane (a k-term dot product over a contiguous packed row against a broadcast
+// row), one barrier per step; the diagonal H[r,r] is kept as the running Schur complement.
 // `dg` holds the diagonal before elimination on entry (pivots are floored at pivot_floor * dg:
 // the interior-point Hessian is positive definite up to rounding) and 1 / L_kk on exit, so
 // that the triangular solves multiply instead of divide.
 template <typename S>
-__device__ __forceinline__ void chol_packed(S* Hp, S* dg, int N, int lane) {
+__device__ __forceinline__ void chol_packed(S* __restrict__ Hp, S* __restrict__ dg, int N, int lane) {
   for (int k = 0; k < N; ++k) {
     S d = max_t(Hp[pidx(k, k)], QpTol<S>::pivot_floor() * dg[k]);
     if (!(d > S(0))) d = S(1);
     const S ipiv = S(1) / sqrt_t(d);
-    for (int r = k + 1 + lane; r < N; r += 32) Hp[pidx(r, k)] *= ipiv;
-    __syncwarp();
-    if (lane == 0) dg[k] = ipiv;
+    const S* rowk = Hp + pidx(k, 0);
     for (int r = k + 1 + lane; r < N; r += 32) {
-      const S lrk = Hp[pidx(r, k)];
       S* row = Hp + pidx(r, 0);
-      for (int c = k + 1; c <= r; ++c) row[c] -= lrk * Hp[pidx(c, k)];
+      S a0 = row[k], a1 = S(0);
+      int c = 0;
+      for (; c + 1 < k; c += 2) { a0 -= row[c] * rowk[c]; a1 -= row[c + 1] * rowk[c + 1]; }
+      if (c < k) a0 -= row[c] * rowk[c];
+      const S v = (a0 + a1) * ipiv;
+      row[k] = v;
+      row[r] -= v * v;
     }
+    if (lane == 0) dg[k] = ipiv;
     __syncwarp();
   }
 }
 
-// solve L L^T x = y in place; invd = 1 / diag(L)
+// solve L L^T x = y in place; invd = 1 / diag(L).  The vector lives in registers (lane owns
+// rows lane, lane+32, lane+64): the pivot element travels by shuffle, no shared-memory round
+// trip or barrier inside the substitution loops.  N <= 96.
 template <typename S>
-__device__ __forceinline__ void chol_solve(const S* Lp, const S* invd, S* y, int N, int lane) {
+__device__ __forceinline__ void chol_solve(const S* __restrict__ Lp, const S* __restrict__ invd, S* y, int N, int lane) {
+  S yr[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) yr[j] = (lane + 32 * j < N) ? y[lane + 32 * j] : S(0);
   for (int k = 0; k < N; ++k) {
-    const S yk = __shfl_sync(FULL, (lane == 0) ? y[k] : S(0), 0) * invd[k];
-    for (int r = k + 1 + lane; r < N; r += 32) y[r] -= Lp[pidx(r, k)] * yk;
-    if (lane == 0) y[k] = yk;
-    __syncwarp();
+    const int slot = k >> 5;
+    const S src = (slot == 0) ? yr[0] : ((slot == 1) ? yr[1] : yr[2]);
+    const S yk = __shfl_sync(FULL, src, k & 31) * invd[k];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int r = lane + 32 * j;
+      if (r > k && r < N) yr[j] -= Lp[pidx(r, k)] * yk;
+      else if (r == k) yr[j] = yk;
+    }
   }
   for (int k = N - 1; k >= 0; --k) {
-    const S xk = __shfl_sync(FULL, (lane == 0) ? y[k] : S(0), 0) * invd[k];
+    const int slot = k >> 5;
+    const S src = (slot == 0) ? yr[0] : ((slot == 1) ? yr[1] : yr[2]);
+    const S xk = __shfl_sync(FULL, src, k & 31) * invd[k];
     const S* row = Lp + pidx(k, 0);
-    for (int r = lane; r < k; r += 32) y[r] -= row[r] * xk;
-    if (lane == 0) y[k] = xk;
-    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int r = lane + 32 * j;
+      if (r < k) yr[j] -= row[r] * xk;
+      else if (r == k) yr[j] = xk;
+    }
   }
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+    if (lane + 32 * j < N) y[lane + 32 * j] = yr[j];
+  __syncwarp();
 }
 
 // Solve A x = y for a symmetric positive SEMI-definite, consistent system (packed lower A):
@@ -220,19 +246,7 @@ __device__ __noinline__ void psd_solve_pivoted(const S* Ap, S* Lp, S* d, S* y, S
   }
   for (int i = lane; i < N; i += 32) tmp[i] = y[perm[i]];
   __syncwarp();
-  for (int k = 0; k < rank; ++k) {
-    const S yk = __shfl_sync(FULL, (lane == 0) ? tmp[k] : S(0), 0) * d[k];
-    for (int r = k + 1 + lane; r < rank; r += 32) tmp[r] -= Lp[pidx(r, k)] * yk;
-    if (lane == 0) tmp[k] = yk;
-    __syncwarp();
-  }
-  for (int k = rank - 1; k >= 0; --k) {
-    const S xk = __shfl_sync(FULL, (lane == 0) ? tmp[k] : S(0), 0) * d[k];
-    const S* row = Lp + pidx(k, 0);
-    for (int r = lane; r < k; r += 32) tmp[r] -= row[r] * xk;
-    if (lane == 0) tmp[k] = xk;
-    __syncwarp();
-  }
+  chol_solve(Lp, d, tmp, rank, lane);
   for (int i = lane; i < N; i += 32) y[perm[i]] = (i < rank) ? tmp[i] : S(0);
   __syncwarp();
 }
@@ -252,7 +266,7 @@ __device__ __forceinline__ void pyr_GT(S mu, const S* w, S* o) {
 // operation (float64 especially): 1/s and 1/z are formed once per iteration and every
 // ratio below multiplies by them; the Cholesky factor carries 1/L_kk.
 template <typename S>
-__device__ __noinline__ void qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int na, S mu_f, int lane) {
+__device__ __noinline__ int qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int na, S mu_f, int lane) {
   const int N = 3 * na, M = 5 * na;
   S* x = vN;
   S* q = vN + N;
@@ -280,7 +294,8 @@ __device__ __noinline__ void qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int n
   const S tol = QpTol<S>::tol();
   const int NP = N * (N + 1) / 2;
   const S inv_M = S(1) / S(M);
-  for (int it = 0; it < QpTol<S>::max_iter; ++it) {
+  int it = 0;
+  for (; it < QpTol<S>::max_iter; ++it) {
     // residuals
     sym_matvec(Qp, x, rd, N, lane);
     __syncwarp();
@@ -413,6 +428,7 @@ __device__ __noinline__ void qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int n
   __syncwarp();
   for (int i = lane; i < N; i += 32) x[i] = xb[i];
   __syncwarp();
+  return it;
 }
 
 // ------------------------------------------------------------------------------------
@@ -483,6 +499,7 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
       env = item & 0x7fffffff;
       impact_only = item < 0;
     }
+    if (P.dbg && lane == 0) atomicAdd(P.dbg + (impact_only ? 5 : 4), 1ull);
 
     // ============================================================== input state
     // (impact_only: the pre-impact result of this step, stored by the previous level)
@@ -1131,7 +1148,13 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
         q[3 * a + 2] = S(val[2] + acc[2] + P.g + bv[2]);
       }
       delassus(na, S(P.reg));
-      qp_pyramids<S>(Qp, Hp, vN, vM, na, S(P.mu), lane);
+      const int qp_it = qp_pyramids<S>(Qp, Hp, vN, vM, na, S(P.mu), lane);
+      if (P.dbg && lane == 0) {
+        atomicAdd(P.dbg + 0, (unsigned long long)qp_it);
+        atomicAdd(P.dbg + 1, 1ull);
+        atomicMax(P.dbg + 2, (unsigned long long)qp_it);
+        atomicAdd(P.dbg + 3, (unsigned long long)na);
+      }
       for (int a = lane; a < na; a += 32) {
         T* pw = pts + (size_t)alist[a] * RPT;
         pw[RP_F] = T(vN[3 * a]); pw[RP_F + 1] = T(vN[3 * a + 1]); pw[RP_F + 2] = T(vN[3 * a + 2]);
@@ -1246,6 +1269,7 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
       continue;
     }
     T dv0[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+    if (P.dbg && lane == 0 && na2 > 0) { atomicAdd(P.dbg + 6, 1ull); atomicAdd(P.dbg + 7, (unsigned long long)na2); }
     if (na2 > 0) {
       link_init(false);
       pass2();

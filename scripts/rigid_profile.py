@@ -50,6 +50,17 @@ p[:, 2] -= z.min(dim=1).values + 0.002 + 0.003 * torch.rand(B, dtype=dtype, devi
 data = js.data.JaxSimModelData.build(m, base_position=p, **kw)
 tau = 10 * torch.rand(B, n, dtype=dtype, device=dev)
 out = js.model.step(m, data, joint_force_references=tau)
+import ctypes  # noqa: E402
+from jaxsim_b200 import _lib  # noqa: E402
+lib = _lib.load()
+cnt = (ctypes.c_ulonglong * 8)()
+lib.b200sim_debug_counters.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+lib.b200sim_debug_counters(m.device_model(dev).handle, cnt)  # enable
+js.model.step(m, data, joint_force_references=tau, out=out)
+lib.b200sim_debug_counters(m.device_model(dev).handle, cnt)
+c = list(cnt)
+print("counters: QPs %d, mean it %.1f, max it %d, mean active %.1f | full items %d, impact-only %d, impacts %d (mean active %.1f)"
+      % (c[1], c[0] / max(c[1], 1), c[2], c[3] / max(c[1], 1), c[4], c[5], c[6], c[7] / max(c[6], 1)))
 for _ in range(3):
     js.model.step(m, data, joint_force_references=tau, out=out)
 torch.cuda.synchronize()
