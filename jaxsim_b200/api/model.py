@@ -31,7 +31,7 @@ from jaxsim_b200.rbda.contacts import RigidContacts, RigidContactsParams, SoftCo
 from jaxsim_b200.terrain import FlatTerrain
 
 from . import data as _data
-from .common import VelRepr, other_representation_to_inertial
+from .common import VelRepr, inertial_to_other_representation, other_representation_to_inertial
 from .kin_dyn_parameters import KinDynParameters
 
 STANDARD_GRAVITY = 9.81  # src/jaxsim/math/__init__.py:14
@@ -514,12 +514,11 @@ def forward_dynamics_aba(
     joint_forces: torch.Tensor | None = None,
     link_forces: torch.Tensor | None = None,
 ) -> tuple[torch.Tensor, torch.Tensor]:
-    """``js.model.forward_dynamics_aba`` (``src/jaxsim/api/model.py:1269-1406``) for
-    ``VelRepr.Inertial`` data: returns the inertial-fixed base acceleration ``(B, 6)`` and
-    the joint accelerations ``(B, n)``.  (The Body/Mixed ``to_active`` conversion of
-    ``:1356-1404`` is a thin host-side shim that is not needed by ``step``.)"""
-    if data.velocity_representation != VelRepr.Inertial:
-        raise NotImplementedError("forward_dynamics_aba: only VelRepr.Inertial data (step forces it, integrators.py:22)")
+    """``js.model.forward_dynamics_aba`` (``src/jaxsim/api/model.py:1269-1406``): returns the
+    base acceleration ``(B, 6)`` in ``data.velocity_representation`` and the joint
+    accelerations ``(B, n)``.  ``link_forces`` are expressed in that representation too
+    (``:1315-1321``).  The kernel works inertial-fixed; the Body/Mixed ``to_active``
+    conversion of ``:1356-1404`` is a few batched torch ops around it."""
     s = _batched(data._joint_positions, 1).contiguous()
     dev, dtype = s.device, s.dtype
     dm = model.device_model(dev)
@@ -536,6 +535,9 @@ def forward_dynamics_aba(
         raise ValueError(tau.shape, (B, n))
     if fext is not None and fext.shape != (B, nL, 6):
         raise ValueError(fext.shape, (B, nL, 6))
+    vr = data.velocity_representation
+    if fext is not None and vr != VelRepr.Inertial:
+        fext = other_representation_to_inertial(fext, vr, _batched(data.link_transforms, 3), is_force=True).contiguous()
     avd = torch.empty(B, 6, dtype=dtype, device=dev)
     sdd = torch.empty(B, n, dtype=dtype, device=dev)
     with torch.cuda.device(dev):
@@ -544,9 +546,48 @@ def forward_dynamics_aba(
             _ptr(tau), _ptr(fext), _ptr(avd), _ptr(sdd), _stream_ptr(dev),
         )
     _lib.check(rc, "b200sim_aba")
+    if vr != VelRepr.Inertial:
+        avd = _base_acceleration_to_active(model, data, avd, vl, om)
     if data._joint_positions.dim() == 1:
         return avd.squeeze(0), sdd.squeeze(0)
     return avd, sdd
+
+
+def _frame_C(data, vl, om):
+    """``W_H_C`` and ``W_v_WC`` of the active representation (``api/model.py:1373-1391``):
+    C = B for Body, C = B[W] for Mixed."""
+    W_H_B = _batched(data.base_transform, 2)
+    W_v_WB = torch.cat([vl, om], dim=-1)
+    if data.velocity_representation == VelRepr.Body:
+        return W_H_B, W_v_WB, W_v_WB
+    W_H_C = W_H_B.clone()
+    W_H_C[..., 0:3, 0:3] = torch.eye(3, dtype=W_H_B.dtype, device=W_H_B.device)
+    # linear velocity of the base origin: the mixed base velocity (api/data.py:288-312)
+    W_pd_B = vl + torch.linalg.cross(om, W_H_B[..., 0:3, 3])
+    W_v_WC = torch.cat([W_pd_B, torch.zeros_like(om)], dim=-1)
+    return W_H_C, W_v_WC, W_v_WB
+
+
+def _cross_vx(v: torch.Tensor) -> torch.Tensor:
+    """``Cross.vx`` (``math/cross.py:10-27``): [[S(w), S(v)], [0, S(w)]], batched."""
+    from .common import _wedge
+
+    X = torch.zeros(v.shape[:-1] + (6, 6), dtype=v.dtype, device=v.device)
+    X[..., 0:3, 0:3] = _wedge(v[..., 3:6])
+    X[..., 0:3, 3:6] = _wedge(v[..., 0:3])
+    X[..., 3:6, 3:6] = _wedge(v[..., 3:6])
+    return X
+
+
+def _base_acceleration_to_active(model, data, W_vd_WB, vl, om):
+    """``to_active`` (``api/model.py:1356-1404``): C_X_W (W_vd_WB - W_v_WC x W_v_WB)."""
+    from .common import adjoint_from_transform
+
+    if not model.floating_base():
+        return torch.zeros_like(W_vd_WB)
+    W_H_C, W_v_WC, W_v_WB = _frame_C(data, vl, om)
+    C_X_W = adjoint_from_transform(W_H_C, inverse=True)
+    return torch.einsum("...ij,...j->...i", C_X_W, W_vd_WB - torch.einsum("...ij,...j->...i", _cross_vx(W_v_WC), W_v_WB))
 
 
 def inverse_dynamics(
@@ -558,10 +599,9 @@ def inverse_dynamics(
     link_forces: torch.Tensor | None = None,
 ) -> tuple[torch.Tensor, torch.Tensor]:
     """``js.model.inverse_dynamics`` (``src/jaxsim/api/model.py:1746-1894``) -> vmapped
-    ``rbda.rnea`` (``rbda/rnea.py:12-238``) for ``VelRepr.Inertial`` data: returns the
-    inertial-fixed 6D base force ``(B, 6)`` and the joint forces ``(B, n)``."""
-    if data.velocity_representation != VelRepr.Inertial:
-        raise NotImplementedError("inverse_dynamics: only VelRepr.Inertial data (the kernel's native representation)")
+    ``rbda.rnea`` (``rbda/rnea.py:12-238``): returns the 6D base force ``(B, 6)`` in
+    ``data.velocity_representation`` and the joint forces ``(B, n)``.  ``base_acceleration``
+    and ``link_forces`` are expressed in that representation (``to_inertial``, ``:1800-1845``)."""
     s = _batched(data._joint_positions, 1).contiguous()
     dev, dtype = s.device, s.dtype
     dm = model.device_model(dev)
@@ -584,6 +624,19 @@ def inverse_dynamics(
     sdd = opt(joint_accelerations, (B, n), 1)
     avd = opt(base_acceleration, (B, 6), 1)
     fext = opt(link_forces, (B, nL, 6), 2)
+    vr = data.velocity_representation
+    if vr != VelRepr.Inertial:
+        from .common import adjoint_from_transform
+
+        if fext is not None:
+            fext = other_representation_to_inertial(fext, vr, _batched(data.link_transforms, 3), is_force=True).contiguous()
+        # to_inertial (:1800-1845): W_X_C (C_vd_WB + C_v_WC x C_v_WB)
+        W_H_C, W_v_WC, W_v_WB = _frame_C(data, vl, om)
+        C_X_W = adjoint_from_transform(W_H_C, inverse=True)
+        mv = lambda X, v: torch.einsum("...ij,...j->...i", X, v)  # noqa: E731
+        C_v_WB = _batched(data.base_velocity, 1)
+        acc = avd if avd is not None else torch.zeros(B, 6, dtype=dtype, device=dev)
+        avd = mv(adjoint_from_transform(W_H_C), acc + mv(_cross_vx(mv(C_X_W, W_v_WC)), C_v_WB)).contiguous()
     W_f = torch.empty(B, 6, dtype=dtype, device=dev)
     tau = torch.empty(B, n, dtype=dtype, device=dev)
     with torch.cuda.device(dev):
@@ -592,6 +645,8 @@ def inverse_dynamics(
             _ptr(avd), _ptr(sdd), _ptr(fext), _ptr(W_f), _ptr(tau), _stream_ptr(dev),
         )
     _lib.check(rc, "b200sim_rnea")
+    if vr != VelRepr.Inertial:
+        W_f = inertial_to_other_representation(W_f, vr, _batched(data.base_transform, 2), is_force=True)
     if data._joint_positions.dim() == 1:
         return W_f.squeeze(0), tau.squeeze(0)
     return W_f, tau

@@ -1,0 +1,73 @@
+"""The golden-fixture case table, shared by the generator (`make_goldens.py`, which runs the
+reference) and by the tests that consume the fixtures (`tests/test_reference_goldens.py`,
+`tests/test_gpu_reference_goldens.py`).
+
+A case names a model of `jaxsim_b200.models`, a contact model and its parameters, an
+integrator, and how the seeded inputs are drawn.  The inputs themselves are stored in the
+fixture next to the reference's outputs, so the tests never regenerate them.
+"""
+
+from __future__ import annotations
+
+import hashlib
+import pathlib
+
+GOLDEN_DIR = pathlib.Path(__file__).resolve().parent
+
+_ICUB = dict(model="icub_like", B=3)
+
+CASES = [
+    # ---- soft contacts, semi-implicit Euler (BASELINE configs[0], [1])
+    dict(id="pendulum_soft", model="pendulum", B=4, seed=0, tau=True, rbda=True),
+    dict(id="double_pendulum_soft", model="double_pendulum", B=3, seed=1, tau=True),
+    dict(id="cartpole_soft", model="cartpole", B=3, seed=2, tau=True, rbda=True),
+    dict(id="box_soft_air", model="box", B=3, seed=3),
+    dict(id="box_soft_contact", model="box", B=4, seed=4, in_contact=True, m=True, rbda=True),
+    dict(id="box_soft_flat", model="box", B=3, seed=5, in_contact="flat", m=True),
+    dict(id="sphere_soft_contact", model="sphere", B=2, seed=6, in_contact=True, m=True),
+    dict(id="icub_soft_air", seed=7, tau=True, rbda=True, **_ICUB),
+    dict(id="icub_soft_contact", seed=8, in_contact=True, tau=True, m=True, rbda=True, **_ICUB),
+    dict(id="icub_soft_flat", seed=9, in_contact="flat", tau=True, m=True, **_ICUB),
+    dict(id="icub_soft_params", seed=10, in_contact=True, tau=True, m=True,
+         contact_params=dict(K=2e5, D=500.0, mu=0.8, p=0.7, q=1.3), **_ICUB),
+    dict(id="icub_soft_nofriction", seed=11, in_contact=True, tau=True,
+         actuation=dict(torque_max=40.0, omega_th=0.3, omega_max=0.9, enable_friction=False), **_ICUB),
+    dict(id="icub_soft_fext_inertial", rbda=True, seed=12, in_contact=True, tau=True, fext=True, velrepr="inertial", **_ICUB),
+    dict(id="icub_soft_fext_mixed", rbda=True, seed=13, in_contact=True, tau=True, fext=True, velrepr="mixed", **_ICUB),
+    dict(id="icub_soft_fext_body", rbda=True, seed=14, in_contact=True, tau=True, fext=True, velrepr="body", **_ICUB),
+    dict(id="ergocub_soft_contact", model="ergocub_like", B=2, seed=15, in_contact=True, tau=True, m=True),
+    # ---- RK4
+    dict(id="icub_rk4_contact", seed=16, in_contact=True, tau=True, m=True, integrator="rk4", **_ICUB),
+    dict(id="box_rk4_contact", model="box", B=3, seed=17, in_contact=True, m=True, integrator="rk4"),
+    # ---- rigid contacts (BASELINE configs[2])
+    dict(id="box_rigid_air", model="box", B=2, seed=18, contact="rigid"),
+    dict(id="box_rigid_contact", model="box", B=4, seed=19, contact="rigid", in_contact=True),
+    dict(id="box_rigid_flat", model="box", B=4, seed=20, contact="rigid", in_contact="flat"),
+    dict(id="box_rigid_flat_baumgarte", model="box", B=3, seed=21, contact="rigid", in_contact="flat",
+         contact_params=dict(mu=0.7, K=1e4, D=20.0)),
+    dict(id="icub_rigid_contact", seed=22, contact="rigid", in_contact=True, tau=True, **_ICUB),
+    dict(id="icub_rigid_flat", seed=23, contact="rigid", in_contact="flat", tau=True, model="icub_like", B=2),
+    dict(id="ergocub_rigid_flat", model="ergocub_like", B=2, seed=24, contact="rigid", in_contact="flat", tau=True),
+]
+
+DEFAULTS = dict(contact="soft", contact_params=None, actuation=None, integrator="semi_implicit_euler", in_contact=False,
+                tau=False, m=False, fext=False, velrepr="inertial", rbda=False, time_step=1e-3)
+
+
+def case(cid: str) -> dict:
+    for c in CASES:
+        if c["id"] == cid:
+            return {**DEFAULTS, **c}
+    raise KeyError(cid)
+
+
+def all_cases() -> list[dict]:
+    return [{**DEFAULTS, **c} for c in CASES]
+
+
+def fixture_path(cid: str) -> pathlib.Path:
+    return GOLDEN_DIR / f"{cid}.npz"
+
+
+def urdf_digest(urdf_text: str) -> str:
+    return hashlib.sha256(urdf_text.encode()).hexdigest()[:16]

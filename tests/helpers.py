@@ -18,6 +18,22 @@ def build_model(name: str, **kw):
     return js.model.JaxSimModel.build_from_model_description(models.urdf(name), **kw)
 
 
+def build_model_for_case(case: dict):
+    """Product model of a golden-fixture case (tests/golden/cases.py)."""
+    from jaxsim_b200.rbda.actuation import ActuationParams
+    from jaxsim_b200.rbda.contacts import RigidContactsParams, SoftContactsParams
+
+    rigid = case["contact"] == "rigid"
+    cm = RigidContacts.build() if rigid else SoftContacts.build()
+    cp = None
+    if case["contact_params"]:
+        cp = (RigidContactsParams if rigid else SoftContactsParams).build(**case["contact_params"])
+    ap = ActuationParams(**case["actuation"]) if case["actuation"] else None
+    integ = {"semi_implicit_euler": js.model.IntegratorType.SemiImplicitEuler, "rk4": js.model.IntegratorType.RungeKutta4}[case["integrator"]]
+    return build_model(case["model"], time_step=case["time_step"], contact_model=cm, contact_params=cp,
+                       actuation_params=ap, integrator=integ)
+
+
 def oracle_model(model) -> O.OracleModel:
     prm = model.contact_params
     soft = isinstance(model.contact_model, SoftContacts)

@@ -1,0 +1,105 @@
+"""-m gpu: the CUDA path (through the C ABI, via the Python mirror of the reference API)
+against fixtures produced by RUNNING THE REFERENCE's own sources
+(tests/golden/make_goldens.py, `oracle/refshim/README.md`).  Same inputs, the reference's
+outputs; north_star tolerances 1e-5 rel (float64) / 1e-3 rel (float32) on every leaf.
+Nothing here needs `/root/reference`: only the committed .npz fixtures travel to the GPU box.
+"""
+
+import json
+
+import numpy as np
+import pytest
+
+import jaxsim_b200.api as js
+from oracle import jaxsim_oracle as O
+from tests.golden import cases as C
+
+from . import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+IDS = [c["id"] for c in C.all_cases()]
+VELREPR = {"inertial": js.common.VelRepr.Inertial, "mixed": js.common.VelRepr.Mixed, "body": js.common.VelRepr.Body}
+
+
+def _dtype(name):
+    import torch
+
+    return {"float64": torch.float64, "float32": torch.float32}[name]
+
+
+def _load(cid):
+    z = np.load(C.fixture_path(cid), allow_pickle=False)
+    return z, json.loads(str(z["spec"]))
+
+
+class _Ref:
+    """The reference's outputs of a fixture, shaped like the oracle's data for compare_data."""
+
+    def __init__(self, z, soft):
+        for oname, pname in H.LEAVES:
+            setattr(self, oname, z["out" + pname])
+        self.tangential_deformation = z["out_tangential_deformation"] if soft else None
+
+
+def _inputs(case, z, model, dtype, dev):
+    om = H.oracle_model(model)
+    od = O.data_replace(om, z["in_joint_positions"], z["in_joint_velocities"], z["in_base_quaternion"],
+                        z["in_base_linear_velocity"], z["in_base_angular_velocity"], z["in_base_position"],
+                        z["in_tangential_deformation"])
+    return H.to_product(model, od, dtype, dev, velocity_representation=VELREPR[case["velrepr"]])
+
+
+def _vel_floors(z):
+    v = max(float(np.abs(z["in_base_linear_velocity"]).max()), float(np.abs(z["in_base_angular_velocity"]).max()),
+            float(np.abs(z["in_joint_velocities"]).max()) if z["in_joint_velocities"].size else 0.0, 1e-3)
+    return {"base_linear_velocity": v, "base_angular_velocity": v, "joint_velocities": v, "link_velocities": v}
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("cid", IDS)
+def test_step_matches_reference(cid, dtype, cuda_device):
+    import torch
+
+    z, _ = _load(cid)
+    case = C.case(cid)
+    model = H.build_model_for_case(case)
+    td = _dtype(dtype)
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=td, device=cuda_device)  # noqa: E731
+    data = _inputs(case, z, model, td, cuda_device)
+    out = js.model.step(model, data, link_forces=t(z["in_link_forces"]) if case["fext"] else None,
+                        joint_force_references=t(z["in_tau"]) if case["tau"] else None)
+    assert out.velocity_representation == data.velocity_representation
+    soft = case["contact"] == "soft"
+    floors = _vel_floors(z) if case["contact"] == "rigid" else None
+    H.compare_data(out, _Ref(z, soft), H.RTOL[dtype], f"golden {cid} {dtype}", floors=floors)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("cid", [c["id"] for c in C.all_cases() if c["rbda"]])
+def test_rbda_matches_reference(cid, dtype, cuda_device):
+    import torch
+
+    z, _ = _load(cid)
+    case = C.case(cid)
+    model = H.build_model_for_case(case)
+    td = _dtype(dtype)
+    rtol = H.RTOL[dtype]
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=td, device=cuda_device)  # noqa: E731
+    data = _inputs(case, z, model, td, cuda_device)
+    g = lambda x: x.detach().cpu().numpy()  # noqa: E731
+    lf = t(z["in_link_forces"]) if case["fext"] else None
+    for name, vr in VELREPR.items():
+        data.velocity_representation = vr
+        vd, sdd = js.model.forward_dynamics_aba(model, data, joint_forces=t(z["in_tau"]), link_forces=lf)
+        assert H.rel_err(g(vd), z[f"aba_base_acceleration_{name}"]) <= rtol, name
+        assert H.rel_err(g(sdd), z[f"aba_joint_accelerations_{name}"]) <= rtol, name
+        fb, tj = js.model.inverse_dynamics(model, data, joint_accelerations=t(z["in_joint_accelerations"]),
+                                           base_acceleration=t(z["in_base_acceleration"]), link_forces=lf)
+        assert H.rel_err(g(fb), z[f"rnea_base_force_{name}"]) <= rtol, name
+        assert H.rel_err(g(tj), z[f"rnea_joint_forces_{name}"]) <= rtol, name
+        M = g(js.model.free_floating_mass_matrix(model, data))
+        ref = z[f"mass_matrix_{name}"]
+        if not model.floating_base():
+            M, ref = M[..., -model.dofs():, -model.dofs():], ref[..., 6:, 6:]
+        assert H.rel_err(M, ref) <= rtol, name

@@ -1,0 +1,158 @@
+"""-m "not gpu": the oracle and the URDF loader against fixtures produced by RUNNING THE
+REFERENCE's own sources (tests/golden/make_goldens.py; `oracle/refshim/README.md` explains
+how the reference is executed without JAX).  This is what pins the oracle: every fixture
+holds the inputs and what `jaxsim.api.model.step` (and `forward_dynamics_aba`,
+`inverse_dynamics`, `free_floating_mass_matrix`, `ode.system_dynamics`) returned for them.
+
+Tolerances: 1e-9 relative for everything that is closed-form (soft contacts, RK4, RBDAs:
+two float64 evaluation orders of the same formulas); 1e-6 for the rigid-contact step, whose
+contact forces are the optimum of a QP found by two different interior-point codes.
+"""
+
+import json
+
+import numpy as np
+import pytest
+
+from oracle import jaxsim_oracle as O
+from oracle import rigid_oracle as R
+from tests.golden import cases as C
+
+from . import helpers as H
+
+IDS = [c["id"] for c in C.all_cases()]
+OUT_LEAVES = [(o, "out" + p) for o, p in H.LEAVES]
+
+
+def _load(cid):
+    path = C.fixture_path(cid)
+    if not path.exists():
+        pytest.fail(f"golden fixture {path.name} is missing: run tests/golden/make_goldens.py in the build container")
+    z = np.load(path, allow_pickle=False)
+    spec = json.loads(str(z["spec"]))
+    return z, spec
+
+
+def _models(case):
+    from jaxsim_b200 import models
+
+    pm = H.build_model_for_case(case)
+    return pm, H.oracle_model(pm), models.urdf(case["model"])
+
+
+def _oracle_data(om, z):
+    return O.data_replace(om, z["in_joint_positions"], z["in_joint_velocities"], z["in_base_quaternion"],
+                          z["in_base_linear_velocity"], z["in_base_angular_velocity"], z["in_base_position"],
+                          z["in_tangential_deformation"])
+
+
+def _link_forces_inertial(case, z, od):
+    if not case["fext"]:
+        return None
+    return O.other_representation_to_inertial(z["in_link_forces"], case["velrepr"], od.link_transforms, is_force=True)
+
+
+def _rel(a, b, floor=1e-12):
+    return float(np.max(np.abs(np.asarray(a, float) - np.asarray(b, float)))) / max(float(np.max(np.abs(b))), floor) if np.size(b) else 0.0
+
+
+@pytest.mark.parametrize("cid", IDS)
+def test_fixture_matches_case_table(cid):
+    """The fixture was generated for the case as it is defined today, on today's URDF text."""
+    z, spec = _load(cid)
+    case = C.case(cid)
+    _, _, urdf = _models(case)
+    assert spec["urdf_sha256_16"] == C.urdf_digest(urdf), "model URDF changed since the fixture was generated"
+    for k, v in case.items():
+        assert spec[k] == v or (isinstance(v, (dict, list)) and json.loads(json.dumps(v)) == spec[k]), (k, v, spec[k])
+
+
+@pytest.mark.parametrize("cid", sorted({c["id"] for c in C.all_cases() if c["id"] in
+                                        ("pendulum_soft", "double_pendulum_soft", "cartpole_soft", "box_soft_air", "sphere_soft_contact",
+                                         "icub_soft_air", "ergocub_soft_contact")}))
+def test_urdf_loader_matches_reference_kinematic_graph(cid):
+    """`jaxsim_b200.parsers.urdf` against the reference's KinDynParameters.build +
+    ModelDescription.build_model_from (fixed-joint lumping, BFS link order, joint model,
+    collidable points)."""
+    z, _ = _load(cid)
+    pm, _, _ = _models(C.case(cid))
+    kd = pm.kin_dyn_parameters
+    assert tuple(kd.link_names) == tuple(str(s) for s in z["kd_link_names"])
+    assert np.array_equal(np.asarray(kd.parent_array), z["kd_parent_array"])
+    assert bool(pm.floating_base()) == bool(z["kd_floating_base"])
+    lp, jm, cp, jp = kd.link_parameters, kd.joint_model, kd.contact_parameters, kd.joint_parameters
+    np.testing.assert_allclose(lp.mass, z["kd_mass"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(lp.center_of_mass, z["kd_center_of_mass"], rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(lp.inertia_elements, z["kd_inertia_elements"], rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(jm.lam_H_pre, z["kd_lam_H_pre"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(jm.suc_H_i, z["kd_suc_H_i"], rtol=1e-12, atol=1e-14)
+    assert tuple(int(t) for t in jm.joint_types) == tuple(int(t) for t in z["kd_joint_types"])
+    np.testing.assert_allclose(np.asarray(jm.joint_axis).reshape(-1, 3), z["kd_joint_axis"].reshape(-1, 3), rtol=1e-12, atol=1e-14)
+    assert tuple(int(b) for b in cp.body) == tuple(int(b) for b in z["kd_contact_body"])
+    np.testing.assert_allclose(np.asarray(cp.point).reshape(-1, 3), z["kd_contact_point"].reshape(-1, 3), rtol=1e-12, atol=1e-14)
+    assert tuple(bool(b) for b in cp.enabled) == tuple(bool(b) for b in z["kd_contact_enabled"])
+    for name in ("friction_static", "friction_viscous", "position_limits_min", "position_limits_max",
+                 "position_limit_spring", "position_limit_damper"):
+        np.testing.assert_allclose(getattr(jp, name), z["kd_" + name], rtol=1e-12, atol=0, err_msg=name)
+
+
+@pytest.mark.parametrize("cid", IDS)
+def test_oracle_step_matches_reference(cid):
+    z, _ = _load(cid)
+    case = C.case(cid)
+    _, om, _ = _models(case)
+    od = _oracle_data(om, z)
+    # the caches the reference built for the INPUT state are what the oracle's data_replace gives
+    W_f = _link_forces_inertial(case, z, od)
+    tau = z["in_tau"] if case["tau"] else None
+    if case["contact"] == "rigid":
+        out, tol = R.step(om, od, link_forces_inertial=W_f, joint_force_references=tau), 1e-6
+    elif case["integrator"] == "rk4":
+        out, tol = O.step_rk4(om, od, link_forces_inertial=W_f, joint_force_references=tau), 1e-9
+    else:
+        out, tol = O.step(om, od, link_forces_inertial=W_f, joint_force_references=tau), 1e-9
+    # velocities can be brought to ~0 by a rigid impact: measure them against their scale before the step
+    vscale = max(float(np.abs(z["in_base_linear_velocity"]).max()), float(np.abs(z["in_base_angular_velocity"]).max()),
+                 float(np.abs(z["in_joint_velocities"]).max()) if z["in_joint_velocities"].size else 0.0, 1e-3)
+    errs = {}
+    for oname, key in OUT_LEAVES:
+        floor = vscale if ("velocit" in oname and case["contact"] == "rigid") else 1e-12
+        errs[oname] = _rel(getattr(out, oname), z[key], floor)
+    if case["contact"] == "soft":
+        errs["tangential_deformation"] = _rel(out.tangential_deformation, z["out_tangential_deformation"], 1e-6)
+    bad = {k: v for k, v in errs.items() if not v <= tol}
+    assert not bad, f"{cid}: oracle differs from the reference beyond {tol}: {bad}"
+
+
+@pytest.mark.parametrize("cid", [c["id"] for c in C.all_cases() if c["rbda"]])
+def test_oracle_rbda_matches_reference(cid):
+    z, _ = _load(cid)
+    case = C.case(cid)
+    _, om, _ = _models(case)
+    od = _oracle_data(om, z)
+    B, nL = od.joint_positions.shape[0], om.number_of_links()
+    # the "_inertial" goldens read the link forces in inertial-fixed representation
+    W_f = z["in_link_forces"] if case["fext"] else np.zeros((B, nL, 6))
+    args = (od.base_position, od.base_orientation, od.joint_positions, od.base_linear_velocity, od.base_angular_velocity,
+            od.joint_velocities)
+    vd, sdd = O.aba(om, *args, z["in_tau"], W_f)
+    assert _rel(vd, z["aba_base_acceleration_inertial"]) <= 1e-9
+    assert _rel(sdd, z["aba_joint_accelerations_inertial"]) <= 1e-9
+    fb, tj = O.rnea(om, *args, z["in_base_acceleration"], z["in_joint_accelerations"], W_f)
+    assert _rel(fb, z["rnea_base_force_inertial"]) <= 1e-9
+    assert _rel(tj, z["rnea_joint_forces_inertial"]) <= 1e-9
+    # joint accelerations do not depend on the representation the base quantities are expressed in,
+    # provided the link forces are the same physical forces
+    if not case["fext"]:
+        for name in ("mixed", "body"):
+            assert _rel(sdd, z[f"aba_joint_accelerations_{name}"]) <= 1e-9
+    M = O.crba(om, od.joint_positions)
+    if om.floating_base:
+        assert _rel(M, z["mass_matrix_body"]) <= 1e-9
+    else:
+        assert _rel(M[:, 6:, 6:], z["mass_matrix_body"][:, 6:, 6:]) <= 1e-9  # joint block of a fixed-base model
+    if "ode_joint_velocities" in z.files:
+        xd = O.system_dynamics(om, od, np.zeros((B, nL, 6)), z["in_tau"])  # joint torques as given (api/ode.py:174-225)
+        for k in ("base_position", "base_quaternion", "joint_positions", "base_linear_velocity", "base_angular_velocity",
+                  "joint_velocities", "tangential_deformation"):
+            assert _rel(xd[k], z["ode_" + k], 1e-9) <= 1e-9, k
