@@ -61,6 +61,7 @@ def parse():
     ap.add_argument("--no-input-caches", action="store_true", help="recompute the kinematics of the input state instead of reading its cached link transforms/velocities")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
     ap.add_argument("--no-tma", action="store_true", help="128-bit stores instead of TMA bulk stores for the joint adjoints")
+    ap.add_argument("--generic-kernel", action="store_true", help="diagnostic: launch the generic step-kernel instance instead of the specialised one")
     ap.add_argument("--profile", action="store_true", help="cudaProfilerStart/Stop around the eager timed region (ncu --profile-from-start off)")
     ap.add_argument("--jvp", action="store_true", help="also time BASELINE config 5: forward-mode d(step)/d(joint q, link masses), fp64")
     ap.add_argument("--config3", action="store_true", help="also time BASELINE config 3: ErgoCub-like ~50-DoF, RIGID contacts, batch 16384 fp32")
@@ -215,8 +216,8 @@ def run_b200(args):
     model = js.model.JaxSimModel.build_from_model_description(models.urdf(args.model), time_step=1e-3)
     if args.lanes:
         model.set_tuning(lanes_per_env=args.lanes)
-    if args.no_tma:
-        model.set_options(tma_store=False)
+    if args.no_tma or args.generic_kernel:
+        model.set_options(tma_store=not args.no_tma, generic_kernel=args.generic_kernel)
     n, nL, nc = model.dofs(), model.number_of_links(), model.number_of_collidable_points()
     B = args.batch
     bytes_env = algorithmic_bytes_per_env(n, nL, nc, w, caches=not args.no_caches)

@@ -116,6 +116,10 @@ int b200sim_model_set_tuning(B200SimModel *model, int lanes_per_env, int envs_pe
  *   workspace per environment is smaller and the step faster. */
 #define B200SIM_OPT_TMA_STORE 1
 #define B200SIM_OPT_RIGID_QP_F32 2
+/*   B200SIM_OPT_GENERIC_KERNEL: always launch the generic step-kernel instance, also where
+ *   the instance specialised for floating-base soft-contact steps applies (same results;
+ *   diagnostic / A-B timing switch). */
+#define B200SIM_OPT_GENERIC_KERNEL 4
 int b200sim_model_set_options(B200SimModel *model, int32_t options);
 
 /* Query sizes / launch geometry chosen for a batch (for benchmarks and tests). */

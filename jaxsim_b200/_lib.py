@@ -63,6 +63,7 @@ class B200SimModelDesc(C.Structure):
 ABI_VERSION = 2
 OPT_TMA_STORE = 1
 OPT_RIGID_QP_F32 = 2
+OPT_GENERIC_KERNEL = 4
 EXPORTED_SYMBOLS = (
     "b200sim_version",
     "b200sim_model_create",

@@ -196,12 +196,23 @@ void fill_model_params(const B200SimModel* m, Params<T>& P) {
   P.tau_max = (T)m->tau_max; P.w_th = (T)m->w_th; P.w_max = (T)m->w_max;
 }
 
-template <typename T, int G>
+template <typename T, int G, int SPEC = 0>
 int launch_g(const Params<T>& P, const Geometry& g, cudaStream_t st) {
-  auto kern = step_kernel<T, G>;
+  auto kern = step_kernel<T, G, SPEC>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
   kern<<<g.grid, g.epb * G, g.smem, st>>>(P);
   return (int)cudaGetLastError();
+}
+
+// The specialised instance (step_kernel<T, G, 1>) covers MODE_STEP of a floating-base model
+// whose FK poses coincide with the ABA chain and whose successor transforms are identities,
+// with soft contacts or no collidable points -- every BASELINE soft-contact configuration.
+template <typename T>
+bool specialised_step_applies(const B200SimModel* m, const Params<T>& P) {
+  if (m->opt_flags & B200SIM_OPT_GENERIC_KERNEL) return false;
+  if (P.mode != MODE_STEP || !P.floating) return false;
+  if (P.flags & (F_SUC_NONID | F_GENERIC_FK)) return false;
+  return P.nc == 0 || P.contact_model == 1;
 }
 
 template <typename T>
@@ -214,12 +225,13 @@ int launch(const B200SimModel* m, Params<T>& P, int dtype, void* stream) {
   CK(cudaGetDevice(&dev));
   if (dev != m->device) CK(cudaSetDevice(m->device));
   cudaStream_t st = (cudaStream_t)stream;
+  const bool spec = specialised_step_applies(m, P);
   switch (g.G) {
     case 1: rc = launch_g<T, 1>(P, g, st); break;
     case 2: rc = launch_g<T, 2>(P, g, st); break;
     case 4: rc = launch_g<T, 4>(P, g, st); break;
-    case 8: rc = launch_g<T, 8>(P, g, st); break;
-    case 16: rc = launch_g<T, 16>(P, g, st); break;
+    case 8: rc = spec ? launch_g<T, 8, 1>(P, g, st) : launch_g<T, 8>(P, g, st); break;
+    case 16: rc = spec ? launch_g<T, 16, 1>(P, g, st) : launch_g<T, 16>(P, g, st); break;
     case 32: rc = launch_g<T, 32>(P, g, st); break;
     default: rc = B200SIM_E_INVALID;
   }
@@ -719,14 +731,15 @@ int b200sim_model_set_tuning(B200SimModel* m, int lanes_per_env, int envs_per_bl
 // Undeclared diagnostic (not part of the ABI): enables, reads and resets the rigid-contact counters
 // [0] QP iterations, [1] QPs, [2] max iterations, [3] active points (QP), [4] full items,
 // [5] impact-only items, [6] impacts, [7] active points (impact).
+constexpr int DBG_WORDS = 8 + 32;  // 8 counters + the phase clocks of step_kernel (B200SIM_PHASE_MARK)
 extern "C" int b200sim_debug_counters(B200SimModel* m, unsigned long long* out8) {
   if (!m) return B200SIM_E_INVALID;
   int prev = 0;
   CK(cudaGetDevice(&prev));
   CK(cudaSetDevice(m->device));
   if (!m->dbg_d) {
-    CK(cudaMalloc((void**)&m->dbg_d, 8 * sizeof(unsigned long long)));
-    CK(cudaMemset(m->dbg_d, 0, 8 * sizeof(unsigned long long)));
+    CK(cudaMalloc((void**)&m->dbg_d, DBG_WORDS * sizeof(unsigned long long)));
+    CK(cudaMemset(m->dbg_d, 0, DBG_WORDS * sizeof(unsigned long long)));
   }
   CK(cudaDeviceSynchronize());
   if (out8) CK(cudaMemcpy(out8, m->dbg_d, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
@@ -735,8 +748,21 @@ extern "C" int b200sim_debug_counters(B200SimModel* m, unsigned long long* out8)
   return 0;
 }
 
+// Undeclared diagnostic: the phase clocks (clock64 of one warp, see B200SIM_PHASE_MARK) of the last
+// step_kernel launch; requires b200sim_debug_counters to have been called once (enables the buffer).
+extern "C" int b200sim_debug_phase_clocks(B200SimModel* m, unsigned long long* out32) {
+  if (!m || !m->dbg_d || !out32) return B200SIM_E_INVALID;
+  int prev = 0;
+  CK(cudaGetDevice(&prev));
+  CK(cudaSetDevice(m->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out32, m->dbg_d + 8, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  cudaSetDevice(prev);
+  return 0;
+}
+
 int b200sim_model_set_options(B200SimModel* m, int32_t options) {
-  if (!m || (options & ~(B200SIM_OPT_TMA_STORE | B200SIM_OPT_RIGID_QP_F32))) return B200SIM_E_INVALID;
+  if (!m || (options & ~(B200SIM_OPT_TMA_STORE | B200SIM_OPT_RIGID_QP_F32 | B200SIM_OPT_GENERIC_KERNEL))) return B200SIM_E_INVALID;
   m->opt_flags = options;
   return 0;
 }

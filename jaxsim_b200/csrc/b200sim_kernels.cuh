@@ -368,7 +368,7 @@ __host__ __device__ inline size_t env_ws_words(int nL, int nc) {
 // math/joint_model.py:146-200, math/rotation.py:58-84) from the precomputed constant
 // matrices: R = M0 + cos(s) M1 + sin(s) M2, t = TPRE + s RA.
 template <typename T>
-__device__ __forceinline__ void joint_rel_transform(const Params<T>& P, const T* c, int jtype, int i, T s,
+__device__ __forceinline__ void joint_rel_transform(const Params<T>& P, const int flags, const T* c, int jtype, int i, T s,
                                                     T* Rrel, T* trel) {
   T sn = T(0), cs = T(1);
   if (jtype == 1) sincos_t(s, &sn, &cs);
@@ -376,7 +376,7 @@ __device__ __forceinline__ void joint_rel_transform(const Params<T>& P, const T*
   for (int k = 0; k < 9; ++k) Rrel[k] = c[C_M0 + k] + cs * c[C_M1 + k] + sn * c[C_M2 + k];
 #pragma unroll
   for (int k = 0; k < 3; ++k) trel[k] = c[C_TPRE + k] + s * c[C_RA + k];
-  if (P.flags & F_SUC_NONID) {
+  if (flags & F_SUC_NONID) {
     const T* su = P.csuc + (size_t)i * 12;
     T Rs[9], ts[3], tmp[9], t2[3];
     ldn<9>(su, Rs);
@@ -462,13 +462,13 @@ __device__ __forceinline__ void make_fk_map(const T* cst0, const BaseState<T>& b
 // FK view of link i: pose (R,p) as the reference's forward_kinematics_model sees it and the
 // link velocity in "mixed at the link origin" form (vlin = velocity of the origin, w).
 template <typename T>
-__device__ __forceinline__ void fk_view(const Params<T>& P, const BaseState<T>& b, const FkMap<T>& fm, const T* rec,
+__device__ __forceinline__ void fk_view(const int flags, const bool floating, const BaseState<T>& b, const FkMap<T>& fm, const T* rec,
                                         T* R, T* p, T* vlin, T* w) {
   T Ra[9], pa[3], va[6];
   ldn<9>(rec + O_R, Ra);
   ldn<3>(rec + O_P, pa);
   ldn<6>(rec + O_V, va);
-  if (!(P.flags & F_GENERIC_FK)) {
+  if (!(flags & F_GENERIC_FK)) {
     stn<9>(R, Ra);
     stn<3>(p, pa);
     vlin[0] = va[0]; vlin[1] = va[1]; vlin[2] = va[2];
@@ -482,7 +482,7 @@ __device__ __forceinline__ void fk_view(const Params<T>& P, const BaseState<T>& 
   T Wv[3], d[3], dw[3], t[3];
   cross3(pa, va + 3, Wv);
   Wv[0] += va[0]; Wv[1] += va[1]; Wv[2] += va[2];
-  const T f = P.floating ? T(1) : T(0);  // chain root velocity: W_v_WB if floating else 0
+  const T f = floating ? T(1) : T(0);  // chain root velocity: W_v_WB if floating else 0
   d[0] = Wv[0] - f * b.vlin[0]; d[1] = Wv[1] - f * b.vlin[1]; d[2] = Wv[2] - f * b.vlin[2];
   dw[0] = va[3] - f * b.w[0]; dw[1] = va[4] - f * b.w[1]; dw[2] = va[5] - f * b.w[2];
   // X_T [d; dw] = [R_T d + p_T x (R_T dw); R_T dw]
@@ -509,10 +509,23 @@ __device__ __forceinline__ void over_push(const Params<T>& P, int env, int impac
   P.over_list[slot] = env | (impact_only << 31);
 }
 
+// Phase timeline of one warp (diagnostic, b200sim_debug_counters): when the debug buffer is
+// enabled, lane 0 of warp 0 of block 0 stores clock64() at the phase boundaries of its first
+// environment into dbg[8 + k].  A uniform, predicted-not-taken branch otherwise.
+#define B200SIM_PHASE_MARK(k)                                                                   \
+  do {                                                                                           \
+    if (P.dbg && blockIdx.x == 0 && threadIdx.x == 0 && env0 == first) P.dbg[8 + (k)] = (unsigned long long)clock64(); \
+  } while (0)
+
 // ------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------
-template <typename T, int G>
+// SPEC = 1 is the instance for the common case -- MODE_STEP of a floating-base URDF model
+// (identity successor transforms, FK poses == ABA chain poses) with soft contacts or no
+// collidable points: the mode / flag / base-type tests fold at compile time, which removes
+// the other modes' code from the instruction stream (the generic instance is ~6.7k SASS
+// instructions walked once per step: instruction fetch is a measurable share of its time).
+template <typename T, int G, int SPEC = 0>
 __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(const Params<T> P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sm_cst = reinterpret_cast<T*>(smem_raw);
@@ -525,12 +538,14 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
 
   // ---- stage the model once per block: 16-byte cp.async chunks, all in flight at once
   // (the device blobs are padded to whole chunks by b200sim_model_create)
+  if (P.dbg && blockIdx.x == 0 && threadIdx.x == 0) P.dbg[8 + 0] = (unsigned long long)clock64();
   stage_async(sm_cst, P.cst, nL * CREC);
   stage_async(sm_pt, P.pt_pos, (int)pt_words);
   stage_async(sm_itab, P.itab, (int)itab_words);
   __pipeline_commit();
   __pipeline_wait_prior(0);
   __syncthreads();
+  if (P.dbg && blockIdx.x == 0 && threadIdx.x == 0) P.dbg[8 + 1] = (unsigned long long)clock64();
 
   const int* parent = sm_itab + P.o_parent;
   const int* jtypes = sm_itab + P.o_jtype;
@@ -550,10 +565,13 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
   T* ptws = ws + (size_t)nL * REC;
   const long long stride = (long long)gridDim.x * P.envs_per_block;
   const T dt = P.dt;
-  const bool with_contacts = (P.mode == MODE_STEP) || (P.mode == MODE_DYN);
-  const bool soft = with_contacts && (P.contact_model == 1) && nc > 0;
-  const bool rigid = (P.mode == MODE_STEP) && (P.contact_model == 2) && nc > 0;
-  const bool tma = (P.flags & F_TMA_STORE) != 0;
+  const int mode = SPEC ? (int)MODE_STEP : P.mode;
+  const int flags = SPEC ? (P.flags & (F_SQRT_P | F_SQRT_Q | F_TMA_STORE)) : P.flags;
+  const bool floating = SPEC ? true : (P.floating != 0);
+  const bool with_contacts = (mode == MODE_STEP) || (mode == MODE_DYN);
+  const bool soft = SPEC ? (nc > 0) : (with_contacts && (P.contact_model == 1) && nc > 0);
+  const bool rigid = SPEC ? false : ((mode == MODE_STEP) && (P.contact_model == 2) && nc > 0);
+  const bool tma = (flags & F_TMA_STORE) != 0;
 
   // the number of loop trips is uniform across the block so that __syncwarp() is safe
   const long long first = (long long)blockIdx.x * P.envs_per_block;
@@ -566,7 +584,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
     // joint state, first-step torque reference and contact state go global -> shared with
     // cp.async; the 13 base scalars go to registers.  Nothing is consumed before the wait.
     if (tma) tma_store_wait_read();  // the previous environment's staging areas are reused below
-    const bool use_cached = (P.mode == MODE_STEP) && P.Hin && P.Vin && !(P.flags & F_GENERIC_FK);
+    const bool use_cached = (mode == MODE_STEP) && P.Hin && P.Vin && !(flags & F_GENERIC_FK);
     if (use_cached) {
       // cached kinematics of the input state: rows [R | p] of W_H_L and the 6D velocity land in
       // the (still unused) IA / c slots of the record, 16 bytes per cp.async
@@ -605,6 +623,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
       }
     }
     __pipeline_commit();
+    B200SIM_PHASE_MARK(2);
 
     // =========================================================== phase 0: base
     BaseState<T> b;
@@ -616,7 +635,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
       ldn<3>(P.omega + env * 3, b.w);
       const T nrm = sqrt_t(qr[0] * qr[0] + qr[1] * qr[1] + qr[2] * qr[2] + qr[3] * qr[3]);
       T den;
-      if (P.mode == MODE_FK) den = (nrm == T(0)) ? T(1) : nrm;            // data.replace (api/data.py:441-447)
+      if (mode == MODE_FK) den = (nrm == T(0)) ? T(1) : nrm;            // data.replace (api/data.py:441-447)
       else den = nrm + Lim<T>::eps() * (nrm == T(0) ? T(1) : T(0));       // base_orientation (api/data.py:283-285)
       const T inv = T(1) / den;
 #pragma unroll
@@ -624,7 +643,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
       quat_to_dcm(b.qn, b.R);
     }
     FkMap<T> fm;
-    if (P.flags & F_GENERIC_FK) make_fk_map(sm_cst, b, fm);
+    if (flags & F_GENERIC_FK) make_fk_map(sm_cst, b, fm);
 
     auto write_base_record = [&](const BaseState<T>& bs) {
       if (lane == 0) {
@@ -632,7 +651,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
         stn<9>(r0 + O_R, bs.R);
         stn<3>(r0 + O_P, bs.p);
         T v0[6];
-        if (P.floating) {
+        if (floating) {
           T t[3];
           cross3(bs.w, bs.p, t);  // velocity of the base origin: v_lin + w x p
           v0[0] = bs.vlin[0] + t[0]; v0[1] = bs.vlin[1] + t[1]; v0[2] = bs.vlin[2] + t[2];
@@ -693,7 +712,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
     auto write_fk_caches = [&](const BaseState<T>& bs, const FkMap<T>& f) {
       for (int i = lane; i < nL; i += G) {
         T R[9], p[3], vl[3], w[3];
-        fk_view(P, bs, f, ws + (size_t)i * REC, R, p, vl, w);
+        fk_view(flags, floating, bs, f, ws + (size_t)i * REC, R, p, vl, w);
         if (P.W_H_L) store_transform(P.W_H_L + (env * nL + i) * 16, R, p);
         if (P.W_v) {
           T t[3];
@@ -718,7 +737,9 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
       }
     };
 
+    B200SIM_PHASE_MARK(3);
     __pipeline_wait_prior(0);
+    B200SIM_PHASE_MARK(4);
     if (!use_cached) write_base_record(b);
 
     if (use_cached) {
@@ -760,16 +781,16 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
       for (int i = 1 + lane; i < nL; i += G) {
         T* ri = ws + (size_t)i * REC;
         T Rrel[9], trel[3];
-        joint_rel_transform(P, sm_cst + (size_t)i * CREC, jtypes[i], i, ri[O_S], Rrel, trel);
+        joint_rel_transform(P, flags, sm_cst + (size_t)i * CREC, jtypes[i], i, ri[O_S], Rrel, trel);
         stn<9>(ri + O_R, Rrel);
         stn<3>(ri + O_P, trel);
-        if (P.mode == MODE_FK && P.iXl && active) emit_joint_adjoint(ri, i, Rrel, trel);
+        if (mode == MODE_FK && P.iXl && active) emit_joint_adjoint(ri, i, Rrel, trel);
       }
       // ========================================================= phase 2: FK chain
-      fk_chain(P.mode != MODE_FK);
+      fk_chain(mode != MODE_FK);
     }
 
-    if (P.mode == MODE_FK) {
+    if (mode == MODE_FK) {
       // JaxSimModelData.build / replace: caches of the given state
       if (active) {
         if (lane == 0) {
@@ -791,6 +812,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
       continue;
     }
 
+    B200SIM_PHASE_MARK(5);
     T Wa[6];
     for (int step = 0; step < P.nsteps; ++step) {
       const bool last = (step == P.nsteps - 1);
@@ -821,7 +843,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
           const int bi = pt_body[k];
           const T* rb = ws + (size_t)bi * REC;
           T R[9], p[3], vl[3], w[3];
-          fk_view(P, b, fm, rb, R, p, vl, w);
+          fk_view(flags, floating, b, fm, rb, R, p, vl, w);
           T Lp[3], d[3], pc[3], pd[3];
           ldn<3>(sm_pt + 3 * k, Lp);
           mat3_vec(R, Lp, d);
@@ -838,8 +860,8 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
             const T delta = max_t(T(0), P.h_terrain - pc[2]);
             const T ddot = (delta > T(0)) ? -pd[2] : T(0);
             const T eps = Lim<T>::eps();
-            const T dp = (P.flags & F_SQRT_P) ? sqrt_t(delta + eps) : pow_t(delta + eps, P.pexp);
-            const T dq = (P.flags & F_SQRT_Q) ? sqrt_t(delta + eps) : pow_t(delta + eps, P.qexp);
+            const T dp = (flags & F_SQRT_P) ? sqrt_t(delta + eps) : pow_t(delta + eps, P.pexp);
+            const T dq = (flags & F_SQRT_Q) ? sqrt_t(delta + eps) : pow_t(delta + eps, P.qexp);
             const T Kdp = P.K * dp, Ddq = P.D * dq;
             const T fn = max_t(T(0), Kdp * delta + Ddq * ddot);
             // tangential quantities (n = z): v_t = (vx,vy,0), m_t = (mx,my,0), m_n = (0,0,mz)
@@ -868,14 +890,14 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
           }
           // lever arm w.r.t. the origin of the ABA-chain frame of the body
           T lev[3];
-          if (P.flags & F_GENERIC_FK) {
+          if (flags & F_GENERIC_FK) {
             lev[0] = pc[0] - rb[O_P]; lev[1] = pc[1] - rb[O_P + 1]; lev[2] = pc[2] - rb[O_P + 2];
           } else {
             lev[0] = d[0]; lev[1] = d[1]; lev[2] = d[2];
           }
           stn<3>(pw + PT_F, f);
           stn<3>(pw + PT_LEV, lev);
-          if (P.mode == MODE_DYN) {
+          if (mode == MODE_DYN) {
             // system_dynamics: the contact-state derivative itself (api/ode.py:174-225)
             if (active && P.m_o) {
               T* mo = P.m_o + (env * nc + k) * 3;
@@ -891,12 +913,13 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
             }
           }
         }
-      } else if (P.mode == MODE_STEP && last && P.m_o && P.m && active) {
+      } else if (mode == MODE_STEP && last && P.m_o && P.m && active) {
         for (int k = lane; k < nc * 3; k += G) P.m_o[env * nc * 3 + k] = P.m[env * nc * 3 + k];
-      } else if (P.mode == MODE_DYN && P.m_o && active) {
+      } else if (mode == MODE_DYN && P.m_o && active) {
         for (int k = lane; k < nc * 3; k += G) P.m_o[env * nc * 3 + k] = T(0);
       }
       __syncwarp();
+      B200SIM_PHASE_MARK(6);
 
       // ========================================================= phase 3: link-parallel
       for (int i = lane; i < nL; i += G) {
@@ -960,7 +983,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
         cross3_add(v + 3, nI, pA + 3);
         pA[0] -= fe[0]; pA[1] -= fe[1]; pA[2] -= fe[2];
         pA[3] -= ne[0]; pA[4] -= ne[1]; pA[5] -= ne[2];
-        if (i == 0 && !P.floating) {
+        if (i == 0 && !floating) {
 #pragma unroll
           for (int k = 0; k < 6; ++k) pA[k] = T(0);
         }
@@ -982,7 +1005,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
           stn<6>(ri + O_C, cc);
           const T tref = ri[O_TREF];
           T tau;
-          if (P.mode != MODE_STEP) {
+          if (mode != MODE_STEP) {
             tau = tref;
           } else {
             // api/actuation_model.py:7-126
@@ -1017,7 +1040,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
         IA[12] = mass * cw[1];   IA[13] = -mass * cw[0]; IA[14] = T(0);
 #pragma unroll
         for (int k = 0; k < 6; ++k) IA[15 + k] = Dw[k];
-        if (i == 0 && !P.floating) {
+        if (i == 0 && !floating) {
 #pragma unroll
           for (int k = 0; k < 21; ++k) IA[k] = T(0);
         }
@@ -1025,6 +1048,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
         stn<6>(ri + O_PA, pA);
       }
       __pipeline_commit();
+      B200SIM_PHASE_MARK(7);
 
       // ========================================================= phase 4: ABA pass 2
       for (int l = P.depth; l >= 1; --l) {
@@ -1076,7 +1100,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
           ri[O_DINV] = dinv;
           ri[O_UU] = u;
           const int par = parent[i];
-          if (par != 0 || P.floating) {
+          if (par != 0 || floating) {
             // Ma = IA - U U^T / d
             const T Uls[3] = {Ul[0] * dinv, Ul[1] * dinv, Ul[2] * dinv};
             const T Uas[3] = {Ua[0] * dinv, Ua[1] * dinv, Ua[2] * dinv};
@@ -1138,11 +1162,12 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
         }
       }
       __syncwarp();
+      B200SIM_PHASE_MARK(8);
 
       // ========================================================= phase 5: base acceleration
       if (lane == 0) {
         T a0[6];
-        if (P.floating) {
+        if (floating) {
           T* r0 = ws;
           T A[6], Bm[9], D[6], pA[6];
           ldn<6>(r0 + O_IA, A);
@@ -1177,6 +1202,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
         stn<6>(ws + O_V, a0);
       }
 
+      B200SIM_PHASE_MARK(9);
       // ========================================================= phase 6: ABA pass 3
       for (int l = 1; l <= P.depth; ++l) {
         __syncwarp();
@@ -1205,8 +1231,9 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
       }
       __syncwarp();
 
+      B200SIM_PHASE_MARK(10);
       // base acceleration in inertial-fixed representation + gravity (rbda/aba.py:284-288)
-      if (P.floating) {
+      if (floating) {
         T a0[6];
         ldn<6>(ws + O_V, a0);
         cross3(b.p, a0 + 3, Wa);
@@ -1216,7 +1243,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
 #pragma unroll
         for (int k = 0; k < 6; ++k) Wa[k] = T(0);
       }
-      if (P.mode != MODE_STEP) break;
+      if (mode != MODE_STEP) break;
 
       // ========================================================= phase 7: semi-implicit Euler
       // (api/integrators.py:14-88), base part replicated in every lane
@@ -1256,6 +1283,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
         quat_to_dcm(nb.qn, nb.R);
         b = nb;
       }
+      B200SIM_PHASE_MARK(11);
       const bool want_caches = last && (P.W_H_L || P.W_v);
       if (last && active && lane == 0) {
         stn<4>(P.q_o + env * 4, b.qn);
@@ -1274,6 +1302,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
       }
       // joints: new velocity/position (+ joint transforms of the new state when kinematics
       // are needed again: next step, or cache outputs)
+      B200SIM_PHASE_MARK(12);
       const bool need_fk = !last || want_caches || (P.iXl != nullptr);
       __pipeline_wait_prior(0);  // next step's torque references have landed
       for (int i = 1 + lane; i < nL; i += G) {
@@ -1288,12 +1317,13 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
         }
         if (need_fk) {
           T Rrel[9], trel[3];
-          joint_rel_transform(P, sm_cst + (size_t)i * CREC, jtypes[i], i, sn, Rrel, trel);
+          joint_rel_transform(P, flags, sm_cst + (size_t)i * CREC, jtypes[i], i, sn, Rrel, trel);
           stn<9>(ri + O_R, Rrel);
           stn<3>(ri + O_P, trel);
           if (last && active && P.iXl) emit_joint_adjoint(ri, i, Rrel, trel);
         }
       }
+      B200SIM_PHASE_MARK(13);
       // ========================================================= phase 8: FK of the new state
       if (!last) {
         // the next fused step starts like a fresh call: base_orientation normalises the
@@ -1304,12 +1334,14 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
         for (int k = 0; k < 4; ++k) b.qn[k] *= inv;
         quat_to_dcm(b.qn, b.R);
       }
-      if (P.flags & F_GENERIC_FK) make_fk_map(sm_cst, b, fm);
+      if (flags & F_GENERIC_FK) make_fk_map(sm_cst, b, fm);
       __syncwarp();  // every lane has read the base acceleration out of record 0
       if (!last || want_caches || rigid) {
         write_base_record(b);
         fk_chain(!last);
+        B200SIM_PHASE_MARK(14);
         if (last && active && want_caches) write_fk_caches(b, fm);
+        B200SIM_PHASE_MARK(15);
       }
       if (rigid) {
         // a point below the ground at t+dt: the impact (rigid.py:385-436) is left to the rigid
@@ -1328,10 +1360,10 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
       __syncwarp();
     }  // steps
 
-    if (P.mode != MODE_STEP) {
+    if (mode != MODE_STEP) {
       if (active) {
         if (lane == 0) stn<6>(P.avd + env * 6, Wa);
-        if (lane == 0 && P.mode == MODE_DYN) {
+        if (lane == 0 && mode == MODE_DYN) {
           // system_position_dynamics (api/ode.py:134-171): Baumgarte K = 1.0
           T pd[3];
           cross3(b.w, b.p, pd);
@@ -1352,6 +1384,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
     }
   }
   if (tma) tma_store_wait_all();
+  if (P.dbg && blockIdx.x == 0 && threadIdx.x == 0) P.dbg[8 + 16] = (unsigned long long)clock64();
 }
 
 }  // namespace b200sim

@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) rnea_kernel(cons
     for (int i = 1 + lane; i < nL; i += G) {
       T* ri = ws + (size_t)i * REC;
       T Rrel[9], trel[3];
-      joint_rel_transform(P, c.cst + (size_t)i * CREC, c.jtypes[i], i, ri[O_S], Rrel, trel);
+      joint_rel_transform(P, P.flags, c.cst + (size_t)i * CREC, c.jtypes[i], i, ri[O_S], Rrel, trel);
       stn<9>(ri + O_R, Rrel);
       stn<3>(ri + O_P, trel);
     }
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) crba_kernel(cons
     for (int i = 1 + lane; i < nL; i += G) {
       T* ri = ws + (size_t)i * REC;
       T Rrel[9], trel[3];
-      joint_rel_transform(P, c.cst + (size_t)i * CREC, c.jtypes[i], i, ri[O_S], Rrel, trel);
+      joint_rel_transform(P, P.flags, c.cst + (size_t)i * CREC, c.jtypes[i], i, ri[O_S], Rrel, trel);
       stn<9>(ri + O_R, Rrel);
       stn<3>(ri + O_P, trel);
     }

@@ -553,7 +553,7 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
       for (int i = 1 + lane; i < nL; i += 32) {
         T* ri = ws + (size_t)i * REC;
         T Rrel[9], trel[3];
-        joint_rel_transform(P, sm_cst + (size_t)i * CREC, jtypes[i], i, ri[O_S], Rrel, trel);
+        joint_rel_transform(P, P.flags, sm_cst + (size_t)i * CREC, jtypes[i], i, ri[O_S], Rrel, trel);
         stn<9>(ri + O_R, Rrel);
         stn<3>(ri + O_P, trel);
         if (emit_adjoints && P.iXl) {

@@ -21,15 +21,19 @@ agreement between the two is evidence, not tautology.  The only liberties taken:
 * ``dtype`` selects float64 (reference default, ``__init__.py:19,35``) or float32
   (``JAX_ENABLE_X64=0``), incl. ``finfo(dtype).eps`` where the reference uses ``finfo(float)``.
 
-PARITY PIN STATUS: JAX is not installable offline and the reference's tests store no
-golden vectors, so this oracle cannot be diffed against the reference's
-own output.  It is pinned instead by the reference's *known-answer and invariant* tests,
-re-run against this restatement in ``tests/test_oracle_pins.py``: ABA == CRB forward
-dynamics and RNEA(ABA(tau)) == tau (``tests/test_api_model.py:495-577``), balanced box
-(``tests/test_simulations.py:15-85``), ballistic box (``:88-167``), soft-contact rest height
-(``:194-242``), joint limits (``:347-401``), torque-speed curve (``tests/test_actuation.py:11-48``),
-plus analytic pendulum/free-fall answers.  Where those pins do not reach (per-step values
-of the contact state), DESIGN.md says "parity unpinned".
+PARITY PIN STATUS: pinned by the reference's own code.  JAX is not installable offline, but
+the UNMODIFIED reference sources are executed over NumPy stand-ins of their third-party
+imports (``oracle/refshim``, ``tests/golden/make_goldens.py``); the committed fixtures
+``tests/golden/*.npz`` hold the reference's outputs and ``tests/test_reference_goldens.py``
+checks every leaf of this oracle's ``step`` / ``step_rk4`` / ``aba`` / ``rnea`` / ``crba`` /
+``system_dynamics`` against them at 1e-9 relative (float64).  In addition the reference's
+*known-answer and invariant* tests are re-run against this restatement in
+``tests/test_oracle_pins.py``: ABA == CRB forward dynamics and RNEA(ABA(tau)) == tau
+(``tests/test_api_model.py:495-577``), balanced box (``tests/test_simulations.py:15-85``),
+ballistic box (``:88-167``), soft-contact rest height (``:194-242``), joint limits
+(``:347-401``), torque-speed curve (``tests/test_actuation.py:11-48``), plus analytic
+pendulum/free-fall answers.  Not covered by the pin: XLA's float32 rounding / fusion (the
+fixtures are float64, evaluated eagerly).
 """
 
 from __future__ import annotations

@@ -30,12 +30,16 @@ restatement of the published algorithm run to tight tolerance; ``tests/test_orac
 pins it by checking the KKT conditions of its answers (a KKT point of a strictly convex QP is
 the optimum) and against ``scipy.optimize`` on small problems.
 
-PARITY PIN STATUS: per-step rigid-contact forces are "parity unpinned" against the reference's
-own numbers (no golden vectors, JAX/qpax not installable).  The path is pinned by the
-reference's known-answer test for it: a box dropped on the ground comes to rest at height h/2
-with ~zero penetration (``tests/test_simulations.py:245-292``), re-run against this restatement,
-plus the invariants J M^-1 J' == Delassus from ABA impulse responses, M^-1 M == I, and
-J(post-impact nu) == 0 on the active points.
+PARITY PIN STATUS: pinned by the reference's own code up to the QP boundary, and on the QP
+optimum beyond it.  The unmodified reference sources (``rbda/contacts/rigid.py``,
+``api/contact.py``, ``rbda/mass_inverse.py``, ``rbda/jacobian.py`` ...) are executed over NumPy
+stand-ins (``oracle/refshim``; its ``qpax.solve_qp`` is a separate interior-point code run to
+tight tolerance) by ``tests/golden/make_goldens.py``; ``tests/test_reference_goldens.py`` checks
+every leaf of this oracle's ``step`` against those fixtures at 1e-6 relative.  The path is
+also pinned by the reference's known-answer test for it: a box dropped on the ground comes to
+rest at height h/2 with ~zero penetration (``tests/test_simulations.py:245-292``), re-run
+against this restatement, plus the invariants J M^-1 J' == Delassus from ABA impulse
+responses, M^-1 M == I, and J(post-impact nu) == 0 on the active points.
 
 Quirks reproduced on purpose:
 * ``update_velocity_after_impact`` replaces the state velocities with ``dataclasses.replace``
