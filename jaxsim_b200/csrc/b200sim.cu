@@ -104,10 +104,10 @@ size_t static_smem_bytes(const B200SimModel* m, size_t ts) {
   return w;
 }
 
-size_t env_smem_bytes(const B200SimModel* m, size_t ts) {
+size_t env_smem_bytes(const B200SimModel* m, size_t ts) {  // == env_ws_words<T>() * sizeof(T)
   size_t w = (size_t)m->nL * REC + (size_t)m->nc * PTREC;
   w = (w + 3) & ~size_t(3);
-  return w * ts;
+  return w * ts + 16;
 }
 
 struct Geometry {
@@ -418,6 +418,9 @@ int step_t(const B200SimModel* m, int dtype, int64_t B, const void* s, const voi
   P.W_H_B = (T*)W_H_B; P.iXl = (T*)iXl; P.W_H_L = (T*)W_H_L; P.W_v = (T*)W_v;
   P.nsteps = nsteps; P.tau_step_stride = tau_stride; P.fext_step_stride = fext_stride;
   P.Hin = (const T*)Hin; P.Vin = (const T*)Vin;
+  // cp.async.bulk needs 16-byte aligned, 16-byte granular blocks per environment
+  if (Hin && Vin && ((uintptr_t)Hin % 16 == 0) && ((uintptr_t)Vin % 16 == 0) && (((size_t)m->nL * 6 * sizeof(T)) % 16 == 0))
+    P.flags |= F_BULK_IN;
   P.mode = MODE_STEP;
   if (m->contact_model == B200SIM_CONTACT_RIGID && m->nc > 0) {
     if (nsteps != 1) return B200SIM_E_UNSUPPORTED;

@@ -64,6 +64,16 @@ constexpr int O_S = 55;     // 1  joint position
 constexpr int O_TAU = 56;   // 1  resultant joint torque
 constexpr int O_SDD = 57;   // 1  joint acceleration
 constexpr int O_TREF = 58;  // 1  joint force reference of the current step
+// Compact layout of the FINAL phase of the last step (joint transforms + FK of the new state +
+// cache outputs), used by the specialised instance when nL <= 4*G + 1.  The ABA scratch is dead
+// by then, so the environment's workspace is re-interpreted as
+//   [ nL x FS words: R(9) p(3) v(6) sd(1) pad ]  [ nL x 36 words: the (nL,6,6) joint adjoints ]
+// The second block is contiguous exactly like the environment's slice of the (B,nL,6,6) output,
+// so it leaves with ONE cp.async.bulk per environment instead of one per link (UBLKCP takes
+// uniform-register operands: per-lane bulk copies are serialised lane by lane).  FS = 20 and 36
+// keep 128-bit accesses of consecutive links on distinct banks.
+constexpr int FS = 20;
+constexpr int F_R = 0, F_P = 9, F_V = 12, F_SD = 18;
 // per collidable point: contact force (3), lever arm (3), tangential deformation (3)
 constexpr int PTREC = 9;
 constexpr int PT_F = 0, PT_LEV = 3, PT_M = 6;
@@ -95,6 +105,8 @@ enum Flags : int {
   F_SQRT_P = 4,      // soft_p == 0.5
   F_SQRT_Q = 8,      // soft_q == 0.5
   F_TMA_STORE = 16,  // joint adjoints leave through cp.async.bulk (TMA) instead of STG.128
+  F_BULK_IN = 32,    // the cached input kinematics may come in with cp.async.bulk (set per launch by the host
+                     // when the (B,nL,4,4) / (B,nL,6) rows of every environment are 16-byte aligned and sized)
 };
 
 template <typename T>
@@ -308,6 +320,35 @@ __device__ __forceinline__ void tma_store_bulk(void* gdst, const void* smem_src,
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// ---- TMA bulk loads global -> shared, completion on an mbarrier (cp.async.bulk + complete_tx)
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "B200SIM_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra B200SIM_MBAR_DONE;\n"
+      "bra B200SIM_MBAR_WAIT;\n"
+      "B200SIM_MBAR_DONE:\n"
+      "}\n" ::"r"(a), "r"(parity) : "memory");
+}
+// bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void tma_load_bulk(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(gsrc),
+               "r"(bytes), "r"(a) : "memory");
+}
+
 // jaxlie SO3(wxyz).as_matrix() (reference call sites rbda/aba.py:79-86)
 template <typename T>
 __device__ __forceinline__ void quat_to_dcm(const T* q, T* R) {
@@ -358,10 +399,17 @@ __device__ __forceinline__ void solve6_spd_neg(T M[6][6], const T* b, T* x) {
   }
 }
 
+// words of T per environment: link records, point records, then 16 bytes that hold the
+// mbarrier of the environment's bulk loads (env_mbar)
 template <typename T>
 __host__ __device__ inline size_t env_ws_words(int nL, int nc) {
   size_t w = (size_t)nL * REC + (size_t)nc * PTREC;
-  return (w + 3) & ~size_t(3);  // keep 16-byte alignment of the next workspace
+  w = (w + 3) & ~size_t(3);  // keep 16-byte alignment
+  return w + 16 / sizeof(T);
+}
+template <typename T>
+__device__ __forceinline__ unsigned long long* env_mbar(T* ws, int nL, int nc) {
+  return reinterpret_cast<unsigned long long*>(ws + env_ws_words<T>(nL, nc) - 16 / sizeof(T));
 }
 
 // lam_H_i = lam_H_pre * J(s) * suc_H_i  (api/kin_dyn_parameters.py:396-451,
@@ -543,6 +591,11 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
   stage_async(sm_pt, P.pt_pos, (int)pt_words);
   stage_async(sm_itab, P.itab, (int)itab_words);
   __pipeline_commit();
+  if (SPEC && (threadIdx.x & (G - 1)) == 0) {
+    mbar_init(env_mbar(ws_base + (size_t)(threadIdx.x / G) * env_ws_words<T>(nL, nc), nL, nc), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   __pipeline_wait_prior(0);
   __syncthreads();
   if (P.dbg && blockIdx.x == 0 && threadIdx.x == 0) P.dbg[8 + 1] = (unsigned long long)clock64();
@@ -566,7 +619,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
   const long long stride = (long long)gridDim.x * P.envs_per_block;
   const T dt = P.dt;
   const int mode = SPEC ? (int)MODE_STEP : P.mode;
-  const int flags = SPEC ? (P.flags & (F_SQRT_P | F_SQRT_Q | F_TMA_STORE)) : P.flags;
+  const int flags = SPEC ? (P.flags & (F_SQRT_P | F_SQRT_Q | F_TMA_STORE | F_BULK_IN)) : P.flags;
   const bool floating = SPEC ? true : (P.floating != 0);
   const bool with_contacts = (mode == MODE_STEP) || (mode == MODE_DYN);
   const bool soft = SPEC ? (nc > 0) : (with_contacts && (P.contact_model == 1) && nc > 0);
@@ -575,6 +628,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
 
   // the number of loop trips is uniform across the block so that __syncwarp() is safe
   const long long first = (long long)blockIdx.x * P.envs_per_block;
+  unsigned in_parity = 0;  // phase of the environment's mbarrier (one bulk-load transaction per trip)
   for (long long env0 = first; env0 < P.B; env0 += stride) {
     long long env = env0 + grp;
     bool active = env < P.B;
@@ -583,33 +637,66 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
     // =========================================================== prefetch (one burst)
     // joint state, first-step torque reference and contact state go global -> shared with
     // cp.async; the 13 base scalars go to registers.  Nothing is consumed before the wait.
-    if (tma) tma_store_wait_read();  // the previous environment's staging areas are reused below
+    if (tma) {
+      // the previous environment's staging areas are reused below; in the compact final phase only
+      // lane 0 of the group owns the bulk store, so the others must not run ahead of its wait
+      tma_store_wait_read();
+      __syncwarp();
+    }
     const bool use_cached = (mode == MODE_STEP) && P.Hin && P.Vin && !(flags & F_GENERIC_FK);
-    if (use_cached) {
-      // cached kinematics of the input state: rows [R | p] of W_H_L and the 6D velocity land in
-      // the (still unused) IA / c slots of the record, 16 bytes per cp.async
-      constexpr int per = 16 / sizeof(T);        // elements per 16-byte chunk
-      for (int i = lane; i < nL; i += G) {
-        T* ri = ws + (size_t)i * REC;
-        const T* H = P.Hin + (env * nL + i) * 16;
-        const T* V = P.Vin + (env * nL + i) * 6;
+    // bulk_in: the environment's (nL,4,4) and (nL,6) blocks are contiguous in HBM, so they arrive
+    // with two cp.async.bulk (one lane, completion on the environment's mbarrier) into the head of
+    // the still empty workspace -- [nL x 16 | nL x 6] words -- instead of 6 LDGSTS per link; the joint
+    // state then goes to registers (its record slots overlap that staging area).
+    const bool bulk_in = SPEC && (sizeof(T) == 4) && use_cached && (flags & F_BULK_IN) && (nL <= 4 * G);  // (float: 84 staging registers)
+    T s_r[4], sd_r[4], tr_r[4];
+    if (bulk_in) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic accesses of the last trip before the async writes
+      __syncwarp();
+      if (lane == 0) {
+        unsigned long long* bar = env_mbar(ws, nL, nc);
+        const unsigned bH = (unsigned)(nL * 16 * sizeof(T)), bV = (unsigned)(nL * 6 * sizeof(T));
+        mbar_expect_tx(bar, bH + bV);
+        tma_load_bulk(ws, P.Hin + env * nL * 16, bH, bar);
+        tma_load_bulk(ws + (size_t)nL * 16, P.Vin + env * nL * 6, bV, bar);
+      }
 #pragma unroll
-        for (int k = 0; k < 12; k += per) __pipeline_memcpy_async(ri + O_X + k, H + k, 16);
-        if (sizeof(T) == 4) {
-#pragma unroll
-          for (int k = 0; k < 6; k += 2) __pipeline_memcpy_async(ri + O_C + k, V + k, 8);
-        } else {
-#pragma unroll
-          for (int k = 0; k < 6; k += per) __pipeline_memcpy_async(ri + O_C + k, V + k, 16);
+      for (int t = 0; t < 4; ++t) {
+        const int i = lane + t * G;
+        s_r[t] = T(0); sd_r[t] = T(0); tr_r[t] = T(0);
+        if (i >= 1 && i < nL) {
+          s_r[t] = P.s[env * n + (i - 1)];
+          sd_r[t] = P.sd[env * n + (i - 1)];
+          if (P.tau) tr_r[t] = P.tau[env * n + (i - 1)];
         }
       }
-    }
-    for (int i = 1 + lane; i < nL; i += G) {
-      T* ri = ws + (size_t)i * REC;
-      cp_async_elem(ri + O_S, P.s + env * n + (i - 1));
-      cp_async_elem(ri + O_SD, P.sd + env * n + (i - 1));
-      if (P.tau) cp_async_elem(ri + O_TREF, P.tau + env * n + (i - 1));
-      else ri[O_TREF] = T(0);
+    } else {
+      if (use_cached) {
+        // cached kinematics of the input state: rows [R | p] of W_H_L and the 6D velocity land in
+        // the (still unused) IA / c slots of the record, 16 bytes per cp.async
+        constexpr int per = 16 / sizeof(T);        // elements per 16-byte chunk
+        for (int i = lane; i < nL; i += G) {
+          T* ri = ws + (size_t)i * REC;
+          const T* H = P.Hin + (env * nL + i) * 16;
+          const T* V = P.Vin + (env * nL + i) * 6;
+#pragma unroll
+          for (int k = 0; k < 12; k += per) __pipeline_memcpy_async(ri + O_X + k, H + k, 16);
+          if (sizeof(T) == 4) {
+#pragma unroll
+            for (int k = 0; k < 6; k += 2) __pipeline_memcpy_async(ri + O_C + k, V + k, 8);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 6; k += per) __pipeline_memcpy_async(ri + O_C + k, V + k, 16);
+          }
+        }
+      }
+      for (int i = 1 + lane; i < nL; i += G) {
+        T* ri = ws + (size_t)i * REC;
+        cp_async_elem(ri + O_S, P.s + env * n + (i - 1));
+        cp_async_elem(ri + O_SD, P.sd + env * n + (i - 1));
+        if (P.tau) cp_async_elem(ri + O_TREF, P.tau + env * n + (i - 1));
+        else ri[O_TREF] = T(0);
+      }
     }
     if (with_contacts) {
       for (int k = lane; k < nc; k += G) {
@@ -742,7 +829,56 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
     B200SIM_PHASE_MARK(4);
     if (!use_cached) write_base_record(b);
 
-    if (use_cached) {
+    if (bulk_in) {
+      // ========================================================= phases 1-2 from the caches (bulk)
+      mbar_wait(env_mbar(ws, nL, nc), in_parity);
+      in_parity ^= 1u;
+      T Hs[4][12], Vs[4][6];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int i = lane + t * G;
+        if (i < nL) {
+          ldn<12>(ws + (size_t)i * 16, Hs[t]);
+          ldn<6>(ws + (size_t)nL * 16 + (size_t)i * 6, Vs[t]);
+        }
+      }
+      __syncwarp();  // the staging area is consumed: the records may now overwrite it
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int i = lane + t * G;
+        if (i < nL) {
+          T* ri = ws + (size_t)i * REC;
+          const T* H = Hs[t];
+          const T* V = Vs[t];
+          const T R[9] = {H[0], H[1], H[2], H[4], H[5], H[6], H[8], H[9], H[10]};
+          const T p[3] = {H[3], H[7], H[11]};
+          T v[6], tt[3];
+          cross3(V + 3, p, tt);  // velocity of the link origin: W_v_lin + w x p
+          v[0] = V[0] + tt[0]; v[1] = V[1] + tt[1]; v[2] = V[2] + tt[2];
+          v[3] = V[3]; v[4] = V[4]; v[5] = V[5];
+          stn<9>(ri + O_R, R);
+          stn<3>(ri + O_P, p);
+          stn<6>(ri + O_V, v);
+          if (i > 0) {
+            T ax[3], aw[3];
+            ldn<3>(sm_cst + (size_t)i * CREC + C_AXIS, ax);
+            mat3_vec(R, ax, aw);
+            stn<3>(ri + O_AX, aw);
+            ri[O_S] = s_r[t];
+            ri[O_SD] = sd_r[t];
+            ri[O_TREF] = tr_r[t];
+          }
+        }
+      }
+      __syncwarp();
+      for (int i = 1 + lane; i < nL; i += G) {
+        T* ri = ws + (size_t)i * REC;
+        const T* rp = ws + (size_t)parent[i] * REC;
+        const T r[3] = {ri[O_P] - rp[O_P], ri[O_P + 1] - rp[O_P + 1], ri[O_P + 2] - rp[O_P + 2]};
+        stn<3>(ri + O_RR, r);
+      }
+      __syncwarp();
+    } else if (use_cached) {
       // ========================================================= phases 1-2 from the caches
       // The input data carries the link transforms / velocities of its own state (they are
       // what the reference's contact code reads, api/contact.py:39-43): 88 B per link from
@@ -1285,13 +1421,14 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
       }
       B200SIM_PHASE_MARK(11);
       const bool want_caches = last && (P.W_H_L || P.W_v);
+      const bool compact = SPEC && last && tma && (P.iXl != nullptr) && (nL <= 4 * G + 1);
       if (last && active && lane == 0) {
         stn<4>(P.q_o + env * 4, b.qn);
         stn<3>(P.p_o + env * 3, b.p);
         stn<3>(P.vlin_o + env * 3, b.vlin);
         stn<3>(P.omega_o + env * 3, b.w);
         if (P.W_H_B) store_transform(P.W_H_B + env * 16, b.R, b.p);
-        if (P.iXl) {
+        if (P.iXl && !compact) {
           T R0[9], p0[3], t[3], X[36];
           mat3_mul(b.R, sm_cst + C_M0, R0);
           mat3_vec(b.R, sm_cst + C_TPRE, t);
@@ -1300,48 +1437,163 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
           stg_vec<36>(P.iXl + env * nL * 36, X);
         }
       }
-      // joints: new velocity/position (+ joint transforms of the new state when kinematics
-      // are needed again: next step, or cache outputs)
-      B200SIM_PHASE_MARK(12);
-      const bool need_fk = !last || want_caches || (P.iXl != nullptr);
-      __pipeline_wait_prior(0);  // next step's torque references have landed
-      for (int i = 1 + lane; i < nL; i += G) {
-        T* ri = ws + (size_t)i * REC;
-        const T sdn = ri[O_SD] + dt * ri[O_SDD];
-        const T sn = ri[O_S] + dt * sdn;
-        ri[O_SD] = sdn;
-        ri[O_S] = sn;
-        if (last && active) {
-          P.sd_o[env * n + (i - 1)] = sdn;
-          P.s_o[env * n + (i - 1)] = sn;
-        }
-        if (need_fk) {
-          T Rrel[9], trel[3];
-          joint_rel_transform(P, flags, sm_cst + (size_t)i * CREC, jtypes[i], i, sn, Rrel, trel);
-          stn<9>(ri + O_R, Rrel);
-          stn<3>(ri + O_P, trel);
-          if (last && active && P.iXl) emit_joint_adjoint(ri, i, Rrel, trel);
-        }
-      }
-      B200SIM_PHASE_MARK(13);
-      // ========================================================= phase 8: FK of the new state
-      if (!last) {
-        // the next fused step starts like a fresh call: base_orientation normalises the
-        // stored quaternion once more (api/data.py:283-285), bit-identical to repeated steps
-        const T nrm = sqrt_t(b.qn[0] * b.qn[0] + b.qn[1] * b.qn[1] + b.qn[2] * b.qn[2] + b.qn[3] * b.qn[3]);
-        const T inv = T(1) / (nrm + Lim<T>::eps() * (nrm == T(0) ? T(1) : T(0)));
+      if (compact) {
+        // ======================================================= compact final phase (see FS above)
+        B200SIM_PHASE_MARK(12);
+        __pipeline_wait_prior(0);
+        T snr[4], sdr[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) b.qn[k] *= inv;
-        quat_to_dcm(b.qn, b.R);
-      }
-      if (flags & F_GENERIC_FK) make_fk_map(sm_cst, b, fm);
-      __syncwarp();  // every lane has read the base acceleration out of record 0
-      if (!last || want_caches || rigid) {
-        write_base_record(b);
-        fk_chain(!last);
-        B200SIM_PHASE_MARK(14);
-        if (last && active && want_caches) write_fk_caches(b, fm);
-        B200SIM_PHASE_MARK(15);
+        for (int t = 0; t < 4; ++t) {
+          const int i = 1 + lane + t * G;
+          snr[t] = T(0); sdr[t] = T(0);
+          if (i < nL) {
+            const T* ri = ws + (size_t)i * REC;
+            const T sdn = ri[O_SD] + dt * ri[O_SDD];
+            const T sn = ri[O_S] + dt * sdn;
+            snr[t] = sn; sdr[t] = sdn;
+            if (active) {
+              P.sd_o[env * n + (i - 1)] = sdn;
+              P.s_o[env * n + (i - 1)] = sn;
+            }
+          }
+        }
+        __syncwarp();  // every lane is done with the records (joint state, base acceleration)
+        T* FX = ws + (((size_t)nL * FS + 3) & ~size_t(3));
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int i = 1 + lane + t * G;
+          if (i < nL) {
+            T Rrel[9], trel[3], X[36];
+            joint_rel_transform(P, flags, sm_cst + (size_t)i * CREC, jtypes[i], i, snr[t], Rrel, trel);
+            T* fi = ws + (size_t)i * FS;
+            stn<9>(fi + F_R, Rrel);
+            stn<3>(fi + F_P, trel);
+            fi[F_SD] = sdr[t];
+            inverse_adjoint(X, Rrel, trel);
+            stn<36>(FX + (size_t)i * 36, X);
+          }
+        }
+        if (lane == 0) {
+          // link 0: Ad((W_H_B suc_H_i[0])^-1) (api/kin_dyn_parameters.py:417-449) and the chain root
+          T R0[9], p0[3], t[3], X[36];
+          mat3_mul(b.R, sm_cst + C_M0, R0);
+          mat3_vec(b.R, sm_cst + C_TPRE, t);
+          p0[0] = b.p[0] + t[0]; p0[1] = b.p[1] + t[1]; p0[2] = b.p[2] + t[2];
+          inverse_adjoint(X, R0, p0);
+          stn<36>(FX, X);
+          T v0[6];
+          cross3(b.w, b.p, t);  // velocity of the base origin: v_lin + w x p
+          v0[0] = b.vlin[0] + t[0]; v0[1] = b.vlin[1] + t[1]; v0[2] = b.vlin[2] + t[2];
+          v0[3] = b.w[0]; v0[4] = b.w[1]; v0[5] = b.w[2];
+          stn<9>(ws + F_R, b.R);
+          stn<3>(ws + F_P, b.p);
+          stn<6>(ws + F_V, v0);
+        }
+        // generic-proxy writes of every lane -> visible to the async proxy, then one bulk store
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0 && active) tma_store_bulk(P.iXl + env * nL * 36, FX, (unsigned)(nL * 36 * sizeof(T)));
+        B200SIM_PHASE_MARK(13);
+        if (want_caches) {
+          // FK + velocity chain over the tree levels on the compact records
+          for (int l = 1; l <= P.depth; ++l) {
+            __syncwarp();
+            const int e = lvl_start[l + 1];
+            for (int idx = lvl_start[l] + lane; idx < e; idx += G) {
+              const int i = lvl_links[idx];
+              const T* rp = ws + (size_t)parent[i] * FS;
+              T* ri = ws + (size_t)i * FS;
+              T Rp[9], pp[3], vp[6], Rrel[9], trel[3];
+              ldn<9>(rp + F_R, Rp);
+              ldn<3>(rp + F_P, pp);
+              ldn<6>(rp + F_V, vp);
+              ldn<9>(ri + F_R, Rrel);
+              ldn<3>(ri + F_P, trel);
+              T R[9], r[3], pw[3];
+              mat3_mul(Rp, Rrel, R);
+              mat3_vec(Rp, trel, r);
+              pw[0] = pp[0] + r[0]; pw[1] = pp[1] + r[1]; pw[2] = pp[2] + r[2];
+              T ax[3], aw[3];
+              ldn<3>(sm_cst + (size_t)i * CREC + C_AXIS, ax);
+              mat3_vec(R, ax, aw);
+              const T sdi = ri[F_SD];
+              T v[6];
+              cross3(vp + 3, r, v);
+              v[0] += vp[0]; v[1] += vp[1]; v[2] += vp[2];
+              v[3] = vp[3]; v[4] = vp[4]; v[5] = vp[5];
+              const int jt = jtypes[i];
+              if (jt == 1) { v[3] += sdi * aw[0]; v[4] += sdi * aw[1]; v[5] += sdi * aw[2]; }
+              else if (jt == 2) { v[0] += sdi * aw[0]; v[1] += sdi * aw[1]; v[2] += sdi * aw[2]; }
+              stn<9>(ri + F_R, R);
+              stn<3>(ri + F_P, pw);
+              stn<6>(ri + F_V, v);
+            }
+          }
+          __syncwarp();
+          B200SIM_PHASE_MARK(14);
+          if (active) {
+            for (int i = lane; i < nL; i += G) {
+              const T* ri = ws + (size_t)i * FS;
+              T R[9], p[3], v[6];
+              ldn<9>(ri + F_R, R);
+              ldn<3>(ri + F_P, p);
+              ldn<6>(ri + F_V, v);
+              if (P.W_H_L) store_transform(P.W_H_L + (env * nL + i) * 16, R, p);
+              if (P.W_v) {
+                T t[3];
+                cross3(p, v + 3, t);  // inertial-fixed linear part: vlin + p x w
+                const T o[6] = {v[0] + t[0], v[1] + t[1], v[2] + t[2], v[3], v[4], v[5]};
+                stg_vec6(P.W_v + (env * nL + i) * 6, o);
+              }
+            }
+          }
+          B200SIM_PHASE_MARK(15);
+        }
+        __syncwarp();
+      } else {
+        // joints: new velocity/position (+ joint transforms of the new state when kinematics
+        // are needed again: next step, or cache outputs)
+        B200SIM_PHASE_MARK(12);
+        const bool need_fk = !last || want_caches || (P.iXl != nullptr);
+        __pipeline_wait_prior(0);  // next step's torque references have landed
+        for (int i = 1 + lane; i < nL; i += G) {
+          T* ri = ws + (size_t)i * REC;
+          const T sdn = ri[O_SD] + dt * ri[O_SDD];
+          const T sn = ri[O_S] + dt * sdn;
+          ri[O_SD] = sdn;
+          ri[O_S] = sn;
+          if (last && active) {
+            P.sd_o[env * n + (i - 1)] = sdn;
+            P.s_o[env * n + (i - 1)] = sn;
+          }
+          if (need_fk) {
+            T Rrel[9], trel[3];
+            joint_rel_transform(P, flags, sm_cst + (size_t)i * CREC, jtypes[i], i, sn, Rrel, trel);
+            stn<9>(ri + O_R, Rrel);
+            stn<3>(ri + O_P, trel);
+            if (last && active && P.iXl) emit_joint_adjoint(ri, i, Rrel, trel);
+          }
+        }
+        B200SIM_PHASE_MARK(13);
+        // ========================================================= phase 8: FK of the new state
+        if (!last) {
+          // the next fused step starts like a fresh call: base_orientation normalises the
+          // stored quaternion once more (api/data.py:283-285), bit-identical to repeated steps
+          const T nrm = sqrt_t(b.qn[0] * b.qn[0] + b.qn[1] * b.qn[1] + b.qn[2] * b.qn[2] + b.qn[3] * b.qn[3]);
+          const T inv = T(1) / (nrm + Lim<T>::eps() * (nrm == T(0) ? T(1) : T(0)));
+  #pragma unroll
+          for (int k = 0; k < 4; ++k) b.qn[k] *= inv;
+          quat_to_dcm(b.qn, b.R);
+        }
+        if (flags & F_GENERIC_FK) make_fk_map(sm_cst, b, fm);
+        __syncwarp();  // every lane has read the base acceleration out of record 0
+        if (!last || want_caches || rigid) {
+          write_base_record(b);
+          fk_chain(!last);
+          B200SIM_PHASE_MARK(14);
+          if (last && active && want_caches) write_fk_caches(b, fm);
+          B200SIM_PHASE_MARK(15);
+        }
       }
       if (rigid) {
         // a point below the ground at t+dt: the impact (rigid.py:385-436) is left to the rigid
