@@ -61,6 +61,7 @@ def parse():
     ap.add_argument("--no-input-caches", action="store_true", help="recompute the kinematics of the input state instead of reading its cached link transforms/velocities")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
     ap.add_argument("--no-tma", action="store_true", help="128-bit stores instead of TMA bulk stores for the joint adjoints")
+    ap.add_argument("--no-bulk-in", action="store_true", help="diagnostic: per-link cp.async instead of cp.async.bulk for the cached input kinematics")
     ap.add_argument("--generic-kernel", action="store_true", help="diagnostic: launch the generic step-kernel instance instead of the specialised one")
     ap.add_argument("--profile", action="store_true", help="cudaProfilerStart/Stop around the eager timed region (ncu --profile-from-start off)")
     ap.add_argument("--jvp", action="store_true", help="also time BASELINE config 5: forward-mode d(step)/d(joint q, link masses), fp64")
@@ -216,8 +217,8 @@ def run_b200(args):
     model = js.model.JaxSimModel.build_from_model_description(models.urdf(args.model), time_step=1e-3)
     if args.lanes:
         model.set_tuning(lanes_per_env=args.lanes)
-    if args.no_tma or args.generic_kernel:
-        model.set_options(tma_store=not args.no_tma, generic_kernel=args.generic_kernel)
+    if args.no_tma or args.generic_kernel or args.no_bulk_in:
+        model.set_options(tma_store=not args.no_tma, generic_kernel=args.generic_kernel, bulk_in=not args.no_bulk_in)
     n, nL, nc = model.dofs(), model.number_of_links(), model.number_of_collidable_points()
     B = args.batch
     bytes_env = algorithmic_bytes_per_env(n, nL, nc, w, caches=not args.no_caches)
@@ -367,36 +368,69 @@ def run_b200(args):
     ev_cmp = [torch.cuda.Event() for _ in range(2)]
     ev_out = [torch.cuda.Event() for _ in range(2)]
 
-    def e2e_run(count):
+    def e2e_run(count, fresh=False):
+        """`count` pipelined steps over three streams.  `fresh`: no event has been recorded yet
+        (first use, or inside a graph capture where only captured events may be waited on)."""
+        seen = set() if fresh else {("cmp", 0), ("cmp", 1), ("out", 0), ("out", 1)}
         for i in range(count):
             j = i & 1
             with torch.cuda.stream(s_in):
-                s_in.wait_event(ev_cmp[j])       # the step that last read d_in[j] is done
+                if ("cmp", j) in seen:
+                    s_in.wait_event(ev_cmp[j])       # the step that last read d_in[j] is done
                 d_in[j].copy_(h_in, non_blocking=True)
                 ev_in[j].record(s_in)
             with torch.cuda.stream(s_cmp):
                 s_cmp.wait_event(ev_in[j])
-                s_cmp.wait_event(ev_out[j])      # the D2H that last read d_out[j] is done
+                if ("out", j) in seen:
+                    s_cmp.wait_event(ev_out[j])      # the D2H that last read d_out[j] is done
                 js.model.step(model, din[j][0], joint_force_references=din[j][1], out=dout[j])
                 ev_cmp[j].record(s_cmp)
+                seen.add(("cmp", j))
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_cmp[j])
                 h_out[j].copy_(d_out[j], non_blocking=True)
                 ev_out[j].record(s_out)
+                seen.add(("out", j))
 
-    e2e_run(4)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(s_cmp)
-    e2e_run(Ke)
-    s_cmp.wait_event(ev_out[0])
-    s_cmp.wait_event(ev_out[1])
-    e1.record(s_cmp)
-    barrier()
-    te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = B * world * Ke / (float(te.item()) * 1e-3)
+    def timed(fn):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(s_cmp)
+        fn()
+        e1.record(s_cmp)
+        barrier()
+        te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return float(te.item())
+
+    # (1) launched call by call from Python (host dispatch of 2 copies + 1 step per iteration included)
+    e2e_run(4, fresh=True)
+
+    def eager():
+        e2e_run(Ke)
+        s_cmp.wait_event(ev_out[0])
+        s_cmp.wait_event(ev_out[1])
+
+    e2e_eager_value = B * world * Ke / (timed(eager) * 1e-3)
+
+    # (2) the same Ke-step pipeline (same API calls, same pinned buffers, same three streams) captured
+    #     once into a CUDA graph and replayed: what a user does to take Python out of the loop
+    e2e_value, e2e_mode = e2e_eager_value, "eager"
+    if not args.no_graph:
+        torch.cuda.synchronize()
+        eg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(eg, stream=s_cmp):
+            s_in.wait_stream(s_cmp)
+            s_out.wait_stream(s_cmp)
+            e2e_run(Ke, fresh=True)
+            s_cmp.wait_stream(s_in)
+            s_cmp.wait_stream(s_out)
+        with torch.cuda.stream(s_cmp):
+            eg.replay()
+            torch.cuda.synchronize()
+            t_graph = timed(eg.replay)
+        e2e_value, e2e_mode = B * world * Ke / (t_graph * 1e-3), "cuda_graph"
 
     # ---- optional batch sweep on this GPU (metric is quoted "batch 4096 -> 65536")
     sweep = None
@@ -560,7 +594,8 @@ def run_b200(args):
                      "bytes_moved_per_env_step": bytes_env + (0 if (args.no_input_caches or args.no_caches) else w * 22 * nL)},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-                "note": "public API js.model.step with pinned host buffers, every step: one H2D (state + contact state + tau), step, one D2H (new state + contact state); double-buffered over 3 streams; the caches are written on the device like in `value` but not copied back"},
+                "launch": e2e_mode, "eager_value": e2e_eager_value,
+                "note": "public API js.model.step with pinned host buffers, every step: one H2D (state + contact state + tau), step, one D2H (new state + contact state); double-buffered over 3 streams; the caches are written on the device like in `value` but not copied back.  `value`: the Ke-step pipeline captured into one CUDA graph and replayed (launch=cuda_graph); `eager_value`: the same calls dispatched from Python one by one"},
         "gpu_launches": args.steps,
         "eager": {"value": B * world * args.steps / (ms_eager_max * 1e-3), "ms_per_step": ms_eager_max / args.steps,
                   "note": "same K steps launched one by one from Python (host launch latency included)"},

@@ -120,6 +120,9 @@ int b200sim_model_set_tuning(B200SimModel *model, int lanes_per_env, int envs_pe
  *   the instance specialised for floating-base soft-contact steps applies (same results;
  *   diagnostic / A-B timing switch). */
 #define B200SIM_OPT_GENERIC_KERNEL 4
+/*   B200SIM_OPT_NO_BULK_IN: read the cached kinematics of the input state with per-link
+ *   cp.async instead of two cp.async.bulk per environment (same results; diagnostic). */
+#define B200SIM_OPT_NO_BULK_IN 8
 int b200sim_model_set_options(B200SimModel *model, int32_t options);
 
 /* Query sizes / launch geometry chosen for a batch (for benchmarks and tests). */

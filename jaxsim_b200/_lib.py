@@ -10,7 +10,10 @@ import ctypes as C
 import pathlib
 
 _HERE = pathlib.Path(__file__).resolve().parent
-LIB_PATH = _HERE / "csrc" / "libb200sim.so"
+import os as _os
+
+# B200SIM_LIB: alternative build of the same library (A/B timing of compile-time variants)
+LIB_PATH = pathlib.Path(_os.environ["B200SIM_LIB"]) if _os.environ.get("B200SIM_LIB") else _HERE / "csrc" / "libb200sim.so"
 
 c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int32)
@@ -64,6 +67,7 @@ ABI_VERSION = 2
 OPT_TMA_STORE = 1
 OPT_RIGID_QP_F32 = 2
 OPT_GENERIC_KERNEL = 4
+OPT_NO_BULK_IN = 8
 EXPORTED_SYMBOLS = (
     "b200sim_version",
     "b200sim_model_create",

@@ -53,7 +53,7 @@ struct B200SimModel {
 
 namespace {
 
-inline int max_threads_for(int G) { return G <= 8 ? 288 : 512; }  // == LaunchBounds<G>::kThreads
+inline int max_threads_for(int G) { return G <= 8 ? B200SIM_KTHREADS : 512; }  // == LaunchBounds<G>::kThreads
 
 #define CK(x)                         \
   do {                                \
@@ -419,7 +419,7 @@ int step_t(const B200SimModel* m, int dtype, int64_t B, const void* s, const voi
   P.nsteps = nsteps; P.tau_step_stride = tau_stride; P.fext_step_stride = fext_stride;
   P.Hin = (const T*)Hin; P.Vin = (const T*)Vin;
   // cp.async.bulk needs 16-byte aligned, 16-byte granular blocks per environment
-  if (Hin && Vin && ((uintptr_t)Hin % 16 == 0) && ((uintptr_t)Vin % 16 == 0) && (((size_t)m->nL * 6 * sizeof(T)) % 16 == 0))
+  if (!(m->opt_flags & B200SIM_OPT_NO_BULK_IN) && Hin && Vin && ((uintptr_t)Hin % 16 == 0) && ((uintptr_t)Vin % 16 == 0) && (((size_t)m->nL * 6 * sizeof(T)) % 16 == 0))
     P.flags |= F_BULK_IN;
   P.mode = MODE_STEP;
   if (m->contact_model == B200SIM_CONTACT_RIGID && m->nc > 0) {
@@ -734,7 +734,7 @@ int b200sim_model_set_tuning(B200SimModel* m, int lanes_per_env, int envs_per_bl
 // Undeclared diagnostic (not part of the ABI): enables, reads and resets the rigid-contact counters
 // [0] QP iterations, [1] QPs, [2] max iterations, [3] active points (QP), [4] full items,
 // [5] impact-only items, [6] impacts, [7] active points (impact).
-constexpr int DBG_WORDS = 8 + 32;  // 8 counters + the phase clocks of step_kernel (B200SIM_PHASE_MARK)
+constexpr int DBG_WORDS = 8 + 32 + 1024 + 512;  // 8 counters + the phase clocks of step_kernel (B200SIM_PHASE_MARK) + per-block start/end ns
 extern "C" int b200sim_debug_counters(B200SimModel* m, unsigned long long* out8) {
   if (!m) return B200SIM_E_INVALID;
   int prev = 0;
@@ -764,8 +764,21 @@ extern "C" int b200sim_debug_phase_clocks(B200SimModel* m, unsigned long long* o
   return 0;
 }
 
+// Undeclared diagnostic: %globaltimer (ns) at the start and end of the first 512 blocks of the last
+// step_kernel launch: out[2*b], out[2*b+1].
+extern "C" int b200sim_debug_block_times(B200SimModel* m, unsigned long long* out1024) {
+  if (!m || !m->dbg_d || !out1024) return B200SIM_E_INVALID;
+  int prev = 0;
+  CK(cudaGetDevice(&prev));
+  CK(cudaSetDevice(m->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out1024, m->dbg_d + 40, (1024 + 512) * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  cudaSetDevice(prev);
+  return 0;
+}
+
 int b200sim_model_set_options(B200SimModel* m, int32_t options) {
-  if (!m || (options & ~(B200SIM_OPT_TMA_STORE | B200SIM_OPT_RIGID_QP_F32 | B200SIM_OPT_GENERIC_KERNEL))) return B200SIM_E_INVALID;
+  if (!m || (options & ~(B200SIM_OPT_TMA_STORE | B200SIM_OPT_RIGID_QP_F32 | B200SIM_OPT_GENERIC_KERNEL | B200SIM_OPT_NO_BULK_IN))) return B200SIM_E_INVALID;
   m->opt_flags = options;
   return 0;
 }

@@ -545,9 +545,12 @@ __device__ __forceinline__ void fk_view(const int flags, const bool floating, co
   vlin[0] = Fv[0] + t[0]; vlin[1] = Fv[1] + t[1]; vlin[2] = Fv[2] + t[2];
 }
 
+#ifndef B200SIM_KTHREADS
+#define B200SIM_KTHREADS 256
+#endif
 template <int G>
 struct LaunchBounds {
-  static constexpr int kThreads = (G <= 8) ? 288 : 512;
+  static constexpr int kThreads = (G <= 8) ? B200SIM_KTHREADS : 512;  // 256 threads: the 255-register budget (288 rounds up to 384 threads = 168 registers)
 };
 
 // append an environment to the produced work list (rigid-contact cascade)
@@ -587,6 +590,11 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
   // ---- stage the model once per block: 16-byte cp.async chunks, all in flight at once
   // (the device blobs are padded to whole chunks by b200sim_model_create)
   if (P.dbg && blockIdx.x == 0 && threadIdx.x == 0) P.dbg[8 + 0] = (unsigned long long)clock64();
+  if (P.dbg && threadIdx.x == 0 && blockIdx.x < 512) {  // per-block start / end wall clock (ns)
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    P.dbg[40 + 2 * blockIdx.x] = t;
+  }
   stage_async(sm_cst, P.cst, nL * CREC);
   stage_async(sm_pt, P.pt_pos, (int)pt_words);
   stage_async(sm_itab, P.itab, (int)itab_words);
@@ -596,7 +604,9 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  __pipeline_wait_prior(0);
+  // The specialised instance reads nothing of the model before the kinematics of the first
+  // environment: it waits for the staging there, behind the input loads it has issued meanwhile.
+  if (!SPEC) __pipeline_wait_prior(0);
   __syncthreads();
   if (P.dbg && blockIdx.x == 0 && threadIdx.x == 0) P.dbg[8 + 1] = (unsigned long long)clock64();
 
@@ -632,7 +642,9 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
   for (long long env0 = first; env0 < P.B; env0 += stride) {
     long long env = env0 + grp;
     bool active = env < P.B;
-    if (!active) env = P.B - 1;  // idle groups shadow the last environment, stores masked
+    // idle groups shadow DISTINCT valid environments with their stores masked (many groups fetching the
+    // same rows serialise in L2: measured +3 us on the one block that carries the ragged tail)
+    if (!active) env = env % P.B;
 
     // =========================================================== prefetch (one burst)
     // joint state, first-step torque reference and contact state go global -> shared with
@@ -648,7 +660,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
     // with two cp.async.bulk (one lane, completion on the environment's mbarrier) into the head of
     // the still empty workspace -- [nL x 16 | nL x 6] words -- instead of 6 LDGSTS per link; the joint
     // state then goes to registers (its record slots overlap that staging area).
-    const bool bulk_in = SPEC && (sizeof(T) == 4) && use_cached && (flags & F_BULK_IN) && (nL <= 4 * G);  // (float: 84 staging registers)
+    const bool bulk_in = SPEC && use_cached && (flags & F_BULK_IN) && (16 * nL <= 54 * G);
     T s_r[4], sd_r[4], tr_r[4];
     if (bulk_in) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic accesses of the last trip before the async writes
@@ -826,6 +838,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
 
     B200SIM_PHASE_MARK(3);
     __pipeline_wait_prior(0);
+    if (SPEC && env0 == first) __syncthreads();  // the model blob staged by all threads of the block
     B200SIM_PHASE_MARK(4);
     if (!use_cached) write_base_record(b);
 
@@ -833,40 +846,40 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
       // ========================================================= phases 1-2 from the caches (bulk)
       mbar_wait(env_mbar(ws, nL, nc), in_parity);
       in_parity ^= 1u;
-      T Hs[4][12], Vs[4][6];
+      // The records (60 words per link) overwrite the staging area (22 words per link) from the
+      // top: the trips run over DESCENDING link indices, each one reads its links' staged rows,
+      // synchronises, then writes their records -- which only clobbers staging words of links that
+      // earlier trips have consumed (16 nL <= 54 G, checked by bulk_in).
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int i = lane + t * G;
-        if (i < nL) {
-          ldn<12>(ws + (size_t)i * 16, Hs[t]);
-          ldn<6>(ws + (size_t)nL * 16 + (size_t)i * 6, Vs[t]);
-        }
-      }
-      __syncwarp();  // the staging area is consumed: the records may now overwrite it
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int i = lane + t * G;
-        if (i < nL) {
-          T* ri = ws + (size_t)i * REC;
-          const T* H = Hs[t];
-          const T* V = Vs[t];
-          const T R[9] = {H[0], H[1], H[2], H[4], H[5], H[6], H[8], H[9], H[10]};
-          const T p[3] = {H[3], H[7], H[11]};
-          T v[6], tt[3];
-          cross3(V + 3, p, tt);  // velocity of the link origin: W_v_lin + w x p
-          v[0] = V[0] + tt[0]; v[1] = V[1] + tt[1]; v[2] = V[2] + tt[2];
-          v[3] = V[3]; v[4] = V[4]; v[5] = V[5];
-          stn<9>(ri + O_R, R);
-          stn<3>(ri + O_P, p);
-          stn<6>(ri + O_V, v);
-          if (i > 0) {
-            T ax[3], aw[3];
-            ldn<3>(sm_cst + (size_t)i * CREC + C_AXIS, ax);
-            mat3_vec(R, ax, aw);
-            stn<3>(ri + O_AX, aw);
-            ri[O_S] = s_r[t];
-            ri[O_SD] = sd_r[t];
-            ri[O_TREF] = tr_r[t];
+      for (int t = 3; t >= 0; --t) {
+        if (t * G < nL) {
+          const int i = lane + t * G;
+          T H[12], V[6];
+          if (i < nL) {
+            ldn<12>(ws + (size_t)i * 16, H);
+            ldn<6>(ws + (size_t)nL * 16 + (size_t)i * 6, V);
+          }
+          __syncwarp();
+          if (i < nL) {
+            T* ri = ws + (size_t)i * REC;
+            const T R[9] = {H[0], H[1], H[2], H[4], H[5], H[6], H[8], H[9], H[10]};
+            const T p[3] = {H[3], H[7], H[11]};
+            T v[6], tt[3];
+            cross3(V + 3, p, tt);  // velocity of the link origin: W_v_lin + w x p
+            v[0] = V[0] + tt[0]; v[1] = V[1] + tt[1]; v[2] = V[2] + tt[2];
+            v[3] = V[3]; v[4] = V[4]; v[5] = V[5];
+            stn<9>(ri + O_R, R);
+            stn<3>(ri + O_P, p);
+            stn<6>(ri + O_V, v);
+            if (i > 0) {
+              T ax[3], aw[3];
+              ldn<3>(sm_cst + (size_t)i * CREC + C_AXIS, ax);
+              mat3_vec(R, ax, aw);
+              stn<3>(ri + O_AX, aw);
+              ri[O_S] = s_r[t];
+              ri[O_SD] = sd_r[t];
+              ri[O_TREF] = tr_r[t];
+            }
           }
         }
       }
@@ -1637,6 +1650,17 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
   }
   if (tma) tma_store_wait_all();
   if (P.dbg && blockIdx.x == 0 && threadIdx.x == 0) P.dbg[8 + 16] = (unsigned long long)clock64();
+  if (P.dbg && blockIdx.x < 512) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      P.dbg[40 + 2 * blockIdx.x + 1] = t;
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      P.dbg[40 + 1024 + blockIdx.x] = smid;
+    }
+  }
 }
 
 }  // namespace b200sim

@@ -20,14 +20,16 @@ ap.add_argument("--model", default="icub_like")
 ap.add_argument("--lanes", type=int, default=0)
 ap.add_argument("--generic", action="store_true")
 ap.add_argument("--no-caches", action="store_true")
+ap.add_argument("--no-bulk-in", action="store_true")
+ap.add_argument("--ring", type=int, default=1, help="number of independent state sets walked round-robin (>= 10 at batch 4096: inputs come from HBM)")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 dtype = torch.float32 if args.dtype == "f32" else torch.float64
 m = js.model.JaxSimModel.build_from_model_description(models.urdf(args.model), time_step=1e-3)
 if args.lanes:
     m.set_tuning(lanes_per_env=args.lanes)
-if args.generic:
-    m.set_options(generic_kernel=True)
+if args.generic or args.no_bulk_in:
+    m.set_options(generic_kernel=args.generic, bulk_in=not args.no_bulk_in)
 B, n = args.batch, m.dofs()
 data = js.data.random_model_data(m, batch_size=B, seed=0, dtype=dtype, device=dev, velocity_representation=js.common.VelRepr.Inertial)
 tau = 10 * torch.rand(B, n, dtype=dtype, device=dev)
@@ -65,3 +67,27 @@ for k in range(1, 17):
     d = t[k] - prev
     print(f"  {NAMES[k]:48s} {d:8d} cyc  {d / mhz:7.2f} us   (cum {(t[k] - t[0]) / mhz:6.2f} us)")
     prev = t[k]
+
+import numpy as np  # noqa: E402
+
+bt = (ctypes.c_ulonglong * 1536)()
+lib.b200sim_debug_block_times.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+geo = m.launch_geometry(B, dtype, dev)
+stats = []
+ring = [js.data.random_model_data(m, batch_size=B, seed=100 + r, dtype=dtype, device=dev, velocity_representation=js.common.VelRepr.Inertial) for r in range(args.ring)]
+outs = [js.model.step(m, d, joint_force_references=tau) for d in ring]
+torch.cuda.synchronize()
+for rep in range(max(5, 2 * args.ring)):
+    r = rep % args.ring
+    js.model.step(m, ring[r], joint_force_references=tau, out=outs[r], update_caches=not args.no_caches)
+    lib.b200sim_debug_block_times(h, bt)
+    a = np.array(list(bt)[:1024], dtype=np.float64).reshape(512, 2)[:min(512, geo["grid"])]
+    smid = np.array(list(bt)[1024:], dtype=np.int64)[:min(512, geo["grid"])]
+    t0 = a[:, 0].min()
+    st, en = (a[:, 0] - t0) / 1e3, (a[:, 1] - t0) / 1e3
+    stats.append((st.max(), np.median(en - st), (en - st).min(), (en - st).max(), en.max(), np.percentile(en, 10), np.percentile(en, 90)))
+dur = en - st
+worst = np.argsort(-dur)[:6]
+print("  slowest blocks of the last launch (block, smid, start, duration us):", [(int(b), int(smid[b]), round(float(st[b]), 2), round(float(dur[b]), 2)) for b in worst])
+s_ = np.median(np.array(stats), axis=0)
+print("  blocks (us, median of 5 launches): last block start %.2f | block duration median %.2f min %.2f max %.2f | last end %.2f (p10 %.2f p90 %.2f)" % tuple(s_))
