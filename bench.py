@@ -61,7 +61,8 @@ def parse():
     ap.add_argument("--no-input-caches", action="store_true", help="recompute the kinematics of the input state instead of reading its cached link transforms/velocities")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
     ap.add_argument("--no-tma", action="store_true", help="128-bit stores instead of TMA bulk stores for the joint adjoints")
-    ap.add_argument("--no-bulk-in", action="store_true", help="diagnostic: per-link cp.async instead of cp.async.bulk for the cached input kinematics")
+    ap.add_argument("--no-pdl", action="store_true", help="diagnostic: ordinary launches instead of programmatic dependent launches")
+    ap.add_argument("--bulk-in", action="store_true", help="diagnostic: cp.async.bulk (TMA) instead of per-link cp.async for the cached input kinematics")
     ap.add_argument("--generic-kernel", action="store_true", help="diagnostic: launch the generic step-kernel instance instead of the specialised one")
     ap.add_argument("--profile", action="store_true", help="cudaProfilerStart/Stop around the eager timed region (ncu --profile-from-start off)")
     ap.add_argument("--jvp", action="store_true", help="also time BASELINE config 5: forward-mode d(step)/d(joint q, link masses), fp64")
@@ -217,8 +218,8 @@ def run_b200(args):
     model = js.model.JaxSimModel.build_from_model_description(models.urdf(args.model), time_step=1e-3)
     if args.lanes:
         model.set_tuning(lanes_per_env=args.lanes)
-    if args.no_tma or args.generic_kernel or args.no_bulk_in:
-        model.set_options(tma_store=not args.no_tma, generic_kernel=args.generic_kernel, bulk_in=not args.no_bulk_in)
+    if args.no_tma or args.generic_kernel or args.bulk_in or args.no_pdl:
+        model.set_options(tma_store=not args.no_tma, generic_kernel=args.generic_kernel, bulk_in=args.bulk_in, pdl=not args.no_pdl)
     n, nL, nc = model.dofs(), model.number_of_links(), model.number_of_collidable_points()
     B = args.batch
     bytes_env = algorithmic_bytes_per_env(n, nL, nc, w, caches=not args.no_caches)
@@ -343,9 +344,11 @@ def run_b200(args):
         hv[k].copy_(getattr(src, leaf).cpu())
     hv["m"].zero_()
     hv["tau"].copy_(10 * torch.rand(B, n, dtype=dtype))
-    h_out = [torch.empty(n_out, dtype=dtype).pin_memory() for _ in range(2)]
-    d_in = [torch.empty(n_in, dtype=dtype, device=dev) for _ in range(2)]
-    d_out = [torch.empty(n_out, dtype=dtype, device=dev) for _ in range(2)]
+    NB = max(2, int(os.environ.get("B200SIM_E2E_BUFFERS", "2")))  # pipeline depth (buffers per stage)
+    e2e_nostep = bool(os.environ.get("B200SIM_E2E_NOSTEP"))       # diagnostic: copies only
+    h_out = [torch.empty(n_out, dtype=dtype).pin_memory() for _ in range(NB)]
+    d_in = [torch.empty(n_in, dtype=dtype, device=dev) for _ in range(NB)]
+    d_out = [torch.empty(n_out, dtype=dtype, device=dev) for _ in range(NB)]
 
     def mk(views, with_tau):
         d = js.data.JaxSimModelData(
@@ -354,8 +357,8 @@ def run_b200(args):
             _base_position=views["p"], contact_state={"tangential_deformation": views["m"]})
         return (d, views["tau"]) if with_tau else d
 
-    din = [mk(carve(d_in[j], in_blocks), True) for j in range(2)]
-    dout = [mk(carve(d_out[j], out_blocks), False) for j in range(2)]
+    din = [mk(carve(d_in[j], in_blocks), True) for j in range(NB)]
+    dout = [mk(carve(d_out[j], out_blocks), False) for j in range(NB)]
     for d in dout:  # the step does the same device work as the `value` arm: caches are written (not copied back)
         d._base_transform = torch.empty(B, 4, 4, dtype=dtype, device=dev)
         d._joint_transforms = torch.empty(B, nL, 6, 6, dtype=dtype, device=dev)
@@ -364,16 +367,16 @@ def run_b200(args):
     h2d = n_in * h_in.element_size()
     d2h = n_out * h_in.element_size()
     s_in, s_cmp, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    ev_in = [torch.cuda.Event() for _ in range(2)]
-    ev_cmp = [torch.cuda.Event() for _ in range(2)]
-    ev_out = [torch.cuda.Event() for _ in range(2)]
+    ev_in = [torch.cuda.Event() for _ in range(NB)]
+    ev_cmp = [torch.cuda.Event() for _ in range(NB)]
+    ev_out = [torch.cuda.Event() for _ in range(NB)]
 
     def e2e_run(count, fresh=False):
         """`count` pipelined steps over three streams.  `fresh`: no event has been recorded yet
         (first use, or inside a graph capture where only captured events may be waited on)."""
-        seen = set() if fresh else {("cmp", 0), ("cmp", 1), ("out", 0), ("out", 1)}
+        seen = set() if fresh else {(k, j) for k in ("cmp", "out") for j in range(NB)}
         for i in range(count):
-            j = i & 1
+            j = i % NB
             with torch.cuda.stream(s_in):
                 if ("cmp", j) in seen:
                     s_in.wait_event(ev_cmp[j])       # the step that last read d_in[j] is done
@@ -383,7 +386,8 @@ def run_b200(args):
                 s_cmp.wait_event(ev_in[j])
                 if ("out", j) in seen:
                     s_cmp.wait_event(ev_out[j])      # the D2H that last read d_out[j] is done
-                js.model.step(model, din[j][0], joint_force_references=din[j][1], out=dout[j])
+                if not e2e_nostep:
+                    js.model.step(model, din[j][0], joint_force_references=din[j][1], out=dout[j])
                 ev_cmp[j].record(s_cmp)
                 seen.add(("cmp", j))
             with torch.cuda.stream(s_out):
@@ -405,12 +409,12 @@ def run_b200(args):
         return float(te.item())
 
     # (1) launched call by call from Python (host dispatch of 2 copies + 1 step per iteration included)
-    e2e_run(4, fresh=True)
+    e2e_run(2 * NB, fresh=True)
 
     def eager():
         e2e_run(Ke)
-        s_cmp.wait_event(ev_out[0])
-        s_cmp.wait_event(ev_out[1])
+        for j in range(NB):
+            s_cmp.wait_event(ev_out[j])
 
     e2e_eager_value = B * world * Ke / (timed(eager) * 1e-3)
 
@@ -571,6 +575,17 @@ def run_b200(args):
         except Exception:
             traffic = None
 
+    # the step is NOT HBM-bound, so the counted arithmetic is reported next to the HBM figure.
+    # flops per env-step = (2*FFMA + FADD + FMUL thread instructions) / batch from the ncu capture of this
+    # configuration (profiles/r01_step_kernel_v5_warm.md: 7530 FFMA + 2913 FADD + 4641 FMUL per env-step)
+    compute = None
+    if args.model == "icub_like" and args.dtype == "f32" and not args.no_caches:
+        fpe = 22615.0
+        peak_fp32 = 148 * 128 * 2 * 1.965e9 / 1e12  # CUDA-core FMA peak at the measured SM clock (nominal, TFLOP/s)
+        compute = {"flops_per_env_step": fpe, "achieved_tflops": fpe * B / (ms_step * 1e-3) / 1e12, "peak_tflops": peak_fp32,
+                   "frac": fpe * B / (ms_step * 1e-3) / 1e12 / peak_fp32, "unit": "TFLOP/s fp32 (CUDA cores; tensor cores do not apply)",
+                   "source": "ncu sm__sass_thread_inst_executed_op_{ffma,fadd,fmul} of this configuration, profiles/r01_step_kernel_v5_warm.md"}
+
     cpu = None
     if not args.no_cpu_baseline:
         threads = max(1, min(os.cpu_count() or 1, 256))
@@ -592,10 +607,11 @@ def run_b200(args):
                      "traffic": traffic, "bytes_per_env_step": bytes_env, "peak_source": peak_src,
                      "note": "algorithmic bytes = B_api (SURVEY.md 8d): read state+contact state+tau, write state+contact state+all caches; the kernel additionally READS the input data's cached link transforms/velocities (88 B/link, +2112 B/env) instead of recomputing them, like the reference's contact code",
                      "bytes_moved_per_env_step": bytes_env + (0 if (args.no_input_caches or args.no_caches) else w * 22 * nL)},
+        "compute": compute,
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                 "launch": e2e_mode, "eager_value": e2e_eager_value,
-                "note": "public API js.model.step with pinned host buffers, every step: one H2D (state + contact state + tau), step, one D2H (new state + contact state); double-buffered over 3 streams; the caches are written on the device like in `value` but not copied back.  `value`: the Ke-step pipeline captured into one CUDA graph and replayed (launch=cuda_graph); `eager_value`: the same calls dispatched from Python one by one"},
+                "note": "public API js.model.step with pinned host buffers, every step: one H2D (state + contact state + tau), step, one D2H (new state + contact state); pipelined over 3 streams (%d buffers per stage); the caches are written on the device like in `value` but not copied back.  `value`: the Ke-step pipeline captured into one CUDA graph and replayed (launch=cuda_graph); `eager_value`: the same calls dispatched from Python one by one" % NB},
         "gpu_launches": args.steps,
         "eager": {"value": B * world * args.steps / (ms_eager_max * 1e-3), "ms_per_step": ms_eager_max / args.steps,
                   "note": "same K steps launched one by one from Python (host launch latency included)"},

@@ -120,9 +120,16 @@ int b200sim_model_set_tuning(B200SimModel *model, int lanes_per_env, int envs_pe
  *   the instance specialised for floating-base soft-contact steps applies (same results;
  *   diagnostic / A-B timing switch). */
 #define B200SIM_OPT_GENERIC_KERNEL 4
-/*   B200SIM_OPT_NO_BULK_IN: read the cached kinematics of the input state with per-link
- *   cp.async instead of two cp.async.bulk per environment (same results; diagnostic). */
-#define B200SIM_OPT_NO_BULK_IN 8
+/*   B200SIM_OPT_BULK_IN: read the cached kinematics of the input state with two cp.async.bulk
+ *   (TMA, mbarrier completion) per environment instead of six cp.async per link (same
+ *   results).  Off by default: measured neutral at batch 4096 / 65536 with inputs from HBM,
+ *   ~1 us faster per step when the inputs are L2-resident, 5 % slower at batch 8192
+ *   (profiles/r01_bulk_in_ab.log). */
+#define B200SIM_OPT_BULK_IN 8
+/*   B200SIM_OPT_NO_PDL: launch the specialised step kernel as an ordinary kernel instead of with
+ *   programmatic stream serialization (the launch set-up of step k+1 then no longer overlaps
+ *   the execution of step k; same results; diagnostic). */
+#define B200SIM_OPT_NO_PDL 16
 int b200sim_model_set_options(B200SimModel *model, int32_t options);
 
 /* Query sizes / launch geometry chosen for a batch (for benchmarks and tests). */

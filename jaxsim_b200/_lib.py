@@ -67,7 +67,8 @@ ABI_VERSION = 2
 OPT_TMA_STORE = 1
 OPT_RIGID_QP_F32 = 2
 OPT_GENERIC_KERNEL = 4
-OPT_NO_BULK_IN = 8
+OPT_BULK_IN = 8
+OPT_NO_PDL = 16
 EXPORTED_SYMBOLS = (
     "b200sim_version",
     "b200sim_model_create",

@@ -37,6 +37,7 @@ struct B200SimModel {
   std::vector<int> itab_h;
   int o_parent = 0, o_jtype = 0, o_lvl_start = 0, o_lvl_links = 0, o_child_start = 0, o_child_idx = 0,
       o_pt_start = 0, o_pt_idx = 0, o_pt_body = 0, o_pt_enabled = 0, o_anc = 0, o_ldepth = 0;
+  int o_rows8 = 0, n_rows8 = 0, o_rows16 = 0, n_rows16 = 0;  // packed level-walk rows for G = 8 / 16 (0 rows: not available)
   double reg = 1e-6;
   unsigned long long* dbg_d = nullptr;  // debug counters, allocated by b200sim_debug_counters
   int* rigid_scratch = nullptr;      // work lists of the rigid-contact cascade
@@ -190,6 +191,7 @@ void fill_model_params(const B200SimModel* m, Params<T>& P) {
   P.o_child_start = m->o_child_start; P.o_child_idx = m->o_child_idx; P.o_pt_start = m->o_pt_start;
   P.o_pt_idx = m->o_pt_idx; P.o_pt_body = m->o_pt_body; P.o_pt_enabled = m->o_pt_enabled;
   P.o_anc = m->o_anc; P.o_ldepth = m->o_ldepth; P.reg = (T)m->reg;
+  P.o_rows8 = m->o_rows8; P.n_rows8 = m->n_rows8; P.o_rows16 = m->o_rows16; P.n_rows16 = m->n_rows16;
   P.dbg = m->dbg_d;
   P.dt = (T)m->dt; P.g = (T)m->g; P.h_terrain = (T)m->h_terrain;
   P.K = (T)m->K; P.D = (T)m->D; P.mu = (T)m->mu; P.pexp = (T)m->pexp; P.qexp = (T)m->qexp;
@@ -197,9 +199,24 @@ void fill_model_params(const B200SimModel* m, Params<T>& P) {
 }
 
 template <typename T, int G, int SPEC = 0>
-int launch_g(const Params<T>& P, const Geometry& g, cudaStream_t st) {
+int launch_g(const Params<T>& P, const Geometry& g, cudaStream_t st, bool pdl = false) {
   auto kern = step_kernel<T, G, SPEC>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+  if (pdl) {
+    // programmatic dependent launch: this launch may be set up while the previous kernel on the
+    // stream still runs; the kernel orders its reads of the state with griddepcontrol.wait
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(g.grid);
+    cfg.blockDim = dim3(g.epb * G);
+    cfg.dynamicSmemBytes = g.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, kern, P);
+  }
   kern<<<g.grid, g.epb * G, g.smem, st>>>(P);
   return (int)cudaGetLastError();
 }
@@ -212,6 +229,7 @@ bool specialised_step_applies(const B200SimModel* m, const Params<T>& P) {
   if (m->opt_flags & B200SIM_OPT_GENERIC_KERNEL) return false;
   if (P.mode != MODE_STEP || !P.floating) return false;
   if (P.flags & (F_SUC_NONID | F_GENERIC_FK)) return false;
+  if (P.n > 0 && (m->n_rows8 == 0 || m->n_rows16 == 0)) return false;  // packed level-walk rows unavailable
   return P.nc == 0 || P.contact_model == 1;
 }
 
@@ -226,12 +244,13 @@ int launch(const B200SimModel* m, Params<T>& P, int dtype, void* stream) {
   if (dev != m->device) CK(cudaSetDevice(m->device));
   cudaStream_t st = (cudaStream_t)stream;
   const bool spec = specialised_step_applies(m, P);
+  const bool pdl = spec && !(m->opt_flags & B200SIM_OPT_NO_PDL);
   switch (g.G) {
     case 1: rc = launch_g<T, 1>(P, g, st); break;
     case 2: rc = launch_g<T, 2>(P, g, st); break;
     case 4: rc = launch_g<T, 4>(P, g, st); break;
-    case 8: rc = spec ? launch_g<T, 8, 1>(P, g, st) : launch_g<T, 8>(P, g, st); break;
-    case 16: rc = spec ? launch_g<T, 16, 1>(P, g, st) : launch_g<T, 16>(P, g, st); break;
+    case 8: rc = spec ? launch_g<T, 8, 1>(P, g, st, pdl) : launch_g<T, 8>(P, g, st); break;
+    case 16: rc = spec ? launch_g<T, 16, 1>(P, g, st, pdl) : launch_g<T, 16>(P, g, st); break;
     case 32: rc = launch_g<T, 32>(P, g, st); break;
     default: rc = B200SIM_E_INVALID;
   }
@@ -419,7 +438,7 @@ int step_t(const B200SimModel* m, int dtype, int64_t B, const void* s, const voi
   P.nsteps = nsteps; P.tau_step_stride = tau_stride; P.fext_step_stride = fext_stride;
   P.Hin = (const T*)Hin; P.Vin = (const T*)Vin;
   // cp.async.bulk needs 16-byte aligned, 16-byte granular blocks per environment
-  if (!(m->opt_flags & B200SIM_OPT_NO_BULK_IN) && Hin && Vin && ((uintptr_t)Hin % 16 == 0) && ((uintptr_t)Vin % 16 == 0) && (((size_t)m->nL * 6 * sizeof(T)) % 16 == 0))
+  if ((m->opt_flags & B200SIM_OPT_BULK_IN) && Hin && Vin && ((uintptr_t)Hin % 16 == 0) && ((uintptr_t)Vin % 16 == 0) && (((size_t)m->nL * 6 * sizeof(T)) % 16 == 0))
     P.flags |= F_BULK_IN;
   P.mode = MODE_STEP;
   if (m->contact_model == B200SIM_CONTACT_RIGID && m->nc > 0) {
@@ -659,6 +678,42 @@ int b200sim_model_create(const B200SimModelDesc* d, int device, B200SimModel** o
     m->o_anc = push(anc.data(), anc.size());
     m->o_ldepth = push(depth.data(), depth.size());
   }
+  // Packed rows of the level walks for the specialised step kernel: row = G consecutive links of
+  // one tree level (levels in order, a level wider than G spans several rows), one int per lane:
+  //   bits 0-7 link (0xFF: none) | 8-15 parent | 16-23 first child | 24-26 number of children | 27-28 joint type
+  // One independent shared-memory load per row replaces the dependent chain lvl_start -> lvl_links ->
+  // parent / child_start -> child_idx / jtype.  Needs nL <= 255 and contiguous child indices (any
+  // breadth-first numbering, e.g. the reference's, parsers/kinematic_graph.py:669-709).
+  {
+    bool ok = nL <= 255;
+    for (int i = 0; i < nL && ok; ++i) {
+      const int c0 = child_start[i], c1 = child_start[i + 1];
+      if (c1 - c0 > 7) ok = false;
+      for (int c = c0; c + 1 < c1; ++c) if (child_idx[c + 1] != child_idx[c] + 1) ok = false;
+    }
+    for (int pass = 0; pass < 2 && ok; ++pass) {
+      const int Gr = pass == 0 ? 8 : 16;
+      std::vector<int> rows;
+      for (int l = 1; l <= maxd; ++l) {
+        const int b = lvl_start[l], e2 = lvl_start[l + 1];
+        for (int r0 = b; r0 < e2; r0 += Gr) {
+          for (int k = 0; k < Gr; ++k) {
+            int ent = 0xFF;
+            if (r0 + k < e2) {
+              const int i = lvl_links[r0 + k];
+              const int nch = child_start[i + 1] - child_start[i];
+              const int fc = nch > 0 ? child_idx[child_start[i]] : 0;
+              ent = i | (d->parent[i] << 8) | (fc << 16) | (nch << 24) | ((d->joint_type[i] & 3) << 27);
+            }
+            rows.push_back(ent);
+          }
+        }
+      }
+      const int nrows = (int)rows.size() / Gr;
+      const int off = rows.empty() ? 0 : push(rows.data(), rows.size());
+      if (pass == 0) { m->o_rows8 = off; m->n_rows8 = nrows; } else { m->o_rows16 = off; m->n_rows16 = nrows; }
+    }
+  }
   if (m->itab_h.empty()) m->itab_h.push_back(0);
 
   // ---- upload
@@ -778,7 +833,7 @@ extern "C" int b200sim_debug_block_times(B200SimModel* m, unsigned long long* ou
 }
 
 int b200sim_model_set_options(B200SimModel* m, int32_t options) {
-  if (!m || (options & ~(B200SIM_OPT_TMA_STORE | B200SIM_OPT_RIGID_QP_F32 | B200SIM_OPT_GENERIC_KERNEL | B200SIM_OPT_NO_BULK_IN))) return B200SIM_E_INVALID;
+  if (!m || (options & ~(B200SIM_OPT_TMA_STORE | B200SIM_OPT_RIGID_QP_F32 | B200SIM_OPT_GENERIC_KERNEL | B200SIM_OPT_BULK_IN | B200SIM_OPT_NO_PDL))) return B200SIM_E_INVALID;
   m->opt_flags = options;
   return 0;
 }

@@ -122,6 +122,7 @@ struct Params {
   int o_parent, o_jtype, o_lvl_start, o_lvl_links, o_child_start, o_child_idx, o_pt_start, o_pt_idx,
       o_pt_body, o_pt_enabled;
   int o_anc, o_ldepth;  // rigid contacts only: ancestors of every link (root-first, [nL*depth]) and their count
+  int o_rows8, n_rows8, o_rows16, n_rows16;  // packed level-walk rows (specialised step kernel), see b200sim_model_create
   T dt, g, h_terrain, K, D, mu, pexp, qexp, tau_max, w_th, w_max;
   T reg;                // rigid contacts: Delassus regularisation
   // ---- batch
@@ -589,6 +590,10 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
 
   // ---- stage the model once per block: 16-byte cp.async chunks, all in flight at once
   // (the device blobs are padded to whole chunks by b200sim_model_create)
+  // Programmatic dependent launch: let the NEXT launch on the stream be set up while this grid runs
+  // (its blocks cannot become resident before ours exit -- one block fills an SM's shared memory --
+  // but its launch latency disappears behind our execution).  No-ops for ordinary launches.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (P.dbg && blockIdx.x == 0 && threadIdx.x == 0) P.dbg[8 + 0] = (unsigned long long)clock64();
   if (P.dbg && threadIdx.x == 0 && blockIdx.x < 512) {  // per-block start / end wall clock (ns)
     unsigned long long t;
@@ -608,6 +613,9 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
   // environment: it waits for the staging there, behind the input loads it has issued meanwhile.
   if (!SPEC) __pipeline_wait_prior(0);
   __syncthreads();
+  // everything above touched only the constant model; the state below may have been written by the
+  // previous launch on the stream: wait for it to complete and flush (no-op without the PDL attribute)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (P.dbg && blockIdx.x == 0 && threadIdx.x == 0) P.dbg[8 + 1] = (unsigned long long)clock64();
 
   const int* parent = sm_itab + P.o_parent;
@@ -620,6 +628,10 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
   const int* pt_idx = sm_itab + P.o_pt_idx;
   const int* pt_body = sm_itab + P.o_pt_body;
   const int* pt_enabled = sm_itab + P.o_pt_enabled;
+  // packed level-walk rows of the specialised instance (G = 8 or 16): one int per lane and row
+  const int* rows = sm_itab + (G == 16 ? P.o_rows16 : P.o_rows8);
+  const int nrows = SPEC ? (G == 16 ? P.n_rows16 : P.n_rows8) : 0;
+  const int rlane = threadIdx.x & (G - 1);
 
   const int lane = threadIdx.x & (G - 1);
   const int grp = threadIdx.x / G;
@@ -768,12 +780,8 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
     // joint axis and the offset to the parent (not needed when only caches follow, and
     // their slots then hold the joint-adjoint staging).
     auto fk_chain = [&](const bool for_aba) {
-      for (int l = 1; l <= P.depth; ++l) {
-        __syncwarp();
-        const int e = lvl_start[l + 1];
-        for (int idx = lvl_start[l] + lane; idx < e; idx += G) {
-          const int i = lvl_links[idx];
-          const T* rp = ws + (size_t)parent[i] * REC;
+      auto fk_link = [&](const int i, const int par, const int jt) {
+          const T* rp = ws + (size_t)par * REC;
           T* ri = ws + (size_t)i * REC;
           T Rp[9], pp[3], vp[6], Rrel[9], trel[3];
           ldn<9>(rp + O_R, Rp);
@@ -793,7 +801,6 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
           cross3(vp + 3, r, v);
           v[0] += vp[0]; v[1] += vp[1]; v[2] += vp[2];
           v[3] = vp[3]; v[4] = vp[4]; v[5] = vp[5];
-          const int jt = jtypes[i];
           if (jt == 1) { v[3] += sdi * aw[0]; v[4] += sdi * aw[1]; v[5] += sdi * aw[2]; }
           else if (jt == 2) { v[0] += sdi * aw[0]; v[1] += sdi * aw[1]; v[2] += sdi * aw[2]; }
           stn<9>(ri + O_R, R);
@@ -802,6 +809,24 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
           if (for_aba) {
             stn<3>(ri + O_RR, r);
             stn<3>(ri + O_AX, aw);
+          }
+      };
+      if (SPEC) {
+        // packed rows: the next row's entry is fetched while the current one is processed
+        int e = nrows > 0 ? rows[rlane] : 0xFF;
+        for (int r = 0; r < nrows; ++r) {
+          __syncwarp();
+          const int en = (r + 1 < nrows) ? rows[(r + 1) * G + rlane] : 0xFF;
+          if ((e & 0xFF) != 0xFF) fk_link(e & 0xFF, (e >> 8) & 0xFF, (e >> 27) & 3);
+          e = en;
+        }
+      } else {
+        for (int l = 1; l <= P.depth; ++l) {
+          __syncwarp();
+          const int e = lvl_start[l + 1];
+          for (int idx = lvl_start[l] + lane; idx < e; idx += G) {
+            const int i = lvl_links[idx];
+            fk_link(i, parent[i], jtypes[i]);
           }
         }
       }
@@ -1200,11 +1225,8 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
       B200SIM_PHASE_MARK(7);
 
       // ========================================================= phase 4: ABA pass 2
-      for (int l = P.depth; l >= 1; --l) {
-        __syncwarp();
-        const int e = lvl_start[l + 1];
-        for (int idx = lvl_start[l] + lane; idx < e; idx += G) {
-          const int i = lvl_links[idx];
+      // children: a contiguous index range from the packed row (SPEC) or the child list (generic)
+      auto pass2_link = [&](const int i, const int par, const int jt, const int cbase, const int ncld) {
           T* ri = ws + (size_t)i * REC;
           T A[6], Bm[9], D[6], pA[6];
           ldn<6>(ri + O_IA, A);
@@ -1212,9 +1234,8 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
           ldn<6>(ri + O_ID, D);
           ldn<6>(ri + O_PA, pA);
           {
-            const int ce = child_start[i + 1];
-            for (int cc = child_start[i]; cc < ce; ++cc) {
-              const T* rc = ws + (size_t)child_idx[cc] * REC;
+            for (int cc = 0; cc < ncld; ++cc) {
+              const T* rc = ws + (size_t)(SPEC ? (cbase + cc) : child_idx[cbase + cc]) * REC;
 #pragma unroll
               for (int k = 0; k < 6; ++k) A[k] += rc[O_IA + k];
 #pragma unroll
@@ -1229,7 +1250,6 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
           ldn<3>(ri + O_AX, aw);
           ldn<6>(ri + O_C, cI);
           ldn<3>(ri + O_RR, r);
-          const int jt = jtypes[i];
           T Ul[3], Ua[3], d, u;
           const T tau = ri[O_TAU];
           if (jt == 1) {
@@ -1248,7 +1268,6 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
           stn<3>(ri + O_U + 3, Ua);
           ri[O_DINV] = dinv;
           ri[O_UU] = u;
-          const int par = parent[i];
           if (par != 0 || floating) {
             // Ma = IA - U U^T / d
             const T Uls[3] = {Ul[0] * dinv, Ul[1] * dinv, Ul[2] * dinv};
@@ -1308,6 +1327,23 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
             stn<6>(ri + O_ID, D2);
             stn<6>(ri + O_PA, pa);
           }
+      };
+      if (SPEC) {
+        int e = nrows > 0 ? rows[(nrows - 1) * G + rlane] : 0xFF;
+        for (int r = nrows - 1; r >= 0; --r) {
+          __syncwarp();
+          const int en = r > 0 ? rows[(r - 1) * G + rlane] : 0xFF;
+          if ((e & 0xFF) != 0xFF) pass2_link(e & 0xFF, (e >> 8) & 0xFF, (e >> 27) & 3, (e >> 16) & 0xFF, (e >> 24) & 7);
+          e = en;
+        }
+      } else {
+        for (int l = P.depth; l >= 1; --l) {
+          __syncwarp();
+          const int e = lvl_start[l + 1];
+          for (int idx = lvl_start[l] + lane; idx < e; idx += G) {
+            const int i = lvl_links[idx];
+            pass2_link(i, parent[i], jtypes[i], child_start[i], child_start[i + 1] - child_start[i]);
+          }
         }
       }
       __syncwarp();
@@ -1353,13 +1389,9 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
 
       B200SIM_PHASE_MARK(9);
       // ========================================================= phase 6: ABA pass 3
-      for (int l = 1; l <= P.depth; ++l) {
-        __syncwarp();
-        const int e = lvl_start[l + 1];
-        for (int idx = lvl_start[l] + lane; idx < e; idx += G) {
-          const int i = lvl_links[idx];
+      auto pass3_link = [&](const int i, const int par, const int jt) {
           T* ri = ws + (size_t)i * REC;
-          const T* rp = ws + (size_t)parent[i] * REC;
+          const T* rp = ws + (size_t)par * REC;
           T ap[6], r[3], cI[6], U[6], aw[3];
           ldn<6>(rp + O_V, ap);
           ldn<3>(ri + O_RR, r);
@@ -1371,11 +1403,27 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
           a[0] += ap[0] + cI[0]; a[1] += ap[1] + cI[1]; a[2] += ap[2] + cI[2];
           a[3] = ap[3] + cI[3]; a[4] = ap[4] + cI[4]; a[5] = ap[5] + cI[5];
           const T sdd = (ri[O_UU] - (U[0] * a[0] + U[1] * a[1] + U[2] * a[2] + U[3] * a[3] + U[4] * a[4] + U[5] * a[5])) * ri[O_DINV];
-          const int jt = jtypes[i];
           if (jt == 1) { a[3] += sdd * aw[0]; a[4] += sdd * aw[1]; a[5] += sdd * aw[2]; }
           else if (jt == 2) { a[0] += sdd * aw[0]; a[1] += sdd * aw[1]; a[2] += sdd * aw[2]; }
           stn<6>(ri + O_V, a);
           ri[O_SDD] = sdd;
+      };
+      if (SPEC) {
+        int e = nrows > 0 ? rows[rlane] : 0xFF;
+        for (int r = 0; r < nrows; ++r) {
+          __syncwarp();
+          const int en = (r + 1 < nrows) ? rows[(r + 1) * G + rlane] : 0xFF;
+          if ((e & 0xFF) != 0xFF) pass3_link(e & 0xFF, (e >> 8) & 0xFF, (e >> 27) & 3);
+          e = en;
+        }
+      } else {
+        for (int l = 1; l <= P.depth; ++l) {
+          __syncwarp();
+          const int e = lvl_start[l + 1];
+          for (int idx = lvl_start[l] + lane; idx < e; idx += G) {
+            const int i = lvl_links[idx];
+            pass3_link(i, parent[i], jtypes[i]);
+          }
         }
       }
       __syncwarp();
@@ -1509,12 +1557,13 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
         B200SIM_PHASE_MARK(13);
         if (want_caches) {
           // FK + velocity chain over the tree levels on the compact records
-          for (int l = 1; l <= P.depth; ++l) {
+          int e = nrows > 0 ? rows[rlane] : 0xFF;
+          for (int r = 0; r < nrows; ++r) {
             __syncwarp();
-            const int e = lvl_start[l + 1];
-            for (int idx = lvl_start[l] + lane; idx < e; idx += G) {
-              const int i = lvl_links[idx];
-              const T* rp = ws + (size_t)parent[i] * FS;
+            const int en = (r + 1 < nrows) ? rows[(r + 1) * G + rlane] : 0xFF;
+            if ((e & 0xFF) != 0xFF) {
+              const int i = e & 0xFF;
+              const T* rp = ws + (size_t)((e >> 8) & 0xFF) * FS;
               T* ri = ws + (size_t)i * FS;
               T Rp[9], pp[3], vp[6], Rrel[9], trel[3];
               ldn<9>(rp + F_R, Rp);
@@ -1534,13 +1583,14 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
               cross3(vp + 3, r, v);
               v[0] += vp[0]; v[1] += vp[1]; v[2] += vp[2];
               v[3] = vp[3]; v[4] = vp[4]; v[5] = vp[5];
-              const int jt = jtypes[i];
+              const int jt = (e >> 27) & 3;
               if (jt == 1) { v[3] += sdi * aw[0]; v[4] += sdi * aw[1]; v[5] += sdi * aw[2]; }
               else if (jt == 2) { v[0] += sdi * aw[0]; v[1] += sdi * aw[1]; v[2] += sdi * aw[2]; }
               stn<9>(ri + F_R, R);
               stn<3>(ri + F_P, pw);
               stn<6>(ri + F_V, v);
             }
+            e = en;
           }
           __syncwarp();
           B200SIM_PHASE_MARK(14);

@@ -36,5 +36,5 @@ for tool in racecheck memcheck synccheck; do
   timeout 900 compute-sanitizer --tool $tool --print-limit 3 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/sanitizer_$tool.log 2>&1
   grep -E "ERROR SUMMARY|RACECHECK SUMMARY|smoke" gpurun_out/sanitizer_$tool.log | head -4
 done
-B200SIM_SMOKE_NO_BULK_IN=1 timeout 900 compute-sanitizer --tool racecheck --print-limit 3 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/sanitizer_racecheck_nobulk.log 2>&1
-grep -E "RACECHECK SUMMARY|smoke" gpurun_out/sanitizer_racecheck_nobulk.log | head -4
+B200SIM_SMOKE_BULK_IN=1 timeout 900 compute-sanitizer --tool racecheck --print-limit 3 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/sanitizer_racecheck_bulk.log 2>&1
+grep -E "RACECHECK SUMMARY|smoke" gpurun_out/sanitizer_racecheck_bulk.log | head -4

@@ -20,7 +20,7 @@ ap.add_argument("--model", default="icub_like")
 ap.add_argument("--lanes", type=int, default=0)
 ap.add_argument("--generic", action="store_true")
 ap.add_argument("--no-caches", action="store_true")
-ap.add_argument("--no-bulk-in", action="store_true")
+ap.add_argument("--bulk-in", action="store_true")
 ap.add_argument("--ring", type=int, default=1, help="number of independent state sets walked round-robin (>= 10 at batch 4096: inputs come from HBM)")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
@@ -28,8 +28,8 @@ dtype = torch.float32 if args.dtype == "f32" else torch.float64
 m = js.model.JaxSimModel.build_from_model_description(models.urdf(args.model), time_step=1e-3)
 if args.lanes:
     m.set_tuning(lanes_per_env=args.lanes)
-if args.generic or args.no_bulk_in:
-    m.set_options(generic_kernel=args.generic, bulk_in=not args.no_bulk_in)
+if args.generic or args.bulk_in:
+    m.set_options(generic_kernel=args.generic, bulk_in=args.bulk_in)
 B, n = args.batch, m.dofs()
 data = js.data.random_model_data(m, batch_size=B, seed=0, dtype=dtype, device=dev, velocity_representation=js.common.VelRepr.Inertial)
 tau = 10 * torch.rand(B, n, dtype=dtype, device=dev)
