@@ -212,7 +212,10 @@ class OracleModel:
     time_step: float = 0.001
     gravity: float = -9.81  # model.gravity (api/model.py:62,206): NEGATIVE
     terrain_height: float = 0.0  # FlatTerrain (terrain/terrain.py:66-113)
-    contact_model: str = "soft"  # "soft" | "rigid" (oracle/rigid_oracle.py) | "none"
+    contact_model: str = "soft"  # "soft" | "rigid" | "relaxed" (oracle/rigid_oracle.py) | "none"
+    # RelaxedRigidContactsParams (rbda/contacts/relaxed_rigid.py:30-82); mu above is shared
+    relaxed: dict = dataclasses.field(default_factory=lambda: dict(
+        time_constant=0.02, damping_coefficient=1.0, d_min=0.9, d_max=0.95, width=0.001, midpoint=0.5, power=2.0))
     regularization_delassus: float = 1e-6  # RigidContacts (rbda/contacts/rigid.py:99-101)
     # SoftContactsParams (rbda/contacts/soft.py:24-46)
     K: float = 1e6

@@ -530,7 +530,15 @@ class lax:
 
     @staticmethod
     def custom_linear_solve(matvec, b, solve, transpose_solve=None, symmetric=False, has_aux=False):
-        return solve(matvec, b)
+        """The solution of matvec(x) = b itself: the operator is materialised column by column and
+        solved directly (minimum-norm where it is singular), instead of running the caller's
+        iterative `solve` -- the only call site (rbda/contacts/relaxed_rigid.py:497-505) passes an
+        L-BFGS loop over optax there, whose fixed point is this solution (README.md)."""
+        rhs = np.asarray(b, dtype=float)
+        n = rhs.shape[0]
+        A = np.stack([np.asarray(matvec(asarray(np.eye(n)[:, k])), dtype=float) for k in range(n)], axis=1) if n else np.zeros((0, 0))
+        x = np.linalg.lstsq(A, rhs, rcond=1e-13)[0] if n else rhs
+        return (asarray(x), None) if has_aux else asarray(x)
 
     @staticmethod
     def dynamic_slice(operand, start_indices, slice_sizes):

@@ -510,6 +510,82 @@ def compute_contact_forces(model, env: _Env, tau, W_f_L):
     return O.other_representation_to_inertial(f6, "mixed", W_H_C, is_force=True)
 
 
+# ---------------------------------------------------------------------------------------
+# rbda/contacts/relaxed_rigid.py
+# ---------------------------------------------------------------------------------------
+
+
+def relaxed_regularizers(model, link_idx, pos, vel):
+    """``RelaxedRigidContacts._regularizers`` (``relaxed_rigid.py:533-653``) for the enabled
+    points: ``pos`` (nc,3) position in the constraint frame (= -delta n), ``vel`` (nc,3).
+    Returns (a_ref (3nc,), r (3nc,)).  As in the reference, the impedance is evaluated per
+    COMPONENT of ``pos`` (``imp_x = |pos| / width`` is a 3-vector) and the parameters K / D are
+    shadowed by the values derived from the time constant (``:585-591``)."""
+    prm = model.relaxed
+    Om, ze, xmin, xmax = prm["time_constant"], prm["damping_coefficient"], prm["d_min"], prm["d_max"]
+    width, mid, pw = prm["width"], prm["midpoint"], prm["power"]
+    mu = float(model.mu)
+    mass = np.asarray(model.kin_dyn_parameters.link_parameters.mass, dtype=np.float64)
+    imp_x = np.abs(pos) / width
+    with np.errstate(invalid="ignore"):
+        imp_a = (1.0 / np.power(mid, pw - 1)) * np.power(imp_x, pw)
+        imp_b = 1 - (1.0 / np.power(1 - mid, pw - 1)) * np.power(1 - imp_x, pw)  # NaN for imp_x > 1 and odd powers: masked below
+    imp_y = np.where(imp_x < mid, imp_a, imp_b)
+    xi = xmin + imp_y * (xmax - xmin)
+    xi = np.clip(xi, xmin, xmax)
+    xi = np.where(imp_x > 1.0, xmax, xi)
+    K = 1 / (xmax * Om * ze) ** 2
+    D = 2 / (xmax * Om)
+    a_ref = -(D * vel + K * xi * pos)
+    # (vector) @ inv(M_L[link, :3, :3]) with M_L[:3, :3] = m 1  (:619-623)
+    r = (2 * mu**2 * (1 - xi) / (xi + 1e-12)) * (1 + mu**2) / mass[link_idx][:, None]
+    active = (np.einsum("ij,ij->i", pos, pos) > 0).astype(np.float64)[:, None]
+    return (a_ref * active).reshape(-1), (r * active).reshape(-1)
+
+
+def relaxed_contact_problem(model, env: _Env, tau, W_f_L):
+    """What ``RelaxedRigidContacts.compute_contact_forces`` assembles before the solver
+    (``relaxed_rigid.py:283-398``): A = J M^-1 J' + diag(r), b = J nu_dot_free + J_dot nu - a_ref,
+    with the rows of inactive points zeroed."""
+    W_p_C, W_pd_C = O.collidable_points_pos_vel(model, env.W_H_L[None], env.W_v_WL[None])
+    W_p_C, W_pd_C = W_p_C[0], W_pd_C[0]
+    en = _enabled(model)[0]
+    W_p_C, W_pd_C = W_p_C[en], W_pd_C[en]
+    delta, _, n_hat = O.compute_penetration_data(model, W_p_C, W_pd_C)
+    pos = -delta[:, None] * n_hat
+    body = np.asarray(model.kin_dyn_parameters.contact_parameters.body, dtype=int)[en]
+    a_ref, r = relaxed_regularizers(model, body, pos, W_pd_C)
+    BW_nu = env.generalized_velocity("mixed")
+    vd_free, sdd_free = aba_mixed(model, env, tau, W_f_L)
+    BW_nud_free = np.concatenate([vd_free, sdd_free])
+    Minv = mass_matrix_inverse_mixed(model, env)
+    act = (delta > 0)[:, None, None]
+    Jl = (contact_jacobian_mixed(model, env, "mixed")[:, 0:3, :] * act).reshape(-1, BW_nu.shape[0])
+    Jdl = (contact_jacobian_derivative_mixed(model, env)[:, 0:3, :] * act).reshape(-1, BW_nu.shape[0])
+    A = Jl @ Minv @ Jl.T + np.diag(r)
+    b = Jl @ BW_nud_free + Jdl @ BW_nu - a_ref
+    return dict(A=A, b=b, active=delta > 0)
+
+
+def relaxed_compute_contact_forces(model, env: _Env, tau, W_f_L):
+    """``RelaxedRigidContacts.compute_contact_forces`` -> W_f_C (nc,6) inertial-fixed.  The
+    reference minimises |A x + b|^2 with L-BFGS started from forces that are zero on the
+    inactive points (``relaxed_rigid.py:465-505``); the minimiser is x = -A^-1 b on the active
+    block (A is positive definite there: Delassus + positive diagonal) and zero elsewhere --
+    parity is defined on that optimum, like for the rigid QP."""
+    pr = relaxed_contact_problem(model, env, tau, W_f_L)
+    A, b, act = pr["A"], pr["b"], pr["active"]
+    x = np.zeros_like(b)
+    sel = np.repeat(act, 3)
+    if sel.any():
+        x[sel] = -np.linalg.solve(A[np.ix_(sel, sel)], b[sel])
+    CW_fl = x.reshape(-1, 3).astype(env.s.dtype)
+    W_H_C = contact_transforms(model, env)
+    f6 = np.zeros((CW_fl.shape[0], 6), dtype=env.s.dtype)
+    f6[:, 0:3] = CW_fl
+    return O.other_representation_to_inertial(f6, "mixed", W_H_C, is_force=True)
+
+
 def compute_impact_velocity(inactive, M, J_WC, nu):
     """``RigidContacts.compute_impact_velocity`` (``rigid.py:163-220``)."""
     Jl = J_WC[:, 0:3, :].copy()
@@ -556,7 +632,8 @@ def link_contact_forces(model, data, W_f_L_external, tau_total):
     B = data.joint_positions.shape[0]
     out = np.zeros_like(W_f_L_external)
     for b in range(B):
-        W_f_C = compute_contact_forces(model, _Env(data, b), tau_total[b], W_f_L_external[b])
+        fn = relaxed_compute_contact_forces if model.contact_model == "relaxed" else compute_contact_forces
+        W_f_C = fn(model, _Env(data, b), tau_total[b], W_f_L_external[b])
         out[b] = O.link_forces_from_contact_forces(model, W_f_C[None])[0]
     return out
 
@@ -574,7 +651,7 @@ def step(model, data, link_forces_inertial=None, joint_force_references=None):
     if nc > 0:
         W_f_total = W_f + link_contact_forces(model, data, W_f, tau_total).astype(dtype)
     data_tf = _integrate(model, data, W_f_total, tau_total)
-    if nc > 0:
+    if nc > 0 and model.contact_model != "relaxed":  # RelaxedRigid: no impact step (relaxed_rigid.py:262-281)
         data_tf = update_velocity_after_impact(model, data_tf)
     return data_tf
 

@@ -48,6 +48,19 @@ CASES = [
     dict(id="icub_rigid_contact", seed=22, contact="rigid", in_contact=True, tau=True, **_ICUB),
     dict(id="icub_rigid_flat", seed=23, contact="rigid", in_contact="flat", tau=True, model="icub_like", B=2),
     dict(id="ergocub_rigid_flat", model="ergocub_like", B=2, seed=24, contact="rigid", in_contact="flat", tau=True),
+    # ---- relaxed-rigid contacts (the contact model of the reference's own step benchmark)
+    dict(id="box_relaxed_air", model="box", B=2, seed=25, contact="relaxed"),
+    dict(id="box_relaxed_contact", model="box", B=4, seed=26, contact="relaxed", in_contact=True),
+    dict(id="box_relaxed_flat", model="box", B=4, seed=27, contact="relaxed", in_contact="flat"),
+    dict(id="box_relaxed_flat_params", model="box", B=3, seed=28, contact="relaxed", in_contact="flat",
+         contact_params=dict(time_constant=0.01, damping_coefficient=0.8, d_min=0.7, d_max=0.9, width=0.004, midpoint=0.4,
+                             power=3.0, mu=0.5)),
+    dict(id="sphere_relaxed_contact", model="sphere", B=2, seed=29, contact="relaxed", in_contact=True),
+    dict(id="icub_relaxed_contact", seed=30, contact="relaxed", in_contact=True, tau=True, **_ICUB),
+    dict(id="icub_relaxed_flat", seed=31, contact="relaxed", in_contact="flat", tau=True, model="icub_like", B=2),
+    dict(id="icub_relaxed_fext_mixed", seed=32, contact="relaxed", in_contact="flat", tau=True, fext=True, velrepr="mixed",
+         model="icub_like", B=2),
+    dict(id="ergocub_relaxed_flat", model="ergocub_like", B=2, seed=33, contact="relaxed", in_contact="flat", tau=True),
 ]
 
 DEFAULTS = dict(contact="soft", contact_params=None, actuation=None, integrator="semi_implicit_euler", in_contact=False,

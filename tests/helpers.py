@@ -7,7 +7,7 @@ import numpy as np
 
 import jaxsim_b200.api as js
 from jaxsim_b200 import models
-from jaxsim_b200.rbda.contacts import RigidContacts, SoftContacts
+from jaxsim_b200.rbda.contacts import RelaxedRigidContacts, RigidContacts, SoftContacts
 from oracle import jaxsim_oracle as O
 
 # north_star tolerances: 1e-5 rel (fp64) / 1e-3 rel (fp32)
@@ -21,13 +21,13 @@ def build_model(name: str, **kw):
 def build_model_for_case(case: dict):
     """Product model of a golden-fixture case (tests/golden/cases.py)."""
     from jaxsim_b200.rbda.actuation import ActuationParams
-    from jaxsim_b200.rbda.contacts import RigidContactsParams, SoftContactsParams
+    from jaxsim_b200.rbda.contacts import RelaxedRigidContactsParams, RigidContactsParams, SoftContactsParams
 
-    rigid = case["contact"] == "rigid"
-    cm = RigidContacts.build() if rigid else SoftContacts.build()
-    cp = None
-    if case["contact_params"]:
-        cp = (RigidContactsParams if rigid else SoftContactsParams).build(**case["contact_params"])
+    kinds = {"soft": (SoftContacts, SoftContactsParams), "rigid": (RigidContacts, RigidContactsParams),
+             "relaxed": (RelaxedRigidContacts, RelaxedRigidContactsParams)}
+    cm_cls, cp_cls = kinds[case["contact"]]
+    cm = cm_cls.build()
+    cp = cp_cls.build(**case["contact_params"]) if case["contact_params"] else None
     ap = ActuationParams(**case["actuation"]) if case["actuation"] else None
     integ = {"semi_implicit_euler": js.model.IntegratorType.SemiImplicitEuler, "rk4": js.model.IntegratorType.RungeKutta4}[case["integrator"]]
     return build_model(case["model"], time_step=case["time_step"], contact_model=cm, contact_params=cp,
@@ -38,15 +38,19 @@ def oracle_model(model) -> O.OracleModel:
     prm = model.contact_params
     soft = isinstance(model.contact_model, SoftContacts)
     rigid = isinstance(model.contact_model, RigidContacts)
+    relaxed = isinstance(model.contact_model, RelaxedRigidContacts)
     kw = dict(K=prm.K, D=prm.D, mu=prm.mu)
     if soft:
         kw.update(p=prm.p, q=prm.q)
     if rigid:
         kw.update(regularization_delassus=model.contact_model.regularization_delassus)
+    if relaxed:
+        kw.update(relaxed=dict(time_constant=prm.time_constant, damping_coefficient=prm.damping_coefficient, d_min=prm.d_min,
+                               d_max=prm.d_max, width=prm.width, midpoint=prm.midpoint, power=prm.power))
     return O.OracleModel(
         kin_dyn_parameters=model.kin_dyn_parameters, floating_base=model.floating_base(),
         time_step=model.time_step, gravity=model.gravity, terrain_height=model.terrain.height(),
-        contact_model="soft" if soft else ("rigid" if rigid else "none"),
+        contact_model="soft" if soft else ("rigid" if rigid else ("relaxed" if relaxed else "none")),
         torque_max=model.actuation_params.torque_max, omega_th=model.actuation_params.omega_th,
         omega_max=model.actuation_params.omega_max, enable_friction=model.actuation_params.enable_friction,
         **kw,
