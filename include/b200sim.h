@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define B200SIM_ABI_VERSION 2
+#define B200SIM_ABI_VERSION 3
 
 #define B200SIM_DTYPE_F32 0
 #define B200SIM_DTYPE_F64 1
@@ -37,6 +37,7 @@ extern "C" {
 #define B200SIM_CONTACT_NONE 0
 #define B200SIM_CONTACT_SOFT 1 /* rbda/contacts/soft.py */
 #define B200SIM_CONTACT_RIGID 2 /* rbda/contacts/rigid.py (b200sim_step only; floating base; enabled points a prefix) */
+#define B200SIM_CONTACT_RELAXED_RIGID 3 /* rbda/contacts/relaxed_rigid.py (same restrictions as RIGID) */
 
 #define B200SIM_E_INVALID (-1)     /* NULL / negative size / bad dtype */
 #define B200SIM_E_UNSUPPORTED (-2) /* valid in the reference, not implemented here */
@@ -87,6 +88,10 @@ typedef struct B200SimModelDesc {
   double torque_max, omega_th, omega_max;
   /* RigidContacts.regularization_delassus (rbda/contacts/rigid.py:99-101), default 1e-6 */
   double rigid_regularization;
+  /* RelaxedRigidContactsParams (rbda/contacts/relaxed_rigid.py:30-82); the friction coefficient
+   * travels in soft_mu.  Ignored unless contact_model == B200SIM_CONTACT_RELAXED_RIGID. */
+  double relaxed_time_constant, relaxed_damping_coefficient, relaxed_d_min, relaxed_d_max, relaxed_width,
+      relaxed_midpoint, relaxed_power;
 } B200SimModelDesc;
 
 typedef struct B200SimModel B200SimModel;

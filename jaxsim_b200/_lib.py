@@ -60,10 +60,13 @@ class B200SimModelDesc(C.Structure):
         ("omega_th", C.c_double),
         ("omega_max", C.c_double),
         ("rigid_regularization", C.c_double),
+        ("relaxed_time_constant", C.c_double), ("relaxed_damping_coefficient", C.c_double), ("relaxed_d_min", C.c_double),
+        ("relaxed_d_max", C.c_double), ("relaxed_width", C.c_double), ("relaxed_midpoint", C.c_double),
+        ("relaxed_power", C.c_double),
     ]
 
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 OPT_TMA_STORE = 1
 OPT_RIGID_QP_F32 = 2
 OPT_GENERIC_KERNEL = 4

@@ -27,7 +27,8 @@ import torch
 from jaxsim_b200 import _lib
 from jaxsim_b200.parsers.urdf import build_kin_dyn_parameters
 from jaxsim_b200.rbda.actuation import ActuationParams
-from jaxsim_b200.rbda.contacts import RigidContacts, RigidContactsParams, SoftContacts, SoftContactsParams
+from jaxsim_b200.rbda.contacts import (RelaxedRigidContacts, RelaxedRigidContactsParams, RigidContacts,
+                                        RigidContactsParams, SoftContacts, SoftContactsParams)
 from jaxsim_b200.terrain import FlatTerrain
 
 from . import data as _data
@@ -73,6 +74,7 @@ class _DeviceModel:
         if n > 0:
             axis[1:] = kd.joint_model.joint_axis
         reg = 1e-6
+        rx = RelaxedRigidContactsParams()
         prm = model.contact_params if isinstance(model.contact_params, SoftContactsParams) else SoftContactsParams()
         if model.contact_model is None or nc == 0:
             cm = 0
@@ -84,6 +86,10 @@ class _DeviceModel:
             # the descriptor's soft_K / soft_D / soft_mu slots carry the rigid K / D / mu (include/b200sim.h)
             prm = SoftContactsParams(K=rp.K, D=rp.D, mu=rp.mu)
             reg = float(model.contact_model.regularization_delassus)
+        elif isinstance(model.contact_model, RelaxedRigidContacts):
+            cm = 3
+            rx = model.contact_params if isinstance(model.contact_params, RelaxedRigidContactsParams) else RelaxedRigidContactsParams()
+            prm = SoftContactsParams(K=rx.K, D=rx.D, mu=rx.mu)  # the friction coefficient travels in soft_mu
         else:
             raise NotImplementedError(f"contact model {type(model.contact_model).__name__} is not implemented")
         jp = kd.joint_parameters
@@ -107,6 +113,9 @@ class _DeviceModel:
             soft_K=prm.K, soft_D=prm.D, soft_mu=prm.mu, soft_p=prm.p, soft_q=prm.q,
             torque_max=model.actuation_params.torque_max, omega_th=model.actuation_params.omega_th,
             omega_max=model.actuation_params.omega_max, rigid_regularization=reg,
+            relaxed_time_constant=rx.time_constant, relaxed_damping_coefficient=rx.damping_coefficient,
+            relaxed_d_min=rx.d_min, relaxed_d_max=rx.d_max, relaxed_width=rx.width, relaxed_midpoint=rx.midpoint,
+            relaxed_power=rx.power,
         )
         handle = C.c_void_p()
         _lib.check(lib.b200sim_model_create(C.byref(d), int(device_index), C.byref(handle)), "b200sim_model_create")
@@ -399,12 +408,12 @@ def _step_impl(model, data, n_steps, link_forces, joint_force_references, update
 
     # the cached kinematics of the input state spare the kernel a sincos + FK pass
     Hin = Vin = None
-    if isinstance(model.contact_model, RigidContacts) and nc > 0:
+    if isinstance(model.contact_model, (RigidContacts, RelaxedRigidContacts)) and nc > 0:
         # RigidContacts READS the cached link velocities on purpose: after an impact they are the
         # pre-impact ones (rbda/contacts/rigid.py:429-434 never refreshes them) and the reference's
         # penetration rate / Jacobian-derivative term use them (api/contact.py:39-43,470-477)
         if n_steps != 1:
-            raise NotImplementedError("step_n is not available with RigidContacts")
+            raise NotImplementedError("step_n is not available with RigidContacts / RelaxedRigidContacts")
         if use_input_caches and data._link_transforms is not None and data._link_velocities is not None:
             Hin = _batched(data._link_transforms, 3).to(dtype).contiguous()
             Vin = _batched(data._link_velocities, 2).to(dtype).contiguous()

@@ -39,6 +39,7 @@ struct B200SimModel {
       o_pt_start = 0, o_pt_idx = 0, o_pt_body = 0, o_pt_enabled = 0, o_anc = 0, o_ldepth = 0;
   int o_rows8 = 0, n_rows8 = 0, o_rows16 = 0, n_rows16 = 0;  // packed level-walk rows for G = 8 / 16 (0 rows: not available)
   double reg = 1e-6;
+  double rx_tc = 0.02, rx_zeta = 1.0, rx_dmin = 0.9, rx_dmax = 0.95, rx_width = 1e-3, rx_mid = 0.5, rx_pow = 2.0;  // RelaxedRigid
   unsigned long long* dbg_d = nullptr;  // debug counters, allocated by b200sim_debug_counters
   int* rigid_scratch = nullptr;      // work lists of the rigid-contact cascade
   long long rigid_scratch_cap = 0;
@@ -193,6 +194,8 @@ void fill_model_params(const B200SimModel* m, Params<T>& P) {
   P.o_anc = m->o_anc; P.o_ldepth = m->o_ldepth; P.reg = (T)m->reg;
   P.o_rows8 = m->o_rows8; P.n_rows8 = m->n_rows8; P.o_rows16 = m->o_rows16; P.n_rows16 = m->n_rows16;
   P.dbg = m->dbg_d;
+  P.rx_tc = (T)m->rx_tc; P.rx_zeta = (T)m->rx_zeta; P.rx_dmin = (T)m->rx_dmin; P.rx_dmax = (T)m->rx_dmax;
+  P.rx_width = (T)m->rx_width; P.rx_mid = (T)m->rx_mid; P.rx_pow = (T)m->rx_pow;
   P.dt = (T)m->dt; P.g = (T)m->g; P.h_terrain = (T)m->h_terrain;
   P.K = (T)m->K; P.D = (T)m->D; P.mu = (T)m->mu; P.pexp = (T)m->pexp; P.qexp = (T)m->qexp;
   P.tau_max = (T)m->tau_max; P.w_th = (T)m->w_th; P.w_max = (T)m->w_max;
@@ -441,7 +444,7 @@ int step_t(const B200SimModel* m, int dtype, int64_t B, const void* s, const voi
   if ((m->opt_flags & B200SIM_OPT_BULK_IN) && Hin && Vin && ((uintptr_t)Hin % 16 == 0) && ((uintptr_t)Vin % 16 == 0) && (((size_t)m->nL * 6 * sizeof(T)) % 16 == 0))
     P.flags |= F_BULK_IN;
   P.mode = MODE_STEP;
-  if (m->contact_model == B200SIM_CONTACT_RIGID && m->nc > 0) {
+  if (m->contact_model >= B200SIM_CONTACT_RIGID && m->nc > 0) {
     if (nsteps != 1) return B200SIM_E_UNSUPPORTED;
     return launch_rigid(m, P, dtype, stream);
   }
@@ -531,9 +534,9 @@ int b200sim_model_create(const B200SimModelDesc* d, int device, B200SimModel** o
     return B200SIM_E_INVALID;
   if (nc > 0 && (!d->point_body || !d->point_position || !d->point_enabled)) return B200SIM_E_INVALID;
   if (d->contact_model != B200SIM_CONTACT_NONE && d->contact_model != B200SIM_CONTACT_SOFT &&
-      d->contact_model != B200SIM_CONTACT_RIGID)
+      d->contact_model != B200SIM_CONTACT_RIGID && d->contact_model != B200SIM_CONTACT_RELAXED_RIGID)
     return B200SIM_E_UNSUPPORTED;
-  if (d->contact_model == B200SIM_CONTACT_RIGID && nc > 0) {
+  if (d->contact_model >= B200SIM_CONTACT_RIGID && nc > 0) {
     // rigid.py:401-409 indexes the enabled subset twice: only a prefix makes that the identity
     bool seen_disabled = false;
     for (int k = 0; k < nc; ++k) {
@@ -561,6 +564,8 @@ int b200sim_model_create(const B200SimModelDesc* d, int device, B200SimModel** o
   m->K = d->soft_K; m->D = d->soft_D; m->mu = d->soft_mu; m->pexp = d->soft_p; m->qexp = d->soft_q;
   m->tau_max = d->torque_max; m->w_th = d->omega_th; m->w_max = d->omega_max;
   m->reg = d->rigid_regularization;
+  m->rx_tc = d->relaxed_time_constant; m->rx_zeta = d->relaxed_damping_coefficient; m->rx_dmin = d->relaxed_d_min;
+  m->rx_dmax = d->relaxed_d_max; m->rx_width = d->relaxed_width; m->rx_mid = d->relaxed_midpoint; m->rx_pow = d->relaxed_power;
 
   // ---- per-link constants
   m->cst_h.assign((size_t)nL * CREC, 0.0);
@@ -668,7 +673,7 @@ int b200sim_model_create(const B200SimModelDesc* d, int device, B200SimModel** o
   m->o_pt_idx = push(pt_idx.data(), pt_idx.size());
   m->o_pt_body = push(d->point_body, nc);
   m->o_pt_enabled = push(d->point_enabled, nc);
-  if (d->contact_model == B200SIM_CONTACT_RIGID && nc > 0) {
+  if (d->contact_model >= B200SIM_CONTACT_RIGID && nc > 0) {
     // ancestors of every link, root's child first, the link itself last
     std::vector<int> anc((size_t)nL * std::max(maxd, 1), 0);
     for (int i = 1; i < nL; ++i) {
@@ -929,7 +934,7 @@ int b200sim_step_jvp(B200SimModel* m, int64_t B, int32_t nsteps, const double* l
                      const void* sd, const void* q, const void* vlin, const void* omega, const void* p, const void* mt,
                      const void* tau, void* s_o, void* sd_o, void* q_o, void* vlin_o, void* omega_o, void* p_o,
                      void* m_o, void* W_H_B, void* iXl, void* W_H_L, void* W_v, void* stream) {
-  if (m && m->contact_model == B200SIM_CONTACT_RIGID && m->nc > 0) return B200SIM_E_UNSUPPORTED;
+  if (m && m->contact_model >= B200SIM_CONTACT_RIGID && m->nc > 0) return B200SIM_E_UNSUPPORTED;
   if (!m || B < 0 || nsteps < 1) return B200SIM_E_INVALID;
   if (B == 0) return 0;
   if (!q || !vlin || !omega || !p || !q_o || !vlin_o || !omega_o || !p_o) return B200SIM_E_INVALID;
@@ -978,7 +983,7 @@ int b200sim_dynamics(const B200SimModel* m, int dtype, int64_t B, const void* s,
                      const void* vlin, const void* omega, const void* p, const void* mt, const void* tau,
                      const void* fext, void* pd, void* qd, void* W_vd, void* sdd, void* md, void* stream) {
   if (!m || B < 0 || (dtype != 0 && dtype != 1)) return B200SIM_E_INVALID;
-  if (m->contact_model == B200SIM_CONTACT_RIGID && m->nc > 0) return B200SIM_E_UNSUPPORTED;
+  if (m->contact_model >= B200SIM_CONTACT_RIGID && m->nc > 0) return B200SIM_E_UNSUPPORTED;
   if (B == 0) return 0;
   if (!q || !vlin || !omega || !p || !W_vd) return B200SIM_E_INVALID;
   if (m->n > 0 && (!s || !sd || !sdd)) return B200SIM_E_INVALID;

@@ -125,6 +125,7 @@ struct Params {
   int o_rows8, n_rows8, o_rows16, n_rows16;  // packed level-walk rows (specialised step kernel), see b200sim_model_create
   T dt, g, h_terrain, K, D, mu, pexp, qexp, tau_max, w_th, w_max;
   T reg;                // rigid contacts: Delassus regularisation
+  T rx_tc, rx_zeta, rx_dmin, rx_dmax, rx_width, rx_mid, rx_pow;  // relaxed-rigid contacts (relaxed_rigid.py:30-82)
   // ---- batch
   long long B;
   const T *s, *sd, *q, *vlin, *omega, *p, *m, *tau, *fext;
@@ -645,7 +646,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
   const bool floating = SPEC ? true : (P.floating != 0);
   const bool with_contacts = (mode == MODE_STEP) || (mode == MODE_DYN);
   const bool soft = SPEC ? (nc > 0) : (with_contacts && (P.contact_model == 1) && nc > 0);
-  const bool rigid = SPEC ? false : ((mode == MODE_STEP) && (P.contact_model == 2) && nc > 0);
+  const bool rigid = SPEC ? false : ((mode == MODE_STEP) && (P.contact_model >= 2) && nc > 0);  // rigid (2) or relaxed-rigid (3)
   const bool tma = (flags & F_TMA_STORE) != 0;
 
   // the number of loop trips is uniform across the block so that __syncwarp() is safe
@@ -1658,9 +1659,10 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
           B200SIM_PHASE_MARK(15);
         }
       }
-      if (rigid) {
+      if (rigid && P.contact_model == 2) {
         // a point below the ground at t+dt: the impact (rigid.py:385-436) is left to the rigid
         // kernel, which starts from the pre-impact result this kernel has just stored
+        // (the relaxed-rigid model has no impact step, relaxed_rigid.py:262-281)
         bool touch = false;
         for (int k = lane; k < nc; k += G) {
           const T* rb = ws + (size_t)pt_body[k] * REC;

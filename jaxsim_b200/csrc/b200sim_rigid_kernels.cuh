@@ -484,6 +484,7 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
   int* clist = alist + nc;                          // [nL] links that carry active points
   int* perm = clist + nL;                           // [3 nc] pivot order of the impact solve
   const T dt = P.dt;
+  const bool relaxed = P.contact_model == 3;  // RelaxedRigidContacts: same assembly, a linear solve, no impact
   const long long stride = (long long)gridDim.x * P.envs_per_block;
 
   // work items: every environment of the batch, or the list produced by the previous level of
@@ -636,7 +637,34 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
           }
           const T ddot = -ps[2];
           cross3(v + 3, ps, bv);                       // omega x pdot  (api/contact.py:470-477 term)
-          bv[2] -= P.K * delta + P.D * ddot;           // Baumgarte, n = z (rigid.py:527-539)
+          if (!relaxed) {
+            bv[2] -= P.K * delta + P.D * ddot;         // Baumgarte, n = z (rigid.py:527-539)
+          } else {
+            // RelaxedRigidContacts._regularizers (relaxed_rigid.py:533-653), FlatTerrain: the position in
+            // the constraint frame is (0, 0, -delta); impedance per COMPONENT as the reference evaluates it
+            // (imp_x = |pos| / width is a 3-vector); K, D derive from the time constant (:585-591)
+            const T xmax = P.rx_dmax, xmin = P.rx_dmin;
+            const T Kc = T(1) / ((xmax * P.rx_tc * P.rx_zeta) * (xmax * P.rx_tc * P.rx_zeta));
+            const T Dc = T(2) / (xmax * P.rx_tc);
+            const T mu2 = P.mu * P.mu;
+            const T imass = T(1) / sm_cst[(size_t)bi * CREC + C_MASS];
+            const T posv[3] = {T(0), T(0), -delta};
+            T rr3[3];
+#pragma unroll
+            for (int c3 = 0; c3 < 3; ++c3) {
+              const T ix = abs_t(posv[c3]) / P.rx_width;
+              T iy;
+              if (ix < P.rx_mid) iy = pow_t(ix, P.rx_pow) / pow_t(P.rx_mid, P.rx_pow - T(1));
+              else iy = T(1) - pow_t(max_t(T(1) - ix, T(0)), P.rx_pow) / pow_t(T(1) - P.rx_mid, P.rx_pow - T(1));
+              T xi = xmin + iy * (xmax - xmin);
+              xi = min_t(max_t(xi, xmin), xmax);
+              if (ix > T(1)) xi = xmax;
+              const T aref = -(Dc * ps[c3] + Kc * xi * posv[c3]);
+              bv[c3] -= aref;                          // b = J nu_dot_free + J_dot nu - a_ref (:386-391)
+              rr3[c3] = (T(2) * mu2 * (T(1) - xi) / (xi + T(1e-12))) * (T(1) + mu2) * imass;
+            }
+            stn<3>(pw + RP_F, rr3);                    // diagonal regulariser, consumed right after delassus()
+          }
         }
         stn<3>(pw + RP_B, bv);
         aidx[k] = act ? 1 : 0;
@@ -1147,13 +1175,32 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
         q[3 * a + 1] = S(val[1] + acc[1] + bv[1]);
         q[3 * a + 2] = S(val[2] + acc[2] + P.g + bv[2]);
       }
-      delassus(na, S(P.reg));
-      const int qp_it = qp_pyramids<S>(Qp, Hp, vN, vM, na, S(P.mu), lane);
-      if (P.dbg && lane == 0) {
-        atomicAdd(P.dbg + 0, (unsigned long long)qp_it);
-        atomicAdd(P.dbg + 1, 1ull);
-        atomicMax(P.dbg + 2, (unsigned long long)qp_it);
-        atomicAdd(P.dbg + 3, (unsigned long long)na);
+      if (!relaxed) {
+        delassus(na, S(P.reg));
+        const int qp_it = qp_pyramids<S>(Qp, Hp, vN, vM, na, S(P.mu), lane);
+        if (P.dbg && lane == 0) {
+          atomicAdd(P.dbg + 0, (unsigned long long)qp_it);
+          atomicAdd(P.dbg + 1, 1ull);
+          atomicMax(P.dbg + 2, (unsigned long long)qp_it);
+          atomicAdd(P.dbg + 3, (unsigned long long)na);
+        }
+      } else {
+        // RelaxedRigid (relaxed_rigid.py:380-505): the reference minimises |A x + b|^2, A = Delassus + diag(r),
+        // with L-BFGS; A is positive definite on the active points, so the minimiser is x = -A^-1 b:
+        // one pivoted Cholesky solve instead of the interior-point iteration of the rigid model.
+        delassus(na, S(0));
+        const int N = 3 * na;
+        S* lam = vN;
+        for (int a = lane; a < na; a += 32) {
+          const T* pw = pts + (size_t)alist[a] * RPT;
+#pragma unroll
+          for (int c3 = 0; c3 < 3; ++c3) {
+            Qp[pidx(3 * a + c3, 3 * a + c3)] += S(pw[RP_F + c3]);
+            lam[3 * a + c3] = -q[3 * a + c3];
+          }
+        }
+        __syncwarp();
+        psd_solve_pivoted<S>(Qp, Hp, vN + 5 * N, lam, vN + N, perm, N, S(sizeof(S) == 8 ? 1e-14 : 1e-7), lane);
       }
       for (int a = lane; a < na; a += 32) {
         T* pw = pts + (size_t)alist[a] * RPT;
@@ -1254,7 +1301,7 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
     }
 
     // impact (rigid.py:385-436): project nu onto {velocity of the active points = 0}
-    const int na2 = contact_points(true);
+    const int na2 = relaxed ? 0 : contact_points(true);  // RelaxedRigid: no impact step (relaxed_rigid.py:262-281)
     if (na2 > cap) {
       // next level applies the impact to the pre-impact result, which must then be complete
       if (!impact_only) {

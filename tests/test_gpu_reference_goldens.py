@@ -71,7 +71,7 @@ def test_step_matches_reference(cid, dtype, cuda_device):
                         joint_force_references=t(z["in_tau"]) if case["tau"] else None)
     assert out.velocity_representation == data.velocity_representation
     soft = case["contact"] == "soft"
-    floors = _vel_floors(z) if case["contact"] == "rigid" else None
+    floors = _vel_floors(z) if case["contact"] in ("rigid", "relaxed") else None
     H.compare_data(out, _Ref(z, soft), H.RTOL[dtype], f"golden {cid} {dtype}", floors=floors)
 
 

@@ -206,3 +206,51 @@ def test_rigid_more_active_points_than_the_fast_workspace(cuda_device):
     pd = H.to_product(model, od, torch.float64, cuda_device)
     out = js.model.step(model, pd)
     H.compare_data(out, ref, 1e-5, "rigid 32 active points", floors=_vel_floors(od))
+
+
+# ------------------------------------------------------------------------------------------
+# RelaxedRigidContacts (rbda/contacts/relaxed_rigid.py): same assembly as the rigid model, the
+# contact forces are the solution of (Delassus + diag(r)) x = -b on the active points, no impact
+# ------------------------------------------------------------------------------------------
+def _relaxed_model(name, **params):
+    from jaxsim_b200.rbda.contacts import RelaxedRigidContacts, RelaxedRigidContactsParams
+
+    return H.build_model(name, contact_model=RelaxedRigidContacts.build(), contact_params=RelaxedRigidContactsParams.build(**params))
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("mode", [False, True, "flat"])
+@pytest.mark.parametrize("name,B", [("box", 16), ("icub_like", 8), ("ergocub_like", 4)])
+def test_relaxed_rigid_step(name, B, mode, dtype, cuda_device):
+    import torch
+
+    model = _relaxed_model(name, mu=0.5)
+    om = H.oracle_model(model)
+    od = _inputs(om, B, 17, mode, dtype)
+    rng = np.random.default_rng(2)
+    tau = 10 * rng.uniform(size=(B, om.dofs())).astype(np.float32).astype(np.float64)
+    ref = R.step(om, od, joint_force_references=tau)
+    pd = H.to_product(model, od, _dtype(dtype), cuda_device)
+    out = js.model.step(model, pd, joint_force_references=torch.as_tensor(tau, dtype=_dtype(dtype), device=cuda_device))
+    assert not out.contact_state
+    H.compare_data(out, ref, H.RTOL[dtype], f"relaxed step {name} {mode} {dtype}", floors=_vel_floors(od))
+
+
+def test_relaxed_rigid_box_settles(cuda_device):
+    """A box dropped from 5 mm onto the ground under the relaxed-rigid model comes to rest on it
+    (the reference's own scenario for this model, tests/test_simulations.py:295-344): bounded
+    penetration, vanishing velocity."""
+    import torch
+
+    model = _relaxed_model("box", mu=0.5)
+    B = 8
+    p = torch.zeros(B, 3, dtype=torch.float64, device=cuda_device)
+    p[:, 2] = 0.05 + 0.005
+    data = js.data.JaxSimModelData.build(model, base_position=p, batch_size=B, dtype=torch.float64, device=cuda_device,
+                                         velocity_representation=js.common.VelRepr.Inertial)
+    for _ in range(600):
+        data = js.model.step(model, data)
+    z = data.base_position[:, 2].cpu().numpy()
+    v = data._base_linear_velocity.abs().max().item()
+    assert np.all(z < 0.05 + 1e-4) and np.all(z > 0.05 - 2e-3), z
+    assert v < 5e-3, v

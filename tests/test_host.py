@@ -99,8 +99,8 @@ def test_library_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(lib, sym), sym
     assert b"sm_100a" in lib.b200sim_version()
-    # descriptor layout: ctypes mirror == C struct (8 int32 + 17 pointers + 12 doubles)
-    assert ctypes.sizeof(_lib.B200SimModelDesc) == 8 * 4 + 17 * 8 + 12 * 8
+    # descriptor layout: ctypes mirror == C struct (8 int32 + 17 pointers + 19 doubles)
+    assert ctypes.sizeof(_lib.B200SimModelDesc) == 8 * 4 + 17 * 8 + 19 * 8
 
 
 def test_invalid_arguments_are_rejected_without_a_gpu():
