@@ -471,12 +471,17 @@ def run_b200(args):
                    "note": "step_n: state kept on chip, per-step HBM traffic = joint force references only; no caches written"}
 
     config3 = None
-    if args.config3:
-        from jaxsim_b200.rbda.contacts import RigidContacts, RigidContactsParams
+    relaxed3 = None
 
+    def time_contact_model(kind):
+        from jaxsim_b200.rbda.contacts import RelaxedRigidContacts, RelaxedRigidContactsParams, RigidContacts, RigidContactsParams
+
+        if kind == "rigid":
+            cm3, cp3 = RigidContacts.build(), RigidContactsParams.build(K=1e4, D=20.0)
+        else:  # the contact model of the reference's own step benchmark (tests/test_benchmark.py:143-152)
+            cm3, cp3 = RelaxedRigidContacts.build(), RelaxedRigidContactsParams.build(mu=0.5)
         m3 = js.model.JaxSimModel.build_from_model_description(
-            models.urdf("ergocub_like"), time_step=1e-3, contact_model=RigidContacts.build(),
-            contact_params=RigidContactsParams.build(K=1e4, D=20.0))
+            models.urdf("ergocub_like"), time_step=1e-3, contact_model=cm3, contact_params=cp3)
         B3 = args.c3_batch
         n3, nL3, nc3 = m3.dofs(), m3.number_of_links(), m3.number_of_collidable_points()
 
@@ -505,8 +510,9 @@ def run_b200(args):
             act = ((H[..., 2, 0:3] * Lp).sum(-1) + H[..., 2, 3] < 0).sum(dim=1).float().mean().item()
             return d1, act
 
-        config3 = {"config": "BASELINE configs[2]: ergocub_like (%d DoF, %d links, %d collidable points), RigidContacts, batch %d %s"
-                             % (n3, nL3, nc3, B3, args.dtype), "unit": "env-steps/s"}
+        config3 = {"config": "%s: ergocub_like (%d DoF, %d links, %d collidable points), %s, batch %d %s"
+                             % ("BASELINE configs[2]" if kind == "rigid" else "reference step benchmark (tests/test_benchmark.py:143-152)",
+                                n3, nL3, nc3, type(cm3).__name__, B3, args.dtype), "unit": "env-steps/s"}
         ring3 = 4
         for label in ("random", "standing"):
             if label == "random":
@@ -536,6 +542,11 @@ def run_b200(args):
                               "mean_active_points": act,
                               "inputs": "random_model_data (base 0.5-1 m above ground: mostly no contact)" if label == "random"
                               else "standing: level base, soles 2-5 mm into the ground"}
+        return config3
+
+    if args.config3:
+        config3 = time_contact_model("rigid")
+        relaxed3 = time_contact_model("relaxed")
 
     jvp = None
     if args.jvp:
@@ -627,6 +638,8 @@ def run_b200(args):
         line["config5_jvp"] = jvp
     if config3 is not None:
         line["config3_rigid"] = config3
+    if relaxed3 is not None:
+        line["relaxed_rigid"] = relaxed3
     emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -119,6 +119,14 @@ def run_case(case: dict) -> dict:
             data = dataclasses.replace(data, velocity_representation=vr)
         lf = inp["link_forces"][e] if case["fext"] else None
         tau = inp["tau"][e] if case["tau"] else None
+        if len(rm.kin_dyn_parameters.contact_parameters.body) > 0:
+            cpos, cvel = js.contact.collidable_point_kinematics(model=rm, data=data)
+            push("cp_position", cpos)
+            push("cp_velocity", cvel)
+            push("links_in_contact", np.asarray(js.contact.in_contact(model=rm, data=data), dtype=float))
+        else:
+            push("cp_position", np.zeros((0, 3)))
+            push("cp_velocity", np.zeros((0, 3)))
         new = js.model.step(model=rm, data=data, link_forces=lf, joint_force_references=tau)
         for leaf in STATE_LEAVES:
             push("out" + leaf, getattr(new, leaf))
@@ -142,6 +150,12 @@ def run_case(case: dict) -> dict:
                 for k in ("base_position", "base_quaternion", "joint_positions", "base_linear_velocity", "base_angular_velocity", "joint_velocities"):
                     push("ode_" + k, xdot[k])
                 push("ode_tangential_deformation", xdot["contact_state"]["tangential_deformation"])
+    # estimate_good_contact_parameters (api/contact.py:155-211): defaults, and the arguments of the
+    # reference's soft-contact rest test (tests/test_simulations.py:205-211)
+    for tag, kw in (("default", {}), ("tuned", dict(number_of_active_collidable_points_steady_state=4,
+                                                     static_friction_coefficient=1.0, damping_ratio=1.0, max_penetration=0.001))):
+        prm = js.contact.estimate_good_contact_parameters(model=rm, **kw)
+        outs[f"egcp_{tag}"] = [np.array([float(prm.K), float(prm.D), float(prm.mu)])]
     out = {k: np.stack(v) for k, v in outs.items()}
     out.update({"in_" + k: np.asarray(v) for k, v in inp.items()})
     out.update(kin_dyn_arrays(rm))

@@ -103,3 +103,25 @@ def test_rbda_matches_reference(cid, dtype, cuda_device):
         if not model.floating_base():
             M, ref = M[..., -model.dofs():, -model.dofs():], ref[..., 6:, 6:]
         assert H.rel_err(M, ref) <= rtol, name
+
+
+@pytest.mark.parametrize("cid", IDS)
+def test_contact_helpers_match_reference(cid, cuda_device):
+    """`js.contact.collidable_point_kinematics`, `in_contact` and `estimate_good_contact_parameters`
+    against the reference's (api/contact.py:18-45, 83-143, 155-211)."""
+    import torch
+
+    z, _ = _load(cid)
+    case = C.case(cid)
+    model = H.build_model_for_case(case)
+    data = _inputs(case, z, model, torch.float64, cuda_device)
+    pos, vel = js.contact.collidable_point_kinematics(model, data)
+    if z["cp_position"].size:
+        assert H.rel_err(pos.cpu().numpy(), z["cp_position"]) <= 1e-9
+        assert H.rel_err(vel.cpu().numpy(), z["cp_velocity"]) <= 1e-9
+        assert np.array_equal(js.contact.in_contact(model, data).cpu().numpy(), z["links_in_contact"] > 0.5)
+    for tag, kw in (("default", {}), ("tuned", dict(number_of_active_collidable_points_steady_state=4,
+                                                     static_friction_coefficient=1.0, damping_ratio=1.0, max_penetration=0.001))):
+        prm = js.contact.estimate_good_contact_parameters(model, device=cuda_device, **kw)
+        ref = z[f"egcp_{tag}"][0]
+        np.testing.assert_allclose([prm.K, prm.D, prm.mu], ref, rtol=1e-9)

@@ -156,3 +156,15 @@ def test_oracle_rbda_matches_reference(cid):
         for k in ("base_position", "base_quaternion", "joint_positions", "base_linear_velocity", "base_angular_velocity",
                   "joint_velocities", "tangential_deformation"):
             assert _rel(xd[k], z["ode_" + k], 1e-9) <= 1e-9, k
+
+
+@pytest.mark.parametrize("cid", IDS)
+def test_oracle_collidable_point_kinematics_match_reference(cid):
+    z, _ = _load(cid)
+    case = C.case(cid)
+    pm, om, _ = _models(case)
+    od = _oracle_data(om, z)
+    W_p, W_pd = O.collidable_points_pos_vel(om, od.link_transforms, od.link_velocities)
+    en = [k for k, e in enumerate(pm.kin_dyn_parameters.contact_parameters.enabled) if e]
+    assert _rel(W_p[:, en], z["cp_position"]) <= 1e-9
+    assert _rel(W_pd[:, en], z["cp_velocity"], 1e-9) <= 1e-9
