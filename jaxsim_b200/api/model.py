@@ -697,6 +697,40 @@ def free_floating_mass_matrix(model: JaxSimModel, data: "_data.JaxSimModelData")
     return M.squeeze(0) if data._joint_positions.dim() == 1 else M
 
 
+def free_floating_bias_forces(model: JaxSimModel, data: "_data.JaxSimModelData") -> torch.Tensor:
+    """``js.model.free_floating_bias_forces`` (``src/jaxsim/api/model.py:1934-1979``): h(q, nu) =
+    inverse dynamics with zero accelerations and no external forces, ``(B, 6+n)`` in the data's
+    velocity representation."""
+    f, tau = inverse_dynamics(model, data)
+    return torch.cat([f, tau], dim=-1)
+
+
+def free_floating_gravity_forces(model: JaxSimModel, data: "_data.JaxSimModelData") -> torch.Tensor:
+    """``js.model.free_floating_gravity_forces`` (``:1896-1931``): g(q) = h(q, 0)."""
+    d0 = data.copy()
+    for leaf in ("_joint_velocities", "_base_linear_velocity", "_base_angular_velocity"):
+        setattr(d0, leaf, torch.zeros_like(getattr(data, leaf)))
+    f, tau = inverse_dynamics(model, d0)
+    return torch.cat([f, tau], dim=-1)
+
+
+def free_floating_mass_matrix_inverse(model: JaxSimModel, data: "_data.JaxSimModelData") -> torch.Tensor:
+    """``js.model.free_floating_mass_matrix_inverse`` (``:1595-1631``).  The reference propagates
+    articulated inertias (``rbda/mass_inverse.py``); M is symmetric positive definite, so this is
+    ``inv(free_floating_mass_matrix)`` up to rounding (one batched Cholesky-based inverse)."""
+    M = free_floating_mass_matrix(model, data)
+    if not model.floating_base():  # the base rows / columns are not degrees of freedom
+        Minv = torch.zeros_like(M)
+        Minv[..., 6:, 6:] = torch.linalg.inv(M[..., 6:, 6:])
+        return Minv
+    return torch.linalg.inv(M)
+
+
+def total_mass(model: JaxSimModel) -> float:
+    """``js.model.total_mass`` (``:1023-1035``)."""
+    return float(np.asarray(model.kin_dyn_parameters.link_parameters.mass).sum())
+
+
 _JVP_LEAVES = (
     ("joint_positions", "_joint_positions"), ("joint_velocities", "_joint_velocities"),
     ("base_quaternion", "_base_quaternion"), ("base_linear_velocity", "_base_linear_velocity"),

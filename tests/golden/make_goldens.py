@@ -145,6 +145,9 @@ def run_case(case: dict) -> dict:
                 push(f"rnea_base_force_{name}", fb)
                 push(f"rnea_joint_forces_{name}", tj)
                 push(f"mass_matrix_{name}", js.model.free_floating_mass_matrix(model=rm, data=d_r))
+                push(f"bias_forces_{name}", js.model.free_floating_bias_forces(model=rm, data=d_r))
+                push(f"gravity_forces_{name}", js.model.free_floating_gravity_forces(model=rm, data=d_r))
+                push(f"mass_matrix_inverse_{name}", js.model.free_floating_mass_matrix_inverse(model=rm, data=d_r))
             if soft and not case["fext"]:
                 xdot = js.ode.system_dynamics(model=rm, data=data, link_forces=None, joint_torques=inp["tau"][e])
                 for k in ("base_position", "base_quaternion", "joint_positions", "base_linear_velocity", "base_angular_velocity", "joint_velocities"):
