@@ -717,13 +717,9 @@ def free_floating_gravity_forces(model: JaxSimModel, data: "_data.JaxSimModelDat
 def free_floating_mass_matrix_inverse(model: JaxSimModel, data: "_data.JaxSimModelData") -> torch.Tensor:
     """``js.model.free_floating_mass_matrix_inverse`` (``:1595-1631``).  The reference propagates
     articulated inertias (``rbda/mass_inverse.py``); M is symmetric positive definite, so this is
-    ``inv(free_floating_mass_matrix)`` up to rounding (one batched Cholesky-based inverse)."""
-    M = free_floating_mass_matrix(model, data)
-    if not model.floating_base():  # the base rows / columns are not degrees of freedom
-        Minv = torch.zeros_like(M)
-        Minv[..., 6:, 6:] = torch.linalg.inv(M[..., 6:, 6:])
-        return Minv
-    return torch.linalg.inv(M)
+    ``inv(free_floating_mass_matrix)`` up to rounding (one batched inverse) -- of the full
+    ``(6+n, 6+n)`` matrix also for fixed-base models, like the reference."""
+    return torch.linalg.inv(free_floating_mass_matrix(model, data))
 
 
 def total_mass(model: JaxSimModel) -> float:

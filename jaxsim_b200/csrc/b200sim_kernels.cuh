@@ -158,7 +158,13 @@ template <> struct Lim<DualD> { static __device__ __forceinline__ DualD eps() { 
 
 __device__ __forceinline__ void sincos_t(float x, float* s, float* c) { sincosf(x, s, c); }
 __device__ __forceinline__ void sincos_t(double x, double* s, double* c) { sincos(x, s, c); }
-__device__ __forceinline__ float sqrt_t(float x) { return sqrtf(x); }
+// float: MUFU-based sqrt / reciprocal (about 1 ulp, far inside the 1e-3 float32 tolerance) instead of the IEEE
+// sequences (each ~15-20 dependent instructions on the latency-bound path); double stays IEEE
+__device__ __forceinline__ float sqrt_t(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ double sqrt_t(double x) { return sqrt(x); }
 __device__ __forceinline__ float pow_t(float x, float y) { return powf(x, y); }
 __device__ __forceinline__ double pow_t(double x, double y) { return pow(x, y); }
@@ -355,7 +361,7 @@ __device__ __forceinline__ void tma_load_bulk(void* smem_dst, const void* gsrc, 
 template <typename T>
 __device__ __forceinline__ void quat_to_dcm(const T* q, T* R) {
   const T nsq = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
-  const T k = T(2) / nsq;
+  const T k = T(2) * rcp_t(nsq);
   const T xx = q[1] * q[1] * k, yy = q[2] * q[2] * k, zz = q[3] * q[3] * k;
   const T xy = q[1] * q[2] * k, xz = q[1] * q[3] * k, yz = q[2] * q[3] * k;
   const T wx = q[0] * q[1] * k, wy = q[0] * q[2] * k, wz = q[0] * q[3] * k;
@@ -749,7 +755,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
       T den;
       if (mode == MODE_FK) den = (nrm == T(0)) ? T(1) : nrm;            // data.replace (api/data.py:441-447)
       else den = nrm + Lim<T>::eps() * (nrm == T(0) ? T(1) : T(0));       // base_orientation (api/data.py:283-285)
-      const T inv = T(1) / den;
+      const T inv = rcp_t(den);
 #pragma unroll
       for (int k = 0; k < 4; ++k) b.qn[k] = qr[k] * inv;
       quat_to_dcm(b.qn, b.R);
@@ -1046,19 +1052,19 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
             const bool nocontact = delta <= T(0);
             const bool sticking = nocontact || (ft0 * ft0 + ft1 * ft1 <= mufn * mufn);
             const T nrm = sqrt_t(ft0 * ft0 + ft1 * ft1);
-            const T idn = T(1) / (nrm + eps * (nrm == T(0) ? T(1) : T(0)));
+            const T idn = rcp_t(nrm + eps * (nrm == T(0) ? T(1) : T(0)));
             if (!sticking) {
               const T sc = min_t(mufn, nrm) * idn;
               ft0 *= sc; ft1 *= sc;
             }
             if (nocontact) { ft0 = T(0); ft1 = T(0); }
-            const T KoD = P.K / P.D;
+            const T KoD = P.K * rcp_t(P.D);
             if (nocontact) {
               md[0] = -KoD * m[0]; md[1] = -KoD * m[1]; md[2] = -KoD * m[2];
             } else if (sticking) {
               md[0] = pd[0]; md[1] = pd[1]; md[2] = -KoD * m[2];
             } else {
-              const T iD = T(1) / Ddq;
+              const T iD = rcp_t(Ddq);
               md[0] = -(ft0 + Kdp * m[0]) * iD; md[1] = -(ft1 + Kdp * m[1]) * iD; md[2] = T(0);
             }
             f[0] = ft0; f[1] = ft1; f[2] = fn;
@@ -1472,7 +1478,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
 #pragma unroll
         for (int rep = 0; rep < 2; ++rep) {
           const T nn = sqrt_t(qn2[0] * qn2[0] + qn2[1] * qn2[1] + qn2[2] * qn2[2] + qn2[3] * qn2[3]);
-          const T inv = T(1) / ((nn == T(0)) ? T(1) : nn);
+          const T inv = rcp_t((nn == T(0)) ? T(1) : nn);
 #pragma unroll
           for (int k = 0; k < 4; ++k) qn2[k] *= inv;
         }
@@ -1644,7 +1650,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
           // the next fused step starts like a fresh call: base_orientation normalises the
           // stored quaternion once more (api/data.py:283-285), bit-identical to repeated steps
           const T nrm = sqrt_t(b.qn[0] * b.qn[0] + b.qn[1] * b.qn[1] + b.qn[2] * b.qn[2] + b.qn[3] * b.qn[3]);
-          const T inv = T(1) / (nrm + Lim<T>::eps() * (nrm == T(0) ? T(1) : T(0)));
+          const T inv = rcp_t(nrm + Lim<T>::eps() * (nrm == T(0) ? T(1) : T(0)));
   #pragma unroll
           for (int k = 0; k < 4; ++k) b.qn[k] *= inv;
           quat_to_dcm(b.qn, b.R);

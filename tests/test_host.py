@@ -131,3 +131,34 @@ def test_product_path_has_no_cpu_fallback():
 def test_product_does_not_import_the_oracle():
     for p in (ROOT / "jaxsim_b200").rglob("*.py"):
         assert "oracle" not in p.read_text(), p
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): exactly ONE line on
+    stdout, valid JSON, with the keys of the contract."""
+    import json
+    import subprocess
+    import sys
+
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--batch", "256"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.split("\n") if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "env-steps/sec" and d["unit"] == "env-steps/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 1
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_relaxed_rigid_model_classes():
+    """RelaxedRigidContacts / Params mirror the reference's defaults (rbda/contacts/relaxed_rigid.py:30-82,186-194)."""
+    from jaxsim_b200.rbda.contacts import RelaxedRigidContacts, RelaxedRigidContactsParams
+
+    p = RelaxedRigidContactsParams.build()
+    assert (p.time_constant, p.damping_coefficient, p.d_min, p.d_max, p.width, p.midpoint, p.power, p.mu) == \
+        (0.02, 1.0, 0.9, 0.95, 0.001, 0.5, 2.0, 0.005)
+    assert p.valid() and not RelaxedRigidContactsParams.build(d_min=0.99, d_max=0.5).valid()
+    m = js.model.JaxSimModel.build_from_model_description(models.urdf("box"), contact_model=RelaxedRigidContacts.build(solver_options={"maxiter": 10}))
+    assert isinstance(m.contact_params, RelaxedRigidContactsParams) and dict(m.contact_model.solver_options)["maxiter"] == 10
