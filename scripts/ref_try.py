@@ -1,3 +1,7 @@
+"""Run the UNMODIFIED reference step (over oracle/refshim) next to the NumPy oracle on the same inputs:
+
+    PYTHONPATH=. python scripts/ref_try.py pendulum box icub_like        (build container only)
+"""
 import numpy as np, time, sys
 from tests.golden import refenv
 jaxsim, js = refenv.load()
