@@ -588,14 +588,14 @@ def run_b200(args):
 
     # the step is NOT HBM-bound, so the counted arithmetic is reported next to the HBM figure.
     # flops per env-step = (2*FFMA + FADD + FMUL thread instructions) / batch from the ncu capture of this
-    # configuration (profiles/r01_step_kernel_v6_warm.md: 7530 FFMA + 2913 FADD + 4641 FMUL per env-step)
+    # configuration (profiles/r01_step_kernel_v7_warm.md: FFMA x2 + FADD + FMUL thread instructions per env-step)
     compute = None
     if args.model == "icub_like" and args.dtype == "f32" and not args.no_caches:
-        fpe = 22615.0
+        fpe = 22020.0
         peak_fp32 = 148 * 128 * 2 * 1.965e9 / 1e12  # CUDA-core FMA peak at the measured SM clock (nominal, TFLOP/s)
         compute = {"flops_per_env_step": fpe, "achieved_tflops": fpe * B / (ms_step * 1e-3) / 1e12, "peak_tflops": peak_fp32,
                    "frac": fpe * B / (ms_step * 1e-3) / 1e12 / peak_fp32, "unit": "TFLOP/s fp32 (CUDA cores; tensor cores do not apply)",
-                   "source": "ncu sm__sass_thread_inst_executed_op_{ffma,fadd,fmul} of this configuration, profiles/r01_step_kernel_v6_warm.md"}
+                   "source": "ncu sm__sass_thread_inst_executed_op_{ffma,fadd,fmul} of this configuration, profiles/r01_step_kernel_v7_warm.md"}
 
     cpu = None
     if not args.no_cpu_baseline:
