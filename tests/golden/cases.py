@@ -61,10 +61,17 @@ CASES = [
     dict(id="icub_relaxed_fext_mixed", seed=32, contact="relaxed", in_contact="flat", tau=True, fext=True, velrepr="mixed",
          model="icub_like", B=2),
     dict(id="ergocub_relaxed_flat", model="ergocub_like", B=2, seed=33, contact="relaxed", in_contact="flat", tau=True),
+    # ---- short rollouts: the reference's `step` applied `rollout` times in a row (state carried through its own
+    #      JaxSimModelData, incl. the contact state and -- for RigidContacts -- the stale cached link velocities)
+    dict(id="box_soft_rollout", model="box", B=3, seed=34, in_contact=True, m=True, rollout=5),
+    dict(id="icub_soft_rollout", seed=35, in_contact=True, tau=True, m=True, rollout=5, model="icub_like", B=2),
+    dict(id="box_rigid_rollout", model="box", B=3, seed=36, contact="rigid", in_contact="flat", rollout=5),
+    dict(id="icub_rigid_rollout", seed=37, contact="rigid", in_contact="flat", tau=True, rollout=4, model="icub_like", B=2),
+    dict(id="icub_relaxed_rollout", seed=38, contact="relaxed", in_contact="flat", tau=True, rollout=4, model="icub_like", B=2),
 ]
 
 DEFAULTS = dict(contact="soft", contact_params=None, actuation=None, integrator="semi_implicit_euler", in_contact=False,
-                tau=False, m=False, fext=False, velrepr="inertial", rbda=False, time_step=1e-3)
+                tau=False, m=False, fext=False, velrepr="inertial", rbda=False, time_step=1e-3, rollout=1)
 
 
 def case(cid: str) -> dict:

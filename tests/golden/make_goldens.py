@@ -128,6 +128,8 @@ def run_case(case: dict) -> dict:
             push("cp_position", np.zeros((0, 3)))
             push("cp_velocity", np.zeros((0, 3)))
         new = js.model.step(model=rm, data=data, link_forces=lf, joint_force_references=tau)
+        for _ in range(case["rollout"] - 1):  # the outputs below are those of the LAST step
+            new = js.model.step(model=rm, data=new, link_forces=lf, joint_force_references=tau)
         for leaf in STATE_LEAVES:
             push("out" + leaf, getattr(new, leaf))
         if soft:
