@@ -598,7 +598,7 @@ def run_b200(args):
                    "source": "ncu sm__sass_thread_inst_executed_op_{ffma,fadd,fmul} of this configuration, profiles/r01_step_kernel_v7_warm.md"}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # contract: the CPU baseline is timed at N = 1 only
         threads = max(1, min(os.cpu_count() or 1, 256))
         v, busy = cpu_oracle_throughput(args.model, B, 10, threads)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
