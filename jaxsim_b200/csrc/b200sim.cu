@@ -127,6 +127,10 @@ int pick_geometry(const B200SimModel* m, int dtype, long long B, Geometry* g) {
     // widest tree level / link count bound the useful lanes; 8 balances the sequential
     // level walks against the link-parallel phases for humanoid-size trees
     G = 8;
+    // larger trees (ErgoCub-like, 50 links): 16 lanes halve the trips of the link-parallel phases and keep
+    // the compact final phase available (nL <= 4 G + 1): measured 58.2 vs 68.1 us at batch 4096, 194 vs 232 us
+    // at 16 384 (profiles/r01_lanes_ergocub.log)
+    if (m->nL > 33) G = 16;
     while (G > 1 && G / 2 >= m->nL) G /= 2;
   }
   const int wg = 32 / G;  // groups per warp
