@@ -91,6 +91,12 @@ template <> struct RankTol<double> { static __device__ __forceinline__ double to
 
 constexpr unsigned FULL = 0xffffffffu;
 
+// phase timeline of one warp (diagnostic, like B200SIM_PHASE_MARK of the step kernel): dbg[8 + 16 + k], k = 1..15
+#define B200SIM_RIGID_MARK(k)                                                                                   \
+  do {                                                                                                           \
+    if (P.dbg && blockIdx.x == 0 && threadIdx.x == 0 && it0 == 0) P.dbg[8 + 16 + (k)] = (unsigned long long)clock64(); \
+  } while (0)
+
 template <typename S>
 __device__ __forceinline__ S warp_sum(S v) {
 #pragma unroll
@@ -1116,8 +1122,10 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
 
     if (!impact_only) {
     // ============================================================== phase A: state at t
+    B200SIM_RIGID_MARK(1);
     kinematics(b, false);
     const int na = contact_points(false);
+    B200SIM_RIGID_MARK(2);
     if (na > cap) {  // more active points than this level's workspace holds: next level, untouched
       if (lane == 0) over_push(P, (int)env, 0);
       continue;
@@ -1157,6 +1165,7 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
     }
     __syncwarp();
 
+    B200SIM_RIGID_MARK(3);
     T a0t[6];  // base acceleration in F_0 (gravity-shifted), free + contact response
     ldn<6>(ws + O_V, a0t);
     if (na > 0) {
@@ -1177,6 +1186,7 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
       }
       if (!relaxed) {
         delassus(na, S(P.reg));
+        B200SIM_RIGID_MARK(4);
         const int qp_it = qp_pyramids<S>(Qp, Hp, vN, vM, na, S(P.mu), lane);
         if (P.dbg && lane == 0) {
           atomicAdd(P.dbg + 0, (unsigned long long)qp_it);
@@ -1202,6 +1212,7 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
         __syncwarp();
         psd_solve_pivoted<S>(Qp, Hp, vN + 5 * N, lam, vN + N, perm, N, S(sizeof(S) == 8 ? 1e-14 : 1e-7), lane);
       }
+      B200SIM_RIGID_MARK(5);
       for (int a = lane; a < na; a += 32) {
         T* pw = pts + (size_t)alist[a] * RPT;
         pw[RP_F] = T(vN[3 * a]); pw[RP_F + 1] = T(vN[3 * a + 1]); pw[RP_F + 2] = T(vN[3 * a + 2]);
@@ -1217,6 +1228,7 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
     }
     __syncwarp();
 
+    B200SIM_RIGID_MARK(6);
     // ============================================================== semi-implicit Euler
     T Wa[6];
     cross3(b.p, a0t + 3, Wa);
@@ -1267,6 +1279,7 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
     // ============================================================== phase B: state at t+dt
     // kinematics of the new state with the PRE-impact velocities: these are the caches the
     // reference returns (rigid.py:429-434 leaves them untouched)
+    B200SIM_RIGID_MARK(7);
     kinematics(b, true);
     if (lane == 0) {
       stn<4>(P.q_o + env * 4, b.qn);
@@ -1301,7 +1314,9 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
     }
 
     // impact (rigid.py:385-436): project nu onto {velocity of the active points = 0}
+    B200SIM_RIGID_MARK(8);
     const int na2 = relaxed ? 0 : contact_points(true);  // RelaxedRigid: no impact step (relaxed_rigid.py:262-281)
+    B200SIM_RIGID_MARK(9);
     if (na2 > cap) {
       // next level applies the impact to the pre-impact result, which must then be complete
       if (!impact_only) {
@@ -1321,6 +1336,7 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
       link_init(false);
       pass2();
       delassus(na2, S(0));
+      B200SIM_RIGID_MARK(10);
       const int N2 = 3 * na2;
       S* lam = vN;
       S* dg = vN + 5 * N2;
@@ -1330,6 +1346,7 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
       }
       __syncwarp();
       psd_solve_pivoted<S>(Qp, Hp, dg, lam, vN + N2, perm, N2, S(RankTol<T>::tol()), lane);
+      B200SIM_RIGID_MARK(11);
       for (int a = lane; a < na2; a += 32) {
         T* pw = pts + (size_t)alist[a] * RPT;
         pw[RP_F] = T(lam[3 * a]); pw[RP_F + 1] = T(lam[3 * a + 1]); pw[RP_F + 2] = T(lam[3 * a + 2]);
@@ -1358,6 +1375,7 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
       stn<3>(P.vlin_o + env * 3, vl);
       stn<3>(P.omega_o + env * 3, w2);
     }
+    B200SIM_RIGID_MARK(12);
     __syncwarp();
   }
 }

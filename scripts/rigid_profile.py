@@ -73,4 +73,18 @@ e1.record()
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
 ms = e0.elapsed_time(e1) / args.steps
+clk = (ctypes.c_ulonglong * 32)()
+lib.b200sim_debug_phase_clocks.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+lib.b200sim_debug_phase_clocks(m.device_model(dev).handle, clk)
+NAMES = {1: "start of item", 2: "kinematics + contact points", 3: "link init + ABA passes 2, 3 (free acceleration)", 4: "Delassus (contact)",
+         5: "QP / linear solve", 6: "forces -> tree response", 7: "semi-implicit Euler", 8: "kinematics of the new state + cache stores",
+         9: "contact points (impact)", 10: "link init + pass 2 + Delassus (impact)", 11: "pivoted Cholesky (impact)", 12: "impulse response + stores"}
+t = [int(v) for v in clk][16:29]
+prev = t[1]
+print("timeline of warp 0 / block 0, first work item of the LAST rigid-kernel launch (clock64, us at 1965 MHz):")
+for k in range(2, 13):
+    if t[k] == 0 or t[k] < prev:
+        continue
+    print("  %-52s %9d cyc %8.1f us" % (NAMES[k], t[k] - prev, (t[k] - prev) / 1965.0))
+    prev = t[k]
 print("rigid step: %.3f ms/step, %.0f env-steps/s (B=%d, %s, qp32=%s)" % (ms, B / ms * 1e3, B, args.dtype, args.qp32))
