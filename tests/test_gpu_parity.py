@@ -91,6 +91,60 @@ def test_step_all_lane_widths(G, cuda_device):
     H.compare_data(out, ref, 1e-5, f"G={G}")
 
 
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("G", [8, 16])
+def test_step_wide_levels_and_large_trees(G, dtype, cuda_device):
+    """ErgoCub-like tree (50 links, a level of 10 links): with 8 lanes a level spans two packed
+    rows and the compact final phase does not apply (nL > 4 G + 1); with 16 lanes both do."""
+    import torch
+
+    model = H.build_model("ergocub_like")
+    model.set_tuning(lanes_per_env=G)
+    om = H.oracle_model(model)
+    B = 37
+    od = O.random_model_data(om, B, seed=21, in_contact=True)
+    tau = 5 * np.random.default_rng(4).uniform(-1, 1, size=(B, om.dofs()))
+    ref = O.step(om, od, joint_force_references=tau)
+    pd = H.to_product(model, od, _dtype(dtype), cuda_device)
+    t = torch.as_tensor(tau, dtype=_dtype(dtype), device=cuda_device)
+    out = js.model.step(model, pd, joint_force_references=t)
+    H.compare_data(out, ref, H.RTOL[dtype], f"ergocub G={G} {dtype}")
+    out3 = js.model.step_n(model, pd, 3, joint_force_references=t)
+    ref3 = ref
+    for _ in range(2):
+        ref3 = O.step(om, ref3, joint_force_references=tau)
+    H.compare_data(out3, ref3, 5 * H.RTOL[dtype], f"ergocub step_n G={G} {dtype}")
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("options", [dict(bulk_in=True), dict(pdl=False), dict(generic_kernel=True), dict(tma_store=False)])
+def test_step_implementation_switches_agree(options, dtype, cuda_device):
+    """The implementation switches (TMA bulk input loads, programmatic dependent launch off, generic
+    kernel instance, 128-bit adjoint stores) never change results: bit-identical to the default."""
+    import torch
+
+    base = H.build_model("icub_like")
+    alt = H.build_model("icub_like")
+    alt.set_options(**options)
+    om = H.oracle_model(base)
+    B = 133  # ragged: not a multiple of the environments per block
+    od = O.random_model_data(om, B, seed=23, in_contact=True)
+    tau = torch.as_tensor(3 * np.random.default_rng(5).uniform(-1, 1, size=(B, om.dofs())), dtype=_dtype(dtype), device=cuda_device)
+    a = js.model.step(base, H.to_product(base, od, _dtype(dtype), cuda_device), joint_force_references=tau)
+    b = js.model.step(alt, H.to_product(alt, od, _dtype(dtype), cuda_device), joint_force_references=tau)
+    exact = "generic_kernel" not in options  # the generic instance may schedule the same arithmetic differently (FMA contraction)
+    for _, leaf in H.LEAVES:
+        x, y = getattr(a, leaf), getattr(b, leaf)
+        if exact:
+            assert torch.equal(x, y), (options, leaf)
+        else:
+            assert H.rel_err(y.cpu().numpy(), x.cpu().numpy()) <= H.RTOL[dtype] * 1e-2, (options, leaf)
+    for _ in range(3):  # back-to-back launches (PDL overlap) keep giving the same answer
+        b = js.model.step(alt, b, joint_force_references=tau)
+        a = js.model.step(base, a, joint_force_references=tau)
+    assert H.rel_err(b._joint_positions.cpu().numpy(), a._joint_positions.cpu().numpy()) <= (0 if exact else H.RTOL[dtype])
+
+
 def test_step_link_forces_representations(cuda_device):
     """link_forces are interpreted in data.velocity_representation (api/model.py:2641-2646)."""
     import torch
