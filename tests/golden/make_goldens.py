@@ -136,6 +136,16 @@ def run_case(case: dict) -> dict:
             push("out_tangential_deformation", new.contact_state["tangential_deformation"])
         if case["rbda"]:
             for name, r in (("inertial", VelRepr.Inertial), ("mixed", VelRepr.Mixed), ("body", VelRepr.Body)):
+                # JaxSimModelData.build with the base velocity GIVEN in representation r (api/data.py:66-202): what it
+                # stores (always inertial-fixed) and what the base_velocity accessor returns (api/data.py:288-312)
+                d_b = js.data.JaxSimModelData.build(
+                    model=rm, base_position=inp["base_position"][e], base_quaternion=inp["base_quaternion"][e],
+                    joint_positions=inp["joint_positions"][e], joint_velocities=inp["joint_velocities"][e],
+                    base_linear_velocity=inp["base_linear_velocity"][e], base_angular_velocity=inp["base_angular_velocity"][e],
+                    velocity_representation=r)
+                push(f"build_{name}_stored_velocity", np.concatenate([np.asarray(d_b._base_linear_velocity).reshape(3), np.asarray(d_b._base_angular_velocity).reshape(3)]))
+                push(f"build_{name}_link_velocities", d_b._link_velocities)
+                push(f"base_velocity_{name}", dataclasses.replace(data, velocity_representation=r).base_velocity)
                 # the same state; link forces / base acceleration are READ in representation r and the
                 # base acceleration / base force / mass matrix are RETURNED in it
                 d_r = dataclasses.replace(data, velocity_representation=r)

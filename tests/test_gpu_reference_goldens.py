@@ -140,3 +140,28 @@ def test_contact_helpers_match_reference(cid, cuda_device):
         prm = js.contact.estimate_good_contact_parameters(model, device=cuda_device, **kw)
         ref = z[f"egcp_{tag}"][0]
         np.testing.assert_allclose([prm.K, prm.D, prm.mu], ref, rtol=1e-9)
+
+
+@pytest.mark.parametrize("cid", [c["id"] for c in C.all_cases() if c["rbda"]])
+def test_data_build_representations_match_reference(cid, cuda_device):
+    """`JaxSimModelData.build` with base velocities given in Inertial / Mixed / Body representation
+    (api/data.py:66-202) and the `base_velocity` accessor (api/data.py:288-312)."""
+    import torch
+
+    z, _ = _load(cid)
+    case = C.case(cid)
+    model = H.build_model_for_case(case)
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=cuda_device)  # noqa: E731
+    B = z["in_base_position"].shape[0]
+    data = _inputs(case, z, model, torch.float64, cuda_device)
+    for name, vr in VELREPR.items():
+        d = js.data.JaxSimModelData.build(
+            model, base_position=t(z["in_base_position"]), base_quaternion=t(z["in_base_quaternion"]),
+            joint_positions=t(z["in_joint_positions"]), joint_velocities=t(z["in_joint_velocities"]),
+            base_linear_velocity=t(z["in_base_linear_velocity"]), base_angular_velocity=t(z["in_base_angular_velocity"]),
+            velocity_representation=vr, batch_size=B, dtype=torch.float64, device=cuda_device)
+        stored = torch.cat([d._base_linear_velocity, d._base_angular_velocity], dim=-1).cpu().numpy()
+        assert H.rel_err(stored, z[f"build_{name}_stored_velocity"]) <= 1e-9, name
+        assert H.rel_err(d.link_velocities.cpu().numpy(), z[f"build_{name}_link_velocities"]) <= 1e-9, name
+        data.velocity_representation = vr
+        assert H.rel_err(data.base_velocity.cpu().numpy(), z[f"base_velocity_{name}"]) <= 1e-9, name
