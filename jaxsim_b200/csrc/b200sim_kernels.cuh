@@ -1039,35 +1039,35 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
           if (pt_enabled[k]) {
             // compute_penetration_data, FlatTerrain: n = z (rbda/contacts/common.py:25-63)
             const T delta = max_t(T(0), P.h_terrain - pc[2]);
-            const T ddot = (delta > T(0)) ? -pd[2] : T(0);
-            const T eps = Lim<T>::eps();
-            const T dp = (flags & F_SQRT_P) ? sqrt_t(delta + eps) : pow_t(delta + eps, P.pexp);
-            const T dq = (flags & F_SQRT_Q) ? sqrt_t(delta + eps) : pow_t(delta + eps, P.qexp);
-            const T Kdp = P.K * dp, Ddq = P.D * dq;
-            const T fn = max_t(T(0), Kdp * delta + Ddq * ddot);
-            // tangential quantities (n = z): v_t = (vx,vy,0), m_t = (mx,my,0), m_n = (0,0,mz)
-            T ft0 = -(Kdp * m[0] + Ddq * pd[0]);
-            T ft1 = -(Kdp * m[1] + Ddq * pd[1]);
-            const T mufn = P.mu * fn;
-            const bool nocontact = delta <= T(0);
-            const bool sticking = nocontact || (ft0 * ft0 + ft1 * ft1 <= mufn * mufn);
-            const T nrm = sqrt_t(ft0 * ft0 + ft1 * ft1);
-            const T idn = rcp_t(nrm + eps * (nrm == T(0) ? T(1) : T(0)));
-            if (!sticking) {
-              const T sc = min_t(mufn, nrm) * idn;
-              ft0 *= sc; ft1 *= sc;
-            }
-            if (nocontact) { ft0 = T(0); ft1 = T(0); }
             const T KoD = P.K * rcp_t(P.D);
-            if (nocontact) {
+            if (delta <= T(0)) {
+              // no contact: zero force, the tangential deformation relaxes (soft.py:318-330).  A branch, not a
+              // select: a warp whose points are all above the ground skips the Hunt/Crossley arithmetic.
               md[0] = -KoD * m[0]; md[1] = -KoD * m[1]; md[2] = -KoD * m[2];
-            } else if (sticking) {
-              md[0] = pd[0]; md[1] = pd[1]; md[2] = -KoD * m[2];
             } else {
-              const T iD = rcp_t(Ddq);
-              md[0] = -(ft0 + Kdp * m[0]) * iD; md[1] = -(ft1 + Kdp * m[1]) * iD; md[2] = T(0);
+              const T ddot = -pd[2];
+              const T eps = Lim<T>::eps();
+              const T dp = (flags & F_SQRT_P) ? sqrt_t(delta + eps) : pow_t(delta + eps, P.pexp);
+              const T dq = (flags & F_SQRT_Q) ? sqrt_t(delta + eps) : pow_t(delta + eps, P.qexp);
+              const T Kdp = P.K * dp, Ddq = P.D * dq;
+              const T fn = max_t(T(0), Kdp * delta + Ddq * ddot);
+              // tangential quantities (n = z): v_t = (vx,vy,0), m_t = (mx,my,0), m_n = (0,0,mz)
+              T ft0 = -(Kdp * m[0] + Ddq * pd[0]);
+              T ft1 = -(Kdp * m[1] + Ddq * pd[1]);
+              const T mufn = P.mu * fn;
+              const bool sticking = ft0 * ft0 + ft1 * ft1 <= mufn * mufn;
+              if (sticking) {
+                md[0] = pd[0]; md[1] = pd[1]; md[2] = -KoD * m[2];
+              } else {
+                const T nrm = sqrt_t(ft0 * ft0 + ft1 * ft1);
+                const T idn = rcp_t(nrm + eps * (nrm == T(0) ? T(1) : T(0)));
+                const T sc = min_t(mufn, nrm) * idn;
+                ft0 *= sc; ft1 *= sc;
+                const T iD = rcp_t(Ddq);
+                md[0] = -(ft0 + Kdp * m[0]) * iD; md[1] = -(ft1 + Kdp * m[1]) * iD; md[2] = T(0);
+              }
+              f[0] = ft0; f[1] = ft1; f[2] = fn;
             }
-            f[0] = ft0; f[1] = ft1; f[2] = fn;
           }
           // lever arm w.r.t. the origin of the ABA-chain frame of the body
           T lev[3];
