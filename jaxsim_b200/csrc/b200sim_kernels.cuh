@@ -1019,6 +1019,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
           active = false;
         }
       }
+      bool env_touches = false;  // some point of this environment is in contact (group-uniform after the ballot)
       if (soft) {
         for (int k = lane; k < nc; k += G) {
           const int bi = pt_body[k];
@@ -1067,6 +1068,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
                 md[0] = -(ft0 + Kdp * m[0]) * iD; md[1] = -(ft1 + Kdp * m[1]) * iD; md[2] = T(0);
               }
               f[0] = ft0; f[1] = ft1; f[2] = fn;
+              env_touches = true;
             }
           }
           // lever arm w.r.t. the origin of the ABA-chain frame of the body
@@ -1099,6 +1101,12 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
       } else if (mode == MODE_DYN && P.m_o && active) {
         for (int k = lane; k < nc * 3; k += G) P.m_o[env * nc * 3 + k] = T(0);
       }
+      {
+        // airborne environments skip the per-link accumulation of the (all zero) contact wrenches below
+        const unsigned bal = __ballot_sync(0xffffffffu, env_touches);
+        const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+        env_touches = (bal & gmask) != 0u;
+      }
       __syncwarp();
       B200SIM_PHASE_MARK(6);
 
@@ -1112,7 +1120,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
         ldn<6>(ri + O_V, v);
         // total external wrench on the link in F_i: contacts + user forces
         T fe[3] = {T(0), T(0), T(0)}, ne[3] = {T(0), T(0), T(0)};
-        if (soft) {
+        if (soft && env_touches) {
           const int e = pt_start[i + 1];
           for (int kk = pt_start[i]; kk < e; ++kk) {
             const T* pw = ptws + (size_t)pt_idx[kk] * PTREC;
