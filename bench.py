@@ -69,6 +69,7 @@ def parse():
     ap.add_argument("--config3", action="store_true", help="also time BASELINE config 3: ErgoCub-like ~50-DoF, RIGID contacts, batch 16384 fp32")
     ap.add_argument("--c3-batch", type=int, default=16384)
     ap.add_argument("--rollout", type=int, default=0, help="also time step_n with this many fused steps per launch")
+    ap.add_argument("--in-contact", action="store_true", help="also time the same batch with every environment touching the ground")
     ap.add_argument("--sweep", action="store_true", help="also time batch 16384 and 65536 on this GPU")
     return ap.parse_args()
 
@@ -229,7 +230,20 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def time_steps(Bq, K, W, use_graph=True):
+    def lowered_to_contact(d, seed):
+        """The same random state with the base lowered so that the lowest collidable point penetrates the
+        ground by 0-5 mm (the second input distribution of BASELINE.md: every environment in contact)."""
+        gen = torch.Generator(device=dev).manual_seed(seed)
+        z = js.contact.collidable_point_positions(model, d)[..., 2].min(dim=-1).values
+        p = d._base_position.clone()
+        p[:, 2] -= z + 0.005 * torch.rand(p.shape[0], dtype=dtype, device=dev, generator=gen)
+        return js.data.JaxSimModelData.build(
+            model, base_position=p, base_quaternion=d._base_quaternion, joint_positions=d._joint_positions,
+            joint_velocities=0.1 * d._joint_velocities, base_linear_velocity=0.1 * d._base_linear_velocity,
+            base_angular_velocity=0.1 * d._base_angular_velocity, velocity_representation=js.common.VelRepr.Inertial,
+            batch_size=p.shape[0], dtype=dtype, device=dev)
+
+    def time_steps(Bq, K, W, use_graph=True, in_contact=False):
         """K device-resident steps over a ring of state sets larger than L2.  Returns
         (ms of the K steps launched eagerly, ms of the same K steps replayed from a CUDA
         graph or None, ring, last output)."""
@@ -237,6 +251,8 @@ def run_b200(args):
         ring = min(ring, 64)
         datas = [js.data.random_model_data(model, batch_size=Bq, seed=1000 * rank + r, dtype=dtype, device=dev,
                                            velocity_representation=js.common.VelRepr.Inertial) for r in range(ring)]
+        if in_contact:
+            datas = [lowered_to_contact(d, 77 + r) for r, d in enumerate(datas)]
         taus = [10 * torch.rand(Bq, n, dtype=dtype, device=dev) for _ in range(ring)]
         # preallocated outputs (`out=`): the step then performs no allocation and is capturable
         outs = [js.model.step(model, datas[r], joint_force_references=taus[r], update_caches=not args.no_caches) for r in range(ring)]
@@ -446,6 +462,15 @@ def run_b200(args):
             msq = msg if msg is not None else mse
             sweep.append({"batch": Bq, "value": Bq * Kq / (msq * 1e-3), "ms_per_step": msq / Kq, "ring": rq})
 
+    contact_leg = None
+    if (args.sweep or args.in_contact) and world == 1 and nc > 0:
+        Kc = max(20, args.steps // 4)
+        mse, msg, rq, _ = time_steps(B, Kc, 3, use_graph=not args.no_graph, in_contact=True)
+        msc = msg if msg is not None else mse
+        contact_leg = {"batch": B, "value": B * Kc / (msc * 1e-3), "ms_per_step": msc / Kc,
+                       "inputs": "every environment touching the ground (lowest point 0-5 mm below it); the default line uses the "
+                                 "reference benchmark's random_model_data, where most environments are airborne"}
+
     rollout = None
     if args.rollout > 0:
         Tn = args.rollout
@@ -588,14 +613,14 @@ def run_b200(args):
 
     # the step is NOT HBM-bound, so the counted arithmetic is reported next to the HBM figure.
     # flops per env-step = (2*FFMA + FADD + FMUL thread instructions) / batch from the ncu capture of this
-    # configuration (profiles/r01_step_kernel_v7_warm.md: FFMA x2 + FADD + FMUL thread instructions per env-step)
+    # configuration (profiles/r01_step_kernel_v8_warm.md: FFMA x2 + FADD + FMUL thread instructions per env-step)
     compute = None
     if args.model == "icub_like" and args.dtype == "f32" and not args.no_caches:
-        fpe = 22020.0
+        fpe = 21400.0
         peak_fp32 = 148 * 128 * 2 * 1.965e9 / 1e12  # CUDA-core FMA peak at the measured SM clock (nominal, TFLOP/s)
         compute = {"flops_per_env_step": fpe, "achieved_tflops": fpe * B / (ms_step * 1e-3) / 1e12, "peak_tflops": peak_fp32,
                    "frac": fpe * B / (ms_step * 1e-3) / 1e12 / peak_fp32, "unit": "TFLOP/s fp32 (CUDA cores; tensor cores do not apply)",
-                   "source": "ncu sm__sass_thread_inst_executed_op_{ffma,fadd,fmul} of this configuration, profiles/r01_step_kernel_v7_warm.md"}
+                   "source": "ncu sm__sass_thread_inst_executed_op_{ffma,fadd,fmul} of this configuration, profiles/r01_step_kernel_v8_warm.md"}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:  # contract: the CPU baseline is timed at N = 1 only
@@ -632,6 +657,8 @@ def run_b200(args):
         line["readback_allgather_ms"] = gather_ms
     if sweep is not None:
         line["sweep"] = sweep
+    if contact_leg is not None:
+        line["in_contact"] = contact_leg
     if rollout is not None:
         line["rollout"] = rollout
     if jvp is not None:

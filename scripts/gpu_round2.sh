@@ -15,7 +15,7 @@ timeout 600 python bench.py --impl reference --steps 5 --warmup 1 2>>gpurun_out/
 echo "== bench extras"
 timeout 900 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --config3 --rollout 100 --sweep 2>>gpurun_out/bench_err.log | tee gpurun_out/bench_extras.json | python -c "
 import sys,json; d=json.loads(sys.stdin.read())
-for k in ('config3_rigid','relaxed_rigid','rollout','sweep'): print(k, json.dumps(d.get(k))[:1500])"
+for k in ('config3_rigid','relaxed_rigid','rollout','sweep','in_contact'): print(k, json.dumps(d.get(k))[:1500])"
 timeout 600 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --dtype f64 --jvp 2>>gpurun_out/bench_err.log | tee gpurun_out/bench_f64.json | python -c "
 import sys,json; d=json.loads(sys.stdin.read()); print('f64 us/step', 1e3*d['ms_per_step'], 'frac', d['roofline']['frac']); print('jvp', json.dumps(d.get('config5_jvp'))[:800])"
 echo "== phase clocks"
