@@ -271,7 +271,7 @@ int launch(const B200SimModel* m, Params<T>& P, int dtype, void* stream) {
 //   level 1: the rigid kernel, one warp per listed environment, shared-memory workspace sized
 //            for RIGID_CAP1 simultaneously active points; environments with more -> list 2;
 //   level 2: the rigid kernel with a full-size workspace (only if nc > RIGID_CAP1).
-constexpr int RIGID_CAP1 = 16;
+constexpr int RIGID_CAP1 = 12;  // 12 active points: 7 resident warps per SM instead of 5 at 16 (the rest overflows to the full-size level)
 
 template <typename T, typename S>
 int rigid_geometry(const B200SimModel* m, long long B, int cap, int* warps, int* grid, size_t* smem) {
