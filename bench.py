@@ -63,6 +63,8 @@ def parse():
     ap.add_argument("--no-tma", action="store_true", help="128-bit stores instead of TMA bulk stores for the joint adjoints")
     ap.add_argument("--no-pdl", action="store_true", help="diagnostic: ordinary launches instead of programmatic dependent launches")
     ap.add_argument("--bulk-in", action="store_true", help="diagnostic: cp.async.bulk (TMA) instead of per-link cp.async for the cached input kinematics")
+    ap.add_argument("--step-v1", action="store_true", help="diagnostic: first-generation specialised step kernel instead of b200sim_step2")
+    ap.add_argument("--no-bulk-in", action="store_true", help="diagnostic (step2): per-link cp.async instead of cp.async.bulk for the cached input kinematics")
     ap.add_argument("--generic-kernel", action="store_true", help="diagnostic: launch the generic step-kernel instance instead of the specialised one")
     ap.add_argument("--profile", action="store_true", help="cudaProfilerStart/Stop around the eager timed region (ncu --profile-from-start off)")
     ap.add_argument("--jvp", action="store_true", help="also time BASELINE config 5: forward-mode d(step)/d(joint q, link masses), fp64")
@@ -219,8 +221,9 @@ def run_b200(args):
     model = js.model.JaxSimModel.build_from_model_description(models.urdf(args.model), time_step=1e-3)
     if args.lanes:
         model.set_tuning(lanes_per_env=args.lanes)
-    if args.no_tma or args.generic_kernel or args.bulk_in or args.no_pdl:
-        model.set_options(tma_store=not args.no_tma, generic_kernel=args.generic_kernel, bulk_in=args.bulk_in, pdl=not args.no_pdl)
+    if args.no_tma or args.generic_kernel or args.bulk_in or args.no_pdl or args.step_v1 or args.no_bulk_in:
+        model.set_options(tma_store=not args.no_tma, generic_kernel=args.generic_kernel, bulk_in=args.bulk_in, pdl=not args.no_pdl,
+                          step_v1=args.step_v1, no_bulk_in=args.no_bulk_in)
     n, nL, nc = model.dofs(), model.number_of_links(), model.number_of_collidable_points()
     B = args.batch
     bytes_env = algorithmic_bytes_per_env(n, nL, nc, w, caches=not args.no_caches)

@@ -135,6 +135,13 @@ int b200sim_model_set_tuning(B200SimModel *model, int lanes_per_env, int envs_pe
  *   programmatic stream serialization (the launch set-up of step k+1 then no longer overlaps
  *   the execution of step k; same results; diagnostic). */
 #define B200SIM_OPT_NO_PDL 16
+/*   B200SIM_OPT_STEP_V1: launch the first-generation specialised step kernel (60-word link records,
+ *   parents gather their children in ABA pass 2) instead of the second-generation one (44-word records,
+ *   children add into the parent; b200sim_step2.cuh).  Same results up to rounding; A-B timing switch. */
+#define B200SIM_OPT_STEP_V1 32
+/*   B200SIM_OPT_NO_BULK_IN: the second-generation kernel reads the cached kinematics of the input state
+ *   with cp.async (LDGSTS) per link even when the rows qualify for cp.async.bulk (diagnostic). */
+#define B200SIM_OPT_NO_BULK_IN 64
 int b200sim_model_set_options(B200SimModel *model, int32_t options);
 
 /* Query sizes / launch geometry chosen for a batch (for benchmarks and tests). */

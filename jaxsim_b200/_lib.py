@@ -72,6 +72,8 @@ OPT_RIGID_QP_F32 = 2
 OPT_GENERIC_KERNEL = 4
 OPT_BULK_IN = 8
 OPT_NO_PDL = 16
+OPT_STEP_V1 = 32
+OPT_NO_BULK_IN = 64
 EXPORTED_SYMBOLS = (
     "b200sim_version",
     "b200sim_model_create",

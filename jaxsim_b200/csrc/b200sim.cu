@@ -9,6 +9,7 @@
 #include "b200sim_kernels.cuh"
 #include "b200sim_rbda_kernels.cuh"
 #include "b200sim_rigid_kernels.cuh"
+#include "b200sim_step2.h"
 
 #include <algorithm>
 #include <cmath>
@@ -38,6 +39,7 @@ struct B200SimModel {
   int o_parent = 0, o_jtype = 0, o_lvl_start = 0, o_lvl_links = 0, o_child_start = 0, o_child_idx = 0,
       o_pt_start = 0, o_pt_idx = 0, o_pt_body = 0, o_pt_enabled = 0, o_anc = 0, o_ldepth = 0;
   int o_rows8 = 0, n_rows8 = 0, o_rows16 = 0, n_rows16 = 0;  // packed level-walk rows for G = 8 / 16 (0 rows: not available)
+  int o_rows2_8 = 0, o_rows2_16 = 0;                          // the same rows in the format of step2_kernel
   double reg = 1e-6;
   double rx_tc = 0.02, rx_zeta = 1.0, rx_dmin = 0.9, rx_dmax = 0.95, rx_width = 1e-3, rx_mid = 0.5, rx_pow = 2.0;  // RelaxedRigid
   unsigned long long* dbg_d = nullptr;  // debug counters, allocated by b200sim_debug_counters
@@ -197,6 +199,7 @@ void fill_model_params(const B200SimModel* m, Params<T>& P) {
   P.o_pt_idx = m->o_pt_idx; P.o_pt_body = m->o_pt_body; P.o_pt_enabled = m->o_pt_enabled;
   P.o_anc = m->o_anc; P.o_ldepth = m->o_ldepth; P.reg = (T)m->reg;
   P.o_rows8 = m->o_rows8; P.n_rows8 = m->n_rows8; P.o_rows16 = m->o_rows16; P.n_rows16 = m->n_rows16;
+  P.o_rows2_8 = m->o_rows2_8; P.o_rows2_16 = m->o_rows2_16;
   P.dbg = m->dbg_d;
   P.rx_tc = (T)m->rx_tc; P.rx_zeta = (T)m->rx_zeta; P.rx_dmin = (T)m->rx_dmin; P.rx_dmax = (T)m->rx_dmax;
   P.rx_width = (T)m->rx_width; P.rx_mid = (T)m->rx_mid; P.rx_pow = (T)m->rx_pow;
@@ -240,8 +243,75 @@ bool specialised_step_applies(const B200SimModel* m, const Params<T>& P) {
   return P.nc == 0 || P.contact_model == 1;
 }
 
+// The second-generation kernel (b200sim_step2.cuh) serves what the specialised instance serves, for
+// float / double, G = 8 / 16 lanes and trees with nL <= 4 G links.
+int pick_geometry2(const B200SimModel* m, size_t ts, long long B, Geometry* g) {
+  const size_t st = static_smem_bytes(m, ts);
+  const size_t pe = step2_env_words(ts, m->nL, m->nc) * ts;
+  const size_t budget = (size_t)m->max_smem_optin - 1024;
+  if (st + pe > budget) return B200SIM_E_TOO_LARGE;
+  int G = m->tune_G;
+  if (G == 0) G = m->nL > 32 ? 16 : 8;
+  if (G != 8 && G != 16) return B200SIM_E_UNSUPPORTED;
+  if (m->nL > 4 * G) return B200SIM_E_UNSUPPORTED;
+  const int wg = 32 / G;
+  const long long epb_smem = (long long)((budget - st) / pe);
+  const long long epb_thr = step2_max_threads(ts, G) / G;
+  long long epb = std::min(epb_smem, epb_thr);
+  if (m->tune_epb > 0) epb = std::min<long long>(epb, m->tune_epb);
+  const long long per_sm = (B + m->num_sms - 1) / m->num_sms;
+  if (m->tune_epb == 0) epb = std::min(epb, std::max<long long>(per_sm, 1));
+  epb = ((epb + wg - 1) / wg) * wg;  // whole warps
+  while (epb > wg && (epb > epb_smem || epb > epb_thr)) epb -= wg;
+  if (epb < 1 || epb > epb_smem || epb > epb_thr) return B200SIM_E_UNSUPPORTED;
+  const long long blocks = (B + epb - 1) / epb;
+  g->G = G;
+  g->epb = (int)epb;
+  g->grid = (int)std::max<long long>(1, std::min<long long>(blocks, m->num_sms));
+  g->smem = st + (size_t)epb * pe;
+  return 0;
+}
+
+template <typename T>
+struct Step2Type { static constexpr bool ok = false; };
+template <> struct Step2Type<float> { static constexpr bool ok = true; };
+template <> struct Step2Type<double> { static constexpr bool ok = true; };
+
+template <typename T>
+int try_launch_step2(const B200SimModel*, Params<T>&, void*, bool* done) { *done = false; return 0; }
+
+template <typename T>
+int launch_step2_impl(const B200SimModel* m, Params<T>& P, void* stream, bool* done) {
+  *done = false;
+  if (m->opt_flags & B200SIM_OPT_STEP_V1) return 0;
+  Geometry g;
+  if (pick_geometry2(m, sizeof(T), P.B, &g) != 0) return 0;
+  *done = true;
+  P.envs_per_block = g.epb;
+  // cp.async.bulk needs 16-byte aligned, 16-byte granular rows per environment
+  P.flags &= ~F_BULK_IN;
+  if (!(m->opt_flags & B200SIM_OPT_NO_BULK_IN) && P.Hin && P.Vin && ((uintptr_t)P.Hin % 16 == 0) && ((uintptr_t)P.Vin % 16 == 0) &&
+      (((size_t)m->nL * 6 * sizeof(T)) % 16 == 0))
+    P.flags |= F_BULK_IN;
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev != m->device) CK(cudaSetDevice(m->device));
+  const int rc = launch_step2<T>(P, g.G, g.grid, g.epb * g.G, g.smem, (cudaStream_t)stream, !(m->opt_flags & B200SIM_OPT_NO_PDL));
+  if (dev != m->device) cudaSetDevice(dev);
+  return rc;
+}
+template <>
+int try_launch_step2<float>(const B200SimModel* m, Params<float>& P, void* stream, bool* done) { return launch_step2_impl(m, P, stream, done); }
+template <>
+int try_launch_step2<double>(const B200SimModel* m, Params<double>& P, void* stream, bool* done) { return launch_step2_impl(m, P, stream, done); }
+
 template <typename T>
 int launch(const B200SimModel* m, Params<T>& P, int dtype, void* stream) {
+  if (specialised_step_applies(m, P) && !P.over_count && !P.work_count) {
+    bool done = false;
+    const int rc2 = try_launch_step2<T>(m, P, stream, &done);
+    if (done) return rc2;
+  }
   Geometry g;
   int rc = pick_geometry(m, dtype, P.B, &g);
   if (rc) return rc;
@@ -721,7 +791,35 @@ int b200sim_model_create(const B200SimModelDesc* d, int device, B200SimModel** o
       const int nrows = (int)rows.size() / Gr;
       const int off = rows.empty() ? 0 : push(rows.data(), rows.size());
       if (pass == 0) { m->o_rows8 = off; m->n_rows8 = nrows; } else { m->o_rows16 = off; m->n_rows16 = nrows; }
+      // step2_kernel format: the children ADD their contribution into the parent's record, siblings that share a
+      // row take turns in the order of their rank:
+      //   bits 0-7 link | 8-15 parent | 16-19 rank among the siblings of this row | 20-23 sub-rounds of the row | 27-28 joint type
+      std::vector<int> rows2(rows.size(), 0xFF);
+      for (int r = 0; r < nrows; ++r) {
+        int nsub = 1;
+        std::vector<int> rank(Gr, 0);
+        for (int k = 0; k < Gr; ++k) {
+          const int ent = rows[(size_t)r * Gr + k];
+          if ((ent & 0xFF) == 0xFF) continue;
+          const int par = (ent >> 8) & 0xFF;
+          for (int k2 = 0; k2 < k; ++k2) {
+            const int e2 = rows[(size_t)r * Gr + k2];
+            if ((e2 & 0xFF) != 0xFF && ((e2 >> 8) & 0xFF) == par) ++rank[k];
+          }
+          nsub = std::max(nsub, rank[k] + 1);
+        }
+        if (nsub > 15) ok = false;
+        for (int k = 0; k < Gr; ++k) {
+          const int ent = rows[(size_t)r * Gr + k];
+          int e2 = 0xFF | (nsub << 20);
+          if ((ent & 0xFF) != 0xFF) e2 = (ent & 0xFFFF) | (rank[k] << 16) | (nsub << 20) | (ent & (3 << 27));
+          rows2[(size_t)r * Gr + k] = e2;
+        }
+      }
+      const int off2 = rows2.empty() ? 0 : push(rows2.data(), rows2.size());
+      if (pass == 0) m->o_rows2_8 = off2; else m->o_rows2_16 = off2;
     }
+    if (!ok) { m->n_rows8 = 0; m->n_rows16 = 0; }
   }
   if (m->itab_h.empty()) m->itab_h.push_back(0);
 
@@ -842,7 +940,7 @@ extern "C" int b200sim_debug_block_times(B200SimModel* m, unsigned long long* ou
 }
 
 int b200sim_model_set_options(B200SimModel* m, int32_t options) {
-  if (!m || (options & ~(B200SIM_OPT_TMA_STORE | B200SIM_OPT_RIGID_QP_F32 | B200SIM_OPT_GENERIC_KERNEL | B200SIM_OPT_BULK_IN | B200SIM_OPT_NO_PDL))) return B200SIM_E_INVALID;
+  if (!m || (options & ~(B200SIM_OPT_TMA_STORE | B200SIM_OPT_RIGID_QP_F32 | B200SIM_OPT_GENERIC_KERNEL | B200SIM_OPT_BULK_IN | B200SIM_OPT_NO_PDL | B200SIM_OPT_STEP_V1 | B200SIM_OPT_NO_BULK_IN))) return B200SIM_E_INVALID;
   m->opt_flags = options;
   return 0;
 }
@@ -850,7 +948,16 @@ int b200sim_model_set_options(B200SimModel* m, int32_t options) {
 int b200sim_model_query(const B200SimModel* m, int dtype, int64_t B, int32_t* G, int32_t* epb, int32_t* grid, int32_t* smem) {
   if (!m || B < 1 || (dtype != 0 && dtype != 1)) return B200SIM_E_INVALID;
   Geometry g;
-  int rc = pick_geometry(m, dtype, B, &g);
+  int rc = B200SIM_E_UNSUPPORTED;
+  {
+    // the geometry of the kernel a soft-contact / contact-free `step` of this model launches
+    Params<float> Pq;
+    std::memset(&Pq, 0, sizeof(Pq));
+    Pq.mode = MODE_STEP; Pq.floating = m->floating; Pq.flags = m->flags; Pq.n = m->n; Pq.nc = m->nc; Pq.contact_model = m->contact_model;
+    if (specialised_step_applies(m, Pq) && !(m->opt_flags & B200SIM_OPT_STEP_V1))
+      rc = pick_geometry2(m, dtype == B200SIM_DTYPE_F64 ? 8 : 4, B, &g);
+  }
+  if (rc) rc = pick_geometry(m, dtype, B, &g);
   if (rc) return rc;
   if (G) *G = g.G;
   if (epb) *epb = g.epb;
