@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--model", default="icub_like")
     ap.add_argument("--lanes", type=int, default=0, help="lanes per env (0 = auto)")
+    ap.add_argument("--epb", type=int, default=0, help="diagnostic: cap on the environments per thread block (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-caches", action="store_true", help="diagnostic: do not materialise the cached transforms (B_min traffic)")
     ap.add_argument("--skip-cache", default="", help="diagnostic: letters of caches NOT to write: X (joint transforms), H (link transforms), V (link velocities), B (base transform)")
@@ -219,8 +220,8 @@ def run_b200(args):
     w = 4 if args.dtype == "f32" else 8
 
     model = js.model.JaxSimModel.build_from_model_description(models.urdf(args.model), time_step=1e-3)
-    if args.lanes:
-        model.set_tuning(lanes_per_env=args.lanes)
+    if args.lanes or args.epb:
+        model.set_tuning(lanes_per_env=args.lanes, envs_per_block=args.epb)
     if args.no_tma or args.generic_kernel or args.bulk_in or args.no_pdl or args.step_v1 or args.no_bulk_in:
         model.set_options(tma_store=not args.no_tma, generic_kernel=args.generic_kernel, bulk_in=args.bulk_in, pdl=not args.no_pdl,
                           step_v1=args.step_v1, no_bulk_in=args.no_bulk_in)

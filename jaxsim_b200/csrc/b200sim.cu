@@ -40,6 +40,10 @@ struct B200SimModel {
       o_pt_start = 0, o_pt_idx = 0, o_pt_body = 0, o_pt_enabled = 0, o_anc = 0, o_ldepth = 0;
   int o_rows8 = 0, n_rows8 = 0, o_rows16 = 0, n_rows16 = 0;  // packed level-walk rows for G = 8 / 16 (0 rows: not available)
   int o_rows2_8 = 0, o_rows2_16 = 0;                          // the same rows in the format of step2_kernel
+  // compact integer table of step2_kernel (only what it reads: a smaller block-static footprint buys environments)
+  std::vector<int> itab2_h;
+  int* itab2_d = nullptr;
+  int t2_parent = 0, t2_jtype = 0, t2_pt_start = 0, t2_pt_idx = 0, t2_pt_body = 0, t2_pt_enabled = 0, t2_rows8 = 0, t2_rows16 = 0;
   double reg = 1e-6;
   double rx_tc = 0.02, rx_zeta = 1.0, rx_dmin = 0.9, rx_dmax = 0.95, rx_width = 1e-3, rx_mid = 0.5, rx_pow = 2.0;  // RelaxedRigid
   unsigned long long* dbg_d = nullptr;  // debug counters, allocated by b200sim_debug_counters
@@ -140,9 +144,13 @@ int pick_geometry(const B200SimModel* m, int dtype, long long B, Geometry* g) {
   long long epb_thr = max_threads_for(G) / G;
   long long epb = std::min(epb_smem, epb_thr);
   if (m->tune_epb > 0) epb = std::min<long long>(epb, m->tune_epb);
-  // spread a small batch over all SMs
+  // spread the batch over all SMs in equally filled trips of the grid-stride loop (a last trip with a few
+  // environments costs a full trip: 16 384 environments = 111 per SM run as 4 x 28, not 3 x 32 + 15)
   long long per_sm = (B + m->num_sms - 1) / m->num_sms;
-  if (m->tune_epb == 0) epb = std::min(epb, std::max<long long>(per_sm, 1));
+  if (m->tune_epb == 0) {
+    const long long trips = (per_sm + epb - 1) / std::max<long long>(epb, 1);
+    epb = std::min(epb, std::max<long long>((per_sm + trips - 1) / std::max<long long>(trips, 1), 1));
+  }
   // whole warps only
   epb = ((epb + wg - 1) / wg) * wg;
   while (epb > wg && (epb > epb_smem || epb > epb_thr)) epb -= wg;
@@ -245,22 +253,34 @@ bool specialised_step_applies(const B200SimModel* m, const Params<T>& P) {
 
 // The second-generation kernel (b200sim_step2.cuh) serves what the specialised instance serves, for
 // float / double, G = 8 / 16 lanes and trees with nL <= 4 G links.
+size_t static_smem_bytes2(const B200SimModel* m, size_t ts) {
+  size_t w = (size_t)m->nL * CREC * ts;
+  w += (((size_t)m->nc * 3 + 3) & ~size_t(3)) * ts;
+  w += (((size_t)m->itab2_h.size() + 3) & ~size_t(3)) * sizeof(int);
+  return w;
+}
+
 int pick_geometry2(const B200SimModel* m, size_t ts, long long B, Geometry* g) {
-  const size_t st = static_smem_bytes(m, ts);
-  const size_t pe = step2_env_words(ts, m->nL, m->nc) * ts;
+  if (m->itab2_h.empty() || !m->itab2_d) return B200SIM_E_UNSUPPORTED;
+  const size_t st = static_smem_bytes2(m, ts);
   const size_t budget = (size_t)m->max_smem_optin - 1024;
-  if (st + pe > budget) return B200SIM_E_TOO_LARGE;
   int G = m->tune_G;
   if (G == 0) G = m->nL > 32 ? 16 : 8;
   if (G != 8 && G != 16) return B200SIM_E_UNSUPPORTED;
   if (m->nL > 4 * G) return B200SIM_E_UNSUPPORTED;
+  if (((size_t)m->nL * 6 * ts) % 16 != 0) return B200SIM_E_UNSUPPORTED;  // (nL,6) rows of an environment leave / arrive as one bulk copy
+  const size_t pe = step2_env_words(ts, m->nL, m->nc, G) * ts;
+  if (st + pe > budget) return B200SIM_E_TOO_LARGE;
   const int wg = 32 / G;
   const long long epb_smem = (long long)((budget - st) / pe);
   const long long epb_thr = step2_max_threads(ts, G) / G;
   long long epb = std::min(epb_smem, epb_thr);
   if (m->tune_epb > 0) epb = std::min<long long>(epb, m->tune_epb);
   const long long per_sm = (B + m->num_sms - 1) / m->num_sms;
-  if (m->tune_epb == 0) epb = std::min(epb, std::max<long long>(per_sm, 1));
+  if (m->tune_epb == 0) {  // equally filled trips of the grid-stride loop
+    const long long trips = (per_sm + epb - 1) / std::max<long long>(epb, 1);
+    epb = std::min(epb, std::max<long long>((per_sm + trips - 1) / std::max<long long>(trips, 1), 1));
+  }
   epb = ((epb + wg - 1) / wg) * wg;  // whole warps
   while (epb > wg && (epb > epb_smem || epb > epb_thr)) epb -= wg;
   if (epb < 1 || epb > epb_smem || epb > epb_thr) return B200SIM_E_UNSUPPORTED;
@@ -273,11 +293,6 @@ int pick_geometry2(const B200SimModel* m, size_t ts, long long B, Geometry* g) {
 }
 
 template <typename T>
-struct Step2Type { static constexpr bool ok = false; };
-template <> struct Step2Type<float> { static constexpr bool ok = true; };
-template <> struct Step2Type<double> { static constexpr bool ok = true; };
-
-template <typename T>
 int try_launch_step2(const B200SimModel*, Params<T>&, void*, bool* done) { *done = false; return 0; }
 
 template <typename T>
@@ -286,8 +301,16 @@ int launch_step2_impl(const B200SimModel* m, Params<T>& P, void* stream, bool* d
   if (m->opt_flags & B200SIM_OPT_STEP_V1) return 0;
   Geometry g;
   if (pick_geometry2(m, sizeof(T), P.B, &g) != 0) return 0;
+  // the cache outputs leave with cp.async.bulk: 16-byte aligned leaves
+  if (((uintptr_t)P.iXl | (uintptr_t)P.W_H_L | (uintptr_t)P.W_v) % 16 != 0) return 0;
   *done = true;
   P.envs_per_block = g.epb;
+  P.ws2_words = (int)step2_env_words(sizeof(T), m->nL, m->nc, g.G);
+  // the kernel stages the compact integer table
+  P.itab = m->itab2_d;
+  P.itab_words = (int)m->itab2_h.size();
+  P.o_parent = m->t2_parent; P.o_jtype = m->t2_jtype; P.o_pt_start = m->t2_pt_start; P.o_pt_idx = m->t2_pt_idx;
+  P.o_pt_body = m->t2_pt_body; P.o_pt_enabled = m->t2_pt_enabled; P.o_rows2_8 = m->t2_rows8; P.o_rows2_16 = m->t2_rows16;
   // cp.async.bulk needs 16-byte aligned, 16-byte granular rows per environment
   P.flags &= ~F_BULK_IN;
   if (!(m->opt_flags & B200SIM_OPT_NO_BULK_IN) && P.Hin && P.Vin && ((uintptr_t)P.Hin % 16 == 0) && ((uintptr_t)P.Vin % 16 == 0) &&
@@ -821,6 +844,22 @@ int b200sim_model_create(const B200SimModelDesc* d, int device, B200SimModel** o
     }
     if (!ok) { m->n_rows8 = 0; m->n_rows16 = 0; }
   }
+  if (m->n_rows8 > 0 && m->n_rows16 > 0) {
+    auto push2 = [&](const int* src, size_t cnt) {
+      int off = (int)m->itab2_h.size();
+      m->itab2_h.insert(m->itab2_h.end(), src, src + cnt);
+      return off;
+    };
+    const int* it = m->itab_h.data();
+    m->t2_parent = push2(it + m->o_parent, nL);
+    m->t2_jtype = push2(it + m->o_jtype, nL);
+    m->t2_pt_start = push2(it + m->o_pt_start, nL + 1);
+    m->t2_pt_idx = push2(it + m->o_pt_idx, nc);
+    m->t2_pt_body = push2(it + m->o_pt_body, nc);
+    m->t2_pt_enabled = push2(it + m->o_pt_enabled, nc);
+    m->t2_rows8 = push2(it + m->o_rows2_8, (size_t)m->n_rows8 * 8);
+    m->t2_rows16 = push2(it + m->o_rows2_16, (size_t)m->n_rows16 * 16);
+  }
   if (m->itab_h.empty()) m->itab_h.push_back(0);
 
   // ---- upload
@@ -848,6 +887,13 @@ int b200sim_model_create(const B200SimModelDesc* d, int device, B200SimModel** o
     if (e == cudaSuccess) e = cudaMemcpy(m->itab_d, padded.data(), padded.size() * sizeof(int), cudaMemcpyHostToDevice);
     rc = (int)e;
   }
+  if (!rc && !m->itab2_h.empty()) {
+    std::vector<int> padded(((m->itab2_h.size() + 3) & ~size_t(3)) + 4, 0);
+    std::copy(m->itab2_h.begin(), m->itab2_h.end(), padded.begin());
+    e = cudaMalloc((void**)&m->itab2_d, padded.size() * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpy(m->itab2_d, padded.data(), padded.size() * sizeof(int), cudaMemcpyHostToDevice);
+    rc = (int)e;
+  }
   cudaSetDevice(prev);
   if (rc) { b200sim_model_destroy(m); return rc; }
   // the model must fit at least one environment per block in both precisions we may be asked for
@@ -864,7 +910,7 @@ void b200sim_model_destroy(B200SimModel* m) {
   cudaGetDevice(&prev);
   cudaSetDevice(m->device);
   cudaFree(m->cst_f); cudaFree(m->cst_d); cudaFree(m->csuc_f); cudaFree(m->csuc_d);
-  cudaFree(m->pt_f); cudaFree(m->pt_d); cudaFree(m->itab_d); cudaFree(m->rigid_scratch); cudaFree(m->dbg_d);
+  cudaFree(m->pt_f); cudaFree(m->pt_d); cudaFree(m->itab_d); cudaFree(m->itab2_d); cudaFree(m->rigid_scratch); cudaFree(m->dbg_d);
   cudaFree(m->cst_dd); cudaFree(m->csuc_dd); cudaFree(m->pt_dd);
   cudaSetDevice(prev);
   delete m;

@@ -50,9 +50,7 @@ int step2_max_threads(size_t scalar_bytes, int G) {
   return 0;
 }
 
-size_t step2_env_words(size_t scalar_bytes, int nL, int nc) {
-  return scalar_bytes == 4 ? env2_ws_words<float>(nL, nc) : env2_ws_words<double>(nL, nc);
-}
+size_t step2_env_words(size_t scalar_bytes, int nL, int nc, int G) { return env2_ws_words(scalar_bytes, nL, nc, G); }
 
 template <>
 int launch_step2<float>(const Params<float>& P, int G, int grid, int threads, size_t smem, cudaStream_t st, bool pdl) {

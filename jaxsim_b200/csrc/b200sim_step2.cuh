@@ -2,29 +2,33 @@
 // soft-contact configuration): `jaxsim.api.model.step` of a floating-base URDF model with
 // SoftContacts (or no collidable points) and SemiImplicitEuler, api/model.py:2601-2681.
 //
-// Same mathematics and lane mapping as step_kernel<T,G,1> (b200sim_kernels.cuh: G lanes per
-// environment, ABA in world-aligned link-origin frames, level walks over packed rows); what
-// changes is everything that bounded that kernel on B200 (profiles/r01_step_kernel_v8_warm.md:
-// 7 resident warps per SM, 28 environments in flight, 16 % of the stall samples waiting for
-// instructions, 37 % in the output phase):
+// Same mathematics as step_kernel<T,G,1> (b200sim_kernels.cuh: G lanes per environment, ABA in
+// world-aligned link-origin frames, level walks over packed rows).  What changed is dictated by
+// what bounds the step on B200: at large batch the LSU data pipe of the SM (shared-memory +
+// global wavefronts, 1 per cycle) runs at 76-83 % (profiles/r02_step2_lsu_bound.md), at batch
+// 4096 it is the latency of one environment through one warp.  So this kernel minimises
+// WAVEFRONTS per environment:
 //
-//  * 44-word link record instead of 60.  Pass 2 of the ABA no longer lets the parent GATHER its
-//    children's shifted articulated inertias (which forced every link to keep I^A, p^A next to
-//    U, 1/d, u): the child ADDS its contribution into the parent's record (ordered sub-rounds
-//    for siblings of the same row: deterministic, race free), so U, 1/d, u reuse the link's own
-//    dead I^A slots; the spatial acceleration reuses the slot of c_i; the velocity lives in the
-//    I^A area while kinematics are needed.  4.8 KB per environment instead of 6.4 KB: 44-46
-//    environments (11 warps) per SM instead of 28 (7 warps).
-//  * <= 168 registers (384-thread launch bound), no 4x unrolled output phase: the SASS shrinks
-//    from 4.8k to ~3k instructions (instruction fetch was 16 % of the stall samples).
-//  * the cached kinematics of the input state ALWAYS arrive with two cp.async.bulk (TMA) per
-//    environment when the rows are 16-byte granular, joint state / torques go to registers.
-//  * one code path for "kinematics of a joint state" (joint transforms + FK level walk): it
-//    serves the un-cached start, the steps of a fused rollout and the cache outputs of the last
-//    step; the joint adjoints leave as 128-bit stores straight from registers (no staging area,
-//    which is what capped the old workspace at 56 words per link in its final phase).
-//  * the 6x6 floating-base solve runs redundantly in every lane of the group (same latency, no
-//    shared-memory round trip of the base acceleration).
+//  * Two lane mappings inside a warp.  Link-/point-parallel phases use G consecutive lanes per
+//    environment (all lanes busy).  The level walks (ABA pass 2 / 3, FK) only have 3-5 links per
+//    tree level: they use the TRANSPOSED mapping lane = slot * (32/G) + environment, so the busy
+//    lanes of the 32/G environments of a warp are packed into the low quarter-warps and a 128-bit
+//    shared-memory access costs 2 wavefronts instead of 4.  The two mappings exchange data through
+//    the environments' shared-memory records only, separated by __syncwarp().
+//  * 44-word link record instead of 60: in pass 2 the child ADDS its shifted articulated inertia
+//    into the parent's record (ordered sub-rounds for siblings of one row: deterministic, race
+//    free) instead of the parent gathering its children, so U, 1/d, u reuse the link's own dead
+//    I^A slots; the spatial acceleration reuses the slot of c_i.  Every group of fields that is
+//    read together starts on a 16-byte boundary: whole record rows move with LDS.128 / STS.128.
+//  * Link poses are kept as 3x4 rows [R | p] like the (B,nL,4,4) leaves, so the cached input rows
+//    are copied, not re-packed, and the cache outputs of the last step are staged in shared
+//    memory in EXACTLY the layout of the output leaves -- W_H_L (nL,4,4), W_v (nL,6) and the joint
+//    adjoints (nL,6,6) -- and leave with three cp.async.bulk (TMA) per environment: no global
+//    store wavefronts (the per-link 128-bit stores of the 6x6 adjoints alone cost 200 L1 tag
+//    requests per environment).  Inputs arrive with two cp.async.bulk per environment.
+//  * One code path for "kinematics of a joint state" (joint transforms + FK walk) with run-time
+//    strides: it serves the un-cached start, the steps of a fused rollout (records) and the cache
+//    outputs of the last step (output-layout staging).
 #pragma once
 
 #include "b200sim_kernels.cuh"
@@ -32,12 +36,9 @@
 namespace b200sim {
 
 constexpr int R2 = 44;  // words per link record (44 = 4*11: 128-bit rows of consecutive links hit distinct banks)
-// Every group of fields that is read together starts on a 128-bit boundary, so the level walks move
-// whole record rows with LDS.128 / STS.128.
 // kinematics view of the record
-constexpr int K_R = 0;    // 9  world rotation (relative rotation before the FK walk)
-constexpr int K_P = 9;    // 3  world position (relative translation before the FK walk)
-constexpr int K_V = 12;   // 6  velocity of the link origin, world axes (lin, ang)
+constexpr int K_H = 0;    // 12 rows [R | p] of the world pose (relative pose before the FK walk)
+constexpr int K_V = 12;   // 6  velocity of the link origin, world axes (lin, ang); word 0 carries sd before the walk
 // ABA view: articulated inertia [[A,B],[B^T,D]] + bias force, children add into it
 constexpr int K_IA = 0;   // 6 (sym)
 constexpr int K_IB = 6;   // 9
@@ -49,11 +50,26 @@ constexpr int K_U = 0;    // 6
 constexpr int K_DINV = 6;
 constexpr int K_UU = 7;
 constexpr int K_C = 28;   // 6  c_i, overwritten by the spatial acceleration a_i in pass 3
-constexpr int K_S = 34, K_SD = 35;
-constexpr int K_AX = 36;  // 3  joint axis, world axes
-constexpr int K_SDD = 39;
-constexpr int K_RR = 40;  // 3  p_i - p_parent, world axes
-constexpr int K_TREF = 43;
+constexpr int K_AX = 34;  // 3  joint axis, world axes
+constexpr int K_RR = 37;  // 3  p_i - p_parent, world axes
+constexpr int K_S = 40, K_SD = 41, K_SDD = 42, K_TREF = 43;
+
+constexpr int S2_NT = 4;  // link trips of the unrolled phases: nL <= 4 G
+
+// shared-memory words of T per environment: the records + point records of the dynamics, or the
+// output staging of the last step ([nL x 16 | nL x 6 | nL x 36]), whichever is larger, + the mbarrier;
+// padded so that consecutive environments of a warp sit 2 or 6 (G = 8) / 4 (G = 16) 16-byte rows apart
+// modulo 8: the transposed walks then read 128-bit rows of neighbouring links without bank conflicts
+__host__ __device__ inline size_t env2_ws_words(size_t ts, int nL, int nc, int G) {
+  size_t w = (size_t)nL * R2 + (size_t)nc * PTREC;
+  const size_t f = (size_t)nL * 16 + (((size_t)nL * 6 + 3) & ~size_t(3)) + (size_t)nL * 36;
+  if (f > w) w = f;
+  w = (w + 3) & ~size_t(3);
+  w += 16 / ts;
+  const size_t per_row = 16 / ts;
+  while (G == 16 ? ((w / per_row) % 8 != 4) : ((w / per_row) % 4 != 2)) w += per_row;
+  return w;
+}
 
 // whole 16-byte rows of shared memory (p 16-byte aligned; N * sizeof(T) a multiple of 16)
 template <int N>
@@ -86,7 +102,6 @@ __device__ __forceinline__ void stv(double* p, const double* d) {
 #pragma unroll
   for (int k = 0; k < N; k += 2) *reinterpret_cast<double2*>(p + k) = make_double2(d[k], d[k + 1]);
 }
-
 // six consecutive words at an 8-byte (float) / 16-byte (double) boundary
 __device__ __forceinline__ void ld6(const float* p, float* d) {
 #pragma unroll
@@ -96,18 +111,25 @@ __device__ __forceinline__ void ld6(const float* p, float* d) {
   }
 }
 __device__ __forceinline__ void ld6(const double* p, double* d) { ldv<6>(p, d); }
+__device__ __forceinline__ void st6(float* p, const float* d) {
+#pragma unroll
+  for (int k = 0; k < 6; k += 2) *reinterpret_cast<float2*>(p + k) = make_float2(d[k], d[k + 1]);
+}
+__device__ __forceinline__ void st6(double* p, const double* d) { stv<6>(p, d); }
 
-constexpr int S2_NT = 4;  // link trips of the unrolled input phase: nL <= 4 G
-
+// rows [R | p] (3x4) <-> R (row-major 3x3), p
 template <typename T>
-__host__ __device__ inline size_t env2_ws_words(int nL, int nc) {
-  size_t w = (size_t)nL * R2 + (size_t)nc * PTREC;
-  w = (w + 3) & ~size_t(3);
-  return w + 16 / sizeof(T);  // + the mbarrier of the environment's bulk loads
+__device__ __forceinline__ void split_pose(const T* H, T* R, T* p) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    R[3 * r] = H[4 * r]; R[3 * r + 1] = H[4 * r + 1]; R[3 * r + 2] = H[4 * r + 2];
+    p[r] = H[4 * r + 3];
+  }
 }
 template <typename T>
-__device__ __forceinline__ unsigned long long* env2_mbar(T* ws, int nL, int nc) {
-  return reinterpret_cast<unsigned long long*>(ws + env2_ws_words<T>(nL, nc) - 16 / sizeof(T));
+__device__ __forceinline__ void st_pose(T* dst, const T* R, const T* p) {
+  const T H[12] = {R[0], R[1], R[2], p[0], R[3], R[4], R[5], p[1], R[6], R[7], R[8], p[2]};
+  stv<12>(dst, H);
 }
 
 #define B200SIM_MARK2(k)                                                                                       \
@@ -121,6 +143,7 @@ __device__ __forceinline__ unsigned long long* env2_mbar(T* ws, int nL, int nc) 
 template <typename T, int G, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) step2_kernel(const Params<T> P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int W4 = 32 / G;  // environments per warp
   T* sm_cst = reinterpret_cast<T*>(smem_raw);
   const int nL = P.nL, n = P.n, nc = P.nc;
   T* sm_pt = sm_cst + (size_t)nL * CREC;
@@ -141,13 +164,20 @@ __global__ void __launch_bounds__(THREADS, 1) step2_kernel(const Params<T> P) {
   stage_async(sm_itab, P.itab, (int)itab_words);
   __pipeline_commit();
 
-  const int lane = threadIdx.x & (G - 1);
-  const int grp = threadIdx.x / G;
-  const size_t wsw = env2_ws_words<T>(nL, nc);
+  const int lane32 = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // link-parallel mapping: G consecutive lanes per environment
+  const int lane = lane32 & (G - 1);
+  const int grp = warp * W4 + lane32 / G;
+  // walk mapping (transposed): lane32 = slot * W4 + environment
+  const int slot = lane32 / W4;
+  const int wgrp = warp * W4 + (lane32 & (W4 - 1));
+  const size_t wsw = (size_t)P.ws2_words;
   T* ws = ws_base + (size_t)grp * wsw;
+  T* wk = ws_base + (size_t)wgrp * wsw;
   T* ptws = ws + (size_t)nL * R2;
+  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(ws + wsw - 16 / sizeof(T));
   if (lane == 0) {
-    mbar_init(env2_mbar(ws, nL, nc), 1);
+    mbar_init(mbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -171,8 +201,10 @@ __global__ void __launch_bounds__(THREADS, 1) step2_kernel(const Params<T> P) {
   const int flags = P.flags;
   const bool use_cached = P.Hin && P.Vin;
   const bool bulk = use_cached && (flags & F_BULK_IN);
-  const int VW = (nL * 6 + 3) & ~3;  // staging: [V: nL x 6, padded][H: nL x 16]
-  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+  const int VW = (nL * 6 + 3) & ~3;  // input staging: [V: nL x 6, padded][H: nL x 16]
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane32 / G * G));
+  // output staging of the last step, in the layout of the output leaves
+  const int o_FV = nL * 16, o_FX = nL * 16 + VW;
 
   const long long first = (long long)blockIdx.x * P.envs_per_block;
   unsigned in_parity = 0;
@@ -182,15 +214,15 @@ __global__ void __launch_bounds__(THREADS, 1) step2_kernel(const Params<T> P) {
     if (!active) env = env % P.B;  // idle groups shadow distinct valid environments, stores masked
 
     // =========================================================== inputs (one burst)
+    if (lane == 0) tma_store_wait_read();  // the bulk stores of the previous environment have read its staging
     if (bulk) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic accesses of the last trip before the async writes
       __syncwarp();
       if (lane == 0) {
-        unsigned long long* bar = env2_mbar(ws, nL, nc);
         const unsigned bH = (unsigned)(nL * 16 * sizeof(T)), bV = (unsigned)(nL * 6 * sizeof(T));
-        mbar_expect_tx(bar, bH + bV);
-        tma_load_bulk(ws, P.Vin + env * nL * 6, bV, bar);
-        tma_load_bulk(ws + VW, P.Hin + env * nL * 16, bH, bar);
+        mbar_expect_tx(mbar, bH + bV);
+        tma_load_bulk(ws, P.Vin + env * nL * 6, bV, mbar);
+        tma_load_bulk(ws + VW, P.Hin + env * nL * 16, bH, mbar);
       }
     } else if (use_cached) {
       __syncwarp();
@@ -264,7 +296,7 @@ __global__ void __launch_bounds__(THREADS, 1) step2_kernel(const Params<T> P) {
       // overwrite the staging area (22 words per link) from the top: trips over DESCENDING link indices, each
       // reads its links' staged rows (and the parent's position), synchronises, then writes their records.
       if (bulk) {
-        mbar_wait(env2_mbar(ws, nL, nc), in_parity);
+        mbar_wait(mbar, in_parity);
         in_parity ^= 1u;
       } else {
         __syncwarp();  // rows staged by other lanes' cp.async
@@ -285,23 +317,21 @@ __global__ void __launch_bounds__(THREADS, 1) step2_kernel(const Params<T> P) {
           __syncwarp();
           if (i < nL) {
             T* ri = ws + (size_t)i * R2;
-            const T R[9] = {H[0], H[1], H[2], H[4], H[5], H[6], H[8], H[9], H[10]};
             const T p[3] = {H[3], H[7], H[11]};
-            T v[6], tt[3];
+            T tt[3];
             cross3(V + 3, p, tt);  // velocity of the link origin: W_v_lin + w x p
-            v[0] = V[0] + tt[0]; v[1] = V[1] + tt[1]; v[2] = V[2] + tt[2];
-            v[3] = V[3]; v[4] = V[4]; v[5] = V[5];
-            const T K[20] = {R[0], R[1], R[2], R[3], R[4], R[5], R[6], R[7], R[8], p[0], p[1], p[2],
-                             v[0], v[1], v[2], v[3], v[4], v[5], T(0), T(0)};
-            stv<20>(ri, K);
+            stv<12>(ri + K_H, H);
+            const T v8[8] = {V[0] + tt[0], V[1] + tt[1], V[2] + tt[2], V[3], V[4], V[5], T(0), T(0)};
+            stv<8>(ri + K_V, v8);
             if (i > 0) {
               T ax[3], aw[3];
               ldn<3>(sm_cst + (size_t)i * CREC + C_AXIS, ax);
-              mat3_vec(R, ax, aw);
-              const T Q[8] = {aw[0], aw[1], aw[2], T(0), p[0] - pp[0], p[1] - pp[1], p[2] - pp[2], tr_r[t]};
-              stv<8>(ri + K_AX, Q);  // axis, (sdd), r, torque reference
-              ri[K_S] = s_r[t];
-              ri[K_SD] = sd_r[t];
+              aw[0] = H[0] * ax[0] + H[1] * ax[1] + H[2] * ax[2];
+              aw[1] = H[4] * ax[0] + H[5] * ax[1] + H[6] * ax[2];
+              aw[2] = H[8] * ax[0] + H[9] * ax[1] + H[10] * ax[2];
+              const T Q[12] = {T(0), T(0), aw[0], aw[1], aw[2], p[0] - pp[0], p[1] - pp[1], p[2] - pp[2],
+                               s_r[t], sd_r[t], T(0), tr_r[t]};
+              stv<12>(ri + 32, Q);  // (c tail), axis, r, s, sd, (sdd), torque reference
             }
           }
         }
@@ -312,13 +342,10 @@ __global__ void __launch_bounds__(THREADS, 1) step2_kernel(const Params<T> P) {
       for (int t = 0; t < S2_NT; ++t) {
         const int i = lane + t * G;
         if (i >= 1 && i < nL) {
-          T* ri = ws + (size_t)i * R2;
-          ri[K_S] = s_r[t];
-          ri[K_SD] = sd_r[t];
-          ri[K_TREF] = tr_r[t];
+          const T Q[4] = {s_r[t], sd_r[t], T(0), tr_r[t]};
+          stv<4>(ws + (size_t)i * R2 + K_S, Q);
         }
       }
-      __syncwarp();
     }
     B200SIM_MARK2(5);
 
@@ -326,6 +353,7 @@ __global__ void __launch_bounds__(THREADS, 1) step2_kernel(const Params<T> P) {
     // step body (joint transforms + FK walk) on the unchanged joint state
     for (int step = use_cached ? 0 : -1; step < P.nsteps; ++step) {
       const bool last = (step == P.nsteps - 1);
+      T a0[6];
       if (step >= 0) {
         const T* fext_step = P.fext ? P.fext + (long long)step * P.fext_step_stride : nullptr;
         // ======================================================= contacts (point-parallel)
@@ -336,14 +364,14 @@ __global__ void __launch_bounds__(THREADS, 1) step2_kernel(const Params<T> P) {
           const T* rb = ws + (size_t)pt_body[k] * R2;
           T Kb[20];
           ldv<20>(rb, Kb);
-          const T* R = Kb + K_R;
           const T* vl = Kb + K_V;
           const T* w = Kb + K_V + 3;
-          const T pz = Kb[K_P + 2];
           T Lp[3], d[3], pd[3];
           ldn<3>(sm_pt + 3 * k, Lp);
-          mat3_vec(R, Lp, d);
-          const T pcz = pz + d[2];
+          d[0] = Kb[0] * Lp[0] + Kb[1] * Lp[1] + Kb[2] * Lp[2];
+          d[1] = Kb[4] * Lp[0] + Kb[5] * Lp[1] + Kb[6] * Lp[2];
+          d[2] = Kb[8] * Lp[0] + Kb[9] * Lp[1] + Kb[10] * Lp[2];
+          const T pcz = Kb[11] + d[2];
           cross3(w, d, pd);
           pd[0] += vl[0]; pd[1] += vl[1]; pd[2] += vl[2];
           T* pw = ptws + (size_t)k * PTREC;
@@ -403,8 +431,8 @@ __global__ void __launch_bounds__(THREADS, 1) step2_kernel(const Params<T> P) {
           const T* c = sm_cst + (size_t)i * CREC;
           T Kk[20];
           ldv<20>(ri, Kk);
-          const T* R = Kk + K_R;
-          const T* p = Kk + K_P;
+          T R[9], p[3];
+          split_pose(Kk, R, p);
           const T* v = Kk + K_V;
           T fe[3] = {T(0), T(0), T(0)}, ne[3] = {T(0), T(0), T(0)};
           if (env_touches) {
@@ -428,10 +456,12 @@ __global__ void __launch_bounds__(THREADS, 1) step2_kernel(const Params<T> P) {
             ne[0] -= t[0]; ne[1] -= t[1]; ne[2] -= t[2];
           }
           // link inertia in world axes about the link origin
-          const T mass = c[C_MASS];
-          T com[3], cw[3], Dl[6];
-          ldn<3>(c + C_COM, com);
-          ldn<6>(c + C_DL, Dl);
+          T Cc[16];
+          ldv<16>(c + C_MASS, Cc);  // mass, com, D_link, limit spring / damper, limits, friction
+          const T mass = Cc[0];
+          const T* com = Cc + (C_COM - C_MASS);
+          const T* Dl = Cc + (C_DL - C_MASS);
+          T cw[3];
           mat3_vec(R, com, cw);
           T Dw[6];
           {
@@ -463,9 +493,10 @@ __global__ void __launch_bounds__(THREADS, 1) step2_kernel(const Params<T> P) {
           if (i > 0) {
             // c_i = v x vJ (rbda/aba.py:143-144) and the resultant joint torque (api/actuation_model.py:7-126)
             const int jt = jtypes[i];
-            const T sdi = ri[K_SD];
-            T aw[3];
-            ldn<3>(ri + K_AX, aw);
+            T Q[12];
+            ldv<12>(ri + 32, Q);  // (c tail), axis, r, s, sd, (sdd), torque reference
+            const T* aw = Q + (K_AX - 32);
+            const T si = Q[K_S - 32], sdi = Q[K_SD - 32], tref = Q[K_TREF - 32];
             T cc[6];
             const T vJ[3] = {sdi * aw[0], sdi * aw[1], sdi * aw[2]};
             if (jt == 1) {
@@ -475,17 +506,19 @@ __global__ void __launch_bounds__(THREADS, 1) step2_kernel(const Params<T> P) {
               cross3(v + 3, vJ, cc);
               cc[3] = cc[4] = cc[5] = T(0);
             }
-            stn<6>(ri + K_C, cc);
-            const T tref = ri[K_TREF];
-            const T si = ri[K_S];
-            const T lower = min_t(si - c[C_SMIN], T(0));
-            const T upper = max_t(si - c[C_SMAX], T(0));
-            T tlim = -c[C_KS] * (lower + upper);
-            tlim = tlim - tlim * c[C_KD] * sdi;
+            {
+              const T c8[8] = {cc[0], cc[1], cc[2], cc[3], cc[4], cc[5], aw[0], aw[1]};
+              stv<8>(ri + K_C, c8);
+            }
+            const T* lc = Cc + (C_KS - C_MASS);  // KS KD SMIN SMAX KC KV
+            const T lower = min_t(si - lc[2], T(0));
+            const T upper = max_t(si - lc[3], T(0));
+            T tlim = -lc[0] * (lower + upper);
+            tlim = tlim - tlim * lc[1] * sdi;
             T tfr = T(0);
             if (P.enable_friction) {
               const T sg = (sdi > T(0)) ? T(1) : ((sdi < T(0)) ? T(-1) : T(0));
-              tfr = -(c[C_KC] * sg + c[C_KV] * sdi);
+              tfr = -(lc[4] * sg + lc[5] * sdi);
             }
             const T tt = tref + tfr + tlim;
             const T av = abs_t(sdi);
@@ -498,7 +531,7 @@ __global__ void __launch_bounds__(THREADS, 1) step2_kernel(const Params<T> P) {
             if (!last && P.tau && P.tau_step_stride)
               cp_async_elem(ri + K_TREF, P.tau + (long long)(step + 1) * P.tau_step_stride + env * n + (i - 1));
           }
-          // articulated inertia init (overwrites R, p, v): A = m 1, B = -m S(c_w), D = D_w
+          // articulated inertia init (overwrites the pose and the velocity): A = m 1, B = -m S(c_w), D = D_w
           T IA[28];
           IA[0] = mass; IA[1] = T(0); IA[2] = T(0); IA[3] = mass; IA[4] = T(0); IA[5] = mass;
           IA[6] = T(0);            IA[7] = mass * cw[2];   IA[8] = -mass * cw[1];
@@ -515,21 +548,22 @@ __global__ void __launch_bounds__(THREADS, 1) step2_kernel(const Params<T> P) {
         B200SIM_MARK2(7);
 
         // ======================================================= ABA pass 2 (rbda/aba.py:184-234), leaves first
+        // transposed lane mapping from here to the end of pass 3
         {
-          int e = nrows > 0 ? rows[(nrows - 1) * G + lane] : 0xFF;
+          int e = nrows > 0 ? rows[(nrows - 1) * G + slot] : 0xFF;
           for (int r = nrows - 1; r >= 0; --r) {
             __syncwarp();
-            const int en = r > 0 ? rows[(r - 1) * G + lane] : 0xFF;
+            const int en = r > 0 ? rows[(r - 1) * G + slot] : 0xFF;
             const bool valid = (e & 0xFF) != 0xFF;
             const int nsub = (e >> 20) & 15;
             const int rank = (e >> 16) & 15;
             T X[27];  // contribution to the parent: A(6) B(9) D(6) pA(6), about the parent's origin
-            T* rp = ws + (size_t)((e >> 8) & 0xFF) * R2;
+            T* rp = wk + (size_t)((e >> 8) & 0xFF) * R2;
             if (valid) {
-              T* ri = ws + (size_t)(e & 0xFF) * R2;
+              T* ri = wk + (size_t)(e & 0xFF) * R2;
               const int jt = (e >> 27) & 3;
-              T W[44];
-              ldv<44>(ri, W);
+              T W[40];
+              ldv<40>(ri, W);
               T* A = W + K_IA;
               T* Bm = W + K_IB;
               T* D = W + K_ID;
@@ -626,11 +660,10 @@ __global__ void __launch_bounds__(THREADS, 1) step2_kernel(const Params<T> P) {
         }
         B200SIM_MARK2(8);
 
-        // ======================================================= base acceleration (rbda/aba.py:240-242), every lane
-        T a0[6];
-        {
+        // ======================================================= base acceleration (rbda/aba.py:240-242)
+        if (slot == 0) {
           T W[28];
-          ldv<28>(ws, W);
+          ldv<28>(wk, W);
           const T* A = W + K_IA;
           const T* Bm = W + K_IB;
           const T* D = W + K_ID;
@@ -644,48 +677,54 @@ __global__ void __launch_bounds__(THREADS, 1) step2_kernel(const Params<T> P) {
             for (int bb = 0; bb < 3; ++bb) { M[a][3 + bb] = Bm[3 * a + bb]; M[3 + bb][a] = Bm[3 * a + bb]; }
           M[3][3] = D[0]; M[3][4] = D[1]; M[3][5] = D[2]; M[4][4] = D[3]; M[4][5] = D[4]; M[5][5] = D[5];
           M[4][3] = D[1]; M[5][3] = D[2]; M[5][4] = D[4];
-          solve6_spd_neg(M, pA, a0);
-          if (lane == 0) {
-            const T a8[8] = {a0[0], a0[1], a0[2], a0[3], a0[4], a0[5], T(0), T(0)};
-            stv<8>(ws + K_C, a8);
-          }
+          T x0[6];
+          solve6_spd_neg(M, pA, x0);
+          const T a8[8] = {x0[0], x0[1], x0[2], x0[3], x0[4], x0[5], T(0), T(0)};
+          stv<8>(wk + K_C, a8);
         }
         B200SIM_MARK2(9);
 
         // ======================================================= ABA pass 3 (rbda/aba.py:244-282), root first
         {
-          int e = nrows > 0 ? rows[lane] : 0xFF;
+          int e = nrows > 0 ? rows[slot] : 0xFF;
           for (int r = 0; r < nrows; ++r) {
             __syncwarp();
-            const int en = (r + 1 < nrows) ? rows[(r + 1) * G + lane] : 0xFF;
+            const int en = (r + 1 < nrows) ? rows[(r + 1) * G + slot] : 0xFF;
             if ((e & 0xFF) != 0xFF) {
-              T* ri = ws + (size_t)(e & 0xFF) * R2;
-              const T* rp = ws + (size_t)((e >> 8) & 0xFF) * R2;
+              T* ri = wk + (size_t)(e & 0xFF) * R2;
+              const T* rp = wk + (size_t)((e >> 8) & 0xFF) * R2;
               const int jt = (e >> 27) & 3;
-              T ap[8], U[8], W[16];
-              ldv<8>(rp + K_C, ap);  // parent's acceleration (+ its s, sd)
+              T ap[8], U[8], W[12];
+              ldv<8>(rp + K_C, ap);  // parent's acceleration (+ two words of its axis)
               ldv<8>(ri + K_U, U);   // U, 1/d, u
-              ldv<16>(ri + K_C, W);  // c, s, sd, axis, (sdd), r, tref
+              ldv<12>(ri + K_C, W);  // c, axis, r
               const T* cI = W;
-              T* aw = W + (K_AX - K_C);
+              const T* aw = W + (K_AX - K_C);
               const T* rr = W + (K_RR - K_C);
-              T a[6];
+              T a[8];
               cross3(ap + 3, rr, a);
               a[0] += ap[0] + cI[0]; a[1] += ap[1] + cI[1]; a[2] += ap[2] + cI[2];
               a[3] = ap[3] + cI[3]; a[4] = ap[4] + cI[4]; a[5] = ap[5] + cI[5];
               const T sdd = (U[7] - (U[0] * a[0] + U[1] * a[1] + U[2] * a[2] + U[3] * a[3] + U[4] * a[4] + U[5] * a[5])) * U[6];
               if (jt == 1) { a[3] += sdd * aw[0]; a[4] += sdd * aw[1]; a[5] += sdd * aw[2]; }
               else { a[0] += sdd * aw[0]; a[1] += sdd * aw[1]; a[2] += sdd * aw[2]; }
-#pragma unroll
-              for (int k = 0; k < 6; ++k) W[k] = a[k];
-              aw[3] = sdd;           // K_SDD follows the axis
-              stv<12>(ri + K_C, W);  // a, s, sd, axis, sdd
+              a[6] = aw[0]; a[7] = aw[1];
+              stv<8>(ri + K_C, a);
+              ri[K_SDD] = sdd;
             }
             e = en;
           }
+          __pipeline_wait_prior(0);  // next step's torque references have landed
           __syncwarp();
         }
         B200SIM_MARK2(10);
+        // back to the link-parallel mapping: the base acceleration of this lane's environment
+        {
+          T a8[8];
+          ldv<8>(ws + K_C, a8);
+#pragma unroll
+          for (int k = 0; k < 6; ++k) a0[k] = a8[k];
+        }
 
         // ======================================================= semi-implicit Euler, base (api/integrators.py:14-88)
         {
@@ -746,126 +785,160 @@ __global__ void __launch_bounds__(THREADS, 1) step2_kernel(const Params<T> P) {
           quat_to_dcm(b.qn, b.R);
         }
         B200SIM_MARK2(11);
-        __pipeline_wait_prior(0);  // next step's torque references have landed
       }
 
       // ========================================================= joints: Euler update + joint transforms
-      // (api/kin_dyn_parameters.py:396-451) of the state the FK walk below needs: the next fused step's, or the
-      // new state's for the cache outputs
+      // (api/kin_dyn_parameters.py:396-451) of the state the FK walk below needs: the next fused step's (in the
+      // records) or the new state's for the cache outputs (in the output staging, which aliases the records:
+      // every lane first reads the joint state of its links, then all write)
       const bool want_caches = last && (P.W_H_L || P.W_v);
       const bool need_kin = !last || want_caches || (P.iXl != nullptr);
-      for (int i = 1 + lane; i < nL; i += G) {
-        T* ri = ws + (size_t)i * R2;
-        T sdn = ri[K_SD], sn = ri[K_S];
-        if (step >= 0) {
-          sdn += dt * ri[K_SDD];
-          sn += dt * sdn;
-          ri[K_SD] = sdn;
-          ri[K_S] = sn;
-          if (last && active) {
-            P.sd_o[env * n + (i - 1)] = sdn;
-            P.s_o[env * n + (i - 1)] = sn;
+      const bool stage_out = last && need_kin;
+      T snr[S2_NT], sdr[S2_NT];
+#pragma unroll
+      for (int t = 0; t < S2_NT; ++t) {
+        const int i = lane + t * G;
+        snr[t] = T(0); sdr[t] = T(0);
+        if (i >= 1 && i < nL) {
+          T* ri = ws + (size_t)i * R2;
+          T Q[4];
+          ldv<4>(ri + K_S, Q);  // s, sd, sdd, tref
+          if (step >= 0) {
+            Q[1] += dt * Q[2];
+            Q[0] += dt * Q[1];
+            if (!last) stv<4>(ri + K_S, Q);
+            if (last && active) {
+              P.sd_o[env * n + (i - 1)] = Q[1];
+              P.s_o[env * n + (i - 1)] = Q[0];
+            }
           }
-        }
-        if (need_kin) {
-          T Rrel[9], trel[3];
-          joint_rel_transform(P, 0, sm_cst + (size_t)i * CREC, jtypes[i], i, sn, Rrel, trel);
-          {
-            const T K[12] = {Rrel[0], Rrel[1], Rrel[2], Rrel[3], Rrel[4], Rrel[5], Rrel[6], Rrel[7], Rrel[8], trel[0], trel[1], trel[2]};
-            stv<12>(ri, K);
-          }
-          if (last && active && P.iXl) {
-            T X[36];
-            inverse_adjoint(X, Rrel, trel);
-            stg_vec<36>(P.iXl + (env * nL + i) * 36, X);
-          }
+          snr[t] = Q[0]; sdr[t] = Q[1];
         }
       }
       B200SIM_MARK2(12);
       if (need_kin) {
+        // pose rows / velocity of link i: records, or the output staging of the last step
+        const int ks = stage_out ? 16 : R2, vs = stage_out ? 6 : R2;
+        T* kb = ws;
+        T* vb = stage_out ? ws + o_FV : ws + K_V;
+        if (stage_out) __syncwarp();  // every lane has read its joint state out of the records
+        for (int t = 0; t * G < nL; ++t) {
+          const int i = lane + t * G;
+          const T sn = t == 0 ? snr[0] : (t == 1 ? snr[1] : (t == 2 ? snr[2] : snr[3]));
+          const T sdn = t == 0 ? sdr[0] : (t == 1 ? sdr[1] : (t == 2 ? sdr[2] : sdr[3]));
+          if (i >= 1 && i < nL) {
+            T Rrel[9], trel[3];
+            joint_rel_transform(P, 0, sm_cst + (size_t)i * CREC, jtypes[i], i, sn, Rrel, trel);
+            st_pose(kb + (size_t)i * ks, Rrel, trel);
+            vb[(size_t)i * vs] = sdn;
+            if (stage_out) {
+              const T row3[4] = {T(0), T(0), T(0), T(1)};
+              stv<4>(kb + (size_t)i * 16 + 12, row3);
+              if (P.iXl) {
+                T X[36];
+                inverse_adjoint(X, Rrel, trel);
+                stv<36>(ws + o_FX + (size_t)i * 36, X);
+              }
+            }
+          }
+        }
         if (lane == 0) {
           // chain root: the base link (suc_H_i[0] = I for the models this kernel serves)
           T v0[6], t[3];
           cross3(b.w, b.p, t);  // velocity of the base origin: v_lin + w x p
           v0[0] = b.vlin[0] + t[0]; v0[1] = b.vlin[1] + t[1]; v0[2] = b.vlin[2] + t[2];
           v0[3] = b.w[0]; v0[4] = b.w[1]; v0[5] = b.w[2];
-          {
-            const T K[20] = {b.R[0], b.R[1], b.R[2], b.R[3], b.R[4], b.R[5], b.R[6], b.R[7], b.R[8], b.p[0], b.p[1], b.p[2],
-                             v0[0], v0[1], v0[2], v0[3], v0[4], v0[5], T(0), T(0)};
-            stv<20>(ws, K);
-          }
-          if (last && active && P.iXl) {
-            // index 0: Ad((W_H_B suc_H_i[0])^-1)  (api/kin_dyn_parameters.py:417-449)
-            T X[36];
-            inverse_adjoint(X, b.R, b.p);
-            stg_vec<36>(P.iXl + env * nL * 36, X);
+          st_pose(kb, b.R, b.p);
+          st6(vb, v0);
+          if (stage_out) {
+            const T row3[4] = {T(0), T(0), T(0), T(1)};
+            stv<4>(kb + 12, row3);
+            if (P.iXl) {
+              // index 0: Ad((W_H_B suc_H_i[0])^-1)  (api/kin_dyn_parameters.py:417-449)
+              T X[36];
+              inverse_adjoint(X, b.R, b.p);
+              stv<36>(ws + o_FX, X);
+            }
           }
         }
-        // ======================================================= FK + velocity walk over the tree levels
-        // (rbda/forward_kinematics.py:80-113, pass 1 of rbda/aba.py:131-171 in F_i coordinates)
-        int e = nrows > 0 ? rows[lane] : 0xFF;
-        for (int r = 0; r < nrows; ++r) {
+        if (stage_out && P.iXl) {
+          // the (nL,6,6) joint adjoints of the environment leave with ONE bulk copy, overlapping the FK walk
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
-          const int en = (r + 1 < nrows) ? rows[(r + 1) * G + lane] : 0xFF;
-          if ((e & 0xFF) != 0xFF) {
-            const int i = e & 0xFF;
-            const T* rp = ws + (size_t)((e >> 8) & 0xFF) * R2;
-            T* ri = ws + (size_t)i * R2;
-            T Kp[20], Ko[12];
-            ldv<20>(rp, Kp);
-            ldv<12>(ri, Ko);
-            const T* Rp = Kp + K_R;
-            const T* pp = Kp + K_P;
-            const T* vp = Kp + K_V;
-            const T* Rrel = Ko + K_R;
-            const T* trel = Ko + K_P;
-            T R[9], rr[3], pw[3];
-            mat3_mul(Rp, Rrel, R);
-            mat3_vec(Rp, trel, rr);
-            pw[0] = pp[0] + rr[0]; pw[1] = pp[1] + rr[1]; pw[2] = pp[2] + rr[2];
-            T ax[3], aw[3];
-            ldn<3>(sm_cst + (size_t)i * CREC + C_AXIS, ax);
-            mat3_vec(R, ax, aw);
-            const T sdi = ri[K_SD];
-            T v[6];
-            cross3(vp + 3, rr, v);
-            v[0] += vp[0]; v[1] += vp[1]; v[2] += vp[2];
-            v[3] = vp[3]; v[4] = vp[4]; v[5] = vp[5];
-            if (((e >> 27) & 3) == 1) { v[3] += sdi * aw[0]; v[4] += sdi * aw[1]; v[5] += sdi * aw[2]; }
-            else { v[0] += sdi * aw[0]; v[1] += sdi * aw[1]; v[2] += sdi * aw[2]; }
-            {
-              const T K[20] = {R[0], R[1], R[2], R[3], R[4], R[5], R[6], R[7], R[8], pw[0], pw[1], pw[2],
-                               v[0], v[1], v[2], v[3], v[4], v[5], T(0), T(0)};
-              stv<20>(ri, K);
-            }
-            stn<3>(ri + K_RR, rr);
-            stn<3>(ri + K_AX, aw);
-          }
-          e = en;
+          if (lane == 0 && active) tma_store_bulk(P.iXl + env * nL * 36, ws + o_FX, (unsigned)(nL * 36 * sizeof(T)));
         }
-        __syncwarp();
         B200SIM_MARK2(13);
-        if (want_caches && active) {
-          for (int i = lane; i < nL; i += G) {
-            const T* ri = ws + (size_t)i * R2;
-            T Kk[20];
-            ldv<20>(ri, Kk);
-            const T* R = Kk + K_R;
-            const T* p = Kk + K_P;
-            const T* v = Kk + K_V;
-            if (P.W_H_L) store_transform(P.W_H_L + (env * nL + i) * 16, R, p);
+        if (!last || want_caches) {
+          // ===================================================== FK + velocity walk over the tree levels
+          // (rbda/forward_kinematics.py:80-113, pass 1 of rbda/aba.py:131-171 in F_i coordinates), transposed mapping
+          T* kbw = wk;
+          T* vbw = stage_out ? wk + o_FV : wk + K_V;
+          int e = nrows > 0 ? rows[slot] : 0xFF;
+          for (int r = 0; r < nrows; ++r) {
+            __syncwarp();
+            const int en = (r + 1 < nrows) ? rows[(r + 1) * G + slot] : 0xFF;
+            if ((e & 0xFF) != 0xFF) {
+              const int i = e & 0xFF, par = (e >> 8) & 0xFF;
+              T Hp[12], vp[6], Ho[12];
+              ldv<12>(kbw + (size_t)par * ks, Hp);
+              ld6(vbw + (size_t)par * vs, vp);
+              ldv<12>(kbw + (size_t)i * ks, Ho);
+              const T sdi = vbw[(size_t)i * vs];
+              T Rp[9], pp[3], Rrel[9], trel[3];
+              split_pose(Hp, Rp, pp);
+              split_pose(Ho, Rrel, trel);
+              T R[9], rr[3], pw[3];
+              mat3_mul(Rp, Rrel, R);
+              mat3_vec(Rp, trel, rr);
+              pw[0] = pp[0] + rr[0]; pw[1] = pp[1] + rr[1]; pw[2] = pp[2] + rr[2];
+              T ax[3], aw[3];
+              ldn<3>(sm_cst + (size_t)i * CREC + C_AXIS, ax);
+              mat3_vec(R, ax, aw);
+              T v[6];
+              cross3(vp + 3, rr, v);
+              v[0] += vp[0]; v[1] += vp[1]; v[2] += vp[2];
+              v[3] = vp[3]; v[4] = vp[4]; v[5] = vp[5];
+              if (((e >> 27) & 3) == 1) { v[3] += sdi * aw[0]; v[4] += sdi * aw[1]; v[5] += sdi * aw[2]; }
+              else { v[0] += sdi * aw[0]; v[1] += sdi * aw[1]; v[2] += sdi * aw[2]; }
+              st_pose(kbw + (size_t)i * ks, R, pw);
+              st6(vbw + (size_t)i * vs, v);
+              if (!last) {
+                const T Q[8] = {T(0), T(0), aw[0], aw[1], aw[2], rr[0], rr[1], rr[2]};
+                stv<8>(wk + (size_t)i * R2 + 32, Q);  // (dead acceleration tail), axis, r
+              }
+            }
+            e = en;
+          }
+          __syncwarp();
+          B200SIM_MARK2(14);
+          if (stage_out) {
+            // link velocities in inertial-fixed representation, in place, then W_H_L and W_v leave with one
+            // bulk copy each
             if (P.W_v) {
-              T t[3];
-              cross3(p, v + 3, t);  // inertial-fixed linear part: vlin + p x w
-              const T o[6] = {v[0] + t[0], v[1] + t[1], v[2] + t[2], v[3], v[4], v[5]};
-              stg_vec6(P.W_v + (env * nL + i) * 6, o);
+              for (int i = lane; i < nL; i += G) {
+                T v[6];
+                ld6(vb + (size_t)i * 6, v);
+                const T* Hk = kb + (size_t)i * 16;
+                const T p[3] = {Hk[3], Hk[7], Hk[11]};
+                T t[3];
+                cross3(p, v + 3, t);  // inertial-fixed linear part: vlin + p x w
+                v[0] += t[0]; v[1] += t[1]; v[2] += t[2];
+                st6(vb + (size_t)i * 6, v);
+              }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0 && active) {
+              if (P.W_H_L) tma_store_bulk(P.W_H_L + env * nL * 16, kb, (unsigned)(nL * 16 * sizeof(T)));
+              if (P.W_v) tma_store_bulk(P.W_v + env * nL * 6, vb, (unsigned)(nL * 6 * sizeof(T)));
             }
           }
+          B200SIM_MARK2(15);
         }
-        B200SIM_MARK2(14);
       }
     }  // steps
   }
+  tma_store_wait_all();
   if (P.dbg && blockIdx.x == 0 && threadIdx.x == 0) P.dbg[8 + 16] = (unsigned long long)clock64();
   if (P.dbg && blockIdx.x < 512) {
     __syncthreads();
