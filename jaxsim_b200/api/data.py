@@ -290,6 +290,20 @@ class JaxSimModelData:
         return d
 
 
+def _map_leaves(data: "JaxSimModelData", f) -> "JaxSimModelData":
+    """A data object with ``f`` applied to every tensor leaf (None leaves stay None)."""
+    g = lambda t: None if t is None else f(t)  # noqa: E731
+    return JaxSimModelData(
+        velocity_representation=data.velocity_representation,
+        _joint_positions=g(data._joint_positions), _joint_velocities=g(data._joint_velocities),
+        _base_quaternion=g(data._base_quaternion), _base_linear_velocity=g(data._base_linear_velocity),
+        _base_angular_velocity=g(data._base_angular_velocity), _base_position=g(data._base_position),
+        _base_transform=g(data._base_transform), _joint_transforms=g(data._joint_transforms),
+        _link_transforms=g(data._link_transforms), _link_velocities=g(data._link_velocities),
+        contact_state={k: g(v) for k, v in data.contact_state.items()},
+    )
+
+
 def _transform_from_quat_pos(q: torch.Tensor, p: torch.Tensor) -> torch.Tensor:
     """``Transform.from_quaternion_and_translation`` (``math/transform.py:14-56``)."""
     nsq = (q * q).sum(-1)

@@ -59,8 +59,13 @@ def rk4_integration(model, data, link_forces_inertial, joint_torques):
 
 def step_rk4(model, data, *, link_forces=None, joint_force_references=None):
     """``js.model.step`` with ``IntegratorType.RungeKutta4`` (``api/model.py:2601-2681``)."""
-    if data._base_quaternion.dim() != 2:
-        raise ValueError("the RK4 path needs batched data")
+    if data._base_quaternion.dim() == 1:  # unbatched data, like every other entry point
+        from .data import _map_leaves
+
+        one = _map_leaves(data, lambda t: t.unsqueeze(0))
+        lf = None if link_forces is None else torch.as_tensor(link_forces, dtype=data._base_quaternion.dtype, device=data._base_quaternion.device).unsqueeze(0)
+        jf = None if joint_force_references is None else torch.as_tensor(joint_force_references, dtype=data._base_quaternion.dtype, device=data._base_quaternion.device).unsqueeze(0)
+        return _map_leaves(step_rk4(model, one, link_forces=lf, joint_force_references=jf), lambda t: t.squeeze(0))
     fext = None
     if link_forces is not None:
         fext = other_representation_to_inertial(

@@ -75,6 +75,12 @@ class _DeviceModel:
             axis[1:] = kd.joint_model.joint_axis
         reg = 1e-6
         rx = RelaxedRigidContactsParams()
+        if (model.contact_model is not None and model.contact_params is not None
+                and not isinstance(model.contact_params, model.contact_model._parameters_class)):
+            raise TypeError(
+                f"contact_params is a {type(model.contact_params).__name__} but {type(model.contact_model).__name__} "
+                f"takes {model.contact_model._parameters_class.__name__}"
+            )
         prm = model.contact_params if isinstance(model.contact_params, SoftContactsParams) else SoftContactsParams()
         if model.contact_model is None or nc == 0:
             cm = 0
@@ -140,9 +146,30 @@ class JaxSimModel:
     integrator: IntegratorType = IntegratorType.SemiImplicitEuler
     built_from: object | None = None
     _floating_base: bool = True
-    _devices: dict = dataclasses.field(default_factory=dict, repr=False)
+    _devices: dict = dataclasses.field(default_factory=dict, repr=False, init=False, compare=False)
     _tuning: tuple = (0, 0)
     _options: int | None = None
+
+    # Fields baked into the device blob (b200sim_model_create).  The reference's models are immutable pytrees
+    # edited through `model.editable()` / `replace` (utils/jaxsim_dataclass.py:22-27,313-334); here the host
+    # container is a plain dataclass, so assigning any of these drops the cached device models and the next step
+    # uploads a blob with the new values.  `dataclasses.replace` builds a new instance with its own (empty) cache.
+    _PHYSICS_FIELDS = frozenset({
+        "time_step", "terrain", "gravity", "contact_model", "contact_params", "actuation_params",
+        "kin_dyn_parameters", "_floating_base",
+    })
+
+    def __setattr__(self, name, value):
+        object.__setattr__(self, name, value)
+        if name in JaxSimModel._PHYSICS_FIELDS:
+            devs = self.__dict__.get("_devices")
+            if devs:
+                devs.clear()
+
+    def replace(self, **changes) -> "JaxSimModel":
+        """A copy with some fields replaced (``replace`` of the reference's dataclasses); the copy creates its
+        own device models lazily, with the new values."""
+        return dataclasses.replace(self, **changes)
 
     # ------------------------------------------------------------------ builders
     @classmethod
@@ -193,6 +220,11 @@ class JaxSimModel:
         contact_model = contact_model if contact_model is not None else SoftContacts.build()
         if contact_params is None:
             contact_params = contact_model._parameters_class()
+        elif not isinstance(contact_params, contact_model._parameters_class):
+            raise TypeError(
+                f"contact_params is a {type(contact_params).__name__} but {type(contact_model).__name__} takes "
+                f"{contact_model._parameters_class.__name__}"
+            )
         integrator = integrator if integrator is not None else IntegratorType.SemiImplicitEuler
         if integrator == IntegratorType.RungeKutta4Fast:
             raise NotImplementedError("IntegratorType.RungeKutta4Fast is not implemented")
@@ -381,8 +413,13 @@ def _step_impl(model, data, n_steps, link_forces, joint_force_references, update
         if O_f.shape[-3:] != (B, nL, 6) or (per_step and O_f.shape[0] != n_steps):
             raise ValueError(O_f.shape, (B, nL, 6))
         if data.velocity_representation != VelRepr.Inertial:
-            if per_step and n_steps > 1:
-                raise NotImplementedError("per-step link_forces of a multi-step launch must be in VelRepr.Inertial")
+            if n_steps > 1:
+                # the reference re-expresses the forces with the link transforms of EVERY step (api/model.py:2641-2646):
+                # converting once with the initial poses would apply a different wrench from the second step on
+                raise NotImplementedError(
+                    "link_forces of a multi-step launch must be expressed in VelRepr.Inertial "
+                    "(Body / Mixed forces follow the moving links: call step() per step, or convert them yourself)"
+                )
             # api/model.py:2641-2646: expressed in data.velocity_representation -> inertial-fixed
             O_f = other_representation_to_inertial(
                 O_f, data.velocity_representation, _batched(data.link_transforms, 3), is_force=True

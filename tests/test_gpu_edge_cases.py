@@ -253,3 +253,61 @@ def test_cached_input_kinematics_path(dtype, cuda_device):
         for _, leaf in H.LEAVES:
             x, y = getattr(a, leaf), getattr(b, leaf)
             assert float((x - y).abs().max()) <= tol * max(float(y.abs().max()), 1e-9), (name, leaf)
+
+
+@pytest.mark.gpu
+def test_model_edits_take_effect_after_the_first_step(cuda_device):
+    """time_step / contact_params assigned after the first step (or `replace`) must reach the device."""
+    import torch
+
+    from jaxsim_b200.rbda.contacts import SoftContactsParams
+
+    model = H.build_model("icub_like")
+    om = H.oracle_model(model)
+    od = O.random_model_data(om, 8, seed=3, in_contact=True)
+    pd = H.to_product(model, od, torch.float64, cuda_device)
+    js.model.step(model, pd)  # creates the device blob with dt = 1e-3
+    model.time_step = 2.5e-4
+    model.contact_params = SoftContactsParams.build(K=2e5, D=300.0, mu=0.8)
+    out = js.model.step(model, pd)
+    ref = O.step(H.oracle_model(model), od)
+    H.compare_data(out, ref, H.RTOL["float64"], "edited model")
+    other = model.replace(time_step=1e-3)
+    H.compare_data(js.model.step(other, pd), O.step(H.oracle_model(other), od), H.RTOL["float64"], "replaced model")
+    H.compare_data(js.model.step(model, pd), ref, H.RTOL["float64"], "original after replace")
+
+
+@pytest.mark.gpu
+def test_step_n_rejects_moving_frame_link_forces(cuda_device):
+    """Body / Mixed link_forces follow the links; a fused multi-step launch must not freeze them."""
+    import torch
+
+    model = H.build_model("icub_like")
+    om = H.oracle_model(model)
+    od = O.random_model_data(om, 4, seed=5)
+    for vr in (js.common.VelRepr.Mixed, js.common.VelRepr.Body):
+        pd = H.to_product(model, od, torch.float64, cuda_device, velocity_representation=vr)
+        f = torch.ones(4, model.number_of_links(), 6, dtype=torch.float64, device=cuda_device)
+        js.model.step_n(model, pd, 1, link_forces=f)
+        with pytest.raises(NotImplementedError):
+            js.model.step_n(model, pd, 3, link_forces=f)
+    pd = H.to_product(model, od, torch.float64, cuda_device, velocity_representation=js.common.VelRepr.Inertial)
+    a = js.model.step_n(model, pd, 3, link_forces=f)
+    b = pd
+    for _ in range(3):
+        b = js.model.step(model, b, link_forces=f)
+    assert torch.allclose(a.joint_positions, b.joint_positions, rtol=0, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_rk4_step_accepts_unbatched_data(cuda_device):
+    import torch
+
+    model = H.build_model("icub_like", integrator=js.model.IntegratorType.RungeKutta4)
+    om = H.oracle_model(model)
+    od = O.random_model_data(om, 2, seed=9, in_contact=True)
+    pd = H.to_product(model, od, torch.float64, cuda_device)
+    full = js.model.step(model, pd)
+    one = js.model.step(model, js.data._map_leaves(pd, lambda t: t[0]))
+    assert one.joint_positions.dim() == 1
+    assert torch.allclose(one.joint_positions, full.joint_positions[0], rtol=0, atol=1e-12)

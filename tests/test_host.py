@@ -162,3 +162,33 @@ def test_relaxed_rigid_model_classes():
     assert p.valid() and not RelaxedRigidContactsParams.build(d_min=0.99, d_max=0.5).valid()
     m = js.model.JaxSimModel.build_from_model_description(models.urdf("box"), contact_model=RelaxedRigidContacts.build(solver_options={"maxiter": 10}))
     assert isinstance(m.contact_params, RelaxedRigidContactsParams) and dict(m.contact_model.solver_options)["maxiter"] == 10
+
+
+def test_model_edits_invalidate_the_device_blob():
+    """The device blob bakes in time step, gravity, contact / actuation parameters: assigning any of them, or
+    `replace`, must drop the cached device models (the reference edits immutable pytrees with replace())."""
+    import dataclasses
+
+    from jaxsim_b200.rbda.contacts import SoftContactsParams
+
+    model = js.model.JaxSimModel.build_from_model_description(models.urdf("icub_like"))
+    model._devices[0] = object()  # stands for a created device model
+    other = dataclasses.replace(model, time_step=2e-3)
+    assert other._devices == {} and other._devices is not model._devices and other.time_step == 2e-3
+    assert model.replace(gravity=-1.0)._devices == {}
+    assert 0 in model._devices  # untouched by the copies
+    model._tuning = (8, 0)      # not a physics field
+    assert 0 in model._devices
+    model.contact_params = SoftContactsParams.build(K=1e5)
+    assert model._devices == {}
+    model._devices[0] = object()
+    model.time_step = 5e-4
+    assert model._devices == {}
+
+
+def test_contact_params_must_match_the_contact_model():
+    from jaxsim_b200.rbda.contacts import RigidContacts, SoftContactsParams
+
+    with pytest.raises(TypeError):
+        js.model.JaxSimModel.build_from_model_description(
+            models.urdf("icub_like"), contact_model=RigidContacts.build(), contact_params=SoftContactsParams.build())
