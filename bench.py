@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="environments per GPU")
+    ap.add_argument("--global-batch", type=int, default=0, help="total environments over all GPUs (overrides --batch: per-GPU batch = global / N); BASELINE configs[3] is --gpus 8 --global-batch 65536")
+    ap.add_argument("--no-extras", action="store_true", help="skip the bounded extra legs of the default N=1 line (large-batch sweep, config 3, config 5, no-PDL)")
+    ap.add_argument("--min-ms", type=float, default=50.0, help="the CUDA-graph of K steps is replayed until the timed region lasts at least this long")
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--model", default="icub_like")
     ap.add_argument("--lanes", type=int, default=0, help="lanes per env (0 = auto)")
@@ -226,7 +229,12 @@ def run_b200(args):
         model.set_options(tma_store=not args.no_tma, generic_kernel=args.generic_kernel, bulk_in=args.bulk_in, pdl=not args.no_pdl,
                           step_v1=args.step_v1, no_bulk_in=args.no_bulk_in)
     n, nL, nc = model.dofs(), model.number_of_links(), model.number_of_collidable_points()
+    if args.global_batch:
+        if args.global_batch % world:
+            raise SystemExit("--global-batch must be a multiple of the number of GPUs")
+        args.batch = args.global_batch // world
     B = args.batch
+    extras = (world == 1) and not args.no_extras and args.model == "icub_like" and args.dtype == "f32" and not args.no_caches
     bytes_env = algorithmic_bytes_per_env(n, nL, nc, w, caches=not args.no_caches)
 
     def barrier():
@@ -247,10 +255,11 @@ def run_b200(args):
             base_angular_velocity=0.1 * d._base_angular_velocity, velocity_representation=js.common.VelRepr.Inertial,
             batch_size=p.shape[0], dtype=dtype, device=dev)
 
-    def time_steps(Bq, K, W, use_graph=True, in_contact=False):
+    def time_steps(Bq, K, W, use_graph=True, in_contact=False, model=model):
         """K device-resident steps over a ring of state sets larger than L2.  Returns
         (ms of the K steps launched eagerly, ms of the same K steps replayed from a CUDA
-        graph or None, ring, last output)."""
+        graph or None, ring, last output).  The graph of K steps is replayed back to back until the
+        timed region lasts at least --min-ms (the figure is the mean over the replays)."""
         ring = max(2, int(np.ceil(2 * L2_BYTES / (Bq * bytes_env))))
         ring = min(ring, 64)
         datas = [js.data.random_model_data(model, batch_size=Bq, seed=1000 * rank + r, dtype=dtype, device=dev,
@@ -298,8 +307,22 @@ def run_b200(args):
             g.replay()
             e1.record()
             barrier()
-            ms_graph = e0.elapsed_time(e1)
+            once = e0.elapsed_time(e1)
+            reps = int(min(2000, max(1, np.ceil(args.min_ms / max(once, 1e-3)))))
+            if world > 1:  # the same number of replays on every rank
+                tr_ = torch.tensor([reps], dtype=torch.int64, device=dev)
+                dist.all_reduce(tr_, op=dist.ReduceOp.MAX)
+                reps = int(tr_.item())
+            e0.record()
+            for _ in range(reps):
+                g.replay()
+            e1.record()
+            barrier()
+            ms_graph = e0.elapsed_time(e1) / reps
+            time_steps.replays = reps
         return ms_eager, ms_graph, ring, out
+
+    time_steps.replays = 1
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -308,6 +331,7 @@ def run_b200(args):
     t0 = time.time()
     ms_eager, ms_graph, ring, out = time_steps(B, args.steps, max(3, args.warmup), use_graph=not args.no_graph)
     ms = ms_graph if ms_graph is not None else ms_eager
+    main_replays = time_steps.replays
     t1 = time.time()
     clocks = sampler.stop(t0, t1) if rank == 0 else None
 
@@ -463,16 +487,30 @@ def run_b200(args):
 
     # ---- optional batch sweep on this GPU (metric is quoted "batch 4096 -> 65536")
     sweep = None
-    if args.sweep and world == 1:
+    peak_gbs, _ = measured_peak_gbs()
+    if (args.sweep or extras) and world == 1:
         sweep = []
-        for Bq in (4096, 16384, 65536):
-            Kq = max(20, args.steps // 4)
+        for Bq in (16384, 65536):
+            Kq = 20
             mse, msg, rq, _ = time_steps(Bq, Kq, 3, use_graph=not args.no_graph)
             msq = msg if msg is not None else mse
-            sweep.append({"batch": Bq, "value": Bq * Kq / (msq * 1e-3), "ms_per_step": msq / Kq, "ring": rq})
+            ach = Bq * bytes_env / (msq / Kq * 1e-3) / 1e9
+            sweep.append({"batch": Bq, "value": Bq * Kq / (msq * 1e-3), "ms_per_step": msq / Kq, "ring": rq, "steps": Kq,
+                          "replays": time_steps.replays, "launch": model.launch_geometry(Bq, dtype, dev),
+                          "roofline": {"bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs}})
+
+    # the same default workload launched WITHOUT programmatic dependent launch (closes the loop on the
+    # launch-to-launch figure being shorter than the kernel duration ncu reports)
+    no_pdl = None
+    if extras and not args.no_pdl and not args.no_graph:
+        m2 = js.model.JaxSimModel.build_from_model_description(models.urdf(args.model), time_step=1e-3)
+        m2.set_options(pdl=False, step_v1=args.step_v1, no_bulk_in=args.no_bulk_in)
+        mse, msg, _, _ = time_steps(B, min(args.steps, 50), 3, model=m2)
+        no_pdl = {"ms_per_step": msg / min(args.steps, 50), "eager_ms_per_step": mse / min(args.steps, 50),
+                  "note": "same K-step CUDA graph with ordinary launches (B200SIM_OPT_NO_PDL): the difference to ms_per_step is the launch set-up hidden by programmatic dependent launch"}
 
     contact_leg = None
-    if (args.sweep or args.in_contact) and world == 1 and nc > 0:
+    if (args.sweep or args.in_contact or extras) and world == 1 and nc > 0:
         Kc = max(20, args.steps // 4)
         mse, msg, rq, _ = time_steps(B, Kc, 3, use_graph=not args.no_graph, in_contact=True)
         msc = msg if msg is not None else mse
@@ -572,18 +610,48 @@ def run_b200(args):
             if world > 1:
                 dist.all_reduce(t3, op=dist.ReduceOp.MAX)
             ms3 = float(t3.item()) / K3
+            b3 = algorithmic_bytes_per_env(n3, nL3, 0, w)  # rigid contacts carry no contact state
+            ach3 = B3 * b3 / (ms3 * 1e-3) / 1e9
             config3[label] = {"ms_per_step": ms3, "value": B3 * world / (ms3 * 1e-3), "steps": K3,
                               "mean_active_points": act,
+                              "roofline": {"bound": "hbm", "achieved": ach3, "peak": peak_gbs, "unit": "GB/s", "frac": ach3 / peak_gbs,
+                                           "bytes_per_env_step": b3,
+                                           "note": "B_api of SURVEY.md 8d for this model; the rigid step is bound by the warp-serial contact QP, not by HBM"},
                               "inputs": "random_model_data (base 0.5-1 m above ground: mostly no contact)" if label == "random"
                               else "standing: level base, soles 2-5 mm into the ground"}
+        if kind == "rigid" and rank == 0 and not args.no_cpu_baseline:
+            config3["cpu_baseline"] = cpu_rigid_oracle_throughput(standing)
         return config3
 
-    if args.config3:
+    def cpu_rigid_oracle_throughput(standing, sample=128):
+        """CPU arm of config 3: the NumPy restatement of the reference's rigid-contact step (oracle/rigid_oracle.py,
+        float64, vectorised over the batch; NumPy/BLAS threads as configured) on a bounded sample of the SAME
+        `standing` inputs."""
+        from oracle import jaxsim_oracle as O3
+        from oracle import rigid_oracle as R3
+        from tests import helpers as H3
+        from jaxsim_b200.rbda.contacts import RigidContacts, RigidContactsParams
+
+        m3 = H3.build_model("ergocub_like", contact_model=RigidContacts.build(), contact_params=RigidContactsParams.build(K=1e4, D=20.0))
+        om3 = H3.oracle_model(m3)
+        d1, _ = standing(70)
+        c = lambda t: t[:sample].detach().cpu().double().numpy()  # noqa: E731
+        od3 = O3.data_replace(om3, c(d1._joint_positions), c(d1._joint_velocities), c(d1._base_quaternion),
+                              c(d1._base_linear_velocity), c(d1._base_angular_velocity), c(d1._base_position))
+        tau3 = 10 * np.random.default_rng(0).uniform(size=(sample, om3.dofs()))
+        t0_ = time.perf_counter()
+        R3.step(om3, od3, joint_force_references=tau3)
+        busy = time.perf_counter() - t0_
+        return {"value": sample / busy, "unit": UNIT, "cores": int(os.cpu_count() or 1), "kind": "port",
+                "sample": f"{sample} 'standing' environments x 1 step, NumPy restatement of the reference's rigid-contact step (float64)"}
+
+    if args.config3 or extras:
         config3 = time_contact_model("rigid")
+    if args.config3:
         relaxed3 = time_contact_model("relaxed")
 
     jvp = None
-    if args.jvp:
+    if args.jvp or extras:
         d64 = js.data.random_model_data(model, batch_size=B, seed=77 + rank, dtype=torch.float64, device=dev,
                                         velocity_representation=js.common.VelRepr.Inertial)
         tq = torch.randn(B, n, dtype=torch.float64, device=dev)
@@ -612,24 +680,25 @@ def run_b200(args):
     ms_step = ms_max / args.steps
     achieved = B * bytes_env / (ms_step * 1e-3) / 1e9
     geo = model.launch_geometry(B, dtype, dev)
-    traffic = None
-    tp = ROOT / "profiles" / "traffic_per_launch.json"
-    if tp.exists():
+    # DRAM traffic and counted arithmetic of this configuration come from the committed ncu counter capture of the same
+    # command line (scripts/step_counters.py -> profiles/r02_step_counters.json): steady-state DRAM bytes per launch
+    # (reads + the drained writes, mean over consecutive launches on a ring of inputs larger than L2) and
+    # 2*FFMA + FADD + FMUL thread instructions per environment step.  None when no capture exists for the configuration.
+    traffic, compute = None, None
+    tp = ROOT / "profiles" / "r02_step_counters.json"
+    if tp.exists() and not args.no_caches:
         try:
-            traffic = json.loads(tp.read_text()).get(f"{args.model}_{args.dtype}_B{B}")
+            rec = json.loads(tp.read_text()).get(f"{args.model}_{args.dtype}_B{B}")
         except Exception:
-            traffic = None
-
-    # the step is NOT HBM-bound, so the counted arithmetic is reported next to the HBM figure.
-    # flops per env-step = (2*FFMA + FADD + FMUL thread instructions) / batch from the ncu capture of this
-    # configuration (profiles/r01_step_kernel_v8_warm.md: FFMA x2 + FADD + FMUL thread instructions per env-step)
-    compute = None
-    if args.model == "icub_like" and args.dtype == "f32" and not args.no_caches:
-        fpe = 21400.0
-        peak_fp32 = 148 * 128 * 2 * 1.965e9 / 1e12  # CUDA-core FMA peak at the measured SM clock (nominal, TFLOP/s)
-        compute = {"flops_per_env_step": fpe, "achieved_tflops": fpe * B / (ms_step * 1e-3) / 1e12, "peak_tflops": peak_fp32,
-                   "frac": fpe * B / (ms_step * 1e-3) / 1e12 / peak_fp32, "unit": "TFLOP/s fp32 (CUDA cores; tensor cores do not apply)",
-                   "source": "ncu sm__sass_thread_inst_executed_op_{ffma,fadd,fmul} of this configuration, profiles/r01_step_kernel_v8_warm.md"}
+            rec = None
+        if rec:
+            traffic = rec.get("dram_bytes_per_launch")
+            fpe = rec.get("flops_per_env_step")
+            if fpe and args.dtype == "f32":
+                peak_fp32 = 148 * 128 * 2 * 1.965e9 / 1e12  # CUDA-core FMA peak at the maximum SM clock (nominal, TFLOP/s)
+                compute = {"flops_per_env_step": fpe, "achieved_tflops": fpe * B / (ms_step * 1e-3) / 1e12, "peak_tflops": peak_fp32,
+                           "frac": fpe * B / (ms_step * 1e-3) / 1e12 / peak_fp32,
+                           "unit": "TFLOP/s fp32 (CUDA cores; tensor cores do not apply)", "source": rec.get("source")}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:  # contract: the CPU baseline is timed at N = 1 only
@@ -657,7 +726,7 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                 "launch": e2e_mode, "eager_value": e2e_eager_value,
                 "note": "public API js.model.step with pinned host buffers, every step: one H2D (state + contact state + tau), step, one D2H (new state + contact state); pipelined over 3 streams (%d buffers per stage); the caches are written on the device like in `value` but not copied back.  `value`: the Ke-step pipeline captured into one CUDA graph and replayed (launch=cuda_graph); `eager_value`: the same calls dispatched from Python one by one" % NB},
-        "gpu_launches": args.steps,
+        "gpu_launches": args.steps * main_replays, "replays": main_replays,
         "eager": {"value": B * world * args.steps / (ms_eager_max * 1e-3), "ms_per_step": ms_eager_max / args.steps,
                   "note": "same K steps launched one by one from Python (host launch latency included)"},
         "clocks": clocks,
@@ -665,7 +734,9 @@ def run_b200(args):
     if gather_ms is not None:
         line["readback_allgather_ms"] = gather_ms
     if sweep is not None:
-        line["sweep"] = sweep
+        line["large_batch"] = sweep
+    if no_pdl is not None:
+        line["no_pdl"] = no_pdl
     if contact_leg is not None:
         line["in_contact"] = contact_leg
     if rollout is not None:

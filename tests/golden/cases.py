@@ -68,10 +68,16 @@ CASES = [
     dict(id="box_rigid_rollout", model="box", B=3, seed=36, contact="rigid", in_contact="flat", rollout=5),
     dict(id="icub_rigid_rollout", seed=37, contact="rigid", in_contact="flat", tau=True, rollout=4, model="icub_like", B=2),
     dict(id="icub_relaxed_rollout", seed=38, contact="relaxed", in_contact="flat", tau=True, rollout=4, model="icub_like", B=2),
+    # ---- larger batches (goldens had 2-4 environments each) with inputs ROUNDED TO FLOAT32, so that the
+    #      float32 kernel and the float64 reference start from exactly the same numbers
+    dict(id="icub_soft_contact_b32", model="icub_like", B=32, seed=39, in_contact=True, tau=True, m=True, round32=True),
+    dict(id="icub_soft_mixed_b32", model="icub_like", B=32, seed=40, in_contact="mixed", tau=True, m=True, round32=True),
+    dict(id="ergocub_soft_flat_b32", model="ergocub_like", B=32, seed=41, in_contact="flat", tau=True, m=True, round32=True),
+    dict(id="icub_rigid_flat_b16", model="icub_like", B=16, seed=42, contact="rigid", in_contact="flat", tau=True, round32=True),
 ]
 
 DEFAULTS = dict(contact="soft", contact_params=None, actuation=None, integrator="semi_implicit_euler", in_contact=False,
-                tau=False, m=False, fext=False, velrepr="inertial", rbda=False, time_step=1e-3, rollout=1)
+                tau=False, m=False, fext=False, velrepr="inertial", rbda=False, time_step=1e-3, rollout=1, round32=False)
 
 
 def case(cid: str) -> dict:

@@ -53,7 +53,14 @@ def draw_inputs(case: dict):
     pm = H.build_model_for_case(case)
     om = H.oracle_model(pm)
     B = case["B"]
-    od = O.random_model_data(om, B, seed=case["seed"], in_contact=case["in_contact"])
+    if case["in_contact"] == "mixed":  # half of the batch airborne, half touching the ground
+        a = O.random_model_data(om, B // 2, seed=case["seed"], in_contact=False)
+        b = O.random_model_data(om, B - B // 2, seed=case["seed"] + 500, in_contact=True)
+        cat = lambda f: np.concatenate([getattr(a, f), getattr(b, f)], axis=0)  # noqa: E731
+        od = O.data_replace(om, cat("joint_positions"), cat("joint_velocities"), cat("base_quaternion"),
+                            cat("base_linear_velocity"), cat("base_angular_velocity"), cat("base_position"))
+    else:
+        od = O.random_model_data(om, B, seed=case["seed"], in_contact=case["in_contact"])
     rng = np.random.Generator(np.random.Philox(1000 + case["seed"]))
     n, nL = om.dofs(), om.number_of_links()
     nc = len(np.asarray(pm.kin_dyn_parameters.contact_parameters.body))
@@ -64,6 +71,8 @@ def draw_inputs(case: dict):
         tau=10.0 * rng.uniform(0, 1, size=(B, n)) if case["tau"] else np.zeros((B, n)),
         tangential_deformation=(1e-4 * rng.uniform(-1, 1, size=(B, nc, 3)) if case["m"] else np.zeros((B, nc, 3))),
     )
+    if case["round32"]:
+        inp = {k: np.asarray(v, dtype=np.float32).astype(np.float64) for k, v in inp.items()}
     if case["fext"]:
         inp["link_forces"] = rng.uniform(-10, 10, size=(B, nL, 6))
     if case["rbda"]:

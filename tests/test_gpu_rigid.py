@@ -254,3 +254,53 @@ def test_relaxed_rigid_box_settles(cuda_device):
     v = data._base_linear_velocity.abs().max().item()
     assert np.all(z < 0.05 + 1e-4) and np.all(z > 0.05 - 2e-3), z
     assert v < 5e-3, v
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_rigid_full_batch_parity(dtype, cuda_device):
+    """BASELINE configs[2] at its FULL size: ErgoCub-like, RigidContacts, 16 384 environments, one third airborne,
+    one third touching the ground with a random attitude, one third standing flat (many active points) -- the
+    work-list cascade at scale (fused kernel / 12-point rigid kernel / full-size rigid kernel).  The NumPy oracle
+    steps a strided sample of 258 environments; the whole batch is checked through size-independent properties:
+    finite results, unit quaternions, and no enabled collidable point moving INTO the ground after the impact."""
+    import torch
+
+    name, B, S = "ergocub_like", 16384, 258
+    model = _model(name, K=1e4, D=20.0)
+    om = H.oracle_model(model)
+    third = B // 3
+    parts = [_inputs(om, third, 41, False, dtype), _inputs(om, third, 42, True, dtype), _inputs(om, B - 2 * third, 43, "flat", dtype)]
+    cat = lambda f: np.concatenate([getattr(p, f) for p in parts], axis=0)  # noqa: E731
+    perm = np.random.default_rng(3).permutation(B)  # interleave the three kinds over the blocks
+    od = O.data_replace(om, cat("joint_positions")[perm], cat("joint_velocities")[perm], cat("base_quaternion")[perm],
+                        cat("base_linear_velocity")[perm], cat("base_angular_velocity")[perm], cat("base_position")[perm])
+    rng = np.random.default_rng(2)
+    tau = 10 * rng.uniform(size=(B, om.dofs())).astype(np.float32).astype(np.float64)
+    td = _dtype(dtype)
+    pd = H.to_product(model, od, td, cuda_device)
+    out = js.model.step(model, pd, joint_force_references=torch.as_tensor(tau, dtype=td, device=cuda_device))
+    torch.cuda.synchronize()
+    # ---- strided sample against the oracle
+    idx = np.arange(0, B, B // S)[:S]
+    sub = O.data_replace(om, od.joint_positions[idx], od.joint_velocities[idx], od.base_quaternion[idx],
+                         od.base_linear_velocity[idx], od.base_angular_velocity[idx], od.base_position[idx])
+    ref = R.step(om, sub, joint_force_references=tau[idx])
+    it = torch.as_tensor(idx, device=cuda_device)
+    sample = js.data._map_leaves(out, lambda t: t[it])
+    H.compare_data(sample, ref, H.RTOL[dtype], f"rigid full batch {dtype}", floors=_vel_floors(sub))
+    # ---- whole batch
+    for _, leaf in H.LEAVES:
+        assert bool(torch.isfinite(getattr(out, leaf)).all()), leaf
+    qn = torch.linalg.norm(out.base_quaternion, dim=-1)
+    assert float((qn - 1).abs().max()) <= (1e-12 if dtype == "float64" else 1e-6)
+    # (fresh kinematics: the rigid step returns the PRE-impact link velocities in its cache, rigid.py:429-434)
+    fresh = js.data.JaxSimModelData.build(
+        model, base_position=out._base_position, base_quaternion=out._base_quaternion, joint_positions=out._joint_positions,
+        joint_velocities=out._joint_velocities, base_linear_velocity=out._base_linear_velocity,
+        base_angular_velocity=out._base_angular_velocity, velocity_representation=js.common.VelRepr.Inertial,
+        batch_size=B, dtype=td, device=cuda_device)
+    pos = js.contact.collidable_point_positions(model, fresh)
+    vel = js.contact.collidable_point_velocities(model, fresh)
+    below = pos[..., 2] < 0
+    if bool(below.any()):  # rigid.py:385-436: active points have no velocity into the ground after the impact
+        assert float(vel[..., 2][below].min()) >= -(1e-6 if dtype == "float64" else 2e-3)

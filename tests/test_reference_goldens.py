@@ -64,6 +64,9 @@ def test_fixture_matches_case_table(cid):
     _, _, urdf = _models(case)
     assert spec["urdf_sha256_16"] == C.urdf_digest(urdf), "model URDF changed since the fixture was generated"
     for k, v in case.items():
+        if k not in spec:  # an option added after this fixture was generated: it must be at its default
+            assert v == C.DEFAULTS[k], (k, v)
+            continue
         assert spec[k] == v or (isinstance(v, (dict, list)) and json.loads(json.dumps(v)) == spec[k]), (k, v, spec[k])
 
 
