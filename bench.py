@@ -203,6 +203,30 @@ def run_reference(args):
     emit(line)
 
 
+def bind_to_gpu_numa_node(index: int) -> dict:
+    """Pin this process to the CPU cores NVML reports as local to GPU `index` (its NUMA node) BEFORE any pinned host
+    buffer is allocated: cudaHostAlloc places pages on the node of the calling thread, and a DMA from the far socket
+    roughly halves the H2D / D2H rate of the e2e pipeline.  A no-op when the local cores are not in the cpuset."""
+    info = {"bound": False}
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        local = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        pick = sorted(local & allowed)
+        info.update(gpu_local_cpus=len(local), allowed_cpus=len(allowed))
+        if pick:
+            os.sched_setaffinity(0, pick)
+            info.update(bound=True, cpus=len(pick))
+    except Exception as exc:  # NVML missing / not permitted: leave the affinity alone
+        info["error"] = repr(exc)[:120]
+    return info
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def run_b200(args):
     import torch
@@ -218,6 +242,7 @@ def run_b200(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     dev = torch.device(f"cuda:{local}")
+    numa = bind_to_gpu_numa_node(local)
     torch.cuda.set_device(dev)
     dtype = torch.float32 if args.dtype == "f32" else torch.float64
     w = 4 if args.dtype == "f32" else 8
@@ -389,7 +414,6 @@ def run_b200(args):
     hv["m"].zero_()
     hv["tau"].copy_(10 * torch.rand(B, n, dtype=dtype))
     NB = max(2, int(os.environ.get("B200SIM_E2E_BUFFERS", "2")))  # pipeline depth (buffers per stage)
-    e2e_nostep = bool(os.environ.get("B200SIM_E2E_NOSTEP"))       # diagnostic: copies only
     h_out = [torch.empty(n_out, dtype=dtype).pin_memory() for _ in range(NB)]
     d_in = [torch.empty(n_in, dtype=dtype, device=dev) for _ in range(NB)]
     d_out = [torch.empty(n_out, dtype=dtype, device=dev) for _ in range(NB)]
@@ -415,7 +439,7 @@ def run_b200(args):
     ev_cmp = [torch.cuda.Event() for _ in range(NB)]
     ev_out = [torch.cuda.Event() for _ in range(NB)]
 
-    def e2e_run(count, fresh=False):
+    def e2e_run(count, fresh=False, e2e_nostep=False):
         """`count` pipelined steps over three streams.  `fresh`: no event has been recorded yet
         (first use, or inside a graph capture where only captured events may be waited on)."""
         seen = set() if fresh else {(k, j) for k in ("cmp", "out") for j in range(NB)}
@@ -462,6 +486,14 @@ def run_b200(args):
 
     e2e_eager_value = B * world * Ke / (timed(eager) * 1e-3)
 
+    def copies_only():
+        e2e_run(Ke, e2e_nostep=True)
+        for j in range(NB):
+            s_cmp.wait_event(ev_out[j])
+
+    copies_only()
+    e2e_copy_only_value = B * world * Ke / (timed(copies_only) * 1e-3)
+
     # (2) the same Ke-step pipeline (same API calls, same pinned buffers, same three streams) captured
     #     once into a CUDA graph and replayed: what a user does to take Python out of the loop
     e2e_value, e2e_mode = e2e_eager_value, "eager"
@@ -479,7 +511,11 @@ def run_b200(args):
                 eg.replay()
                 torch.cuda.synchronize()
                 t_graph = timed(eg.replay)
-            e2e_value, e2e_mode = B * world * Ke / (t_graph * 1e-3), "cuda_graph"
+            e2e_graph_value = B * world * Ke / (t_graph * 1e-3)
+            if e2e_graph_value >= e2e_eager_value:
+                e2e_value, e2e_mode = e2e_graph_value, "cuda_graph"
+            else:  # the driver sometimes serialises the three captured streams: the eager pipeline is the better user path then
+                e2e_value, e2e_mode = e2e_eager_value, "eager (faster than the captured pipeline: %.3e)" % e2e_graph_value
         except Exception as exc:  # a failed capture must not cost the run its result line: keep the eager figure
             print(f"[bench] e2e graph capture failed ({exc!r}); reporting the eagerly dispatched pipeline", file=sys.stderr)
             torch.cuda.synchronize()
@@ -724,7 +760,7 @@ def run_b200(args):
         "compute": compute,
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-                "launch": e2e_mode, "eager_value": e2e_eager_value,
+                "launch": e2e_mode, "eager_value": e2e_eager_value, "copy_only_value": e2e_copy_only_value, "numa": numa,
                 "note": "public API js.model.step with pinned host buffers, every step: one H2D (state + contact state + tau), step, one D2H (new state + contact state); pipelined over 3 streams (%d buffers per stage); the caches are written on the device like in `value` but not copied back.  `value`: the Ke-step pipeline captured into one CUDA graph and replayed (launch=cuda_graph); `eager_value`: the same calls dispatched from Python one by one" % NB},
         "gpu_launches": args.steps * main_replays, "replays": main_replays,
         "eager": {"value": B * world * args.steps / (ms_eager_max * 1e-3), "ms_per_step": ms_eager_max / args.steps,

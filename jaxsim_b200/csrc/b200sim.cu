@@ -942,7 +942,7 @@ int b200sim_model_set_tuning(B200SimModel* m, int lanes_per_env, int envs_per_bl
 // Undeclared diagnostic (not part of the ABI): enables, reads and resets the rigid-contact counters
 // [0] QP iterations, [1] QPs, [2] max iterations, [3] active points (QP), [4] full items,
 // [5] impact-only items, [6] impacts, [7] active points (impact).
-constexpr int DBG_WORDS = 8 + 32 + 1024 + 512;  // 8 counters + the phase clocks of step_kernel (B200SIM_PHASE_MARK) + per-block start/end ns
+constexpr int DBG_WORDS = 8 + 32 + 1024 + 512 + 24 + 512;  // ... + the contact-problem dump of B200SIM_RIGID_DEBUG builds at word 1600  // 8 counters + the phase clocks of step_kernel (B200SIM_PHASE_MARK) + per-block start/end ns
 extern "C" int b200sim_debug_counters(B200SimModel* m, unsigned long long* out8) {
   if (!m) return B200SIM_E_INVALID;
   int prev = 0;
@@ -981,6 +981,18 @@ extern "C" int b200sim_debug_block_times(B200SimModel* m, unsigned long long* ou
   CK(cudaSetDevice(m->device));
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(out1024, m->dbg_d + 40, (1024 + 512) * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  cudaSetDevice(prev);
+  return 0;
+}
+
+// Undeclared diagnostic (B200SIM_RIGID_DEBUG builds): the 512-double dump of environment 0's contact problem.
+extern "C" int b200sim_debug_rigid_dump(B200SimModel* m, double* out512) {
+  if (!m || !m->dbg_d || !out512) return B200SIM_E_INVALID;
+  int prev = 0;
+  CK(cudaGetDevice(&prev));
+  CK(cudaSetDevice(m->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out512, m->dbg_d + 1600, 512 * sizeof(double), cudaMemcpyDeviceToHost));
   cudaSetDevice(prev);
   return 0;
 }

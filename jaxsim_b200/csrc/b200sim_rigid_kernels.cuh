@@ -335,9 +335,16 @@ __device__ __noinline__ int qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int na
     }
     rdn = warp_max(rdn); rpn = warp_max(rpn); sz = warp_sum(sz);
     const S mu = sz * inv_M;
+    // A non-finite iterate (the Hessian Q + G' diag(z/s) G loses definiteness to rounding once z/s spans the whole
+    // exponent range, a few iterations past the resolution of S) must never become the answer.  The maxima above are
+    // NaN-blind (fmax returns the other operand), the SUMS are not: x'Qx, q'x and s'z carry any NaN / Inf of x, s, z.
+    {
+      const S chk = abs_t(xQx) + abs_t(qx) + abs_t(sz);
+      if (!(chk < S(sizeof(S) == 8 ? 1e290 : 1e30f))) break;  // keep the best finite iterate found so far
+    }
     const S m_d = rdn / (S(1) + qm + Qxm), m_p = rpn / (S(1) + xm), m_g = mu / (S(1) + abs_t(S(0.5) * xQx + qx));
     const S merit = max_t(m_d, max_t(m_p, m_g));
-    if (merit < best) {  // false for NaN: a diverged iterate never replaces the best one
+    if (merit < best) {
       best = merit;
       for (int i = lane; i < N; i += 32) xb[i] = x[i];
     }
@@ -1187,7 +1194,25 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
       if (!relaxed) {
         delassus(na, S(P.reg));
         B200SIM_RIGID_MARK(4);
+#ifdef B200SIM_RIGID_DEBUG
+        if (P.dbg && lane == 0 && env == 0) {  // dump of the contact problem of environment 0 (diagnostic builds only)
+          double* D = reinterpret_cast<double*>(P.dbg + 1600);
+          D[0] = (double)na;
+          for (int k = 0; k < 6; ++k) D[1 + k] = (double)a0t[k];
+          for (int k = 0; k < 3 * na; ++k) D[8 + k] = (double)q[k];
+          for (int k = 0; k < 3 * na; ++k) D[8 + 96 + k] = (double)Qp[pidx(k, k)];
+        }
+        __syncwarp();
+#endif
         const int qp_it = qp_pyramids<S>(Qp, Hp, vN, vM, na, S(P.mu), lane);
+#ifdef B200SIM_RIGID_DEBUG
+        if (P.dbg && lane == 0 && env == 0) {
+          double* D = reinterpret_cast<double*>(P.dbg + 1600);
+          for (int k = 0; k < 3 * na; ++k) D[8 + 192 + k] = (double)vN[k];
+          D[7] = (double)qp_it;
+        }
+        __syncwarp();
+#endif
         if (P.dbg && lane == 0) {
           atomicAdd(P.dbg + 0, (unsigned long long)qp_it);
           atomicAdd(P.dbg + 1, 1ull);
@@ -1225,6 +1250,13 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
       }
 #pragma unroll
       for (int k = 0; k < 6; ++k) a0t[k] += ws[O_C + k];
+#ifdef B200SIM_RIGID_DEBUG
+      if (P.dbg && lane == 0 && env == 0) {
+        double* D = reinterpret_cast<double*>(P.dbg + 1600);
+        for (int k = 0; k < 6; ++k) D[8 + 288 + k] = (double)a0t[k];
+        for (int i = 1; i < nL && i < 64; ++i) D[8 + 300 + i] = (double)ws[(size_t)i * REC + O_SDD];
+      }
+#endif
     }
     __syncwarp();
 

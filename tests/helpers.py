@@ -145,10 +145,13 @@ def compare_data(pd, od: O.OracleData, rtol: float, what="", floors: dict | None
         assert got.shape == ref.shape, (got.shape, ref.shape)
         if ref.size == 0:
             ref = got = np.zeros(1)
-        # the deformation state is O(1e-6) m: its scale is dt * (sliding velocity), never below 1e-6
         scale = max(float(np.max(np.abs(ref))), 1e-6)
         errs["tangential_deformation"] = float(np.max(np.abs(got - ref))) / scale
-        viol["tangential_deformation"] = elementwise_violation(got, ref, rtol, batched, 1e-6)
+        # The deformation state integrates the tangential velocity of the points (O(0.1) m/s) over dt = 1e-3 s: its
+        # natural scale is 1e-4 m whatever an individual point currently holds (a point that has just touched the
+        # ground holds ~1e-7 m), and its float32 error is set by the cancellation in delta = h - p_z (|p| ~ 1 m),
+        # not by the point's own value.  Scale floor 1e-4 m: atol = 1e-7 m (float32) / 1e-9 m (float64).
+        viol["tangential_deformation"] = elementwise_violation(got, ref, rtol, batched, 1e-4)
     bad = {k: v for k, v in viol.items() if not (v <= 1.0)}
     assert not bad, (f"{what}: entries outside |x - ref| <= {rtol} * (|ref| + per-environment leaf scale) by the factor "
                      f"{bad} (leaf-max relative errors: {errs})")
