@@ -195,6 +195,28 @@ int b200sim_step_n(const B200SimModel *model, int dtype, int64_t B, int32_t nste
                    void *W_H_B, void *i_X_lam, void *W_H_L, void *W_v_WL,
                    void *stream);
 
+/* Per-environment status flags.  The reference can only raise these conditions as host exceptions, and only when
+ * JAXSIM_ENABLE_EXCEPTIONS is set (rbda/utils.py:136-146, exceptions.py:43-48); qpax's convergence flag is dropped
+ * (rbda/contacts/rigid.py:359-362).  Here they are evaluated on the device:
+ *   QUATERNION_NAN       the stored base quaternion of the INPUT state contains a NaN;
+ *   QUATERNION_NOT_UNIT  its squared norm differs from 1 beyond jnp.allclose's defaults (rtol 1e-5, atol 1e-8);
+ *   NON_FINITE           a state leaf of the OUTPUT (s, sd, q, v_lin, omega, p) is NaN or infinite;
+ *   QP_NOT_CONVERGED     the contact QP of a RigidContacts step left its iteration without meeting the tolerance
+ *                        (the best iterate was used). */
+#define B200SIM_STATUS_QUATERNION_NAN 1
+#define B200SIM_STATUS_QUATERNION_NOT_UNIT 2
+#define B200SIM_STATUS_NON_FINITE 4
+#define B200SIM_STATUS_QP_NOT_CONVERGED 8
+/* b200sim_step_n plus `status_flags`: (B,) int32 on the device, overwritten with the flags of every environment
+ * (0 = nothing to report).  One small extra launch on the same stream; NULL falls back to b200sim_step_n.  The
+ * output quaternion buffer must not alias the input one. */
+int b200sim_step_n_status(const B200SimModel *model, int dtype, int64_t B, int32_t nsteps, const void *s,
+                          const void *sd, const void *q_wxyz, const void *v_lin, const void *omega, const void *p,
+                          const void *m_tan, const void *tau, int64_t tau_step_stride, const void *f_ext_inertial,
+                          int64_t f_ext_step_stride, const void *W_H_L_in, const void *W_v_in, void *s_o, void *sd_o,
+                          void *q_o, void *v_lin_o, void *omega_o, void *p_o, void *m_tan_o, void *W_H_B, void *i_X_lam,
+                          void *W_H_L, void *W_v_WL, int32_t *status_flags, void *stream);
+
 /* Cache computation only (JaxSimModelData.build / .replace, api/data.py:66-202,406-523):
  * normalises q (written to q_o if not NULL) and fills the requested caches. */
 int b200sim_fk(const B200SimModel *model, int dtype, int64_t B,

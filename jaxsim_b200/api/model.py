@@ -364,7 +364,8 @@ def _alloc_outputs(model, B, dtype, dev, update_caches, soft):
     return out
 
 
-def _step_impl(model, data, n_steps, link_forces, joint_force_references, update_caches, out, use_input_caches=True):
+def _step_impl(model, data, n_steps, link_forces, joint_force_references, update_caches, out, use_input_caches=True,
+               status_flags=None):
     s = data._joint_positions
     unbatched = s.dim() == 1
     dev = s.device
@@ -470,14 +471,24 @@ def _step_impl(model, data, n_steps, link_forces, joint_force_references, update
         ctx = torch.cuda.device(dev)
     else:
         ctx = _NULLCTX
+    args = (
+        dm.handle, code, B, int(n_steps),
+        _ptr(s), _ptr(sd), _ptr(q), _ptr(vl), _ptr(om), _ptr(p), _ptr(m), _ptr(tau), tau_stride,
+        _ptr(fext), fext_stride, _ptr(Hin), _ptr(Vin),
+        _ptr(o["s"]), _ptr(o["sd"]), _ptr(o["q"]), _ptr(o["vl"]), _ptr(o["om"]), _ptr(o["p"]), _ptr(g("m")),
+        _ptr(g("W_H_B")), _ptr(g("iXl")), _ptr(g("W_H_L")), _ptr(g("W_v")),
+    )
+    if status_flags is not None:
+        if (status_flags.dtype != torch.int32 or status_flags.shape != (B,) or status_flags.device != dev
+                or not status_flags.is_contiguous()):
+            raise ValueError("status_flags must be a contiguous int32 tensor of shape (B,) on the device of `data`")
+        if o["q"].data_ptr() == q.data_ptr():
+            raise ValueError("status_flags describe the input quaternion too: not available for an in-place step")
     with ctx:
-        rc = _lib.load().b200sim_step_n(
-            dm.handle, code, B, int(n_steps),
-            _ptr(s), _ptr(sd), _ptr(q), _ptr(vl), _ptr(om), _ptr(p), _ptr(m), _ptr(tau), tau_stride,
-            _ptr(fext), fext_stride, _ptr(Hin), _ptr(Vin),
-            _ptr(o["s"]), _ptr(o["sd"]), _ptr(o["q"]), _ptr(o["vl"]), _ptr(o["om"]), _ptr(o["p"]), _ptr(g("m")),
-            _ptr(g("W_H_B")), _ptr(g("iXl")), _ptr(g("W_H_L")), _ptr(g("W_v")), _stream_ptr(dev),
-        )
+        if status_flags is None:
+            rc = _lib.load().b200sim_step_n(*args, _stream_ptr(dev))
+        else:
+            rc = _lib.load().b200sim_step_n_status(*args, _ptr(status_flags), _stream_ptr(dev))
     _lib.check(rc, "b200sim_step_n")
 
     if out is not None:
@@ -507,6 +518,7 @@ def step(
     update_caches: bool = True,
     out: "_data.JaxSimModelData | None" = None,
     use_input_caches: bool = True,
+    status_flags: torch.Tensor | None = None,
 ) -> "_data.JaxSimModelData":
     """Perform a simulation step: drop-in for ``jaxsim.api.model.step``
     (``src/jaxsim/api/model.py:2601-2681``), batched over the leading axis of ``data``.
@@ -526,6 +538,10 @@ def step(
             reference's contact code does) instead of recomputing the kinematics of the
             input state; they are consistent with the state for every object this API
             produces.  Set False for data whose private leaves were edited by hand.
+        status_flags: optional ``(B,)`` int32 device tensor that receives per-environment flags
+            (``jaxsim_b200._lib.STATUS_*``: NaN / non-unit input quaternion, non-finite output, contact QP not
+            converged) -- the conditions the reference raises as exceptions only under
+            ``JAXSIM_ENABLE_EXCEPTIONS`` (``rbda/utils.py:136-146``) or drops (``rigid.py:359-362``).
 
     Returns:
         The new ``JaxSimModelData`` (same velocity representation; new tensors unless
@@ -535,7 +551,7 @@ def step(
         from .integrators import step_rk4
 
         return step_rk4(model, data, link_forces=link_forces, joint_force_references=joint_force_references)
-    return _step_impl(model, data, 1, link_forces, joint_force_references, update_caches, out, use_input_caches)
+    return _step_impl(model, data, 1, link_forces, joint_force_references, update_caches, out, use_input_caches, status_flags)
 
 
 def step_n(

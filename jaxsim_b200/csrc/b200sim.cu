@@ -525,10 +525,11 @@ int step_t(const B200SimModel* m, int dtype, int64_t B, const void* s, const voi
            const void* vlin, const void* omega, const void* p, const void* mt, const void* tau, const void* fext,
            void* s_o, void* sd_o, void* q_o, void* vlin_o, void* omega_o, void* p_o, void* m_o, void* W_H_B,
            void* iXl, void* W_H_L, void* W_v, int nsteps, long long tau_stride, long long fext_stride, const void* Hin,
-           const void* Vin, void* stream) {
+           const void* Vin, void* stream, int* status = nullptr) {
   Params<T> P;
   std::memset(&P, 0, sizeof(P));
   fill_model_params(m, P);
+  P.status = status;
   P.B = B;
   P.s = (const T*)s; P.sd = (const T*)sd; P.q = (const T*)q; P.vlin = (const T*)vlin; P.omega = (const T*)omega;
   P.p = (const T*)p; P.m = (const T*)mt; P.tau = (const T*)tau; P.fext = (const T*)fext;
@@ -612,6 +613,27 @@ int launch_dual(const B200SimModel* m, Params<DualD>& P, void* stream) {
   }
   if (dev != m->device) cudaSetDevice(dev);
   return rc;
+}
+
+// Per-environment status flags of a step (b200sim_step_n_status): the conditions the reference can only raise as
+// exceptions under JAXSIM_ENABLE_EXCEPTIONS (rbda/utils.py:136-146), evaluated on the device after the step.
+template <typename T>
+__global__ void status_kernel(long long B, int n, const T* __restrict__ q_in, const T* __restrict__ s_o, const T* __restrict__ sd_o,
+                              const T* __restrict__ q_o, const T* __restrict__ vl_o, const T* __restrict__ om_o,
+                              const T* __restrict__ p_o, int* __restrict__ status) {
+  const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= B) return;
+  int f = 0;
+  const T* q = q_in + env * 4;
+  const T qq = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+  if (!(qq == qq)) f |= B200SIM_STATUS_QUATERNION_NAN;
+  else if (!(fabs((double)qq - 1.0) <= 1e-8 + 1e-5)) f |= B200SIM_STATUS_QUATERNION_NOT_UNIT;  // jnp.allclose(q.q, 1.0)
+  T acc = T(0);  // x - x is 0 for finite x, NaN for +-Inf and NaN
+  for (int j = 0; j < n; ++j) { const T a = s_o[env * n + j], b = sd_o[env * n + j]; acc += (a - a) + (b - b); }
+  for (int j = 0; j < 4; ++j) { const T a = q_o[env * 4 + j]; acc += a - a; }
+  for (int j = 0; j < 3; ++j) { const T a = vl_o[env * 3 + j], b = om_o[env * 3 + j], c = p_o[env * 3 + j]; acc += (a - a) + (b - b) + (c - c); }
+  if (!(acc == T(0))) f |= B200SIM_STATUS_NON_FINITE;
+  if (f) status[env] |= f;
 }
 
 extern "C" {
@@ -1046,6 +1068,52 @@ int b200sim_step_n(const B200SimModel* m, int dtype, int64_t B, int32_t nsteps, 
                          W_H_B, iXl, W_H_L, W_v, nsteps, tau_step_stride, fext_step_stride, W_H_L_in, W_v_in, stream);
   return step_t<double>(m, dtype, B, s, sd, q, vlin, omega, p, mt, tau, fext, s_o, sd_o, q_o, vlin_o, omega_o, p_o, m_o,
                         W_H_B, iXl, W_H_L, W_v, nsteps, tau_step_stride, fext_step_stride, W_H_L_in, W_v_in, stream);
+}
+
+int b200sim_step_n_status(const B200SimModel* m, int dtype, int64_t B, int32_t nsteps, const void* s, const void* sd,
+                          const void* q, const void* vlin, const void* omega, const void* p, const void* mt, const void* tau,
+                          int64_t tau_step_stride, const void* fext, int64_t fext_step_stride, const void* W_H_L_in,
+                          const void* W_v_in, void* s_o, void* sd_o, void* q_o, void* vlin_o, void* omega_o, void* p_o,
+                          void* m_o, void* W_H_B, void* iXl, void* W_H_L, void* W_v, int32_t* status_flags, void* stream) {
+  if (!status_flags)
+    return b200sim_step_n(m, dtype, B, nsteps, s, sd, q, vlin, omega, p, mt, tau, tau_step_stride, fext, fext_step_stride,
+                          W_H_L_in, W_v_in, s_o, sd_o, q_o, vlin_o, omega_o, p_o, m_o, W_H_B, iXl, W_H_L, W_v, stream);
+  if (!m || B < 0 || nsteps < 1 || (dtype != 0 && dtype != 1)) return B200SIM_E_INVALID;
+  if (tau_step_stride < 0 || fext_step_stride < 0) return B200SIM_E_INVALID;
+  if (B == 0) return 0;
+  if (!q || !vlin || !omega || !p || !q_o || !vlin_o || !omega_o || !p_o) return B200SIM_E_INVALID;
+  if (m->n > 0 && (!s || !sd || !s_o || !sd_o)) return B200SIM_E_INVALID;
+  if (!aligned(W_H_B, 16) || !aligned(iXl, 16) || !aligned(W_H_L, 16) || !aligned(W_v, dtype == 0 ? 8 : 16))
+    return B200SIM_E_INVALID;
+  if ((W_H_L_in == nullptr) != (W_v_in == nullptr)) return B200SIM_E_INVALID;
+  if (!aligned(W_H_L_in, 16) || !aligned(W_v_in, dtype == 0 ? 8 : 16)) return B200SIM_E_INVALID;
+  if (q == q_o) return B200SIM_E_INVALID;  // the flags describe the INPUT quaternion too: no in-place step here
+  cudaStream_t st = (cudaStream_t)stream;
+  int prev = 0;
+  CK(cudaGetDevice(&prev));
+  if (prev != m->device) CK(cudaSetDevice(m->device));
+  int rc = (int)cudaMemsetAsync(status_flags, 0, (size_t)B * sizeof(int32_t), st);
+  if (!rc) {
+    rc = dtype == 0
+             ? step_t<float>(m, dtype, B, s, sd, q, vlin, omega, p, mt, tau, fext, s_o, sd_o, q_o, vlin_o, omega_o, p_o, m_o, W_H_B,
+                             iXl, W_H_L, W_v, nsteps, tau_step_stride, fext_step_stride, W_H_L_in, W_v_in, stream, status_flags)
+             : step_t<double>(m, dtype, B, s, sd, q, vlin, omega, p, mt, tau, fext, s_o, sd_o, q_o, vlin_o, omega_o, p_o, m_o, W_H_B,
+                              iXl, W_H_L, W_v, nsteps, tau_step_stride, fext_step_stride, W_H_L_in, W_v_in, stream, status_flags);
+  }
+  if (!rc) {
+    const int threads = 128;
+    const int blocks = (int)((B + threads - 1) / threads);
+    if (dtype == 0)
+      status_kernel<float><<<blocks, threads, 0, st>>>(B, m->n, (const float*)q, (const float*)s_o, (const float*)sd_o, (const float*)q_o,
+                                                       (const float*)vlin_o, (const float*)omega_o, (const float*)p_o, status_flags);
+    else
+      status_kernel<double><<<blocks, threads, 0, st>>>(B, m->n, (const double*)q, (const double*)s_o, (const double*)sd_o,
+                                                        (const double*)q_o, (const double*)vlin_o, (const double*)omega_o,
+                                                        (const double*)p_o, status_flags);
+    rc = (int)cudaGetLastError();
+  }
+  if (prev != m->device) cudaSetDevice(prev);
+  return rc;
 }
 
 int b200sim_step(const B200SimModel* m, int dtype, int64_t B, const void* s, const void* sd, const void* q,

@@ -125,6 +125,7 @@ struct Params {
   int o_rows8, n_rows8, o_rows16, n_rows16;  // packed level-walk rows (specialised step kernel), see b200sim_model_create
   int o_rows2_8, o_rows2_16;                 // same rows in the format of step2_kernel (sibling ranks instead of child ranges)
   int ws2_words;                             // step2_kernel: shared-memory words per environment (env2_ws_words)
+  int* status;                               // optional per-environment status flags (b200sim_step_n_status), OR-ed into
   T dt, g, h_terrain, K, D, mu, pexp, qexp, tau_max, w_th, w_max;
   T reg;                // rigid contacts: Delassus regularisation
   T rx_tc, rx_zeta, rx_dmin, rx_dmax, rx_width, rx_mid, rx_pow;  // relaxed-rigid contacts (relaxed_rigid.py:30-82)

@@ -90,6 +90,8 @@ template <> struct RankTol<float> { static __device__ __forceinline__ double tol
 template <> struct RankTol<double> { static __device__ __forceinline__ double tol() { return 1e-10; } };
 
 constexpr unsigned FULL = 0xffffffffu;
+__device__ __forceinline__ float rsqrt_t(float x) { return rsqrtf(x); }
+__device__ __forceinline__ double rsqrt_t(double x) { return rsqrt(x); }
 
 // phase timeline of one warp (diagnostic, like B200SIM_PHASE_MARK of the step kernel): dbg[8 + 16 + k], k = 1..15
 #define B200SIM_RIGID_MARK(k)                                                                                   \
@@ -142,15 +144,19 @@ __device__ __forceinline__ void chol_packed(S* __restrict__ Hp, S* __restrict__ 
   for (int k = 0; k < N; ++k) {
     S d = max_t(Hp[pidx(k, k)], QpTol<S>::pivot_floor() * dg[k]);
     if (!(d > S(0))) d = S(1);
-    const S ipiv = S(1) / sqrt_t(d);
+    const S ipiv = rsqrt_t(d);
     const S* rowk = Hp + pidx(k, 0);
     for (int r = k + 1 + lane; r < N; r += 32) {
       S* row = Hp + pidx(r, 0);
-      S a0 = row[k], a1 = S(0);
+      // four independent partial sums: the shared-memory loads of a trip do not wait for the previous trip's FMAs
+      S a0 = row[k], a1 = S(0), a2 = S(0), a3 = S(0);
       int c = 0;
-      for (; c + 1 < k; c += 2) { a0 -= row[c] * rowk[c]; a1 -= row[c + 1] * rowk[c + 1]; }
-      if (c < k) a0 -= row[c] * rowk[c];
-      const S v = (a0 + a1) * ipiv;
+      for (; c + 3 < k; c += 4) {
+        a0 -= row[c] * rowk[c]; a1 -= row[c + 1] * rowk[c + 1];
+        a2 -= row[c + 2] * rowk[c + 2]; a3 -= row[c + 3] * rowk[c + 3];
+      }
+      for (; c < k; ++c) a0 -= row[c] * rowk[c];
+      const S v = ((a0 + a1) + (a2 + a3)) * ipiv;
       row[k] = v;
       row[r] -= v * v;
     }
@@ -272,7 +278,7 @@ __device__ __forceinline__ void pyr_GT(S mu, const S* w, S* o) {
 // operation (float64 especially): 1/s and 1/z are formed once per iteration and every
 // ratio below multiplies by them; the Cholesky factor carries 1/L_kk.
 template <typename S>
-__device__ __noinline__ int qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int na, S mu_f, int lane) {
+__device__ __noinline__ int qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int na, S mu_f, int lane, const S tol) {
   const int N = 3 * na, M = 5 * na;
   S* x = vN;
   S* q = vN + N;
@@ -293,11 +299,11 @@ __device__ __noinline__ int qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int na
   for (int i = lane; i < N; i += 32) { x[i] = S(0); xb[i] = S(0); }
   for (int j = lane; j < M; j += 32) { s[j] = S(1); z[j] = S(1); }
   S best = S(1e30);
+  bool converged = false;
   S qm = S(0);
   for (int i = lane; i < N; i += 32) qm = max_t(qm, abs_t(q[i]));
   qm = warp_max(qm);
   __syncwarp();
-  const S tol = QpTol<S>::tol();
   const int NP = N * (N + 1) / 2;
   const S inv_M = S(1) / S(M);
   int it = 0;
@@ -349,7 +355,8 @@ __device__ __noinline__ int qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int na
       for (int i = lane; i < N; i += 32) xb[i] = x[i];
     }
     // converged, or the gap is far below the tolerance while a residual stalls at rounding level
-    if (!(merit > tol) || !(m_g > S(1e-3) * tol) || !(mu > S(0))) break;
+    if (!(merit > tol)) { converged = true; break; }
+    if (!(m_g > S(1e-3) * tol) || !(mu > S(0))) break;
     // H = Q + G' diag(z/s) G
     for (int e = lane; e < NP; e += 32) Hp[e] = Qp[e];
     __syncwarp();
@@ -441,7 +448,9 @@ __device__ __noinline__ int qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int na
   __syncwarp();
   for (int i = lane; i < N; i += 32) x[i] = xb[i];
   __syncwarp();
-  return it;
+  // bit 16: the iteration ended without meeting the tolerance (iteration limit, stall at the resolution of S, or a
+  // non-finite iterate): the best iterate is returned.  The reference ignores qpax's flag (rigid.py:359-362).
+  return it | ((converged || best <= S(100) * tol) ? 0 : 0x10000);
 }
 
 // ------------------------------------------------------------------------------------
@@ -1204,7 +1213,12 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
         }
         __syncwarp();
 #endif
-        const int qp_it = qp_pyramids<S>(Qp, Hp, vN, vM, na, S(P.mu), lane);
+        // iterate to the resolution of the DATA: float32 states carry 6e-8 relative rounding, so a float64 solve of a
+        // float32 problem stops at 1e-8 (4-5 interior-point iterations earlier than the 1e-11 of float64 data)
+        const S qp_tol = (sizeof(S) == 8 && sizeof(T) == 4) ? S(1e-8) : QpTol<S>::tol();
+        const int qp_rc = qp_pyramids<S>(Qp, Hp, vN, vM, na, S(P.mu), lane, qp_tol);
+        const int qp_it = qp_rc & 0xFFFF;
+        if (P.status && lane == 0 && (qp_rc & 0x10000)) atomicOr(P.status + env, 8);  // B200SIM_STATUS_QP_NOT_CONVERGED
 #ifdef B200SIM_RIGID_DEBUG
         if (P.dbg && lane == 0 && env == 0) {
           double* D = reinterpret_cast<double*>(P.dbg + 1600);

@@ -311,3 +311,36 @@ def test_rk4_step_accepts_unbatched_data(cuda_device):
     one = js.model.step(model, js.data._map_leaves(pd, lambda t: t[0]))
     assert one.joint_positions.dim() == 1
     assert torch.allclose(one.joint_positions, full.joint_positions[0], rtol=0, atol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("contact", ["soft", "rigid"])
+def test_status_flags(contact, cuda_device):
+    """Device-side status flags (b200sim_step_n_status): what rbda/utils.py:136-146 raises under
+    JAXSIM_ENABLE_EXCEPTIONS, per environment."""
+    import torch
+
+    from jaxsim_b200 import _lib
+    from jaxsim_b200.rbda.contacts import RigidContacts, RigidContactsParams
+
+    kw = dict(contact_model=RigidContacts.build(), contact_params=RigidContactsParams.build()) if contact == "rigid" else {}
+    model = H.build_model("icub_like", **kw)
+    om = H.oracle_model(model)
+    B = 37
+    od = O.random_model_data(om, B, seed=13, in_contact="flat")
+    pd = H.to_product(model, od, torch.float64, cuda_device)
+    pd._base_quaternion[3, 1] = float("nan")
+    pd._base_quaternion[5] *= 1.01
+    pd._joint_velocities[7, 2] = float("inf")
+    flags = torch.full((B,), -1, dtype=torch.int32, device=cuda_device)
+    out = js.model.step(model, pd, status_flags=flags, use_input_caches=False)
+    f = flags.cpu().numpy()
+    assert f[3] & _lib.STATUS_QUATERNION_NAN and f[3] & _lib.STATUS_NON_FINITE
+    assert f[5] == _lib.STATUS_QUATERNION_NOT_UNIT
+    assert f[7] & _lib.STATUS_NON_FINITE
+    clean = np.ones(B, dtype=bool)
+    clean[[3, 5, 7]] = False
+    assert not (f[clean] & (_lib.STATUS_QUATERNION_NAN | _lib.STATUS_QUATERNION_NOT_UNIT | _lib.STATUS_NON_FINITE)).any()
+    assert bool(torch.isfinite(out._joint_positions[clean]).all())
+    with pytest.raises(ValueError):
+        js.model.step(model, pd, status_flags=flags, out=pd)
