@@ -263,7 +263,8 @@ size_t static_smem_bytes2(const B200SimModel* m, size_t ts) {
 int pick_geometry2(const B200SimModel* m, size_t ts, long long B, Geometry* g) {
   if (m->itab2_h.empty() || !m->itab2_d) return B200SIM_E_UNSUPPORTED;
   const size_t st = static_smem_bytes2(m, ts);
-  const size_t budget = (size_t)m->max_smem_optin - 1024;
+  // sharedMemPerBlockOptin bounds static + dynamic shared memory; 512 covers the kernel's static mbarrier array
+  const size_t budget = (size_t)m->max_smem_optin - 512;
   int G = m->tune_G;
   if (G == 0) G = m->nL > 32 ? 16 : 8;
   if (G != 8 && G != 16) return B200SIM_E_UNSUPPORTED;

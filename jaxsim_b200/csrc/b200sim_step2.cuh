@@ -57,15 +57,14 @@ constexpr int K_S = 40, K_SD = 41, K_SDD = 42, K_TREF = 43;
 constexpr int S2_NT = 4;  // link trips of the unrolled phases: nL <= 4 G
 
 // shared-memory words of T per environment: the records + point records of the dynamics, or the
-// output staging of the last step ([nL x 16 | nL x 6 | nL x 36]), whichever is larger, + the mbarrier;
-// padded so that consecutive environments of a warp sit 2 or 6 (G = 8) / 4 (G = 16) 16-byte rows apart
+// output staging of the last step ([nL x 16 | nL x 6 | nL x 36]), whichever is larger (the mbarriers of the bulk
+// loads live in a static shared array); padded so that consecutive environments of a warp sit 2 or 6 (G = 8) / 4 (G = 16) 16-byte rows apart
 // modulo 8: the transposed walks then read 128-bit rows of neighbouring links without bank conflicts
 __host__ __device__ inline size_t env2_ws_words(size_t ts, int nL, int nc, int G) {
   size_t w = (size_t)nL * R2 + (size_t)nc * PTREC;
   const size_t f = (size_t)nL * 16 + (((size_t)nL * 6 + 3) & ~size_t(3)) + (size_t)nL * 36;
   if (f > w) w = f;
   w = (w + 3) & ~size_t(3);
-  w += 16 / ts;
   const size_t per_row = 16 / ts;
   while (G == 16 ? ((w / per_row) % 8 != 4) : ((w / per_row) % 4 != 2)) w += per_row;
   return w;
@@ -143,6 +142,7 @@ __device__ __forceinline__ void st_pose(T* dst, const T* R, const T* p) {
 template <typename T, int G, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) step2_kernel(const Params<T> P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ unsigned long long sm_mbar[THREADS / G];  // one mbarrier per environment slot (bulk input loads)
   constexpr int W4 = 32 / G;  // environments per warp
   T* sm_cst = reinterpret_cast<T*>(smem_raw);
   const int nL = P.nL, n = P.n, nc = P.nc;
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(THREADS, 1) step2_kernel(const Params<T> P) {
   T* ws = ws_base + (size_t)grp * wsw;
   T* wk = ws_base + (size_t)wgrp * wsw;
   T* ptws = ws + (size_t)nL * R2;
-  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(ws + wsw - 16 / sizeof(T));
+  unsigned long long* mbar = sm_mbar + grp;
   if (lane == 0) {
     mbar_init(mbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

@@ -21,6 +21,7 @@ ap.add_argument("--lanes", type=int, default=0)
 ap.add_argument("--generic", action="store_true")
 ap.add_argument("--no-caches", action="store_true")
 ap.add_argument("--bulk-in", action="store_true")
+ap.add_argument("--step-v1", action="store_true", help="first-generation specialised kernel (default: step2_kernel)")
 ap.add_argument("--ring", type=int, default=1, help="number of independent state sets walked round-robin (>= 10 at batch 4096: inputs come from HBM)")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
@@ -28,8 +29,8 @@ dtype = torch.float32 if args.dtype == "f32" else torch.float64
 m = js.model.JaxSimModel.build_from_model_description(models.urdf(args.model), time_step=1e-3)
 if args.lanes:
     m.set_tuning(lanes_per_env=args.lanes)
-if args.generic or args.bulk_in:
-    m.set_options(generic_kernel=args.generic, bulk_in=args.bulk_in)
+if args.generic or args.bulk_in or args.step_v1:
+    m.set_options(generic_kernel=args.generic, bulk_in=args.bulk_in, step_v1=args.step_v1)
 B, n = args.batch, m.dofs()
 data = js.data.random_model_data(m, batch_size=B, seed=0, dtype=dtype, device=dev, velocity_representation=js.common.VelRepr.Inertial)
 tau = 10 * torch.rand(B, n, dtype=dtype, device=dev)
@@ -44,6 +45,11 @@ lib.b200sim_debug_counters(h, cnt)  # enable
 NAMES = ["start", "model staged", "input burst issued", "base state ready", "inputs landed", "kinematics of input (cached unpack / jt+FK)",
          "contacts", "phase 3 link-parallel", "ABA pass 2", "base acceleration", "ABA pass 3", "Euler (base)", "base outputs stored",
          "joints + joint transforms + adjoint emit", "FK chain (new state)", "cache stores issued", "end (bulk stores drained)"]
+if not (args.generic or args.step_v1):  # marks of step2_kernel (B200SIM_MARK2)
+    NAMES = ["start", "model staged, previous launch complete", "input burst issued (2 bulk loads + joint state)", "base state ready", "inputs landed",
+             "records from the cached rows", "contacts", "link-parallel (inertias, bias forces, actuation)", "ABA pass 2", "base acceleration",
+             "ABA pass 3", "Euler (base) + base outputs", "joints: Euler update", "joint transforms, adjoints staged, bulk store",
+             "FK walk (new state)", "link velocities + bulk stores of W_H_L / W_v", "end (bulk stores drained)"]
 rows = []
 for rep in range(5):
     for _ in range(3):
