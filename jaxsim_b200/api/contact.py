@@ -89,3 +89,49 @@ def estimate_good_contact_parameters(model, *, standard_gravity: float = STANDAR
     stiffness = float(np.clip(f_average / max_penetration ** (1 + p), 0, MAX_STIFFNESS))
     damping = float(np.clip(damping_ratio * 2 * np.sqrt(stiffness * m), 0, MAX_DAMPING))
     return model.contact_model._parameters_class.build(K=stiffness, D=damping, mu=static_friction_coefficient, p=p, q=q)
+
+
+def soft_link_contact_forces(model, data) -> tuple[torch.Tensor, torch.Tensor]:
+    """``js.contact.link_contact_forces`` for ``SoftContacts`` (``api/contact.py:516-554``): the inertial-fixed 6D
+    contact force on every link, ``(B, nL, 6)``, and the derivative of the tangential deformation, ``(B, nc, 3)``
+    (zero for disabled points), from the data's cached link transforms / velocities.  Hunt/Crossley with flat terrain
+    (``rbda/contacts/soft.py:195-444``) as batched torch ops: used by the RungeKutta4Fast integrator, which evaluates the
+    contact model once per step OUTSIDE the dynamics kernel (``api/integrators.py:175-188``); every other path evaluates
+    the same model inside the CUDA kernels."""
+    prm = model.contact_params
+    cp = model.kin_dyn_parameters.contact_parameters
+    W_p, W_pd = collidable_point_kinematics(model, data)
+    dtype, dev = W_p.dtype, W_p.device
+    idx = torch.as_tensor([k for k, e in enumerate(cp.enabled) if e], dtype=torch.long, device=dev)
+    m_all = data.contact_state["tangential_deformation"]
+    m = m_all[..., idx, :]
+    K, D, mu = float(prm.K), float(prm.D), float(prm.mu)
+    eps = torch.finfo(dtype).eps
+    delta = torch.clamp(model.terrain.height() - W_p[..., 2], min=0.0)
+    ddot = torch.where(delta > 0, -W_pd[..., 2], torch.zeros_like(delta))
+    dp = torch.pow(delta + eps, float(prm.p))
+    dq = torch.pow(delta + eps, float(prm.q))
+    fn = torch.clamp((K * dp) * delta + (D * dq) * ddot, min=0.0)
+    zero = torch.zeros_like(delta)
+    v_t = torch.stack([W_pd[..., 0], W_pd[..., 1], zero], dim=-1)
+    m_n = torch.stack([zero, zero, m[..., 2]], dim=-1)
+    m_t = torch.stack([m[..., 0], m[..., 1], zero], dim=-1)
+    f_t = -((K * dp)[..., None] * m_t + (D * dq)[..., None] * v_t)
+    sticking = (delta <= 0) | ((f_t * f_t).sum(-1) <= (mu * fn) ** 2)
+    nrm = torch.linalg.norm(f_t, dim=-1)
+    direction = f_t / (nrm + eps * (nrm == 0))[..., None]
+    f_t = torch.where(sticking[..., None], f_t, torch.minimum(mu * fn, nrm)[..., None] * direction)
+    f_t = torch.where((delta <= 0)[..., None], torch.zeros_like(f_t), f_t)
+    md_no = -(K / D) * m
+    md_stick = v_t - (K / D) * m_n
+    md_slip = -(f_t + (K * dp)[..., None] * m_t) / (D * dq)[..., None]
+    status = sticking.to(torch.int64) + (delta <= 0).to(torch.int64)
+    md = torch.where((status == 0)[..., None], md_slip, torch.where((status == 1)[..., None], md_stick, md_no))
+    f = f_t + torch.stack([zero, zero, fn], dim=-1)
+    W_f_C = torch.cat([f, torch.linalg.cross(W_p, f)], dim=-1)  # W_f = [f; p x f] (soft.py:378-386)
+    body, _ = _enabled(model, dev)
+    W_f_L = torch.zeros(W_f_C.shape[:-2] + (model.number_of_links(), 6), dtype=dtype, device=dev)
+    W_f_L.index_add_(-2, body, W_f_C)
+    m_dot = torch.zeros_like(m_all)
+    m_dot[..., idx, :] = md
+    return W_f_L, m_dot

@@ -57,8 +57,74 @@ def rk4_integration(model, data, link_forces_inertial, joint_torques):
     )
 
 
+def rk4fast_integration(model, data, link_forces_inertial, joint_torques):
+    """``rk4fast_integration`` (``api/integrators.py:159-263``) for batched data, quirks included: the contact forces
+    are evaluated once at the initial state and held over the four stages; the integrated contact state starts from
+    ``update_contact_state(m_dot)`` = the derivative itself (``soft.py:164-176``) and each stage returns its contact
+    state as the "derivative"; the position derivatives come from the ORIGINAL data (``:206-209``).  Each stage is one
+    ABA launch (``b200sim_aba``) on the stage's state with the frozen link forces."""
+    from . import contact as _contact
+    from . import model as _model
+    from .data import JaxSimModelData
+    from jaxsim_b200.rbda.contacts import SoftContacts
+
+    if not isinstance(model.contact_model, SoftContacts) or model.number_of_collidable_points() == 0:
+        raise NotImplementedError(
+            "RungeKutta4Fast: the reference only runs with collidable points (api/integrators.py:175-190); "
+            "implemented for SoftContacts")
+    dt = model.time_step
+    q = data._base_quaternion
+    nrm = torch.linalg.norm(q, dim=-1, keepdim=True)
+    q = q / torch.where(nrm == 0, torch.ones_like(nrm), nrm)
+    W_f_L, m_dot = _contact.soft_link_contact_forces(model, data)
+    W_f_total = W_f_L if link_forces_inertial is None else W_f_L + link_forces_inertial
+    # system_position_dynamics(data) with Baumgarte K = 1.0 (api/ode.py:134-171), of the ORIGINAL data
+    w, p = data._base_angular_velocity, data._base_position
+    pd = data._base_linear_velocity + torch.linalg.cross(w, p)
+    qn = data.base_orientation
+    nw = torch.linalg.norm(w, dim=-1, keepdim=True)
+    nq = torch.linalg.norm(qn, dim=-1, keepdim=True)
+    v0 = nw * (1.0 - nq)
+    qw, qx, qy, qz = qn.unbind(-1)
+    wx, wy, wz = w.unbind(-1)
+    v0 = v0.squeeze(-1)
+    qd = 0.5 * torch.stack([qw * v0 - qx * wx - qy * wy - qz * wz, qx * v0 + qw * wx + qz * wy - qy * wz,
+                            qy * v0 - qz * wx + qw * wy + qx * wz, qz * v0 + qy * wx - qx * wy + qw * wz], dim=-1)
+    sd0 = data._joint_velocities
+
+    def f(x):
+        d = JaxSimModelData(
+            velocity_representation=VelRepr.Inertial, _joint_positions=x["joint_positions"], _joint_velocities=x["joint_velocities"],
+            _base_quaternion=x["base_quaternion"], _base_linear_velocity=x["base_linear_velocity"],
+            _base_angular_velocity=x["base_angular_velocity"], _base_position=x["base_position"], contact_state={})
+        vd, sdd = _model.forward_dynamics_aba(model, d, joint_forces=joint_torques, link_forces=W_f_total)
+        return dict(base_position=pd, base_quaternion=qd, joint_positions=sd0, base_linear_velocity=vd[:, 0:3],
+                    base_angular_velocity=vd[:, 3:6], joint_velocities=sdd,
+                    contact_state={"tangential_deformation": x["contact_state"]["tangential_deformation"]})
+
+    x0 = dict(
+        base_position=data._base_position, base_quaternion=q, joint_positions=data._joint_positions,
+        base_linear_velocity=data._base_linear_velocity, base_angular_velocity=data._base_angular_velocity,
+        joint_velocities=data._joint_velocities, contact_state={"tangential_deformation": m_dot},
+    )
+    mid = lambda x, d: x + (0.5 * dt) * d  # noqa: E731
+    fin = lambda x, d: x + dt * d  # noqa: E731
+    k1 = f(x0)
+    k2 = f(_tree(mid, x0, k1))
+    k3 = f(_tree(mid, x0, k2))
+    k4 = f(_tree(fin, x0, k3))
+    dxdt = _tree(lambda a, b, c, d: (a + 2 * b + 2 * c + d) / 6, k1, k2, k3, k4)
+    xf = _tree(fin, x0, dxdt)
+    return data.replace(
+        model, joint_positions=xf["joint_positions"], joint_velocities=xf["joint_velocities"],
+        base_quaternion=xf["base_quaternion"], base_position=xf["base_position"],
+        contact_state=xf["contact_state"],
+        _inertial_base_velocity=(xf["base_linear_velocity"], xf["base_angular_velocity"]),
+    )
+
+
 def step_rk4(model, data, *, link_forces=None, joint_force_references=None):
-    """``js.model.step`` with ``IntegratorType.RungeKutta4`` (``api/model.py:2601-2681``)."""
+    """``js.model.step`` with ``IntegratorType.RungeKutta4`` / ``RungeKutta4Fast`` (``api/model.py:2601-2681``)."""
     if data._base_quaternion.dim() == 1:  # unbatched data, like every other entry point
         from .data import _map_leaves
 
@@ -73,4 +139,8 @@ def step_rk4(model, data, *, link_forces=None, joint_force_references=None):
             data.velocity_representation, data.link_transforms, is_force=True,
         )
     tau = ode.compute_resultant_torques(model, data, joint_force_references=joint_force_references)
+    from .model import IntegratorType
+
+    if model.integrator == IntegratorType.RungeKutta4Fast:
+        return rk4fast_integration(model, data, fext, tau)
     return rk4_integration(model, data, fext, tau)

@@ -226,8 +226,6 @@ class JaxSimModel:
                 f"{contact_model._parameters_class.__name__}"
             )
         integrator = integrator if integrator is not None else IntegratorType.SemiImplicitEuler
-        if integrator == IntegratorType.RungeKutta4Fast:
-            raise NotImplementedError("IntegratorType.RungeKutta4Fast is not implemented")
         return cls(
             model_name=model_name,
             time_step=float(time_step) if time_step is not None else 0.001,
@@ -547,7 +545,7 @@ def step(
         The new ``JaxSimModelData`` (same velocity representation; new tensors unless
         ``out`` is given: the input is not modified, like the reference's immutable pytrees).
     """
-    if model.integrator == IntegratorType.RungeKutta4:
+    if model.integrator in (IntegratorType.RungeKutta4, IntegratorType.RungeKutta4Fast):
         from .integrators import step_rk4
 
         return step_rk4(model, data, link_forces=link_forces, joint_force_references=joint_force_references)

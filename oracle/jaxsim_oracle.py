@@ -943,3 +943,72 @@ def step_rk4(model: OracleModel, data: OracleData, link_forces_inertial=None, jo
     tau_ref = np.zeros((B, n), dtype=dtype) if joint_force_references is None else np.asarray(joint_force_references, dtype=dtype)
     tau_total = compute_resultant_torques(model, data.joint_positions, data.joint_velocities, tau_ref)
     return rk4_integration(model, data, W_f, tau_total)
+
+
+# =============================================================================
+# api/integrators.py:159-263  (RK4Fast)
+# =============================================================================
+
+
+def rk4fast_integration(model: OracleModel, data: OracleData, W_f_L_external, tau_total) -> OracleData:
+    """``rk4fast_integration`` (``api/integrators.py:159-263``), literally, quirks included:
+
+    * the contact forces are evaluated ONCE, at the initial state (``:175-188``), and held over the four stages;
+    * the contact state that enters the integration is ``update_contact_state(contact_state_derivative)``, which for
+      SoftContacts returns the DERIVATIVE m_dot under the key ``tangential_deformation`` (``soft.py:164-176``), and the
+      stages return the stage's contact state itself as its "derivative" (``:218-219``);
+    * the position derivatives come from ``system_position_dynamics(data=data)`` -- the ORIGINAL data, not the stage's
+      (``:206-209``) -- so positions advance with the initial velocities.
+    Only models with collidable points reach the end of the reference function (``W_f_L_terrain`` is undefined
+    otherwise, ``:175-190``)."""
+    dtype = data.joint_positions.dtype
+    dt = dtype.type(model.time_step)
+    nc = len(model.kin_dyn_parameters.contact_parameters.body)
+    if nc == 0 or model.contact_model != "soft":
+        raise NotImplementedError("rk4fast_integration: the reference only runs with collidable points; oracle: SoftContacts")
+    W_f_C, m_dot = soft_compute_contact_forces(model, data)
+    W_f_L_total = W_f_L_external + link_forces_from_contact_forces(model, W_f_C)
+    W_w = data.base_angular_velocity
+    W_pd_B = data.base_linear_velocity + np.einsum("bij,bj->bi", wedge(W_w), data.base_position)
+    W_Qd_B = quaternion_derivative(data.base_orientation, W_w, K=1.0)
+    sd0 = data.joint_velocities
+
+    def f(x):
+        d = data_replace(model, x["joint_positions"], x["joint_velocities"], x["base_quaternion"],
+                         x["base_linear_velocity"], x["base_angular_velocity"], x["base_position"],
+                         x["tangential_deformation"])
+        W_vd_WB, sdd = aba(model, d.base_position, d.base_orientation, d.joint_positions, d.base_linear_velocity,
+                           d.base_angular_velocity, d.joint_velocities, tau_total, W_f_L_total)
+        return dict(base_position=W_pd_B, base_quaternion=W_Qd_B, joint_positions=sd0,
+                    base_linear_velocity=W_vd_WB[:, 0:3], base_angular_velocity=W_vd_WB[:, 3:6], joint_velocities=sdd,
+                    tangential_deformation=x["tangential_deformation"])
+
+    qn = safe_norm(data.base_quaternion, axis=-1)
+    q0 = data.base_quaternion / np.where(qn == 0, 1.0, qn)[:, None]
+    x0 = dict(
+        base_position=data.base_position, base_quaternion=q0, joint_positions=data.joint_positions,
+        base_linear_velocity=data.base_linear_velocity, base_angular_velocity=data.base_angular_velocity,
+        joint_velocities=data.joint_velocities, tangential_deformation=m_dot,
+    )
+    mid = lambda x, k: {n: x[n] + (0.5 * dt) * k[n] for n in x}  # noqa: E731
+    fin = lambda x, k: {n: x[n] + dt * k[n] for n in x}  # noqa: E731
+    k1 = f(x0)
+    k2 = f(mid(x0, k1))
+    k3 = f(mid(x0, k2))
+    k4 = f(fin(x0, k3))
+    dxdt = {n: (k1[n] + 2 * k2[n] + 2 * k3[n] + k4[n]) / 6 for n in x0}
+    xf = fin(x0, dxdt)
+    return data_replace(model, xf["joint_positions"], xf["joint_velocities"], xf["base_quaternion"],
+                        xf["base_linear_velocity"], xf["base_angular_velocity"], xf["base_position"],
+                        xf["tangential_deformation"])
+
+
+def step_rk4fast(model: OracleModel, data: OracleData, link_forces_inertial=None, joint_force_references=None) -> OracleData:
+    """``js.model.step`` with ``IntegratorType.RungeKutta4Fast`` (``api/model.py:2601-2681``)."""
+    B = data.joint_positions.shape[0]
+    dtype = data.joint_positions.dtype
+    nL, n = model.number_of_links(), model.dofs()
+    W_f = np.zeros((B, nL, 6), dtype=dtype) if link_forces_inertial is None else np.asarray(link_forces_inertial, dtype=dtype)
+    tau_ref = np.zeros((B, n), dtype=dtype) if joint_force_references is None else np.asarray(joint_force_references, dtype=dtype)
+    tau_total = compute_resultant_torques(model, data.joint_positions, data.joint_velocities, tau_ref)
+    return rk4fast_integration(model, data, W_f, tau_total)

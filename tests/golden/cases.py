@@ -39,6 +39,8 @@ CASES = [
     # ---- RK4
     dict(id="icub_rk4_contact", seed=16, in_contact=True, tau=True, m=True, integrator="rk4", **_ICUB),
     dict(id="box_rk4_contact", model="box", B=3, seed=17, in_contact=True, m=True, integrator="rk4"),
+    dict(id="icub_rk4fast_contact", seed=43, in_contact=True, tau=True, m=True, integrator="rk4fast", **_ICUB),
+    dict(id="box_rk4fast_flat", model="box", B=3, seed=44, in_contact="flat", m=True, integrator="rk4fast"),
     # ---- rigid contacts (BASELINE configs[2])
     dict(id="box_rigid_air", model="box", B=2, seed=18, contact="rigid"),
     dict(id="box_rigid_contact", model="box", B=4, seed=19, contact="rigid", in_contact=True),

@@ -29,7 +29,8 @@ def build_model_for_case(case: dict):
     cm = cm_cls.build()
     cp = cp_cls.build(**case["contact_params"]) if case["contact_params"] else None
     ap = ActuationParams(**case["actuation"]) if case["actuation"] else None
-    integ = {"semi_implicit_euler": js.model.IntegratorType.SemiImplicitEuler, "rk4": js.model.IntegratorType.RungeKutta4}[case["integrator"]]
+    integ = {"semi_implicit_euler": js.model.IntegratorType.SemiImplicitEuler, "rk4": js.model.IntegratorType.RungeKutta4,
+             "rk4fast": js.model.IntegratorType.RungeKutta4Fast}[case["integrator"]]
     return build_model(case["model"], time_step=case["time_step"], contact_model=cm, contact_params=cp,
                        actuation_params=ap, integrator=integ)
 

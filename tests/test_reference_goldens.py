@@ -112,6 +112,8 @@ def test_oracle_step_matches_reference(cid):
     for _ in range(case["rollout"]):
         if case["contact"] in ("rigid", "relaxed"):
             out, tol = R.step(om, out, link_forces_inertial=W_f, joint_force_references=tau), 1e-6
+        elif case["integrator"] == "rk4fast":
+            out, tol = O.step_rk4fast(om, out, link_forces_inertial=W_f, joint_force_references=tau), 1e-9
         elif case["integrator"] == "rk4":
             out, tol = O.step_rk4(om, out, link_forces_inertial=W_f, joint_force_references=tau), 1e-9
         else:
