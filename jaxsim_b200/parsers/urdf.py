@@ -158,6 +158,7 @@ def _parse(xml_text: str):
     name = root.get("name", "model")
 
     links: dict[str, _Link] = {}
+    seq = 0  # position of a collision shape in the file: the reference keeps this order (parsers/rod/parser.py:303-345)
     for le in root.findall("link"):
         lname = le.get("name")
         ine = le.find("inertial")
@@ -181,9 +182,11 @@ def _parse(xml_text: str):
                 continue
             if geo.find("box") is not None:
                 size = [float(v) for v in geo.find("box").get("size").split()]
-                cols.append(("box", H, size))
+                cols.append(("box", H, size, seq))
+                seq += 1
             elif geo.find("sphere") is not None:
-                cols.append(("sphere", H, float(geo.find("sphere").get("radius"))))
+                cols.append(("sphere", H, float(geo.find("sphere").get("radius")), seq))
+                seq += 1
             # cylinder / capsule / mesh: not supported by the reference defaults either.
         links[lname] = _Link(name=lname, mass=mass, inertia=M, collisions=cols)
 
@@ -263,8 +266,8 @@ def build_kin_dyn_parameters(model_description: str | pathlib.Path) -> tuple[str
             X = _adjoint_inverse(p_H_c)  # c_X_p
             parent.inertia = parent.inertia + X.T @ child.inertia @ X
             parent.mass = parent.mass + child.mass
-        for kind, H, prm in child.collisions:
-            parent.collisions.append((kind, p_H_c @ H, prm))
+        for kind, H, prm, sq in child.collisions:
+            parent.collisions.append((kind, p_H_c @ H, prm, sq))
         # joints whose parent link was removed are re-expressed in the lumped parent
         for jj in joints:
             if jj is not j and jj.parent == child.name:
@@ -338,14 +341,15 @@ def build_kin_dyn_parameters(model_description: str | pathlib.Path) -> tuple[str
         position_limit_damper=arr(lambda j: j.position_limit_damper),
     )
 
-    # collidable points: shape order in the file, link order = BFS
-    # (parsers/descriptions/model.py:88-138, api/kin_dyn_parameters.py:811-835)
+    # collidable points: ONE list of shapes in the order of the file; the shapes of lumped links keep their slot and
+    # are only re-parented / transformed (parsers/rod/parser.py:303-345, parsers/descriptions/model.py:88-138,
+    # api/kin_dyn_parameters.py:811-835) -- not grouped by link index
     bodies, points = [], []
-    for l in order:
-        for kind, H, prm in l.collisions:
-            P = _box_points(prm, H) if kind == "box" else _sphere_points(prm, H)
-            points.append(P)
-            bodies.extend([l.index] * P.shape[0])
+    shapes = sorted(((sq, l.index, kind, H, prm) for l in order for kind, H, prm, sq in l.collisions), key=lambda t: t[0])
+    for _, lidx, kind, H, prm in shapes:
+        P = _box_points(prm, H) if kind == "box" else _sphere_points(prm, H)
+        points.append(P)
+        bodies.extend([lidx] * P.shape[0])
     cp = (
         ContactParameters(body=tuple(bodies), point=np.vstack(points), enabled=tuple(True for _ in bodies))
         if bodies

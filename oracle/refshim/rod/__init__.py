@@ -1,27 +1,35 @@
-"""Name-only stand-in for `rod` (the reference's URDF/SDF front end).  The goldens build the
-reference's `ModelDescription` directly (tests/golden/make_goldens.py), so nothing here runs."""
+"""Stand-in for `rod` (the reference's URDF/SDF front end, `pyproject.toml: rod >= 0.3.3`), far enough for the
+reference's OWN `jaxsim.parsers.rod.parser.extract_model_data` / `build_model_description` (parser.py:36-420) and
+`jaxsim.parsers.rod.utils` (inertial -> 6D inertia :21-66, joint types :69-101, box / sphere collisions -> collidable
+points :104-225) to run UNMODIFIED on a URDF string.
+
+What the real stack does and this file restates: `rod.Sdf.load(urdf)` converts the URDF to SDF with sdformat and hands
+out a tree of dataclasses (`Model`, `Link`, `Inertial`, `Joint`, `Axis`, `Collision`, `Geometry`, `Pose`, ...); after
+`switch_frame_convention(FrameConvention.Urdf)` every joint pose is expressed in its parent link and every link pose is
+the identity w.r.t. its parent joint -- which is what a URDF says in the first place, so this stand-in builds that tree
+straight from the URDF elements:
+
+    <link><inertial><origin xyz rpy/><mass value/><inertia ixx.. /></inertial>
+          <collision><origin/><geometry><box size/>|<sphere radius/></geometry></collision></link>
+    <joint type><origin/><parent link/><child link/><axis xyz/><limit lower upper effort velocity/>
+           <dynamics damping friction/></joint>
+
+Fixed joints are kept as joints (sdformat's `preserveFixedJoint`); the reference's `ModelDescription.build_model_from`
+lumps them (parsers/kinematic_graph.py:379-611).  Only the attributes those two reference files read are provided.
+Test infrastructure (fixture generation in the build container), never imported by the product.
+"""
+
+from __future__ import annotations
+
+import dataclasses
 import enum
+import pathlib
+import xml.etree.ElementTree as ET
+
+import numpy as np
 
 from . import urdf  # noqa: F401
-
-
-class _Unavailable:
-    def __init__(self, *a, **k):
-        raise NotImplementedError("rod is not available: build a ModelDescription directly")
-
-
-class Model(_Unavailable): pass
-class Sdf(_Unavailable): pass
-class Link(_Unavailable): pass
-class Joint(_Unavailable): pass
-class Pose(_Unavailable): pass
-class Inertia(_Unavailable): pass
-class Box(_Unavailable): pass
-class Sphere(_Unavailable): pass
-class Cylinder(_Unavailable): pass
-class Mesh(_Unavailable): pass
-class Collision(_Unavailable): pass
-class Frame(_Unavailable): pass
+from . import utils  # noqa: F401
 
 
 class FrameConvention(enum.Enum):
@@ -29,3 +37,255 @@ class FrameConvention(enum.Enum):
     Sdf = enum.auto()
     World = enum.auto()
     Model = enum.auto()
+
+
+def _floats(text, n=None, default=None):
+    if text is None:
+        return default
+    v = [float(x) for x in text.split()]
+    assert n is None or len(v) == n, (text, n)
+    return v
+
+
+@dataclasses.dataclass
+class Pose:
+    """`<pose relative_to=...>x y z roll pitch yaw</pose>`; URDF `<origin xyz rpy>` has the same fixed-axis XYZ meaning:
+    R = Rz(yaw) Ry(pitch) Rx(roll)."""
+
+    pose: list
+    relative_to: str | None = None
+
+    def transform(self) -> np.ndarray:
+        x, y, z, r, p, yw = self.pose
+        cr, sr, cp, sp, cy, sy = np.cos(r), np.sin(r), np.cos(p), np.sin(p), np.cos(yw), np.sin(yw)
+        Rx = np.array([[1, 0, 0], [0, cr, -sr], [0, sr, cr]])
+        Ry = np.array([[cp, 0, sp], [0, 1, 0], [-sp, 0, cp]])
+        Rz = np.array([[cy, -sy, 0], [sy, cy, 0], [0, 0, 1]])
+        H = np.eye(4)
+        H[0:3, 0:3] = Rz @ Ry @ Rx
+        H[0:3, 3] = [x, y, z]
+        return H
+
+
+def _origin(elem, relative_to=None) -> Pose | None:
+    o = None if elem is None else elem.find("origin")
+    if o is None:
+        return None
+    return Pose(pose=_floats(o.get("xyz"), 3, [0.0, 0.0, 0.0]) + _floats(o.get("rpy"), 3, [0.0, 0.0, 0.0]), relative_to=relative_to)
+
+
+@dataclasses.dataclass
+class Inertia:
+    ixx: float = 0.0
+    iyy: float = 0.0
+    izz: float = 0.0
+    ixy: float | None = None
+    ixz: float | None = None
+    iyz: float | None = None
+
+
+@dataclasses.dataclass
+class Inertial:
+    mass: float = 0.0
+    inertia: Inertia = dataclasses.field(default_factory=Inertia)
+    pose: Pose | None = None
+
+
+@dataclasses.dataclass
+class Box:
+    size: list
+
+
+@dataclasses.dataclass
+class Sphere:
+    radius: float
+
+
+@dataclasses.dataclass
+class Cylinder:
+    radius: float
+    length: float
+
+
+@dataclasses.dataclass
+class Mesh:
+    uri: str
+    scale: list | None = None
+
+
+@dataclasses.dataclass
+class Geometry:
+    box: Box | None = None
+    sphere: Sphere | None = None
+    cylinder: Cylinder | None = None
+    mesh: Mesh | None = None
+
+
+@dataclasses.dataclass
+class Collision:
+    name: str
+    geometry: Geometry
+    pose: Pose | None = None
+
+
+@dataclasses.dataclass
+class Link:
+    name: str
+    inertial: Inertial
+    pose: Pose | None = None
+    collision: list = dataclasses.field(default_factory=list)
+
+    def collisions(self) -> list:
+        return list(self.collision)
+
+
+@dataclasses.dataclass
+class Xyz:
+    xyz: list
+
+
+@dataclasses.dataclass
+class Limit:
+    lower: float | None = None
+    upper: float | None = None
+    effort: float | None = None
+    velocity: float | None = None
+    stiffness: float | None = None
+    dissipation: float | None = None
+
+
+@dataclasses.dataclass
+class Dynamics:
+    damping: float | None = None
+    friction: float | None = None
+
+
+@dataclasses.dataclass
+class Axis:
+    xyz: Xyz | None = None
+    limit: Limit | None = None
+    dynamics: Dynamics | None = None
+
+
+@dataclasses.dataclass
+class Joint:
+    name: str
+    type: str
+    parent: str
+    child: str
+    pose: Pose | None = None
+    axis: Axis | None = None
+
+
+@dataclasses.dataclass
+class Frame:
+    name: str
+    attached_to: str
+    pose: Pose | None = None
+
+
+@dataclasses.dataclass
+class Model:
+    name: str
+    link: list
+    joint: list
+    frame: list = dataclasses.field(default_factory=list)
+    pose: Pose | None = None
+    canonical_link: str | None = None
+
+    def links(self) -> list:
+        return list(self.link)
+
+    def joints(self) -> list:
+        return list(self.joint)
+
+    def frames(self) -> list:
+        return list(self.frame)
+
+    def is_fixed_base(self) -> bool:
+        return any(j.parent == "world" for j in self.joint)
+
+    def get_canonical_link(self) -> str:
+        if self.canonical_link is not None:
+            return self.canonical_link
+        if self.is_fixed_base():
+            return next(j.child for j in self.joint if j.parent == "world")
+        children = {j.child for j in self.joint}
+        roots = [l.name for l in self.link if l.name not in children]
+        assert len(roots) == 1, roots
+        return roots[0]
+
+    def switch_frame_convention(self, frame_convention: FrameConvention, explicit_frames: bool = True, **_) -> None:
+        # the tree is built in URDF convention (joint poses in the parent link, identity link poses)
+        if frame_convention is not FrameConvention.Urdf:
+            raise NotImplementedError("the stand-in only holds models in URDF frame convention")
+
+
+def _link_from_urdf(e) -> Link:
+    ine = e.find("inertial")
+    inertial = Inertial()
+    if ine is not None:
+        m = ine.find("mass")
+        I = ine.find("inertia")
+        g = (lambda k: float(I.get(k)) if (I is not None and I.get(k) is not None) else None)  # noqa: E731
+        inertial = Inertial(
+            mass=float(m.get("value")) if m is not None else 0.0,
+            inertia=Inertia(ixx=g("ixx") or 0.0, iyy=g("iyy") or 0.0, izz=g("izz") or 0.0, ixy=g("ixy"), ixz=g("ixz"), iyz=g("iyz")),
+            pose=_origin(ine),
+        )
+    cols = []
+    for k, c in enumerate(e.findall("collision")):
+        ge = c.find("geometry")
+        geo = Geometry()
+        if ge is not None:
+            if ge.find("box") is not None:
+                geo.box = Box(size=_floats(ge.find("box").get("size"), 3))
+            elif ge.find("sphere") is not None:
+                geo.sphere = Sphere(radius=float(ge.find("sphere").get("radius")))
+            elif ge.find("cylinder") is not None:
+                geo.cylinder = Cylinder(radius=float(ge.find("cylinder").get("radius")), length=float(ge.find("cylinder").get("length")))
+            elif ge.find("mesh") is not None:
+                geo.mesh = Mesh(uri=ge.find("mesh").get("filename"), scale=_floats(ge.find("mesh").get("scale")))
+        cols.append(Collision(name=c.get("name") or f"{e.get('name')}_collision_{k}", geometry=geo, pose=_origin(c)))
+    return Link(name=e.get("name"), inertial=inertial, pose=None, collision=cols)
+
+
+def _joint_from_urdf(e) -> Joint:
+    jt = e.get("type")
+    parent, child = e.find("parent").get("link"), e.find("child").get("link")
+    # a fixed joint carries the URDF default axis (1 0 0): the reference hashes joint descriptions and a None axis is
+    # not hashable (parsers/descriptions/joint.py:108-114); its value is never used (utils.py:85-86 returns Fixed first)
+    axis = Axis(xyz=Xyz(xyz=[1.0, 0.0, 0.0])) if jt == "fixed" else None
+    if jt in ("revolute", "continuous", "prismatic"):
+        ax = e.find("axis")
+        lim, dyn = e.find("limit"), e.find("dynamics")
+        f = (lambda el, k: float(el.get(k)) if (el is not None and el.get(k) is not None) else None)  # noqa: E731
+        # a continuous joint has no position limits (URDF); <limit effort velocity> may still be present
+        limit = Limit(lower=None if jt == "continuous" else f(lim, "lower"), upper=None if jt == "continuous" else f(lim, "upper"),
+                      effort=f(lim, "effort"), velocity=f(lim, "velocity")) if lim is not None else None
+        dynamics = Dynamics(damping=f(dyn, "damping"), friction=f(dyn, "friction")) if dyn is not None else None
+        axis = Axis(xyz=Xyz(xyz=_floats(ax.get("xyz"), 3) if ax is not None else [1.0, 0.0, 0.0]), limit=limit, dynamics=dynamics)
+    # joint pose = <origin>, expressed in the parent link (the model frame for joints attached to the world)
+    pose = _origin(e, relative_to=None if parent == "world" else parent) or Pose(pose=[0.0] * 6, relative_to=None if parent == "world" else parent)
+    return Joint(name=e.get("name"), type=jt, parent=parent, child=child, pose=pose, axis=axis)
+
+
+class Sdf:
+    def __init__(self, model=None, version: str = "1.7"):
+        self.model = model if isinstance(model, list) else ([model] if model is not None else [])
+        self.version = version
+
+    def models(self) -> list:
+        return list(self.model)
+
+    @staticmethod
+    def load(sdf, is_urdf: bool | None = None) -> "Sdf":
+        text = sdf
+        if isinstance(sdf, pathlib.Path) or (isinstance(sdf, str) and len(sdf) < 1024 and "<" not in sdf):
+            text = pathlib.Path(sdf).read_text()
+        root = ET.fromstring(text)
+        if root.tag != "robot":
+            raise NotImplementedError("the rod stand-in reads URDF (<robot>) documents only")
+        links = [_link_from_urdf(e) for e in root.findall("link") if e.get("name") != "world"]
+        joints = [_joint_from_urdf(e) for e in root.findall("joint")]
+        return Sdf(model=Model(name=root.get("name"), link=links, joint=joints))
