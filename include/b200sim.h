@@ -217,6 +217,25 @@ int b200sim_step_n_status(const B200SimModel *model, int dtype, int64_t B, int32
                           void *q_o, void *v_lin_o, void *omega_o, void *p_o, void *m_tan_o, void *W_H_B, void *i_X_lam,
                           void *W_H_L, void *W_v_WL, int32_t *status_flags, void *stream);
 
+/* b200sim_step_n with both extras.  `f_ext_representation`: how `f_ext_inertial` is expressed -- the reference's
+ * `link_forces` argument is given in `data.velocity_representation` (api/model.py:2617-2618) and re-expressed with the
+ * link transforms of EVERY step (api/model.py:2641-2646, api/common.py:160-222):
+ *   B200SIM_REPR_INERTIAL  inertial-fixed (what b200sim_step / b200sim_step_n expect);
+ *   B200SIM_REPR_BODY      body-fixed: frame of the link;
+ *   B200SIM_REPR_MIXED     mixed: origin of the link, world axes.
+ * The conversion happens inside the kernels with the link poses of the current step, so a fused rollout applies the
+ * forces exactly like repeated `step` calls.  B200SIM_E_UNSUPPORTED for body-fixed / mixed forces on models whose link
+ * poses differ from the ABA chain (fixed base with an offset mount, SDF-posed base link). */
+#define B200SIM_REPR_INERTIAL 0
+#define B200SIM_REPR_BODY 1
+#define B200SIM_REPR_MIXED 2
+int b200sim_step_n_ex(const B200SimModel *model, int dtype, int64_t B, int32_t nsteps, const void *s, const void *sd,
+                      const void *q_wxyz, const void *v_lin, const void *omega, const void *p, const void *m_tan,
+                      const void *tau, int64_t tau_step_stride, const void *f_ext, int64_t f_ext_step_stride,
+                      const void *W_H_L_in, const void *W_v_in, void *s_o, void *sd_o, void *q_o, void *v_lin_o,
+                      void *omega_o, void *p_o, void *m_tan_o, void *W_H_B, void *i_X_lam, void *W_H_L, void *W_v_WL,
+                      int32_t f_ext_representation, int32_t *status_flags, void *stream);
+
 /* Cache computation only (JaxSimModelData.build / .replace, api/data.py:66-202,406-523):
  * normalises q (written to q_o if not NULL) and fills the requested caches. */
 int b200sim_fk(const B200SimModel *model, int dtype, int64_t B,

@@ -74,6 +74,7 @@ OPT_BULK_IN = 8
 OPT_NO_PDL = 16
 OPT_STEP_V1 = 32
 OPT_NO_BULK_IN = 64
+REPR_INERTIAL, REPR_BODY, REPR_MIXED = 0, 1, 2
 STATUS_QUATERNION_NAN = 1
 STATUS_QUATERNION_NOT_UNIT = 2
 STATUS_NON_FINITE = 4
@@ -89,6 +90,7 @@ EXPORTED_SYMBOLS = (
     "b200sim_step",
     "b200sim_step_n",
     "b200sim_step_n_status",
+    "b200sim_step_n_ex",
     "b200sim_fk",
     "b200sim_aba",
     "b200sim_rnea",
@@ -133,6 +135,10 @@ def load() -> C.CDLL:
         [vp, C.c_int, C.c_int64, C.c_int32] + [vp] * 8 + [C.c_int64, vp, C.c_int64] + [vp] * 15
     )
     lib.b200sim_step_n_status.restype = C.c_int
+    lib.b200sim_step_n_ex.argtypes = (
+        [vp, C.c_int, C.c_int64, C.c_int32] + [vp] * 8 + [C.c_int64, vp, C.c_int64] + [vp] * 13 + [C.c_int32, vp, vp]
+    )
+    lib.b200sim_step_n_ex.restype = C.c_int
     lib.b200sim_step.argtypes = [vp, C.c_int, C.c_int64] + [vp] * 21
     lib.b200sim_step.restype = C.c_int
     lib.b200sim_fk.argtypes = [vp, C.c_int, C.c_int64] + [vp] * 12

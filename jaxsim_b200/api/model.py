@@ -362,6 +362,13 @@ def _alloc_outputs(model, B, dtype, dev, update_caches, soft):
     return out
 
 
+def _links_follow_aba_chain(model) -> bool:
+    """True where the FK link poses coincide with the ABA chain poses (floating base, suc_H_i[0] = I: every URDF
+    floating-base model): the kernels can then re-express Body / Mixed link forces themselves."""
+    H0 = np.asarray(model.kin_dyn_parameters.joint_model.suc_H_i)[0]
+    return bool(model.floating_base()) and bool(np.array_equal(H0, np.eye(4)))
+
+
 def _step_impl(model, data, n_steps, link_forces, joint_force_references, update_caches, out, use_input_caches=True,
                status_flags=None):
     s = data._joint_positions
@@ -404,7 +411,7 @@ def _step_impl(model, data, n_steps, link_forces, joint_force_references, update
                 raise ValueError(tau.shape, (B, n))
         tau = tau.contiguous()
 
-    fext, fext_stride = None, 0
+    fext, fext_stride, fext_repr = None, 0, _lib.REPR_INERTIAL
     if link_forces is not None:
         O_f = torch.as_tensor(link_forces, dtype=dtype, device=dev)
         per_step = O_f.dim() == 4
@@ -412,17 +419,20 @@ def _step_impl(model, data, n_steps, link_forces, joint_force_references, update
         if O_f.shape[-3:] != (B, nL, 6) or (per_step and O_f.shape[0] != n_steps):
             raise ValueError(O_f.shape, (B, nL, 6))
         if data.velocity_representation != VelRepr.Inertial:
-            if n_steps > 1:
-                # the reference re-expresses the forces with the link transforms of EVERY step (api/model.py:2641-2646):
-                # converting once with the initial poses would apply a different wrench from the second step on
-                raise NotImplementedError(
-                    "link_forces of a multi-step launch must be expressed in VelRepr.Inertial "
-                    "(Body / Mixed forces follow the moving links: call step() per step, or convert them yourself)"
+            # api/model.py:2641-2646: expressed in data.velocity_representation, re-expressed with the link
+            # transforms of every step.  The kernels do that themselves (b200sim_step_n_ex) wherever the link poses
+            # are the ABA chain poses; otherwise (fixed base with an offset mount, SDF-posed base) a torch shim converts
+            # with the transforms of the input state, which is only right for a single step.
+            if _links_follow_aba_chain(model):
+                fext_repr = _lib.REPR_BODY if data.velocity_representation == VelRepr.Body else _lib.REPR_MIXED
+            else:
+                if n_steps > 1:
+                    raise NotImplementedError(
+                        "Body / Mixed link_forces of a multi-step launch on a model whose base link pose is offset "
+                        "from the chain root: call step() per step, or give the forces in VelRepr.Inertial")
+                O_f = other_representation_to_inertial(
+                    O_f, data.velocity_representation, _batched(data.link_transforms, 3), is_force=True
                 )
-            # api/model.py:2641-2646: expressed in data.velocity_representation -> inertial-fixed
-            O_f = other_representation_to_inertial(
-                O_f, data.velocity_representation, _batched(data.link_transforms, 3), is_force=True
-            )
         fext = O_f.contiguous()
         fext_stride = B * nL * 6 if per_step else 0
 
@@ -483,10 +493,10 @@ def _step_impl(model, data, n_steps, link_forces, joint_force_references, update
         if o["q"].data_ptr() == q.data_ptr():
             raise ValueError("status_flags describe the input quaternion too: not available for an in-place step")
     with ctx:
-        if status_flags is None:
+        if status_flags is None and fext_repr == _lib.REPR_INERTIAL:
             rc = _lib.load().b200sim_step_n(*args, _stream_ptr(dev))
         else:
-            rc = _lib.load().b200sim_step_n_status(*args, _ptr(status_flags), _stream_ptr(dev))
+            rc = _lib.load().b200sim_step_n_ex(*args, int(fext_repr), _ptr(status_flags), _stream_ptr(dev))
     _lib.check(rc, "b200sim_step_n")
 
     if out is not None:

@@ -526,11 +526,12 @@ int step_t(const B200SimModel* m, int dtype, int64_t B, const void* s, const voi
            const void* vlin, const void* omega, const void* p, const void* mt, const void* tau, const void* fext,
            void* s_o, void* sd_o, void* q_o, void* vlin_o, void* omega_o, void* p_o, void* m_o, void* W_H_B,
            void* iXl, void* W_H_L, void* W_v, int nsteps, long long tau_stride, long long fext_stride, const void* Hin,
-           const void* Vin, void* stream, int* status = nullptr) {
+           const void* Vin, void* stream, int* status = nullptr, int fext_repr = 0) {
   Params<T> P;
   std::memset(&P, 0, sizeof(P));
   fill_model_params(m, P);
   P.status = status;
+  P.fext_repr = fext_repr;
   P.B = B;
   P.s = (const T*)s; P.sd = (const T*)sd; P.q = (const T*)q; P.vlin = (const T*)vlin; P.omega = (const T*)omega;
   P.p = (const T*)p; P.m = (const T*)mt; P.tau = (const T*)tau; P.fext = (const T*)fext;
@@ -1071,12 +1072,16 @@ int b200sim_step_n(const B200SimModel* m, int dtype, int64_t B, int32_t nsteps, 
                         W_H_B, iXl, W_H_L, W_v, nsteps, tau_step_stride, fext_step_stride, W_H_L_in, W_v_in, stream);
 }
 
-int b200sim_step_n_status(const B200SimModel* m, int dtype, int64_t B, int32_t nsteps, const void* s, const void* sd,
-                          const void* q, const void* vlin, const void* omega, const void* p, const void* mt, const void* tau,
-                          int64_t tau_step_stride, const void* fext, int64_t fext_step_stride, const void* W_H_L_in,
-                          const void* W_v_in, void* s_o, void* sd_o, void* q_o, void* vlin_o, void* omega_o, void* p_o,
-                          void* m_o, void* W_H_B, void* iXl, void* W_H_L, void* W_v, int32_t* status_flags, void* stream) {
-  if (!status_flags)
+int b200sim_step_n_ex(const B200SimModel* m, int dtype, int64_t B, int32_t nsteps, const void* s, const void* sd,
+                      const void* q, const void* vlin, const void* omega, const void* p, const void* mt, const void* tau,
+                      int64_t tau_step_stride, const void* fext, int64_t fext_step_stride, const void* W_H_L_in,
+                      const void* W_v_in, void* s_o, void* sd_o, void* q_o, void* vlin_o, void* omega_o, void* p_o,
+                      void* m_o, void* W_H_B, void* iXl, void* W_H_L, void* W_v, int32_t f_ext_representation,
+                      int32_t* status_flags, void* stream) {
+  if (f_ext_representation < 0 || f_ext_representation > 2) return B200SIM_E_INVALID;
+  // body-fixed / mixed forces are re-expressed with the ABA chain poses: available where they ARE the link poses
+  if (m && f_ext_representation != 0 && fext && (m->flags & F_GENERIC_FK)) return B200SIM_E_UNSUPPORTED;
+  if (!status_flags && (f_ext_representation == 0 || !fext))
     return b200sim_step_n(m, dtype, B, nsteps, s, sd, q, vlin, omega, p, mt, tau, tau_step_stride, fext, fext_step_stride,
                           W_H_L_in, W_v_in, s_o, sd_o, q_o, vlin_o, omega_o, p_o, m_o, W_H_B, iXl, W_H_L, W_v, stream);
   if (!m || B < 0 || nsteps < 1 || (dtype != 0 && dtype != 1)) return B200SIM_E_INVALID;
@@ -1088,20 +1093,22 @@ int b200sim_step_n_status(const B200SimModel* m, int dtype, int64_t B, int32_t n
     return B200SIM_E_INVALID;
   if ((W_H_L_in == nullptr) != (W_v_in == nullptr)) return B200SIM_E_INVALID;
   if (!aligned(W_H_L_in, 16) || !aligned(W_v_in, dtype == 0 ? 8 : 16)) return B200SIM_E_INVALID;
-  if (q == q_o) return B200SIM_E_INVALID;  // the flags describe the INPUT quaternion too: no in-place step here
+  if (status_flags && q == q_o) return B200SIM_E_INVALID;  // the flags describe the INPUT quaternion too: no in-place step
   cudaStream_t st = (cudaStream_t)stream;
   int prev = 0;
   CK(cudaGetDevice(&prev));
   if (prev != m->device) CK(cudaSetDevice(m->device));
-  int rc = (int)cudaMemsetAsync(status_flags, 0, (size_t)B * sizeof(int32_t), st);
+  int rc = status_flags ? (int)cudaMemsetAsync(status_flags, 0, (size_t)B * sizeof(int32_t), st) : 0;
   if (!rc) {
     rc = dtype == 0
              ? step_t<float>(m, dtype, B, s, sd, q, vlin, omega, p, mt, tau, fext, s_o, sd_o, q_o, vlin_o, omega_o, p_o, m_o, W_H_B,
-                             iXl, W_H_L, W_v, nsteps, tau_step_stride, fext_step_stride, W_H_L_in, W_v_in, stream, status_flags)
+                             iXl, W_H_L, W_v, nsteps, tau_step_stride, fext_step_stride, W_H_L_in, W_v_in, stream, status_flags,
+                             f_ext_representation)
              : step_t<double>(m, dtype, B, s, sd, q, vlin, omega, p, mt, tau, fext, s_o, sd_o, q_o, vlin_o, omega_o, p_o, m_o, W_H_B,
-                              iXl, W_H_L, W_v, nsteps, tau_step_stride, fext_step_stride, W_H_L_in, W_v_in, stream, status_flags);
+                              iXl, W_H_L, W_v, nsteps, tau_step_stride, fext_step_stride, W_H_L_in, W_v_in, stream, status_flags,
+                              f_ext_representation);
   }
-  if (!rc) {
+  if (!rc && status_flags) {
     const int threads = 128;
     const int blocks = (int)((B + threads - 1) / threads);
     if (dtype == 0)
@@ -1115,6 +1122,16 @@ int b200sim_step_n_status(const B200SimModel* m, int dtype, int64_t B, int32_t n
   }
   if (prev != m->device) cudaSetDevice(prev);
   return rc;
+}
+
+int b200sim_step_n_status(const B200SimModel* m, int dtype, int64_t B, int32_t nsteps, const void* s, const void* sd,
+                          const void* q, const void* vlin, const void* omega, const void* p, const void* mt, const void* tau,
+                          int64_t tau_step_stride, const void* fext, int64_t fext_step_stride, const void* W_H_L_in,
+                          const void* W_v_in, void* s_o, void* sd_o, void* q_o, void* vlin_o, void* omega_o, void* p_o,
+                          void* m_o, void* W_H_B, void* iXl, void* W_H_L, void* W_v, int32_t* status_flags, void* stream) {
+  return b200sim_step_n_ex(m, dtype, B, nsteps, s, sd, q, vlin, omega, p, mt, tau, tau_step_stride, fext, fext_step_stride,
+                           W_H_L_in, W_v_in, s_o, sd_o, q_o, vlin_o, omega_o, p_o, m_o, W_H_B, iXl, W_H_L, W_v, 0, status_flags,
+                           stream);
 }
 
 int b200sim_step(const B200SimModel* m, int dtype, int64_t B, const void* s, const void* sd, const void* q,

@@ -126,6 +126,7 @@ struct Params {
   int o_rows2_8, o_rows2_16;                 // same rows in the format of step2_kernel (sibling ranks instead of child ranges)
   int ws2_words;                             // step2_kernel: shared-memory words per environment (env2_ws_words)
   int* status;                               // optional per-environment status flags (b200sim_step_n_status), OR-ed into
+  int fext_repr;                             // representation of `fext`: 0 inertial-fixed, 1 body-fixed, 2 mixed (api/common.py:160-222)
   T dt, g, h_terrain, K, D, mu, pexp, qexp, tau_max, w_th, w_max;
   T reg;                // rigid contacts: Delassus regularisation
   T rx_tc, rx_zeta, rx_dmin, rx_dmax, rx_width, rx_mid, rx_pow;  // relaxed-rigid contacts (relaxed_rigid.py:30-82)
@@ -407,6 +408,33 @@ __device__ __forceinline__ void solve6_spd_neg(T M[6][6], const T* b, T* x) {
 #pragma unroll
     for (int k = i + 1; k < 6; ++k) v -= M[k][i] * x[k];
     x[i] = v;
+  }
+}
+
+// External 6D force on a link, given in the representation `repr` of the data (api/model.py:2641-2646,
+// api/common.py:160-222), added to the wrench (fe, ne) about the link origin in world axes (the frame F_i):
+//   inertial-fixed: moment about the world origin          -> ne += n - p x f
+//   mixed:          frame at the link origin, world axes    == F_i, taken as is
+//   body-fixed:     frame at the link origin, link axes     -> rotate both parts by W_R_L
+// (R, p): world pose of the link AT THE CURRENT STEP, so the forces of a fused rollout follow the links exactly like
+// repeated `step` calls re-express them with every state's link transforms.
+template <typename T>
+__device__ __forceinline__ void add_external_wrench(const int repr, const T* fx, const T* R, const T* p, T* fe, T* ne) {
+  const T f[3] = {fx[0], fx[1], fx[2]}, mo[3] = {fx[3], fx[4], fx[5]};
+  if (repr == 1) {
+    T a[3], b[3];
+    mat3_vec(R, f, a);
+    mat3_vec(R, mo, b);
+    fe[0] += a[0]; fe[1] += a[1]; fe[2] += a[2];
+    ne[0] += b[0]; ne[1] += b[1]; ne[2] += b[2];
+  } else {
+    fe[0] += f[0]; fe[1] += f[1]; fe[2] += f[2];
+    ne[0] += mo[0]; ne[1] += mo[1]; ne[2] += mo[2];
+    if (repr == 0) {
+      T t[3];
+      cross3(p, f, t);
+      ne[0] -= t[0]; ne[1] -= t[1]; ne[2] -= t[2];
+    }
   }
 }
 
@@ -1136,12 +1164,7 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
         }
         if (fext_step) {
           const T* fx = fext_step + (env * nL + i) * 6;
-          T f[3] = {fx[0], fx[1], fx[2]};
-          fe[0] += f[0]; fe[1] += f[1]; fe[2] += f[2];
-          ne[0] += fx[3]; ne[1] += fx[4]; ne[2] += fx[5];
-          T t[3];
-          cross3(p, f, t);  // moment about the link origin = moment about W origin - p x f
-          ne[0] -= t[0]; ne[1] -= t[1]; ne[2] -= t[2];
+          add_external_wrench(P.fext_repr, fx, R, p, fe, ne);
         }
         // link inertia in world axes about the link origin
         const T mass = c[C_MASS];

@@ -755,15 +755,7 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
         T tau = T(0);
         if (bias) {
           T fe[3] = {T(0), T(0), T(0)}, ne[3] = {T(0), T(0), T(0)};
-          if (P.fext) {
-            const T* fx = P.fext + (env * nL + i) * 6;
-            const T f[3] = {fx[0], fx[1], fx[2]};
-            fe[0] = f[0]; fe[1] = f[1]; fe[2] = f[2];
-            ne[0] = fx[3]; ne[1] = fx[4]; ne[2] = fx[5];
-            T t[3];
-            cross3(p, f, t);
-            ne[0] -= t[0]; ne[1] -= t[1]; ne[2] -= t[2];
-          }
+          if (P.fext) add_external_wrench(P.fext_repr, P.fext + (env * nL + i) * 6, R, p, fe, ne);
           T fI[3], nI[3], t[3];
           cross3(v + 3, cw, t);
           fI[0] = mass * (v[0] + t[0]); fI[1] = mass * (v[1] + t[1]); fI[2] = mass * (v[2] + t[2]);

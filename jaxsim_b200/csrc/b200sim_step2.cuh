@@ -446,15 +446,7 @@ __global__ void __launch_bounds__(THREADS, 1) step2_kernel(const Params<T> P) {
               cross3_add(lev, f, ne);
             }
           }
-          if (fext_step) {
-            const T* fx = fext_step + (env * nL + i) * 6;
-            T f[3] = {fx[0], fx[1], fx[2]};
-            fe[0] += f[0]; fe[1] += f[1]; fe[2] += f[2];
-            ne[0] += fx[3]; ne[1] += fx[4]; ne[2] += fx[5];
-            T t[3];
-            cross3(p, f, t);  // moment about the link origin = moment about W origin - p x f
-            ne[0] -= t[0]; ne[1] -= t[1]; ne[2] -= t[2];
-          }
+          if (fext_step) add_external_wrench(P.fext_repr, fext_step + (env * nL + i) * 6, R, p, fe, ne);
           // link inertia in world axes about the link origin
           T Cc[16];
           ldv<16>(c + C_MASS, Cc);  // mass, com, D_link, limit spring / damper, limits, friction

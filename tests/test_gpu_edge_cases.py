@@ -278,25 +278,41 @@ def test_model_edits_take_effect_after_the_first_step(cuda_device):
 
 
 @pytest.mark.gpu
-def test_step_n_rejects_moving_frame_link_forces(cuda_device):
-    """Body / Mixed link_forces follow the links; a fused multi-step launch must not freeze them."""
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_step_n_with_moving_frame_link_forces(dtype, cuda_device):
+    """Body / Mixed link_forces follow the links.  The kernels re-express them with the link poses of EVERY
+    fused step (b200sim_step_n_ex), so step_n equals repeated step -- which equals the oracle fed with the forces
+    converted by the reference's formula at every state (api/model.py:2641-2646)."""
     import torch
 
+    td = torch.float64 if dtype == "float64" else torch.float32
     model = H.build_model("icub_like")
     om = H.oracle_model(model)
-    od = O.random_model_data(om, 4, seed=5)
-    for vr in (js.common.VelRepr.Mixed, js.common.VelRepr.Body):
-        pd = H.to_product(model, od, torch.float64, cuda_device, velocity_representation=vr)
-        f = torch.ones(4, model.number_of_links(), 6, dtype=torch.float64, device=cuda_device)
-        js.model.step_n(model, pd, 1, link_forces=f)
-        with pytest.raises(NotImplementedError):
-            js.model.step_n(model, pd, 3, link_forces=f)
-    pd = H.to_product(model, od, torch.float64, cuda_device, velocity_representation=js.common.VelRepr.Inertial)
-    a = js.model.step_n(model, pd, 3, link_forces=f)
-    b = pd
-    for _ in range(3):
-        b = js.model.step(model, b, link_forces=f)
-    assert torch.allclose(a.joint_positions, b.joint_positions, rtol=0, atol=1e-12)
+    B, T = 6, 4
+    od = O.random_model_data(om, B, seed=5, in_contact=True)
+    rng = np.random.default_rng(8)
+    f_np = rng.uniform(-20, 20, size=(B, model.number_of_links(), 6))
+    f = torch.as_tensor(f_np, dtype=td, device=cuda_device)
+    for name, vr in (("mixed", js.common.VelRepr.Mixed), ("body", js.common.VelRepr.Body)):
+        pd = H.to_product(model, od, td, cuda_device, velocity_representation=vr)
+        fused = js.model.step_n(model, pd, T, link_forces=f)
+        seq, ref = pd, od
+        for _ in range(T):
+            seq = js.model.step(model, seq, link_forces=f)
+            W_f = O.other_representation_to_inertial(f_np, name, ref.link_transforms, is_force=True)
+            ref = O.step(om, ref, link_forces_inertial=W_f)
+        # (not bit-identical: repeated steps read the cached inertial-fixed link velocities back, v + p x w - p x w)
+        H.compare_data(fused, ref, 5 * H.RTOL[dtype], f"step_n link_forces {name} {dtype}")
+        H.compare_data(seq, ref, 5 * H.RTOL[dtype], f"repeated step link_forces {name} {dtype}")
+    # a model whose base link pose is offset from the chain root keeps the single-step shim and refuses fused steps
+    fixed = H.build_model("pendulum")
+    omf = H.oracle_model(fixed)
+    odf = O.random_model_data(omf, 3, seed=2)
+    pdf = H.to_product(fixed, odf, td, cuda_device, velocity_representation=js.common.VelRepr.Mixed)
+    ff = torch.ones(3, fixed.number_of_links(), 6, dtype=td, device=cuda_device)
+    js.model.step(fixed, pdf, link_forces=ff)
+    with pytest.raises(NotImplementedError):
+        js.model.step_n(fixed, pdf, 3, link_forces=ff)
 
 
 @pytest.mark.gpu
