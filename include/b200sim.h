@@ -36,7 +36,8 @@ extern "C" {
 
 #define B200SIM_CONTACT_NONE 0
 #define B200SIM_CONTACT_SOFT 1 /* rbda/contacts/soft.py */
-#define B200SIM_CONTACT_RIGID 2 /* rbda/contacts/rigid.py (b200sim_step only; floating base; enabled points a prefix) */
+#define B200SIM_CONTACT_RIGID 2 /* rbda/contacts/rigid.py (floating base; enabled points a prefix; b200sim_step_n with nsteps > 1 runs
+                                    nsteps cascades on the stream and needs the W_H_L / W_v_WL outputs, which feed the next step) */
 #define B200SIM_CONTACT_RELAXED_RIGID 3 /* rbda/contacts/relaxed_rigid.py (same restrictions as RIGID) */
 
 #define B200SIM_E_INVALID (-1)     /* NULL / negative size / bad dtype */

@@ -462,8 +462,9 @@ def _step_impl(model, data, n_steps, link_forces, joint_force_references, update
         # RigidContacts READS the cached link velocities on purpose: after an impact they are the
         # pre-impact ones (rbda/contacts/rigid.py:429-434 never refreshes them) and the reference's
         # penetration rate / Jacobian-derivative term use them (api/contact.py:39-43,470-477)
-        if n_steps != 1:
-            raise NotImplementedError("step_n is not available with RigidContacts / RelaxedRigidContacts")
+        if n_steps != 1 and not update_caches:
+            raise NotImplementedError("step_n with RigidContacts / RelaxedRigidContacts needs update_caches=True "
+                                      "(every step reads the cached link transforms / velocities of the previous one)")
         if use_input_caches and data._link_transforms is not None and data._link_velocities is not None:
             Hin = _batched(data._link_transforms, 3).to(dtype).contiguous()
             Vin = _batched(data._link_velocities, 2).to(dtype).contiguous()

@@ -17,6 +17,8 @@
 #include <cstdlib>
 #include <cstdint>
 #include <cstring>
+#include <mutex>
+#include <unordered_map>
 #include <new>
 #include <vector>
 
@@ -47,8 +49,11 @@ struct B200SimModel {
   double reg = 1e-6;
   double rx_tc = 0.02, rx_zeta = 1.0, rx_dmin = 0.9, rx_dmax = 0.95, rx_width = 1e-3, rx_mid = 0.5, rx_pow = 2.0;  // RelaxedRigid
   unsigned long long* dbg_d = nullptr;  // debug counters, allocated by b200sim_debug_counters
-  int* rigid_scratch = nullptr;      // work lists of the rigid-contact cascade
-  long long rigid_scratch_cap = 0;
+  // work lists of the rigid-contact cascade: one scratch buffer per (model, stream), so that steps of the same model on
+  // different streams do not share counters
+  struct RigidScratch { int* buf = nullptr; long long cap = 0; };
+  std::unordered_map<void*, RigidScratch> rigid_scratch;
+  std::mutex rigid_mutex;
   // device blobs
   float *cst_f = nullptr, *csuc_f = nullptr, *pt_f = nullptr;
   double *cst_d = nullptr, *csuc_d = nullptr, *pt_d = nullptr;
@@ -123,12 +128,12 @@ struct Geometry {
   size_t smem;
 };
 
-int pick_geometry(const B200SimModel* m, int dtype, long long B, Geometry* g) {
+int pick_geometry(const B200SimModel* m, int dtype, long long B, Geometry* g, int force_G = 0) {
   const size_t ts = dtype == 2 ? 16 : (dtype == B200SIM_DTYPE_F64 ? 8 : 4);  // 2: Dual<double>
   const size_t st = static_smem_bytes(m, ts), pe = env_smem_bytes(m, ts);
   const size_t budget = (size_t)m->max_smem_optin - 1024;
   if (st + pe > budget) return B200SIM_E_TOO_LARGE;
-  int G = m->tune_G;
+  int G = force_G ? force_G : m->tune_G;
   if (G == 0) {
     // widest tree level / link count bound the useful lanes; 8 balances the sequential
     // level walks against the link-parallel phases for humanoid-size trees
@@ -400,12 +405,24 @@ int launch_rigid_level(const B200SimModel* m, Params<T>& P, int cap, cudaStream_
 
 // work lists: [0..3] counters, then two lists of `cap` ints.  Grown on demand (not during a
 // stream capture: run one eager step of the largest batch first).
-int ensure_rigid_scratch(B200SimModel* m, long long B) {
-  if (m->rigid_scratch && m->rigid_scratch_cap >= B) return 0;
-  if (m->rigid_scratch) CK(cudaFree(m->rigid_scratch));
-  m->rigid_scratch = nullptr;
-  CK(cudaMalloc((void**)&m->rigid_scratch, sizeof(int) * (4 + 2 * (size_t)B)));
-  m->rigid_scratch_cap = B;
+int ensure_rigid_scratch(B200SimModel* m, long long B, cudaStream_t st, int** buf, long long* cap) {
+  std::lock_guard<std::mutex> lock(m->rigid_mutex);
+  B200SimModel::RigidScratch& sc = m->rigid_scratch[(void*)st];
+  if (!sc.buf || sc.cap < B) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone)
+      return B200SIM_E_UNSUPPORTED;  // cannot allocate inside a capture: run one eager step of the largest batch first
+    if (sc.buf) {
+      CK(cudaStreamSynchronize(st));
+      CK(cudaFree(sc.buf));
+    }
+    sc.buf = nullptr;
+    sc.cap = 0;
+    CK(cudaMalloc((void**)&sc.buf, sizeof(int) * (4 + 2 * (size_t)B)));
+    sc.cap = B;
+  }
+  *buf = sc.buf;
+  *cap = sc.cap;
   return 0;
 }
 
@@ -416,10 +433,11 @@ int launch_rigid(const B200SimModel* cm, Params<T>& P, int dtype, void* stream) 
   CK(cudaGetDevice(&dev));
   if (dev != m->device) CK(cudaSetDevice(m->device));
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = ensure_rigid_scratch(m, P.B);
-  int* cnt = m->rigid_scratch;
+  int* cnt = nullptr;
+  long long scap = 0;
+  int rc = ensure_rigid_scratch(m, P.B, st, &cnt, &scap);
   int* list1 = cnt ? cnt + 4 : nullptr;
-  int* list2 = cnt ? list1 + m->rigid_scratch_cap : nullptr;
+  int* list2 = cnt ? list1 + scap : nullptr;
   if (!rc) rc = (int)cudaMemsetAsync(cnt, 0, 4 * sizeof(int), st);
   if (!rc) {
     // level 0: never reads the cached link velocities (they may be the pre-impact ones)
@@ -545,8 +563,27 @@ int step_t(const B200SimModel* m, int dtype, int64_t B, const void* s, const voi
     P.flags |= F_BULK_IN;
   P.mode = MODE_STEP;
   if (m->contact_model >= B200SIM_CONTACT_RIGID && m->nc > 0) {
-    if (nsteps != 1) return B200SIM_E_UNSUPPORTED;
-    return launch_rigid(m, P, dtype, stream);
+    if (nsteps == 1) return launch_rigid(m, P, dtype, stream);
+    // n consecutive rigid steps = n cascades on the stream.  From the second step on the state is stepped IN PLACE in
+    // the output buffers and the cached link transforms / velocities written by the previous step are the cached inputs
+    // -- exactly what repeated `step` calls hand over, including the pre-impact link velocities the reference leaves in
+    // its cache (rbda/contacts/rigid.py:429-434).
+    if (!W_H_L || !W_v) return B200SIM_E_UNSUPPORTED;
+    Params<T> Pk = P;
+    Pk.nsteps = 1;
+    Pk.tau_step_stride = 0;
+    Pk.fext_step_stride = 0;
+    for (int k = 0; k < nsteps; ++k) {
+      Pk.tau = P.tau ? P.tau + (long long)k * tau_stride : nullptr;
+      Pk.fext = P.fext ? P.fext + (long long)k * fext_stride : nullptr;
+      if (k == 1) {
+        Pk.s = P.s_o; Pk.sd = P.sd_o; Pk.q = P.q_o; Pk.vlin = P.vlin_o; Pk.omega = P.omega_o; Pk.p = P.p_o;
+        Pk.Hin = P.W_H_L; Pk.Vin = P.W_v;
+      }
+      const int rc = launch_rigid(m, Pk, dtype, stream);
+      if (rc) return rc;
+    }
+    return 0;
   }
   return launch(m, P, dtype, stream);
 }
@@ -594,12 +631,10 @@ int upload_dual(const std::vector<double>& val, const std::vector<double>& tan, 
 }
 
 int launch_dual(const B200SimModel* m, Params<DualD>& P, void* stream) {
-  B200SimModel tuned = *m;  // geometry only: lanes fixed to the instantiated width
-  tuned.tune_G = 8;
-  while (tuned.tune_G > 1 && tuned.tune_G / 2 >= m->nL) tuned.tune_G /= 2;
+  int fG = 8;  // lanes fixed to the instantiated widths
+  while (fG > 1 && fG / 2 >= m->nL) fG /= 2;
   Geometry g;
-  int rc = pick_geometry(&tuned, 2, P.B, &g);
-  tuned.cst_h.clear();
+  int rc = pick_geometry(m, 2, P.B, &g, fG);
   if (rc) return rc;
   P.envs_per_block = g.epb;
   int dev = 0;
@@ -934,7 +969,8 @@ void b200sim_model_destroy(B200SimModel* m) {
   cudaGetDevice(&prev);
   cudaSetDevice(m->device);
   cudaFree(m->cst_f); cudaFree(m->cst_d); cudaFree(m->csuc_f); cudaFree(m->csuc_d);
-  cudaFree(m->pt_f); cudaFree(m->pt_d); cudaFree(m->itab_d); cudaFree(m->itab2_d); cudaFree(m->rigid_scratch); cudaFree(m->dbg_d);
+  cudaFree(m->pt_f); cudaFree(m->pt_d); cudaFree(m->itab_d); cudaFree(m->itab2_d); cudaFree(m->dbg_d);
+  for (auto& kv : m->rigid_scratch) cudaFree(kv.second.buf);
   cudaFree(m->cst_dd); cudaFree(m->csuc_dd); cudaFree(m->pt_dd);
   cudaSetDevice(prev);
   delete m;

@@ -105,6 +105,13 @@ def test_rigid_rollout_uses_stale_link_velocities(dtype, cuda_device):
         pd = js.model.step(model, pd)
     tol = {"float64": 1e-5, "float32": 5e-3}[dtype]
     H.compare_data(pd, od, tol, f"rigid rollout {dtype}", floors=floors)
+    # the same 20 steps as ONE step_n call (20 cascades on the stream, stepping in place from the second step on,
+    # each reading the caches the previous one wrote): bit-identical to the loop above
+    import torch
+
+    fused = js.model.step_n(model, H.to_product(model, _inputs(om, B, 3, "flat", dtype), _dtype(dtype), cuda_device), 20)
+    for _, leaf in H.LEAVES:
+        assert torch.equal(getattr(fused, leaf), getattr(pd, leaf)), leaf
     # the quirk is observable: the cached link velocities differ from those of the state
     fresh = O.data_replace(om, od.joint_positions, od.joint_velocities, od.base_quaternion, od.base_linear_velocity,
                            od.base_angular_velocity, od.base_position)
@@ -139,8 +146,9 @@ def test_rigid_unsupported_configurations(cuda_device):
         js.data.JaxSimModelData.build(model, batch_size=2, dtype=torch.float64, device=cuda_device)
     model = _model("box")
     data = js.data.JaxSimModelData.build(model, batch_size=2, dtype=torch.float64, device=cuda_device)
-    with pytest.raises(NotImplementedError):
-        js.model.step_n(model, data, 2)
+    with pytest.raises(NotImplementedError):  # every rigid step reads the caches the previous one wrote
+        js.model.step_n(model, data, 2, update_caches=False)
+    js.model.step_n(model, data, 2)
 
 
 @pytest.mark.parametrize("dtype", ["float64", "float32"])
