@@ -1,2 +1,2 @@
 """Functional API mirroring ``jaxsim.api`` for the hot path (``model``, ``data``, ``common``)."""
-from . import common, contact, data, integrators, kin_dyn_parameters, model, ode  # noqa: F401
+from . import common, contact, data, frame, integrators, kin_dyn_parameters, model, ode  # noqa: F401

@@ -130,6 +130,48 @@ class FrameParameters:
     transform: np.ndarray = dataclasses.field(default_factory=lambda: np.zeros((0, 4, 4)))
 
 
+class ConstraintType:
+    """``api/kin_dyn_parameters.py:1248-1255``: the reference implements the weld constraint only."""
+
+    Weld = 0
+
+
+@dataclasses.dataclass(frozen=True)
+class ConstraintMap:
+    """Kinematic constraints between pairs of frames (``api/kin_dyn_parameters.py:1258-1350``).  Immutable like the
+    reference's: ``add_constraint`` returns a new map.  Frame indices count after the links (``api/frame.py``)."""
+
+    frame_idxs_1: tuple[int, ...] = ()
+    frame_idxs_2: tuple[int, ...] = ()
+    constraint_types: tuple[int, ...] = ()
+    K_P: tuple[float, ...] = ()
+    K_D: tuple[float, ...] = ()
+    parent_link_idxs_1: tuple[int, ...] = ()
+    parent_link_idxs_2: tuple[int, ...] = ()
+
+    def add_constraint(self, model, frame_idx_1: int, frame_idx_2: int, constraint_type: int,
+                       K_P: float | None = None, K_D: float | None = None) -> "ConstraintMap":
+        """``ConstraintMap.add_constraint`` (``:1287-1350``): Baumgarte gains default to K_P = 1000 and
+        K_D = 2 sqrt(K_P) (critical damping)."""
+        from . import frame as _frame
+
+        if constraint_type != ConstraintType.Weld:
+            raise NotImplementedError("only ConstraintType.Weld exists in the reference (kin_dyn_parameters.py:1253-1255)")
+        K_P = 1000.0 if K_P is None else float(K_P)
+        K_D = 2.0 * float(np.sqrt(K_P)) if K_D is None else float(K_D)
+        l1 = _frame.idx_of_parent_link(model, frame_index=frame_idx_1)
+        l2 = _frame.idx_of_parent_link(model, frame_index=frame_idx_2)
+        return ConstraintMap(
+            frame_idxs_1=self.frame_idxs_1 + (int(frame_idx_1),), frame_idxs_2=self.frame_idxs_2 + (int(frame_idx_2),),
+            constraint_types=self.constraint_types + (int(constraint_type),),
+            K_P=self.K_P + (K_P,), K_D=self.K_D + (K_D,),
+            parent_link_idxs_1=self.parent_link_idxs_1 + (int(l1),), parent_link_idxs_2=self.parent_link_idxs_2 + (int(l2),),
+        )
+
+    def __len__(self) -> int:
+        return len(self.frame_idxs_1)
+
+
 @dataclasses.dataclass
 class KinDynParameters:
     """``api/kin_dyn_parameters.py:21-63``."""
@@ -142,6 +184,8 @@ class KinDynParameters:
     joint_parameters: JointParameters
     contact_parameters: ContactParameters
     frame_parameters: FrameParameters = dataclasses.field(default_factory=FrameParameters)
+    # kinematic constraints (``:62-63``); None / empty = unconstrained
+    constraints: ConstraintMap | None = None
 
     def number_of_links(self) -> int:
         return len(self.link_names)

@@ -14,6 +14,7 @@ calling these functions without the CUDA library or with CPU tensors raises.
 from __future__ import annotations
 
 import contextlib
+import copy
 import ctypes as C
 import dataclasses
 import enum
@@ -170,6 +171,13 @@ class JaxSimModel:
         """A copy with some fields replaced (``replace`` of the reference's dataclasses); the copy creates its
         own device models lazily, with the new values."""
         return dataclasses.replace(self, **changes)
+
+    @contextlib.contextmanager
+    def editable(self, validate: bool = True):
+        """``with model.editable(validate=False) as model:`` of the reference (``utils/jaxsim_dataclass.py:22-27``):
+        yields a copy whose fields -- and whose ``kin_dyn_parameters`` container -- can be assigned without touching the
+        original (e.g. ``model.kin_dyn_parameters.constraints = ...``, ``tests/test_simulations.py:438-440``)."""
+        yield dataclasses.replace(self, kin_dyn_parameters=copy.copy(self.kin_dyn_parameters))
 
     # ------------------------------------------------------------------ builders
     @classmethod
@@ -369,6 +377,47 @@ def _links_follow_aba_chain(model) -> bool:
     return bool(model.floating_base()) and bool(np.array_equal(H0, np.eye(4)))
 
 
+def _link_forces_with_constraints(model, data, n_steps, link_forces, joint_force_references):
+    """Inertial-fixed link forces of ONE step of a model with weld constraints: the caller's forces plus the constraint
+    wrenches (``api/ode.py:60-107``).  The wrenches depend on the state, so a fused multi-step launch cannot carry them."""
+    from jaxsim_b200.rbda import kinematic_constraints as _kc
+
+    from . import contact as _contact
+    from . import ode as _ode
+
+    if n_steps != 1:
+        raise NotImplementedError("kinematic constraints are re-solved at every step: use step() (step_n loops for you)")
+    nc = model.number_of_collidable_points()
+    soft = isinstance(model.contact_model, SoftContacts)
+    if nc > 0 and not soft:
+        raise NotImplementedError("kinematic constraints with RigidContacts / RelaxedRigidContacts collidable points: the "
+                                  "contact forces of those models are solved inside the step kernel")
+    dtype, dev = data._joint_positions.dtype, data._joint_positions.device
+    nL = model.number_of_links()
+    # The solve is ill-conditioned by construction: the regulariser (1e-3) sits next to Delassus eigenvalues of O(1/mass),
+    # and a planar loop leaves half of the 6 weld directions to the regulariser alone -- directions that still act on
+    # the base through the body/mixed mix of the reference's Jacobian.  Rounding of the right-hand side is amplified
+    # by ~1e3-1e4, so everything that feeds it (kinematics, contact forces, ABA, mass matrix) is evaluated in float64
+    # whatever the precision of the state; only the resulting link forces are rounded to the state's dtype.
+    d = _kc.float64_data(model, data)
+    lead = d._base_quaternion.shape[:-1]
+    if link_forces is None:
+        W_f = torch.zeros(lead + (nL, 6), dtype=torch.float64, device=dev)
+    else:
+        W_f = torch.as_tensor(link_forces, dtype=dtype, device=dev)
+        if W_f.shape[-2:] != (nL, 6) or W_f.dim() != data._base_quaternion.dim() + 1:
+            raise ValueError(W_f.shape, (nL, 6))
+        W_f = other_representation_to_inertial(W_f.to(torch.float64).reshape(lead + (nL, 6)), data.velocity_representation,
+                                               d.link_transforms, is_force=True)
+    tau = None if joint_force_references is None else torch.as_tensor(joint_force_references, dtype=torch.float64, device=dev)
+    tau_total = _ode.compute_resultant_torques(model, d, joint_force_references=None if tau is None else tau.reshape(lead + (-1,)))
+    W_f_terrain = 0
+    if nc > 0:
+        W_f_terrain, _ = _contact.soft_link_contact_forces(model, d)
+    W_f = W_f + _kc.constraint_link_forces(model, d, joint_torques=tau_total, link_forces_inertial=W_f + W_f_terrain)
+    return W_f.to(dtype).reshape(data._base_quaternion.shape[:-1] + (nL, 6))
+
+
 def _step_impl(model, data, n_steps, link_forces, joint_force_references, update_caches, out, use_input_caches=True,
                status_flags=None):
     s = data._joint_positions
@@ -411,6 +460,13 @@ def _step_impl(model, data, n_steps, link_forces, joint_force_references, update
                 raise ValueError(tau.shape, (B, n))
         tau = tau.contiguous()
 
+    forces_are_inertial = data.velocity_representation == VelRepr.Inertial
+    cmap = model.kin_dyn_parameters.constraints
+    if cmap is not None and len(cmap) > 0:
+        # api/ode.py:75-107: the weld-constraint wrenches, solved against external + contact forces, join the link forces
+        link_forces = _link_forces_with_constraints(model, data, n_steps, link_forces, joint_force_references)
+        forces_are_inertial = True
+
     fext, fext_stride, fext_repr = None, 0, _lib.REPR_INERTIAL
     if link_forces is not None:
         O_f = torch.as_tensor(link_forces, dtype=dtype, device=dev)
@@ -418,7 +474,7 @@ def _step_impl(model, data, n_steps, link_forces, joint_force_references, update
         O_f = O_f if per_step else _batched(O_f, 2)
         if O_f.shape[-3:] != (B, nL, 6) or (per_step and O_f.shape[0] != n_steps):
             raise ValueError(O_f.shape, (B, nL, 6))
-        if data.velocity_representation != VelRepr.Inertial:
+        if not forces_are_inertial:
             # api/model.py:2641-2646: expressed in data.velocity_representation, re-expressed with the link
             # transforms of every step.  The kernels do that themselves (b200sim_step_n_ex) wherever the link poses
             # are the ABA chain poses; otherwise (fixed base with an offset mount, SDF-posed base) a torch shim converts
@@ -559,6 +615,10 @@ def step(
     if model.integrator in (IntegratorType.RungeKutta4, IntegratorType.RungeKutta4Fast):
         from .integrators import step_rk4
 
+        cmap = model.kin_dyn_parameters.constraints
+        if cmap is not None and len(cmap) > 0:
+            raise NotImplementedError("kinematic constraints are wired into the SemiImplicitEuler step only")
+
         return step_rk4(model, data, link_forces=link_forces, joint_force_references=joint_force_references)
     return _step_impl(model, data, 1, link_forces, joint_force_references, update_caches, out, use_input_caches, status_flags)
 
@@ -583,6 +643,19 @@ def step_n(
         raise ValueError(n_steps)
     if model.integrator != IntegratorType.SemiImplicitEuler:
         raise NotImplementedError("step_n fuses SemiImplicitEuler steps only")
+    cmap = model.kin_dyn_parameters.constraints
+    if cmap is not None and len(cmap) > 0 and n_steps > 1:
+        # the constraint wrenches are a function of every intermediate state (api/ode.py:83-88): one launch per step
+        tau, lf = joint_force_references, link_forces
+        per_tau = tau is not None and torch.as_tensor(tau).dim() == 3
+        per_lf = lf is not None and torch.as_tensor(lf).dim() == 4
+        for k in range(int(n_steps)):
+            last = k == n_steps - 1
+            data = _step_impl(model, data, 1, lf[k] if per_lf else lf, tau[k] if per_tau else tau, True,
+                              out if last else None)
+        if not update_caches:
+            data._base_transform = data._joint_transforms = data._link_transforms = data._link_velocities = None
+        return data
     return _step_impl(model, data, int(n_steps), link_forces, joint_force_references, update_caches, out)
 
 

@@ -157,6 +157,28 @@ def cartpole_urdf() -> str:
     return b.urdf()
 
 
+def four_bar_urdf() -> str:
+    """Floating-base planar linkage opened at its coupler: a base bar, two cranks and the two halves of the coupler,
+    each half ending in a massless frame link.  Welding `tip_a_frame` to `tip_b_frame` closes the loop (same topology as the
+    reference's tests/assets/4_bar_opened.urdf, rbda/kinematic_constraints.py; dimensions and masses are this repo's own)."""
+    b = UrdfBuilder("four_bar")
+    L, H, W = 0.6, 0.35, 0.08
+    b.link("ground_bar", 1.2, box_inertia(1.2, (W, L, W)), collisions=[("box", (0, 0, 0), (0, 0, 0), (W, L, W))])
+    b.link("crank_a", 0.6, box_inertia(0.6, (W, W, H)), com=(0, 0, H / 2))
+    b.link("crank_b", 0.6, box_inertia(0.6, (W, W, H)), com=(0, 0, H / 2))
+    b.link("coupler_a", 0.4, box_inertia(0.4, (W, L / 2, W)), com=(0, L / 4, 0))
+    b.link("coupler_b", 0.4, box_inertia(0.4, (W, L / 2, W)), com=(0, -L / 4, 0))
+    b.massless_link("tip_a_frame")
+    b.massless_link("tip_b_frame")
+    b.joint("pivot_a", "revolute", "ground_bar", "crank_a", xyz=(0, -L / 2, 0), axis=(1, 0, 0), limit=(-1.5, 1.5), damping=0.02)
+    b.joint("pivot_b", "revolute", "ground_bar", "crank_b", xyz=(0, L / 2, 0), axis=(1, 0, 0), limit=(-1.5, 1.5), damping=0.02)
+    b.joint("elbow_a", "revolute", "crank_a", "coupler_a", xyz=(0, 0, H), axis=(1, 0, 0), limit=(-2.5, 2.5))
+    b.joint("elbow_b", "revolute", "crank_b", "coupler_b", xyz=(0, 0, H), axis=(1, 0, 0), limit=(-2.5, 2.5))
+    b.joint("tip_a_fix", "fixed", "coupler_a", "tip_a_frame", xyz=(0, L / 2, 0))
+    b.joint("tip_b_fix", "fixed", "coupler_b", "tip_b_frame", xyz=(0, -L / 2, 0), rpy=(0, 0, 0))
+    return b.urdf()
+
+
 # ---------------------------------------------------------------------- humanoids
 def _leg(b: UrdfBuilder, side: str, parent: str, sgn: float, foot_boxes: int = 1):
     p = side + "_"
@@ -279,6 +301,7 @@ MODELS = {
     "cartpole": cartpole_urdf,
     "icub_like": icub_like_urdf,
     "ergocub_like": ergocub_like_urdf,
+    "four_bar": four_bar_urdf,
 }
 
 

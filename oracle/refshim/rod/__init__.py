@@ -288,4 +288,33 @@ class Sdf:
             raise NotImplementedError("the rod stand-in reads URDF (<robot>) documents only")
         links = [_link_from_urdf(e) for e in root.findall("link") if e.get("name") != "world"]
         joints = [_joint_from_urdf(e) for e in root.findall("joint")]
-        return Sdf(model=Model(name=root.get("name"), link=links, joint=joints))
+        # sdformat turns a massless link that hangs on a FIXED joint into a frame attached to the parent link, with the
+        # joint's pose (what `model.frame_names()` lists in the reference, e.g. the `*_frame` links of
+        # tests/assets/4_bar_opened.urdf); frames of frames are re-attached to the first real link
+        frames = []
+        massless = {l.name for l in links if not (l.inertial.mass > 0)}
+        changed = True
+        while changed:
+            changed = False
+            for j in list(joints):
+                if j.type == "fixed" and j.child in massless and j.parent != "world" and not any(jj.parent == j.child for jj in joints):
+                    frames.append(Frame(name=j.child, attached_to=j.parent, pose=Pose(pose=list(j.pose.pose), relative_to=j.parent)))
+                    joints.remove(j)
+                    links = [l for l in links if l.name != j.child]
+                    changed = True
+        real = {l.name for l in links}
+        for f in frames:  # a frame attached to another frame: compose the poses down to a real link
+            while f.attached_to not in real:
+                parent = next(g for g in frames if g.name == f.attached_to)
+                H = parent.pose.transform() @ f.pose.transform()
+                f.attached_to = parent.attached_to
+                f.pose = _pose_from_transform(H, relative_to=parent.attached_to)
+        return Sdf(model=Model(name=root.get("name"), link=links, joint=joints, frame=frames))
+
+
+def _pose_from_transform(H, relative_to=None) -> Pose:
+    R = H[0:3, 0:3]
+    pitch = np.arcsin(-np.clip(R[2, 0], -1.0, 1.0))
+    roll = np.arctan2(R[2, 1], R[2, 2])
+    yaw = np.arctan2(R[1, 0], R[0, 0])
+    return Pose(pose=[float(H[0, 3]), float(H[1, 3]), float(H[2, 3]), float(roll), float(pitch), float(yaw)], relative_to=relative_to)

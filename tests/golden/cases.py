@@ -76,10 +76,31 @@ CASES = [
     dict(id="icub_soft_mixed_b32", model="icub_like", B=32, seed=40, in_contact="mixed", tau=True, m=True, round32=True),
     dict(id="ergocub_soft_flat_b32", model="ergocub_like", B=32, seed=41, in_contact="flat", tau=True, m=True, round32=True),
     dict(id="icub_rigid_flat_b16", model="icub_like", B=16, seed=42, contact="rigid", in_contact="flat", tau=True, round32=True),
+    # ---- weld constraints (rbda/kinematic_constraints.py): a floating closed linkage whose loop is
+    #      closed by one weld between two frames, like the reference's 4-bar test (tests/test_simulations.py:549-612).
+    #      constraints = [(frame_1, frame_2, K_P or None, K_D or None)]
+    #      The first two draw the joint angles over their whole range: the loop is wide open (gaps of ~0.5 m) and the
+    #      solve returns wrench pairs of 1e6-1e7 N that cancel to ~1e3 N on the mechanism (three of the six weld directions
+    #      of a planar loop are held by the 1e-3 regulariser alone).  No float32 link-force array can carry that
+    #      cancellation -- the reference in float32 could not either -- so these two are float64-only (fp32=False); the
+    #      `closed` cases scale the joint angles down to a nearly closed loop, the regime a weld runs in.
+    dict(id="four_bar_weld", model="four_bar", B=4, seed=45, tau=True, round32=True, fp32=False,
+         constraints=[("tip_a_frame", "tip_b_frame", None, None)]),
+    dict(id="four_bar_weld_gains_fext", model="four_bar", B=4, seed=46, tau=True, fext=True, velrepr="mixed", round32=True, fp32=False,
+         constraints=[("tip_a_frame", "tip_b_frame", 1e4, 50.0)]),
+    dict(id="four_bar_weld_closed", model="four_bar", B=8, seed=49, tau=True, round32=True, joint_scale=0.02,
+         constraints=[("tip_a_frame", "tip_b_frame", None, None)]),
+    dict(id="four_bar_weld_closed_contact_fext", model="four_bar", B=8, seed=50, tau=True, fext=True, velrepr="body", round32=True,
+         joint_scale=0.02, in_contact=True, m=True, constraints=[("tip_a_frame", "tip_b_frame", 1e4, None)]),
+    dict(id="four_bar_weld_rollout", model="four_bar", B=2, seed=47, rollout=6, round32=True,
+         constraints=[("tip_a_frame", "tip_b_frame", 1e4, None)]),
+    dict(id="four_bar_weld_contact", model="four_bar", B=4, seed=48, in_contact=True, m=True, tau=True, round32=True,
+         constraints=[("tip_a_frame", "tip_b_frame", None, None)]),
 ]
 
 DEFAULTS = dict(contact="soft", contact_params=None, actuation=None, integrator="semi_implicit_euler", in_contact=False,
-                tau=False, m=False, fext=False, velrepr="inertial", rbda=False, time_step=1e-3, rollout=1, round32=False)
+                tau=False, m=False, fext=False, velrepr="inertial", rbda=False, time_step=1e-3, rollout=1, round32=False, constraints=None, fp32=True,
+                joint_scale=1.0)
 
 
 def case(cid: str) -> dict:

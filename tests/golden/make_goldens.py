@@ -71,10 +71,15 @@ def draw_inputs(case: dict):
         tau=10.0 * rng.uniform(0, 1, size=(B, n)) if case["tau"] else np.zeros((B, n)),
         tangential_deformation=(1e-4 * rng.uniform(-1, 1, size=(B, nc, 3)) if case["m"] else np.zeros((B, nc, 3))),
     )
+    if case["joint_scale"] != 1.0:  # joint angles (and rates) drawn over their range, then scaled towards zero
+        inp["joint_positions"] = case["joint_scale"] * inp["joint_positions"]
+        inp["joint_velocities"] = case["joint_scale"] * inp["joint_velocities"]
     if case["round32"]:
         inp = {k: np.asarray(v, dtype=np.float32).astype(np.float64) for k, v in inp.items()}
     if case["fext"]:
         inp["link_forces"] = rng.uniform(-10, 10, size=(B, nL, 6))
+        if case["round32"]:
+            inp["link_forces"] = inp["link_forces"].astype(np.float32).astype(np.float64)
     if case["rbda"]:
         inp["joint_accelerations"] = rng.uniform(-5, 5, size=(B, n))
         inp["base_acceleration"] = rng.uniform(-5, 5, size=(B, 6))
@@ -108,6 +113,18 @@ def run_case(case: dict) -> dict:
     urdf_text, inp = draw_inputs(case)
     rm = refenv.reference_model(urdf_text, contact=case["contact"], contact_params=case["contact_params"],
                                 time_step=case["time_step"], integrator=case["integrator"], actuation=case["actuation"])
+    if case["constraints"]:  # attached like tests/test_simulations.py:429-440 does
+        import jax.numpy as jnp
+
+        cmap = js.kin_dyn_parameters.ConstraintMap()
+        for f1, f2, kp, kd in case["constraints"]:
+            cmap = cmap.add_constraint(
+                model=rm, frame_idx_1=js.frame.name_to_idx(model=rm, frame_name=f1),
+                frame_idx_2=js.frame.name_to_idx(model=rm, frame_name=f2),
+                constraint_type=js.kin_dyn_parameters.ConstraintType.Weld,
+                K_P=None if kp is None else jnp.array([kp]), K_D=None if kd is None else jnp.array([kd]))
+        with rm.editable(validate=False) as rm:
+            rm.kin_dyn_parameters.constraints = cmap
     vr = {"inertial": VelRepr.Inertial, "mixed": VelRepr.Mixed, "body": VelRepr.Body}[case["velrepr"]]
     B = case["B"]
     soft = case["contact"] == "soft"
@@ -136,6 +153,13 @@ def run_case(case: dict) -> dict:
         else:
             push("cp_position", np.zeros((0, 3)))
             push("cp_velocity", np.zeros((0, 3)))
+        if case["constraints"]:
+            from jaxsim.rbda.kinematic_constraints import compute_constraint_wrenches
+
+            # the wrench pairs of the input state with no other forces (the quantity the step adds to the link forces)
+            push("constraint_wrenches_free", compute_constraint_wrenches(model=rm, data=data))
+            fi = np.array([js.frame.name_to_idx(model=rm, frame_name=f) for c_ in case["constraints"] for f in c_[:2]])
+            push("constraint_frame_transforms", np.stack([js.frame.transform(model=rm, data=data, frame_index=int(i)) for i in fi]))
         new = js.model.step(model=rm, data=data, link_forces=lf, joint_force_references=tau)
         for _ in range(case["rollout"] - 1):  # the outputs below are those of the LAST step
             new = js.model.step(model=rm, data=new, link_forces=lf, joint_force_references=tau)

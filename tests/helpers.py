@@ -31,8 +31,23 @@ def build_model_for_case(case: dict):
     ap = ActuationParams(**case["actuation"]) if case["actuation"] else None
     integ = {"semi_implicit_euler": js.model.IntegratorType.SemiImplicitEuler, "rk4": js.model.IntegratorType.RungeKutta4,
              "rk4fast": js.model.IntegratorType.RungeKutta4Fast}[case["integrator"]]
-    return build_model(case["model"], time_step=case["time_step"], contact_model=cm, contact_params=cp,
-                       actuation_params=ap, integrator=integ)
+    model = build_model(case["model"], time_step=case["time_step"], contact_model=cm, contact_params=cp,
+                        actuation_params=ap, integrator=integ)
+    return with_constraints(model, case.get("constraints"))
+
+
+def with_constraints(model, spec):
+    """The model with the weld constraints ``[(frame_1, frame_2, K_P, K_D)]`` attached the way the reference's tests do
+    (``tests/test_simulations.py:429-440``)."""
+    if not spec:
+        return model
+    cmap = js.kin_dyn_parameters.ConstraintMap()
+    for f1, f2, kp, kd in spec:
+        cmap = cmap.add_constraint(model, js.frame.name_to_idx(model, frame_name=f1), js.frame.name_to_idx(model, frame_name=f2),
+                                   js.kin_dyn_parameters.ConstraintType.Weld, K_P=kp, K_D=kd)
+    with model.editable(validate=False) as model:
+        model.kin_dyn_parameters.constraints = cmap
+    return model
 
 
 def oracle_model(model) -> O.OracleModel:

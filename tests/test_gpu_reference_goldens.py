@@ -63,6 +63,8 @@ def test_step_matches_reference(cid, dtype, cuda_device):
 
     z, _ = _load(cid)
     case = C.case(cid)
+    if dtype == "float32" and not case["fp32"]:
+        pytest.skip("float64-only fixture (tests/golden/cases.py says why)")
     model = H.build_model_for_case(case)
     td = _dtype(dtype)
     t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=td, device=cuda_device)  # noqa: E731
@@ -73,7 +75,10 @@ def test_step_matches_reference(cid, dtype, cuda_device):
                             joint_force_references=t(z["in_tau"]) if case["tau"] else None)
     assert out.velocity_representation == data.velocity_representation
     soft = case["contact"] == "soft"
-    floors = _vel_floors(z) if (case["contact"] in ("rigid", "relaxed") or case["rollout"] > 1) else None
+    # weld constraints: the solve returns wrench pairs of 1e4-1e5 N that cancel to a few N on the mechanism (see
+    # tests/golden/cases.py), so the velocity error is set by eps * |wrench| and is measured against the velocity scale of
+    # the whole state, not of the (scaled-down) joint rates alone
+    floors = _vel_floors(z) if (case["contact"] in ("rigid", "relaxed") or case["rollout"] > 1 or case["constraints"]) else None
     # a rollout accumulates the rounding of its steps (contacts amplify it): 5x the one-step tolerance
     rtol = H.RTOL[dtype] * (5 if case["rollout"] > 1 else 1)
     H.compare_data(out, _Ref(z, soft), rtol, f"golden {cid} {dtype}", floors=floors)

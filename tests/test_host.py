@@ -192,3 +192,36 @@ def test_contact_params_must_match_the_contact_model():
     with pytest.raises(TypeError):
         js.model.JaxSimModel.build_from_model_description(
             models.urdf("icub_like"), contact_model=RigidContacts.build(), contact_params=SoftContactsParams.build())
+
+
+def test_constraint_map_and_frames():
+    """ConstraintMap / js.frame host logic (api/kin_dyn_parameters.py:1258-1350, api/frame.py:21-109)."""
+    import math
+
+    import jaxsim_b200.api as js
+    from jaxsim_b200 import models
+
+    model = js.model.JaxSimModel.build_from_model_description(models.urdf("four_bar"))
+    nL = model.number_of_links()
+    assert model.kin_dyn_parameters.frame_parameters.name == ("tip_a_frame", "tip_b_frame")
+    ia = js.frame.name_to_idx(model, frame_name="tip_a_frame")
+    ib = js.frame.name_to_idx(model, frame_name="tip_b_frame")
+    assert (ia, ib) == (nL, nL + 1)
+    assert js.frame.idx_to_name(model, frame_index=ib) == "tip_b_frame"
+    assert model.link_names()[js.frame.idx_of_parent_link(model, frame_index=ia)] == "coupler_a"
+    with pytest.raises(ValueError):
+        js.frame.name_to_idx(model, frame_name="nope")
+    with pytest.raises(ValueError):
+        js.frame.idx_of_parent_link(model, frame_index=nL - 1)  # a link index is not a frame index
+    empty = js.kin_dyn_parameters.ConstraintMap()
+    cmap = empty.add_constraint(model, ia, ib, js.kin_dyn_parameters.ConstraintType.Weld)
+    assert len(empty) == 0 and len(cmap) == 1  # immutable: add_constraint returns a new map
+    assert cmap.K_P == (1000.0,) and cmap.K_D == (2 * math.sqrt(1000.0),)
+    assert model.link_names()[cmap.parent_link_idxs_2[0]] == "coupler_b"
+    cmap2 = cmap.add_constraint(model, ib, ia, js.kin_dyn_parameters.ConstraintType.Weld, K_P=1e4, K_D=3.0)
+    assert cmap2.K_P == (1000.0, 1e4) and cmap2.K_D[1] == 3.0 and cmap2.frame_idxs_1 == (ia, ib)
+    with pytest.raises(NotImplementedError):
+        cmap.add_constraint(model, ia, ib, 1)
+    with model.editable(validate=False) as edited:
+        edited.kin_dyn_parameters.constraints = cmap
+    assert model.kin_dyn_parameters.constraints is None and len(edited.kin_dyn_parameters.constraints) == 1

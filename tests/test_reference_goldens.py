@@ -15,6 +15,7 @@ import numpy as np
 import pytest
 
 from oracle import jaxsim_oracle as O
+from oracle import constraints_oracle as KC
 from oracle import rigid_oracle as R
 from tests.golden import cases as C
 
@@ -110,7 +111,9 @@ def test_oracle_step_matches_reference(cid):
     tau = z["in_tau"] if case["tau"] else None
     out = od
     for _ in range(case["rollout"]):
-        if case["contact"] in ("rigid", "relaxed"):
+        if case["constraints"]:
+            out, tol = KC.step(om, out, link_forces_inertial=W_f, joint_force_references=tau), 1e-9
+        elif case["contact"] in ("rigid", "relaxed"):
             out, tol = R.step(om, out, link_forces_inertial=W_f, joint_force_references=tau), 1e-6
         elif case["integrator"] == "rk4fast":
             out, tol = O.step_rk4fast(om, out, link_forces_inertial=W_f, joint_force_references=tau), 1e-9
@@ -233,3 +236,22 @@ def test_urdf_front_end_matches_reference_parser(name):
         for f in ("friction_static", "friction_viscous", "position_limits_min", "position_limits_max", "position_limit_spring",
                   "position_limit_damper"):
             np.testing.assert_allclose(getattr(kd.joint_parameters, f), np.asarray(getattr(rk.joint_parameters, f)), rtol=1e-12, atol=0, err_msg=f)
+
+
+@pytest.mark.parametrize("cid", [c["id"] for c in C.all_cases() if c["constraints"]])
+def test_oracle_constraint_wrenches_match_reference(cid):
+    """`compute_constraint_wrenches` (rbda/kinematic_constraints.py:172-345) and `js.frame.transform` of the constrained
+    frames, as the reference evaluated them on the input state with no other forces."""
+    z, _ = _load(cid)
+    case = C.case(cid)
+    _, om, _ = _models(case)
+    od = _oracle_data(om, z)
+    B, nL, n = case["B"], om.number_of_links(), om.dofs()
+    for b in range(B):
+        W = KC.compute_constraint_wrenches(om, od, b, np.zeros((nL, 6)), np.zeros(n))
+        assert _rel(W, z["constraint_wrenches_free"][b]) <= 1e-9
+        T = KC.constraint_transforms(om, R._Env(od, b))
+        assert _rel(T.reshape(-1, 4, 4), z["constraint_frame_transforms"][b]) <= 1e-12
+    # equal and opposite forces on the two frames (the torques differ by the lever arm between the frames)
+    W = z["constraint_wrenches_free"]
+    np.testing.assert_allclose(W[:, :, 0, 0:3], -W[:, :, 1, 0:3], rtol=1e-12, atol=1e-12)
