@@ -157,12 +157,15 @@ def cartpole_urdf() -> str:
     return b.urdf()
 
 
-def four_bar_urdf() -> str:
+def four_bar_urdf(fixed_base: bool = False) -> str:
     """Floating-base planar linkage opened at its coupler: a base bar, two cranks and the two halves of the coupler,
     each half ending in a massless frame link.  Welding `tip_a_frame` to `tip_b_frame` closes the loop (same topology as the
     reference's tests/assets/4_bar_opened.urdf, rbda/kinematic_constraints.py; dimensions and masses are this repo's own)."""
-    b = UrdfBuilder("four_bar")
+    b = UrdfBuilder("four_bar_fixed" if fixed_base else "four_bar")
     L, H, W = 0.6, 0.35, 0.08
+    if fixed_base:  # the ground bar bolted to the world, like the reference's fixed-base constraint tests
+        b.massless_link("world")
+        b.joint("world_to_ground_bar", "fixed", "world", "ground_bar", xyz=(0, 0, 0.5))
     b.link("ground_bar", 1.2, box_inertia(1.2, (W, L, W)), collisions=[("box", (0, 0, 0), (0, 0, 0), (W, L, W))])
     b.link("crank_a", 0.6, box_inertia(0.6, (W, W, H)), com=(0, 0, H / 2))
     b.link("crank_b", 0.6, box_inertia(0.6, (W, W, H)), com=(0, 0, H / 2))
@@ -302,6 +305,7 @@ MODELS = {
     "icub_like": icub_like_urdf,
     "ergocub_like": ergocub_like_urdf,
     "four_bar": four_bar_urdf,
+    "four_bar_fixed": lambda: four_bar_urdf(fixed_base=True),
 }
 
 

@@ -89,7 +89,8 @@ def _link_jacobians_body(model, data, links: list[int]) -> torch.Tensor:
     W_H_L = data.link_transforms
     dtype, dev = W_H_L.dtype, W_H_L.device
     nL, n = kd.number_of_links(), kd.number_of_joints()
-    B_H_L = torch.linalg.inv(data.base_transform)[..., None, :, :] @ W_H_L
+    # poses relative to the base LINK (rbda/jacobian.py:166-170 starts the chain with the identity at link 0)
+    B_H_L = torch.linalg.inv(W_H_L[..., 0:1, :, :]) @ W_H_L
     B_X_L = adjoint_from_transform(B_H_L)  # (B, nL, 6, 6)
     S = torch.as_tensor(np.asarray(kd.motion_subspaces), dtype=dtype, device=dev)  # (nL, 6)
     cols = _matvec(B_X_L[..., 1:, :, :], S[1:])  # (B, n, 6)
@@ -130,8 +131,6 @@ def compute_constraint_wrenches(model, data, *, joint_force_references: torch.Te
     q = data._base_quaternion
     if nk == 0:
         return torch.zeros(q.shape[:-1] + (0, 2, 6), dtype=q.dtype, device=q.device)
-    if not _model._links_follow_aba_chain(model) and model.floating_base():
-        raise NotImplementedError("kinematic constraints on a model whose base link pose is offset from the chain root")
     dtype, dev = q.dtype, q.device
     if dtype != torch.float64:
         # ill-conditioned by construction (see api/model.py:_link_forces_with_constraints): solved in float64

@@ -92,6 +92,8 @@ CASES = [
          constraints=[("tip_a_frame", "tip_b_frame", None, None)]),
     dict(id="four_bar_weld_closed_contact_fext", model="four_bar", B=8, seed=50, tau=True, fext=True, velrepr="body", round32=True,
          joint_scale=0.02, in_contact=True, m=True, constraints=[("tip_a_frame", "tip_b_frame", 1e4, None)]),
+    dict(id="four_bar_fixed_weld", model="four_bar_fixed", B=4, seed=51, tau=True, round32=True, joint_scale=0.02,
+         constraints=[("tip_a_frame", "tip_b_frame", None, None)]),
     dict(id="four_bar_weld_rollout", model="four_bar", B=2, seed=47, rollout=6, round32=True,
          constraints=[("tip_a_frame", "tip_b_frame", 1e4, None)]),
     dict(id="four_bar_weld_contact", model="four_bar", B=4, seed=48, in_contact=True, m=True, tau=True, round32=True,

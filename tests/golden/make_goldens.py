@@ -100,6 +100,9 @@ def kin_dyn_arrays(rm) -> dict:
         kd_contact_body=np.asarray(cp.body), kd_contact_point=np.asarray(cp.point), kd_contact_enabled=np.asarray(cp.enabled),
         kd_floating_base=np.asarray(bool(rm.floating_base())),
     )
+    fp = kd.frame_parameters
+    if len(fp.name) > 0:  # api/kin_dyn_parameters.py:843-917
+        out.update(kd_frame_names=np.array(fp.name), kd_frame_body=np.asarray(fp.body), kd_frame_transform=np.asarray(fp.transform))
     if jp is not None:
         out.update(kd_friction_static=np.asarray(jp.friction_static), kd_friction_viscous=np.asarray(jp.friction_viscous),
                    kd_position_limits_min=np.asarray(jp.position_limits_min), kd_position_limits_max=np.asarray(jp.position_limits_max),

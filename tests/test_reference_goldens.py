@@ -255,3 +255,16 @@ def test_oracle_constraint_wrenches_match_reference(cid):
     # equal and opposite forces on the two frames (the torques differ by the lever arm between the frames)
     W = z["constraint_wrenches_free"]
     np.testing.assert_allclose(W[:, :, 0, 0:3], -W[:, :, 1, 0:3], rtol=1e-12, atol=1e-12)
+
+
+def test_urdf_loader_frames_match_reference():
+    """Massless links on fixed joints become frames of their parent link (parsers/rod/parser.py:90-124,
+    api/kin_dyn_parameters.py:843-917): names, parent link and L_H_F as the reference's front end produced them."""
+    z, _ = _load("four_bar_weld")
+    pm, _, _ = _models(C.case("four_bar_weld"))
+    fp = pm.kin_dyn_parameters.frame_parameters
+    assert tuple(fp.name) == tuple(str(s) for s in z["kd_frame_names"])
+    assert tuple(int(b) for b in fp.body) == tuple(int(b) for b in z["kd_frame_body"])
+    np.testing.assert_allclose(np.asarray(fp.transform), z["kd_frame_transform"], rtol=1e-12, atol=1e-14)
+    c = pm.kin_dyn_parameters.constraints
+    assert (c.frame_idxs_1, c.frame_idxs_2) == ((pm.number_of_links(),), (pm.number_of_links() + 1,))
