@@ -266,6 +266,25 @@ int b200sim_dynamics(const B200SimModel *model, int dtype, int64_t B,
                      const void *f_ext, void *pd, void *qd, void *W_vd, void *sdd, void *md,
                      void *stream);
 
+/* One RungeKutta4 step == vmapped jaxsim.api.model.step with IntegratorType.RungeKutta4
+ * (api/model.py:2601-2681 -> api/integrators.py:91-156): the actuation model on the input state
+ * (api/actuation_model.py:7-126; tau_ref (B,n) or NULL), four evaluations of ode.system_dynamics
+ * (api/ode.py:174-225; contact state integrated with the rest of the state) on x0, x0 + dt/2 k1,
+ * x0 + dt/2 k2, x0 + dt k3, the (1,2,2,1)/6 combination, then data.replace (api/data.py:441-447:
+ * quaternion normalised, caches of the new state).  Five launches of the dynamics / FK kernel and
+ * five elementwise ones, all on `stream`, no host round trip; the stage buffers live in a per-
+ * (model, stream) scratch block, so the first call on a stream (or with a larger batch) must not be
+ * inside a stream capture.  f_ext (B,nL,6) inertial-fixed or NULL, held over the stages like the
+ * reference does.  Outputs as b200sim_step (the four cache pointers may be NULL); out may alias
+ * in.  RigidContacts / RelaxedRigidContacts with collidable points: B200SIM_E_UNSUPPORTED. */
+int b200sim_step_rk4(B200SimModel *model, int dtype, int64_t B,
+                     const void *s, const void *sd, const void *q_wxyz, const void *v_lin,
+                     const void *omega, const void *p, const void *m_tan, const void *tau_ref,
+                     const void *f_ext,
+                     void *s_o, void *sd_o, void *q_o, void *v_lin_o, void *omega_o, void *p_o,
+                     void *m_o, void *W_H_B, void *joint_X, void *W_H_L, void *W_v_WL,
+                     void *stream);
+
 /* Inverse dynamics == vmapped rbda.rnea (rbda/rnea.py:12-238).  in: state as above,
  * W_vd_WB (B,6) inertial-fixed base acceleration or NULL (zeros), sdd (B,n) or NULL,
  * f_ext (B,nL,6) inertial-fixed link forces or NULL.  out: W_f_B (B,6) the inertial-fixed

@@ -97,6 +97,7 @@ EXPORTED_SYMBOLS = (
     "b200sim_crba",
     "b200sim_step_jvp",
     "b200sim_dynamics",
+    "b200sim_step_rk4",
 )
 
 _lib = None
@@ -153,6 +154,8 @@ def load() -> C.CDLL:
     lib.b200sim_step_jvp.restype = C.c_int
     lib.b200sim_dynamics.argtypes = [vp, C.c_int, C.c_int64] + [vp] * 15
     lib.b200sim_dynamics.restype = C.c_int
+    lib.b200sim_step_rk4.argtypes = [vp, C.c_int, C.c_int64] + [vp] * 21
+    lib.b200sim_step_rk4.restype = C.c_int
     _lib = lib
     return lib
 

@@ -1,14 +1,18 @@
 """Integrators beyond the fused semi-implicit Euler step.
 
-``rk4_integration`` restates ``src/jaxsim/api/integrators.py:91-156``: four evaluations of
-``system_dynamics`` (one kernel launch each, ``b200sim_dynamics``) combined with elementwise
-torch ops, then the cache refresh of ``data.replace`` (``b200sim_fk``).  The semi-implicit
-Euler scheme (``:14-88``) lives entirely inside ``b200sim_step``.
+``rk4_integration`` (``src/jaxsim/api/integrators.py:91-156``) is one call of ``b200sim_step_rk4``: the four
+``system_dynamics`` evaluations, the stage updates and the cache refresh of ``data.replace`` run as launches on the
+current stream with the stage state in device scratch.  ``rk4fast_integration`` (``:159-263``) freezes the contact forces
+and glues four ``b200sim_aba`` launches with elementwise torch ops.  The semi-implicit Euler scheme (``:14-88``) lives
+entirely inside ``b200sim_step``.
 """
 
 from __future__ import annotations
 
 import torch
+
+from jaxsim_b200 import _lib
+from jaxsim_b200.rbda.contacts import SoftContacts
 
 from . import ode
 from .common import VelRepr, other_representation_to_inertial
@@ -24,36 +28,46 @@ def _tree(f, *trees):
     return out
 
 
-def rk4_integration(model, data, link_forces_inertial, joint_torques):
-    """``rk4_integration`` (``api/integrators.py:91-156``) for batched data."""
-    dt = model.time_step
-    q = data._base_quaternion
-    nrm = torch.linalg.norm(q, dim=-1, keepdim=True)
-    q = q / torch.where(nrm == 0, torch.ones_like(nrm), nrm)
+def rk4_integration(model, data, link_forces_inertial, joint_force_references):
+    """``step`` with ``IntegratorType.RungeKutta4`` (``api/integrators.py:91-156``) for batched data: one call of
+    ``b200sim_step_rk4`` -- the actuation model, the four ``system_dynamics`` evaluations, the stage updates and the
+    ``data.replace`` of the result (normalised quaternion, caches) run as ten launches on the current stream with the
+    stage state in device scratch; nothing returns to the host in between."""
+    from .model import _alloc_outputs, _dtype_code, _ptr, _stream_ptr
 
-    def f(x):
-        # data.replace(model, **x) normalises the quaternion before anything is computed
-        # from it (api/data.py:441-447); the kernel does the same on entry
-        return ode.system_dynamics(model, x, link_forces_inertial=link_forces_inertial, joint_torques=joint_torques)
+    q = data._base_quaternion.contiguous()
+    dev, dtype = q.device, q.dtype
+    dm = model.device_model(dev)
+    B = q.shape[0]
+    nL, n, nc = model.number_of_links(), model.dofs(), model.number_of_collidable_points()
+    soft = isinstance(model.contact_model, SoftContacts)
+    c = lambda t: None if t is None else torch.as_tensor(t, dtype=dtype, device=dev).contiguous()  # noqa: E731
+    m = c(data.contact_state.get("tangential_deformation")) if (soft and data.contact_state) else None
+    tau, fext = c(joint_force_references), c(link_forces_inertial)
+    if tau is not None and tau.shape != (B, n):
+        raise ValueError(tau.shape, (B, n))
+    if fext is not None and fext.shape != (B, nL, 6):
+        raise ValueError(fext.shape, (B, nL, 6))
+    o = _alloc_outputs(model, B, dtype, dev, True, soft)
+    g = o.get
+    with torch.cuda.device(dev):
+        rc = _lib.load().b200sim_step_rk4(
+            dm.handle, _dtype_code(dtype), B, _ptr(c(data._joint_positions)), _ptr(c(data._joint_velocities)), _ptr(q),
+            _ptr(c(data._base_linear_velocity)), _ptr(c(data._base_angular_velocity)), _ptr(c(data._base_position)), _ptr(m),
+            _ptr(tau), _ptr(fext), _ptr(o["s"]), _ptr(o["sd"]), _ptr(o["q"]), _ptr(o["vl"]), _ptr(o["om"]), _ptr(o["p"]),
+            _ptr(g("m")), _ptr(g("W_H_B")), _ptr(g("iXl")), _ptr(g("W_H_L")), _ptr(g("W_v")), _stream_ptr(dev),
+        )
+    _lib.check(rc, "b200sim_step_rk4")
+    contact_state = dict(data.contact_state) if data.contact_state else {}
+    if soft:
+        contact_state["tangential_deformation"] = o["m"]
+    from .data import JaxSimModelData
 
-    x0 = dict(
-        base_position=data._base_position, base_quaternion=q, joint_positions=data._joint_positions,
-        base_linear_velocity=data._base_linear_velocity, base_angular_velocity=data._base_angular_velocity,
-        joint_velocities=data._joint_velocities, contact_state=dict(data.contact_state),
-    )
-    mid = lambda x, d: x + (0.5 * dt) * d  # noqa: E731
-    fin = lambda x, d: x + dt * d  # noqa: E731
-    k1 = f(x0)
-    k2 = f(_tree(mid, x0, k1))
-    k3 = f(_tree(mid, x0, k2))
-    k4 = f(_tree(fin, x0, k3))
-    dxdt = _tree(lambda a, b, c, d: (a + 2 * b + 2 * c + d) / 6, k1, k2, k3, k4)
-    xf = _tree(fin, x0, dxdt)
-    return data.replace(
-        model, joint_positions=xf["joint_positions"], joint_velocities=xf["joint_velocities"],
-        base_quaternion=xf["base_quaternion"], base_position=xf["base_position"],
-        contact_state=xf["contact_state"],
-        _inertial_base_velocity=(xf["base_linear_velocity"], xf["base_angular_velocity"]),
+    return JaxSimModelData(
+        velocity_representation=data.velocity_representation,
+        _joint_positions=o["s"], _joint_velocities=o["sd"], _base_quaternion=o["q"], _base_linear_velocity=o["vl"],
+        _base_angular_velocity=o["om"], _base_position=o["p"], _base_transform=g("W_H_B"), _joint_transforms=g("iXl"),
+        _link_transforms=g("W_H_L"), _link_velocities=g("W_v"), contact_state=contact_state,
     )
 
 
@@ -138,9 +152,9 @@ def step_rk4(model, data, *, link_forces=None, joint_force_references=None):
             torch.as_tensor(link_forces, dtype=data._base_quaternion.dtype, device=data._base_quaternion.device),
             data.velocity_representation, data.link_transforms, is_force=True,
         )
-    tau = ode.compute_resultant_torques(model, data, joint_force_references=joint_force_references)
     from .model import IntegratorType
 
     if model.integrator == IntegratorType.RungeKutta4Fast:
+        tau = ode.compute_resultant_torques(model, data, joint_force_references=joint_force_references)
         return rk4fast_integration(model, data, fext, tau)
-    return rk4_integration(model, data, fext, tau)
+    return rk4_integration(model, data, fext, joint_force_references)

@@ -54,6 +54,9 @@ struct B200SimModel {
   struct RigidScratch { int* buf = nullptr; long long cap = 0; };
   std::unordered_map<void*, RigidScratch> rigid_scratch;
   std::mutex rigid_mutex;
+  // stage buffers of b200sim_step_rk4, one per (model, stream) like the work lists above
+  struct StageScratch { void* buf = nullptr; size_t bytes = 0; };
+  std::unordered_map<void*, StageScratch> rk4_scratch;
   // device blobs
   float *cst_f = nullptr, *csuc_f = nullptr, *pt_f = nullptr;
   double *cst_d = nullptr, *csuc_d = nullptr, *pt_d = nullptr;
@@ -619,6 +622,182 @@ int aba_t(const B200SimModel* m, int dtype, int64_t B, const void* s, const void
   return launch(m, P, dtype, stream);
 }
 
+// ---- RungeKutta4 (api/integrators.py:91-156) --------------------------------------------------------------------
+// Four evaluations of the system dynamics (the MODE_DYN launch of the step kernel: contacts -> ABA -> position dynamics)
+// joined by one small elementwise launch each, all on the caller's stream with no host round trip; the stage state, the
+// running sum of the slopes and the resultant torques live in a per-(model, stream) scratch block.
+template <typename T>
+struct Rk4Bufs {
+  // stage state (what the dynamics launch reads)
+  T *s, *sd, *q, *vl, *om, *p, *m;
+  // slopes written by the dynamics launch (the slope of s is the stage's sd)
+  T *pd, *qd, *vd, *sdd, *md;
+  // running sums of the slopes, the normalised input quaternion and the resultant torques
+  T *ks, *ksd, *kq, *kvl, *kom, *kp, *km, *q0, *tau;
+};
+
+template <typename T>
+struct Rk4Io {
+  const T *s, *sd, *q, *vl, *om, *p, *m, *tau_ref;
+  T *s_o, *sd_o, *q_o, *vl_o, *om_o, *p_o, *m_o;
+};
+
+// stage -1: x_stage = x0 (quaternion normalised, integrators.py:105-110), sums = 0, tau = actuation model
+// (api/actuation_model.py:7-126, evaluated ONCE on the input state: api/model.py:2658).
+// stage 0..2: sums += w k; x_stage = x0 + c k.   stage 3: out = x0 + dt/6 (sums + k).
+template <typename T>
+__global__ void rk4_stage_kernel(long long B, int n, int nc, int stage, T dt, Rk4Io<T> io, Rk4Bufs<T> b, const T* __restrict__ cst,
+                                 int enable_friction, T tau_max, T w_th, T w_max) {
+  const int E = n + 13 + 3 * nc;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= B * E) return;
+  const long long e = tid / E;
+  const int k = (int)(tid - e * E);
+  const T w = (stage == 0) ? T(1) : T(2);
+  const T c = (stage == 2) ? dt : T(0.5) * dt;
+  // one (x0, slope, sum, stage, out) tuple per element; joints carry two (s and sd) so that the slope of s -- the
+  // stage's own sd -- is read before it is overwritten
+  auto advance = [&](T x0, T slope, T* sum, T* xs, T* out) {
+    if (stage < 0) { *sum = T(0); *xs = x0; return; }
+    if (stage < 3) { *sum += w * slope; *xs = x0 + c * slope; return; }
+    *out = x0 + dt * ((*sum + slope) / T(6));
+  };
+  if (k < n) {
+    const long long j = e * n + k;
+    const T s0 = io.s[j], sd0 = io.sd[j];
+    if (stage < 0) {
+      const T* cl = cst + (size_t)(k + 1) * CREC;
+      const T lower = min_t(s0 - cl[C_SMIN], T(0));
+      const T upper = max_t(s0 - cl[C_SMAX], T(0));
+      T tlim = -cl[C_KS] * (lower + upper);
+      tlim = tlim - tlim * cl[C_KD] * sd0;
+      T tfr = T(0);
+      if (enable_friction) {
+        const T sg = (sd0 > T(0)) ? T(1) : ((sd0 < T(0)) ? T(-1) : T(0));
+        tfr = -(cl[C_KC] * sg + cl[C_KV] * sd0);
+      }
+      const T tt = (io.tau_ref ? io.tau_ref[j] : T(0)) + tfr + tlim;
+      const T av = abs_t(sd0);
+      T lim;
+      if (av <= w_th) lim = tau_max;
+      else if (av <= w_max) lim = tau_max * (T(1) - (av - w_th) / (w_max - w_th));
+      else lim = T(0);
+      b.tau[j] = min_t(max_t(tt, -lim), lim);
+    }
+    const T sd_stage = (stage < 0) ? T(0) : b.sd[j];
+    const T sdd = (stage < 0) ? T(0) : b.sdd[j];
+    advance(s0, sd_stage, b.ks + j, b.s + j, io.s_o + j);
+    advance(sd0, sdd, b.ksd + j, b.sd + j, io.sd_o + j);
+    return;
+  }
+  int r = k - n;
+  if (r < 4) {
+    const long long j = e * 4 + r;
+    T q0;
+    if (stage < 0) {
+      const T* q = io.q + e * 4;
+      const T nn = sqrt_t(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+      q0 = q[r] / ((nn == T(0)) ? T(1) : nn);
+      b.q0[j] = q0;
+    } else {
+      q0 = b.q0[j];
+    }
+    advance(q0, stage < 0 ? T(0) : b.qd[j], b.kq + j, b.q + j, io.q_o + j);
+    return;
+  }
+  r -= 4;
+  if (r < 9) {
+    const int a = r / 3, x = r - 3 * a;
+    const long long j = e * 3 + x;
+    if (a == 0) advance(io.p[j], stage < 0 ? T(0) : b.pd[j], b.kp + j, b.p + j, io.p_o + j);
+    else if (a == 1) advance(io.vl[j], stage < 0 ? T(0) : b.vd[e * 6 + x], b.kvl + j, b.vl + j, io.vl_o + j);
+    else advance(io.om[j], stage < 0 ? T(0) : b.vd[e * 6 + 3 + x], b.kom + j, b.om + j, io.om_o + j);
+    return;
+  }
+  r -= 9;
+  {
+    const long long j = e * 3 * nc + r;
+    advance(io.m ? io.m[j] : T(0), stage < 0 ? T(0) : b.md[j], b.km + j, b.m + j, io.m_o ? io.m_o + j : b.m + j);
+  }
+}
+
+template <typename T>
+int dyn_t(const B200SimModel* m, int dtype, int64_t B, const T* s, const T* sd, const T* q, const T* vlin, const T* omega,
+          const T* p, const T* mt, const T* tau, const T* fext, T* pd, T* qd, T* W_vd, T* sdd, T* md, void* stream) {
+  Params<T> P;
+  std::memset(&P, 0, sizeof(P));
+  fill_model_params(m, P);
+  P.B = B;
+  P.s = s; P.sd = sd; P.q = q; P.vlin = vlin; P.omega = omega; P.p = p; P.m = mt; P.tau = tau; P.fext = fext;
+  P.p_o = pd; P.q_o = qd; P.avd = W_vd; P.sdd_o = sdd; P.m_o = md;
+  P.nsteps = 1; P.mode = MODE_DYN;
+  return launch(m, P, dtype, stream);
+}
+
+template <typename T>
+int step_rk4_t(B200SimModel* m, int dtype, int64_t B, Rk4Io<T> io, const T* fext, T* W_H_B, T* iXl, T* W_H_L, T* W_v, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = m->n, nc = (m->contact_model == 1) ? m->nc : 0;  // the contact state exists for SoftContacts only
+  const size_t per_env = (size_t)(2 * n + 13 + 3 * nc)      // stage state
+                         + (size_t)(3 + 4 + 6 + n + 3 * nc)  // slopes
+                         + (size_t)(2 * n + 13 + 3 * nc)     // sums
+                         + 4 + (size_t)n;                    // q0, tau
+  const size_t bytes = (per_env * (size_t)B + 64) * sizeof(T) + 21 * 16;
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev != m->device) CK(cudaSetDevice(m->device));
+  void* base = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(m->rigid_mutex);
+    B200SimModel::StageScratch& sc = m->rk4_scratch[(void*)st];
+    if (!sc.buf || sc.bytes < bytes) {
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone)
+        return B200SIM_E_UNSUPPORTED;  // cannot allocate inside a capture: run one eager step first
+      if (sc.buf) {
+        CK(cudaStreamSynchronize(st));
+        CK(cudaFree(sc.buf));
+      }
+      sc.buf = nullptr;
+      sc.bytes = 0;
+      CK(cudaMalloc(&sc.buf, bytes));
+      sc.bytes = bytes;
+    }
+    base = sc.buf;
+  }
+  char* cur = (char*)base;
+  auto take = [&](size_t count) {
+    T* ptr = (T*)cur;
+    cur += ((count * sizeof(T) + 15) / 16) * 16;  // every leaf 16-byte aligned
+    return ptr;
+  };
+  Rk4Bufs<T> b;
+  const size_t Bn = (size_t)B * n, Bm = (size_t)B * 3 * nc, B3 = (size_t)B * 3, B4 = (size_t)B * 4;
+  b.s = take(Bn); b.sd = take(Bn); b.q = take(B4); b.vl = take(B3); b.om = take(B3); b.p = take(B3); b.m = take(Bm);
+  b.pd = take(B3); b.qd = take(B4); b.vd = take((size_t)B * 6); b.sdd = take(Bn); b.md = take(Bm);
+  b.ks = take(Bn); b.ksd = take(Bn); b.kq = take(B4); b.kvl = take(B3); b.kom = take(B3); b.kp = take(B3); b.km = take(Bm);
+  b.q0 = take(B4); b.tau = take(Bn);
+  const int E = n + 13 + 3 * nc;
+  const long long total = (long long)B * E;
+  const int threads = 256;
+  const unsigned grid = (unsigned)((total + threads - 1) / threads);
+  const T dt = (T)m->dt;
+  int rc = 0;
+  for (int stage = -1; stage <= 3 && !rc; ++stage) {
+    if (stage >= 0)
+      rc = dyn_t<T>(m, dtype, B, b.s, b.sd, b.q, b.vl, b.om, b.p, nc ? b.m : nullptr, b.tau, fext, b.pd, b.qd, b.vd, b.sdd,
+                    nc ? b.md : nullptr, stream);
+    if (rc) break;
+    rk4_stage_kernel<T><<<grid, threads, 0, st>>>(B, n, nc, stage, dt, io, b, Blob<T>::cst(m), m->enable_friction, (T)m->tau_max,
+                                                   (T)m->w_th, (T)m->w_max);
+    rc = (int)cudaGetLastError();
+  }
+  // data.replace (api/data.py:441-447): quaternion normalised, caches of the new state
+  if (!rc) rc = fk_t<T>(m, dtype, B, io.s_o, io.sd_o, io.q_o, io.vl_o, io.om_o, io.p_o, io.q_o, W_H_B, iXl, W_H_L, W_v, stream);
+  if (dev != m->device) cudaSetDevice(dev);
+  return rc;
+}
+
 }  // namespace
 
 // ---- forward-mode AD (Dual<double>) -------------------------------------------------
@@ -971,6 +1150,7 @@ void b200sim_model_destroy(B200SimModel* m) {
   cudaFree(m->cst_f); cudaFree(m->cst_d); cudaFree(m->csuc_f); cudaFree(m->csuc_d);
   cudaFree(m->pt_f); cudaFree(m->pt_d); cudaFree(m->itab_d); cudaFree(m->itab2_d); cudaFree(m->dbg_d);
   for (auto& kv : m->rigid_scratch) cudaFree(kv.second.buf);
+  for (auto& kv : m->rk4_scratch) cudaFree(kv.second.buf);
   cudaFree(m->cst_dd); cudaFree(m->csuc_dd); cudaFree(m->pt_dd);
   cudaSetDevice(prev);
   delete m;
@@ -1268,6 +1448,29 @@ int b200sim_step_jvp(B200SimModel* m, int64_t B, int32_t nsteps, const double* l
   P.nsteps = nsteps;
   P.mode = MODE_STEP;
   return launch_dual(m, P, stream);
+}
+
+int b200sim_step_rk4(B200SimModel* m, int dtype, int64_t B, const void* s, const void* sd, const void* q, const void* vlin,
+                     const void* omega, const void* p, const void* mt, const void* tau_ref, const void* fext, void* s_o,
+                     void* sd_o, void* q_o, void* vlin_o, void* omega_o, void* p_o, void* m_o, void* W_H_B, void* iXl,
+                     void* W_H_L, void* W_v, void* stream) {
+  if (!m || B < 0 || (dtype != 0 && dtype != 1)) return B200SIM_E_INVALID;
+  if (m->contact_model >= B200SIM_CONTACT_RIGID && m->nc > 0) return B200SIM_E_UNSUPPORTED;
+  if (B == 0) return 0;
+  if (!q || !vlin || !omega || !p || !q_o || !vlin_o || !omega_o || !p_o) return B200SIM_E_INVALID;
+  if (m->n > 0 && (!s || !sd || !s_o || !sd_o)) return B200SIM_E_INVALID;
+  if (!aligned(W_H_B, 16) || !aligned(iXl, 16) || !aligned(W_H_L, 16) || !aligned(W_v, dtype == 0 ? 8 : 16))
+    return B200SIM_E_INVALID;
+  if (dtype == 0) {
+    typedef float T;
+    Rk4Io<T> io = {(const T*)s, (const T*)sd, (const T*)q, (const T*)vlin, (const T*)omega, (const T*)p, (const T*)mt,
+                   (const T*)tau_ref, (T*)s_o, (T*)sd_o, (T*)q_o, (T*)vlin_o, (T*)omega_o, (T*)p_o, (T*)m_o};
+    return step_rk4_t<T>(m, dtype, B, io, (const T*)fext, (T*)W_H_B, (T*)iXl, (T*)W_H_L, (T*)W_v, stream);
+  }
+  typedef double T;
+  Rk4Io<T> io = {(const T*)s, (const T*)sd, (const T*)q, (const T*)vlin, (const T*)omega, (const T*)p, (const T*)mt,
+                 (const T*)tau_ref, (T*)s_o, (T*)sd_o, (T*)q_o, (T*)vlin_o, (T*)omega_o, (T*)p_o, (T*)m_o};
+  return step_rk4_t<T>(m, dtype, B, io, (const T*)fext, (T*)W_H_B, (T*)iXl, (T*)W_H_L, (T*)W_v, stream);
 }
 
 int b200sim_dynamics(const B200SimModel* m, int dtype, int64_t B, const void* s, const void* sd, const void* q,

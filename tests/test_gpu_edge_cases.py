@@ -330,6 +330,50 @@ def test_rk4_step_accepts_unbatched_data(cuda_device):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_rk4_step_is_one_abi_call_and_graph_capturable(dtype, cuda_device):
+    """b200sim_step_rk4: the whole RungeKutta4 step runs as launches on the caller's stream (no host round trip), so it
+    can be captured in a CUDA graph once its scratch exists; replays give the eager result bit for bit, and external
+    forces in Body representation plus joint references match the oracle."""
+    import torch
+
+    td = torch.float64 if dtype == "float64" else torch.float32
+    model = H.build_model("icub_like", integrator=js.model.IntegratorType.RungeKutta4)
+    om = H.oracle_model(model)
+    B = 33
+    od = O.random_model_data(om, B, seed=21, in_contact=True)
+    rng = np.random.default_rng(3)
+    f32 = lambda a: np.asarray(a, np.float32).astype(np.float64)  # noqa: E731
+    od = O.data_replace(om, f32(od.joint_positions), f32(od.joint_velocities), f32(od.base_quaternion), f32(od.base_linear_velocity),
+                        f32(od.base_angular_velocity), f32(od.base_position),
+                        f32(1e-4 * rng.uniform(-1, 1, (B, model.number_of_collidable_points(), 3))))
+    tau = f32(rng.uniform(-5, 5, (B, om.dofs())))
+    fb = f32(rng.uniform(-5, 5, (B, om.number_of_links(), 6)))
+    ref = O.step_rk4(om, od, link_forces_inertial=O.other_representation_to_inertial(fb, "body", od.link_transforms, is_force=True),
+                     joint_force_references=tau)
+    data = H.to_product(model, od, td, cuda_device, velocity_representation=js.common.VelRepr.Body)
+    t = lambda a: torch.as_tensor(a, dtype=td, device=cuda_device)  # noqa: E731
+    lf, jf = t(fb), t(tau)
+    eager = js.model.step(model, data, link_forces=lf, joint_force_references=jf)
+    H.compare_data(eager, ref, H.RTOL[dtype], f"rk4 abi {dtype}")
+    side = torch.cuda.Stream(device=cuda_device)
+    side.wait_stream(torch.cuda.current_stream(cuda_device))
+    with torch.cuda.stream(side):
+        js.model.step(model, data, link_forces=lf, joint_force_references=jf)  # creates the scratch of this stream
+    torch.cuda.current_stream(cuda_device).wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        captured = js.model.step(model, data, link_forces=lf, joint_force_references=jf)
+    for leaf in ("_joint_positions", "_base_quaternion", "_link_velocities"):
+        getattr(captured, leaf).zero_()
+    graph.replay()
+    torch.cuda.synchronize(cuda_device)
+    for _, leaf in H.LEAVES:
+        assert torch.equal(getattr(captured, leaf), getattr(eager, leaf)), leaf
+    assert torch.equal(captured.contact_state["tangential_deformation"], eager.contact_state["tangential_deformation"])
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("contact", ["soft", "rigid"])
 def test_status_flags(contact, cuda_device):
     """Device-side status flags (b200sim_step_n_status): what rbda/utils.py:136-146 raises under
