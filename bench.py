@@ -555,8 +555,8 @@ def run_b200(args):
                                  "reference benchmark's random_model_data, where most environments are airborne"}
 
     rollout = None
-    if args.rollout > 0:
-        Tn = args.rollout
+    if args.rollout > 0 or extras:
+        Tn = args.rollout if args.rollout > 0 else 32
         d0 = js.data.random_model_data(model, batch_size=B, seed=55 + rank, dtype=dtype, device=dev,
                                        velocity_representation=js.common.VelRepr.Inertial)
         tau_T = 10 * torch.rand(Tn, B, n, dtype=dtype, device=dev)
@@ -564,7 +564,7 @@ def run_b200(args):
         for _ in range(3):
             js.model.step_n(model, d0, Tn, joint_force_references=tau_T, update_caches=False, out=o)
         barrier()
-        reps = 5
+        reps = 20
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
@@ -576,7 +576,8 @@ def run_b200(args):
             dist.all_reduce(tr, op=dist.ReduceOp.MAX)
         rollout = {"steps_per_launch": Tn, "value": B * world * Tn * reps / (float(tr.item()) * 1e-3), "unit": UNIT,
                    "ms_per_step": float(tr.item()) / (reps * Tn),
-                   "note": "step_n: state kept on chip, per-step HBM traffic = joint force references only; no caches written"}
+                   "note": "step_n (SURVEY.md 8f-1): the user loop `for _ in range(T): data = step(model, data, tau[t])` as ONE launch, "
+                           "state kept on chip, per-step HBM traffic = that step's joint force references; no caches written (B_min regime)"}
 
     config3 = None
     relaxed3 = None

@@ -659,6 +659,78 @@ def step_n(
     return _step_impl(model, data, int(n_steps), link_forces, joint_force_references, update_caches, out)
 
 
+def rollout(
+    model: JaxSimModel,
+    data: "_data.JaxSimModelData",
+    n_steps: int,
+    *,
+    link_forces: torch.Tensor | None = None,
+    joint_force_references: torch.Tensor | None = None,
+    record_every: int = 1,
+) -> tuple["_data.JaxSimModelData", "_data.JaxSimModelData"]:
+    """``n_steps`` steps with the state recorded every ``record_every`` steps (the ``lax.scan``
+    users write around ``step``, with trajectory subsampling): returns ``(final, trajectory)`` where the leaves of
+    ``trajectory`` (state and contact state, no caches) carry a leading axis of ``n_steps // record_every`` samples,
+    sample ``t`` being the state after ``(t + 1) * record_every`` steps.  Each sample is ONE fused ``step_n`` launch that
+    writes straight into its slice of the trajectory buffers (no copies); ``joint_force_references`` / ``link_forces``
+    are held constant or given per step (``(n_steps, B, ...)``) like in ``step_n``.  ``final`` is the last sample with
+    its caches.  Batched data only."""
+    k = int(record_every)
+    if n_steps < 1 or k < 1 or n_steps % k:
+        raise ValueError(f"n_steps = {n_steps} must be a positive multiple of record_every = {record_every}")
+    q = data._base_quaternion
+    if q.dim() != 2:
+        raise ValueError("rollout needs batched data")
+    T = int(n_steps) // k
+    B, dtype, dev = q.shape[0], q.dtype, q.device
+    nL, n, nc = model.number_of_links(), model.dofs(), model.number_of_collidable_points()
+    soft = isinstance(model.contact_model, SoftContacts)
+    new = lambda *shape: torch.empty(shape, dtype=dtype, device=dev)  # noqa: E731
+    traj = {"s": new(T, B, n), "sd": new(T, B, n), "q": new(T, B, 4), "vl": new(T, B, 3), "om": new(T, B, 3), "p": new(T, B, 3)}
+    if soft:
+        traj["m"] = new(T, B, nc, 3)
+    # the caches travel from sample to sample (the rigid contact models read them) in two alternating sets
+    caches = [(new(B, 4, 4), new(B, nL, 6, 6), new(B, nL, 4, 4), new(B, nL, 6)) for _ in range(min(T, 2))]
+    tau = None if joint_force_references is None else torch.as_tensor(joint_force_references, dtype=dtype, device=dev)
+    lf = None if link_forces is None else torch.as_tensor(link_forces, dtype=dtype, device=dev)
+    per_tau, per_lf = tau is not None and tau.dim() == 3, lf is not None and lf.dim() == 4
+    if (per_tau and tau.shape[0] != n_steps) or (per_lf and lf.shape[0] != n_steps):
+        raise ValueError("per-step references / forces need a leading axis of n_steps")
+    fused = model.integrator == IntegratorType.SemiImplicitEuler
+    cur = data
+    for t in range(T):
+        W_H_B, iXl, W_H_L, W_v = caches[t % 2]
+        out = _data.JaxSimModelData(
+            velocity_representation=data.velocity_representation,
+            _joint_positions=traj["s"][t], _joint_velocities=traj["sd"][t], _base_quaternion=traj["q"][t],
+            _base_linear_velocity=traj["vl"][t], _base_angular_velocity=traj["om"][t], _base_position=traj["p"][t],
+            _base_transform=W_H_B, _joint_transforms=iXl, _link_transforms=W_H_L, _link_velocities=W_v,
+            contact_state={"tangential_deformation": traj["m"][t]} if soft else dict(cur.contact_state or {}),
+        )
+        tau_t = tau[t * k:(t + 1) * k] if per_tau else tau
+        lf_t = lf[t * k:(t + 1) * k] if per_lf else lf
+        if fused:
+            if k == 1:
+                tau_t = tau_t[0] if per_tau else tau_t
+                lf_t = lf_t[0] if per_lf else lf_t
+            cur = step_n(model, cur, k, link_forces=lf_t, joint_force_references=tau_t, update_caches=True, out=out)
+        else:  # RungeKutta4 / RungeKutta4Fast: one ABI call per step, the sample copied into its slice
+            for j in range(k):
+                cur = step(model, cur, link_forces=lf_t[j] if per_lf else lf_t, joint_force_references=tau_t[j] if per_tau else tau_t)
+            for name, leaf in (("s", "_joint_positions"), ("sd", "_joint_velocities"), ("q", "_base_quaternion"),
+                               ("vl", "_base_linear_velocity"), ("om", "_base_angular_velocity"), ("p", "_base_position")):
+                traj[name][t].copy_(getattr(cur, leaf))
+            if soft:
+                traj["m"][t].copy_(cur.contact_state["tangential_deformation"])
+    trajectory = _data.JaxSimModelData(
+        velocity_representation=data.velocity_representation,
+        _joint_positions=traj["s"], _joint_velocities=traj["sd"], _base_quaternion=traj["q"], _base_linear_velocity=traj["vl"],
+        _base_angular_velocity=traj["om"], _base_position=traj["p"], _base_transform=None, _joint_transforms=None,
+        _link_transforms=None, _link_velocities=None, contact_state={"tangential_deformation": traj["m"]} if soft else {},
+    )
+    return cur, trajectory
+
+
 def forward_dynamics_aba(
     model: JaxSimModel,
     data: "_data.JaxSimModelData",

@@ -484,3 +484,40 @@ def test_full_size_parity(name, B, dtype, cuda_device):
     acc, sdd = js.model.forward_dynamics_aba(model, pd, joint_forces=tau_t)
     _, tau_id = js.model.inverse_dynamics(model, pd, joint_accelerations=sdd, base_acceleration=acc)
     assert float((tau_id - tau_t).abs().max()) / 10.0 <= (1e-9 if dtype == "float64" else 2e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("contact", ["soft", "rigid"])
+def test_rollout_records_the_trajectory(contact, cuda_device):
+    """js.model.rollout (trajectory subsampling): sample t is the state after (t+1) * record_every steps,
+    identical to stepping one at a time; the final data carries its caches."""
+    import torch
+
+    from jaxsim_b200.rbda.contacts import RigidContacts, RigidContactsParams
+
+    kw = dict(contact_model=RigidContacts.build(), contact_params=RigidContactsParams.build()) if contact == "rigid" else {}
+    model = H.build_model("icub_like", **kw)
+    om = H.oracle_model(model)
+    B, T, k = 9, 12, 3
+    od = O.random_model_data(om, B, seed=31, in_contact="flat" if contact == "rigid" else True)
+    data = H.to_product(model, od, torch.float64, cuda_device)
+    tau = torch.as_tensor(np.random.default_rng(2).uniform(-3, 3, (T, B, om.dofs())), device=cuda_device)
+    final, traj = js.model.rollout(model, data, T, joint_force_references=tau, record_every=k)
+    assert traj.joint_positions.shape == (T // k, B, om.dofs()) and traj._link_transforms is None
+    cur, samples = data, []
+    for t in range(T):
+        cur = js.model.step(model, cur, joint_force_references=tau[t])
+        if (t + 1) % k == 0:
+            samples.append(cur)
+    for i, ref in enumerate(samples):
+        for _, leaf in H.LEAVES[:6]:
+            got, want = getattr(traj, leaf)[i], getattr(ref, leaf)
+            # (a fused launch carries the kinematics on chip, single steps re-read them from the caches: rounding-level)
+            assert torch.allclose(got, want, rtol=1e-9, atol=1e-11), (i, leaf)
+    for _, leaf in H.LEAVES:
+        assert torch.allclose(getattr(final, leaf), getattr(samples[-1], leaf), rtol=1e-9, atol=1e-11), leaf
+    if contact == "soft":
+        assert torch.allclose(traj.contact_state["tangential_deformation"][-1], samples[-1].contact_state["tangential_deformation"],
+                              rtol=1e-9, atol=1e-13)
+    with pytest.raises(ValueError):
+        js.model.rollout(model, data, 10, record_every=3)
