@@ -704,9 +704,22 @@ def run_b200(args):
         e1.record()
         barrier()
         ms_j = e0.elapsed_time(e1) / reps
+        from jaxsim_b200.api import autodiff
+
+        autodiff.step_jacobian(model, d64, ("joint_positions", "link_masses"))
+        barrier()
+        e0.record()
+        for _ in range(3):
+            autodiff.step_jacobian(model, d64, ("joint_positions", "link_masses"))
+        e1.record()
+        barrier()
+        ms_jac = e0.elapsed_time(e1) / 3
         jvp = {"config": "BASELINE configs[4]: icub_like fp64, d(step)/d(joint q, link masses), batch %d" % B,
                "ms_per_jvp": ms_j, "env_jvps_per_s": B / (ms_j * 1e-3),
-               "ms_full_jacobian": ms_j * (n + nL), "note": "one tangent direction per launch (value + tangent of every output leaf incl. caches); full Jacobian = n + nL launches"}
+               "ms_full_jacobian": ms_jac, "jacobian_columns": n + nL,
+               "note": "ms_per_jvp: one tangent direction, value + tangent of every output leaf incl. caches.  ms_full_jacobian: "
+                       "MEASURED autodiff.step_jacobian w.r.t. (joint positions, link masses) -> (B, n_out, n + nL): the n joint "
+                       "directions as one launch over n replicas of the batch, one launch per link mass, no caches"}
 
     if rank != 0:
         if world > 1:

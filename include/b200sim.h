@@ -306,8 +306,12 @@ int b200sim_crba(const B200SimModel *model, int dtype, int64_t B, const void *s,
  * tangent (e.g. s is (B,n,2)).  link_mass_tangent: HOST (nL) direction in the space of
  * LinkParameters.mass (api/kin_dyn_parameters.py:596) or NULL; it enters through
  * Inertia.to_sixd (math/inertia.py:32-39) with the CoM and the CoM inertia held fixed.
- * Outputs: value and tangent of every output leaf of b200sim_step (same NULL rules).
- * Synchronises `stream` once (constant upload); not thread-safe per model. */
+ * Outputs: value and tangent of every output leaf of b200sim_step (same NULL rules: with the four
+ * cache pointers NULL the kinematics of the new state are neither computed nor stored).
+ * Several directions of per-environment inputs = one launch over replicas of the batch.
+ * The (value, tangent) image of the model constants is rewritten -- ordered on `stream`, no host
+ * synchronisation -- only when a mass direction is given or the previous call had one; JVPs of
+ * one model belong on one stream.  Not thread-safe per model. */
 int b200sim_step_jvp(B200SimModel *model, int64_t B, int32_t nsteps,
                      const double *link_mass_tangent,
                      const void *s, const void *sd, const void *q_wxyz, const void *v_lin,

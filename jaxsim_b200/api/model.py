@@ -952,6 +952,7 @@ def step_jvp(
     *,
     joint_force_references: torch.Tensor | None = None,
     n_steps: int = 1,
+    update_caches: bool = True,
 ) -> tuple["_data.JaxSimModelData", "_data.JaxSimModelData"]:
     """Forward-mode derivative of ``step`` (BASELINE config 5): the counterpart of
     ``jax.jvp(lambda theta: js.model.step(model(theta), data(theta)), ...)`` checked by the
@@ -965,7 +966,8 @@ def step_jvp(
     ``Inertia.to_sixd`` with CoM and CoM-inertia held fixed.
     Missing entries are zero.  float64, batched data, ``VelRepr`` is irrelevant (no link
     forces).  Returns ``(data_out, tangent_out)``: the stepped data and a data object whose
-    leaves (state, contact state and caches) hold the directional derivatives."""
+    leaves (state, contact state and caches) hold the directional derivatives.  ``update_caches=False`` skips the
+    caches of both (the kernel then neither computes nor stores the kinematics of the new state)."""
     q = data._base_quaternion
     if q.dim() != 2 or q.dtype != torch.float64:
         raise ValueError("step_jvp needs batched float64 data")
@@ -1000,7 +1002,7 @@ def step_jvp(
     new = lambda *shape: torch.empty(*shape, 2, dtype=torch.float64, device=dev)  # noqa: E731
     outs = [new(B, n), new(B, n), new(B, 4), new(B, 3), new(B, 3), new(B, 3)]
     m_o = new(B, nc, 3) if soft else None
-    caches = [new(B, 4, 4), new(B, nL, 6, 6), new(B, nL, 4, 4), new(B, nL, 6)]
+    caches = [new(B, 4, 4), new(B, nL, 6, 6), new(B, nL, 4, 4), new(B, nL, 6)] if update_caches else [None] * 4
     with torch.cuda.device(dev):
         rc = _lib.load().b200sim_step_jvp(
             dm.handle, B, int(n_steps), None if dmass is None else dmass.ctypes.data_as(_lib.c_dp),

@@ -62,6 +62,7 @@ struct B200SimModel {
   double *cst_d = nullptr, *csuc_d = nullptr, *pt_d = nullptr;
   int* itab_d = nullptr;
   DualD *cst_dd = nullptr, *csuc_dd = nullptr, *pt_dd = nullptr;  // forward-mode AD blobs (value, tangent)
+  bool cst_dd_has_tangent = false;                                // the resident cst_dd carries a mass direction
   // tuning
   int tune_G = 0, tune_epb = 0;
   int opt_flags = B200SIM_OPT_TMA_STORE;
@@ -801,11 +802,12 @@ int step_rk4_t(B200SimModel* m, int dtype, int64_t B, Rk4Io<T> io, const T* fext
 }  // namespace
 
 // ---- forward-mode AD (Dual<double>) -------------------------------------------------
-int upload_dual(const std::vector<double>& val, const std::vector<double>& tan, DualD** d) {
+int upload_dual(const std::vector<double>& val, const std::vector<double>& tan, DualD** d, cudaStream_t st) {
   std::vector<DualD> tmp(((val.size() + 3) & ~size_t(3)) + 4, DualD(0.0, 0.0));
   for (size_t i = 0; i < val.size(); ++i) tmp[i] = DualD(val[i], tan.empty() ? 0.0 : tan[i]);
   if (!*d) CK(cudaMalloc((void**)d, tmp.size() * sizeof(DualD)));
-  CK(cudaMemcpy(*d, tmp.data(), tmp.size() * sizeof(DualD), cudaMemcpyHostToDevice));
+  // pageable source: the runtime stages it before returning, the device-side copy is ordered on `st`
+  CK(cudaMemcpyAsync(*d, tmp.data(), tmp.size() * sizeof(DualD), cudaMemcpyHostToDevice, st));
   return 0;
 }
 
@@ -1165,6 +1167,7 @@ int b200sim_model_update_link_params(B200SimModel* m, const double* mass, const 
   CK(cudaDeviceSynchronize());
   int rc = upload(m->cst_h, &m->cst_f);
   if (!rc) rc = upload(m->cst_h, &m->cst_d);
+  m->cst_dd_has_tangent = true;  // the forward-mode image is stale: the next JVP rewrites it
   cudaSetDevice(prev);
   return rc;
 }
@@ -1428,10 +1431,16 @@ int b200sim_step_jvp(B200SimModel* m, int64_t B, int32_t nsteps, const double* l
   int prev = 0;
   CK(cudaGetDevice(&prev));
   CK(cudaSetDevice(m->device));
-  CK(cudaStreamSynchronize((cudaStream_t)stream));  // the blobs may still be in use by a previous JVP
-  int rc = upload_dual(m->cst_h, tan, &m->cst_dd);
-  if (!rc && !m->csuc_dd) rc = upload_dual(m->csuc_h, {}, &m->csuc_dd);
-  if (!rc && !m->pt_dd) rc = upload_dual(m->pt_h, {}, &m->pt_dd);
+  // The (value, tangent) image of the link constants is rewritten only when its tangent part changes: a mass direction
+  // is given, or the resident image still carries the previous call's.  The copy is ordered on the caller's stream
+  // (JVPs of one model are expected on one stream), so consecutive directions need no host synchronisation.
+  int rc = 0;
+  if (!m->cst_dd || link_mass_tangent || m->cst_dd_has_tangent) {
+    rc = upload_dual(m->cst_h, tan, &m->cst_dd, (cudaStream_t)stream);
+    m->cst_dd_has_tangent = link_mass_tangent != nullptr;
+  }
+  if (!rc && !m->csuc_dd) rc = upload_dual(m->csuc_h, {}, &m->csuc_dd, (cudaStream_t)stream);
+  if (!rc && !m->pt_dd) rc = upload_dual(m->pt_h, {}, &m->pt_dd, (cudaStream_t)stream);
   cudaSetDevice(prev);
   if (rc) return rc;
   Params<DualD> P;
