@@ -62,3 +62,62 @@ def test_step_jacobian_wrt_masses_and_joint_positions(cuda_device):
     g = autodiff.step_vjp(model, pd, ct, joint_force_references=torch.as_tensor(tau, device=cuda_device))
     ref = torch.einsum("bo,boi->bi", ct, J)
     assert torch.allclose(g["joint_positions"], ref[:, :23]) and torch.allclose(g["link_masses"], ref[:, 23:])
+
+
+def test_jvp_full_batch_properties(cuda_device):
+    """BASELINE config 5 at its full size (4096 environments, float64): size-independent properties of the derivative --
+    linearity in the tangent, the primal equals `step`, and the batched Jacobian columns (one launch over replicas of the
+    batch) equal single-direction JVPs; finite differences of the C oracle on a strided sample."""
+    import torch
+
+    from jaxsim_b200.api import autodiff
+
+    model = H.build_model("icub_like")
+    om = H.oracle_model(model)
+    B, n, nL = 4096, 23, 24
+    od = O.random_model_data(om, B, seed=123, in_contact=True)
+    rng = np.random.default_rng(9)
+    tau = 2 * rng.uniform(-1, 1, size=(B, n))
+    pd = H.to_product(model, od, torch.float64, cuda_device)
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64, device=cuda_device)  # noqa: E731
+    t1 = {"joint_positions": t(rng.uniform(-1, 1, (B, n))), "link_masses": t(rng.uniform(0, 1, nL))}
+    t2 = {"joint_positions": t(rng.uniform(-1, 1, (B, n))), "link_masses": t(rng.uniform(0, 1, nL))}
+    a, b = 0.7, -1.3
+    t3 = {k: a * t1[k] + b * t2[k] for k in t1}
+    kw = dict(joint_force_references=t(tau), update_caches=False)
+    p1, d1 = js.model.step_jvp(model, pd, t1, **kw)
+    _, d2 = js.model.step_jvp(model, pd, t2, **kw)
+    _, d3 = js.model.step_jvp(model, pd, t3, **kw)
+    assert d1._link_transforms is None and p1._link_transforms is None
+    ref = js.model.step(model, pd, joint_force_references=t(tau))
+    for _, leaf in H.LEAVES[:6]:
+        assert torch.allclose(getattr(p1, leaf), getattr(ref, leaf), rtol=1e-12, atol=1e-14), leaf
+        lin = a * getattr(d1, leaf) + b * getattr(d2, leaf)
+        scale = float(lin.abs().max()) + 1e-30
+        assert float((getattr(d3, leaf) - lin).abs().max()) <= 1e-10 * scale, leaf
+    # batched Jacobian columns == single directions; finite differences on a strided sample
+    sample = torch.arange(0, B, 512, device=cuda_device)
+    from jaxsim_b200.api.data import _map_leaves
+    ps = _map_leaves(pd, lambda x: x[sample].contiguous())
+    _, J, layout = autodiff.step_jacobian(model, ps, ("joint_positions", "link_masses"), joint_force_references=t(tau)[sample])
+    e = torch.zeros(len(sample), n, dtype=torch.float64, device=cuda_device)
+    e[:, 5] = 1.0
+    _, dj = js.model.step_jvp(model, ps, {"joint_positions": e}, joint_force_references=t(tau)[sample], update_caches=False)
+    assert torch.allclose(J[:, :n, 5], dj._joint_positions, rtol=1e-12, atol=1e-14)
+    idx = sample.cpu().numpy()
+    ods = O.data_replace(om, od.joint_positions[idx], od.joint_velocities[idx], od.base_quaternion[idx], od.base_linear_velocity[idx],
+                         od.base_angular_velocity[idx], od.base_position[idx], od.tangential_deformation[idx])
+    eps = 1e-6
+    Jn = J.cpu().numpy()
+    for j in (0, 11, 22):
+        dp, dm = copy.deepcopy(ods), copy.deepcopy(ods)
+        dp.joint_positions[:, j] += eps
+        dm.joint_positions[:, j] -= eps
+        fd = (_flat(CO.step(om, dp, joint_force_references=tau[idx], caches=False)) - _flat(CO.step(om, dm, joint_force_references=tau[idx], caches=False))) / (2 * eps)
+        assert np.abs(Jn[:, :, j] - fd).max() / max(np.abs(fd).max(), 1e-3) <= 5e-5, ("q", j)
+    for k in (0, 7, 23):
+        omp, omm = copy.deepcopy(om), copy.deepcopy(om)
+        omp.kin_dyn_parameters.link_parameters.mass[k] += eps
+        omm.kin_dyn_parameters.link_parameters.mass[k] -= eps
+        fd = (_flat(CO.step(omp, ods, joint_force_references=tau[idx], caches=False)) - _flat(CO.step(omm, ods, joint_force_references=tau[idx], caches=False))) / (2 * eps)
+        assert np.abs(Jn[:, :, n + k] - fd).max() / max(np.abs(fd).max(), 1e-3) <= 5e-5, ("mass", k)
