@@ -200,7 +200,12 @@ BRANCHED_URDF = """<robot name="branched">
 </robot>"""
 
 
-@pytest.mark.parametrize("name", ["pendulum", "double_pendulum", "cartpole", "box", "sphere", "icub_like", "ergocub_like", "branched"])
+# URDF files the reference ships (read in place: never copied into this repository; build container only)
+REFERENCE_URDFS = {"ref:cartpole": "examples/assets/cartpole.urdf", "ref:4_bar_opened": "tests/assets/4_bar_opened.urdf"}
+
+
+@pytest.mark.parametrize("name", ["pendulum", "double_pendulum", "cartpole", "box", "sphere", "icub_like", "ergocub_like", "four_bar",
+                                  "four_bar_fixed", "branched", *REFERENCE_URDFS])
 def test_urdf_front_end_matches_reference_parser(name):
     """The product's URDF loader against the reference's OWN front end run on the same URDF text:
     `jaxsim.parsers.rod.build_model_description` = parsers/rod/parser.py:36-420 + parsers/rod/utils.py:21-225 (inertial ->
@@ -217,7 +222,13 @@ def test_urdf_front_end_matches_reference_parser(name):
     jaxsim, js = refenv.load()
     # "branched": rotated inertial frames, fixed-joint lumping of links WITH collision shapes on two branches (the
     # reference keeps the shapes in file order and only re-parents them: ADVICE r1), prismatic + revolute joints
-    text = BRANCHED_URDF if name == "branched" else models.urdf(name)
+    if name in REFERENCE_URDFS:  # the reference's own model files: its example cart-pole and the 4-bar linkage of its tests
+        path = refenv.REFERENCE_SRC.parent / REFERENCE_URDFS[name]
+        if not path.is_file():
+            pytest.skip(f"{path} not available")
+        text = path.read_text()
+    else:
+        text = BRANCHED_URDF if name == "branched" else models.urdf(name)
     ref = js.model.JaxSimModel.build(model_description=refenv.reference_model_description(text), time_step=1e-3,
                                      gravity=-jaxsim.math.STANDARD_GRAVITY)
     rk = ref.kin_dyn_parameters
@@ -236,6 +247,11 @@ def test_urdf_front_end_matches_reference_parser(name):
         for f in ("friction_static", "friction_viscous", "position_limits_min", "position_limits_max", "position_limit_spring",
                   "position_limit_damper"):
             np.testing.assert_allclose(getattr(kd.joint_parameters, f), np.asarray(getattr(rk.joint_parameters, f)), rtol=1e-12, atol=0, err_msg=f)
+    # frames: massless links on fixed joints (parsers/rod/parser.py:90-124, api/kin_dyn_parameters.py:843-917)
+    fp, rf = kd.frame_parameters, rk.frame_parameters
+    assert tuple(fp.name) == tuple(rf.name) and tuple(int(b) for b in fp.body) == tuple(int(b) for b in np.asarray(rf.body).reshape(-1))
+    if len(fp.name):
+        np.testing.assert_allclose(np.asarray(fp.transform), np.asarray(rf.transform), rtol=1e-12, atol=1e-14)
 
 
 @pytest.mark.parametrize("cid", [c["id"] for c in C.all_cases() if c["constraints"]])
