@@ -714,12 +714,23 @@ def run_b200(args):
         e1.record()
         barrier()
         ms_jac = e0.elapsed_time(e1) / 3
+        n_out = 2 * n + 13 + 3 * nc
+        ct = torch.randn(B, n_out, dtype=torch.float64, device=dev)
+        autodiff.step_vjp(model, d64, ct)
+        barrier()
+        e0.record()
+        for _ in range(3):
+            autodiff.step_vjp(model, d64, ct)
+        e1.record()
+        barrier()
+        ms_vjp = e0.elapsed_time(e1) / 3
         jvp = {"config": "BASELINE configs[4]: icub_like fp64, d(step)/d(joint q, link masses), batch %d" % B,
                "ms_per_jvp": ms_j, "env_jvps_per_s": B / (ms_j * 1e-3),
-               "ms_full_jacobian": ms_jac, "jacobian_columns": n + nL,
+               "ms_full_jacobian": ms_jac, "jacobian_columns": n + nL, "ms_vjp": ms_vjp,
                "note": "ms_per_jvp: one tangent direction, value + tangent of every output leaf incl. caches.  ms_full_jacobian: "
                        "MEASURED autodiff.step_jacobian w.r.t. (joint positions, link masses) -> (B, n_out, n + nL): the n joint "
-                       "directions as one launch over n replicas of the batch, one launch per link mass, no caches"}
+                       "directions and the nL link-mass directions as launches over replicas of the batch (b200sim_step_jvp_ex), no caches.  ms_vjp: b200sim_step_vjp, the "
+                       "gradient of <cotangent, step> w.r.t. (joint positions, link masses): the same columns contracted on the device"}
 
     if rank != 0:
         if world > 1:

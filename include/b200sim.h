@@ -321,6 +321,35 @@ int b200sim_step_jvp(B200SimModel *model, int64_t B, int32_t nsteps,
                      void *W_H_B, void *i_X_lam, void *W_H_L, void *W_v_WL, void *stream);
 
 /* Library / build information: "b200sim <abi> sm_100a ..." */
+/* b200sim_step_jvp with SEVERAL mass directions in one launch: with mass_direction_period = P > 0 the batch is read as
+ * B / P replicas of P environments and replica r differentiates w.r.t. link_mass_tangent[k] * (mass of link k),
+ * k = mass_direction_first_link + r, alone (the entries of link_mass_tangent scale the directions; pass ones for unit
+ * columns).  Replicas whose link index falls outside [0, nL) carry no mass direction.  P = 0: b200sim_step_jvp. */
+int b200sim_step_jvp_ex(B200SimModel *model, int64_t B, int32_t nsteps,
+                        const double *link_mass_tangent, int64_t mass_direction_period,
+                        int32_t mass_direction_first_link,
+                        const void *s, const void *sd, const void *q_wxyz, const void *v_lin,
+                        const void *omega, const void *p, const void *m_tan, const void *tau,
+                        void *s_o, void *sd_o, void *q_o, void *v_lin_o, void *omega_o, void *p_o,
+                        void *m_o, void *W_H_B, void *joint_X, void *W_H_L, void *W_v_WL,
+                        void *stream);
+
+/* Gradient of the scalar <cotangent, step(x, theta)> with respect to the joint positions (per environment) and the link
+ * masses (per environment; sum over the batch for a shared-parameter loss): what jax.grad / jax.vjp of the reference's
+ * step returns for those arguments (tests/test_automatic_differentiation.py:346-420).  float64.  in: the primal state and
+ * joint force references as for b200sim_step (NULL rules alike), the cotangents ct_* of the new state leaves in the
+ * shapes of the leaves (any may be NULL = zero).  out: grad_s (B,n) and / or grad_link_mass (B,nL); either may be NULL.
+ * Implementation: forward-mode columns contracted on the device -- the n joint directions run as replicas of the batch
+ * in one launch of the forward-mode step kernel, each mass direction as one launch -- all on `stream`; the dual buffers
+ * live in a per-(model, stream) scratch block (first call / larger batch: not inside a stream capture).  Cost: about
+ * (n + nL) forward-mode steps.  RigidContacts / RelaxedRigidContacts with collidable points: B200SIM_E_UNSUPPORTED. */
+int b200sim_step_vjp(B200SimModel *model, int64_t B,
+                     const void *s, const void *sd, const void *q_wxyz, const void *v_lin,
+                     const void *omega, const void *p, const void *m_tan, const void *tau,
+                     const void *ct_s, const void *ct_sd, const void *ct_q, const void *ct_v_lin,
+                     const void *ct_omega, const void *ct_p, const void *ct_m_tan,
+                     void *grad_s, void *grad_link_mass, void *stream);
+
 const char *b200sim_version(void);
 
 #ifdef __cplusplus

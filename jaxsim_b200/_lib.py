@@ -98,6 +98,8 @@ EXPORTED_SYMBOLS = (
     "b200sim_step_jvp",
     "b200sim_dynamics",
     "b200sim_step_rk4",
+    "b200sim_step_vjp",
+    "b200sim_step_jvp_ex",
 )
 
 _lib = None
@@ -156,6 +158,10 @@ def load() -> C.CDLL:
     lib.b200sim_dynamics.restype = C.c_int
     lib.b200sim_step_rk4.argtypes = [vp, C.c_int, C.c_int64] + [vp] * 21
     lib.b200sim_step_rk4.restype = C.c_int
+    lib.b200sim_step_jvp_ex.argtypes = [vp, C.c_int64, C.c_int32, c_dp, C.c_int64, C.c_int32] + [vp] * 20
+    lib.b200sim_step_jvp_ex.restype = C.c_int
+    lib.b200sim_step_vjp.argtypes = [vp, C.c_int64] + [vp] * 18
+    lib.b200sim_step_vjp.restype = C.c_int
     _lib = lib
     return lib
 

@@ -8,9 +8,9 @@ directions per launch by replicating the batch):
 * :func:`jaxsim_b200.api.model.step_jvp` -- one Jacobian-vector product;
 * :func:`step_jacobian` -- the full Jacobian d(step outputs)/d(joint positions, link masses, ...)
   assembled from batched launches (per-environment inputs) and one launch per shared model parameter;
-* :func:`step_vjp` -- a vector-Jacobian product (the "gradient" of a scalar loss), assembled
-  from the same columns.  Cost = number of input coordinates x one JVP launch, which is the
-  right trade for the low-dimensional parameter sets of hardware co-design (n + nL inputs).
+* :func:`step_vjp` -- a vector-Jacobian product (the "gradient" of a scalar loss): one call of
+  ``b200sim_step_vjp``, which contracts the same forward-mode columns on the device.  Cost = about one forward-mode
+  step per input coordinate, the right trade for the low-dimensional parameter sets of hardware co-design (n + nL).
 """
 
 from __future__ import annotations
@@ -62,8 +62,8 @@ def step_jacobian(model, data, wrt=("joint_positions", "link_masses"), *, joint_
     ``LinkParameters.mass`` vector (``api/kin_dyn_parameters.py:596``).
 
     Directions of per-environment inputs are batched: K unit directions run as ONE launch over K replicas of the
-    batch (K x B dual environments), which keeps the forward-mode kernel in its throughput regime; a mass direction
-    changes the (shared) model constants and takes a launch of its own.  Without ``with_caches`` the kernel skips the
+    batch (K x B dual environments), which keeps the forward-mode kernel in its throughput regime -- link-mass directions
+    too (``b200sim_step_jvp_ex``: the constants carry the unit direction of every link, each replica keeps one).  Without ``with_caches`` the kernel skips the
     kinematics of the new state altogether."""
     from .data import _map_leaves
 
@@ -87,15 +87,19 @@ def step_jacobian(model, data, wrt=("joint_positions", "link_masses"), *, joint_
         k = sizes[name]
         layout[name] = slice(o, o + k)
         o += k
-        if name == "link_masses":
-            for j in range(k):
-                e = torch.zeros(k, dtype=torch.float64)
-                e[j] = 1.0
-                po, dout = _model.step_jvp(model, data, {name: e}, joint_force_references=tau, update_caches=with_caches)
-                out = po if out is None else out
-                cols.append(_flatten_outputs(dout, with_caches))
-            continue
         Kmax = max(1, min(k, _MAX_DUAL_ENVS // max(B, 1)))
+        if name == "link_masses":
+            # the constants carry the unit direction of every link; replica r keeps it for link j0 + r alone
+            for j0 in range(0, k, Kmax):
+                K = min(Kmax, k - j0)
+                dK, tauK = replicated(K)
+                po, dout = _model.step_jvp(model, dK, {name: torch.ones(k, dtype=torch.float64)}, joint_force_references=tauK,
+                                           update_caches=with_caches, mass_direction_period=B, mass_direction_first_link=j0)
+                if out is None:
+                    out = _map_leaves(po, lambda t: t[:B])
+                flat = _flatten_outputs(dout, with_caches).reshape(K, B, -1)
+                cols.extend(flat[i] for i in range(K))
+            continue
         for j0 in range(0, k, Kmax):
             K = min(Kmax, k - j0)
             dK, tauK = replicated(K)
@@ -110,12 +114,51 @@ def step_jacobian(model, data, wrt=("joint_positions", "link_masses"), *, joint_
     return out, J, layout
 
 
-def step_vjp(model, data, cotangent: torch.Tensor, wrt=("joint_positions", "link_masses"), *,
+def step_vjp(model, data, cotangent, wrt=("joint_positions", "link_masses"), *,
              joint_force_references=None) -> dict:
-    """Vector-Jacobian product: ``cotangent`` is ``(B, n_out)`` over the flattened new state
-    (same ordering as :func:`step_jacobian`, no caches).  Returns ``{name: gradient}`` with
-    per-environment gradients ``(B, size)`` (for ``link_masses`` too: sum over the batch for
-    the gradient of a batch-summed loss w.r.t. the shared masses)."""
-    _, J, layout = step_jacobian(model, data, wrt, joint_force_references=joint_force_references)
-    g = torch.einsum("bo,boi->bi", cotangent.to(J.dtype), J)
-    return {name: g[:, sl] for name, sl in layout.items()}
+    """Vector-Jacobian product of one ``step``: ``cotangent`` is ``(B, n_out)`` over the flattened new state (same
+    ordering as :func:`step_jacobian`, no caches) or a ``JaxSimModelData``-like object / dict of cotangent leaves.
+    Returns ``{name: gradient}`` with per-environment gradients ``(B, size)`` (for ``link_masses`` too: sum over the
+    batch for the gradient of a batch-summed loss w.r.t. the shared masses).
+
+    For ``wrt`` within (joint positions, link masses) -- BASELINE config 5 -- this is ONE call of ``b200sim_step_vjp``:
+    forward-mode columns contracted on the device.  Other inputs go through :func:`step_jacobian`."""
+    from jaxsim_b200 import _lib
+    from jaxsim_b200.rbda.contacts import SoftContacts
+
+    q = data._base_quaternion
+    if q.dim() != 2 or q.dtype != torch.float64:
+        raise ValueError("step_vjp needs batched float64 data")
+    B, dev = q.shape[0], q.device
+    n, nL, nc = model.dofs(), model.number_of_links(), model.number_of_collidable_points()
+    soft = isinstance(model.contact_model, SoftContacts) and nc > 0
+    widths = [("s", n), ("sd", n), ("q", 4), ("vl", 3), ("om", 3), ("p", 3)] + ([("m", 3 * nc)] if soft else [])
+    ct = torch.as_tensor(cotangent, dtype=torch.float64, device=dev)
+    if ct.shape != (B, sum(w for _, w in widths)):
+        raise ValueError(ct.shape, (B, sum(w for _, w in widths)))
+    if not set(wrt) <= {"joint_positions", "link_masses"}:
+        _, J, layout = step_jacobian(model, data, wrt, joint_force_references=joint_force_references)
+        g = torch.einsum("bo,boi->bi", ct, J)
+        return {name: g[:, sl] for name, sl in layout.items()}
+    parts, o = {}, 0
+    for name, w in widths:
+        parts[name] = ct[:, o:o + w].contiguous()
+        o += w
+    c = lambda t: None if t is None else torch.as_tensor(t, dtype=torch.float64, device=dev).contiguous()  # noqa: E731
+    m = c(data.contact_state.get("tangential_deformation")) if (soft and data.contact_state) else None
+    tau = None if joint_force_references is None else c(torch.as_tensor(joint_force_references, dtype=torch.float64, device=dev).expand(B, n))
+    g_s = torch.empty(B, n, dtype=torch.float64, device=dev) if "joint_positions" in wrt else None
+    g_m = torch.empty(B, nL, dtype=torch.float64, device=dev) if "link_masses" in wrt else None
+    dm = model.device_model(dev)
+    ptr, stream = _model._ptr, _model._stream_ptr(dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().b200sim_step_vjp(
+            dm.handle, B, ptr(c(data._joint_positions)), ptr(c(data._joint_velocities)), ptr(c(q)), ptr(c(data._base_linear_velocity)),
+            ptr(c(data._base_angular_velocity)), ptr(c(data._base_position)), ptr(m), ptr(tau),
+            ptr(parts["s"]), ptr(parts["sd"]), ptr(parts["q"]), ptr(parts["vl"]), ptr(parts["om"]), ptr(parts["p"]), ptr(parts.get("m")),
+            ptr(g_s), ptr(g_m), stream)
+    _lib.check(rc, "b200sim_step_vjp")
+    out = {}
+    for name in wrt:
+        out[name] = g_s if name == "joint_positions" else g_m
+    return out

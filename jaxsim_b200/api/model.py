@@ -953,6 +953,8 @@ def step_jvp(
     joint_force_references: torch.Tensor | None = None,
     n_steps: int = 1,
     update_caches: bool = True,
+    mass_direction_period: int = 0,
+    mass_direction_first_link: int = 0,
 ) -> tuple["_data.JaxSimModelData", "_data.JaxSimModelData"]:
     """Forward-mode derivative of ``step`` (BASELINE config 5): the counterpart of
     ``jax.jvp(lambda theta: js.model.step(model(theta), data(theta)), ...)`` checked by the
@@ -967,7 +969,10 @@ def step_jvp(
     Missing entries are zero.  float64, batched data, ``VelRepr`` is irrelevant (no link
     forces).  Returns ``(data_out, tangent_out)``: the stepped data and a data object whose
     leaves (state, contact state and caches) hold the directional derivatives.  ``update_caches=False`` skips the
-    caches of both (the kernel then neither computes nor stores the kinematics of the new state)."""
+    caches of both (the kernel then neither computes nor stores the kinematics of the new state).  With
+    ``mass_direction_period = P > 0`` the batch is read as replicas of ``P`` environments and replica ``r`` takes the
+    ``link_masses`` direction of link ``mass_direction_first_link + r`` alone (``b200sim_step_jvp_ex``: many mass columns
+    in one launch)."""
     q = data._base_quaternion
     if q.dim() != 2 or q.dtype != torch.float64:
         raise ValueError("step_jvp needs batched float64 data")
@@ -1004,8 +1009,9 @@ def step_jvp(
     m_o = new(B, nc, 3) if soft else None
     caches = [new(B, 4, 4), new(B, nL, 6, 6), new(B, nL, 4, 4), new(B, nL, 6)] if update_caches else [None] * 4
     with torch.cuda.device(dev):
-        rc = _lib.load().b200sim_step_jvp(
+        rc = _lib.load().b200sim_step_jvp_ex(
             dm.handle, B, int(n_steps), None if dmass is None else dmass.ctypes.data_as(_lib.c_dp),
+            int(mass_direction_period), int(mass_direction_first_link),
             *[_ptr(t) for t in ins], _ptr(m_in), _ptr(tau_in),
             *[_ptr(t) for t in outs], _ptr(m_o), *[_ptr(t) for t in caches], _stream_ptr(dev),
         )

@@ -57,6 +57,7 @@ struct B200SimModel {
   // stage buffers of b200sim_step_rk4, one per (model, stream) like the work lists above
   struct StageScratch { void* buf = nullptr; size_t bytes = 0; };
   std::unordered_map<void*, StageScratch> rk4_scratch;
+  std::unordered_map<void*, StageScratch> vjp_scratch;  // dual inputs / outputs of b200sim_step_vjp
   // device blobs
   float *cst_f = nullptr, *csuc_f = nullptr, *pt_f = nullptr;
   double *cst_d = nullptr, *csuc_d = nullptr, *pt_d = nullptr;
@@ -833,6 +834,175 @@ int launch_dual(const B200SimModel* m, Params<DualD>& P, void* stream) {
   return rc;
 }
 
+// (value, tangent) image of the model constants for a mass direction dm (HOST, nL; NULL = no direction):
+// d(mass) = dm, d(D_link) = dm (|c|^2 1 - c c^T) (Inertia.to_sixd with the CoM and the CoM inertia held fixed); everything
+// else is constant.  The image is rewritten only when its tangent part changes: a direction is given, or the resident
+// image still carries the previous call's.  The copy is ordered on the caller's stream (JVPs of one model are expected
+// on one stream), so consecutive directions need no host synchronisation.
+int ensure_dual_blobs(B200SimModel* m, const double* link_mass_tangent, void* stream) {
+  int prev = 0;
+  CK(cudaGetDevice(&prev));
+  CK(cudaSetDevice(m->device));
+  int rc = 0;
+  if (!m->cst_dd || link_mass_tangent || m->cst_dd_has_tangent) {
+    std::vector<double> tan(m->cst_h.size(), 0.0);
+    if (link_mass_tangent) {
+      for (int i = 0; i < m->nL; ++i) {
+        const double* c = m->cst_h.data() + (size_t)i * CREC;
+        double* tc = tan.data() + (size_t)i * CREC;
+        const double dm = link_mass_tangent[i];
+        const double cx = c[C_COM], cy = c[C_COM + 1], cz = c[C_COM + 2];
+        const double cc = cx * cx + cy * cy + cz * cz;
+        tc[C_MASS] = dm;
+        tc[C_DL + 0] = dm * (cc - cx * cx); tc[C_DL + 1] = -dm * cx * cy; tc[C_DL + 2] = -dm * cx * cz;
+        tc[C_DL + 3] = dm * (cc - cy * cy); tc[C_DL + 4] = -dm * cy * cz; tc[C_DL + 5] = dm * (cc - cz * cz);
+      }
+    }
+    rc = upload_dual(m->cst_h, tan, &m->cst_dd, (cudaStream_t)stream);
+    m->cst_dd_has_tangent = link_mass_tangent != nullptr;
+  }
+  if (!rc && !m->csuc_dd) rc = upload_dual(m->csuc_h, {}, &m->csuc_dd, (cudaStream_t)stream);
+  if (!rc && !m->pt_dd) rc = upload_dual(m->pt_h, {}, &m->pt_dd, (cudaStream_t)stream);
+  cudaSetDevice(prev);
+  return rc;
+}
+
+// ---- b200sim_step_vjp: gradient of <cotangent, step(x, theta)> w.r.t. joint positions and link masses ----------------
+// Forward-mode columns contracted on the device.  The joint directions run as replicas of the batch in ONE launch of the
+// forward-mode step kernel (replica r of environment b carries the unit tangent of joint j0 + r); a mass direction
+// changes the shared model constants and takes a launch of its own over the un-replicated batch.
+struct VjpIn { const double *s, *sd, *q, *vl, *om, *p, *m, *tau; };
+struct VjpCt { const double *s, *sd, *q, *vl, *om, *p, *m; };
+struct VjpDual { DualD *s, *sd, *q, *vl, *om, *p, *m, *tau, *s_o, *sd_o, *q_o, *vl_o, *om_o, *p_o, *m_o; };
+
+__global__ void vjp_pack_kernel(long long B, int K, int n, int nc, int j0, VjpIn in, VjpDual d) {
+  const int E = 3 * n + 13 + 3 * nc;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= (long long)K * B * E) return;
+  const long long e = tid / E;  // dual environment = replica * B + environment
+  int k = (int)(tid - e * E);
+  const long long b = e % B;
+  const int r = (int)(e / B);
+  if (k < n) { d.s[e * n + k] = DualD(in.s[b * n + k], (j0 >= 0 && k == j0 + r) ? 1.0 : 0.0); return; }
+  k -= n;
+  if (k < n) { d.sd[e * n + k] = DualD(in.sd[b * n + k], 0.0); return; }
+  k -= n;
+  if (k < n) { d.tau[e * n + k] = DualD(in.tau ? in.tau[b * n + k] : 0.0, 0.0); return; }
+  k -= n;
+  if (k < 4) { d.q[e * 4 + k] = DualD(in.q[b * 4 + k], 0.0); return; }
+  k -= 4;
+  if (k < 3) { d.vl[e * 3 + k] = DualD(in.vl[b * 3 + k], 0.0); return; }
+  k -= 3;
+  if (k < 3) { d.om[e * 3 + k] = DualD(in.om[b * 3 + k], 0.0); return; }
+  k -= 3;
+  if (k < 3) { d.p[e * 3 + k] = DualD(in.p[b * 3 + k], 0.0); return; }
+  k -= 3;
+  d.m[e * 3 * nc + k] = DualD(in.m ? in.m[b * 3 * nc + k] : 0.0, 0.0);
+}
+
+// g[b * g_stride + g_col0 + r] = sum over the output leaves of cotangent[b, :] . tangent_out[replica r, b, :]
+__global__ void vjp_contract_kernel(long long B, int K, int n, int nc, VjpCt ct, VjpDual d, double* g, int g_stride, int g_col0) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)K * B) return;
+  const long long b = e % B;
+  const int r = (int)(e / B);
+  double acc = 0.0;
+  if (ct.s) for (int k = 0; k < n; ++k) acc += ct.s[b * n + k] * d.s_o[e * n + k].d;
+  if (ct.sd) for (int k = 0; k < n; ++k) acc += ct.sd[b * n + k] * d.sd_o[e * n + k].d;
+  if (ct.q) for (int k = 0; k < 4; ++k) acc += ct.q[b * 4 + k] * d.q_o[e * 4 + k].d;
+  if (ct.vl) for (int k = 0; k < 3; ++k) acc += ct.vl[b * 3 + k] * d.vl_o[e * 3 + k].d;
+  if (ct.om) for (int k = 0; k < 3; ++k) acc += ct.om[b * 3 + k] * d.om_o[e * 3 + k].d;
+  if (ct.p) for (int k = 0; k < 3; ++k) acc += ct.p[b * 3 + k] * d.p_o[e * 3 + k].d;
+  if (ct.m) for (int k = 0; k < 3 * nc; ++k) acc += ct.m[b * 3 * nc + k] * d.m_o[e * 3 * nc + k].d;
+  g[b * g_stride + g_col0 + r] = acc;
+}
+
+int step_vjp_impl(B200SimModel* m, int64_t B, const VjpIn& in, const VjpCt& ct, double* g_s, double* g_mass, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = m->n, nL = m->nL, nc = (m->contact_model == 1) ? m->nc : 0;
+  // replicas per launch: enough dual environments to keep the forward-mode kernel in its throughput regime
+  const int Kc = std::max(1, std::min(std::max(n, nL), (int)(131072 / std::max<int64_t>(B, 1))));
+  const size_t envs = (size_t)Kc * (size_t)B;
+  const size_t per_env = (size_t)(3 * n + 13 + 3 * nc) + (size_t)(2 * n + 13 + 3 * nc);
+  const size_t bytes = per_env * envs * sizeof(DualD) + 16 * 16;
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev != m->device) CK(cudaSetDevice(m->device));
+  void* base = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(m->rigid_mutex);
+    B200SimModel::StageScratch& sc = m->vjp_scratch[(void*)st];
+    if (!sc.buf || sc.bytes < bytes) {
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) return B200SIM_E_UNSUPPORTED;
+      if (sc.buf) {
+        CK(cudaStreamSynchronize(st));
+        CK(cudaFree(sc.buf));
+      }
+      sc.buf = nullptr;
+      sc.bytes = 0;
+      CK(cudaMalloc(&sc.buf, bytes));
+      sc.bytes = bytes;
+    }
+    base = sc.buf;
+  }
+  DualD* cur = (DualD*)base;
+  auto take = [&](size_t count) { DualD* ptr = cur; cur += count; return ptr; };  // sizeof(DualD) = 16: every leaf aligned
+  VjpDual d;
+  d.s = take(envs * n); d.sd = take(envs * n); d.q = take(envs * 4); d.vl = take(envs * 3); d.om = take(envs * 3);
+  d.p = take(envs * 3); d.m = take(envs * 3 * nc); d.tau = take(envs * n);
+  d.s_o = take(envs * n); d.sd_o = take(envs * n); d.q_o = take(envs * 4); d.vl_o = take(envs * 3); d.om_o = take(envs * 3);
+  d.p_o = take(envs * 3); d.m_o = take(envs * 3 * nc);
+  const int E = 3 * n + 13 + 3 * nc;
+  const int threads = 256;
+  auto launch_step = [&](long long Bd, long long mass_period = 0, int mass_first = 0) {
+    Params<DualD> P;
+    std::memset(&P, 0, sizeof(P));
+    fill_model_params(m, P);
+    P.flags &= ~F_TMA_STORE;
+    P.B = Bd;
+    P.mass_dir_period = mass_period;
+    P.mass_dir_first = mass_first;
+    P.s = d.s; P.sd = d.sd; P.q = d.q; P.vlin = d.vl; P.omega = d.om; P.p = d.p; P.m = nc ? d.m : nullptr; P.tau = d.tau;
+    P.s_o = d.s_o; P.sd_o = d.sd_o; P.q_o = d.q_o; P.vlin_o = d.vl_o; P.omega_o = d.om_o; P.p_o = d.p_o;
+    P.m_o = nc ? d.m_o : nullptr;
+    P.nsteps = 1;
+    P.mode = MODE_STEP;
+    return launch_dual(m, P, stream);
+  };
+  int rc = 0;
+  if (g_s && n > 0) {
+    rc = ensure_dual_blobs(m, nullptr, stream);
+    for (int j0 = 0; j0 < n && !rc; j0 += Kc) {
+      const int K = std::min(Kc, n - j0);
+      const long long total = (long long)K * B * E;
+      vjp_pack_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, st>>>(B, K, n, nc, j0, in, d);
+      rc = (int)cudaGetLastError();
+      if (!rc) rc = launch_step((long long)K * B);
+      if (rc) break;
+      vjp_contract_kernel<<<(unsigned)(((long long)K * B + threads - 1) / threads), threads, 0, st>>>(B, K, n, nc, ct, d, g_s, n, j0);
+      rc = (int)cudaGetLastError();
+    }
+  }
+  if (!rc && g_mass) {
+    // the tangent part of the constants holds the unit mass direction of EVERY link; replica r keeps it for link k0 + r
+    std::vector<double> ones(nL, 1.0);
+    rc = ensure_dual_blobs(m, ones.data(), stream);
+    for (int k0 = 0; k0 < nL && !rc; k0 += Kc) {
+      const int K = std::min(Kc, nL - k0);
+      const long long total = (long long)K * B * E;
+      vjp_pack_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, st>>>(B, K, n, nc, -1, in, d);
+      rc = (int)cudaGetLastError();
+      if (!rc) rc = launch_step((long long)K * B, B, k0);
+      if (rc) break;
+      vjp_contract_kernel<<<(unsigned)(((long long)K * B + threads - 1) / threads), threads, 0, st>>>(B, K, n, nc, ct, d, g_mass, nL, k0);
+      rc = (int)cudaGetLastError();
+    }
+  }
+  if (dev != m->device) cudaSetDevice(dev);
+  return rc;
+}
+
 // Per-environment status flags of a step (b200sim_step_n_status): the conditions the reference can only raise as
 // exceptions under JAXSIM_ENABLE_EXCEPTIONS (rbda/utils.py:136-146), evaluated on the device after the step.
 template <typename T>
@@ -1153,6 +1323,7 @@ void b200sim_model_destroy(B200SimModel* m) {
   cudaFree(m->pt_f); cudaFree(m->pt_d); cudaFree(m->itab_d); cudaFree(m->itab2_d); cudaFree(m->dbg_d);
   for (auto& kv : m->rigid_scratch) cudaFree(kv.second.buf);
   for (auto& kv : m->rk4_scratch) cudaFree(kv.second.buf);
+  for (auto& kv : m->vjp_scratch) cudaFree(kv.second.buf);
   cudaFree(m->cst_dd); cudaFree(m->csuc_dd); cudaFree(m->pt_dd);
   cudaSetDevice(prev);
   delete m;
@@ -1408,40 +1579,22 @@ int b200sim_step_jvp(B200SimModel* m, int64_t B, int32_t nsteps, const double* l
                      const void* sd, const void* q, const void* vlin, const void* omega, const void* p, const void* mt,
                      const void* tau, void* s_o, void* sd_o, void* q_o, void* vlin_o, void* omega_o, void* p_o,
                      void* m_o, void* W_H_B, void* iXl, void* W_H_L, void* W_v, void* stream) {
+  return b200sim_step_jvp_ex(m, B, nsteps, link_mass_tangent, 0, 0, s, sd, q, vlin, omega, p, mt, tau, s_o, sd_o, q_o, vlin_o,
+                             omega_o, p_o, m_o, W_H_B, iXl, W_H_L, W_v, stream);
+}
+
+int b200sim_step_jvp_ex(B200SimModel* m, int64_t B, int32_t nsteps, const double* link_mass_tangent,
+                        int64_t mass_direction_period, int32_t mass_direction_first_link, const void* s, const void* sd,
+                        const void* q, const void* vlin, const void* omega, const void* p, const void* mt, const void* tau,
+                        void* s_o, void* sd_o, void* q_o, void* vlin_o, void* omega_o, void* p_o, void* m_o, void* W_H_B,
+                        void* iXl, void* W_H_L, void* W_v, void* stream) {
   if (m && m->contact_model >= B200SIM_CONTACT_RIGID && m->nc > 0) return B200SIM_E_UNSUPPORTED;
-  if (!m || B < 0 || nsteps < 1) return B200SIM_E_INVALID;
+  if (!m || B < 0 || nsteps < 1 || mass_direction_period < 0) return B200SIM_E_INVALID;
+  if (mass_direction_period > 0 && !link_mass_tangent) return B200SIM_E_INVALID;
   if (B == 0) return 0;
   if (!q || !vlin || !omega || !p || !q_o || !vlin_o || !omega_o || !p_o) return B200SIM_E_INVALID;
   if (m->n > 0 && (!s || !sd || !s_o || !sd_o)) return B200SIM_E_INVALID;
-  // (value, tangent) image of the model constants for the requested mass direction:
-  // d(mass) = dm, d(D_link) = dm (|c|^2 1 - c c^T); everything else is constant
-  std::vector<double> tan(m->cst_h.size(), 0.0);
-  if (link_mass_tangent) {
-    for (int i = 0; i < m->nL; ++i) {
-      const double* c = m->cst_h.data() + (size_t)i * CREC;
-      double* tc = tan.data() + (size_t)i * CREC;
-      const double dm = link_mass_tangent[i];
-      const double cx = c[C_COM], cy = c[C_COM + 1], cz = c[C_COM + 2];
-      const double cc = cx * cx + cy * cy + cz * cz;
-      tc[C_MASS] = dm;
-      tc[C_DL + 0] = dm * (cc - cx * cx); tc[C_DL + 1] = -dm * cx * cy; tc[C_DL + 2] = -dm * cx * cz;
-      tc[C_DL + 3] = dm * (cc - cy * cy); tc[C_DL + 4] = -dm * cy * cz; tc[C_DL + 5] = dm * (cc - cz * cz);
-    }
-  }
-  int prev = 0;
-  CK(cudaGetDevice(&prev));
-  CK(cudaSetDevice(m->device));
-  // The (value, tangent) image of the link constants is rewritten only when its tangent part changes: a mass direction
-  // is given, or the resident image still carries the previous call's.  The copy is ordered on the caller's stream
-  // (JVPs of one model are expected on one stream), so consecutive directions need no host synchronisation.
-  int rc = 0;
-  if (!m->cst_dd || link_mass_tangent || m->cst_dd_has_tangent) {
-    rc = upload_dual(m->cst_h, tan, &m->cst_dd, (cudaStream_t)stream);
-    m->cst_dd_has_tangent = link_mass_tangent != nullptr;
-  }
-  if (!rc && !m->csuc_dd) rc = upload_dual(m->csuc_h, {}, &m->csuc_dd, (cudaStream_t)stream);
-  if (!rc && !m->pt_dd) rc = upload_dual(m->pt_h, {}, &m->pt_dd, (cudaStream_t)stream);
-  cudaSetDevice(prev);
+  int rc = ensure_dual_blobs(m, link_mass_tangent, stream);
   if (rc) return rc;
   Params<DualD> P;
   std::memset(&P, 0, sizeof(P));
@@ -1456,7 +1609,24 @@ int b200sim_step_jvp(B200SimModel* m, int64_t B, int32_t nsteps, const double* l
   P.W_H_B = (T*)W_H_B; P.iXl = (T*)iXl; P.W_H_L = (T*)W_H_L; P.W_v = (T*)W_v;
   P.nsteps = nsteps;
   P.mode = MODE_STEP;
+  P.mass_dir_period = mass_direction_period;
+  P.mass_dir_first = mass_direction_first_link;
   return launch_dual(m, P, stream);
+}
+
+int b200sim_step_vjp(B200SimModel* m, int64_t B, const void* s, const void* sd, const void* q, const void* vlin,
+                     const void* omega, const void* p, const void* mt, const void* tau, const void* ct_s, const void* ct_sd,
+                     const void* ct_q, const void* ct_vlin, const void* ct_omega, const void* ct_p, const void* ct_m,
+                     void* grad_s, void* grad_link_mass, void* stream) {
+  if (m && m->contact_model >= B200SIM_CONTACT_RIGID && m->nc > 0) return B200SIM_E_UNSUPPORTED;
+  if (!m || B < 0) return B200SIM_E_INVALID;
+  if (B == 0) return 0;
+  if (!q || !vlin || !omega || !p) return B200SIM_E_INVALID;
+  if (m->n > 0 && (!s || !sd)) return B200SIM_E_INVALID;
+  typedef const double* cd;
+  VjpIn in = {(cd)s, (cd)sd, (cd)q, (cd)vlin, (cd)omega, (cd)p, (cd)mt, (cd)tau};
+  VjpCt ct = {(cd)ct_s, (cd)ct_sd, (cd)ct_q, (cd)ct_vlin, (cd)ct_omega, (cd)ct_p, (m->contact_model == 1 && m->nc > 0) ? (cd)ct_m : nullptr};
+  return step_vjp_impl(m, B, in, ct, (double*)grad_s, (double*)grad_link_mass, stream);
 }
 
 int b200sim_step_rk4(B200SimModel* m, int dtype, int64_t B, const void* s, const void* sd, const void* q, const void* vlin,

@@ -76,6 +76,7 @@ __device__ __forceinline__ DualD min_t(DualD a, DualD b) {
   if (a.v > b.v) return b;
   return DualD(a.v, 0.5 * (a.d + b.d));
 }
+__device__ __forceinline__ DualD keep_tangent(DualD x, bool keep) { return DualD(x.v, keep ? x.d : 0.0); }
 __device__ __forceinline__ DualD rcp_t(DualD x) {
   const double r = 1.0 / x.v;
   return DualD(r, -r * r * x.d);

@@ -127,6 +127,11 @@ struct Params {
   int ws2_words;                             // step2_kernel: shared-memory words per environment (env2_ws_words)
   int* status;                               // optional per-environment status flags (b200sim_step_n_status), OR-ed into
   int fext_repr;                             // representation of `fext`: 0 inertial-fixed, 1 body-fixed, 2 mixed (api/common.py:160-222)
+  // forward mode only: with mass_dir_period > 0 environment e differentiates w.r.t. the mass of link
+  // mass_dir_first + e / mass_dir_period -- the tangent part of the model constants then holds the unit mass direction
+  // of EVERY link and is kept for that link alone (many mass directions in one launch over replicas of the batch)
+  long long mass_dir_period;
+  int mass_dir_first;
   T dt, g, h_terrain, K, D, mu, pexp, qexp, tau_max, w_th, w_max;
   T reg;                // rigid contacts: Delassus regularisation
   T rx_tc, rx_zeta, rx_dmin, rx_dmax, rx_width, rx_mid, rx_pow;  // relaxed-rigid contacts (relaxed_rigid.py:30-82)
@@ -172,6 +177,9 @@ __device__ __forceinline__ float sqrt_t(float x) {
 __device__ __forceinline__ double sqrt_t(double x) { return sqrt(x); }
 __device__ __forceinline__ float pow_t(float x, float y) { return powf(x, y); }
 __device__ __forceinline__ double pow_t(double x, double y) { return pow(x, y); }
+// forward-mode scalars drop their tangent part when `keep` is false (b200sim_dual.cuh); plain scalars are unchanged
+__device__ __forceinline__ float keep_tangent(float x, bool) { return x; }
+__device__ __forceinline__ double keep_tangent(double x, bool) { return x; }
 __device__ __forceinline__ float abs_t(float x) { return fabsf(x); }
 __device__ __forceinline__ double abs_t(double x) { return fabs(x); }
 __device__ __forceinline__ float max_t(float a, float b) { return fmaxf(a, b); }
@@ -1167,10 +1175,16 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
           add_external_wrench(P.fext_repr, fx, R, p, fe, ne);
         }
         // link inertia in world axes about the link origin
-        const T mass = c[C_MASS];
+        T mass = c[C_MASS];
         T com[3], cw[3], Dl[6];
         ldn<3>(c + C_COM, com);
         ldn<6>(c + C_DL, Dl);
+        if (P.mass_dir_period > 0) {
+          const bool keep = (long long)i == (long long)P.mass_dir_first + env / P.mass_dir_period;
+          mass = keep_tangent(mass, keep);
+#pragma unroll
+          for (int k = 0; k < 6; ++k) Dl[k] = keep_tangent(Dl[k], keep);
+        }
         mat3_vec(R, com, cw);
         T Dw[6];
         {

@@ -57,11 +57,62 @@ def test_step_jacobian_wrt_masses_and_joint_positions(cuda_device):
         fd = (_flat(CO.step(omp, od, joint_force_references=tau, caches=False)) - _flat(CO.step(omm, od, joint_force_references=tau, caches=False))) / (2 * eps)
         scale = max(np.abs(fd).max(), 1e-3)
         assert np.abs(Jn[:, :, 23 + k] - fd).max() / scale <= 5e-5, ("mass", k)
-    # VJP == J^T cotangent
+    # VJP (b200sim_step_vjp: the columns contracted on the device) == J^T cotangent
     ct = torch.randn(B, n_out, dtype=torch.float64, device=cuda_device)
     g = autodiff.step_vjp(model, pd, ct, joint_force_references=torch.as_tensor(tau, device=cuda_device))
     ref = torch.einsum("bo,boi->bi", ct, J)
-    assert torch.allclose(g["joint_positions"], ref[:, :23]) and torch.allclose(g["link_masses"], ref[:, 23:])
+    assert torch.allclose(g["joint_positions"], ref[:, :23], rtol=1e-10, atol=1e-12)
+    assert torch.allclose(g["link_masses"], ref[:, 23:], rtol=1e-10, atol=1e-12)
+    only = autodiff.step_vjp(model, pd, ct, ("link_masses",), joint_force_references=torch.as_tensor(tau, device=cuda_device))
+    assert set(only) == {"link_masses"} and torch.equal(only["link_masses"], g["link_masses"])
+    # another input set goes through the Jacobian
+    gv = autodiff.step_vjp(model, pd, ct, ("joint_velocities",), joint_force_references=torch.as_tensor(tau, device=cuda_device))
+    _, Jv, _ = autodiff.step_jacobian(model, pd, ("joint_velocities",), joint_force_references=torch.as_tensor(tau, device=cuda_device))
+    assert torch.allclose(gv["joint_velocities"], torch.einsum("bo,boi->bi", ct, Jv))
+
+
+def test_step_vjp_gradient_of_a_scalar_loss(cuda_device):
+    """The use the reference makes of reverse mode (tests/test_automatic_differentiation.py:346-420): the gradient of a
+    scalar function of the stepped state w.r.t. joint positions and link masses, here at 512 environments and for models
+    with and without collidable points, against central finite differences of the C oracle."""
+    import torch
+
+    from jaxsim_b200.api import autodiff
+
+    for name, in_contact in (("icub_like", True), ("double_pendulum", False)):
+        model = H.build_model(name)
+        om = H.oracle_model(model)
+        n, nL = om.dofs(), om.number_of_links()
+        B = 512
+        od = O.random_model_data(om, B, seed=5, in_contact=in_contact)
+        rng = np.random.default_rng(4)
+        tau = rng.uniform(-1, 1, size=(B, n))
+        w = rng.uniform(-1, 1, size=_flat(CO.step(om, od, joint_force_references=tau, caches=False)).shape)
+
+        def loss(model_, data_):
+            return float((w * _flat(CO.step(model_, data_, joint_force_references=tau, caches=False))).sum())
+
+        pd = H.to_product(model, od, torch.float64, cuda_device)
+        g = autodiff.step_vjp(model, pd, torch.as_tensor(w, device=cuda_device), joint_force_references=torch.as_tensor(tau, device=cuda_device))
+        assert g["joint_positions"].shape == (B, n) and g["link_masses"].shape == (B, nL)
+        eps = 1e-6
+        gm = g["link_masses"].sum(dim=0).cpu().numpy()  # the masses are shared by the batch
+        for k in range(0, nL, max(1, nL // 4)):
+            omp, omm = copy.deepcopy(om), copy.deepcopy(om)
+            omp.kin_dyn_parameters.link_parameters.mass[k] += eps
+            omm.kin_dyn_parameters.link_parameters.mass[k] -= eps
+            fd = (loss(omp, od) - loss(omm, od)) / (2 * eps)
+            assert abs(gm[k] - fd) <= 5e-5 * max(abs(fd), np.abs(gm).max(), 1e-3), (name, "mass", k, gm[k], fd)
+        gs = g["joint_positions"].cpu().numpy()
+        for j in range(0, n, max(1, n // 4)):
+            dp, dmn = copy.deepcopy(od), copy.deepcopy(od)
+            dp.joint_positions[:, j] += eps
+            dmn.joint_positions[:, j] -= eps
+            # every environment is perturbed at once: the loss separates over environments
+            fp = (w * _flat(CO.step(om, dp, joint_force_references=tau, caches=False))).sum(axis=1)
+            fm = (w * _flat(CO.step(om, dmn, joint_force_references=tau, caches=False))).sum(axis=1)
+            fd = (fp - fm) / (2 * eps)
+            assert np.abs(gs[:, j] - fd).max() <= 5e-5 * max(np.abs(fd).max(), 1e-3), (name, "q", j)
 
 
 def test_jvp_full_batch_properties(cuda_device):
