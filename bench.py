@@ -593,6 +593,9 @@ def run_b200(args):
             models.urdf("ergocub_like"), time_step=1e-3, contact_model=cm3, contact_params=cp3)
         B3 = args.c3_batch
         n3, nL3, nc3 = m3.dofs(), m3.number_of_links(), m3.number_of_collidable_points()
+        mono3 = bool(os.environ.get("B200SIM_RIGID_MONO"))  # A/B switch: contact QP inside the rigid kernel (round-1 path)
+        if mono3:
+            m3.set_options(rigid_mono=True)
 
         def standing(seed):
             """level base, near-zero joints, soles 2-5 mm into the ground: several points active"""
@@ -622,6 +625,9 @@ def run_b200(args):
         config3 = {"config": "%s: ergocub_like (%d DoF, %d links, %d collidable points), %s, batch %d %s"
                              % ("BASELINE configs[2]" if kind == "rigid" else "reference step benchmark (tests/test_benchmark.py:143-152)",
                                 n3, nL3, nc3, type(cm3).__name__, B3, args.dtype), "unit": "env-steps/s"}
+        if kind == "rigid":
+            config3["level1"] = ("monolithic rigid kernel (B200SIM_OPT_RIGID_MONO)" if mono3 else
+                                 "split: assemble (rigid kernel) / solve (rigid_qp_kernel, QPs of <= 8 and 9-12 active points) / resume (rigid kernel)")
         ring3 = 4
         for label in ("random", "standing"):
             if label == "random":

@@ -143,6 +143,9 @@ int b200sim_model_set_tuning(B200SimModel *model, int lanes_per_env, int envs_pe
 /*   B200SIM_OPT_NO_BULK_IN: the second-generation kernel reads the cached kinematics of the input state
  *   with cp.async (LDGSTS) per link even when the rows qualify for cp.async.bulk (diagnostic). */
 #define B200SIM_OPT_NO_BULK_IN 64
+/*   B200SIM_OPT_RIGID_MONO: RigidContacts steps solve the contact QP inside the rigid kernel (one launch per
+ *   cascade level) instead of the default assemble / solve / resume launches of level 1 (A/B timing). */
+#define B200SIM_OPT_RIGID_MONO 128
 int b200sim_model_set_options(B200SimModel *model, int32_t options);
 
 /* Query sizes / launch geometry chosen for a batch (for benchmarks and tests). */

@@ -74,6 +74,7 @@ OPT_BULK_IN = 8
 OPT_NO_PDL = 16
 OPT_STEP_V1 = 32
 OPT_NO_BULK_IN = 64
+OPT_RIGID_MONO = 128
 REPR_INERTIAL, REPR_BODY, REPR_MIXED = 0, 1, 2
 STATUS_QUATERNION_NAN = 1
 STATUS_QUATERNION_NOT_UNIT = 2

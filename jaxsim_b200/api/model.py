@@ -300,7 +300,8 @@ class JaxSimModel:
             _lib.check(_lib.load().b200sim_model_set_tuning(dm.handle, *self._tuning), "set_tuning")
 
     def set_options(self, tma_store: bool = True, rigid_qp_f32: bool = False, generic_kernel: bool = False,
-                    bulk_in: bool = False, pdl: bool = True, step_v1: bool = False, no_bulk_in: bool = False) -> None:
+                    bulk_in: bool = False, pdl: bool = True, step_v1: bool = False, no_bulk_in: bool = False,
+                    rigid_mono: bool = False) -> None:
         """Implementation switches: ``b200sim_model_set_options``.  ``rigid_qp_f32`` makes
         float32 rigid-contact steps solve the contact QP / impact system in float32 too
         (default float64; forces then only good to ~1e-3 relative, smaller workspace).
@@ -311,7 +312,8 @@ class JaxSimModel:
         ``no_bulk_in`` makes the new one read the input caches with per-link ``cp.async``."""
         self._options = ((_lib.OPT_TMA_STORE if tma_store else 0) | (_lib.OPT_RIGID_QP_F32 if rigid_qp_f32 else 0)
                          | (_lib.OPT_GENERIC_KERNEL if generic_kernel else 0) | (_lib.OPT_BULK_IN if bulk_in else 0) | (0 if pdl else _lib.OPT_NO_PDL)
-                         | (_lib.OPT_STEP_V1 if step_v1 else 0) | (_lib.OPT_NO_BULK_IN if no_bulk_in else 0))
+                         | (_lib.OPT_STEP_V1 if step_v1 else 0) | (_lib.OPT_NO_BULK_IN if no_bulk_in else 0)
+                         | (_lib.OPT_RIGID_MONO if rigid_mono else 0))
         for dm in self._devices.values():
             _lib.check(_lib.load().b200sim_model_set_options(dm.handle, self._options), "set_options")
 

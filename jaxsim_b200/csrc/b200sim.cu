@@ -51,7 +51,10 @@ struct B200SimModel {
   unsigned long long* dbg_d = nullptr;  // debug counters, allocated by b200sim_debug_counters
   // work lists of the rigid-contact cascade: one scratch buffer per (model, stream), so that steps of the same model on
   // different streams do not share counters
-  struct RigidScratch { int* buf = nullptr; long long cap = 0; };
+  struct RigidScratch {
+    int* buf = nullptr; long long cap = 0;
+    unsigned char* qp = nullptr; size_t qp_bytes = 0;  // contact-QP records of the split rigid level (one per work item)
+  };
   std::unordered_map<void*, RigidScratch> rigid_scratch;
   std::mutex rigid_mutex;
   // stage buffers of b200sim_step_rk4, one per (model, stream) like the work lists above
@@ -431,6 +434,65 @@ int ensure_rigid_scratch(B200SimModel* m, long long B, cudaStream_t st, int** bu
   return 0;
 }
 
+// records of the split rigid level, grown like the work lists (same rule under stream capture)
+int ensure_qp_scratch(B200SimModel* m, size_t bytes, cudaStream_t st, unsigned char** buf) {
+  std::lock_guard<std::mutex> lock(m->rigid_mutex);
+  B200SimModel::RigidScratch& sc = m->rigid_scratch[(void*)st];
+  if (!sc.qp || sc.qp_bytes < bytes) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) return B200SIM_E_UNSUPPORTED;
+    if (sc.qp) {
+      CK(cudaStreamSynchronize(st));
+      CK(cudaFree(sc.qp));
+    }
+    sc.qp = nullptr;
+    sc.qp_bytes = 0;
+    CK(cudaMalloc((void**)&sc.qp, bytes));
+    sc.qp_bytes = bytes;
+  }
+  *buf = sc.qp;
+  return 0;
+}
+
+// the contact QPs of a split level's work items (rigid_qp_kernel)
+template <typename S>
+int launch_rigid_qp(const B200SimModel* m, long long B, const int* work_count, int* next_item, unsigned char* qp_buf, long long qp_stride,
+                    int cap, double mu, double tol, int* status, unsigned long long* dbg, cudaStream_t st) {
+  const QpLayout L = qp_layout<S>(cap);
+  const size_t smem = (size_t)QP_WARPS * L.total;
+  static const int minb = [] { const char* e = std::getenv("B200SIM_QP_MINB"); return e ? std::atoi(e) : 10; }();  // diagnostic A/B
+  auto kern = minb == 8 ? rigid_qp_kernel<S, 8> : (minb == 12 ? rigid_qp_kernel<S, 12> : rigid_qp_kernel<S, 10>);
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;  // exactly one resident wave: the blocks draw their items from `next_item`
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * QP_WARPS, smem));
+  const long long want = (B + QP_WARPS - 1) / QP_WARPS;
+  const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)m->num_sms * std::max(per_sm, 1)));
+  kern<<<grid, 32 * QP_WARPS, smem, st>>>(work_count, next_item, qp_buf, qp_stride, cap, (S)mu, (S)tol, status, dbg);
+  return (int)cudaGetLastError();
+}
+
+// level 1 of the cascade as three launches -- assemble (rigid kernel, qp_mode 1), solve (rigid_qp_kernel: 3-4x the
+// resident warps of the monolithic kernel, where the interior-point iteration is 88 % of the time), resume (qp_mode 2)
+template <typename T, typename S>
+int launch_rigid_level_split(B200SimModel* m, Params<T>& P1, int cap1, cudaStream_t st) {
+  const size_t stride = qp_record_bytes<S>(cap1);
+  unsigned char* qp = nullptr;
+  int rc = ensure_qp_scratch(m, stride * (size_t)P1.B, st, &qp);
+  if (rc) return rc;
+  P1.qp_buf = qp;
+  P1.qp_stride = (long long)stride;
+  P1.qp_mode = 1;
+  rc = launch_rigid_level<T, S>(m, P1, cap1, st);
+  // same stopping rule as the monolithic kernel: a float64 solve of float32 data stops at the resolution of the data
+  const double tol = (sizeof(S) == 8) ? (sizeof(T) == 4 ? 1e-8 : 1e-11) : 1e-5;
+  // counter [2] of the cascade's scratch (zeroed with the list counters) hands out the items of the solve launch
+  int* cnt = const_cast<int*>(P1.work_count);
+  if (!rc) rc = launch_rigid_qp<S>(m, P1.B, P1.work_count, cnt + 2, qp, (long long)stride, cap1, (double)P1.mu, tol, P1.status, P1.dbg, st);
+  P1.qp_mode = 2;
+  if (!rc) rc = launch_rigid_level<T, S>(m, P1, cap1, st);
+  return rc;
+}
+
 template <typename T>
 int launch_rigid(const B200SimModel* cm, Params<T>& P, int dtype, void* stream) {
   B200SimModel* m = const_cast<B200SimModel*>(cm);
@@ -457,7 +519,11 @@ int launch_rigid(const B200SimModel* cm, Params<T>& P, int dtype, void* stream) 
     Params<T> P1 = P;
     P1.work_count = cnt; P1.work_list = list1;
     P1.over_count = cnt + 1; P1.over_list = list2;
-    rc = qp32 ? launch_rigid_level<T, T>(m, P1, cap1, st) : launch_rigid_level<T, double>(m, P1, cap1, st);
+    // RigidContacts: split level (the records of a very large batch would not be worth their memory: monolithic then)
+    const bool split = m->contact_model == B200SIM_CONTACT_RIGID && !(m->opt_flags & B200SIM_OPT_RIGID_MONO) &&
+                       (size_t)P.B * qp_record_bytes<double>(cap1) <= ((size_t)2 << 30);
+    if (split) rc = qp32 ? launch_rigid_level_split<T, T>(m, P1, cap1, st) : launch_rigid_level_split<T, double>(m, P1, cap1, st);
+    else rc = qp32 ? launch_rigid_level<T, T>(m, P1, cap1, st) : launch_rigid_level<T, double>(m, P1, cap1, st);
   }
   if (!rc && cap1 < m->nc) {
     Params<T> P2 = P;
@@ -1321,7 +1387,7 @@ void b200sim_model_destroy(B200SimModel* m) {
   cudaSetDevice(m->device);
   cudaFree(m->cst_f); cudaFree(m->cst_d); cudaFree(m->csuc_f); cudaFree(m->csuc_d);
   cudaFree(m->pt_f); cudaFree(m->pt_d); cudaFree(m->itab_d); cudaFree(m->itab2_d); cudaFree(m->dbg_d);
-  for (auto& kv : m->rigid_scratch) cudaFree(kv.second.buf);
+  for (auto& kv : m->rigid_scratch) { cudaFree(kv.second.buf); cudaFree(kv.second.qp); }
   for (auto& kv : m->rk4_scratch) cudaFree(kv.second.buf);
   for (auto& kv : m->vjp_scratch) cudaFree(kv.second.buf);
   cudaFree(m->cst_dd); cudaFree(m->csuc_dd); cudaFree(m->pt_dd);
@@ -1412,7 +1478,7 @@ extern "C" int b200sim_debug_rigid_dump(B200SimModel* m, double* out512) {
 }
 
 int b200sim_model_set_options(B200SimModel* m, int32_t options) {
-  if (!m || (options & ~(B200SIM_OPT_TMA_STORE | B200SIM_OPT_RIGID_QP_F32 | B200SIM_OPT_GENERIC_KERNEL | B200SIM_OPT_BULK_IN | B200SIM_OPT_NO_PDL | B200SIM_OPT_STEP_V1 | B200SIM_OPT_NO_BULK_IN))) return B200SIM_E_INVALID;
+  if (!m || (options & ~(B200SIM_OPT_TMA_STORE | B200SIM_OPT_RIGID_QP_F32 | B200SIM_OPT_GENERIC_KERNEL | B200SIM_OPT_BULK_IN | B200SIM_OPT_NO_PDL | B200SIM_OPT_STEP_V1 | B200SIM_OPT_NO_BULK_IN | B200SIM_OPT_RIGID_MONO))) return B200SIM_E_INVALID;
   m->opt_flags = options;
   return 0;
 }

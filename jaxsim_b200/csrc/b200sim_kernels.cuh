@@ -154,6 +154,12 @@ struct Params {
   int* over_count;
   int* over_list;
   int na_cap;  // active points the consumer's shared-memory workspace is sized for
+  // split rigid level (b200sim_rigid_kernels.cuh): 0 = the rigid kernel solves its contact QP itself; 1 = it assembles the
+  // QP of every work item into qp_buf and stops; 2 = it resumes with the solution rigid_qp_kernel left there.
+  // Record of work item k at qp_buf + k * qp_stride: int na, rc, env, pad | S q[3 cap] | S x[3 cap] | S Q[packed, 3 cap]
+  int qp_mode;
+  unsigned char* qp_buf;
+  long long qp_stride;
   unsigned long long* dbg;  // optional counters (b200sim_debug_counters): QP iterations, items per level, ...
 };
 

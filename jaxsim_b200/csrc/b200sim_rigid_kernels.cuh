@@ -72,6 +72,15 @@ __host__ __device__ inline RigidLayout rigid_layout(int nL, int nc, int depth, i
   return L;
 }
 
+// Split rigid level: record of one work item in global memory, written by the assembling launch (qp_mode 1), solved
+// by rigid_qp_kernel, consumed by the resuming launch (qp_mode 2):  int na, rc, env, pad | S q[3 cap] | S x[3 cap] |
+// S Q[packed lower triangle of order 3 cap; an item with na active points uses the leading 3 na (3 na + 1) / 2 entries]
+template <typename S>
+__host__ __device__ inline size_t qp_record_bytes(int cap) {
+  const size_t N = 3 * (size_t)cap;
+  return rl_align(16 + sizeof(S) * (2 * N + N * (N + 1) / 2));
+}
+
 template <typename S> struct QpTol;
 template <> struct QpTol<float> {
   static __device__ __forceinline__ float tol() { return 1e-5f; }
@@ -168,17 +177,21 @@ __device__ __forceinline__ void chol_packed(S* __restrict__ Hp, S* __restrict__ 
 // solve L L^T x = y in place; invd = 1 / diag(L).  The vector lives in registers (lane owns
 // rows lane, lane+32, lane+64): the pivot element travels by shuffle, no shared-memory round
 // trip or barrier inside the substitution loops.  N <= 96.
-template <typename S>
+// NS = number of 32-row slots a lane may own (N <= 32 NS): the per-step work of the two substitution loops -- the
+// critical path of an interior-point iteration next to the factorisation -- shrinks with it.
+template <typename S, int NS = 3>
 __device__ __forceinline__ void chol_solve(const S* __restrict__ Lp, const S* __restrict__ invd, S* y, int N, int lane) {
-  S yr[3];
+  S yr[NS];
 #pragma unroll
-  for (int j = 0; j < 3; ++j) yr[j] = (lane + 32 * j < N) ? y[lane + 32 * j] : S(0);
+  for (int j = 0; j < NS; ++j) yr[j] = (lane + 32 * j < N) ? y[lane + 32 * j] : S(0);
   for (int k = 0; k < N; ++k) {
     const int slot = k >> 5;
-    const S src = (slot == 0) ? yr[0] : ((slot == 1) ? yr[1] : yr[2]);
+    S src = yr[0];
+#pragma unroll
+    for (int j = 1; j < NS; ++j) src = (slot == j) ? yr[j] : src;
     const S yk = __shfl_sync(FULL, src, k & 31) * invd[k];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
+    for (int j = 0; j < NS; ++j) {
       const int r = lane + 32 * j;
       if (r > k && r < N) yr[j] -= Lp[pidx(r, k)] * yk;
       else if (r == k) yr[j] = yk;
@@ -186,18 +199,20 @@ __device__ __forceinline__ void chol_solve(const S* __restrict__ Lp, const S* __
   }
   for (int k = N - 1; k >= 0; --k) {
     const int slot = k >> 5;
-    const S src = (slot == 0) ? yr[0] : ((slot == 1) ? yr[1] : yr[2]);
+    S src = yr[0];
+#pragma unroll
+    for (int j = 1; j < NS; ++j) src = (slot == j) ? yr[j] : src;
     const S xk = __shfl_sync(FULL, src, k & 31) * invd[k];
     const S* row = Lp + pidx(k, 0);
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
+    for (int j = 0; j < NS; ++j) {
       const int r = lane + 32 * j;
       if (r < k) yr[j] -= row[r] * xk;
       else if (r == k) yr[j] = xk;
     }
   }
 #pragma unroll
-  for (int j = 0; j < 3; ++j)
+  for (int j = 0; j < NS; ++j)
     if (lane + 32 * j < N) y[lane + 32 * j] = yr[j];
   __syncwarp();
 }
@@ -277,7 +292,8 @@ __device__ __forceinline__ void pyr_GT(S mu, const S* w, S* o) {
 // Primal-dual interior point, Mehrotra predictor-corrector.  Divisions are the expensive
 // operation (float64 especially): 1/s and 1/z are formed once per iteration and every
 // ratio below multiplies by them; the Cholesky factor carries 1/L_kk.
-template <typename S>
+// Q is read once per iteration, in order (H <- Q), so it may live in global memory (rigid_qp_kernel); NS as in chol_solve.
+template <typename S, int NS = 3>
 __device__ __noinline__ int qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int na, S mu_f, int lane, const S tol) {
   const int N = 3 * na, M = 5 * na;
   S* x = vN;
@@ -306,10 +322,12 @@ __device__ __noinline__ int qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int na
   __syncwarp();
   const int NP = N * (N + 1) / 2;
   const S inv_M = S(1) / S(M);
-  int it = 0;
+  int it = 0, it_prog = 0;
   for (; it < QpTol<S>::max_iter; ++it) {
-    // residuals
-    sym_matvec(Qp, x, rd, N, lane);
+    // H <- Q (the factor of the previous iteration is dead); residuals
+    for (int e = lane; e < NP; e += 32) Hp[e] = Qp[e];
+    __syncwarp();
+    sym_matvec(Hp, x, rd, N, lane);
     __syncwarp();
     S xQx = S(0), qx = S(0), xm = S(0), Qxm = S(0);
     for (int i = lane; i < N; i += 32) {
@@ -351,15 +369,18 @@ __device__ __noinline__ int qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int na
     const S m_d = rdn / (S(1) + qm + Qxm), m_p = rpn / (S(1) + xm), m_g = mu / (S(1) + abs_t(S(0.5) * xQx + qx));
     const S merit = max_t(m_d, max_t(m_p, m_g));
     if (merit < best) {
+      if (merit < S(0.5) * best) it_prog = it;
       best = merit;
       for (int i = lane; i < N; i += 32) xb[i] = x[i];
     }
+    // stalled above the tolerance (a degenerate problem at the resolution of S): ten iterations without halving the
+    // merit.  A healthy iteration gains a factor 3-10 per step; the stragglers used to run into max_iter, and ONE of
+    // them holds its whole launch (60 iterations = 1.7 ms).
+    if (it - it_prog >= 10) break;
     // converged, or the gap is far below the tolerance while a residual stalls at rounding level
     if (!(merit > tol)) { converged = true; break; }
     if (!(m_g > S(1e-3) * tol) || !(mu > S(0))) break;
     // H = Q + G' diag(z/s) G
-    for (int e = lane; e < NP; e += 32) Hp[e] = Qp[e];
-    __syncwarp();
     for (int a = lane; a < na; a += 32) {
       S w[5];
 #pragma unroll
@@ -385,7 +406,7 @@ __device__ __noinline__ int qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int na
       for (int d = 0; d < 3; ++d) dxa[3 * a + d] = -(rd[3 * a + d] + g[d]);
     }
     __syncwarp();
-    chol_solve(Hp, dg, dxa, N, lane);
+    chol_solve<S, NS>(Hp, dg, dxa, N, lane);
     // largest step keeping s, z positive: alpha = 1 / max_j(-ds_j / s_j, -dz_j / z_j)
     S rmax = S(1);
     for (int a = lane; a < na; a += 32) {
@@ -422,7 +443,7 @@ __device__ __noinline__ int qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int na
       for (int d = 0; d < 3; ++d) dx[3 * a + d] = -(rd[3 * a + d] + g[d]);
     }
     __syncwarp();
-    chol_solve(Hp, dg, dx, N, lane);
+    chol_solve<S, NS>(Hp, dg, dx, N, lane);
     S rm2 = S(0);
     for (int a = lane; a < na; a += 32) {
       S g[5];
@@ -522,7 +543,13 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
       env = item & 0x7fffffff;
       impact_only = item < 0;
     }
-    if (P.dbg && lane == 0) atomicAdd(P.dbg + (impact_only ? 5 : 4), 1ull);
+    int* qp_hdr = P.qp_mode ? reinterpret_cast<int*>(P.qp_buf + item_idx * P.qp_stride) : nullptr;
+    if (P.qp_mode == 1) {
+      if (lane == 0) { qp_hdr[0] = 0; qp_hdr[1] = 0; qp_hdr[2] = (int)env; }  // nothing to solve unless set below
+      if (impact_only) continue;
+      __syncwarp();
+    }
+    if (P.dbg && lane == 0 && P.qp_mode != 1) atomicAdd(P.dbg + (impact_only ? 5 : 4), 1ull);
 
     // ============================================================== input state
     // (impact_only: the pre-impact result of this step, stored by the previous level)
@@ -1135,9 +1162,10 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
     const int na = contact_points(false);
     B200SIM_RIGID_MARK(2);
     if (na > cap) {  // more active points than this level's workspace holds: next level, untouched
-      if (lane == 0) over_push(P, (int)env, 0);
+      if (lane == 0 && P.qp_mode != 2) over_push(P, (int)env, 0);  // (the assembling launch already pushed it)
       continue;
     }
+    if (P.qp_mode == 1 && na == 0) continue;
     link_init(true);
     pass2();
     // free acceleration (ABA pass 3, rbda/aba.py:233-288)
@@ -1192,9 +1220,24 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
         q[3 * a + 1] = S(val[1] + acc[1] + bv[1]);
         q[3 * a + 2] = S(val[2] + acc[2] + P.g + bv[2]);
       }
-      if (!relaxed) {
+      if (!relaxed && P.qp_mode == 2) {
+        // the contact forces were found by rigid_qp_kernel from the problem the assembling launch left in the record
+        const S* xg = reinterpret_cast<const S*>(qp_hdr + 4) + 3 * cap;
+        for (int i = lane; i < 3 * na; i += 32) vN[i] = xg[i];
+        __syncwarp();
+      } else if (!relaxed) {
         delassus(na, S(P.reg));
         B200SIM_RIGID_MARK(4);
+        if (P.qp_mode == 1) {
+          S* qg = reinterpret_cast<S*>(qp_hdr + 4);
+          S* Qg = qg + 6 * cap;
+          const int N = 3 * na, NP = N * (N + 1) / 2;
+          for (int i = lane; i < N; i += 32) qg[i] = q[i];
+          for (int e = lane; e < NP; e += 32) Qg[e] = Qp[e];
+          if (lane == 0) qp_hdr[0] = na;
+          __syncwarp();
+          continue;
+        }
 #ifdef B200SIM_RIGID_DEBUG
         if (P.dbg && lane == 0 && env == 0) {  // dump of the contact problem of environment 0 (diagnostic builds only)
           double* D = reinterpret_cast<double*>(P.dbg + 1600);
@@ -1414,6 +1457,73 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
       stn<3>(P.omega_o + env * 3, w2);
     }
     B200SIM_RIGID_MARK(12);
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// the contact QPs of a split rigid level, one warp per work item
+// ------------------------------------------------------------------------------------
+// The interior-point iteration is a chain of dependent shared-memory round trips on ONE warp; inside the monolithic
+// kernel an environment also holds its link records, so only 5-7 warps fit an SM and the schedulers idle 80 % of the
+// time (profiles/r01_rigid_kernel_v1.md).  On its own the solver needs H and a few vectors in shared memory (Q stays
+// in the item's record: it is read once per iteration, in order): 11.7 KB for 12 active points -- 19-20 resident warps.
+struct QpLayout { size_t Hp, vecN, vecM, total; };
+template <typename S>
+__host__ __device__ inline QpLayout qp_layout(int cap) {
+  QpLayout L;
+  const size_t N = 3 * (size_t)cap, M = 5 * (size_t)cap, NP = N * (N + 1) / 2;
+  size_t o = 0;
+  L.Hp = o;   o = rl_align(o + sizeof(S) * NP);
+  L.vecN = o; o = rl_align(o + sizeof(S) * 7 * N);
+  L.vecM = o; o = rl_align(o + sizeof(S) * 9 * M);
+  L.total = o;
+  return L;
+}
+
+constexpr int QP_WARPS = 2;  // warps per block (no block-level barrier: small blocks even out the iteration counts)
+
+// MINB = resident blocks per SM the register allocation aims at (8: 128 registers, 10: 96, 12: 80 + spills)
+template <typename S, int MINB>
+__global__ void __launch_bounds__(32 * QP_WARPS, MINB) rigid_qp_kernel(const int* work_count, int* next_item, unsigned char* qp_buf,
+                                                                  long long qp_stride, int cap, S mu_f, S tol, int* status,
+                                                                  unsigned long long* dbg) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const QpLayout L = qp_layout<S>(cap);
+  unsigned char* wb = smem_raw + (size_t)wrp * L.total;
+  S* Hp = reinterpret_cast<S*>(wb + L.Hp);
+  S* vN = reinterpret_cast<S*>(wb + L.vecN);
+  S* vM = reinterpret_cast<S*>(wb + L.vecM);
+  const int total = *work_count;
+  // iteration counts differ from item to item (5 ... 60): the warps draw items from a counter instead of striding
+  for (;;) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(next_item, 1);
+    item = __shfl_sync(FULL, item, 0);
+    if (item >= total) break;
+    int* hdr = reinterpret_cast<int*>(qp_buf + (long long)item * qp_stride);
+    const int na = hdr[0];
+    if (na <= 0) continue;  // whole warp: no contact at t, impact-only, or handed to the next level
+    const int N = 3 * na;
+    S* qg = reinterpret_cast<S*>(hdr + 4);
+    S* xg = qg + 3 * cap;
+    const S* Qg = qg + 6 * cap;
+    for (int i = lane; i < N; i += 32) vN[N + i] = qg[i];  // qp_pyramids reads q at vN + N
+    __syncwarp();
+    const int rc = (N <= 32) ? qp_pyramids<S, 1>(Qg, Hp, vN, vM, na, mu_f, lane, tol) : qp_pyramids<S, 3>(Qg, Hp, vN, vM, na, mu_f, lane, tol);
+    for (int i = lane; i < N; i += 32) xg[i] = vN[i];
+    if (lane == 0) {
+      hdr[1] = rc;
+      if (status && (rc & 0x10000)) atomicOr(status + hdr[2], 8);  // B200SIM_STATUS_QP_NOT_CONVERGED
+      if (dbg) {
+        const int it = rc & 0xFFFF;
+        atomicAdd(dbg + 0, (unsigned long long)it);
+        atomicAdd(dbg + 1, 1ull);
+        atomicMax(dbg + 2, (unsigned long long)it);
+        atomicAdd(dbg + 3, (unsigned long long)na);
+      }
+    }
     __syncwarp();
   }
 }

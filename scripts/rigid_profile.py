@@ -22,14 +22,16 @@ ap.add_argument("--model", default="ergocub_like")
 ap.add_argument("--dtype", default="f32")
 ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--qp32", action="store_true")
+ap.add_argument("--mono", action="store_true", help="contact QP inside the rigid kernel (B200SIM_OPT_RIGID_MONO)")
+ap.add_argument("--inputs", default="standing", choices=("standing", "random"))
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 dtype = torch.float32 if args.dtype == "f32" else torch.float64
 m = js.model.JaxSimModel.build_from_model_description(
     models.urdf(args.model), time_step=1e-3, contact_model=RigidContacts.build(),
     contact_params=RigidContactsParams.build(K=1e4, D=20.0))
-if args.qp32:
-    m.set_options(rigid_qp_f32=True)
+if args.qp32 or args.mono:
+    m.set_options(rigid_qp_f32=args.qp32, rigid_mono=args.mono)
 B, n = args.batch, m.dofs()
 gen = torch.Generator(device=dev).manual_seed(0)
 u = lambda *sh: 2 * torch.rand(*sh, dtype=dtype, device=dev, generator=gen) - 1  # noqa: E731
@@ -48,6 +50,8 @@ H = d0.link_transforms[:, body]
 z = (H[..., 2, 0:3] * Lp).sum(-1) + H[..., 2, 3]
 p[:, 2] -= z.min(dim=1).values + 0.002 + 0.003 * torch.rand(B, dtype=dtype, device=dev, generator=gen)
 data = js.data.JaxSimModelData.build(m, base_position=p, **kw)
+if args.inputs == "random":
+    data = js.data.random_model_data(m, batch_size=B, seed=51, dtype=dtype, device=dev, velocity_representation=js.common.VelRepr.Inertial)
 tau = 10 * torch.rand(B, n, dtype=dtype, device=dev)
 out = js.model.step(m, data, joint_force_references=tau)
 import ctypes  # noqa: E402
@@ -87,4 +91,4 @@ for k in range(2, 13):
         continue
     print("  %-52s %9d cyc %8.1f us" % (NAMES[k], t[k] - prev, (t[k] - prev) / 1965.0))
     prev = t[k]
-print("rigid step: %.3f ms/step, %.0f env-steps/s (B=%d, %s, qp32=%s)" % (ms, B / ms * 1e3, B, args.dtype, args.qp32))
+print("rigid step: %.3f ms/step, %.0f env-steps/s (B=%d, %s, qp32=%s, mono=%s, inputs=%s)" % (ms, B / ms * 1e3, B, args.dtype, args.qp32, args.mono, args.inputs))
