@@ -54,6 +54,9 @@ struct B200SimModel {
   struct RigidScratch {
     int* buf = nullptr; long long cap = 0;
     unsigned char* qp = nullptr; size_t qp_bytes = 0;  // contact-QP records of the split rigid level (one per work item)
+    // split cascade: level 2 runs on a side stream next to the solve / resume launches of level 1
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   };
   std::unordered_map<void*, RigidScratch> rigid_scratch;
   std::mutex rigid_mutex;
@@ -411,26 +414,35 @@ int launch_rigid_level(const B200SimModel* m, Params<T>& P, int cap, cudaStream_
   return (int)cudaGetLastError();
 }
 
-// work lists: [0..3] counters, then two lists of `cap` ints.  Grown on demand (not during a
+// work lists: [0..7] counters, then three lists of `cap` ints.  Grown on demand (not during a
 // stream capture: run one eager step of the largest batch first).
-int ensure_rigid_scratch(B200SimModel* m, long long B, cudaStream_t st, int** buf, long long* cap) {
+//   counters: [0] list 1 (level 0 -> level 1), [1] list 2 (level 1 -> level 2), [2] next item of the solve launch,
+//             [3] list 3 (split cascade: impact overflows of the resuming launch -> second level-2 launch)
+constexpr int RIGID_COUNTERS = 8;
+int ensure_rigid_scratch(B200SimModel* m, long long B, cudaStream_t st, B200SimModel::RigidScratch** out) {
   std::lock_guard<std::mutex> lock(m->rigid_mutex);
   B200SimModel::RigidScratch& sc = m->rigid_scratch[(void*)st];
-  if (!sc.buf || sc.cap < B) {
+  if (!sc.buf || sc.cap < B || !sc.aux) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone)
       return B200SIM_E_UNSUPPORTED;  // cannot allocate inside a capture: run one eager step of the largest batch first
-    if (sc.buf) {
-      CK(cudaStreamSynchronize(st));
-      CK(cudaFree(sc.buf));
+    if (!sc.aux) {
+      CK(cudaStreamCreateWithFlags(&sc.aux, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&sc.ev_fork, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&sc.ev_join, cudaEventDisableTiming));
     }
-    sc.buf = nullptr;
-    sc.cap = 0;
-    CK(cudaMalloc((void**)&sc.buf, sizeof(int) * (4 + 2 * (size_t)B)));
-    sc.cap = B;
+    if (!sc.buf || sc.cap < B) {
+      if (sc.buf) {
+        CK(cudaStreamSynchronize(st));
+        CK(cudaFree(sc.buf));
+      }
+      sc.buf = nullptr;
+      sc.cap = 0;
+      CK(cudaMalloc((void**)&sc.buf, sizeof(int) * (RIGID_COUNTERS + 3 * (size_t)B)));
+      sc.cap = B;
+    }
   }
-  *buf = sc.buf;
-  *cap = sc.cap;
+  *out = &sc;
   return 0;
 }
 
@@ -471,25 +483,53 @@ int launch_rigid_qp(const B200SimModel* m, long long B, const int* work_count, i
   return (int)cudaGetLastError();
 }
 
-// level 1 of the cascade as three launches -- assemble (rigid kernel, qp_mode 1), solve (rigid_qp_kernel: 3-4x the
-// resident warps of the monolithic kernel, where the interior-point iteration is 88 % of the time), resume (qp_mode 2)
+// RigidContacts, split cascade.  Level 1 is three launches -- assemble (rigid kernel, qp_mode 1), solve
+// (rigid_qp_kernel: 3-4x the resident warps of the monolithic kernel, where the interior-point iteration is 88 % of the
+// time), resume (qp_mode 2).  Level 2 (environments with more active points than level 1 holds, monolithic full-size
+// kernel, two warps per SM) starts on a side stream as soon as the assembling launch has listed them and runs NEXT TO
+// the solve / resume launches; the few environments whose IMPACT overflows level 1 go to a second list and a second,
+// usually empty, level-2 launch after the join.
 template <typename T, typename S>
-int launch_rigid_level_split(B200SimModel* m, Params<T>& P1, int cap1, cudaStream_t st) {
+int launch_rigid_split(B200SimModel* m, const Params<T>& P, B200SimModel::RigidScratch* sc, int cap1, cudaStream_t st) {
+  int* cnt = sc->buf;
+  int* list1 = cnt + RIGID_COUNTERS;
+  int* list2 = list1 + sc->cap;
+  int* list3 = list2 + sc->cap;
   const size_t stride = qp_record_bytes<S>(cap1);
   unsigned char* qp = nullptr;
-  int rc = ensure_qp_scratch(m, stride * (size_t)P1.B, st, &qp);
+  int rc = ensure_qp_scratch(m, stride * (size_t)P.B, st, &qp);
   if (rc) return rc;
-  P1.qp_buf = qp;
-  P1.qp_stride = (long long)stride;
+  const bool level2 = cap1 < m->nc;
+  Params<T> P1 = P;
+  P1.work_count = cnt; P1.work_list = list1;
+  P1.over_count = cnt + 1; P1.over_list = list2;
+  P1.qp_buf = qp; P1.qp_stride = (long long)stride;
   P1.qp_mode = 1;
   rc = launch_rigid_level<T, S>(m, P1, cap1, st);
+  if (rc) return rc;
+  if (level2) {
+    CK(cudaEventRecord(sc->ev_fork, st));
+    CK(cudaStreamWaitEvent(sc->aux, sc->ev_fork, 0));
+    Params<T> P2 = P;
+    P2.work_count = cnt + 1; P2.work_list = list2;
+    rc = launch_rigid_level<T, S>(m, P2, m->nc, sc->aux);
+    // the join is recorded whatever happened, so that a capture of `st` never ends with the side stream forked
+    CK(cudaEventRecord(sc->ev_join, sc->aux));
+  }
   // same stopping rule as the monolithic kernel: a float64 solve of float32 data stops at the resolution of the data
   const double tol = (sizeof(S) == 8) ? (sizeof(T) == 4 ? 1e-8 : 1e-11) : 1e-5;
-  // counter [2] of the cascade's scratch (zeroed with the list counters) hands out the items of the solve launch
-  int* cnt = const_cast<int*>(P1.work_count);
-  if (!rc) rc = launch_rigid_qp<S>(m, P1.B, P1.work_count, cnt + 2, qp, (long long)stride, cap1, (double)P1.mu, tol, P1.status, P1.dbg, st);
+  if (!rc) rc = launch_rigid_qp<S>(m, P.B, cnt, cnt + 2, qp, (long long)stride, cap1, (double)P.mu, tol, P.status, P.dbg, st);
   P1.qp_mode = 2;
+  P1.over_count = cnt + 3; P1.over_list = list3;
   if (!rc) rc = launch_rigid_level<T, S>(m, P1, cap1, st);
+  if (level2) {
+    CK(cudaStreamWaitEvent(st, sc->ev_join, 0));
+    if (!rc) {
+      Params<T> P3 = P;
+      P3.work_count = cnt + 3; P3.work_list = list3;
+      rc = launch_rigid_level<T, S>(m, P3, m->nc, st);
+    }
+  }
   return rc;
 }
 
@@ -500,12 +540,12 @@ int launch_rigid(const B200SimModel* cm, Params<T>& P, int dtype, void* stream) 
   CK(cudaGetDevice(&dev));
   if (dev != m->device) CK(cudaSetDevice(m->device));
   cudaStream_t st = (cudaStream_t)stream;
-  int* cnt = nullptr;
-  long long scap = 0;
-  int rc = ensure_rigid_scratch(m, P.B, st, &cnt, &scap);
-  int* list1 = cnt ? cnt + 4 : nullptr;
-  int* list2 = cnt ? list1 + scap : nullptr;
-  if (!rc) rc = (int)cudaMemsetAsync(cnt, 0, 4 * sizeof(int), st);
+  B200SimModel::RigidScratch* sc = nullptr;
+  int rc = ensure_rigid_scratch(m, P.B, st, &sc);
+  int* cnt = sc ? sc->buf : nullptr;
+  int* list1 = cnt ? cnt + RIGID_COUNTERS : nullptr;
+  int* list2 = cnt ? list1 + sc->cap : nullptr;
+  if (!rc) rc = (int)cudaMemsetAsync(cnt, 0, RIGID_COUNTERS * sizeof(int), st);
   if (!rc) {
     // level 0: never reads the cached link velocities (they may be the pre-impact ones)
     Params<T> P0 = P;
@@ -515,20 +555,23 @@ int launch_rigid(const B200SimModel* cm, Params<T>& P, int dtype, void* stream) 
   }
   const bool qp32 = sizeof(T) == 4 && (m->opt_flags & B200SIM_OPT_RIGID_QP_F32);
   const int cap1 = std::min(m->nc, RIGID_CAP1);
-  if (!rc) {
-    Params<T> P1 = P;
-    P1.work_count = cnt; P1.work_list = list1;
-    P1.over_count = cnt + 1; P1.over_list = list2;
-    // RigidContacts: split level (the records of a very large batch would not be worth their memory: monolithic then)
-    const bool split = m->contact_model == B200SIM_CONTACT_RIGID && !(m->opt_flags & B200SIM_OPT_RIGID_MONO) &&
-                       (size_t)P.B * qp_record_bytes<double>(cap1) <= ((size_t)2 << 30);
-    if (split) rc = qp32 ? launch_rigid_level_split<T, T>(m, P1, cap1, st) : launch_rigid_level_split<T, double>(m, P1, cap1, st);
-    else rc = qp32 ? launch_rigid_level<T, T>(m, P1, cap1, st) : launch_rigid_level<T, double>(m, P1, cap1, st);
-  }
-  if (!rc && cap1 < m->nc) {
-    Params<T> P2 = P;
-    P2.work_count = cnt + 1; P2.work_list = list2;
-    rc = qp32 ? launch_rigid_level<T, T>(m, P2, m->nc, st) : launch_rigid_level<T, double>(m, P2, m->nc, st);
+  // RigidContacts: split cascade (the records of a very large batch would not be worth their memory: monolithic then)
+  const bool split = m->contact_model == B200SIM_CONTACT_RIGID && !(m->opt_flags & B200SIM_OPT_RIGID_MONO) &&
+                     (size_t)P.B * qp_record_bytes<double>(cap1) <= ((size_t)2 << 30);
+  if (!rc && split) {
+    rc = qp32 ? launch_rigid_split<T, T>(m, P, sc, cap1, st) : launch_rigid_split<T, double>(m, P, sc, cap1, st);
+  } else {
+    if (!rc) {
+      Params<T> P1 = P;
+      P1.work_count = cnt; P1.work_list = list1;
+      P1.over_count = cnt + 1; P1.over_list = list2;
+      rc = qp32 ? launch_rigid_level<T, T>(m, P1, cap1, st) : launch_rigid_level<T, double>(m, P1, cap1, st);
+    }
+    if (!rc && cap1 < m->nc) {
+      Params<T> P2 = P;
+      P2.work_count = cnt + 1; P2.work_list = list2;
+      rc = qp32 ? launch_rigid_level<T, T>(m, P2, m->nc, st) : launch_rigid_level<T, double>(m, P2, m->nc, st);
+    }
   }
   if (dev != m->device) cudaSetDevice(dev);
   return rc;
@@ -1387,7 +1430,11 @@ void b200sim_model_destroy(B200SimModel* m) {
   cudaSetDevice(m->device);
   cudaFree(m->cst_f); cudaFree(m->cst_d); cudaFree(m->csuc_f); cudaFree(m->csuc_d);
   cudaFree(m->pt_f); cudaFree(m->pt_d); cudaFree(m->itab_d); cudaFree(m->itab2_d); cudaFree(m->dbg_d);
-  for (auto& kv : m->rigid_scratch) { cudaFree(kv.second.buf); cudaFree(kv.second.qp); }
+  for (auto& kv : m->rigid_scratch) {
+    cudaFree(kv.second.buf);
+    cudaFree(kv.second.qp);
+    if (kv.second.aux) { cudaStreamDestroy(kv.second.aux); cudaEventDestroy(kv.second.ev_fork); cudaEventDestroy(kv.second.ev_join); }
+  }
   for (auto& kv : m->rk4_scratch) cudaFree(kv.second.buf);
   for (auto& kv : m->vjp_scratch) cudaFree(kv.second.buf);
   cudaFree(m->cst_dd); cudaFree(m->csuc_dd); cudaFree(m->pt_dd);

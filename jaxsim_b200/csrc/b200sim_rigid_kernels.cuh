@@ -1251,7 +1251,8 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
         // iterate to the resolution of the DATA: float32 states carry 6e-8 relative rounding, so a float64 solve of a
         // float32 problem stops at 1e-8 (4-5 interior-point iterations earlier than the 1e-11 of float64 data)
         const S qp_tol = (sizeof(S) == 8 && sizeof(T) == 4) ? S(1e-8) : QpTol<S>::tol();
-        const int qp_rc = qp_pyramids<S>(Qp, Hp, vN, vM, na, S(P.mu), lane, qp_tol);
+        const int qp_rc = (3 * na <= 32) ? qp_pyramids<S, 1>(Qp, Hp, vN, vM, na, S(P.mu), lane, qp_tol)
+                                         : qp_pyramids<S, 3>(Qp, Hp, vN, vM, na, S(P.mu), lane, qp_tol);
         const int qp_it = qp_rc & 0xFFFF;
         if (P.status && lane == 0 && (qp_rc & 0x10000)) atomicOr(P.status + env, 8);  // B200SIM_STATUS_QP_NOT_CONVERGED
 #ifdef B200SIM_RIGID_DEBUG

@@ -216,6 +216,67 @@ def test_rigid_more_active_points_than_the_fast_workspace(cuda_device):
     H.compare_data(out, ref, 1e-5, "rigid 32 active points", floors=_vel_floors(od))
 
 
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_rigid_split_cascade_equals_monolithic_and_is_graph_capturable(dtype, cuda_device):
+    """The default cascade runs level 1 as assemble / solve / resume launches with level 2 on a side stream
+    (csrc/b200sim.cu: launch_rigid_split); ``rigid_mono`` keeps the contact QP inside the rigid kernel.  Both call the
+    same solver on the same numbers: every leaf agrees bit for bit, on a batch that takes every route of the cascade
+    (airborne, few active points, more than the 12 of level 1, landing during the step).  The split cascade is also
+    captured in a CUDA graph (the side stream forks and joins inside the capture) and replayed."""
+    import torch
+
+    from jaxsim_b200.terrain import FlatTerrain
+
+    B = 96
+    om0 = H.oracle_model(_model("ergocub_like", K=1e4, D=20.0))
+    a = _inputs(om0, B // 4, 41, False, dtype)     # airborne
+    b = _inputs(om0, B // 4, 42, "flat", dtype)    # standing: several active points
+    c = _inputs(om0, B // 4, 43, True, dtype)      # touching with a random orientation
+    d = _inputs(om0, B // 4, 44, "flat", dtype)    # sunk 4 mm: 14-16 active points -> level 2
+    pd_ = d.base_position.copy()
+    pd_[:, 2] -= 0.004
+    cat = lambda f: np.concatenate([getattr(a, f), getattr(b, f), getattr(c, f), getattr(d, f)], axis=0)  # noqa: E731
+    p = np.concatenate([a.base_position, b.base_position, c.base_position, pd_], axis=0)
+    perm = np.random.default_rng(5).permutation(B)
+    od = O.data_replace(om0, cat("joint_positions")[perm], cat("joint_velocities")[perm], cat("base_quaternion")[perm],
+                        cat("base_linear_velocity")[perm], cat("base_angular_velocity")[perm], p[perm])
+    W_p_C, _ = O.collidable_points_pos_vel(om0, od.link_transforms, od.link_velocities)
+    n_act = (W_p_C[..., 2] < 0).sum(axis=1)
+    assert (n_act == 0).any() and ((n_act > 0) & (n_act <= 12)).any() and (n_act > 12).any(), n_act
+    outs = {}
+    for mono in (False, True):
+        model = _model("ergocub_like", K=1e4, D=20.0)
+        if mono:
+            model.set_options(rigid_mono=True)
+        pd = H.to_product(model, od, _dtype(dtype), cuda_device)
+        status = torch.zeros(B, dtype=torch.int32, device=cuda_device)
+        out = js.model.step(model, pd, status_flags=status)
+        out = js.model.step(model, out, status_flags=status)  # second step: stale cached velocities, impacts
+        outs[mono] = (model, pd, out, status.clone())
+    for leaf in ("_joint_positions", "_joint_velocities", "_base_quaternion", "_base_position", "_base_linear_velocity",
+                 "_base_angular_velocity", "_link_transforms", "_link_velocities", "_joint_transforms"):
+        x, y = getattr(outs[False][2], leaf), getattr(outs[True][2], leaf)
+        assert torch.isfinite(x).all(), leaf
+        assert torch.equal(x, y), (leaf, float((x - y).abs().max()))
+    assert torch.equal(outs[False][3], outs[True][3])
+    # CUDA graph of the split cascade on a side stream of the caller
+    model, pd, _, _ = outs[False]
+    side = torch.cuda.Stream(cuda_device)
+    with torch.cuda.stream(side):
+        eager = js.model.step(model, pd)            # scratch of (model, side stream) grows outside the capture
+        buf = js.model.step(model, pd)
+        side.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            js.model.step(model, pd, out=buf)
+        for leaf in ("_joint_velocities", "_base_position", "_link_velocities"):
+            getattr(buf, leaf).zero_()
+        graph.replay()
+        side.synchronize()
+    for leaf in ("_joint_positions", "_joint_velocities", "_base_position", "_base_linear_velocity", "_link_velocities"):
+        assert torch.equal(getattr(buf, leaf), getattr(eager, leaf)), leaf
+
+
 # ------------------------------------------------------------------------------------------
 # RelaxedRigidContacts (rbda/contacts/relaxed_rigid.py): same assembly as the rigid model, the
 # contact forces are the solution of (Delassus + diag(r)) x = -b on the active points, no impact
