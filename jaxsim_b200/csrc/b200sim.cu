@@ -384,9 +384,9 @@ int launch(const B200SimModel* m, Params<T>& P, int dtype, void* stream) {
 constexpr int RIGID_CAP1 = 12;  // 12 active points: 7 resident warps per SM instead of 5 at 16 (the rest overflows to the full-size level)
 
 template <typename T, typename S>
-int rigid_geometry(const B200SimModel* m, long long B, int cap, int* warps, int* grid, size_t* smem) {
+int rigid_geometry(const B200SimModel* m, long long B, int cap, int qp_mode, int* warps, int* grid, size_t* smem) {
   const size_t st = static_smem_bytes(m, sizeof(T));
-  const RigidLayout L = rigid_layout<T, S>(m->nL, m->nc, m->depth, cap);
+  const RigidLayout L = rigid_layout<T, S>(m->nL, m->nc, m->depth, cap, qp_mode);
   const size_t budget = (size_t)m->max_smem_optin - 1024;
   if (st + L.total > budget) return B200SIM_E_TOO_LARGE;
   long long w = std::min<long long>(RIGID_MAX_WARPS, (long long)((budget - st) / L.total));
@@ -404,7 +404,7 @@ template <typename T, typename S>
 int launch_rigid_level(const B200SimModel* m, Params<T>& P, int cap, cudaStream_t st) {
   int warps = 0, grid = 0;
   size_t smem = 0;
-  int rc = rigid_geometry<T, S>(m, P.B, cap, &warps, &grid, &smem);
+  int rc = rigid_geometry<T, S>(m, P.B, cap, P.qp_mode, &warps, &grid, &smem);
   if (rc) return rc;
   P.envs_per_block = warps;
   P.na_cap = cap;
@@ -472,8 +472,8 @@ int launch_rigid_qp(const B200SimModel* m, long long B, const int* work_count, i
                     int cap, double mu, double tol, int* status, unsigned long long* dbg, cudaStream_t st) {
   const QpLayout L = qp_layout<S>(cap);
   const size_t smem = (size_t)QP_WARPS * L.total;
-  static const int minb = [] { const char* e = std::getenv("B200SIM_QP_MINB"); return e ? std::atoi(e) : 10; }();  // diagnostic A/B
-  auto kern = minb == 8 ? rigid_qp_kernel<S, 8> : (minb == 12 ? rigid_qp_kernel<S, 12> : rigid_qp_kernel<S, 10>);
+  static const int minb = [] { const char* e = std::getenv("B200SIM_QP_MINB"); return e ? std::atoi(e) : 8; }();  // diagnostic A/B
+  auto kern = minb == 10 ? rigid_qp_kernel<S, 10> : rigid_qp_kernel<S, 8>;  // 128 registers without spills beat 96 with (4.64 / 4.82 ms)
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;  // exactly one resident wave: the blocks draw their items from `next_item`
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * QP_WARPS, smem));

@@ -46,6 +46,16 @@ constexpr int RPT = 9;
 constexpr int RP_LEV = 0, RP_B = 3, RP_F = 6;
 constexpr int RIGID_MAX_WARPS = 8;
 
+// Packed lower triangle, every row starting on a 16-byte boundary (rows of odd length carry one pad element): the
+// row-times-row products of the factorisation then read two elements per shared-memory access (the contact-QP kernel
+// is bound by shared-memory wavefronts in that loop, profiles/r02_rigid_qp_kernel.md).
+//   prow(r) = start of row r = sum of the padded lengths (i + 2) & ~1 of the rows above; npk(N) = words of an order-N matrix
+__host__ __device__ __forceinline__ int prow(int r) { const int m = r >> 1; return 2 * (m + 1) * (m + (r & 1)); }
+__host__ __device__ __forceinline__ int pidx(int r, int c) { return prow(r) + c; }  // r >= c
+__host__ __device__ __forceinline__ size_t npk(size_t N) { return (size_t)prow((int)N); }
+__device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+
 struct RigidLayout {  // byte offsets inside one environment's (= one warp's) workspace
   size_t links, pts, ainv, ucol, Qp, Hp, vecN, vecM, ints, total;
 };
@@ -53,18 +63,20 @@ struct RigidLayout {  // byte offsets inside one environment's (= one warp's) wo
 __host__ __device__ inline size_t rl_align(size_t x) { return (x + 15) & ~size_t(15); }
 
 // `cap` = number of simultaneously active points the solver arrays are sized for (<= nc)
+// `qp_mode` (Params::qp_mode): the launches of a split level never run the interior-point method, so they do not carry
+// its vectors (mode 1, assemble only: nor the second matrix) -- one or two more resident warps per SM
 template <typename T, typename S>
-__host__ __device__ inline RigidLayout rigid_layout(int nL, int nc, int depth, int cap) {
+__host__ __device__ inline RigidLayout rigid_layout(int nL, int nc, int depth, int cap, int qp_mode = 0) {
   RigidLayout L;
   size_t o = 0;
-  const size_t N = 3 * (size_t)cap, M = 5 * (size_t)cap, NP = N * (N + 1) / 2;
+  const size_t N = 3 * (size_t)cap, M = qp_mode ? 0 : 5 * (size_t)cap, NP = npk(N);
   const size_t dd = depth > 0 ? depth : 1;
   L.links = o; o = rl_align(o + sizeof(T) * (size_t)nL * REC);
   L.pts = o;   o = rl_align(o + sizeof(T) * (size_t)nc * RPT);
   L.ainv = o;  o = rl_align(o + sizeof(T) * 36);
   L.ucol = o;  o = rl_align(o + sizeof(T) * 32 * dd);
   L.Qp = o;    o = rl_align(o + sizeof(S) * NP);
-  L.Hp = o;    o = rl_align(o + sizeof(S) * NP);
+  L.Hp = o;    o = rl_align(o + sizeof(S) * (qp_mode == 1 ? 0 : NP));
   L.vecN = o;  o = rl_align(o + sizeof(S) * 7 * N);
   L.vecM = o;  o = rl_align(o + sizeof(S) * 9 * M);
   L.ints = o;  o = rl_align(o + sizeof(int) * (5 * (size_t)nc + (size_t)nL + 4));
@@ -78,7 +90,7 @@ __host__ __device__ inline RigidLayout rigid_layout(int nL, int nc, int depth, i
 template <typename S>
 __host__ __device__ inline size_t qp_record_bytes(int cap) {
   const size_t N = 3 * (size_t)cap;
-  return rl_align(16 + sizeof(S) * (2 * N + N * (N + 1) / 2));
+  return rl_align(16 + sizeof(S) * (2 * N + npk(N)));
 }
 
 template <typename S> struct QpTol;
@@ -120,6 +132,16 @@ __device__ __forceinline__ S warp_max(S v) {
   for (int o = 16; o > 0; o >>= 1) v = max_t(v, __shfl_xor_sync(FULL, v, o));
   return v;
 }
+// maximum of FINITE operands as compare + select (3 instructions; fmax on doubles is an 8-instruction sequence, and the
+// solver takes ~60 maxima per lane and iteration).  Non-finite iterates are caught through the sums (see qp_pyramids).
+template <typename S>
+__device__ __forceinline__ S qmax(S a, S b) { return a > b ? a : b; }
+template <typename S>
+__device__ __forceinline__ S warp_qmax(S v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = qmax(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
 template <typename S>
 __device__ __forceinline__ S warp_min(S v) {
 #pragma unroll
@@ -127,14 +149,13 @@ __device__ __forceinline__ S warp_min(S v) {
   return v;
 }
 
-__device__ __forceinline__ int pidx(int r, int c) { return r * (r + 1) / 2 + c; }  // r >= c
 
 // y = A x for a packed lower-triangular symmetric A (rows lane-strided)
 template <typename S>
 __device__ __forceinline__ void sym_matvec(const S* Ap, const S* x, S* y, int N, int lane) {
   for (int r = lane; r < N; r += 32) {
     S acc = S(0);
-    const S* row = Ap + pidx(r, 0);
+    const S* row = Ap + prow(r);
     for (int c = 0; c <= r; ++c) acc += row[c] * x[c];
     for (int c = r + 1; c < N; ++c) acc += Ap[pidx(c, r)] * x[c];
     y[r] = acc;
@@ -154,17 +175,24 @@ __device__ __forceinline__ void chol_packed(S* __restrict__ Hp, S* __restrict__ 
     S d = max_t(Hp[pidx(k, k)], QpTol<S>::pivot_floor() * dg[k]);
     if (!(d > S(0))) d = S(1);
     const S ipiv = rsqrt_t(d);
-    const S* rowk = Hp + pidx(k, 0);
+    const S* rowk = Hp + prow(k);
     for (int r = k + 1 + lane; r < N; r += 32) {
-      S* row = Hp + pidx(r, 0);
-      // four independent partial sums: the shared-memory loads of a trip do not wait for the previous trip's FMAs
+      S* row = Hp + prow(r);
+      // four independent partial sums, two elements of either row per shared-memory access
       S a0 = row[k], a1 = S(0), a2 = S(0), a3 = S(0);
       int c = 0;
       for (; c + 3 < k; c += 4) {
-        a0 -= row[c] * rowk[c]; a1 -= row[c + 1] * rowk[c + 1];
-        a2 -= row[c + 2] * rowk[c + 2]; a3 -= row[c + 3] * rowk[c + 3];
+        const auto p0 = ld2(row + c), q0 = ld2(rowk + c), p1 = ld2(row + c + 2), q1 = ld2(rowk + c + 2);
+        a0 -= p0.x * q0.x; a1 -= p0.y * q0.y;
+        a2 -= p1.x * q1.x; a3 -= p1.y * q1.y;
       }
-      for (; c < k; ++c) a0 -= row[c] * rowk[c];
+      // the 0-3 leftover terms, predicated (no loop)
+      if (c + 1 < k) {
+        const auto p0 = ld2(row + c), q0 = ld2(rowk + c);
+        a0 -= p0.x * q0.x; a1 -= p0.y * q0.y;
+        c += 2;
+      }
+      if (c < k) a2 -= row[c] * rowk[c];
       const S v = ((a0 + a1) + (a2 + a3)) * ipiv;
       row[k] = v;
       row[r] -= v * v;
@@ -182,8 +210,12 @@ __device__ __forceinline__ void chol_packed(S* __restrict__ Hp, S* __restrict__ 
 template <typename S, int NS = 3>
 __device__ __forceinline__ void chol_solve(const S* __restrict__ Lp, const S* __restrict__ invd, S* y, int N, int lane) {
   S yr[NS];
+  const S* rowr[NS];  // start of this lane's packed rows
 #pragma unroll
-  for (int j = 0; j < NS; ++j) yr[j] = (lane + 32 * j < N) ? y[lane + 32 * j] : S(0);
+  for (int j = 0; j < NS; ++j) {
+    yr[j] = (lane + 32 * j < N) ? y[lane + 32 * j] : S(0);
+    rowr[j] = Lp + prow(lane + 32 * j);
+  }
   for (int k = 0; k < N; ++k) {
     const int slot = k >> 5;
     S src = yr[0];
@@ -193,17 +225,18 @@ __device__ __forceinline__ void chol_solve(const S* __restrict__ Lp, const S* __
 #pragma unroll
     for (int j = 0; j < NS; ++j) {
       const int r = lane + 32 * j;
-      if (r > k && r < N) yr[j] -= Lp[pidx(r, k)] * yk;
+      if (r > k && r < N) yr[j] -= rowr[j][k] * yk;
       else if (r == k) yr[j] = yk;
     }
   }
+  const S* row = Lp + prow(N);
   for (int k = N - 1; k >= 0; --k) {
     const int slot = k >> 5;
     S src = yr[0];
 #pragma unroll
     for (int j = 1; j < NS; ++j) src = (slot == j) ? yr[j] : src;
     const S xk = __shfl_sync(FULL, src, k & 31) * invd[k];
-    const S* row = Lp + pidx(k, 0);
+    row -= (k + 2) & ~1;  // == Lp + prow(k)
 #pragma unroll
     for (int j = 0; j < NS; ++j) {
       const int r = lane + 32 * j;
@@ -317,10 +350,10 @@ __device__ __noinline__ int qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int na
   S best = S(1e30);
   bool converged = false;
   S qm = S(0);
-  for (int i = lane; i < N; i += 32) qm = max_t(qm, abs_t(q[i]));
-  qm = warp_max(qm);
+  for (int i = lane; i < N; i += 32) qm = qmax(qm, abs_t(q[i]));
+  qm = warp_qmax(qm);
   __syncwarp();
-  const int NP = N * (N + 1) / 2;
+  const int NP = prow(N);
   const S inv_M = S(1) / S(M);
   int it = 0, it_prog = 0;
   for (; it < QpTol<S>::max_iter; ++it) {
@@ -332,9 +365,9 @@ __device__ __noinline__ int qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int na
     S xQx = S(0), qx = S(0), xm = S(0), Qxm = S(0);
     for (int i = lane; i < N; i += 32) {
       xQx += x[i] * rd[i]; qx += q[i] * x[i];
-      xm = max_t(xm, abs_t(x[i])); Qxm = max_t(Qxm, abs_t(rd[i]));
+      xm = qmax(xm, abs_t(x[i])); Qxm = qmax(Qxm, abs_t(rd[i]));
     }
-    xQx = warp_sum(xQx); qx = warp_sum(qx); xm = warp_max(xm); Qxm = warp_max(Qxm);
+    xQx = warp_sum(xQx); qx = warp_sum(qx); xm = warp_qmax(xm); Qxm = warp_qmax(Qxm);
     S rdn = S(0), rpn = S(0), sz = S(0);
     for (int a = lane; a < na; a += 32) {
       S gz[3], gx[5];
@@ -344,30 +377,30 @@ __device__ __noinline__ int qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int na
       for (int d = 0; d < 3; ++d) {
         const S v = rd[3 * a + d] + q[3 * a + d] + gz[d];
         rd[3 * a + d] = v;
-        rdn = max_t(rdn, abs_t(v));
+        rdn = qmax(rdn, abs_t(v));
       }
 #pragma unroll
       for (int j = 0; j < 5; ++j) {
         const S sj = s[5 * a + j], zj = z[5 * a + j];
         const S v = gx[j] + sj;
         rp[5 * a + j] = v;
-        rpn = max_t(rpn, abs_t(v));
+        rpn = qmax(rpn, abs_t(v));
         sz += sj * zj;
         is[5 * a + j] = S(1) / sj;
         iz[5 * a + j] = S(1) / zj;
       }
     }
-    rdn = warp_max(rdn); rpn = warp_max(rpn); sz = warp_sum(sz);
+    rdn = warp_qmax(rdn); rpn = warp_qmax(rpn); sz = warp_sum(sz);
     const S mu = sz * inv_M;
     // A non-finite iterate (the Hessian Q + G' diag(z/s) G loses definiteness to rounding once z/s spans the whole
-    // exponent range, a few iterations past the resolution of S) must never become the answer.  The maxima above are
-    // NaN-blind (fmax returns the other operand), the SUMS are not: x'Qx, q'x and s'z carry any NaN / Inf of x, s, z.
+    // exponent range, a few iterations past the resolution of S) must never become the answer.  The maxima above may
+    // drop a NaN (compare + select), the SUMS cannot: x'Qx, q'x and s'z carry any NaN / Inf of x, s, z.
     {
       const S chk = abs_t(xQx) + abs_t(qx) + abs_t(sz);
       if (!(chk < S(sizeof(S) == 8 ? 1e290 : 1e30f))) break;  // keep the best finite iterate found so far
     }
     const S m_d = rdn / (S(1) + qm + Qxm), m_p = rpn / (S(1) + xm), m_g = mu / (S(1) + abs_t(S(0.5) * xQx + qx));
-    const S merit = max_t(m_d, max_t(m_p, m_g));
+    const S merit = qmax(m_d, qmax(m_p, m_g));
     if (merit < best) {
       if (merit < S(0.5) * best) it_prog = it;
       best = merit;
@@ -418,10 +451,10 @@ __device__ __noinline__ int qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int na
         const S dsj = -rp[5 * a + j] - g[j];
         const S dzj = -(sj * zj + zj * dsj) * is[5 * a + j];
         dsa[5 * a + j] = dsj; dza[5 * a + j] = dzj;
-        rmax = max_t(rmax, max_t(-dsj * is[5 * a + j], -dzj * iz[5 * a + j]));
+        rmax = qmax(rmax, qmax(-dsj * is[5 * a + j], -dzj * iz[5 * a + j]));
       }
     }
-    rmax = warp_max(rmax);
+    rmax = warp_qmax(rmax);
     const S amax = S(1) / rmax;  // rmax >= 1
     __syncwarp();  // ds_a / dz_a were written point-wise, read element-wise below
     S mua = S(0);
@@ -455,10 +488,10 @@ __device__ __noinline__ int qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int na
         const S dsj = -rp[5 * a + j] - g[j];
         const S dzj = -(rc + zj * dsj) * is[5 * a + j];
         ds[5 * a + j] = dsj; dz[5 * a + j] = dzj;
-        rm2 = max_t(rm2, max_t(-dsj * is[5 * a + j], -dzj * iz[5 * a + j]));
+        rm2 = qmax(rm2, qmax(-dsj * is[5 * a + j], -dzj * iz[5 * a + j]));
       }
     }
-    rm2 = warp_max(rm2);
+    rm2 = warp_qmax(rm2);
     // alpha = min(1, 0.99 / rm2)
     const S al = (rm2 > S(0.99)) ? S(0.99) / rm2 : S(1);
     __syncwarp();
@@ -472,6 +505,16 @@ __device__ __noinline__ int qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int na
   // bit 16: the iteration ended without meeting the tolerance (iteration limit, stall at the resolution of S, or a
   // non-finite iterate): the best iterate is returned.  The reference ignores qpax's flag (rigid.py:359-362).
   return it | ((converged || best <= S(100) * tol) ? 0 : 0x10000);
+}
+
+// the instance whose substitution loops fit the problem; both cascades (monolithic / split) go through here, so that they
+// run the same code on the same numbers (tests/test_gpu_rigid.py: bit-identical results)
+template <typename S>
+__device__ __forceinline__ int qp_solve(const S* Qp, S* Hp, S* vN, S* vM, int na, S mu_f, int lane, const S tol) {
+  const int N = 3 * na;
+  if (N <= 32) return qp_pyramids<S, 1>(Qp, Hp, vN, vM, na, mu_f, lane, tol);
+  if (N <= 64) return qp_pyramids<S, 2>(Qp, Hp, vN, vM, na, mu_f, lane, tol);
+  return qp_pyramids<S, 3>(Qp, Hp, vN, vM, na, mu_f, lane, tol);
 }
 
 // ------------------------------------------------------------------------------------
@@ -512,7 +555,7 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
   const int lane = threadIdx.x & 31;
   const int wrp = threadIdx.x >> 5;
   const int cap = P.na_cap;
-  const RigidLayout L = rigid_layout<T, S>(nL, nc, depth, cap);
+  const RigidLayout L = rigid_layout<T, S>(nL, nc, depth, cap, P.qp_mode);
   unsigned char* wb = ws_base + (size_t)wrp * L.total;
   T* ws = reinterpret_cast<T*>(wb + L.links);
   T* pts = reinterpret_cast<T*>(wb + L.pts);
@@ -1231,7 +1274,7 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
         if (P.qp_mode == 1) {
           S* qg = reinterpret_cast<S*>(qp_hdr + 4);
           S* Qg = qg + 6 * cap;
-          const int N = 3 * na, NP = N * (N + 1) / 2;
+          const int N = 3 * na, NP = prow(N);
           for (int i = lane; i < N; i += 32) qg[i] = q[i];
           for (int e = lane; e < NP; e += 32) Qg[e] = Qp[e];
           if (lane == 0) qp_hdr[0] = na;
@@ -1251,8 +1294,7 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
         // iterate to the resolution of the DATA: float32 states carry 6e-8 relative rounding, so a float64 solve of a
         // float32 problem stops at 1e-8 (4-5 interior-point iterations earlier than the 1e-11 of float64 data)
         const S qp_tol = (sizeof(S) == 8 && sizeof(T) == 4) ? S(1e-8) : QpTol<S>::tol();
-        const int qp_rc = (3 * na <= 32) ? qp_pyramids<S, 1>(Qp, Hp, vN, vM, na, S(P.mu), lane, qp_tol)
-                                         : qp_pyramids<S, 3>(Qp, Hp, vN, vM, na, S(P.mu), lane, qp_tol);
+        const int qp_rc = qp_solve<S>(Qp, Hp, vN, vM, na, S(P.mu), lane, qp_tol);
         const int qp_it = qp_rc & 0xFFFF;
         if (P.status && lane == 0 && (qp_rc & 0x10000)) atomicOr(P.status + env, 8);  // B200SIM_STATUS_QP_NOT_CONVERGED
 #ifdef B200SIM_RIGID_DEBUG
@@ -1473,7 +1515,7 @@ struct QpLayout { size_t Hp, vecN, vecM, total; };
 template <typename S>
 __host__ __device__ inline QpLayout qp_layout(int cap) {
   QpLayout L;
-  const size_t N = 3 * (size_t)cap, M = 5 * (size_t)cap, NP = N * (N + 1) / 2;
+  const size_t N = 3 * (size_t)cap, M = 5 * (size_t)cap, NP = npk(N);
   size_t o = 0;
   L.Hp = o;   o = rl_align(o + sizeof(S) * NP);
   L.vecN = o; o = rl_align(o + sizeof(S) * 7 * N);
@@ -1484,7 +1526,7 @@ __host__ __device__ inline QpLayout qp_layout(int cap) {
 
 constexpr int QP_WARPS = 2;  // warps per block (no block-level barrier: small blocks even out the iteration counts)
 
-// MINB = resident blocks per SM the register allocation aims at (8: 128 registers, 10: 96, 12: 80 + spills)
+// MINB = resident blocks per SM the register allocation aims at (8: 128 registers, 9: 112, 10: 96)
 template <typename S, int MINB>
 __global__ void __launch_bounds__(32 * QP_WARPS, MINB) rigid_qp_kernel(const int* work_count, int* next_item, unsigned char* qp_buf,
                                                                   long long qp_stride, int cap, S mu_f, S tol, int* status,
@@ -1512,7 +1554,7 @@ __global__ void __launch_bounds__(32 * QP_WARPS, MINB) rigid_qp_kernel(const int
     const S* Qg = qg + 6 * cap;
     for (int i = lane; i < N; i += 32) vN[N + i] = qg[i];  // qp_pyramids reads q at vN + N
     __syncwarp();
-    const int rc = (N <= 32) ? qp_pyramids<S, 1>(Qg, Hp, vN, vM, na, mu_f, lane, tol) : qp_pyramids<S, 3>(Qg, Hp, vN, vM, na, mu_f, lane, tol);
+    const int rc = qp_solve<S>(Qg, Hp, vN, vM, na, mu_f, lane, tol);
     for (int i = lane; i < N; i += 32) xg[i] = vN[i];
     if (lane == 0) {
       hdr[1] = rc;
