@@ -296,6 +296,30 @@ def ergocub_like_urdf() -> str:
     return b.urdf()
 
 
+# An SDF document that exercises the pose semantics parsers/sdf.py resolves: a floating base whose link frame is posed
+# in the model frame, a joint posed in the model frame (not in its child), a child link offset from its joint
+# (non-identity successor transform), an explicit <frame> attached to a link, <limit> stiffness / dissipation.
+POSED_SDF = """<?xml version="1.0"?>
+<sdf version="1.9"><model name="posed">
+  <link name="trunk"><pose>0.1 0.2 0.3 0.1 -0.2 0.3</pose>
+    <inertial><pose>0.01 0 0.02 0 0.1 0</pose><mass>3</mass><inertia><ixx>0.03</ixx><iyy>0.04</iyy><izz>0.05</izz><ixy>0.001</ixy><ixz>0</ixz><iyz>0.002</iyz></inertia></inertial>
+    <collision name="c0"><pose>0 0 -0.05 0 0 0.2</pose><geometry><box><size>0.2 0.1 0.05</size></box></geometry></collision></link>
+  <joint name="hip" type="revolute"><pose relative_to="__model__">0.1 0.3 0.3 0.2 0 0</pose><parent>trunk</parent><child>thigh</child>
+    <axis><xyz>0 1 0</xyz><limit><lower>-1</lower><upper>1.5</upper><stiffness>50</stiffness><dissipation>2</dissipation></limit>
+      <dynamics><damping>0.1</damping><friction>0.05</friction></dynamics></axis></joint>
+  <link name="thigh"><pose relative_to="hip">0 0 0 0 0 0</pose>
+    <inertial><pose>0 0 -0.1 0 0 0</pose><mass>1</mass><inertia><ixx>0.01</ixx><iyy>0.01</iyy><izz>0.002</izz></inertia></inertial></link>
+  <joint name="knee" type="revolute"><pose>0 0 0.05 0 0 0</pose><parent>thigh</parent><child>shin</child><axis><xyz>1 0 0</xyz></axis></joint>
+  <link name="shin"><pose relative_to="thigh">0.02 0 -0.3 0 0.1 0</pose>
+    <inertial><pose>0 0 -0.1 0 0 0</pose><mass>0.5</mass><inertia><ixx>0.004</ixx><iyy>0.004</iyy><izz>0.001</izz></inertia></inertial>
+    <collision name="c1"><pose>0 0 -0.15 0 0 0</pose><geometry><sphere><radius>0.03</radius></sphere></geometry></collision></link>
+  <joint name="slide" type="prismatic"><parent>trunk</parent><child>arm</child><axis><xyz>1 0 0</xyz><limit><lower>-0.2</lower><upper>0.3</upper></limit></axis></joint>
+  <link name="arm"><pose relative_to="trunk">0 -0.1 0.1 0 0 0.5</pose>
+    <inertial><mass>0.8</mass><inertia><ixx>0.002</ixx><iyy>0.008</iyy><izz>0.008</izz></inertia></inertial></link>
+  <frame name="camera" attached_to="trunk"><pose>0.05 0 0.1 0 0.3 0</pose></frame>
+</model></sdf>"""
+
+
 MODELS = {
     "box": box_urdf,
     "sphere": sphere_urdf,
@@ -306,8 +330,10 @@ MODELS = {
     "ergocub_like": ergocub_like_urdf,
     "four_bar": four_bar_urdf,
     "four_bar_fixed": lambda: four_bar_urdf(fixed_base=True),
+    "posed_sdf": lambda: POSED_SDF,
 }
 
 
 def urdf(name: str) -> str:
+    """The description of a built-in model: URDF text, or SDF text for ``posed_sdf`` (the loader tells them apart)."""
     return MODELS[name]()

@@ -122,6 +122,7 @@ class _Joint:
     position_limit_damper: float
     position_limit_spring: float
     index: int = -1
+    suc: np.ndarray = dataclasses.field(default_factory=lambda: np.eye(4))  # joint_H_child (identity in a URDF; SDF: parsers/sdf.py)
 
 
 def _box_points(size, H) -> np.ndarray:
@@ -151,10 +152,14 @@ def _sphere_points(radius, H) -> np.ndarray:
     return pts @ H[0:3, 0:3].T + H[0:3, 3]
 
 
+def _root_tag(xml_text: str) -> str:
+    return ET.fromstring(xml_text).tag
+
+
 def _parse(xml_text: str):
     root = ET.fromstring(xml_text)
     if root.tag != "robot":
-        raise ValueError("Only URDF (<robot>) descriptions are supported by this loader")
+        raise ValueError("Expected a URDF (<robot>) description; SDF documents go through parsers/sdf.py")
     name = root.get("name", "model")
 
     links: dict[str, _Link] = {}
@@ -234,7 +239,15 @@ def build_kin_dyn_parameters(model_description: str | pathlib.Path) -> tuple[str
     text = str(model_description)
     if not text.lstrip().startswith("<"):
         text = pathlib.Path(model_description).read_text()
-    name, links, joints = _parse(text)
+    frames0: list[tuple[str, str, np.ndarray]] = []
+    base_link_pose = np.eye(4)  # pose of the base link in the model frame (SDF only; a URDF root link IS the model frame)
+    if _root_tag(text) == "sdf":
+        from . import sdf as _sdf
+
+        name, links, joints, frames0, link_poses = _sdf.parse(text)
+    else:
+        link_poses = None
+        name, links, joints = _parse(text)
 
     # ---- fixed-base detection (parsers/rod/parser.py:147-197)
     world_joints = [j for j in joints if j.parent == "world"]
@@ -247,12 +260,12 @@ def build_kin_dyn_parameters(model_description: str | pathlib.Path) -> tuple[str
         if len(world_joints) != 1 or world_joints[0].jtype != JointType.Fixed:
             raise ValueError("Found more/less than one fixed joint connecting the model to the world")
         base_name = world_joints[0].child
-        base_pose = world_joints[0].pose.copy()
+        base_pose = world_joints[0].pose @ world_joints[0].suc  # parser.py:192-197: joint pose @ pose of the base link
         joints = [j for j in joints if j.parent != "world"]
 
     # ---- lump the children of fixed joints into their parents, leaves first
     #      (parsers/kinematic_graph.py:379-611, parsers/descriptions/link.py:86-115).
-    frames: list[tuple[str, str, np.ndarray]] = []  # (frame name, parent link, parent_H_frame)
+    frames: list[tuple[str, str, np.ndarray]] = list(frames0)  # (frame name, parent link, parent_H_frame)
     while True:
         fixed = [j for j in joints if j.jtype == JointType.Fixed]
         if not fixed:
@@ -261,7 +274,7 @@ def build_kin_dyn_parameters(model_description: str | pathlib.Path) -> tuple[str
         parents_of_fixed = {j.parent for j in fixed}
         j = next((f for f in fixed if f.child not in parents_of_fixed), fixed[0])
         parent, child = links[j.parent], links[j.child]
-        p_H_c = j.pose
+        p_H_c = j.pose @ j.suc
         if child.mass > 0:
             X = _adjoint_inverse(p_H_c)  # c_X_p
             parent.inertia = parent.inertia + X.T @ child.inertia @ X
@@ -317,10 +330,13 @@ def build_kin_dyn_parameters(model_description: str | pathlib.Path) -> tuple[str
     lam_H_pre = np.tile(np.eye(4), (nL, 1, 1))
     suc_H_i = np.tile(np.eye(4), (nL, 1, 1))
     suc_H_i[0] = base_pose  # math/joint_model.py:78-83 (+ parser.py:192-197 for fixed base)
+    if floating_base and link_poses is not None:
+        suc_H_i[0] = link_poses[root.name]  # SDF: pose of the base link w.r.t. the model frame (joint_model.py:74-78)
     S = np.zeros((nL, 6))
     axes = np.zeros((n, 3))
     for j in ordered_joints:
         lam_H_pre[j.index] = j.pose
+        suc_H_i[j.index] = j.suc  # math/joint_model.py:96-98
         axes[j.index - 1] = j.axis
         if j.jtype == JointType.Revolute:
             S[j.index, 3:6] = j.axis

@@ -192,6 +192,7 @@ class Model:
     frame: list = dataclasses.field(default_factory=list)
     pose: Pose | None = None
     canonical_link: str | None = None
+    sdf_convention: bool = False  # poses as written in an SDF file (switch_frame_convention re-expresses them)
 
     def links(self) -> list:
         return list(self.link)
@@ -216,9 +217,57 @@ class Model:
         return roots[0]
 
     def switch_frame_convention(self, frame_convention: FrameConvention, explicit_frames: bool = True, **_) -> None:
-        # the tree is built in URDF convention (joint poses in the parent link, identity link poses)
         if frame_convention is not FrameConvention.Urdf:
-            raise NotImplementedError("the stand-in only holds models in URDF frame convention")
+            raise NotImplementedError("the stand-in only converts to the URDF frame convention")
+        if not self.sdf_convention:
+            return  # built from a URDF: joint poses already in the parent link, identity link poses
+        # rod re-expresses every pose without moving any frame: joints in their parent link, links in their parent joint
+        # (the canonical link in the model frame), frames in the link they are attached to.  Poses in the model frame
+        # first, from the SDF 1.7+ defaults: a link pose is given in the model frame, a joint pose in its CHILD link,
+        # a frame pose in what it is attached to (else the model).
+        raw = {}
+        for l in self.link:
+            raw[l.name] = (l.pose.transform() if l.pose is not None else np.eye(4), (l.pose.relative_to if l.pose is not None else None) or "__model__")
+        for j in self.joint:
+            raw[j.name] = (j.pose.transform() if j.pose is not None else np.eye(4), (j.pose.relative_to if j.pose is not None else None) or j.child)
+        for f in self.frame:
+            raw[f.name] = (f.pose.transform() if f.pose is not None else np.eye(4),
+                           (f.pose.relative_to if f.pose is not None else None) or f.attached_to or "__model__")
+        done = {"__model__": np.eye(4), "world": np.eye(4)}
+
+        def in_model(name, depth=0):
+            if name not in done:
+                assert depth < 64, f"cyclic relative_to chain at {name}"
+                H, rel = raw[name]
+                done[name] = in_model(rel, depth + 1) @ H
+            return done[name]
+
+        link_names = {l.name for l in self.link}
+        parent_joint = {j.child: j for j in self.joint}
+        canonical = self.get_canonical_link()
+        for j in self.joint:
+            if j.parent == "world":
+                j.pose = _pose_from_transform(in_model(j.name), relative_to="__model__")
+            else:
+                j.pose = _pose_from_transform(np.linalg.inv(in_model(j.parent)) @ in_model(j.name), relative_to=j.parent)
+        for l in self.link:
+            if l.name in parent_joint:
+                pj = parent_joint[l.name]
+                l.pose = _pose_from_transform(np.linalg.inv(in_model(pj.name)) @ in_model(l.name), relative_to=pj.name)
+            else:
+                assert l.name == canonical, (l.name, canonical)
+                l.pose = _pose_from_transform(in_model(l.name), relative_to="__model__")
+        joint_child = {j.name: j.child for j in self.joint}
+        frames_by_name = {f.name: f for f in self.frame}
+        for f in self.frame:
+            target = f.attached_to
+            while target is not None and target not in link_names:  # attached to a frame / a joint: follow to a link
+                target = frames_by_name[target].attached_to if target in frames_by_name else joint_child.get(target)
+            if target is None:
+                continue
+            f.pose = _pose_from_transform(np.linalg.inv(in_model(target)) @ in_model(f.name), relative_to=target)
+            f.attached_to = target
+        self.sdf_convention = False
 
 
 def _link_from_urdf(e) -> Link:
@@ -284,8 +333,10 @@ class Sdf:
         if isinstance(sdf, pathlib.Path) or (isinstance(sdf, str) and len(sdf) < 1024 and "<" not in sdf):
             text = pathlib.Path(sdf).read_text()
         root = ET.fromstring(text)
+        if root.tag == "sdf":
+            return Sdf(model=[_model_from_sdf(m) for m in root.findall("model")], version=root.get("version", "1.7"))
         if root.tag != "robot":
-            raise NotImplementedError("the rod stand-in reads URDF (<robot>) documents only")
+            raise NotImplementedError("the rod stand-in reads URDF (<robot>) and SDF (<sdf>) documents")
         links = [_link_from_urdf(e) for e in root.findall("link") if e.get("name") != "world"]
         joints = [_joint_from_urdf(e) for e in root.findall("joint")]
         # sdformat turns a massless link that hangs on a FIXED joint into a frame attached to the parent link, with the
@@ -310,6 +361,63 @@ class Sdf:
                 f.attached_to = parent.attached_to
                 f.pose = _pose_from_transform(H, relative_to=parent.attached_to)
         return Sdf(model=Model(name=root.get("name"), link=links, joint=joints, frame=frames))
+
+
+def _sdf_pose(e) -> Pose | None:
+    pe = None if e is None else e.find("pose")
+    if pe is None:
+        return None
+    return Pose(pose=_floats(pe.text, None, None) or [0.0] * 6, relative_to=pe.get("relative_to") or None)
+
+
+def _sdf_float(e, path):
+    x = None if e is None else e.find(path)
+    return float(x.text) if (x is not None and x.text is not None and x.text.strip()) else None
+
+
+def _model_from_sdf(me) -> Model:
+    """rod's dataclass tree straight from the SDF elements (rod is SDF-native: element names == attribute names)."""
+    links = []
+    for le in me.findall("link"):
+        ine = le.find("inertial")
+        inertial = Inertial()
+        if ine is not None:
+            g = lambda k: _sdf_float(ine, f"inertia/{k}")  # noqa: E731
+            inertial = Inertial(mass=_sdf_float(ine, "mass") or 0.0,
+                                inertia=Inertia(ixx=g("ixx") or 0.0, iyy=g("iyy") or 0.0, izz=g("izz") or 0.0, ixy=g("ixy"), ixz=g("ixz"), iyz=g("iyz")),
+                                pose=_sdf_pose(ine))
+        cols = []
+        for k, c in enumerate(le.findall("collision")):
+            ge, geo = c.find("geometry"), Geometry()
+            if ge is not None:
+                if ge.find("box") is not None:
+                    geo.box = Box(size=_floats(ge.find("box/size").text, 3))
+                elif ge.find("sphere") is not None:
+                    geo.sphere = Sphere(radius=float(ge.find("sphere/radius").text))
+                elif ge.find("cylinder") is not None:
+                    geo.cylinder = Cylinder(radius=float(ge.find("cylinder/radius").text), length=float(ge.find("cylinder/length").text))
+                elif ge.find("mesh") is not None:
+                    geo.mesh = Mesh(uri=ge.find("mesh/uri").text, scale=_floats(ge.find("mesh/scale").text) if ge.find("mesh/scale") is not None else None)
+            cols.append(Collision(name=c.get("name") or f"{le.get('name')}_collision_{k}", geometry=geo, pose=_sdf_pose(c)))
+        links.append(Link(name=le.get("name"), inertial=inertial, pose=_sdf_pose(le), collision=cols))
+    joints = []
+    for je in me.findall("joint"):
+        ax, axis = je.find("axis"), None
+        if ax is not None:
+            xyz = ax.find("xyz")
+            lim, dyn = ax.find("limit"), ax.find("dynamics")
+            axis = Axis(xyz=Xyz(xyz=_floats(xyz.text, 3)) if xyz is not None else None,
+                        limit=Limit(lower=_sdf_float(lim, "lower"), upper=_sdf_float(lim, "upper"), effort=_sdf_float(lim, "effort"),
+                                    velocity=_sdf_float(lim, "velocity"), stiffness=_sdf_float(lim, "stiffness"),
+                                    dissipation=_sdf_float(lim, "dissipation")) if lim is not None else None,
+                        dynamics=Dynamics(damping=_sdf_float(dyn, "damping"), friction=_sdf_float(dyn, "friction")) if dyn is not None else None)
+        elif je.get("type") == "fixed":
+            axis = Axis(xyz=Xyz(xyz=[1.0, 0.0, 0.0]))  # hashable stand-in, never used (see _joint_from_urdf)
+        joints.append(Joint(name=je.get("name"), type=je.get("type"), parent=je.find("parent").text.strip(), child=je.find("child").text.strip(),
+                            pose=_sdf_pose(je), axis=axis))
+    frames = [Frame(name=fe.get("name"), attached_to=fe.get("attached_to"), pose=_sdf_pose(fe)) for fe in me.findall("frame")]
+    return Model(name=me.get("name"), link=links, joint=joints, frame=frames, pose=_sdf_pose(me), canonical_link=me.get("canonical_link"),
+                 sdf_convention=True)
 
 
 def _pose_from_transform(H, relative_to=None) -> Pose:

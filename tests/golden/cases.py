@@ -36,6 +36,9 @@ CASES = [
     dict(id="icub_soft_fext_mixed", rbda=True, seed=13, in_contact=True, tau=True, fext=True, velrepr="mixed", **_ICUB),
     dict(id="icub_soft_fext_body", rbda=True, seed=14, in_contact=True, tau=True, fext=True, velrepr="body", **_ICUB),
     dict(id="ergocub_soft_contact", model="ergocub_like", B=2, seed=15, in_contact=True, tau=True, m=True),
+    # ---- a model given in SDF (jaxsim_b200/models: POSED_SDF): posed base link, joint posed in the model frame, a link
+    #      offset from its joint (non-identity successor transform), <limit> stiffness / dissipation (limit spring / damper)
+    dict(id="posed_sdf_soft_contact", model="posed_sdf", B=6, seed=52, in_contact=True, tau=True, m=True, rbda=True, round32=True),
     # ---- RK4
     dict(id="icub_rk4_contact", seed=16, in_contact=True, tau=True, m=True, integrator="rk4", **_ICUB),
     dict(id="box_rk4_contact", model="box", B=3, seed=17, in_contact=True, m=True, integrator="rk4"),

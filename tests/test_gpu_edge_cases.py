@@ -170,6 +170,18 @@ def test_non_identity_successor_transforms(cuda_device):
     _run(model2, om, od, cuda_device, tau=rng.uniform(-3, 3, (10, 23)))
 
 
+def test_model_loaded_from_sdf(cuda_device):
+    """A model description in SDF (jaxsim_b200/parsers/sdf.py: poses `relative_to` other frames -> lam_H_pre, non-identity
+    suc_H_i, posed base link): the loader's result is pinned against the reference's front end on the CPU
+    (test_urdf_front_end_matches_reference_parser[posed_sdf]); here the kernels step it like the oracle does."""
+    model = H.build_model("posed_sdf")
+    kd = model.kin_dyn_parameters
+    assert not np.allclose(kd.joint_model.suc_H_i[0], np.eye(4)) and not all(np.allclose(h, np.eye(4)) for h in kd.joint_model.suc_H_i[1:])
+    om = H.oracle_model(model)
+    od = O.random_model_data(om, 12, seed=17, in_contact=True)
+    _run(model, om, od, cuda_device, tau=np.random.default_rng(3).uniform(-2, 2, (12, model.dofs())))
+
+
 @pytest.mark.parametrize("vr", ["Body", "Mixed", "Inertial"])
 def test_build_converts_base_velocity_representation(vr, cuda_device):
     """JaxSimModelData.build stores the base velocity inertial-fixed whatever representation it

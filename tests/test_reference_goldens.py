@@ -200,12 +200,17 @@ BRANCHED_URDF = """<robot name="branched">
 </robot>"""
 
 
-# URDF files the reference ships (read in place: never copied into this repository; build container only)
-REFERENCE_URDFS = {"ref:cartpole": "examples/assets/cartpole.urdf", "ref:4_bar_opened": "tests/assets/4_bar_opened.urdf"}
+# model files the reference ships (read in place: never copied into this repository; build container only); the last one
+# is SDF: poses `relative_to` other frames, resolved by parsers/sdf.py and, on the reference's side, by the stand-in's
+# `switch_frame_convention` (tests/conftest.py:718 loads it the same way)
+REFERENCE_URDFS = {"ref:cartpole": "examples/assets/cartpole.urdf", "ref:4_bar_opened": "tests/assets/4_bar_opened.urdf",
+                   "ref:double_pendulum.sdf": "tests/assets/double_pendulum.sdf"}
 
-
+# SDF pose semantics beyond the reference's asset: a floating base whose link frame is posed in the model frame, a joint
+# posed in the model frame (not in its child), a child link offset from its joint (non-identity successor transform), an
+# explicit <frame> attached to a link, <limit> stiffness / dissipation
 @pytest.mark.parametrize("name", ["pendulum", "double_pendulum", "cartpole", "box", "sphere", "icub_like", "ergocub_like", "four_bar",
-                                  "four_bar_fixed", "branched", *REFERENCE_URDFS])
+                                  "four_bar_fixed", "branched", "posed_sdf", *REFERENCE_URDFS])
 def test_urdf_front_end_matches_reference_parser(name):
     """The product's URDF loader against the reference's OWN front end run on the same URDF text:
     `jaxsim.parsers.rod.build_model_description` = parsers/rod/parser.py:36-420 + parsers/rod/utils.py:21-225 (inertial ->
@@ -228,7 +233,7 @@ def test_urdf_front_end_matches_reference_parser(name):
             pytest.skip(f"{path} not available")
         text = path.read_text()
     else:
-        text = BRANCHED_URDF if name == "branched" else models.urdf(name)
+        text = BRANCHED_URDF if name == "branched" else models.urdf(name)  # "posed_sdf" is an SDF document (jaxsim_b200/models)
     ref = js.model.JaxSimModel.build(model_description=refenv.reference_model_description(text), time_step=1e-3,
                                      gravity=-jaxsim.math.STANDARD_GRAVITY)
     rk = ref.kin_dyn_parameters
