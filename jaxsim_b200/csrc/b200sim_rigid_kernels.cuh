@@ -197,6 +197,7 @@ __device__ __forceinline__ void chol_packed(S* __restrict__ Hp, S* __restrict__ 
       row[k] = v;
       row[r] -= v * v;
     }
+    __syncwarp();  // every lane has read dg[k] (the pivot floor) before lane 0 replaces it (racecheck: write after read)
     if (lane == 0) dg[k] = ipiv;
     __syncwarp();
   }
