@@ -517,7 +517,7 @@ int launch_rigid_split(B200SimModel* m, const Params<T>& P, B200SimModel::RigidS
     CK(cudaEventRecord(sc->ev_join, sc->aux));
   }
   // same stopping rule as the monolithic kernel: a float64 solve of float32 data stops at the resolution of the data
-  double tol = (sizeof(S) == 8) ? (sizeof(T) == 4 ? 1e-8 : 1e-11) : 1e-5;
+  double tol = (sizeof(S) == 8) ? (sizeof(T) == 4 ? 1e-9 : 1e-12) : 1e-5;
   static const double tol_f32 = [] { const char* e = std::getenv("B200SIM_QP_TOL_F32"); return e ? std::atof(e) : 0.0; }();  // diagnostic A/B
   if (tol_f32 > 0 && sizeof(S) == 8 && sizeof(T) == 4) tol = tol_f32;
   if (!rc) rc = launch_rigid_qp<S>(m, P.B, cnt, cnt + 2, qp, (long long)stride, cap1, (double)P.mu, tol, P.status, P.dbg, st);

@@ -100,7 +100,7 @@ template <> struct QpTol<float> {
   static constexpr int max_iter = 40;
 };
 template <> struct QpTol<double> {
-  static __device__ __forceinline__ double tol() { return 1e-11; }
+  static __device__ __forceinline__ double tol() { return 1e-12; }
   static __device__ __forceinline__ double pivot_floor() { return 1e-15; }
   static constexpr int max_iter = 60;
 };
@@ -350,16 +350,31 @@ __device__ __noinline__ int qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int na
   for (int j = lane; j < M; j += 32) { s[j] = S(1); z[j] = S(1); }
   S best = S(1e30);
   bool converged = false;
-  S qm = S(0);
-  for (int i = lane; i < N; i += 32) qm = qmax(qm, abs_t(q[i]));
+  // Normalisation.  The constraints are a cone (G x <= 0), so x = (alpha sigma) y solves the problem iff y solves it
+  // for Q' = alpha^2 Q, q' = alpha q / sigma.  With alpha^2 = 1 / mean(diag Q) and sigma = 0.3 max|alpha q| the solution,
+  // its slacks and its multipliers are O(1) -- where the start s = z = 1 and the "1 +" floors of the merit assume them to
+  // be.  In physical units (forces of 1e2-1e3 N, accelerations of 1e1-1e2 m/s^2) the interior-point iteration spent a
+  // quarter of its steps growing s: 12.4 -> 8.6 iterations on the standing ErgoCub-like contact problems at equal accuracy
+  // of Q x (scratch/polish_proto.py; the tolerances were tightened by 10 to pay for the floors that no longer bind).
+  S qm = S(0), dsum = S(0);
+  for (int i = lane; i < N; i += 32) { qm = qmax(qm, abs_t(q[i])); dsum += Qp[pidx(i, i)]; }
   qm = warp_qmax(qm);
+  dsum = warp_sum(dsum);
+  const S alpha2 = (dsum > S(0)) ? S(N) / dsum : S(1);
+  const S alpha = sqrt_t(alpha2);
+  const S sigma = (qm > S(0)) ? S(0.3) * alpha * qm : S(1);
+  {
+    const S qs = alpha / sigma;
+    for (int i = lane; i < N; i += 32) q[i] *= qs;
+    qm *= qs;
+  }
   __syncwarp();
   const int NP = prow(N);
   const S inv_M = S(1) / S(M);
   int it = 0, it_prog = 0;
   for (; it < QpTol<S>::max_iter; ++it) {
     // H <- Q (the factor of the previous iteration is dead); residuals
-    for (int e = lane; e < NP; e += 32) Hp[e] = Qp[e];
+    for (int e = lane; e < NP; e += 32) Hp[e] = alpha2 * Qp[e];
     __syncwarp();
     sym_matvec(Hp, x, rd, N, lane);
     __syncwarp();
@@ -501,7 +516,10 @@ __device__ __noinline__ int qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int na
     __syncwarp();
   }
   __syncwarp();
-  for (int i = lane; i < N; i += 32) x[i] = xb[i];
+  {
+    const S xs = alpha * sigma;  // back to physical units
+    for (int i = lane; i < N; i += 32) x[i] = xb[i] * xs;
+  }
   __syncwarp();
   // bit 16: the iteration ended without meeting the tolerance (iteration limit, stall at the resolution of S, or a
   // non-finite iterate): the best iterate is returned.  The reference ignores qpax's flag (rigid.py:359-362).
@@ -1293,8 +1311,9 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
         __syncwarp();
 #endif
         // iterate to the resolution of the DATA: float32 states carry 6e-8 relative rounding, so a float64 solve of a
-        // float32 problem stops at 1e-8 (4-5 interior-point iterations earlier than the 1e-11 of float64 data)
-        const S qp_tol = (sizeof(S) == 8 && sizeof(T) == 4) ? S(1e-8) : QpTol<S>::tol();
+        // float32 problem stops at 1e-9 of the normalised problem (3-4 interior-point iterations earlier than the 1e-12 of
+        // float64 data)
+        const S qp_tol = (sizeof(S) == 8 && sizeof(T) == 4) ? S(1e-9) : QpTol<S>::tol();
         const int qp_rc = qp_solve<S>(Qp, Hp, vN, vM, na, S(P.mu), lane, qp_tol);
         const int qp_it = qp_rc & 0xFFFF;
         if (P.status && lane == 0 && (qp_rc & 0x10000)) atomicOr(P.status + env, 8);  // B200SIM_STATUS_QP_NOT_CONVERGED
