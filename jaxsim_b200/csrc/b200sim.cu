@@ -495,7 +495,7 @@ int launch_rigid_split(B200SimModel* m, const Params<T>& P, B200SimModel::RigidS
   int* list1 = cnt + RIGID_COUNTERS;
   int* list2 = list1 + sc->cap;
   int* list3 = list2 + sc->cap;
-  const size_t stride = qp_record_bytes<S>(cap1);
+  const size_t stride = qp_record_bytes<T, S>(m->nL, m->nc, cap1);
   unsigned char* qp = nullptr;
   int rc = ensure_qp_scratch(m, stride * (size_t)P.B, st, &qp);
   if (rc) return rc;
@@ -559,7 +559,7 @@ int launch_rigid(const B200SimModel* cm, Params<T>& P, int dtype, void* stream) 
   const int cap1 = std::min(m->nc, RIGID_CAP1);
   // RigidContacts: split cascade (the records of a very large batch would not be worth their memory: monolithic then)
   const bool split = m->contact_model == B200SIM_CONTACT_RIGID && !(m->opt_flags & B200SIM_OPT_RIGID_MONO) &&
-                     (size_t)P.B * qp_record_bytes<double>(cap1) <= ((size_t)2 << 30);
+                     (size_t)P.B * qp_record_bytes<double, double>(m->nL, m->nc, cap1) <= ((size_t)2 << 30);
   if (!rc && split) {
     rc = qp32 ? launch_rigid_split<T, T>(m, P, sc, cap1, st) : launch_rigid_split<T, double>(m, P, sc, cap1, st);
   } else {

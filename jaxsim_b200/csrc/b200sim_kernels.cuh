@@ -1063,6 +1063,9 @@ __global__ void __launch_bounds__(LaunchBounds<G>::kThreads, 1) step_kernel(cons
           if (active && lane == 0) over_push(P, (int)env, 0);
           active = false;
         }
+        // every environment of this warp is left to the rigid kernel (a standing batch: all of them): nothing to finish
+        // here (no block-level barrier inside the trip loop; the steps loop runs once for the rigid cascade)
+        if (__all_sync(0xffffffffu, !active)) break;
       }
       bool env_touches = false;  // some point of this environment is in contact (group-uniform after the ballot)
       if (soft) {
