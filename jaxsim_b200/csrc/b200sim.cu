@@ -404,7 +404,7 @@ template <typename T, typename S>
 int launch_rigid_level(const B200SimModel* m, Params<T>& P, int cap, cudaStream_t st) {
   int warps = 0, grid = 0;
   size_t smem = 0;
-  int rc = rigid_geometry<T, S>(m, P.B, cap, P.qp_mode, &warps, &grid, &smem);
+  int rc = rigid_geometry<T, S>(m, P.B, cap, m->contact_model == B200SIM_CONTACT_RELAXED_RIGID ? 2 : P.qp_mode, &warps, &grid, &smem);
   if (rc) return rc;
   P.envs_per_block = warps;
   P.na_cap = cap;

@@ -605,7 +605,8 @@ __global__ void __launch_bounds__(32 * RIGID_MAX_WARPS, 1) rigid_step_kernel(con
   const int lane = threadIdx.x & 31;
   const int wrp = threadIdx.x >> 5;
   const int cap = P.na_cap;
-  const RigidLayout L = rigid_layout<T, S>(nL, nc, depth, cap, P.qp_mode);
+  // RelaxedRigidContacts never runs the interior-point method either: the layout of a resuming launch (no solver vectors)
+  const RigidLayout L = rigid_layout<T, S>(nL, nc, depth, cap, P.contact_model == 3 ? 2 : P.qp_mode);
   unsigned char* wb = ws_base + (size_t)wrp * L.total;
   T* ws = reinterpret_cast<T*>(wb + L.links);
   T* pts = reinterpret_cast<T*>(wb + L.pts);

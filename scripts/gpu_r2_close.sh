@@ -27,6 +27,13 @@ timeout 1200 compute-sanitizer --tool racecheck --print-limit 5 python scripts/s
 echo "rigid racecheck: $(grep -E 'RACECHECK SUMMARY' gpurun_out/sanitizer_rigid_racecheck.log | head -1)"
 timeout 1200 compute-sanitizer --tool memcheck --print-limit 5 python scripts/san_rigid.py > gpurun_out/sanitizer_rigid_memcheck.log 2>&1
 echo "rigid memcheck: $(grep -E 'ERROR SUMMARY' gpurun_out/sanitizer_rigid_memcheck.log | head -1)"
+echo "== rigid + relaxed-rigid legs"
+timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-extras --config3 2>gpurun_out/c3_err.log | python -c "
+import sys,json
+d=json.loads(sys.stdin.read())
+for k in ('config3_rigid','relaxed_rigid'):
+    c=d[k]
+    for lab in ('random','standing'): print(k, lab, 'ms/step %.3f' % c[lab]['ms_per_step'], 'env-steps/s %.3e' % c[lab]['value'])"
 echo "== default bench line"
 timeout 1200 python bench.py 2>gpurun_out/bench_err.log > gpurun_out/bench_default.json
 tail -2 gpurun_out/bench_err.log
