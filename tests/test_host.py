@@ -225,3 +225,42 @@ def test_constraint_map_and_frames():
     with model.editable(validate=False) as edited:
         edited.kin_dyn_parameters.constraints = cmap
     assert model.kin_dyn_parameters.constraints is None and len(edited.kin_dyn_parameters.constraints) == 1
+
+
+def test_sdf_pose_semantics_and_errors():
+    """parsers/sdf.py: poses resolve through `relative_to` chains with the SDF 1.7+ default frames (link -> model,
+    joint -> child link, frame -> attached_to); what the loader cannot give the reference's meaning to raises."""
+    from jaxsim_b200 import models
+    from jaxsim_b200.parsers.urdf import build_kin_dyn_parameters
+
+    name, kd, floating = build_kin_dyn_parameters(models.urdf("posed_sdf"))
+    assert name == "posed" and floating and kd.link_names[0] == "trunk" and kd.number_of_links() == 4
+    jm = kd.joint_model
+    # base link posed in the model frame -> suc_H_i[0]; the hip is given in the MODEL frame, so lam_H_pre = trunk^-1 hip
+    M_H_trunk = jm.suc_H_i[0]
+    assert np.allclose(M_H_trunk[0:3, 3], [0.1, 0.2, 0.3])
+    i_thigh = kd.link_names.index("thigh")
+    M_H_hip = M_H_trunk @ jm.lam_H_pre[i_thigh]
+    assert np.allclose(M_H_hip[0:3, 3], [0.1, 0.3, 0.3], atol=1e-12)
+    assert np.allclose(jm.suc_H_i[i_thigh], np.eye(4), atol=1e-12)          # thigh posed at its joint
+    i_shin = kd.link_names.index("shin")
+    assert not np.allclose(jm.suc_H_i[i_shin], np.eye(4))                    # knee posed 5 cm above its child link
+    assert np.allclose(np.linalg.inv(jm.suc_H_i[i_shin])[0:3, 3], [0, 0, 0.05], atol=1e-12)
+    assert kd.frame_parameters.name == ("camera",) and int(kd.frame_parameters.body[0]) == 0
+    k = kd.joint_model.joint_names.index("hip") - 1
+    assert kd.joint_parameters.position_limit_spring[k] == 50.0 and kd.joint_parameters.position_limit_damper[k] == 2.0
+
+    def sdf(body):
+        return f'<?xml version="1.0"?><sdf version="1.9"><model name="m">{body}</model></sdf>'
+
+    link = ('<link name="{n}"><pose relative_to="{r}">0 0 0 0 0 0</pose><inertial><mass>1</mass><inertia><ixx>1</ixx><iyy>1</iyy>'
+            '<izz>1</izz></inertia></inertial></link>')
+    with pytest.raises(ValueError, match="cyclic"):
+        build_kin_dyn_parameters(sdf(link.format(n="a", r="b") + link.format(n="b", r="a")))
+    with pytest.raises(ValueError, match="unknown frame"):
+        build_kin_dyn_parameters(sdf(link.format(n="a", r="nowhere")))
+    with pytest.raises(ValueError, match="not supported"):
+        build_kin_dyn_parameters(sdf(link.format(n="a", r="__model__") + link.format(n="b", r="a")
+                                     + '<joint name="j" type="ball"><parent>a</parent><child>b</child></joint>'))
+    with pytest.raises(NotImplementedError, match="inertial"):
+        build_kin_dyn_parameters(sdf('<link name="a"><inertial><pose relative_to="__model__">0 0 0 0 0 0</pose><mass>1</mass></inertial></link>'))
