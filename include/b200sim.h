@@ -39,6 +39,14 @@ extern "C" {
 #define B200SIM_CONTACT_RIGID 2 /* rbda/contacts/rigid.py (floating base; enabled points a prefix; b200sim_step_n with nsteps > 1 runs
                                     nsteps cascades on the stream and needs the W_H_L / W_v_WL outputs, which feed the next step) */
 #define B200SIM_CONTACT_RELAXED_RIGID 3 /* rbda/contacts/relaxed_rigid.py (same restrictions as RIGID) */
+/* A RIGID / RELAXED_RIGID step is a cascade of launches on the caller's stream (csrc/b200sim.cu: launch_rigid):
+ * the fused step kernel for the environments without contact, then one warp per environment in contact.  RIGID
+ * (default): assemble / rigid_qp_kernel / resume launches for up to 12 active points, the full-size level on a side
+ * stream that forks from and joins the caller's stream through events -- the call stays stream-ordered and CUDA-graph
+ * capturable.  Its work lists and contact-QP records live in a per-(model, stream) scratch block (5.9 KB per
+ * environment of the batch for float32 data, 20 KB for float64, where the records also carry the assembling launch's
+ * workspace; above 2 GiB the contact QP stays inside the rigid kernel): the first call on a stream (or with a larger
+ * batch) must not be inside a stream capture (B200SIM_E_UNSUPPORTED). */
 
 #define B200SIM_E_INVALID (-1)     /* NULL / negative size / bad dtype */
 #define B200SIM_E_UNSUPPORTED (-2) /* valid in the reference, not implemented here */
