@@ -385,7 +385,7 @@ __device__ __noinline__ int qp_pyramids(const S* Qp, S* Hp, S* vN, S* vM, int na
   // its slacks and its multipliers are O(1) -- where the start s = z = 1 and the "1 +" floors of the merit assume them to
   // be.  In physical units (forces of 1e2-1e3 N, accelerations of 1e1-1e2 m/s^2) the interior-point iteration spent a
   // quarter of its steps growing s: 12.4 -> 8.6 iterations on the standing ErgoCub-like contact problems at equal accuracy
-  // of Q x (scratch/polish_proto.py; the tolerances were tightened by 10 to pay for the floors that no longer bind).
+  // of Q x (scripts/experiments/qp_polish_proto.py; the tolerances were tightened by 10 to pay for the floors that no longer bind).
   S qm = S(0), dsum = S(0);
   for (int i = lane; i < N; i += 32) { qm = qmax(qm, abs_t(q[i])); dsum += Qp[pidx(i, i)]; }
   qm = warp_qmax(qm);
