@@ -426,10 +426,19 @@ int ensure_rigid_scratch(B200SimModel* m, long long B, cudaStream_t st, B200SimM
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone)
       return B200SIM_E_UNSUPPORTED;  // cannot allocate inside a capture: run one eager step of the largest batch first
-    if (!sc.aux) {
-      CK(cudaStreamCreateWithFlags(&sc.aux, cudaStreamNonBlocking));
-      CK(cudaEventCreateWithFlags(&sc.ev_fork, cudaEventDisableTiming));
-      CK(cudaEventCreateWithFlags(&sc.ev_join, cudaEventDisableTiming));
+    if (!sc.aux) {  // all three or none: a failure must not leave a stream without its events behind
+      cudaStream_t aux = nullptr;
+      cudaEvent_t e0 = nullptr, e1 = nullptr;
+      cudaError_t err = cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking);
+      if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e0, cudaEventDisableTiming);
+      if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e1, cudaEventDisableTiming);
+      if (err != cudaSuccess) {
+        if (e1) cudaEventDestroy(e1);
+        if (e0) cudaEventDestroy(e0);
+        if (aux) cudaStreamDestroy(aux);
+        return (int)err;
+      }
+      sc.aux = aux; sc.ev_fork = e0; sc.ev_join = e1;
     }
     if (!sc.buf || sc.cap < B) {
       if (sc.buf) {
