@@ -264,3 +264,17 @@ def test_sdf_pose_semantics_and_errors():
                                      + '<joint name="j" type="ball"><parent>a</parent><child>b</child></joint>'))
     with pytest.raises(NotImplementedError, match="inertial"):
         build_kin_dyn_parameters(sdf('<link name="a"><inertial><pose relative_to="__model__">0 0 0 0 0 0</pose><mass>1</mass></inertial></link>'))
+
+
+def test_option_flags_match_the_header():
+    """The Python mirror of the implementation switches and include/b200sim.h agree (incl. the round-2 rigid switch)."""
+    import pathlib
+    import re
+
+    from jaxsim_b200 import _lib
+
+    hdr = (pathlib.Path(__file__).resolve().parent.parent / "include" / "b200sim.h").read_text()
+    flags = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define B200SIM_OPT_(\w+) (\d+)", hdr)}
+    assert flags["RIGID_MONO"] == 128
+    for name, value in flags.items():
+        assert getattr(_lib, "OPT_" + name) == value, name
